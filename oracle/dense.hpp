@@ -1,0 +1,1441 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product path.
+//
+// CPU restatement (Eigen-free, C++17) of the small dense kernels on the hot path of
+// yixuan/spectra @ db1d5cc.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+// legs may use anything in oracle/.
+//
+// Parity status: the reference needs Eigen 3.4 which is not available in this environment, so
+// the reference itself cannot be compiled here.  This restatement is pinned against the
+// reference's own known-answer fixtures and test properties (see tests/test_oracle_*.py):
+// diag(1..10) KAT, cycle-graph Laplacian (Example1), the 5x5 literals of Example2, the
+// zero/null-space cases of Example4, gen_sparse_data fixtures + dense numpy / ARPACK truth.
+//
+// Every function cites the reference file:line it follows (paths relative to
+// /root/reference/include/Spectra/).
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstddef>
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace oracle {
+
+using Index = std::ptrdiff_t;
+using Complex = std::complex<double>;
+
+// Util/TypeTraits.h:63-74
+constexpr double kEps = std::numeric_limits<double>::epsilon();
+constexpr double kMin = (std::numeric_limits<double>::min)();
+constexpr double kNear0 = kMin * 10.0;  // Arnoldi.h:50, HermEigsBase.h:184, DoubleShiftQR.h:35
+
+// Column-major dense matrix (Eigen default layout: data[i + j*rows]).
+struct Mat
+{
+    Index r = 0, c = 0;
+    std::vector<double> a;
+    Mat() {}
+    Mat(Index rows, Index cols) : r(rows), c(cols), a(static_cast<size_t>(rows * cols), 0.0) {}
+    void resize(Index rows, Index cols)
+    {
+        r = rows;
+        c = cols;
+        a.assign(static_cast<size_t>(rows * cols), 0.0);
+    }
+    void set_zero() { std::fill(a.begin(), a.end(), 0.0); }
+    void set_identity()
+    {
+        set_zero();
+        for (Index i = 0; i < std::min(r, c); i++)
+            a[i + i * r] = 1.0;
+    }
+    double& operator()(Index i, Index j) { return a[i + j * r]; }
+    double operator()(Index i, Index j) const { return a[i + j * r]; }
+    double* col(Index j) { return a.data() + j * r; }
+    const double* col(Index j) const { return a.data() + j * r; }
+    double* data() { return a.data(); }
+    const double* data() const { return a.data(); }
+};
+
+struct CMat
+{
+    Index r = 0, c = 0;
+    std::vector<Complex> a;
+    CMat() {}
+    CMat(Index rows, Index cols) : r(rows), c(cols), a(static_cast<size_t>(rows * cols)) {}
+    void resize(Index rows, Index cols)
+    {
+        r = rows;
+        c = cols;
+        a.assign(static_cast<size_t>(rows * cols), Complex(0, 0));
+    }
+    Complex& operator()(Index i, Index j) { return a[i + j * r]; }
+    const Complex& operator()(Index i, Index j) const { return a[i + j * r]; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Eigen 3.4 primitives used by the reference (Eigen source is not under /root/reference; these
+// follow the published Eigen 3.4.0 definitions).
+// ---------------------------------------------------------------------------------------------
+
+// Eigen::numext::hypot  (used at TridiagEigen.h:65, DoubleShiftQR.h:123)
+inline double eigen_hypot(double x, double y)
+{
+    x = std::abs(x);
+    y = std::abs(y);
+    if (std::isinf(x) || std::isinf(y))
+        return std::numeric_limits<double>::infinity();
+    if (std::isnan(x) || std::isnan(y))
+        return std::numeric_limits<double>::quiet_NaN();
+    const double p = std::max(x, y);
+    if (p == 0.0)
+        return 0.0;
+    const double qp = std::min(y, x) / p;
+    return p * std::sqrt(1.0 + qp * qp);
+}
+
+// Eigen::JacobiRotation<double>::makeGivens(p, q, r*)  (TridiagEigen.h:79-80,
+// UpperHessenbergSchur.h:92,324).  Convention: c*p - s*q = r, s*p + c*q = 0.
+struct Jacobi
+{
+    double c = 1.0, s = 0.0;
+    void make_givens(double p, double q, double* r = nullptr)
+    {
+        if (q == 0.0)
+        {
+            c = p < 0.0 ? -1.0 : 1.0;
+            s = 0.0;
+            if (r)
+                *r = std::abs(p);
+        }
+        else if (p == 0.0)
+        {
+            c = 0.0;
+            s = q < 0.0 ? 1.0 : -1.0;
+            if (r)
+                *r = std::abs(q);
+        }
+        else if (std::abs(p) > std::abs(q))
+        {
+            const double t = q / p;
+            double u = std::sqrt(1.0 + t * t);
+            if (p < 0.0)
+                u = -u;
+            c = 1.0 / u;
+            s = -t * c;
+            if (r)
+                *r = p * u;
+        }
+        else
+        {
+            const double t = p / q;
+            double u = std::sqrt(1.0 + t * t);
+            if (q < 0.0)
+                u = -u;
+            s = -1.0 / u;
+            c = -t * s;
+            if (r)
+                *r = q * u;
+        }
+    }
+};
+
+// M.applyOnTheRight(p, q, rot) restricted to rows [0, nrow)
+inline void apply_on_the_right(Mat& M, Index nrow, Index p, Index q, const Jacobi& rot)
+{
+    double* x = M.col(p);
+    double* y = M.col(q);
+    for (Index i = 0; i < nrow; i++)
+    {
+        const double xi = x[i], yi = y[i];
+        x[i] = rot.c * xi - rot.s * yi;
+        y[i] = rot.s * xi + rot.c * yi;
+    }
+}
+
+// M.rightCols(ncol_from..end).applyOnTheLeft(p, q, rot.adjoint())
+inline void apply_on_the_left_adj(Mat& M, Index col_from, Index p, Index q, const Jacobi& rot)
+{
+    for (Index j = col_from; j < M.c; j++)
+    {
+        const double x = M(p, j), y = M(q, j);
+        M(p, j) = rot.c * x - rot.s * y;
+        M(q, j) = rot.s * x + rot.c * y;
+    }
+}
+
+// v.makeHouseholder(ess, tau, beta) for v in R^3  (UpperHessenbergSchur.h:302)
+inline void make_householder3(const double v[3], double ess[2], double& tau, double& beta)
+{
+    const double tail_sq = v[1] * v[1] + v[2] * v[2];
+    const double c0 = v[0];
+    if (tail_sq <= kMin)
+    {
+        tau = 0.0;
+        beta = c0;
+        ess[0] = ess[1] = 0.0;
+    }
+    else
+    {
+        beta = std::sqrt(c0 * c0 + tail_sq);
+        if (c0 >= 0.0)
+            beta = -beta;
+        ess[0] = v[1] / (c0 - beta);
+        ess[1] = v[2] / (c0 - beta);
+        tau = (beta - c0) / beta;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LinAlg/Givens.h
+// ---------------------------------------------------------------------------------------------
+
+// StableScaling<double>::run  (Givens.h:28-86): given a >= b > 0
+inline void stable_scaling(double a, double b, double& r, double& c, double& s)
+{
+    const double t = b / a;
+    const double cutoff = 0.1 * std::pow(kEps, 0.25);
+    if (t >= cutoff)
+    {
+        r = std::hypot(a, b);
+        c = a / r;
+        s = b / r;
+    }
+    else
+    {
+        const double t2 = t * t;
+        c = 1.0 - t2 * (0.5 - t2 * (0.375 - 0.3125 * t2));
+        s = t * c;
+        r = a + 0.5 * b * t * (1.0 - t2 * (0.25 - 0.125 * t2));
+    }
+}
+
+// Givens<double>::compute_rotation  (Givens.h:166-205): c*x - s*y = r, s*x + c*y = 0
+inline void givens_rotation(double x, double y, double& r, double& c, double& s)
+{
+    const double xsign = (x > 0.0) ? 1.0 : -1.0;
+    const double xabs = std::abs(x);
+    if (y == 0.0)
+    {
+        c = (x == 0.0) ? 1.0 : xsign;
+        s = 0.0;
+        r = xabs;
+        return;
+    }
+    const double ysign = (y > 0.0) ? 1.0 : -1.0;
+    const double yabs = std::abs(y);
+    if (x == 0.0)
+    {
+        c = 0.0;
+        s = -ysign;
+        r = yabs;
+        return;
+    }
+    if (xabs >= yabs)
+    {
+        stable_scaling(xabs, yabs, r, c, s);
+        c = xsign * c;
+        s = -ysign * s;
+    }
+    else
+    {
+        stable_scaling(yabs, xabs, r, s, c);
+        c = xsign * c;
+        s = -ysign * s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LinAlg/UpperHessenbergQR.h
+// ---------------------------------------------------------------------------------------------
+
+// UpperHessenbergQR<double>  (UpperHessenbergQR.h:46-447)
+class UpperHessenbergQR
+{
+protected:
+    Index m_n;
+    double m_shift = 0.0;
+    std::vector<double> m_rot_cos, m_rot_sin;
+    bool m_computed = false;
+
+private:
+    Mat m_mat_R;
+
+public:
+    explicit UpperHessenbergQR(Index size) : m_n(size), m_rot_cos(size > 0 ? size - 1 : 0), m_rot_sin(size > 0 ? size - 1 : 0) {}
+    virtual ~UpperHessenbergQR() {}
+
+    // :136-195
+    virtual void compute(const Mat& mat, double shift = 0.0)
+    {
+        m_n = mat.r;
+        if (m_n != mat.c)
+            throw std::invalid_argument("UpperHessenbergQR: matrix must be square");
+        m_shift = shift;
+        m_mat_R = mat;
+        m_rot_cos.assign(m_n - 1, 0.0);
+        m_rot_sin.assign(m_n - 1, 0.0);
+        for (Index i = 0; i < m_n; i++)
+            m_mat_R(i, i) -= m_shift;
+
+        const Index n1 = m_n - 1;
+        for (Index i = 0; i < n1; i++)
+        {
+            double* Rii = &m_mat_R(i, i);
+            std::fill(Rii + 2, Rii + m_n - i, 0.0);
+            const double xi = Rii[0], xj = Rii[1];
+            double r, c, s;
+            givens_rotation(xi, xj, r, c, s);
+            m_rot_cos[i] = c;
+            m_rot_sin[i] = s;
+            Rii[0] = r;
+            Rii[1] = 0.0;
+            double* ptr = Rii + m_n;
+            for (Index j = i + 1; j < m_n; j++, ptr += m_n)
+            {
+                const double tmp = ptr[0];
+                ptr[0] = c * tmp - s * ptr[1];
+                ptr[1] = s * tmp + c * ptr[1];
+            }
+        }
+        m_computed = true;
+    }
+
+    virtual Mat matrix_R() const
+    {
+        if (!m_computed)
+            throw std::logic_error("UpperHessenbergQR: need to call compute() first");
+        return m_mat_R;
+    }
+
+    // :219-255  dest = RQ + sI
+    virtual void matrix_QtHQ(Mat& dest) const
+    {
+        if (!m_computed)
+            throw std::logic_error("UpperHessenbergQR: need to call compute() first");
+        dest = m_mat_R;
+        const Index n1 = m_n - 1;
+        for (Index i = 0; i < n1; i++)
+        {
+            const double c = m_rot_cos[i], s = m_rot_sin[i];
+            double* Yi = dest.col(i);
+            double* Yi1 = Yi + m_n;
+            const Index i2 = i + 2;
+            for (Index j = 0; j < i2; j++)
+            {
+                const double tmp = Yi[j];
+                Yi[j] = c * tmp - s * Yi1[j];
+                Yi1[j] = s * tmp + c * Yi1[j];
+            }
+        }
+        for (Index i = 0; i < m_n; i++)
+            dest(i, i) += m_shift;
+    }
+
+    // :383-417  Y -> Y*Q
+    void apply_YQ(Mat& Y) const
+    {
+        if (!m_computed)
+            throw std::logic_error("UpperHessenbergQR: need to call compute() first");
+        const Index n1 = m_n - 1;
+        const Index nrow = Y.r;
+        for (Index i = 0; i < n1; i++)
+        {
+            const double c = m_rot_cos[i], s = m_rot_sin[i];
+            double* Yi = Y.col(i);
+            double* Yi1 = Y.col(i + 1);
+            for (Index j = 0; j < nrow; j++)
+            {
+                const double tmp = Yi[j];
+                Yi[j] = c * tmp - s * Yi1[j];
+                Yi1[j] = s * tmp + c * Yi1[j];
+            }
+        }
+    }
+
+    // :307-380  Y -> Q'Y (row form)
+    void apply_QtY(Mat& Y) const
+    {
+        const Index n1 = m_n - 1;
+        for (Index i = 0; i < n1; i++)
+        {
+            const double c = m_rot_cos[i], s = m_rot_sin[i];
+            for (Index j = 0; j < Y.c; j++)
+            {
+                const double yi = Y(i, j), yi1 = Y(i + 1, j);
+                Y(i, j) = c * yi - s * yi1;
+                Y(i + 1, j) = s * yi + c * yi1;
+            }
+        }
+    }
+
+    const std::vector<double>& rot_cos() const { return m_rot_cos; }
+    const std::vector<double>& rot_sin() const { return m_rot_sin; }
+};
+
+// TridiagQR<double>  (UpperHessenbergQR.h:459-709)
+class TridiagQR : public UpperHessenbergQR
+{
+private:
+    std::vector<double> m_T_diag, m_T_subd, m_R_diag, m_R_supd, m_R_supd2;
+
+public:
+    explicit TridiagQR(Index size) : UpperHessenbergQR(size) {}
+
+    // :515-598
+    void compute(const Mat& mat, double shift = 0.0) override
+    {
+        m_n = mat.r;
+        if (m_n != mat.c)
+            throw std::invalid_argument("TridiagQR: matrix must be square");
+        m_shift = shift;
+        m_rot_cos.assign(m_n - 1, 0.0);
+        m_rot_sin.assign(m_n - 1, 0.0);
+        m_T_diag.resize(m_n);
+        m_T_subd.resize(m_n - 1);
+        for (Index i = 0; i < m_n; i++)
+            m_T_diag[i] = mat(i, i);
+        for (Index i = 0; i < m_n - 1; i++)
+            m_T_subd[i] = mat(i + 1, i);
+
+        // Deflation of small sub-diagonal elements :533-539
+        for (Index i = 0; i < m_n - 1; i++)
+        {
+            if (std::abs(m_T_subd[i]) <= kEps * (std::abs(m_T_diag[i]) + std::abs(m_T_diag[i + 1])))
+                m_T_subd[i] = 0.0;
+        }
+
+        m_R_diag.resize(m_n);
+        m_R_supd.resize(m_n - 1);
+        m_R_supd2.assign(m_n > 2 ? m_n - 2 : 0, 0.0);
+        for (Index i = 0; i < m_n; i++)
+            m_R_diag[i] = m_T_diag[i] - m_shift;
+        for (Index i = 0; i < m_n - 1; i++)
+            m_R_supd[i] = m_T_subd[i];
+
+        const Index n1 = m_n - 1, n2 = m_n - 2;
+        for (Index i = 0; i < n1; i++)
+        {
+            double r, c, s;
+            givens_rotation(m_R_diag[i], m_T_subd[i], r, c, s);
+            m_rot_cos[i] = c;
+            m_rot_sin[i] = s;
+            m_R_diag[i] = r;
+            const double Tii1 = m_R_supd[i];
+            const double Ti1i1 = m_R_diag[i + 1];
+            m_R_supd[i] = c * Tii1 - s * Ti1i1;
+            m_R_diag[i + 1] = s * Tii1 + c * Ti1i1;
+            if (i < n2)
+            {
+                m_R_supd2[i] = -s * m_R_supd[i + 1];
+                m_R_supd[i + 1] *= c;
+            }
+        }
+        m_computed = true;
+    }
+
+    // :607-618
+    Mat matrix_R() const override
+    {
+        if (!m_computed)
+            throw std::logic_error("TridiagQR: need to call compute() first");
+        Mat R(m_n, m_n);
+        for (Index i = 0; i < m_n; i++)
+            R(i, i) = m_R_diag[i];
+        for (Index i = 0; i < m_n - 1; i++)
+            R(i, i + 1) = m_R_supd[i];
+        for (Index i = 0; i < m_n - 2; i++)
+            R(i, i + 2) = m_R_supd2[i];
+        return R;
+    }
+
+    // :627-693  apply Q' and Q to T directly, then deflate, then symmetrise
+    void matrix_QtHQ(Mat& dest) const override
+    {
+        if (!m_computed)
+            throw std::logic_error("TridiagQR: need to call compute() first");
+        dest.resize(m_n, m_n);
+        for (Index i = 0; i < m_n; i++)
+            dest(i, i) = m_T_diag[i];
+        for (Index i = 0; i < m_n - 1; i++)
+            dest(i + 1, i) = m_T_subd[i];
+
+        const Index n1 = m_n - 1, n2 = m_n - 2;
+        for (Index i = 0; i < n1; i++)
+        {
+            const double c = m_rot_cos[i];
+            const double s = m_rot_sin[i];
+            const double cs = c * s, c2 = c * c, s2 = s * s;
+            const double x = dest(i, i), y = dest(i + 1, i), z = dest(i + 1, i + 1);
+            const double c2x = c2 * x, s2x = s2 * x, c2z = c2 * z, s2z = s2 * z;
+            const double csy2 = 2.0 * c * s * y;
+
+            dest(i, i) = c2x - csy2 + s2z;
+            dest(i + 1, i) = cs * (x - z) + (c2 - s2) * y;
+            dest(i + 1, i + 1) = s2x + csy2 + c2z;
+
+            if (i < n2)
+            {
+                const double ci1 = m_rot_cos[i + 1];
+                const double si1 = m_rot_sin[i + 1];
+                const double o = -s * m_T_subd[i + 1];
+                dest(i + 2, i + 1) *= c;
+                dest(i + 1, i) = ci1 * dest(i + 1, i) - si1 * o;
+            }
+        }
+
+        for (Index i = 0; i < n1; i++)
+        {
+            const double diag = std::abs(dest(i, i)) + std::abs(dest(i + 1, i + 1));
+            if (std::abs(dest(i + 1, i)) <= kEps * diag)
+                dest(i + 1, i) = 0.0;
+        }
+        for (Index i = 0; i < n1; i++)
+            dest(i, i + 1) = dest(i + 1, i);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// LinAlg/DoubleShiftQR.h  (:20-438)
+// ---------------------------------------------------------------------------------------------
+class DoubleShiftQR
+{
+private:
+    Index m_n;
+    Mat m_mat_H;
+    double m_shift_s = 0, m_shift_t = 0;
+    std::vector<double> m_ref_u;  // 3 x n, column-major
+    std::vector<unsigned char> m_ref_nr;
+    bool m_computed = false;
+
+    // :55-84
+    static double stable_norm3(double x1, double x2, double x3)
+    {
+        x1 = std::abs(x1);
+        x2 = std::abs(x2);
+        x3 = std::abs(x3);
+        if (x1 < x2)
+            std::swap(x1, x2);
+        if (x1 < x3)
+            std::swap(x1, x3);
+        if (x1 < kNear0)
+            return 0.0;
+        const double r2 = x2 / x1, r3 = x3 / x1;
+        const double cutoff = 0.1 * std::pow(kEps, 0.25);
+        double r = r2 * r2 + r3 * r3;
+        r = (r2 >= cutoff || r3 >= cutoff) ? std::sqrt(1.0 + r) : (1.0 + r * (0.5 - 0.125 * r));
+        return x1 * r;
+    }
+
+    // :88-104
+    static void stable_scaling3(double& x1, double& x2, double& x3)
+    {
+        const double x1sign = (x1 > 0.0) ? 1.0 : -1.0;
+        x1 = std::abs(x1);
+        const double r2 = x2 / x1, r3 = x3 / x1;
+        const double cutoff = 0.1 * std::pow(kEps, 0.25);
+        double r = r2 * r2 + r3 * r3;
+        r = (std::abs(r2) >= cutoff || std::abs(r3) >= cutoff) ? 1.0 / std::sqrt(1.0 + r) : (1.0 - r * (0.5 - 0.375 * r));
+        x1 = x1sign * r;
+        x2 = r2 * r;
+        x3 = r3 * r;
+    }
+
+    // :106-145
+    void compute_reflector(double x1, double x2, double x3, Index ind)
+    {
+        double* u = &m_ref_u[3 * ind];
+        const double x2m = std::abs(x2), x3m = std::abs(x3);
+        if (x2m < kNear0 && x3m < kNear0)
+        {
+            m_ref_nr[ind] = 1;
+            return;
+        }
+        m_ref_nr[ind] = (x3m < kNear0) ? 2 : 3;
+        const double x_norm = (x3m < kNear0) ? eigen_hypot(x1, x2) : stable_norm3(x1, x2, x3);
+        const double rho = double(x1 <= 0.0) - double(x1 > 0.0);
+        const double x1_new = x1 - rho * x_norm, x1m = std::abs(x1_new);
+        u[0] = x1_new;
+        u[1] = x2;
+        u[2] = x3;
+        if (x1m >= x2m && x1m >= x3m)
+            stable_scaling3(u[0], u[1], u[2]);
+        else if (x2m >= x1m && x2m >= x3m)
+            stable_scaling3(u[1], u[0], u[2]);
+        else
+            stable_scaling3(u[2], u[0], u[1]);
+    }
+
+    // :218-253  X is the block of m_mat_H starting at (r0, c0) with nrow x ncol
+    void apply_PX(Mat& M, Index r0, Index c0, Index nrow, Index ncol, Index u_ind) const
+    {
+        const Index nr = m_ref_nr[u_ind];
+        if (nr == 1)
+            return;
+        const double u0 = m_ref_u[3 * u_ind], u1 = m_ref_u[3 * u_ind + 1];
+        const double u0_2 = 2.0 * u0, u1_2 = 2.0 * u1;
+        if (nr == 2 || nrow == 2)
+        {
+            for (Index j = 0; j < ncol; j++)
+            {
+                double* x = &M(r0, c0 + j);
+                const double tmp = u0_2 * x[0] + u1_2 * x[1];
+                x[0] -= tmp * u0;
+                x[1] -= tmp * u1;
+            }
+        }
+        else
+        {
+            const double u2 = m_ref_u[3 * u_ind + 2];
+            const double u2_2 = 2.0 * u2;
+            for (Index j = 0; j < ncol; j++)
+            {
+                double* x = &M(r0, c0 + j);
+                const double tmp = u0_2 * x[0] + u1_2 * x[1] + u2_2 * x[2];
+                x[0] -= tmp * u0;
+                x[1] -= tmp * u1;
+                x[2] -= tmp * u2;
+            }
+        }
+    }
+
+    // :278-314
+    void apply_XP(Mat& M, Index r0, Index c0, Index nrow, Index ncol, Index u_ind) const
+    {
+        const Index nr = m_ref_nr[u_ind];
+        if (nr == 1)
+            return;
+        const double u0 = m_ref_u[3 * u_ind], u1 = m_ref_u[3 * u_ind + 1];
+        const double u0_2 = 2.0 * u0, u1_2 = 2.0 * u1;
+        double* X0 = &M(r0, c0);
+        double* X1 = X0 + M.r;
+        if (nr == 2 || ncol == 2)
+        {
+            for (Index i = 0; i < nrow; i++)
+            {
+                const double tmp = u0_2 * X0[i] + u1_2 * X1[i];
+                X0[i] -= tmp * u0;
+                X1[i] -= tmp * u1;
+            }
+        }
+        else
+        {
+            double* X2 = X1 + M.r;
+            const double u2 = m_ref_u[3 * u_ind + 2];
+            const double u2_2 = 2.0 * u2;
+            for (Index i = 0; i < nrow; i++)
+            {
+                const double tmp = u0_2 * X0[i] + u1_2 * X1[i] + u2_2 * X2[i];
+                X0[i] -= tmp * u0;
+                X1[i] -= tmp * u1;
+                X2[i] -= tmp * u2;
+            }
+        }
+    }
+
+    // :153-214
+    void update_block(Index il, Index iu)
+    {
+        const Index bsize = iu - il + 1;
+        if (bsize == 1)
+        {
+            m_ref_nr[il] = 1;
+            return;
+        }
+        const double x00 = m_mat_H(il, il), x01 = m_mat_H(il, il + 1), x10 = m_mat_H(il + 1, il), x11 = m_mat_H(il + 1, il + 1);
+        const double m00 = x00 * (x00 - m_shift_s) + x01 * x10 + m_shift_t;
+        const double m10 = x10 * (x00 + x11 - m_shift_s);
+        if (bsize == 2)
+        {
+            compute_reflector(m00, m10, 0.0, il);
+            apply_PX(m_mat_H, il, il, 2, m_n - il, il);
+            apply_XP(m_mat_H, 0, il, il + 2, 2, il);
+            m_ref_nr[il + 1] = 1;
+            return;
+        }
+        const double m20 = m_mat_H(il + 2, il + 1) * m_mat_H(il + 1, il);
+        compute_reflector(m00, m10, m20, il);
+        apply_PX(m_mat_H, il, il, 3, m_n - il, il);
+        apply_XP(m_mat_H, 0, il, il + std::min(bsize, Index(4)), 3, il);
+        for (Index i = 1; i < bsize - 2; i++)
+        {
+            const double* x = &m_mat_H(il + i, il + i - 1);
+            compute_reflector(x[0], x[1], x[2], il + i);
+            apply_PX(m_mat_H, il + i, il + i - 1, 3, m_n - il - i + 1, il + i);
+            apply_XP(m_mat_H, 0, il + i, il + std::min(bsize, Index(i + 4)), 3, il + i);
+        }
+        compute_reflector(m_mat_H(iu - 1, iu - 2), m_mat_H(iu, iu - 2), 0.0, iu - 1);
+        apply_PX(m_mat_H, iu - 1, iu - 2, 2, m_n - iu + 2, iu - 1);
+        apply_XP(m_mat_H, 0, iu - 1, il + bsize, 2, iu - 1);
+        m_ref_nr[iu] = 1;
+    }
+
+public:
+    explicit DoubleShiftQR(Index size) : m_n(size) {}
+
+    // :334-398
+    void compute(const Mat& mat, double s, double t)
+    {
+        m_n = mat.r;
+        if (m_n != mat.c)
+            throw std::invalid_argument("DoubleShiftQR: matrix must be square");
+        m_mat_H = mat;
+        m_shift_s = s;
+        m_shift_t = t;
+        m_ref_u.assign(3 * m_n, 0.0);
+        m_ref_nr.assign(m_n, 0);
+
+        const double eps_abs = kNear0 * (double(m_n) / kEps);
+        const double eps_rel = kEps;
+        std::vector<Index> zero_ind;
+        zero_ind.reserve(m_n - 1);
+        zero_ind.push_back(0);
+        for (Index i = 0; i < m_n - 1; i++)
+        {
+            double* Hii = &m_mat_H(i, i);
+            const double h = std::abs(Hii[1]);
+            const double diag = std::abs(Hii[0]) + std::abs(Hii[m_n + 1]);
+            if (h <= eps_abs || h <= eps_rel * diag)
+            {
+                Hii[1] = 0.0;
+                zero_ind.push_back(i + 1);
+            }
+            std::fill(Hii + 2, Hii + m_n - i, 0.0);
+        }
+        zero_ind.push_back(m_n);
+
+        const Index len = Index(zero_ind.size()) - 1;
+        for (Index i = 0; i < len; i++)
+        {
+            const Index start = zero_ind[i];
+            const Index end = zero_ind[i + 1] - 1;
+            update_block(start, end);
+        }
+
+        for (Index i = 0; i < m_n - 1; i++)
+        {
+            double* Hii = &m_mat_H(i, i);
+            const double h = std::abs(Hii[1]);
+            const double diag = std::abs(Hii[0]) + std::abs(Hii[m_n + 1]);
+            if (h <= eps_abs || h <= eps_rel * diag)
+                Hii[1] = 0.0;
+        }
+        m_computed = true;
+    }
+
+    // :400-406
+    void matrix_QtHQ(Mat& dest) const
+    {
+        if (!m_computed)
+            throw std::logic_error("DoubleShiftQR: need to call compute() first");
+        dest = m_mat_H;
+    }
+
+    // :425-437
+    void apply_YQ(Mat& Y) const
+    {
+        if (!m_computed)
+            throw std::logic_error("DoubleShiftQR: need to call compute() first");
+        const Index nrow = Y.r;
+        const Index n2 = m_n - 2;
+        for (Index i = 0; i < n2; i++)
+            apply_XP(Y, 0, i, nrow, 3, i);
+        apply_XP(Y, 0, n2, nrow, 2, n2);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// LinAlg/TridiagEigen.h  (:24-229)
+// ---------------------------------------------------------------------------------------------
+class TridiagEigen
+{
+private:
+    Index m_n = 0;
+    std::vector<double> m_main_diag, m_sub_diag;
+    Mat m_evecs;
+    bool m_computed = false;
+
+    // :44-108
+    static void tridiagonal_qr_step(double* diag, double* subdiag, Index start, Index end, Mat& Q, Index n)
+    {
+        double td = (diag[end - 1] - diag[end]) * 0.5;
+        double e = subdiag[end - 1];
+        double mu = diag[end];
+        if (td == 0.0)
+            mu -= std::abs(e);
+        else if (e != 0.0)
+        {
+            const double e2 = e * e;
+            const double h = eigen_hypot(td, e);
+            if (e2 == 0.0)
+                mu -= e / ((td + (td > 0.0 ? h : -h)) / e);
+            else
+                mu -= e2 / (td + (td > 0.0 ? h : -h));
+        }
+
+        double x = diag[start] - mu;
+        double z = subdiag[start];
+        for (Index k = start; k < end && z != 0.0; ++k)
+        {
+            Jacobi rot;
+            rot.make_givens(x, z);
+            const double s = rot.s, c = rot.c;
+
+            const double sdk = s * diag[k] + c * subdiag[k];
+            const double dkp1 = s * subdiag[k] + c * diag[k + 1];
+
+            diag[k] = c * (c * diag[k] - s * subdiag[k]) - s * (c * subdiag[k] - s * diag[k + 1]);
+            diag[k + 1] = s * sdk + c * dkp1;
+            subdiag[k] = c * sdk - s * dkp1;
+
+            if (k > start)
+                subdiag[k - 1] = c * subdiag[k - 1] - s * z;
+
+            x = subdiag[k];
+            if (k < end - 1)
+            {
+                z = -s * subdiag[k + 1];
+                subdiag[k + 1] = c * subdiag[k + 1];
+            }
+            apply_on_the_right(Q, n, k, k + 1, rot);
+        }
+    }
+
+public:
+    TridiagEigen() {}
+    explicit TridiagEigen(const Mat& mat) { compute(mat); }
+
+    // :121-210
+    void compute(const Mat& mat)
+    {
+        m_n = mat.r;
+        if (m_n != mat.c)
+            throw std::invalid_argument("TridiagEigen: matrix must be square");
+        m_main_diag.assign(m_n, 0.0);
+        m_sub_diag.assign(m_n > 0 ? m_n - 1 : 0, 0.0);
+        m_evecs.resize(m_n, m_n);
+        m_evecs.set_identity();
+
+        double scale = 0.0;
+        for (Index i = 0; i < m_n; i++)
+            scale = std::max(scale, std::abs(mat(i, i)));
+        for (Index i = 0; i < m_n - 1; i++)
+            scale = std::max(scale, std::abs(mat(i + 1, i)));
+        if (scale < kNear0)
+        {
+            m_computed = true;
+            return;
+        }
+        for (Index i = 0; i < m_n; i++)
+            m_main_diag[i] = mat(i, i) / scale;
+        for (Index i = 0; i < m_n - 1; i++)
+            m_sub_diag[i] = mat(i + 1, i) / scale;
+
+        double* diag = m_main_diag.data();
+        double* subdiag = m_sub_diag.data();
+        Index end = m_n - 1;
+        Index start = 0;
+        Index iter = 0;
+        int info = 0;
+        const double considerAsZero = kMin;
+        const double precision_inv = 1.0 / kEps;
+
+        while (end > 0)
+        {
+            for (Index i = start; i < end; i++)
+            {
+                if (std::abs(subdiag[i]) <= considerAsZero)
+                    subdiag[i] = 0.0;
+                else
+                {
+                    const double scaled_subdiag = precision_inv * subdiag[i];
+                    if (scaled_subdiag * scaled_subdiag <= (std::abs(diag[i]) + std::abs(diag[i + 1])))
+                        subdiag[i] = 0.0;
+                }
+            }
+            while (end > 0 && subdiag[end - 1] == 0.0)
+                end--;
+            if (end <= 0)
+                break;
+            iter++;
+            if (iter > 30 * m_n)
+            {
+                info = 1;
+                break;
+            }
+            start = end - 1;
+            while (start > 0 && subdiag[start - 1] != 0.0)
+                start--;
+            tridiagonal_qr_step(diag, subdiag, start, end, m_evecs, m_n);
+        }
+        if (info > 0)
+            throw std::runtime_error("TridiagEigen: eigen decomposition failed");
+        for (Index i = 0; i < m_n; i++)
+            m_main_diag[i] *= scale;
+        m_computed = true;
+    }
+
+    const std::vector<double>& eigenvalues() const
+    {
+        if (!m_computed)
+            throw std::logic_error("TridiagEigen: need to call compute() first");
+        return m_main_diag;
+    }
+    const Mat& eigenvectors() const
+    {
+        if (!m_computed)
+            throw std::logic_error("TridiagEigen: need to call compute() first");
+        return m_evecs;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// LinAlg/UpperHessenbergSchur.h  (:29-452)
+// ---------------------------------------------------------------------------------------------
+class UpperHessenbergSchur
+{
+private:
+    Index m_n = 0;
+    Mat m_T, m_U;
+    bool m_computed = false;
+
+    // :44-51
+    static double upper_hessenberg_l1_norm(const Mat& x)
+    {
+        const Index n = x.c;
+        double norm = 0.0;
+        for (Index j = 0; j < n; j++)
+        {
+            const Index len = std::min(n, j + 2);
+            double s = 0.0;
+            for (Index i = 0; i < len; i++)
+                s += std::abs(x(i, j));
+            norm += s;
+        }
+        return norm;
+    }
+
+    // :54-73
+    Index find_small_subdiag(Index iu, double near_0) const
+    {
+        Index res = iu;
+        while (res > 0)
+        {
+            double s = std::abs(m_T(res - 1, res - 1)) + std::abs(m_T(res, res));
+            s = std::max(s * kEps, near_0);
+            if (std::abs(m_T(res, res - 1)) <= s)
+                break;
+            res--;
+        }
+        return res;
+    }
+
+    // :76-100
+    void split_off_two_rows(Index iu, double ex_shift)
+    {
+        const double p = 0.5 * (m_T(iu - 1, iu - 1) - m_T(iu, iu));
+        const double q = p * p + m_T(iu, iu - 1) * m_T(iu - 1, iu);
+        m_T(iu, iu) += ex_shift;
+        m_T(iu - 1, iu - 1) += ex_shift;
+        if (q >= 0.0)
+        {
+            const double z = std::sqrt(std::abs(q));
+            Jacobi rot;
+            rot.make_givens((p >= 0.0) ? (p + z) : (p - z), m_T(iu, iu - 1));
+            apply_on_the_left_adj(m_T, iu - 1, iu - 1, iu, rot);  // rightCols(m_n - iu + 1)
+            apply_on_the_right(m_T, iu + 1, iu - 1, iu, rot);     // topRows(iu + 1)
+            m_T(iu, iu - 1) = 0.0;
+            apply_on_the_right(m_U, m_n, iu - 1, iu, rot);
+        }
+        if (iu > 1)
+            m_T(iu - 1, iu - 2) = 0.0;
+    }
+
+    // :103-142
+    void compute_shift(Index iu, Index iter, double& ex_shift, double shift_info[3])
+    {
+        shift_info[0] = m_T(iu, iu);
+        shift_info[1] = m_T(iu - 1, iu - 1);
+        shift_info[2] = m_T(iu, iu - 1) * m_T(iu - 1, iu);
+        if (iter == 10)
+        {
+            ex_shift += shift_info[0];
+            for (Index i = 0; i <= iu; ++i)
+                m_T(i, i) -= shift_info[0];
+            const double s = std::abs(m_T(iu, iu - 1)) + std::abs(m_T(iu - 1, iu - 2));
+            shift_info[0] = 0.75 * s;
+            shift_info[1] = 0.75 * s;
+            shift_info[2] = -0.4375 * s * s;
+        }
+        if (iter == 30)
+        {
+            double s = (shift_info[1] - shift_info[0]) / 2.0;
+            s = s * s + shift_info[2];
+            if (s > 0.0)
+            {
+                s = std::sqrt(s);
+                if (shift_info[1] < shift_info[0])
+                    s = -s;
+                s = s + (shift_info[1] - shift_info[0]) / 2.0;
+                s = shift_info[0] - shift_info[2] / s;
+                ex_shift += s;
+                for (Index i = 0; i <= iu; ++i)
+                    m_T(i, i) -= s;
+                shift_info[0] = shift_info[1] = shift_info[2] = 0.964;
+            }
+        }
+    }
+
+    // :145-166
+    void init_francis_qr_step(Index il, Index iu, const double shift_info[3], Index& im, double v[3]) const
+    {
+        for (im = iu - 2; im >= il; --im)
+        {
+            const double Tmm = m_T(im, im);
+            const double r = shift_info[0] - Tmm;
+            const double s = shift_info[1] - Tmm;
+            v[0] = (r * s - shift_info[2]) / m_T(im + 1, im) + m_T(im, im + 1);
+            v[1] = m_T(im + 1, im + 1) - Tmm - r - s;
+            v[2] = m_T(im + 2, im + 1);
+            if (im == il)
+                break;
+            const double lhs = m_T(im, im - 1) * (std::abs(v[1]) + std::abs(v[2]));
+            const double rhs = v[0] * (std::abs(m_T(im - 1, im - 1)) + std::abs(Tmm) + std::abs(m_T(im + 1, im + 1)));
+            if (std::abs(lhs) < kEps * rhs)
+                break;
+        }
+    }
+
+    // :170-181
+    static void apply_householder_left(const double ess[2], double tau, double* x, Index ncol, Index stride)
+    {
+        const double v1 = ess[0], v2 = ess[1];
+        const double* const x_end = x + ncol * stride;
+        for (; x < x_end; x += stride)
+        {
+            const double tvx = tau * (x[0] + v1 * x[1] + v2 * x[2]);
+            x[0] -= tvx;
+            x[1] -= tvx * v1;
+            x[2] -= tvx * v2;
+        }
+    }
+
+    // :185-198 (the SIMD variant :202-284 performs the same per-row arithmetic)
+    static void apply_householder_right(const double ess[2], double tau, double* x, Index nrow, Index stride)
+    {
+        const double v1 = ess[0], v2 = ess[1];
+        double* x0 = x;
+        double* x1 = x + stride;
+        double* x2 = x1 + stride;
+        for (Index i = 0; i < nrow; i++)
+        {
+            const double txv = tau * (x0[i] + v1 * x1[i] + v2 * x2[i]);
+            x0[i] -= txv;
+            x1[i] -= txv * v1;
+            x2[i] -= txv * v2;
+        }
+    }
+
+    // :287-341
+    void perform_francis_qr_step(Index il, Index im, Index iu, const double first_householder_vec[3], double near_0)
+    {
+        for (Index k = im; k <= iu - 2; ++k)
+        {
+            const bool first_iter = (k == im);
+            double v[3];
+            if (first_iter)
+            {
+                v[0] = first_householder_vec[0];
+                v[1] = first_householder_vec[1];
+                v[2] = first_householder_vec[2];
+            }
+            else
+            {
+                v[0] = m_T(k, k - 1);
+                v[1] = m_T(k + 1, k - 1);
+                v[2] = m_T(k + 2, k - 1);
+            }
+            double tau, beta, ess[2];
+            make_householder3(v, ess, tau, beta);
+            if (std::abs(beta) > near_0)
+            {
+                if (first_iter && k > il)
+                    m_T(k, k - 1) = -m_T(k, k - 1);
+                else if (!first_iter)
+                    m_T(k, k - 1) = beta;
+                apply_householder_left(ess, tau, &m_T(k, k), m_n - k, m_n);
+                apply_householder_right(ess, tau, &m_T(0, k), std::min(iu, k + 3) + 1, m_n);
+                apply_householder_right(ess, tau, &m_U(0, k), m_n, m_n);
+            }
+        }
+        Jacobi rot;
+        double beta;
+        rot.make_givens(m_T(iu - 1, iu - 2), m_T(iu, iu - 2), &beta);
+        if (std::abs(beta) > near_0)
+        {
+            m_T(iu - 1, iu - 2) = beta;
+            apply_on_the_left_adj(m_T, iu - 1, iu - 1, iu, rot);
+            apply_on_the_right(m_T, iu + 1, iu - 1, iu, rot);
+            apply_on_the_right(m_U, m_n, iu - 1, iu, rot);
+        }
+        for (Index i = im + 2; i <= iu; ++i)
+        {
+            m_T(i, i - 2) = 0.0;
+            if (i > im + 2)
+                m_T(i, i - 3) = 0.0;
+        }
+    }
+
+public:
+    UpperHessenbergSchur() {}
+
+    // :354-425
+    void compute(const Mat& mat)
+    {
+        if (mat.r != mat.c)
+            throw std::invalid_argument("UpperHessenbergSchur: matrix must be square");
+        m_n = mat.r;
+        const Index max_iter = m_n * 40;
+        m_T = mat;
+        m_U.resize(m_n, m_n);
+        m_U.set_identity();
+
+        Index iu = m_n - 1;
+        Index iter = 0;
+        Index total_iter = 0;
+        double ex_shift = 0.0;
+        const double norm = upper_hessenberg_l1_norm(m_T);
+        const double near_0 = std::max(norm * kEps * kEps, kMin);
+
+        if (norm != 0.0)
+        {
+            while (iu >= 0)
+            {
+                const Index il = find_small_subdiag(iu, near_0);
+                if (il == iu)
+                {
+                    m_T(iu, iu) += ex_shift;
+                    if (iu > 0)
+                        m_T(iu, iu - 1) = 0.0;
+                    iu--;
+                    iter = 0;
+                }
+                else if (il == iu - 1)
+                {
+                    split_off_two_rows(iu, ex_shift);
+                    iu -= 2;
+                    iter = 0;
+                }
+                else
+                {
+                    double first_householder_vec[3] = {0, 0, 0}, shift_info[3];
+                    compute_shift(iu, iter, ex_shift, shift_info);
+                    iter++;
+                    total_iter++;
+                    if (total_iter > max_iter)
+                        break;
+                    Index im;
+                    init_francis_qr_step(il, iu, shift_info, im, first_householder_vec);
+                    perform_francis_qr_step(il, im, iu, first_householder_vec, near_0);
+                }
+            }
+        }
+        if (total_iter > max_iter)
+            throw std::runtime_error("UpperHessenbergSchur: Schur decomposition failed");
+        m_computed = true;
+    }
+
+    const Mat& matrix_T() const { return m_T; }
+    const Mat& matrix_U() const { return m_U; }
+    void swap_T(Mat& other) { std::swap(m_T, other); }
+    void swap_U(Mat& other) { std::swap(m_U, other); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// LinAlg/UpperHessenbergEigen.h  (real specialisation, :32-321)
+// ---------------------------------------------------------------------------------------------
+class UpperHessenbergEigen
+{
+private:
+    Index m_n = 0;
+    UpperHessenbergSchur m_schur;
+    Mat m_matT, m_eivec;
+    std::vector<Complex> m_eivalues;
+    bool m_computed = false;
+
+    // row(i).segment(l, len) . col(n).segment(l, len)
+    double row_col_dot(Index i, Index n, Index l, Index len) const
+    {
+        double s = 0.0;
+        for (Index k = 0; k < len; k++)
+            s += m_matT(i, l + k) * m_matT(l + k, n);
+        return s;
+    }
+
+    // :53-208
+    void doComputeEigenvectors()
+    {
+        using std::abs;
+        const Index size = m_eivec.c;
+        const double eps = kEps;
+
+        double norm = 0.0;
+        for (Index j = 0; j < size; ++j)
+        {
+            const Index from = std::max(j - 1, Index(0));
+            double s = 0.0;
+            for (Index k = from; k < size; k++)
+                s += abs(m_matT(j, k));
+            norm += s;
+        }
+        if (norm == 0.0)
+            return;
+
+        for (Index n = size - 1; n >= 0; n--)
+        {
+            const double p = m_eivalues[n].real();
+            const double q = m_eivalues[n].imag();
+
+            if (q == 0.0)
+            {
+                double lastr = 0.0, lastw = 0.0;
+                Index l = n;
+                m_matT(n, n) = 1.0;
+                for (Index i = n - 1; i >= 0; i--)
+                {
+                    const double w = m_matT(i, i) - p;
+                    const double r = row_col_dot(i, n, l, n - l + 1);
+                    if (m_eivalues[i].imag() < 0.0)
+                    {
+                        lastw = w;
+                        lastr = r;
+                    }
+                    else
+                    {
+                        l = i;
+                        if (m_eivalues[i].imag() == 0.0)
+                        {
+                            if (w != 0.0)
+                                m_matT(i, n) = -r / w;
+                            else
+                                m_matT(i, n) = -r / (eps * norm);
+                        }
+                        else
+                        {
+                            const double x = m_matT(i, i + 1);
+                            const double y = m_matT(i + 1, i);
+                            const double denom = (m_eivalues[i].real() - p) * (m_eivalues[i].real() - p) + m_eivalues[i].imag() * m_eivalues[i].imag();
+                            const double t = (x * lastr - lastw * r) / denom;
+                            m_matT(i, n) = t;
+                            if (abs(x) > abs(lastw))
+                                m_matT(i + 1, n) = (-r - w * t) / x;
+                            else
+                                m_matT(i + 1, n) = (-lastr - y * t) / lastw;
+                        }
+                        const double t = abs(m_matT(i, n));
+                        if ((eps * t) * t > 1.0)
+                            for (Index k = i; k < size; k++)
+                                m_matT(k, n) /= t;
+                    }
+                }
+            }
+            else if (q < 0.0 && n > 0)
+            {
+                double lastra = 0.0, lastsa = 0.0, lastw = 0.0;
+                Index l = n - 1;
+                if (abs(m_matT(n, n - 1)) > abs(m_matT(n - 1, n)))
+                {
+                    m_matT(n - 1, n - 1) = q / m_matT(n, n - 1);
+                    m_matT(n - 1, n) = -(m_matT(n, n) - p) / m_matT(n, n - 1);
+                }
+                else
+                {
+                    const Complex cc = Complex(0.0, -m_matT(n - 1, n)) / Complex(m_matT(n - 1, n - 1) - p, q);
+                    m_matT(n - 1, n - 1) = cc.real();
+                    m_matT(n - 1, n) = cc.imag();
+                }
+                m_matT(n, n - 1) = 0.0;
+                m_matT(n, n) = 1.0;
+                for (Index i = n - 2; i >= 0; i--)
+                {
+                    const double ra = row_col_dot(i, n - 1, l, n - l + 1);
+                    const double sa = row_col_dot(i, n, l, n - l + 1);
+                    const double w = m_matT(i, i) - p;
+                    if (m_eivalues[i].imag() < 0.0)
+                    {
+                        lastw = w;
+                        lastra = ra;
+                        lastsa = sa;
+                    }
+                    else
+                    {
+                        l = i;
+                        if (m_eivalues[i].imag() == 0.0)
+                        {
+                            const Complex cc = Complex(-ra, -sa) / Complex(w, q);
+                            m_matT(i, n - 1) = cc.real();
+                            m_matT(i, n) = cc.imag();
+                        }
+                        else
+                        {
+                            const double x = m_matT(i, i + 1);
+                            const double y = m_matT(i + 1, i);
+                            double vr = (m_eivalues[i].real() - p) * (m_eivalues[i].real() - p) + m_eivalues[i].imag() * m_eivalues[i].imag() - q * q;
+                            const double vi = (m_eivalues[i].real() - p) * 2.0 * q;
+                            if ((vr == 0.0) && (vi == 0.0))
+                                vr = eps * norm * (abs(w) + abs(q) + abs(x) + abs(y) + abs(lastw));
+
+                            Complex cc = Complex(x * lastra - lastw * ra + q * sa, x * lastsa - lastw * sa - q * ra) / Complex(vr, vi);
+                            m_matT(i, n - 1) = cc.real();
+                            m_matT(i, n) = cc.imag();
+                            if (abs(x) > (abs(lastw) + abs(q)))
+                            {
+                                m_matT(i + 1, n - 1) = (-ra - w * m_matT(i, n - 1) + q * m_matT(i, n)) / x;
+                                m_matT(i + 1, n) = (-sa - w * m_matT(i, n) - q * m_matT(i, n - 1)) / x;
+                            }
+                            else
+                            {
+                                cc = Complex(-lastra - y * m_matT(i, n - 1), -lastsa - y * m_matT(i, n)) / Complex(lastw, q);
+                                m_matT(i + 1, n - 1) = cc.real();
+                                m_matT(i + 1, n) = cc.imag();
+                            }
+                        }
+                        const double t = std::max(abs(m_matT(i, n - 1)), abs(m_matT(i, n)));
+                        if ((eps * t) * t > 1.0)
+                            for (Index k = i; k < size; k++)
+                            {
+                                m_matT(k, n - 1) /= t;
+                                m_matT(k, n) /= t;
+                            }
+                    }
+                }
+                n--;
+            }
+        }
+
+        // Back transformation :202-207
+        std::vector<double> tmp(size);
+        for (Index j = size - 1; j >= 0; j--)
+        {
+            for (Index i = 0; i < size; i++)
+            {
+                double s = 0.0;
+                for (Index k = 0; k <= j; k++)
+                    s += m_eivec(i, k) * m_matT(k, j);
+                tmp[i] = s;
+            }
+            for (Index i = 0; i < size; i++)
+                m_eivec(i, j) = tmp[i];
+        }
+    }
+
+public:
+    UpperHessenbergEigen() {}
+    explicit UpperHessenbergEigen(const Mat& mat) { compute(mat); }
+
+    // :221-277
+    void compute(const Mat& mat)
+    {
+        using std::abs;
+        if (mat.r != mat.c)
+            throw std::invalid_argument("UpperHessenbergEigen: matrix must be square");
+        m_n = mat.r;
+        double scale = 0.0;
+        for (double v : mat.a)
+            scale = std::max(scale, abs(v));
+        Mat scaled = mat;
+        for (double& v : scaled.a)
+            v /= scale;  // no zero guard in the reference (:231-234)
+
+        m_schur.compute(scaled);
+        m_schur.swap_T(m_matT);
+        m_schur.swap_U(m_eivec);
+
+        m_eivalues.assign(m_n, Complex(0, 0));
+        Index i = 0;
+        while (i < m_n)
+        {
+            if (i == m_n - 1 || m_matT(i + 1, i) == 0.0)
+            {
+                m_eivalues[i] = Complex(m_matT(i, i), 0.0);
+                ++i;
+            }
+            else
+            {
+                const double p = 0.5 * (m_matT(i, i) - m_matT(i + 1, i + 1));
+                double z;
+                {
+                    double t0 = m_matT(i + 1, i);
+                    double t1 = m_matT(i, i + 1);
+                    const double maxval = std::max(abs(p), std::max(abs(t0), abs(t1)));
+                    t0 /= maxval;
+                    t1 /= maxval;
+                    const double p0 = p / maxval;
+                    z = maxval * std::sqrt(abs(p0 * p0 + t0 * t1));
+                }
+                m_eivalues[i] = Complex(m_matT(i + 1, i + 1) + p, z);
+                m_eivalues[i + 1] = Complex(m_matT(i + 1, i + 1) + p, -z);
+                i += 2;
+            }
+        }
+        doComputeEigenvectors();
+        for (auto& v : m_eivalues)
+            v *= scale;
+        m_computed = true;
+    }
+
+    const std::vector<Complex>& eigenvalues() const
+    {
+        if (!m_computed)
+            throw std::logic_error("UpperHessenbergEigen: need to call compute() first");
+        return m_eivalues;
+    }
+
+    // :287-320
+    CMat eigenvectors() const
+    {
+        if (!m_computed)
+            throw std::logic_error("UpperHessenbergEigen: need to call compute() first");
+        const Index n = m_eivec.c;
+        CMat matV(n, n);
+        auto normalize_col = [&](Index j) {
+            double sq = 0.0;
+            for (Index i = 0; i < n; i++)
+                sq += std::norm(matV(i, j));
+            if (sq > 0.0)
+            {
+                const double nr = std::sqrt(sq);
+                for (Index i = 0; i < n; i++)
+                    matV(i, j) /= nr;
+            }
+        };
+        for (Index j = 0; j < n; ++j)
+        {
+            if (m_eivalues[j].imag() == 0.0 || j + 1 == n)
+            {
+                for (Index i = 0; i < n; i++)
+                    matV(i, j) = Complex(m_eivec(i, j), 0.0);
+                normalize_col(j);
+            }
+            else
+            {
+                for (Index i = 0; i < n; ++i)
+                {
+                    matV(i, j) = Complex(m_eivec(i, j), m_eivec(i, j + 1));
+                    matV(i, j + 1) = Complex(m_eivec(i, j), -m_eivec(i, j + 1));
+                }
+                normalize_col(j);
+                normalize_col(j + 1);
+                ++j;
+            }
+        }
+        return matV;
+    }
+};
+
+}  // namespace oracle
