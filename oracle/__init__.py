@@ -110,6 +110,19 @@ class Csr:
         self.h = h
 
     @classmethod
+    def adopt(cls, n, rowptr, col, val):
+        """Full CSR used as is (no triangle expansion / transpose)."""
+        self = cls.__new__(cls)
+        self.n = int(n)
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        val = _f64(val)
+        h = C.c_void_p()
+        _check(lib().oracle_csr_adopt(C.c_int64(self.n), _p(rowptr), _p(col), _p(val), C.byref(h)))
+        self.h = h
+        return self
+
+    @classmethod
     def from_scipy(cls, A, mode="gen"):
         import scipy.sparse as sp
 

@@ -72,6 +72,18 @@ int oracle_csr_create(int64_t n, const int64_t* outer, const int32_t* inner, con
     *out = new CsrOp(build_full_csr(n, outer, inner, val, order, mode));
     ORACLE_CATCH
 }
+// adopt an existing full CSR (rows ascending, no expansion) — used for the large synthetic inputs
+int oracle_csr_adopt(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val, void** out)
+{
+    ORACLE_TRY
+    auto* op = new CsrOp();
+    op->n = n;
+    op->rowptr.assign(rowptr, rowptr + n + 1);
+    op->col.assign(col, col + rowptr[n]);
+    op->val.assign(val, val + rowptr[n]);
+    *out = op;
+    ORACLE_CATCH
+}
 void oracle_csr_free(void* h) { delete static_cast<CsrOp*>(h); }
 int64_t oracle_csr_nnz(void* h) { return static_cast<CsrOp*>(h)->rowptr.back(); }
 void oracle_csr_export(void* h, int64_t* rowptr, int32_t* col, double* val)

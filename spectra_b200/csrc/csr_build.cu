@@ -1,0 +1,317 @@
+// Device-side construction of the full CSR operand from the user's compressed arrays.
+//
+// Semantics follow the reference wrappers:
+//   SB200_GENERAL   : y = M x with every stored entry            (MatOp/SparseGenMatProd.h:82-87)
+//   SB200_SYM_LOWER : y = M.selfadjointView<Lower>() x — only entries with row >= col are read and
+//                     mirrored; the strictly-upper stored entries are ignored
+//                                                                  (MatOp/SparseSymMatProd.h:83-88)
+//   SB200_SYM_UPPER : same with row <= col.
+// ColMajor input (Eigen default, CSC) is transposed on the fly.  The arrays are uploaded once; the
+// expansion / transpose (count -> exclusive scan -> scatter -> per-row sort by column) runs on the
+// GPU, so the one-time cost is dominated by the H2D copy.  Duplicate entries of an uncompressed
+// input are kept as separate terms (they add up in the SpMV), columns ascend inside a row, so the
+// SpMV summation order is reproducible.
+#include "kernels.h"
+
+namespace sb200 {
+
+namespace {
+
+template <typename OuterT>
+__global__ void count_kernel(const OuterT* __restrict__ outer, const int* __restrict__ inner, int64_t n, int order, int mode, int64_t row0, int64_t nrows,
+                             int* __restrict__ cnt)
+{
+    for (int64_t o = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int64_t pb = outer[o], pe = outer[o + 1];
+        for (int64_t p = pb; p < pe; p++)
+        {
+            const int64_t in = inner[p];
+            const int64_t i = (order == SB200_COL_MAJOR) ? in : o;
+            const int64_t j = (order == SB200_COL_MAJOR) ? o : in;
+            if (mode == SB200_GENERAL)
+            {
+                if (i >= row0 && i < row0 + nrows)
+                    atomicAdd(cnt + (i - row0), 1);
+            }
+            else
+            {
+                const bool used = (mode == SB200_SYM_LOWER) ? (i >= j) : (i <= j);
+                if (!used)
+                    continue;
+                if (i >= row0 && i < row0 + nrows)
+                    atomicAdd(cnt + (i - row0), 1);
+                if (i != j && j >= row0 && j < row0 + nrows)
+                    atomicAdd(cnt + (j - row0), 1);
+            }
+        }
+    }
+}
+
+template <typename OuterT>
+__global__ void fill_kernel(const OuterT* __restrict__ outer, const int* __restrict__ inner, const double* __restrict__ values, int64_t n, int order, int mode,
+                            int64_t row0, int64_t nrows, const int* __restrict__ rowptr, int* __restrict__ cursor, int* __restrict__ col, double* __restrict__ val)
+{
+    for (int64_t o = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int64_t pb = outer[o], pe = outer[o + 1];
+        for (int64_t p = pb; p < pe; p++)
+        {
+            const int64_t in = inner[p];
+            const int64_t i = (order == SB200_COL_MAJOR) ? in : o;
+            const int64_t j = (order == SB200_COL_MAJOR) ? o : in;
+            const double v = values[p];
+            bool put_ij = false, put_ji = false;
+            if (mode == SB200_GENERAL)
+                put_ij = true;
+            else
+            {
+                const bool used = (mode == SB200_SYM_LOWER) ? (i >= j) : (i <= j);
+                put_ij = used;
+                put_ji = used && (i != j);
+            }
+            if (put_ij && i >= row0 && i < row0 + nrows)
+            {
+                const int li = (int) (i - row0);
+                const int q = rowptr[li] + atomicAdd(cursor + li, 1);
+                col[q] = (int) j;
+                val[q] = v;
+            }
+            if (put_ji && j >= row0 && j < row0 + nrows)
+            {
+                const int lj = (int) (j - row0);
+                const int q = rowptr[lj] + atomicAdd(cursor + lj, 1);
+                col[q] = (int) i;
+                val[q] = v;
+            }
+        }
+    }
+}
+
+// Per-row insertion sort by column id (rows are short; long rows only appear in small test inputs).
+__global__ void sort_rows_kernel(const int* __restrict__ rowptr, int* __restrict__ col, double* __restrict__ val, int64_t nrows)
+{
+    for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int b = rowptr[r], e = rowptr[r + 1];
+        for (int p = b + 1; p < e; p++)
+        {
+            const int c = col[p];
+            const double v = val[p];
+            int q = p - 1;
+            while (q >= b && col[q] > c)
+            {
+                col[q + 1] = col[q];
+                val[q + 1] = val[q];
+                q--;
+            }
+            col[q + 1] = c;
+            val[q + 1] = v;
+        }
+    }
+}
+
+// ---- exclusive scan of int counts (three-phase) ----
+constexpr int kScanBlock = 1024;
+constexpr int kScanItems = 4;  // items per thread
+
+__global__ void scan_block_sums_kernel(const int* __restrict__ cnt, int64_t n, long long* __restrict__ block_sums)
+{
+    __shared__ long long s[kScanBlock / 32];
+    const int64_t base = (int64_t) blockIdx.x * kScanBlock * kScanItems;
+    long long acc = 0;
+    for (int t = 0; t < kScanItems; t++)
+    {
+        const int64_t idx = base + (int64_t) threadIdx.x * kScanItems + t;
+        if (idx < n)
+            acc += cnt[idx];
+    }
+    for (int o = 16; o > 0; o >>= 1)
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0)
+        s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        long long t = 0;
+        for (int q = 0; q < kScanBlock / 32; q++)
+            t += s[q];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void scan_offsets_kernel(long long* block_sums, int nblocks, long long* total)
+{
+    // single thread: nblocks is a few thousand at most
+    long long run = 0;
+    for (int b = 0; b < nblocks; b++)
+    {
+        const long long t = block_sums[b];
+        block_sums[b] = run;
+        run += t;
+    }
+    *total = run;
+}
+
+__global__ void scan_write_kernel(const int* __restrict__ cnt, int64_t n, const long long* __restrict__ block_offs, int* __restrict__ rowptr)
+{
+    __shared__ long long s_warp[kScanBlock / 32];
+    const int64_t base = (int64_t) blockIdx.x * kScanBlock * kScanItems;
+    int v[kScanItems];
+    long long mine = 0;
+    for (int t = 0; t < kScanItems; t++)
+    {
+        const int64_t idx = base + (int64_t) threadIdx.x * kScanItems + t;
+        v[t] = (idx < n) ? cnt[idx] : 0;
+        mine += v[t];
+    }
+    // inclusive scan of `mine` across the block
+    long long incl = mine;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl += t;
+    }
+    if (lane == 31)
+        s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0)
+    {
+        long long w = s_warp[lane];
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const long long t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o)
+                w += t;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    long long excl = incl - mine + (warp > 0 ? s_warp[warp - 1] : 0) + block_offs[blockIdx.x];
+    for (int t = 0; t < kScanItems; t++)
+    {
+        const int64_t idx = base + (int64_t) threadIdx.x * kScanItems + t;
+        if (idx < n)
+            rowptr[idx] = (int) excl;
+        excl += v[t];
+    }
+}
+
+// rowptr[n] = total, cursor reset happens by the caller
+__global__ void set_last_kernel(int* rowptr, int64_t n, const long long* total) { rowptr[n] = (int) *total; }
+
+__global__ void narrow_rowptr_kernel(const long long* __restrict__ src, long long base, int* __restrict__ dst, int64_t n)
+{
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+        dst[i] = (int) (src[i] - base);
+}
+
+int grid_for(int64_t n, int block)
+{
+    const int sms = device_info().sm_count;
+    const int64_t need = (n + block - 1) / block;
+    return (int) std::max<int64_t>(1, std::min<int64_t>(need, (int64_t) sms * 16));
+}
+
+template <typename OuterT>
+void build_impl(int64_t n, const OuterT* h_outer, const int32_t* h_inner, const double* h_values, int order, int mode, int64_t row0, int64_t nrows,
+                cudaStream_t stream, DeviceCsr& out)
+{
+    const int64_t nnz_in = (int64_t) h_outer[n] - (int64_t) h_outer[0];
+    SB200_REQUIRE(h_outer[0] == 0, SB200_INVALID_ARGUMENT, "sparse matrix must be in compressed form (outer[0] == 0)");
+    DevBuf<OuterT> d_outer(n + 1);
+    DevBuf<int> d_inner(std::max<int64_t>(nnz_in, 1));
+    DevBuf<double> d_values(std::max<int64_t>(nnz_in, 1));
+    SB200_CUDA_CHECK(cudaMemcpyAsync(d_outer.get(), h_outer, sizeof(OuterT) * (n + 1), cudaMemcpyHostToDevice, stream));
+    if (nnz_in > 0)
+    {
+        SB200_CUDA_CHECK(cudaMemcpyAsync(d_inner.get(), h_inner, sizeof(int) * nnz_in, cudaMemcpyHostToDevice, stream));
+        SB200_CUDA_CHECK(cudaMemcpyAsync(d_values.get(), h_values, sizeof(double) * nnz_in, cudaMemcpyHostToDevice, stream));
+    }
+
+    out.n = n;
+    out.row0 = row0;
+    out.nrows = nrows;
+    out.rowptr.alloc(nrows + 1);
+    DevBuf<int> cnt(std::max<int64_t>(nrows, 1));
+    cnt.zero(stream);
+    const int g = grid_for(n, 256);
+    count_kernel<OuterT><<<g, 256, 0, stream>>>(d_outer.get(), d_inner.get(), n, order, mode, row0, nrows, cnt.get());
+    SB200_CUDA_CHECK(cudaGetLastError());
+
+    const int nblocks = (int) ((nrows + (int64_t) kScanBlock * kScanItems - 1) / ((int64_t) kScanBlock * kScanItems));
+    DevBuf<long long> block_sums(std::max(nblocks, 1) + 1);
+    long long* d_total = block_sums.get() + std::max(nblocks, 1);
+    if (nrows > 0)
+    {
+        scan_block_sums_kernel<<<nblocks, kScanBlock, 0, stream>>>(cnt.get(), nrows, block_sums.get());
+        scan_offsets_kernel<<<1, 1, 0, stream>>>(block_sums.get(), nblocks, d_total);
+        scan_write_kernel<<<nblocks, kScanBlock, 0, stream>>>(cnt.get(), nrows, block_sums.get(), out.rowptr.get());
+        set_last_kernel<<<1, 1, 0, stream>>>(out.rowptr.get(), nrows, d_total);
+        SB200_CUDA_CHECK(cudaGetLastError());
+    }
+    long long total = 0;
+    if (nrows > 0)
+        SB200_CUDA_CHECK(cudaMemcpyAsync(&total, d_total, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+    SB200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    SB200_REQUIRE(total < (1LL << 31), SB200_INVALID_ARGUMENT, "local nnz exceeds the int32 index range");
+    out.nnz = total;
+    out.col.alloc(std::max<int64_t>(total, 1));
+    out.val.alloc(std::max<int64_t>(total, 1));
+    if (total > 0)
+    {
+        cnt.zero(stream);  // reuse as the per-row cursor
+        fill_kernel<OuterT><<<g, 256, 0, stream>>>(d_outer.get(), d_inner.get(), d_values.get(), n, order, mode, row0, nrows, out.rowptr.get(), cnt.get(),
+                                                   out.col.get(), out.val.get());
+        sort_rows_kernel<<<grid_for(nrows, 128), 128, 0, stream>>>(out.rowptr.get(), out.col.get(), out.val.get(), nrows);
+        SB200_CUDA_CHECK(cudaGetLastError());
+    }
+    SB200_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+}  // namespace
+
+void build_device_csr(int64_t n, const void* outer, bool outer64, const int32_t* inner, const double* values, int order, int mode, int64_t row0, int64_t nrows,
+                      cudaStream_t stream, DeviceCsr& out)
+{
+    SB200_REQUIRE(n >= 1, SB200_INVALID_ARGUMENT, "matrix order must be positive");
+    SB200_REQUIRE(n < (1LL << 31), SB200_INVALID_ARGUMENT, "matrix order exceeds the int32 index range");
+    SB200_REQUIRE(order == SB200_COL_MAJOR || order == SB200_ROW_MAJOR, SB200_INVALID_ARGUMENT, "bad storage order");
+    SB200_REQUIRE(mode >= SB200_GENERAL && mode <= SB200_SYM_UPPER, SB200_INVALID_ARGUMENT, "bad matrix mode");
+    if (outer64)
+        build_impl<long long>(n, static_cast<const long long*>(outer), inner, values, order, mode, row0, nrows, stream, out);
+    else
+        build_impl<int>(n, static_cast<const int*>(outer), inner, values, order, mode, row0, nrows, stream, out);
+}
+
+void upload_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64_t* rowptr_local, const int32_t* col, const double* values, cudaStream_t stream,
+                     DeviceCsr& out)
+{
+    SB200_REQUIRE(n >= 1 && n < (1LL << 31), SB200_INVALID_ARGUMENT, "matrix order out of range");
+    SB200_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= n, SB200_INVALID_ARGUMENT, "row slab out of range");
+    const int64_t base = rowptr_local[0];
+    const int64_t nnz = rowptr_local[nrows] - base;
+    SB200_REQUIRE(nnz < (1LL << 31), SB200_INVALID_ARGUMENT, "local nnz exceeds the int32 index range");
+    out.n = n;
+    out.row0 = row0;
+    out.nrows = nrows;
+    out.nnz = nnz;
+    out.rowptr.alloc(nrows + 1);
+    out.col.alloc(std::max<int64_t>(nnz, 1));
+    out.val.alloc(std::max<int64_t>(nnz, 1));
+    DevBuf<long long> tmp(nrows + 1);
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+    SB200_CUDA_CHECK(cudaMemcpyAsync(tmp.get(), rowptr_local, sizeof(int64_t) * (nrows + 1), cudaMemcpyHostToDevice, stream));
+    narrow_rowptr_kernel<<<grid_for(nrows + 1, 256), 256, 0, stream>>>(tmp.get(), base, out.rowptr.get(), nrows + 1);
+    SB200_CUDA_CHECK(cudaGetLastError());
+    if (nnz > 0)
+    {
+        SB200_CUDA_CHECK(cudaMemcpyAsync(out.col.get(), col + base, sizeof(int) * nnz, cudaMemcpyHostToDevice, stream));
+        SB200_CUDA_CHECK(cudaMemcpyAsync(out.val.get(), values + base, sizeof(double) * nnz, cudaMemcpyHostToDevice, stream));
+    }
+    SB200_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+}  // namespace sb200

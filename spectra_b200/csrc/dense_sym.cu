@@ -1,0 +1,511 @@
+// Single-CTA device kernels for the symmetric restart (K7, K8, K10 of SURVEY.md §2.1):
+//   TridiagEigen::compute          LinAlg/TridiagEigen.h:121-210 (+ tridiagonal_qr_step :44-108)
+//   TridiagQR::compute/matrix_QtHQ LinAlg/UpperHessenbergQR.h:515-598, :627-693 ; apply_YQ :383-417
+//   retrieve_ritzpair / num_converged / nev_adjusted / shift loop of restart
+//                                  HermEigsBase.h:205-224, :158-175, :178-202, :105-147
+// so the whole restart decision stays on the device; the host reads back one 16-byte status.
+//
+// Parallelisation: the scalar recurrences (rotation generation on the tridiagonal) are inherently
+// sequential and run on thread 0; applying a sweep of rotations to the m x m eigenvector / Q
+// matrix is row-parallel (thread t owns row t, matrix column-major in shared memory so a warp
+// touches consecutive addresses).  The tridiagonal H is carried as (diag, subdiag) in shared
+// memory.
+#include "dense_common.cuh"
+#include "kernels.h"
+
+namespace sb200 {
+
+namespace {
+
+using namespace dense;
+
+constexpr int kDenseBlock = 128;
+
+struct TriShared
+{
+    double* d;    // working diag        [m]
+    double* e;    // working subdiag     [m]
+    double* rc;   // rotation cosines    [m]
+    double* rs;   // rotation sines      [m]
+    double* ev;   // eigenvalues / keys  [m]
+    double* aux;  // scratch             [m]
+    int* idx;     // sort permutation    [m]
+    double* Z;    // m x m
+};
+
+__device__ __forceinline__ TriShared carve(double* smem, int m)
+{
+    TriShared s;
+    s.d = smem;
+    s.e = s.d + m;
+    s.rc = s.e + m;
+    s.rs = s.rc + m;
+    s.ev = s.rs + m;
+    s.aux = s.ev + m;
+    s.idx = reinterpret_cast<int*>(s.aux + m);
+    s.Z = reinterpret_cast<double*>(s.idx + 2 * ((m + 1) / 2));
+    return s;
+}
+size_t tri_smem_bytes(int m) { return sizeof(double) * (size_t) (6 * m + m * m) + sizeof(int) * (size_t) (2 * ((m + 1) / 2)); }
+
+// One implicit Wilkinson-shift QR step on rows start..end of the (scaled) tridiagonal (thread 0).
+// Stores the rotations in rc/rs[start .. start+nrot) and returns nrot.   TridiagEigen.h:44-108
+__device__ int tridiagonal_qr_step(double* diag, double* subdiag, int start, int end, double* rc, double* rs)
+{
+    const double td = (diag[end - 1] - diag[end]) * 0.5;
+    const double e = subdiag[end - 1];
+    double mu = diag[end];
+    if (td == 0.0)
+        mu -= fabs(e);
+    else if (e != 0.0)
+    {
+        const double e2 = e * e;
+        const double h = eigen_hypot(td, e);
+        if (e2 == 0.0)
+            mu -= e / ((td + (td > 0.0 ? h : -h)) / e);
+        else
+            mu -= e2 / (td + (td > 0.0 ? h : -h));
+    }
+    double x = diag[start] - mu;
+    double z = subdiag[start];
+    int nrot = 0;
+    for (int k = start; k < end && z != 0.0; ++k)
+    {
+        double c, s;
+        make_givens(x, z, c, s);
+        const double sdk = s * diag[k] + c * subdiag[k];
+        const double dkp1 = s * subdiag[k] + c * diag[k + 1];
+        diag[k] = c * (c * diag[k] - s * subdiag[k]) - s * (c * subdiag[k] - s * diag[k + 1]);
+        diag[k + 1] = s * sdk + c * dkp1;
+        subdiag[k] = c * sdk - s * dkp1;
+        if (k > start)
+            subdiag[k - 1] = c * subdiag[k - 1] - s * z;
+        x = subdiag[k];
+        if (k < end - 1)
+        {
+            z = -s * subdiag[k + 1];
+            subdiag[k + 1] = c * subdiag[k + 1];
+        }
+        rc[k] = c;
+        rs[k] = s;
+        nrot++;
+    }
+    return nrot;
+}
+
+// TridiagEigen::compute on (hd, he) = diag / subdiag of H.  On exit sh.ev = eigenvalues (unsorted),
+// sh.Z = eigenvectors.  Returns 0 on success, 1 when the 30*m sweep cap is hit.  Block-collective.
+__device__ int tridiag_eigen_block(const double* hd, const double* he, int m, TriShared& sh)
+{
+    __shared__ int s_state[4];  // 0: action (0 stop, 1 apply), 1: start, 2: nrot, 3: info
+    __shared__ double s_scale;
+    const int tid = threadIdx.x;
+    for (int t = tid; t < m * m; t += kDenseBlock)
+        sh.Z[t] = ((t % m) == (t / m)) ? 1.0 : 0.0;
+    if (tid == 0)
+    {
+        double scale = 0.0;
+        for (int i = 0; i < m; i++)
+            scale = fmax(scale, fabs(hd[i]));
+        for (int i = 0; i < m - 1; i++)
+            scale = fmax(scale, fabs(he[i]));
+        s_scale = scale;
+    }
+    __syncthreads();
+    const double scale = s_scale;
+    if (scale < kNear0)  // zero matrix: eigenvalues 0, vectors identity   (TridiagEigen.h:142-150)
+    {
+        for (int t = tid; t < m; t += kDenseBlock)
+            sh.ev[t] = 0.0;
+        __syncthreads();
+        return 0;
+    }
+    for (int t = tid; t < m; t += kDenseBlock)
+    {
+        sh.d[t] = hd[t] / scale;
+        if (t < m - 1)
+            sh.e[t] = he[t] / scale;
+    }
+    if (tid == 0)
+    {
+        s_state[3] = 0;
+    }
+    __syncthreads();
+
+    // thread-0 loop state lives in registers of thread 0; other threads follow s_state
+    int end = m - 1, start = 0, iter = 0;
+    const double considerAsZero = kMin;
+    const double precision_inv = 1.0 / kEps;
+    while (true)
+    {
+        if (tid == 0)
+        {
+            int action = 0;
+            while (end > 0)
+            {
+                for (int i = start; i < end; i++)
+                {
+                    if (fabs(sh.e[i]) <= considerAsZero)
+                        sh.e[i] = 0.0;
+                    else
+                    {
+                        const double scaled = precision_inv * sh.e[i];
+                        if (scaled * scaled <= (fabs(sh.d[i]) + fabs(sh.d[i + 1])))
+                            sh.e[i] = 0.0;
+                    }
+                }
+                while (end > 0 && sh.e[end - 1] == 0.0)
+                    end--;
+                if (end <= 0)
+                    break;
+                iter++;
+                if (iter > 30 * m)
+                {
+                    s_state[3] = 1;
+                    break;
+                }
+                start = end - 1;
+                while (start > 0 && sh.e[start - 1] != 0.0)
+                    start--;
+                const int nrot = tridiagonal_qr_step(sh.d, sh.e, start, end, sh.rc, sh.rs);
+                if (nrot > 0)
+                {
+                    s_state[1] = start;
+                    s_state[2] = nrot;
+                    action = 1;
+                    break;
+                }
+            }
+            s_state[0] = action;
+        }
+        __syncthreads();
+        if (s_state[0] == 0)
+            break;
+        const int st = s_state[1], nrot = s_state[2];
+        // q.applyOnTheRight(k, k+1, rot)  (TridiagEigen.h:106): row t of Z
+        for (int t = tid; t < m; t += kDenseBlock)
+        {
+            double xk = sh.Z[t + st * m];
+            for (int k = st; k < st + nrot; k++)
+            {
+                const double c = sh.rc[k], s = sh.rs[k];
+                const double yk = sh.Z[t + (k + 1) * m];
+                sh.Z[t + k * m] = c * xk - s * yk;
+                xk = s * xk + c * yk;
+            }
+            sh.Z[t + (st + nrot) * m] = xk;
+        }
+        __syncthreads();
+    }
+    const int info = s_state[3];
+    for (int t = tid; t < m; t += kDenseBlock)
+        sh.ev[t] = sh.d[t] * scale;
+    __syncthreads();
+    return info;
+}
+
+// TridiagQR::compute + matrix_QtHQ on the tridiagonal (d, e) with shift mu (thread 0).
+// Rotations go to rc/rs[0..m-1); (d, e) are replaced by Q'TQ.   UpperHessenbergQR.h:515-598, :627-693
+__device__ void tridiag_qr_step_scalar(double* d, double* e, int m, double mu, double* rc, double* rs, double* rdiag, double* rsupd)
+{
+    const int n1 = m - 1, n2 = m - 2;
+    // deflation of small sub-diagonal elements (:533-539)
+    for (int i = 0; i < n1; i++)
+        if (fabs(e[i]) <= kEps * (fabs(d[i]) + fabs(d[i + 1])))
+            e[i] = 0.0;
+    // R = T - mu I, only what the rotation generation needs (:542-598)
+    for (int i = 0; i < m; i++)
+        rdiag[i] = d[i] - mu;
+    for (int i = 0; i < n1; i++)
+        rsupd[i] = e[i];
+    for (int i = 0; i < n1; i++)
+    {
+        double r, c, s;
+        givens_rotation(rdiag[i], e[i], r, c, s);
+        rc[i] = c;
+        rs[i] = s;
+        rdiag[i] = r;
+        const double Tii1 = rsupd[i];
+        const double Ti1i1 = rdiag[i + 1];
+        rsupd[i] = c * Tii1 - s * Ti1i1;
+        rdiag[i + 1] = s * Tii1 + c * Ti1i1;
+        if (i < n2)
+            rsupd[i + 1] *= c;
+    }
+    // Q'TQ applied to T directly (:627-693).  dest(i+1,i) lives in e[i]; o' needs the ORIGINAL
+    // (deflated) T_subd(i+1), which is read before e[i+1] is overwritten.
+    double e_next_orig = (n1 > 0) ? e[0] : 0.0;
+    for (int i = 0; i < n1; i++)
+    {
+        const double c = rc[i], s = rs[i];
+        const double cs = c * s, c2 = c * c, s2 = s * s;
+        const double x = d[i], y = e[i], z = d[i + 1];
+        const double c2x = c2 * x, s2x = s2 * x, c2z = c2 * z, s2z = s2 * z;
+        const double csy2 = 2.0 * c * s * y;
+        d[i] = c2x - csy2 + s2z;
+        e[i] = cs * (x - z) + (c2 - s2) * y;
+        d[i + 1] = s2x + csy2 + c2z;
+        (void) e_next_orig;
+        if (i < n2)
+        {
+            const double ci1 = rc[i + 1], si1 = rs[i + 1];
+            const double tsub = e[i + 1];      // m_T_subd[i+1] (still original here)
+            const double o = -s * tsub;        // o'
+            e[i + 1] = tsub * c;               // w' = dest(i+2,i+1) *= c
+            e[i] = ci1 * e[i] - si1 * o;       // y''
+        }
+    }
+    for (int i = 0; i < n1; i++)
+        if (fabs(e[i]) <= kEps * (fabs(d[i]) + fabs(d[i + 1])))
+            e[i] = 0.0;
+}
+
+// Y <- Y Q for the rotation sequence rc/rs (UpperHessenbergQR.h:383-417), row-parallel.
+__device__ void apply_yq_block(double* Y, int m, const double* rc, const double* rs)
+{
+    for (int t = threadIdx.x; t < m; t += kDenseBlock)
+    {
+        double yi = Y[t];
+        for (int i = 0; i < m - 1; i++)
+        {
+            const double c = rc[i], s = rs[i];
+            const double yi1 = Y[t + (i + 1) * m];
+            Y[t + i * m] = c * yi - s * yi1;
+            yi = s * yi + c * yi1;
+        }
+        Y[t + (m - 1) * m] = yi;
+    }
+}
+
+__global__ void __launch_bounds__(kDenseBlock)
+    sym_restart_kernel(double* H, int m, int nev, const FacCtl* ctl, double beta_override, int use_override, int selection, double tol, double* ritz_val,
+                       double* ritz_est, double* ritz_vec, int* ritz_conv, double* Q, SymRestartOut* out, int do_restart)
+{
+    extern __shared__ double smem[];
+    TriShared sh = carve(smem, m);
+    __shared__ double s_hd[kMaxNcv], s_he[kMaxNcv];
+    __shared__ int s_k, s_nconv, s_go;
+    const int tid = threadIdx.x;
+    for (int t = tid; t < m; t += kDenseBlock)
+    {
+        s_hd[t] = H[t + (int64_t) t * m];
+        if (t < m - 1)
+            s_he[t] = H[(t + 1) + (int64_t) t * m];
+    }
+    __syncthreads();
+
+    // ---- retrieve_ritzpair (HermEigsBase.h:205-224) ----
+    const int info = tridiag_eigen_block(s_hd, s_he, m, sh);
+    if (tid == 0)
+    {
+        for (int i = 0; i < m; i++)
+            sh.aux[i] = sort_key_real(selection, sh.ev[i]);
+        argsort_keys(sh.aux, sh.idx, m);
+        if (selection == SB200_BOTH_ENDS)  // SelectionRule.h:272-284
+        {
+            int* tmp = reinterpret_cast<int*>(sh.rc);
+            for (int i = 0; i < m; i++)
+                tmp[i] = sh.idx[i];
+            for (int i = 0; i < m; i++)
+                sh.idx[i] = (i % 2 == 0) ? tmp[i / 2] : tmp[m - 1 - i / 2];
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < m; t += kDenseBlock)
+    {
+        const int id = sh.idx[t];
+        const double rv = sh.ev[id];
+        const double re = sh.Z[(m - 1) + id * m];
+        ritz_val[t] = rv;
+        ritz_est[t] = re;
+        sh.d[t] = rv;   // keep sorted Ritz values / estimates for the scalar logic below
+        sh.e[t] = re;
+    }
+    for (int t = tid; t < m * nev; t += kDenseBlock)
+    {
+        const int r = t % m, c = t / m;
+        ritz_vec[t] = sh.Z[r + sh.idx[c] * m];
+    }
+    __syncthreads();
+
+    if (tid == 0)
+    {
+        // ---- num_converged (HermEigsBase.h:158-175) ----
+        const double beta = use_override ? beta_override : ctl->beta;
+        const double eps23 = 3.666852862501036e-11;  // eps^(2/3)
+        int nconv = 0;
+        for (int i = 0; i < nev; i++)
+        {
+            const double thresh = tol * fmax(fabs(sh.d[i]), eps23);
+            const double resid = fabs(sh.e[i]) * beta;
+            const int cv = resid < thresh;
+            ritz_conv[i] = cv;
+            nconv += cv;
+        }
+        // ---- nev_adjusted (HermEigsBase.h:178-202) ----
+        int nev_new = nev;
+        for (int i = nev; i < m; i++)
+            if (fabs(sh.e[i]) < kNear0)
+                nev_new++;
+        nev_new += min(nconv, (m - nev_new) / 2);
+        if (nev_new == 1 && m >= 6)
+            nev_new = m / 2;
+        else if (nev_new == 1 && m > 2)
+            nev_new = 2;
+        if (nev_new > m - 1)
+            nev_new = m - 1;
+        s_k = nev_new;
+        s_nconv = nconv;
+        s_go = (do_restart && nconv < nev && info == 0 && nev_new < m) ? 1 : 0;
+        out->nconv = nconv;
+        out->k = nev_new;
+        out->info = info;
+    }
+    __syncthreads();
+    if (!s_go)
+        return;
+
+    // ---- shift loop of restart() (HermEigsBase.h:112-147) ----
+    const int k = s_k;
+    const int nshift = m - k;
+    double* shifts = sh.ev;  // reuse
+    if (tid == 0)
+    {
+        // shifts = ritz_val.tail(nshift) sorted by |.| descending (:118-121)
+        for (int i = 0; i < nshift; i++)
+            sh.aux[i] = -fabs(sh.d[k + i]);
+        argsort_keys(sh.aux, sh.idx, nshift);
+        for (int i = 0; i < nshift; i++)
+            shifts[i] = sh.d[k + sh.idx[i]];
+    }
+    // Q = I in the (now free) Z buffer; working tridiagonal back to (s_hd, s_he)
+    for (int t = tid; t < m * m; t += kDenseBlock)
+        sh.Z[t] = ((t % m) == (t / m)) ? 1.0 : 0.0;
+    __syncthreads();
+    for (int ish = 0; ish < nshift; ish++)
+    {
+        if (tid == 0)
+            tridiag_qr_step_scalar(s_hd, s_he, m, shifts[ish], sh.rc, sh.rs, sh.d, sh.e);
+        __syncthreads();
+        apply_yq_block(sh.Z, m, sh.rc, sh.rs);
+        __syncthreads();
+    }
+    // write back Q and the (untrimmed) tridiagonal H
+    for (int t = tid; t < m * m; t += kDenseBlock)
+    {
+        Q[t] = sh.Z[t];
+        const int r = t % m, c = t / m;
+        double h = 0.0;
+        if (r == c)
+            h = s_hd[r];
+        else if (r == c + 1)
+            h = s_he[c];
+        else if (c == r + 1)
+            h = s_he[r];
+        H[t] = h;
+    }
+}
+
+__global__ void __launch_bounds__(kDenseBlock) tridiag_eigen_kernel(const double* H, int m, double* evals, double* evecs, int* info)
+{
+    extern __shared__ double smem[];
+    TriShared sh = carve(smem, m);
+    __shared__ double s_hd[kMaxNcv], s_he[kMaxNcv];
+    for (int t = threadIdx.x; t < m; t += kDenseBlock)
+    {
+        s_hd[t] = H[t + (int64_t) t * m];
+        if (t < m - 1)
+            s_he[t] = H[(t + 1) + (int64_t) t * m];
+    }
+    __syncthreads();
+    const int rc = tridiag_eigen_block(s_hd, s_he, m, sh);
+    for (int t = threadIdx.x; t < m; t += kDenseBlock)
+        evals[t] = sh.ev[t];
+    for (int t = threadIdx.x; t < m * m; t += kDenseBlock)
+        evecs[t] = sh.Z[t];
+    if (threadIdx.x == 0)
+        *info = rc;
+}
+
+__global__ void __launch_bounds__(kDenseBlock) tridiag_qr_kernel(const double* H, int m, double shift, double* QtHQ, double* Q)
+{
+    extern __shared__ double smem[];
+    TriShared sh = carve(smem, m);
+    __shared__ double s_hd[kMaxNcv], s_he[kMaxNcv];
+    for (int t = threadIdx.x; t < m; t += kDenseBlock)
+    {
+        s_hd[t] = H[t + (int64_t) t * m];
+        if (t < m - 1)
+            s_he[t] = H[(t + 1) + (int64_t) t * m];
+    }
+    for (int t = threadIdx.x; t < m * m; t += kDenseBlock)
+        sh.Z[t] = ((t % m) == (t / m)) ? 1.0 : 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        tridiag_qr_step_scalar(s_hd, s_he, m, shift, sh.rc, sh.rs, sh.d, sh.e);
+    __syncthreads();
+    apply_yq_block(sh.Z, m, sh.rc, sh.rs);
+    __syncthreads();
+    for (int t = threadIdx.x; t < m * m; t += kDenseBlock)
+    {
+        Q[t] = sh.Z[t];
+        const int r = t % m, c = t / m;
+        double h = 0.0;
+        if (r == c)
+            h = s_hd[r];
+        else if (r == c + 1)
+            h = s_he[c];
+        else if (c == r + 1)
+            h = s_he[r];
+        QtHQ[t] = h;
+    }
+}
+
+void ensure_smem(const void* fn, size_t bytes)
+{
+    if (bytes > 48 * 1024)
+        SB200_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes));
+}
+
+}  // namespace
+
+void launch_sym_restart(double* H, int m, int nev, const FacCtl* ctl, int selection, double tol, double* ritz_val, double* ritz_est, double* ritz_vec,
+                        int* ritz_conv, double* Q, SymRestartOut* out, int do_restart, cudaStream_t stream)
+{
+    SB200_REQUIRE(m >= 2 && m <= kMaxNcv, SB200_INVALID_ARGUMENT, "ncv out of range for the device restart kernel");
+    const size_t smem = tri_smem_bytes(m);
+    ensure_smem((const void*) sym_restart_kernel, smem);
+    sym_restart_kernel<<<1, kDenseBlock, smem, stream>>>(H, m, nev, ctl, 0.0, 0, selection, tol, ritz_val, ritz_est, ritz_vec, ritz_conv, Q, out, do_restart);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+// test hook: beta passed by value instead of through a control block
+void launch_sym_restart_beta(double* H, int m, int nev, double beta, int selection, double tol, double* ritz_val, double* ritz_est, double* ritz_vec,
+                             int* ritz_conv, double* Q, SymRestartOut* out, cudaStream_t stream)
+{
+    SB200_REQUIRE(m >= 2 && m <= kMaxNcv, SB200_INVALID_ARGUMENT, "ncv out of range for the device restart kernel");
+    const size_t smem = tri_smem_bytes(m);
+    ensure_smem((const void*) sym_restart_kernel, smem);
+    sym_restart_kernel<<<1, kDenseBlock, smem, stream>>>(H, m, nev, nullptr, beta, 1, selection, tol, ritz_val, ritz_est, ritz_vec, ritz_conv, Q, out, 1);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_tridiag_eigen(const double* H, int m, double* evals, double* evecs, int* info, cudaStream_t stream)
+{
+    SB200_REQUIRE(m >= 1 && m <= kMaxNcv, SB200_INVALID_ARGUMENT, "matrix order out of range");
+    const size_t smem = tri_smem_bytes(m);
+    ensure_smem((const void*) tridiag_eigen_kernel, smem);
+    tridiag_eigen_kernel<<<1, kDenseBlock, smem, stream>>>(H, m, evals, evecs, info);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_tridiag_qr(const double* H, int m, double shift, double* QtHQ, double* Q, cudaStream_t stream)
+{
+    SB200_REQUIRE(m >= 2 && m <= kMaxNcv, SB200_INVALID_ARGUMENT, "matrix order out of range");
+    const size_t smem = tri_smem_bytes(m);
+    ensure_smem((const void*) tridiag_qr_kernel, smem);
+    tridiag_qr_kernel<<<1, kDenseBlock, smem, stream>>>(H, m, shift, QtHQ, Q);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace sb200

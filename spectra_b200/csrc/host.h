@@ -1,0 +1,44 @@
+// Host-side objects behind the C ABI handles.
+#pragma once
+
+#include <memory>
+
+#include "kernels.h"
+
+struct sb200_comm
+{
+    int rank = 0, nranks = 1;
+    void* nccl = nullptr;  // ncclComm_t
+};
+
+namespace sb200 {
+
+// ---- NCCL, loaded lazily with dlopen so that single-GPU use has no NCCL dependency ----
+void nccl_unique_id(void* id128);
+void nccl_comm_init(sb200_comm* c, const void* id128);
+void nccl_comm_destroy(sb200_comm* c);
+// in-place sum / max all-reduce of `count` doubles, all-gather of `count` doubles per rank
+void nccl_allreduce_sum(sb200_comm* c, double* buf, size_t count, cudaStream_t s);
+void nccl_allreduce_max(sb200_comm* c, double* buf, size_t count, cudaStream_t s);
+void nccl_allgather(sb200_comm* c, const double* send, double* recv, size_t count_per_rank, cudaStream_t s);
+
+}  // namespace sb200
+
+// Device-resident operator: full CSR rows [row0, row0+nrows) of an n x n matrix.
+struct sb200_op
+{
+    sb200::DeviceCsr A;
+    sb200::SpmvPlan plan;
+    sb200_comm* comm = nullptr;
+    cudaStream_t stream = nullptr;
+    int64_t slab = 0;                 // rows per rank (ceil(n / nranks)); nrows <= slab
+    sb200::DevBuf<double> x_full;     // n_pad = slab * nranks entries (sharded), else n
+    sb200::DevBuf<double> y_loc;      // host-pointer perform_op staging
+    sb200::DevBuf<double> x_stage;    // slab-sized send buffer for the all-gather
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool symmetric_hint = false;      // created through a SYM mode
+
+    int nranks() const { return comm ? comm->nranks : 1; }
+    int rank() const { return comm ? comm->rank : 0; }
+    ~sb200_op();
+};

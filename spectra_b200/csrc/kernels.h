@@ -1,0 +1,136 @@
+// Host-side launch interface of the sm_100a kernels (implemented in spmv.cu, panel.cu,
+// vecops.cu, csr_build.cu, dense_sym.cu, dense_gen.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace sb200 {
+
+constexpr int kPanelMaxCols = 64;   // widest Krylov panel one fused pass handles
+constexpr int kRedStride = 128;     // slots per CTA in the reduction scratch
+constexpr int kRedNrm = 64;         // red[kRedNrm] = ||f||^2 of the last panel pass
+
+// Device-resident control block of one running Lanczos/Arnoldi factorisation.  All data-dependent
+// scalars of the inner loop live here so that kernels chain on the stream without host round trips.
+struct FacCtl
+{
+    // ---- status block (first 64 bytes; the host reads exactly this part after a decide kernel) ----
+    double beta;                  // ||f||                                   (Arnoldi.h:61 m_beta)
+    double ortho_err;             // max |V^T f|                              (Lanczos.h:153)
+    double hnorm;                 // ||h|| of the Arnoldi step                (Arnoldi.h:257)
+    double hsub;                  // H(i, i-1) of the step being built (beta, or 0 after a restart)
+    int i;                        // column being built
+    int count;                    // correction passes done in this step      (Lanczos.h:155)
+    int need_corr;                // another correction pass is required      (Lanczos.h:156)
+    int f_zeroed;                 // beta < eps*sqrt(n): f forced to zero     (Lanczos.h:163-168)
+    int dgks_skip;                // Arnoldi: beta > 0.717 ||h||, no re-orth  (Arnoldi.h:257)
+    int pad[3];
+    // ---- reduction outputs / coefficients -------------------------------------------------------
+    double red_a[8];              // SpMV-epilogue reduction: [0] = <v_i, w>  (Lanczos.h:142)
+    double c[kRedStride];         // coefficients applied by the next correction pass  (Vf, Lanczos.h:152)
+    double red[kRedStride];       // output of the last panel reduction: [0..j) = V^T f, [kRedNrm] = ||f||^2
+};
+constexpr size_t kFacCtlStatusBytes = 64;
+
+// Reduction scratch shared by all kernels of one solver (one stream => no overlap).
+struct RedScratch
+{
+    double* partials;       // max_grid * kRedStride doubles
+    unsigned int* ticket;   // zero-initialised
+    int max_grid;
+};
+
+// ---- CSR build (csr_build.cu) -----------------------------------------------------------------
+struct DeviceCsr
+{
+    int64_t n = 0;        // global order
+    int64_t row0 = 0;     // first local row
+    int64_t nrows = 0;    // local rows
+    int64_t nnz = 0;      // local nnz
+    DevBuf<int> rowptr;   // nrows + 1
+    DevBuf<int> col;      // nnz (global column ids)
+    DevBuf<double> val;   // nnz
+};
+// Builds the full CSR (columns ascending in each row, duplicates summed) from host compressed
+// arrays.  mode/order as in sb200_matrix_mode / sb200_storage_order.  Keeps rows [row0,row0+nrows).
+void build_device_csr(int64_t n, const void* outer, bool outer64, const int32_t* inner, const double* values, int order, int mode, int64_t row0, int64_t nrows,
+                      cudaStream_t stream, DeviceCsr& out);
+void upload_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64_t* rowptr_local, const int32_t* col, const double* values, cudaStream_t stream,
+                     DeviceCsr& out);
+
+// ---- SpMV (spmv.cu) -----------------------------------------------------------------------------
+struct SpmvPlan
+{
+    int lanes = 8;  // lanes per row
+    int grid = 0;
+};
+SpmvPlan make_spmv_plan(const DeviceCsr& A);
+// y = A x   (x: full vector of A.n entries, y: A.nrows)
+void launch_spmv(const DeviceCsr& A, const SpmvPlan& plan, const double* x, double* y, cudaStream_t stream);
+// Fused Lanczos/Arnoldi step head (K-A):  V[:,i] = f_loc/beta;  w = (A x)/beta - hsub*V[:,i-1]
+// (sym only);  red_a[0] = <V[:,i], w> (sym only).   x is the full (un-normalised) residual.
+// V points at column 0 (ld = ldv).  Reads i, beta, hsub from ctl.
+// Also performs the step bookkeeping (block 0): ctl->i = i, count = 0, hsub = restarted ? 0 : beta,
+// H(i,i-1) = hsub (and H(i-1,i) when symmetric)      (Lanczos.h:127-128, Arnoldi.h:239).
+void launch_spmv_step(const DeviceCsr& A, const SpmvPlan& plan, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
+                      double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream);
+
+// ---- fused Krylov-panel passes (panel.cu) ---------------------------------------------------------
+enum PanelMode
+{
+    PANEL_DOT = 0,   // red = V^T x, ||x||^2          (x unchanged)
+    PANEL_FORM = 1,  // f = w - alpha*V[:,j-1]; red = V^T f, ||f||^2       (Lanczos.h:145-152)
+    PANEL_CORR = 2,  // f = x - V c;            red = V^T f, ||f||^2       (Lanczos.h:171-179, Arnoldi.h:254)
+};
+// j = number of panel columns (<= kPanelMaxCols) is read from ctl->i + 1 when j_host < 0.
+// x: input vector (w for FORM, f or w for CORR/DOT), f_out: output residual (may alias x).
+// coef: device pointer to the coefficients (CORR) or to alpha (FORM).
+void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out,
+                       const RedScratch& rs, cudaStream_t stream);
+
+// Decide kernels: consume ctl->red after a panel pass (and after the all-reduce when sharded).
+//  first = 1: after the FORM pass of a Lanczos step; first = 0: after a CORR pass (also applies
+//  the H update of Lanczos.h:172-175 with the coefficients that were just used).
+void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int first, cudaStream_t stream);
+// Arnoldi flavours (Arnoldi.h:242-290): stage 0 = after h = V^T w (copies h into H(:,i) and c),
+// stage 1 = after f = w - V h (DGKS test), stage 2 = after a correction pass.
+void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream);
+
+// ---- restart GEMM (panel.cu) ------------------------------------------------------------------------
+// Vout[:, c] = sum_j V[:, j] * Q[j, c]  for c < kk  (Q: m x m column-major on device, ldq = m).
+// In place when Vout == V.  When f != nullptr also  f = f*Q(m-1,kk-2) + Vout[:,kk-1]*H(kk-1,kk-2)
+// and red_out[0] = ||f||^2   (Arnoldi.h:320-340).
+void launch_compress(const double* V, int64_t ldv, int64_t nrows, int m, const double* Q, int kk, double* Vout, int64_t ldo, double* f, const double* H,
+                     double* red_out, const RedScratch& rs, cudaStream_t stream);
+
+// ---- BLAS-1 helpers for init / expand_basis (vecops.cu) ------------------------------------------------
+enum VecReduceOp
+{
+    VR_SUMSQ = 0,
+    VR_DOT = 1,
+    VR_MAXABS = 2
+};
+void launch_vec_reduce(int op, const double* x, const double* y, int64_t n, double* out, const RedScratch& rs, cudaStream_t stream);
+void launch_vec_scale(const double* x, double s, int divide, double* y, int64_t n, cudaStream_t stream);          // y = x*s or x/s
+void launch_vec_axpy(const double* w, const double* v, double a, double* f, int64_t n, cudaStream_t stream);      // f = w - a*v
+void launch_set_beta(FacCtl* ctl, const double* red_slot, int take_sqrt, cudaStream_t stream);                      // ctl->beta = (sqrt) *red_slot
+void launch_set_scalar(double* dst, double v, cudaStream_t stream);
+
+// ---- small dense restart kernels (dense_sym.cu) ----------------------------------------------------------
+struct SymRestartOut
+{
+    int nconv;
+    int k;      // nev_adjusted
+    int info;   // 0 ok, 1 TridiagEigen failed
+    int pad;
+};
+// retrieve_ritzpair + num_converged (+ nev_adjusted + shifted-QR chain when not converged), all on
+// the device in one single-CTA kernel.  H (m x m) is replaced by Q'HQ, Q receives the accumulated
+// rotations.  ritz_vec: m x nev.  do_restart = 0 skips the QR chain (used after the last step).
+void launch_sym_restart(double* H, int m, int nev, const FacCtl* ctl, int selection, double tol, double* ritz_val, double* ritz_est, double* ritz_vec,
+                        int* ritz_conv, double* Q, SymRestartOut* out, int do_restart, cudaStream_t stream);
+// standalone pieces for the unit tier
+void launch_tridiag_eigen(const double* H, int m, double* evals, double* evecs, int* info, cudaStream_t stream);
+void launch_tridiag_qr(const double* H, int m, double shift, double* QtHQ, double* Q, cudaStream_t stream);
+
+}  // namespace sb200

@@ -1,0 +1,139 @@
+// Device-resident operator behind sb200_op (replaces Sparse{Sym,Gen}MatProd).
+#include <cstring>
+#include <mutex>
+
+#include "host.h"
+
+namespace sb200 {
+
+int g_profiling_level = 0;
+
+static thread_local std::string t_last_error;
+void set_last_error(const std::string& msg) { t_last_error = msg; }
+const char* last_error_cstr() { return t_last_error.c_str(); }
+
+const DeviceInfo& device_info()
+{
+    static DeviceInfo info;
+    static std::once_flag once;
+    static std::string err;
+    std::call_once(once, [] {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+        {
+            err = std::string("no CUDA device available: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+            cudaGetLastError();
+            return;
+        }
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess)
+        {
+            err = "cudaGetDevice failed";
+            return;
+        }
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess)
+        {
+            err = "cudaGetDeviceProperties failed";
+            return;
+        }
+        info.device = dev;
+        info.sm_count = p.multiProcessorCount;
+        info.cc_major = p.major;
+        info.cc_minor = p.minor;
+        info.total_mem = p.totalGlobalMem;
+        info.l2_bytes = p.l2CacheSize;
+        if (p.major < 10)
+            err = "this library contains sm_100a code only; device compute capability is " + std::to_string(p.major) + "." + std::to_string(p.minor);
+    });
+    if (!err.empty())
+        throw Error(SB200_CUDA, err);
+    return info;
+}
+
+}  // namespace sb200
+
+using namespace sb200;
+
+sb200_op::~sb200_op()
+{
+    if (ev0)
+        cudaEventDestroy(ev0);
+    if (ev1)
+        cudaEventDestroy(ev1);
+    if (stream)
+        cudaStreamDestroy(stream);
+}
+
+namespace sb200 {
+
+static void finish_op(sb200_op* op)
+{
+    op->plan = make_spmv_plan(op->A);
+    const int P = op->nranks();
+    op->slab = (op->A.n + P - 1) / P;
+    if (P > 1)
+    {
+        op->x_full.alloc((size_t) op->slab * P);
+        op->x_full.zero(op->stream);
+        op->x_stage.alloc((size_t) op->slab);
+        op->x_stage.zero(op->stream);
+    }
+    SB200_CUDA_CHECK(cudaEventCreate(&op->ev0));
+    SB200_CUDA_CHECK(cudaEventCreate(&op->ev1));
+    SB200_CUDA_CHECK(cudaStreamSynchronize(op->stream));
+}
+
+sb200_op* op_create_sparse(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values, int storage_order, int matrix_mode,
+                           sb200_comm* comm)
+{
+    device_info();
+    SB200_REQUIRE(outer && (inner || true), SB200_INVALID_ARGUMENT, "null matrix arrays");
+    std::unique_ptr<sb200_op> op(new sb200_op());
+    op->comm = comm;
+    SB200_CUDA_CHECK(cudaStreamCreateWithFlags(&op->stream, cudaStreamNonBlocking));
+    const int P = op->nranks();
+    const int64_t slab = (n + P - 1) / P;
+    const int64_t row0 = std::min<int64_t>(n, slab * op->rank());
+    const int64_t nrows = std::max<int64_t>(0, std::min<int64_t>(slab, n - row0));
+    build_device_csr(n, outer, outer_is_64 != 0, inner, values, storage_order, matrix_mode, row0, nrows, op->stream, op->A);
+    op->symmetric_hint = (matrix_mode != SB200_GENERAL);
+    finish_op(op.get());
+    return op.release();
+}
+
+sb200_op* op_create_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64_t* rowptr_local, const int32_t* col, const double* values, sb200_comm* comm)
+{
+    device_info();
+    std::unique_ptr<sb200_op> op(new sb200_op());
+    op->comm = comm;
+    SB200_CUDA_CHECK(cudaStreamCreateWithFlags(&op->stream, cudaStreamNonBlocking));
+    const int P = op->nranks();
+    const int64_t slab = (n + P - 1) / P;
+    SB200_REQUIRE(row0 == std::min<int64_t>(n, slab * op->rank()) && nrows == std::max<int64_t>(0, std::min<int64_t>(slab, n - row0)), SB200_INVALID_ARGUMENT,
+                  "row slab must be rows [rank*ceil(n/P), ...) of the matrix");
+    upload_csr_slab(n, row0, nrows, rowptr_local, col, values, op->stream, op->A);
+    finish_op(op.get());
+    return op.release();
+}
+
+// y_dev (local rows) = A * x_dev (full vector).  Sharded: x_dev must already hold all n entries.
+void op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev) { launch_spmv(op->A, op->plan, x_dev, y_dev, op->stream); }
+
+// Host-pointer perform_op (SparseSymMatProd.h:83-88): H2D x, kernel, D2H y (local rows).
+void op_perform_op_host(sb200_op* op, const double* x_host, double* y_host)
+{
+    const int64_t n = op->A.n;
+    if (op->x_full.n < (size_t) n)
+        op->x_full.alloc((size_t) n);
+    if (op->y_loc.n < (size_t) std::max<int64_t>(op->A.nrows, 1))
+        op->y_loc.alloc((size_t) std::max<int64_t>(op->A.nrows, 1));
+    SB200_CUDA_CHECK(cudaMemcpyAsync(op->x_full.get(), x_host, sizeof(double) * n, cudaMemcpyHostToDevice, op->stream));
+    op_spmv_device(op, op->x_full.get(), op->y_loc.get());
+    if (op->A.nrows > 0)
+        SB200_CUDA_CHECK(cudaMemcpyAsync(y_host, op->y_loc.get(), sizeof(double) * op->A.nrows, cudaMemcpyDeviceToHost, op->stream));
+    SB200_CUDA_CHECK(cudaStreamSynchronize(op->stream));
+}
+
+}  // namespace sb200

@@ -1,0 +1,429 @@
+// Fused Krylov-panel kernels for sm_100a (K3/K4/K5/K6 of SURVEY.md §2.1).
+//
+// One pass over the tall-skinny basis V (nrows x j, column-major, ld = ldv) does what the
+// reference does in two or three BLAS-2 calls:
+//   PANEL_FORM : f = w - alpha v_i; c = V^T f; ||f||^2          Lanczos.h:145-152
+//   PANEL_CORR : f = x - V c;       c' = V^T f; ||f||^2         Lanczos.h:171-179, Arnoldi.h:254-262,281-287
+//   PANEL_DOT  : c = V^T x; ||x||^2                             ArnoldiOp.h:144-148 (adjoint_product)
+// f_new[r] only needs row r of V, so the pass is row-local and V is read exactly once:
+// algorithmic bytes = 8*nrows*j (V) + 8*nrows (x) + 8*nrows (f)   (SURVEY §8d "fused K4+K3").
+//
+// Mapping: a CTA of 8 warps is split into NG column groups (16 columns each) x RS = 8/NG row
+// slices.  A lane owns 2 consecutive rows (one 128-bit load per column), keeps its 16x2 tile of V
+// in registers, and (CORR) exchanges the 16-column partial dot products through shared memory so
+// that every group sees the complete f_new of its rows.  Per-thread accumulators are combined by a
+// shuffle tree, then across row slices and CTAs in a fixed order (bit-reproducible run to run).
+// V is streamed with L1::no_allocate / L2 evict_first; x, f stay L2-resident between kernels.
+//
+// The restart GEMM  V[:, :kk] <- V Q  (Arnoldi.h:320-340) and  X = V S  (HermEigsBase.h:467) use
+// one thread per row with the whole row of V in registers and Q staged in shared memory.
+#include "kernels.h"
+
+namespace sb200 {
+
+namespace {
+
+constexpr int kPanelBlock = 256;
+constexpr int kColsPerGroup = 16;
+
+template <int NG, int MODE>
+__global__ void __launch_bounds__(kPanelBlock, 2)
+    panel_kernel(const double* __restrict__ V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* __restrict__ coef,
+                 double* red_out, double* partials, unsigned int* ticket)
+{
+    constexpr int RS = 8 / NG;        // row slices
+    constexpr int RPI = RS * 64;      // rows per CTA iteration
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = warp % NG, rs = warp / NG;
+    const uint64_t pol = l2_policy_evict_first();
+
+    __shared__ double s_c[kPanelMaxCols];
+    __shared__ double2 s_p[2][NG][RS * 32];     // CORR: per-group partial  sum_k c_k V[r,k]
+    __shared__ double s_part[RS][kPanelMaxCols + 1];
+    __shared__ double s_out[kRedStride];
+
+    if (MODE == PANEL_CORR)
+    {
+        if (threadIdx.x < kPanelMaxCols)
+            s_c[threadIdx.x] = (threadIdx.x < j) ? coef[threadIdx.x] : 0.0;
+        __syncthreads();
+    }
+    const double alpha = (MODE == PANEL_FORM) ? coef[0] : 0.0;
+
+    double acc[kColsPerGroup];
+#pragma unroll
+    for (int kk = 0; kk < kColsPerGroup; kk++)
+        acc[kk] = 0.0;
+    double nrm = 0.0;
+    const double* cg = s_c + g * kColsPerGroup;  // CORR coefficients of this group (shared-memory broadcast)
+
+    const double* __restrict__ vi = V + (int64_t) (j - 1) * ldv;  // FORM: v_i is the last panel column
+    int buf = 0;
+    for (int64_t base = (int64_t) blockIdx.x * RPI; base < nrows; base += (int64_t) gridDim.x * RPI)
+    {
+        const int64_t r0 = base + rs * 64 + lane * 2;
+        const bool valid = r0 < ldv;  // padding rows [nrows, ldv) hold zeros
+        double2 v[kColsPerGroup];
+#pragma unroll
+        for (int kk = 0; kk < kColsPerGroup; kk++)
+        {
+            const int k = g * kColsPerGroup + kk;
+            v[kk] = (valid && k < j) ? ld_stream_f64x2(V + r0 + (int64_t) k * ldv, pol) : make_double2(0.0, 0.0);
+        }
+        double2 xv = valid ? *reinterpret_cast<const double2*>(x + r0) : make_double2(0.0, 0.0);
+        double2 fn;
+        if (MODE == PANEL_FORM)
+        {
+            const double2 vv = valid ? *reinterpret_cast<const double2*>(vi + r0) : make_double2(0.0, 0.0);
+            fn.x = xv.x - alpha * vv.x;  // f = w - H(i,i) v_i   (Lanczos.h:145)
+            fn.y = xv.y - alpha * vv.y;
+        }
+        else if (MODE == PANEL_CORR)
+        {
+            double2 p = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int kk = 0; kk < kColsPerGroup; kk++)
+            {
+                p.x = fma(cg[kk], v[kk].x, p.x);
+                p.y = fma(cg[kk], v[kk].y, p.y);
+            }
+            if (NG > 1)
+            {
+                s_p[buf][g][rs * 32 + lane] = p;
+                __syncthreads();
+                p = s_p[buf][0][rs * 32 + lane];
+#pragma unroll
+                for (int q = 1; q < NG; q++)
+                {
+                    const double2 t = s_p[buf][q][rs * 32 + lane];
+                    p.x += t.x;
+                    p.y += t.y;
+                }
+                buf ^= 1;
+            }
+            fn.x = xv.x - p.x;  // f -= V * Vf   (Lanczos.h:171)
+            fn.y = xv.y - p.y;
+        }
+        else
+        {
+            fn = xv;
+        }
+        if (MODE != PANEL_DOT && g == 0 && valid)
+            *reinterpret_cast<double2*>(f_out + r0) = fn;
+#pragma unroll
+        for (int kk = 0; kk < kColsPerGroup; kk++)
+        {
+            acc[kk] = fma(v[kk].x, fn.x, acc[kk]);
+            acc[kk] = fma(v[kk].y, fn.y, acc[kk]);
+        }
+        if (g == 0)
+        {
+            nrm = fma(fn.x, fn.x, nrm);
+            nrm = fma(fn.y, fn.y, nrm);
+        }
+    }
+
+    // ---- CTA-level combine (fixed order) ----
+#pragma unroll
+    for (int kk = 0; kk < kColsPerGroup; kk++)
+    {
+        const double s = warp_sum(acc[kk]);
+        if (lane == 0)
+            s_part[rs][g * kColsPerGroup + kk] = s;
+    }
+    if (g == 0)
+    {
+        const double s = warp_sum(nrm);
+        if (lane == 0)
+            s_part[rs][kPanelMaxCols] = s;
+    }
+    if (NG < 4)
+    {
+        // columns of the unused groups
+        for (int t = threadIdx.x; t < RS * kPanelMaxCols; t += kPanelBlock)
+        {
+            const int c = t % kPanelMaxCols, r = t / kPanelMaxCols;
+            if (c >= NG * kColsPerGroup)
+                s_part[r][c] = 0.0;
+        }
+    }
+    __syncthreads();
+    double cta = 0.0;
+    const int t = threadIdx.x;
+    if (t <= j)
+    {
+        const int src = (t == j) ? kPanelMaxCols : t;  // slot j carries ||f||^2
+#pragma unroll
+        for (int q = 0; q < RS; q++)
+            cta += s_part[q][src];
+    }
+    if (grid_reduce_fixed_order<kPanelBlock>(cta, j + 1, partials, ticket, s_out))
+    {
+        if (t < j)
+            red_out[t] = s_out[t];
+        if (t == 0)
+            red_out[kRedNrm] = s_out[j];
+    }
+}
+
+template <int MODE>
+void launch_panel_mode(const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out, int grid,
+                       const RedScratch& rs, cudaStream_t stream)
+{
+    if (j <= 16)
+        panel_kernel<1, MODE><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket);
+    else if (j <= 32)
+        panel_kernel<2, MODE><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket);
+    else
+        panel_kernel<4, MODE><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket);
+}
+
+// ---------------------------------------------------------------------------------------------
+// decide kernels (single warp)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ double panel_max_abs(const double* red, int j, int lane)
+{
+    double mx = 0.0;
+    for (int k = lane; k < j; k += 32)
+        mx = fmax(mx, fabs(red[k]));
+    return warp_max(mx);
+}
+
+__global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int first)
+{
+    const int lane = threadIdx.x;
+    const int i = ctl->i, j = i + 1;
+    int count = ctl->count;
+    if (lane == 0)
+    {
+        if (first)
+        {
+            H[i + (int64_t) i * m] = ctl->red_a[0];  // H(i,i) = <v, w>   (Lanczos.h:142)
+        }
+        else
+        {
+            // h <- h + Vf   (Lanczos.h:172-175) with the coefficients the pass just applied
+            const double hu = H[(i - 1) + (int64_t) i * m] + ctl->c[i - 1];
+            H[(i - 1) + (int64_t) i * m] = hu;
+            H[i + (int64_t) (i - 1) * m] = hu;
+            H[i + (int64_t) i * m] += ctl->c[i];
+        }
+    }
+    if (!first)
+        count += 1;
+    const double ortho_err = panel_max_abs(ctl->red, j, lane);
+    double beta = sqrt(ctl->red[kRedNrm]);  // ||f||   (Lanczos.h:146,177)
+    __syncwarp();
+    for (int k = lane; k < j; k += 32)
+        ctl->c[k] = ctl->red[k];
+    int need = (count < 5) && (ortho_err > kEps * beta);  // Lanczos.h:156
+    int zeroed = 0;
+    if (need && beta < beta_thresh)  // Lanczos.h:163-168
+    {
+        zeroed = 1;
+        beta = 0.0;
+        need = 0;
+    }
+    if (lane == 0)
+    {
+        ctl->beta = beta;
+        ctl->ortho_err = ortho_err;
+        ctl->count = count;
+        ctl->need_corr = need;
+        ctl->f_zeroed = zeroed;
+    }
+}
+
+__global__ void arnoldi_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int stage)
+{
+    const int lane = threadIdx.x;
+    const int i = ctl->i, j = i + 1;
+    if (stage == 0)
+    {
+        // h = V^T w -> H(0:i, i)  (Arnoldi.h:249-251); it is also the coefficient vector of f = w - V h
+        for (int k = lane; k < j; k += 32)
+        {
+            const double h = ctl->red[k];
+            H[k + (int64_t) i * m] = h;
+            ctl->c[k] = h;
+        }
+        if (lane == 0)
+        {
+            double s = 0.0;
+            for (int k = 0; k < j; k++)
+                s += ctl->red[k] * ctl->red[k];
+            ctl->hnorm = sqrt(s);  // ||h||   (Arnoldi.h:257)
+        }
+        return;
+    }
+    int count = ctl->count;
+    if (stage == 2)
+    {
+        for (int k = lane; k < j; k += 32)
+            H[k + (int64_t) i * m] += ctl->c[k];  // h += Vf   (Arnoldi.h:283)
+        count += 1;
+    }
+    double beta = sqrt(ctl->red[kRedNrm]);
+    const double ortho_err = panel_max_abs(ctl->red, j, lane);
+    __syncwarp();
+    int need, skip = 0, zeroed = 0;
+    if (stage == 1 && beta > 0.717 * ctl->hnorm)  // DGKS   (Arnoldi.h:257)
+    {
+        skip = 1;
+        need = 0;
+    }
+    else
+    {
+        for (int k = lane; k < j; k += 32)
+            ctl->c[k] = ctl->red[k];
+        need = (count < 5) && (ortho_err > kEps * beta);  // Arnoldi.h:266
+        if (need && beta < beta_thresh)                    // Arnoldi.h:273-278
+        {
+            zeroed = 1;
+            beta = 0.0;
+            need = 0;
+        }
+    }
+    if (lane == 0)
+    {
+        ctl->beta = beta;
+        ctl->ortho_err = ortho_err;
+        ctl->count = count;
+        ctl->need_corr = need;
+        ctl->f_zeroed = zeroed;
+        ctl->dgks_skip = skip;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Restart GEMM: one thread per row, row of V in registers (MP = padded panel width), Q in smem.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGemmBlock = 128;
+
+template <int MP>
+__global__ void __launch_bounds__(kGemmBlock)
+    compress_kernel(const double* V, int64_t ldv, int64_t nrows, int m, const double* __restrict__ Q, int kk, double* Vout, int64_t ldo, double* f,
+                    const double* __restrict__ H, double* red_out, double* partials, unsigned int* ticket)
+{
+    extern __shared__ double s_q[];  // MP x kk, column-major, rows >= m zero
+    for (int t = threadIdx.x; t < MP * kk; t += kGemmBlock)
+    {
+        const int r = t % MP, c = t / MP;
+        s_q[t] = (r < m) ? Q[r + (int64_t) c * m] : 0.0;
+    }
+    __syncthreads();
+    const uint64_t pol = l2_policy_evict_first();
+    double fq = 0.0, fh = 0.0;
+    if (f)
+    {
+        fq = Q[(m - 1) + (int64_t) (kk - 2) * m];   // Q(m-1, k-1)
+        fh = H[(kk - 1) + (int64_t) (kk - 2) * m];  // H(k, k-1)
+    }
+    double nrm = 0.0;
+    for (int64_t r = (int64_t) blockIdx.x * kGemmBlock + threadIdx.x; r < nrows; r += (int64_t) gridDim.x * kGemmBlock)
+    {
+        double v[MP];
+#pragma unroll
+        for (int jx = 0; jx < MP; jx++)
+            v[jx] = (jx < m) ? ld_stream_f64(V + r + (int64_t) jx * ldv, pol) : 0.0;
+        double last = 0.0;
+        for (int c = 0; c < kk; c++)
+        {
+            const double* q = s_q + c * MP;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int jx = 0; jx < MP; jx += 2)
+            {
+                const double2 qq = *reinterpret_cast<const double2*>(q + jx);
+                s0 = fma(v[jx], qq.x, s0);
+                s1 = fma(v[jx + 1], qq.y, s1);
+            }
+            last = s0 + s1;
+            Vout[r + (int64_t) c * ldo] = last;
+        }
+        if (f)
+        {
+            const double fn = f[r] * fq + last * fh;  // Arnoldi.h:337
+            f[r] = fn;
+            nrm = fma(fn, fn, nrm);
+        }
+    }
+    if (f)
+    {
+        __shared__ double s_w[kGemmBlock / 32];
+        nrm = warp_sum(nrm);
+        if ((threadIdx.x & 31) == 0)
+            s_w[threadIdx.x >> 5] = nrm;
+        __syncthreads();
+        double cta = 0.0;
+        if (threadIdx.x == 0)
+            for (int q = 0; q < kGemmBlock / 32; q++)
+                cta += s_w[q];
+        grid_reduce_fixed_order<kGemmBlock>(cta, 1, partials, ticket, red_out);
+    }
+}
+
+}  // namespace
+
+void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out,
+                       const RedScratch& rs, cudaStream_t stream)
+{
+    SB200_REQUIRE(j >= 1 && j <= kPanelMaxCols, SB200_INVALID_ARGUMENT, "panel width must be in [1, 64]");
+    const int sms = device_info().sm_count;
+    const int ng = j <= 16 ? 1 : (j <= 32 ? 2 : 4);
+    const int64_t rpi = (8 / ng) * 64;
+    const int64_t need = (nrows + rpi - 1) / rpi;
+    const int grid = (int) std::max<int64_t>(1, std::min<int64_t>(need, (int64_t) sms * 2));
+    SB200_REQUIRE(grid <= rs.max_grid, SB200_LOGIC, "panel: reduction scratch too small");
+    switch (mode)
+    {
+        case PANEL_DOT: launch_panel_mode<PANEL_DOT>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, stream); break;
+        case PANEL_FORM: launch_panel_mode<PANEL_FORM>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, stream); break;
+        case PANEL_CORR: launch_panel_mode<PANEL_CORR>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, stream); break;
+        default: throw Error(SB200_LOGIC, "bad panel mode");
+    }
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int first, cudaStream_t stream)
+{
+    lanczos_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, first);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream)
+{
+    arnoldi_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_compress(const double* V, int64_t ldv, int64_t nrows, int m, const double* Q, int kk, double* Vout, int64_t ldo, double* f, const double* H,
+                     double* red_out, const RedScratch& rs, cudaStream_t stream)
+{
+    SB200_REQUIRE(m >= 1 && m <= kPanelMaxCols && kk >= 1 && kk <= m, SB200_INVALID_ARGUMENT, "compress: bad dimensions");
+    SB200_REQUIRE(!f || kk >= 2, SB200_INVALID_ARGUMENT, "compress: residual update needs k >= 1");
+    const int sms = device_info().sm_count;
+    const int64_t need = (nrows + kGemmBlock - 1) / kGemmBlock;
+    const int grid = (int) std::max<int64_t>(1, std::min<int64_t>(need, (int64_t) sms * 3));
+    SB200_REQUIRE(grid <= rs.max_grid, SB200_LOGIC, "compress: reduction scratch too small");
+    const int mp = m <= 16 ? 16 : (m <= 32 ? 32 : (m <= 48 ? 48 : 64));
+    const size_t smem = (size_t) mp * kk * sizeof(double);
+    switch (mp)
+    {
+        case 16: compress_kernel<16><<<grid, kGemmBlock, smem, stream>>>(V, ldv, nrows, m, Q, kk, Vout, ldo, f, H, red_out, rs.partials, rs.ticket); break;
+        case 32: compress_kernel<32><<<grid, kGemmBlock, smem, stream>>>(V, ldv, nrows, m, Q, kk, Vout, ldo, f, H, red_out, rs.partials, rs.ticket); break;
+        case 48: compress_kernel<48><<<grid, kGemmBlock, smem, stream>>>(V, ldv, nrows, m, Q, kk, Vout, ldo, f, H, red_out, rs.partials, rs.ticket); break;
+        default: compress_kernel<64><<<grid, kGemmBlock, smem, stream>>>(V, ldv, nrows, m, Q, kk, Vout, ldo, f, H, red_out, rs.partials, rs.ticket); break;
+    }
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace sb200

@@ -1,0 +1,153 @@
+// BLAS-1 helpers used outside the steady-state loop: Arnoldi::init (Arnoldi.h:136-195),
+// expand_basis (Arnoldi.h:66-115) and the rare restart tests of Lanczos.h:99-121.
+// Reductions are bit-reproducible (fixed combine order).
+#include "kernels.h"
+
+namespace sb200 {
+
+namespace {
+
+constexpr int kVecBlock = 256;
+
+template <int OP>
+__global__ void __launch_bounds__(kVecBlock) vec_reduce_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n, double* out,
+                                                               double* partials, unsigned int* ticket)
+{
+    double acc = 0.0;
+    for (int64_t i = (int64_t) blockIdx.x * kVecBlock + threadIdx.x; i < n; i += (int64_t) gridDim.x * kVecBlock)
+    {
+        const double a = x[i];
+        if (OP == VR_SUMSQ)
+            acc = fma(a, a, acc);
+        else if (OP == VR_DOT)
+            acc = fma(a, y[i], acc);
+        else
+            acc = fmax(acc, fabs(a));
+    }
+    __shared__ double s_w[kVecBlock / 32];
+    if (OP == VR_MAXABS)
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            acc = fmax(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+    }
+    else
+        acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0)
+        s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    double cta = 0.0;
+    if (threadIdx.x == 0)
+    {
+        for (int q = 0; q < kVecBlock / 32; q++)
+            cta = (OP == VR_MAXABS) ? fmax(cta, s_w[q]) : cta + s_w[q];
+    }
+    if (OP == VR_MAXABS)
+    {
+        // max is order independent: reuse the ticket scheme with a max combine
+        __shared__ bool s_last;
+        if (threadIdx.x == 0)
+        {
+            partials[(size_t) blockIdx.x * 128] = cta;
+            __threadfence();
+            const unsigned int t = atomicAdd(ticket, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last)
+        {
+            __threadfence();
+            double mx = 0.0;
+            for (int b = threadIdx.x; b < (int) gridDim.x; b += kVecBlock)
+                mx = fmax(mx, ld_cg_f64(partials + (size_t) b * 128));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0)
+                s_w[threadIdx.x >> 5] = mx;
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                double r = 0.0;
+                for (int q = 0; q < kVecBlock / 32; q++)
+                    r = fmax(r, s_w[q]);
+                out[0] = r;
+                *ticket = 0u;
+            }
+        }
+    }
+    else
+    {
+        grid_reduce_fixed_order<kVecBlock>(cta, 1, partials, ticket, out);
+    }
+}
+
+__global__ void vec_scale_kernel(const double* __restrict__ x, double s, int divide, double* __restrict__ y, int64_t n)
+{
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+        y[i] = divide ? x[i] / s : x[i] * s;
+}
+
+__global__ void vec_axpy_kernel(const double* __restrict__ w, const double* __restrict__ v, double a, double* __restrict__ f, int64_t n)
+{
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+        f[i] = w[i] - v[i] * a;  // f = w - v * H(0,0)   (Arnoldi.h:177)
+}
+
+__global__ void set_beta_kernel(FacCtl* ctl, const double* slot, int take_sqrt)
+{
+    const double v = *slot;
+    ctl->beta = take_sqrt ? sqrt(v) : v;
+}
+
+__global__ void set_scalar_kernel(double* dst, double v) { *dst = v; }
+
+int vec_grid(int64_t n)
+{
+    const int sms = device_info().sm_count;
+    const int64_t need = (n + kVecBlock - 1) / kVecBlock;
+    return (int) std::max<int64_t>(1, std::min<int64_t>(need, (int64_t) sms * 4));
+}
+
+}  // namespace
+
+void launch_vec_reduce(int op, const double* x, const double* y, int64_t n, double* out, const RedScratch& rs, cudaStream_t stream)
+{
+    const int grid = vec_grid(n);
+    SB200_REQUIRE(grid <= rs.max_grid, SB200_LOGIC, "vec_reduce: reduction scratch too small");
+    switch (op)
+    {
+        case VR_SUMSQ: vec_reduce_kernel<VR_SUMSQ><<<grid, kVecBlock, 0, stream>>>(x, y, n, out, rs.partials, rs.ticket); break;
+        case VR_DOT: vec_reduce_kernel<VR_DOT><<<grid, kVecBlock, 0, stream>>>(x, y, n, out, rs.partials, rs.ticket); break;
+        case VR_MAXABS: vec_reduce_kernel<VR_MAXABS><<<grid, kVecBlock, 0, stream>>>(x, y, n, out, rs.partials, rs.ticket); break;
+        default: throw Error(SB200_LOGIC, "bad reduce op");
+    }
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_vec_scale(const double* x, double s, int divide, double* y, int64_t n, cudaStream_t stream)
+{
+    vec_scale_kernel<<<vec_grid(n), kVecBlock, 0, stream>>>(x, s, divide, y, n);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_vec_axpy(const double* w, const double* v, double a, double* f, int64_t n, cudaStream_t stream)
+{
+    vec_axpy_kernel<<<vec_grid(n), kVecBlock, 0, stream>>>(w, v, a, f, n);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_set_beta(FacCtl* ctl, const double* red_slot, int take_sqrt, cudaStream_t stream)
+{
+    set_beta_kernel<<<1, 1, 0, stream>>>(ctl, red_slot, take_sqrt);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_set_scalar(double* dst, double v, cudaStream_t stream)
+{
+    set_scalar_kernel<<<1, 1, 0, stream>>>(dst, v);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace sb200

@@ -1,0 +1,329 @@
+"""GPU parity tests of the symmetric path, mirroring the three tiers of the reference's tests
+(operator / factorisation / solver) through the C ABI, checked against the CPU oracle on the same
+inputs.  Tolerances: operator 1e-13 relative (summation order differs), factorisation and dense
+kernels 1e-12 (test/Arnoldi.cpp, test/QR.cpp, test/Eigen.cpp), solver ||AU-UD||_inf <= 1e-9
+(test/SymEigs.cpp:60-64) and eigenvalues within 1e-10 relative of the oracle (north star)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle as O
+from helpers import EXAMPLE2, cycle_laplacian, dense_as_csc, sym_full
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------- operator tier
+@pytest.mark.parametrize("fmt", ["csc", "csr"])
+@pytest.mark.parametrize("uplo", ["lower", "upper"])
+def test_sparse_sym_mat_prod(gpu, fmt, uplo):
+    # test/SparseSymMatProd.cpp:37-54
+    rng = np.random.default_rng(0)
+    A = O.gen_sparse_data(100, 0.1)
+    A = A.tocsc() if fmt == "csc" else A.tocsr()
+    op = gpu.SparseSymMatProd(A, uplo=uplo)
+    ref = O.Csr.from_scipy(A, uplo)
+    assert op.rows() == 100 and op.cols() == 100
+    for _ in range(3):
+        x = rng.standard_normal(100)
+        y, y0 = op.perform_op(x), ref.spmv(x)
+        assert np.abs(y - y0).max() <= 1e-13 * max(1.0, np.abs(y0).max())
+    M = rng.standard_normal((100, 7))
+    Y0 = ref.to_scipy() @ M
+    assert np.abs(op @ M - Y0).max() <= 1e-13 * np.abs(Y0).max()
+    assert op(45, 22) == A[45, 22]  # the STORED coefficient (SparseSymMatProd.h:101-104)
+
+
+@pytest.mark.parametrize("fmt", ["csc", "csr"])
+def test_sparse_gen_mat_prod(gpu, fmt):
+    # test/SparseGenMatProd.cpp:37-53
+    rng = np.random.default_rng(1)
+    A = O.gen_sparse_data(100, 0.1)
+    A = A.tocsc() if fmt == "csc" else A.tocsr()
+    op = gpu.SparseGenMatProd(A)
+    x = rng.standard_normal(100)
+    y0 = A @ x
+    assert np.abs(op.perform_op(x) - y0).max() <= 1e-13 * np.abs(y0).max()
+    assert op(45, 22) == A[45, 22]
+
+
+def test_operator_edge_cases(gpu):
+    # empty matrix, empty rows, a long row, int64 outer index
+    Z = gpu.SparseSymMatProd(sp.csc_matrix((50, 50)))
+    assert np.array_equal(Z.perform_op(np.ones(50)), np.zeros(50))
+    rng = np.random.default_rng(2)
+    n = 3000
+    A = sp.random(n, n, density=0.002, random_state=3, format="csr")
+    A = A.tolil()
+    A[7, :] = rng.standard_normal(n)  # dense row
+    A[11, :] = 0
+    A = A.tocsr()
+    x = rng.standard_normal(n)
+    op = gpu.SparseGenMatProd((n, A.indptr.astype(np.int64), A.indices, A.data, "row"))
+    y0 = A @ x
+    assert np.abs(op.perform_op(x) - y0).max() <= 1e-12 * np.abs(y0).max()
+
+
+def test_spmv_large_synthetic(gpu):
+    from spectra_b200 import synth
+
+    n = 200000
+    rp, ci, v = synth.csr(n, 20, 0, True)
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    op = gpu.SparseGenMatProd.from_csr_slab(n, 0, rp, ci, v)
+    x = O.simple_random(7, n)
+    y0 = A @ x
+    assert np.abs(op.perform_op(x) - y0).max() <= 1e-13 * np.abs(y0).max()
+    # the symmetric wrapper (lower triangle, CSC storage == CSR arrays of a symmetric matrix) gives the same operator
+    op2 = gpu.SparseSymMatProd((n, rp, ci, v, "col"))
+    assert op2.nnz == op.nnz
+    assert np.abs(op2.perform_op(x) - y0).max() <= 1e-13 * np.abs(y0).max()
+
+
+# ---------------------------------------------------------------- dense-kernel tier
+def _rand_tridiag(rng, m):
+    d, e = rng.standard_normal(m), rng.standard_normal(m - 1)
+    return np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+
+
+@pytest.mark.parametrize("m", [2, 3, 6, 20, 50, 60, 64, 100])
+def test_tridiag_eigen_device(gpu, m):
+    # test/Eigen.cpp:68-86 tolerance 1e-12; bitwise-close to the oracle
+    rng = np.random.default_rng(m)
+    T = _rand_tridiag(rng, m)
+    ev, Z = gpu.dense.tridiag_eigen(T)
+    ev0, Z0 = O.tridiag_eigen(T)
+    assert np.abs(T @ Z - Z * ev).max() <= 1e-12 * m
+    assert np.abs(Z.T @ Z - np.eye(m)).max() <= 1e-12 * m
+    assert np.abs(ev - ev0).max() <= 1e-12 * max(1, np.abs(ev0).max())
+    # zero matrix early exit (TridiagEigen.h:142-150)
+    ev, Z = gpu.dense.tridiag_eigen(np.zeros((m, m)))
+    assert np.array_equal(ev, np.zeros(m)) and np.array_equal(Z, np.eye(m))
+
+
+@pytest.mark.parametrize("m", [2, 3, 6, 20, 60, 64])
+def test_tridiag_qr_device(gpu, m):
+    # test/QR.cpp:115-129 tolerance 1e-12
+    rng = np.random.default_rng(100 + m)
+    T = _rand_tridiag(rng, m)
+    for shift in (0.0, 0.37, float(np.linalg.eigvalsh(T)[0])):
+        D, Q = gpu.dense.shifted_qr(T, shift, "tridiag")
+        R0, D0, Q0 = O.shifted_qr(T, shift, "tridiag")
+        assert np.abs(Q.T @ Q - np.eye(m)).max() <= 1e-12
+        assert np.abs(Q - Q0).max() <= 1e-12 and np.abs(D - D0).max() <= 1e-12 * max(1, np.abs(D0).max())
+        assert np.abs(np.tril(Q.T @ (T - shift * np.eye(m)), -1)).max() <= 1e-12 * m
+
+
+@pytest.mark.parametrize("rule", [O.LargestMagn, O.LargestAlge, O.SmallestMagn, O.SmallestAlge, O.BothEnds])
+def test_sym_restart_step_device(gpu, rule):
+    # one HermEigsBase restart-prepare step vs the oracle on a Lanczos H of the n=1000 fixture
+    A = O.gen_sparse_data(1000, 0.01)
+    fz = O.factorize(O.Csr.from_scipy(A, "lower"), 50)
+    H, beta = fz["H"], fz["beta"]
+    a = gpu.dense.sym_restart(H, beta, 20, rule, 1e-10)
+    b = O.sym_restart_prepare(H, beta, 20, rule, 1e-10)
+    assert a["nconv"] == b["nconv"] and a["k"] == b["k"]
+    assert np.abs(a["ritz_val"] - b["ritz_val"]).max() <= 1e-12 * np.abs(b["ritz_val"]).max()
+    assert np.abs(np.abs(a["ritz_est"]) - np.abs(b["ritz_est"])).max() <= 1e-10
+    assert np.array_equal(a["conv"], b["conv"])
+    assert np.abs(a["Q"] - b["Q"]).max() <= 1e-9
+    assert np.abs(a["H"] - b["H"]).max() <= 1e-9 * np.abs(b["H"]).max()
+    Q = a["Q"]
+    assert np.abs(Q.T @ Q - np.eye(50)).max() <= 1e-12
+
+
+# ---------------------------------------------------------------- factorisation tier
+@pytest.mark.parametrize("n,m", [(10, 6), (100, 20), (1000, 50), (5000, 64)])
+def test_lanczos_factorization(gpu, n, m):
+    # test/Arnoldi.cpp:19-85: init, factorize_from(1, m/2), factorize_from(m/2, m); AV - VH = f e', V'V = I (1e-12)
+    if n <= 1000:
+        A = O.gen_sparse_data(n, {10: 0.5, 100: 0.1, 1000: 0.01}[n])
+    else:
+        A = sp.random(n, n, density=0.002, random_state=5, format="csc")
+    Af = sym_full(A)
+    op = gpu.SparseSymMatProd(A)
+    eigs = gpu.SymEigsSolver(op, min(3, n - 1), m)
+    v0 = O.simple_random(3, n)
+    eigs.init(v0)
+    eigs.factorize_from(1, m // 2)
+    eigs.factorize_from(m // 2, m)
+    fz = eigs.factorization()
+    V, H, f = fz["V"], fz["H"], fz["f"]
+    E = Af @ V - V @ H
+    E[:, -1] -= f
+    scale = max(1.0, np.abs(H).max())
+    assert np.abs(E).max() <= 1e-12 * scale
+    assert np.abs(V.T @ V - np.eye(m)).max() <= 1e-12
+    assert abs(np.linalg.norm(f) - fz["beta"]) <= 1e-12 * scale
+    assert np.abs(H - H.T).max() == 0.0 and np.abs(np.triu(H, 2)).max() == 0.0
+    # step-for-step agreement with the oracle's H
+    ref = O.factorize(O.Csr.from_scipy(A, "lower"), m, v0=v0)
+    assert np.abs(H - ref["H"]).max() <= 1e-9 * scale
+    with pytest.raises(gpu.InvalidArgument):
+        eigs2 = gpu.SymEigsSolver(op, min(3, n - 1), m)
+        eigs2.init(v0)
+        eigs2.factorize_from(5, m)  # from_k > current dimension (Lanczos.h:70-75)
+
+
+# ---------------------------------------------------------------- solver tier
+SYM_CASES = [(10, 0.5, 3, 6), (100, 0.1, 10, 20), (1000, 0.01, 20, 50)]
+RULES = ["LargestMagn", "LargestAlge", "SmallestMagn", "SmallestAlge", "BothEnds"]
+
+
+@pytest.mark.parametrize("n,prob,k,m", SYM_CASES)
+@pytest.mark.parametrize("rule", RULES)
+def test_sym_eigs_sparse_reference_cases(gpu, n, prob, k, m, rule):
+    # test/SymEigs.cpp:44-65,133-167
+    if n == 1000 and rule == "SmallestMagn":
+        pytest.skip("~23k matvecs; interior selection is covered at n <= 100")
+    A = O.gen_sparse_data(n, prob)
+    Af = sym_full(A)
+    op = gpu.SparseSymMatProd(A)
+    eigs = gpu.SymEigsSolver(op, k, m)
+    eigs.init()
+    nconv = eigs.compute(gpu.SortRule[rule])
+    assert eigs.info() == gpu.CompInfo.Successful and nconv == k
+    evals, evecs = eigs.eigenvalues(), eigs.eigenvectors()
+    assert np.abs(Af @ evecs - evecs * evals).max() <= 1e-9
+    ref = O.sym_eigs(O.Csr.from_scipy(A, "lower"), k, m, int(gpu.SortRule[rule]))
+    assert ref.info == O.Successful
+    assert np.abs(evals - ref.eigenvalues).max() <= 1e-10 * np.abs(ref.eigenvalues).max()
+    # the restart sequence is the same algorithm: iteration / operation counts agree (allow rounding-induced drift)
+    assert abs(eigs.num_operations() - ref.nops) <= max(3 * m, ref.nops // 5)
+    st = eigs.stats()
+    assert st["kernel_launches"] > 0 and st["spmv_launches"] == eigs.num_operations()
+
+
+def test_readme_diag_kat(gpu):
+    # SymEigsSolver.h:99-126 with the operator given as a sparse diagonal matrix
+    A = sp.diags(np.arange(1.0, 11.0)).tocsc()
+    eigs = gpu.SymEigsSolver(gpu.SparseSymMatProd(A), 3, 6)
+    eigs.init()
+    eigs.compute(gpu.SortRule.LargestAlge)
+    assert eigs.info() == gpu.CompInfo.Successful
+    assert np.allclose(eigs.eigenvalues(), [10, 9, 8], atol=1e-10)
+    assert eigs.num_iterations() > 0 and eigs.num_operations() > 0
+
+
+@pytest.mark.parametrize("k,m", [(3, 6), (5, 12), (6, 12)])
+def test_example1_cycle_laplacian(gpu, k, m):
+    # test/Example1.cpp (issue #144): repeated eigenvalues exercise expand_basis; tol = 1e-15
+    M = cycle_laplacian(20)
+    true = np.linalg.eigvalsh(M)
+    eigs = gpu.SymEigsSolver(gpu.SparseSymMatProd(dense_as_csc(M)), k, m)
+    eigs.init()
+    eigs.compute(gpu.SortRule.LargestMagn, 1000, 1e-15, gpu.SortRule.SmallestAlge)
+    assert eigs.info() == gpu.CompInfo.Successful
+    evals, U = eigs.eigenvalues(), eigs.eigenvectors()
+    assert np.abs(M @ U - U * evals).max() <= 1e-9
+    assert np.abs(true[-k:] - evals).max() <= 1e-9
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_example2_near_rank_one(gpu, idx):
+    # test/Example2.cpp (issue #159): beta < sqrt(eps) restart heuristic, n = 5, nev = 1, ncv = 3
+    M = EXAMPLE2[idx]
+    eigs = gpu.SymEigsSolver(gpu.SparseSymMatProd(dense_as_csc(M)), 1, 3)
+    eigs.init()
+    eigs.compute(gpu.SortRule.LargestMagn)
+    assert eigs.info() == gpu.CompInfo.Successful
+    evals, U = eigs.eigenvalues(), eigs.eigenvectors()
+    assert np.abs(M @ U - U * evals).max() <= 1e-8
+    assert abs(np.linalg.eigvalsh(M)[-1] - evals[0]) <= 1e-8
+
+
+def test_example4_zero_matrix_and_null_init(gpu):
+    # test/Example4.cpp:59-92
+    n = 100
+    rng = np.random.default_rng(123)
+    v0 = rng.uniform(-1, 1, n)
+    eigs = gpu.SymEigsSolver(gpu.SparseSymMatProd(sp.csc_matrix((n, n))), 3, 6)
+    eigs.init(v0)
+    eigs.compute(gpu.SortRule.LargestAlge)
+    assert eigs.info() == gpu.CompInfo.Successful and np.abs(eigs.eigenvalues()).max() <= 1e-8
+    U = rng.uniform(-1, 1, (n, n))
+    w, Q = np.linalg.eigh(U + U.T)
+    w[-1] = 0.0
+    A = (Q * w) @ Q.T
+    A = (A + A.T) / 2
+    eigs = gpu.SymEigsSolver(gpu.SparseSymMatProd(dense_as_csc(A)), 3, 6)
+    eigs.init(Q[:, -1].copy())
+    eigs.compute(gpu.SortRule.LargestAlge)
+    assert eigs.info() == gpu.CompInfo.Successful
+    true = np.sort(np.linalg.eigvalsh(A))
+    evals, Uv = eigs.eigenvalues(), eigs.eigenvectors()
+    assert np.abs(true[-3:][::-1] - evals).max() <= 1e-8
+    assert np.abs(A @ Uv - Uv * evals).max() <= 1e-8
+
+
+def test_argument_and_error_behaviour(gpu):
+    op = gpu.SparseSymMatProd(sp.identity(10, format="csc"))
+    for nev, ncv in [(0, 5), (10, 12), (3, 3), (3, 11)]:
+        with pytest.raises(gpu.InvalidArgument):  # HermEigsBase.h:267-271
+            gpu.SymEigsSolver(op, nev, ncv)
+    eigs = gpu.SymEigsSolver(op, 3, 6)
+    with pytest.raises(gpu.InvalidArgument):  # Arnoldi.h:147-148
+        eigs.init(np.zeros(10))
+    with pytest.raises(gpu.LogicError):
+        gpu.SymEigsSolver(op, 3, 6).compute()
+    eigs.init()
+    with pytest.raises(gpu.InvalidArgument):  # HermEigsBase.h:231-233
+        eigs.compute(gpu.SortRule.LargestAlge, 1000, 1e-10, gpu.SortRule.BothEnds)
+    eigs = gpu.SymEigsSolver(op, 3, 6)
+    eigs.init()
+    with pytest.raises(gpu.InvalidArgument):  # SelectionRule.h:261-262
+        eigs.compute(gpu.SortRule.LargestReal)
+    # not converging: maxit = 1 on a hard problem -> NotConverging, min(nev, nconv) returned (HermEigsBase.h:387-389)
+    A = O.gen_sparse_data(1000, 0.01)
+    e2 = gpu.SymEigsSolver(gpu.SparseSymMatProd(A), 20, 50)
+    e2.init()
+    nconv = e2.compute(gpu.SortRule.SmallestMagn, 1)
+    ref = O.sym_eigs(O.Csr.from_scipy(A, "lower"), 20, 50, O.SmallestMagn, 1)
+    assert e2.info() == gpu.CompInfo.NotConverging and nconv == ref.nconv
+    assert e2.num_iterations() == ref.niter and e2.num_operations() == ref.nops
+    assert len(e2.eigenvalues()) == nconv
+
+
+def test_sym_eigs_medium_vs_oracle_and_arpack(gpu):
+    # synthetic G_sym at a size the oracle finishes in seconds
+    from scipy.sparse.linalg import eigsh
+    from spectra_b200 import synth
+
+    n = 50000
+    rp, ci, v = synth.csr(n, 20, 0, True)
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    op = gpu.SparseSymMatProd((n, rp, ci, v, "col"))
+    eigs = gpu.SymEigsSolver(op, 20, 60)
+    eigs.init()
+    nconv = eigs.compute(gpu.SortRule.LargestAlge)
+    assert eigs.info() == gpu.CompInfo.Successful and nconv == 20
+    evals, X = eigs.eigenvalues(), eigs.eigenvectors()
+    res = np.linalg.norm(A @ X - X * evals, axis=0) / np.abs(evals)
+    assert res.max() <= 1e-10
+    ref = O.sym_eigs(O.Csr.adopt(n, rp, ci, v), 20, 60, O.LargestAlge, want_vectors=False)
+    assert np.abs(evals - ref.eigenvalues).max() <= 1e-10 * np.abs(ref.eigenvalues).max()
+    w = eigsh(A, k=20, which="LA", ncv=60, tol=1e-12, return_eigenvectors=False)
+    assert np.abs(np.sort(evals) - np.sort(w)).max() <= 1e-10 * np.abs(w).max()
+
+
+def test_sym_eigs_full_size_properties(gpu):
+    # BASELINE config C2: n = 1e6, nnz/row = 20, k = 20, ncv = 60.  Size-independent properties only.
+    from spectra_b200 import synth
+
+    n = 1_000_000
+    rp, ci, v = synth.csr(n, 20, 0, True)
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    op = gpu.SparseGenMatProd.from_csr_slab(n, 0, rp, ci, v)
+    eigs = gpu.SymEigsSolver(op, 20, 60)
+    eigs.init()
+    nconv = eigs.compute(gpu.SortRule.LargestAlge)
+    assert eigs.info() == gpu.CompInfo.Successful and nconv == 20
+    evals, X = eigs.eigenvalues(), eigs.eigenvectors()
+    assert np.all(np.diff(evals) <= 0)  # sorted LargestAlge
+    res = np.linalg.norm(A @ X - X * evals, axis=0) / np.abs(evals)
+    assert res.max() <= 1e-10
+    assert np.abs(X.T @ X - np.eye(20)).max() <= 1e-10
+    # run-to-run bit reproducibility (fixed-order reductions)
+    eigs.init()
+    eigs.compute(gpu.SortRule.LargestAlge)
+    assert np.array_equal(evals, eigs.eigenvalues())
