@@ -1,0 +1,372 @@
+// Device-resident Krylov factorisation state shared by the Lanczos (solver_sym.cu) and Arnoldi
+// (solver_gen.cu) drivers: A V = V H + f e_k'.  Mirrors the members and the non-virtual parts of
+// LinAlg/Arnoldi.h (state :47-61, expand_basis :66-115, init :136-195, compress_V :320-340).
+#pragma once
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "host.h"
+
+namespace sb200 {
+
+// Util/SimpleRandom.h:30-123 (default residual and expand_basis vectors); host side, O(n) integers.
+struct SimpleRandom
+{
+    long m_rand;
+    explicit SimpleRandom(unsigned long init_seed)
+    {
+        const unsigned long m_max = 2147483647L;
+        m_rand = init_seed ? (long) (init_seed & m_max) : 1;
+    }
+    static long next_long_rand(long seed)
+    {
+        const unsigned int m_a = 16807;
+        const unsigned long m_max = 2147483647L;
+        unsigned long lo, hi;
+        lo = (unsigned long) m_a * (unsigned long) (seed & 0xFFFFUL);
+        hi = (unsigned long) m_a * (unsigned long) ((unsigned long) seed >> 16);
+        lo += (hi & 0x7FFF) << 16;
+        if (lo > m_max)
+        {
+            lo &= m_max;
+            ++lo;
+        }
+        lo += hi >> 15;
+        if (lo > m_max)
+        {
+            lo &= m_max;
+            ++lo;
+        }
+        return (long) lo;
+    }
+    double random()
+    {
+        m_rand = next_long_rand(m_rand);
+        return double(m_rand) / double(2147483647L) - 0.5;
+    }
+    void random_vec(double* v, int64_t len)
+    {
+        for (int64_t i = 0; i < len; i++)
+            v[i] = random();
+    }
+};
+
+void launch_trim_h(double* H, int m, int from_k, cudaStream_t s);
+
+struct FacBase
+{
+    sb200_op* op = nullptr;
+    int64_t n = 0, nloc = 0, ld = 0;
+    int nev = 0, m = 0;
+
+    DevBuf<double> V, f, w, t0, H, Q, S, X;
+    DevBuf<FacCtl> ctl;
+    DevBuf<double> partials;
+    DevBuf<unsigned int> ticket;
+    RedScratch rs;
+    PinnedBuf<char> hstat;   // status readback
+    PinnedBuf<double> hred;  // reduction readback (rare paths)
+
+    int64_t k = 0;  // current subspace dimension (m_k)
+    int64_t nmatop = 0, niter = 0;
+    int info = SB200_NOT_COMPUTED;
+    double h_beta = 0.0;
+    bool initialised = false;
+
+    Profiler prof;
+    sb200_stats stats;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+
+    cudaStream_t stream() const { return op->stream; }
+    int P() const { return op->nranks(); }
+
+    ~FacBase()
+    {
+        if (ev_begin)
+            cudaEventDestroy(ev_begin);
+        if (ev_end)
+            cudaEventDestroy(ev_end);
+    }
+
+    void alloc_common(sb200_op* op_, int64_t nev_, int64_t m_)
+    {
+        op = op_;
+        n = op->A.n;
+        nloc = op->A.nrows;
+        // leading dimension: multiple of 16 doubles (128 B) and at least the all-gather slab
+        ld = round_up(std::max<int64_t>(std::max<int64_t>(nloc, op->slab), 2), 16);
+        nev = (int) nev_;
+        m = (int) m_;
+        V.alloc((size_t) ld * m);
+        f.alloc((size_t) ld);
+        w.alloc((size_t) ld);
+        t0.alloc((size_t) std::max<int64_t>(ld, n));
+        H.alloc((size_t) m * m);
+        Q.alloc((size_t) m * m);
+        S.alloc((size_t) 2 * m * m);
+        ctl.alloc(1);
+        const int max_grid = device_info().sm_count * 16;
+        partials.alloc((size_t) max_grid * kRedStride);
+        ticket.alloc(1);
+        ticket.zero(op->stream);
+        rs.partials = partials.get();
+        rs.ticket = ticket.get();
+        rs.max_grid = max_grid;
+        hstat.alloc(256);
+        hred.alloc(kRedStride + 8);
+        SB200_CUDA_CHECK(cudaEventCreate(&ev_begin));
+        SB200_CUDA_CHECK(cudaEventCreate(&ev_end));
+        std::memset(&stats, 0, sizeof(stats));
+    }
+
+    // ---- small helpers -------------------------------------------------------------------------
+    const FacCtl* read_status()
+    {
+        SB200_CUDA_CHECK(cudaMemcpyAsync(hstat.get(), ctl.get(), kFacCtlStatusBytes, cudaMemcpyDeviceToHost, stream()));
+        SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+        return reinterpret_cast<const FacCtl*>(hstat.get());
+    }
+    void allreduce_sum(double* buf, size_t count)
+    {
+        if (P() > 1)
+        {
+            ScopedKernelTimer t(&prof, stream(), KC_COMM, 0);
+            nccl_allreduce_sum(op->comm, buf, count, stream());
+        }
+    }
+    void allreduce_max(double* buf, size_t count)
+    {
+        if (P() > 1)
+        {
+            ScopedKernelTimer t(&prof, stream(), KC_COMM, 0);
+            nccl_allreduce_max(op->comm, buf, count, stream());
+        }
+    }
+    // x_full <- all-gather of a local vector (sharded); returns the pointer the SpMV must read
+    const double* gather_full(const double* local)
+    {
+        if (P() == 1)
+            return local;
+        ScopedKernelTimer t(&prof, stream(), KC_COMM, 0);
+        // local vectors have ld >= slab entries allocated; padding rows are zero
+        nccl_allgather(op->comm, local, op->x_full.get(), (size_t) op->slab, stream());
+        return op->x_full.get();
+    }
+    double reduce_scalar(int opk, const double* x, const double* y)
+    {
+        double* slot = ctl.get()->red_a + 1;
+        {
+            ScopedKernelTimer t(&prof, stream(), KC_PANEL);
+            launch_vec_reduce(opk, x, y, nloc, slot, rs, stream());
+        }
+        if (opk == VR_MAXABS)
+            allreduce_max(slot, 1);
+        else
+            allreduce_sum(slot, 1);
+        SB200_CUDA_CHECK(cudaMemcpyAsync(hred.get(), slot, sizeof(double), cudaMemcpyDeviceToHost, stream()));
+        SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+        return hred.get()[0];
+    }
+    void set_beta_host(double b)
+    {
+        h_beta = b;
+        launch_set_scalar(&ctl.get()->beta, b, stream());
+        prof.launches++;
+    }
+    void spmv_plain(const double* xfull, double* y)
+    {
+        {
+            ScopedKernelTimer t(&prof, stream(), KC_SPMV);
+            launch_spmv(op->A, op->plan, xfull, y, stream());
+        }
+        stats.spmv_launches++;
+        nmatop++;
+    }
+    void spmv_step(int i, bool restarted, bool symmetric)
+    {
+        const double* xfull = gather_full(f.get());
+        {
+            ScopedKernelTimer t(&prof, stream(), KC_SPMV);
+            launch_spmv_step(op->A, op->plan, xfull, f.get(), V.get(), ld, w.get(), ctl.get(), H.get(), m, i, restarted ? 1 : 0, symmetric, rs, stream());
+        }
+        stats.spmv_launches++;
+        nmatop++;
+    }
+    void panel(int mode, int j, const double* x, double* fo, const double* coef)
+    {
+        stats.panel_launches++;
+        stats.panel_cols += j;
+        {
+            ScopedKernelTimer t(&prof, stream(), KC_PANEL);
+            launch_panel_pass(mode, V.get(), ld, nloc, j, x, fo, coef, ctl.get()->red, rs, stream());
+        }
+        allreduce_sum(ctl.get()->red, kRedNrm + 1);
+    }
+    // host copy of red[0..j) and red[kRedNrm]
+    void fetch_red(int j, double& ortho_err, double& nrm2)
+    {
+        SB200_CUDA_CHECK(cudaMemcpyAsync(hred.get(), ctl.get()->red, sizeof(double) * (kRedNrm + 1), cudaMemcpyDeviceToHost, stream()));
+        SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+        ortho_err = 0.0;
+        for (int q = 0; q < j; q++)
+            ortho_err = std::max(ortho_err, std::fabs(hred.get()[q]));
+        nrm2 = hred.get()[kRedNrm];
+    }
+
+    // ---- Arnoldi::expand_basis (Arnoldi.h:66-115), V = first i columns ----
+    void expand_basis(int i, int64_t seed)
+    {
+        stats.expand_calls++;
+        std::vector<double> rnd((size_t) n);
+        const int64_t row0 = op->A.row0;
+        for (int iter = 0; iter < 5; iter++)
+        {
+            SimpleRandom rng((unsigned long) (seed + 123 * iter));
+            rng.random_vec(rnd.data(), n);
+            if (iter == 0)
+            {
+                // the first try forces f into the range of A: f = A * rand
+                double* xfull = (P() > 1) ? op->x_full.get() : t0.get();
+                SB200_CUDA_CHECK(cudaMemcpyAsync(xfull, rnd.data(), sizeof(double) * n, cudaMemcpyHostToDevice, stream()));
+                spmv_plain(xfull, f.get());
+            }
+            else if (nloc > 0)
+            {
+                SB200_CUDA_CHECK(cudaMemcpyAsync(f.get(), rnd.data() + row0, sizeof(double) * nloc, cudaMemcpyHostToDevice, stream()));
+            }
+            // Vf = V^T f ; f -= V Vf ; fnorm ; Vf = V^T f   (:88-95) — the last three in one fused pass
+            panel(PANEL_DOT, i, f.get(), nullptr, nullptr);
+            SB200_CUDA_CHECK(cudaMemcpyAsync(ctl.get()->c, ctl.get()->red, sizeof(double) * i, cudaMemcpyDeviceToDevice, stream()));
+            panel(PANEL_CORR, i, f.get(), f.get(), ctl.get()->c);
+            double ortho_err, nrm2;
+            fetch_red(i, ortho_err, nrm2);
+            double fnorm = std::sqrt(nrm2);
+            int count = 0;
+            while (count < 3 && ortho_err >= kEps * fnorm)
+            {
+                SB200_CUDA_CHECK(cudaMemcpyAsync(ctl.get()->c, ctl.get()->red, sizeof(double) * i, cudaMemcpyDeviceToDevice, stream()));
+                panel(PANEL_CORR, i, f.get(), f.get(), ctl.get()->c);
+                fetch_red(i, ortho_err, nrm2);
+                fnorm = std::sqrt(nrm2);
+                count++;
+            }
+            set_beta_host(fnorm);
+            if (ortho_err < kEps * fnorm)
+                return;
+        }
+    }
+
+    // ---- Arnoldi::init (Arnoldi.h:136-195) ----
+    void init_factorization(const double* init_resid)
+    {
+        std::vector<double> gen;
+        if (!init_resid)
+        {
+            // HermEigsBase.h:337-342 / GenEigsBase.h:470-475: SimpleRandom<Scalar> rng(0); random_vec(n)
+            gen.resize((size_t) n);
+            SimpleRandom rng(0);
+            rng.random_vec(gen.data(), n);
+            init_resid = gen.data();
+        }
+        prof.reset();
+        std::memset(&stats, 0, sizeof(stats));
+        SB200_CUDA_CHECK(cudaEventRecord(ev_begin, stream()));
+        V.zero(stream());
+        f.zero(stream());
+        w.zero(stream());
+        t0.zero(stream());
+        H.zero(stream());
+        ctl.zero(stream());
+        nmatop = 0;
+        niter = 0;
+        k = 0;
+        info = SB200_NOT_COMPUTED;
+
+        const int64_t row0 = op->A.row0;
+        // full v0 on the device for the first product, local slice in t0
+        double* xfull = (P() > 1) ? op->x_full.get() : t0.get();
+        SB200_CUDA_CHECK(cudaMemcpyAsync(xfull, init_resid, sizeof(double) * n, cudaMemcpyHostToDevice, stream()));
+        if (P() > 1 && nloc > 0)
+            SB200_CUDA_CHECK(cudaMemcpyAsync(t0.get(), init_resid + row0, sizeof(double) * nloc, cudaMemcpyHostToDevice, stream()));
+        const double v0norm = std::sqrt(reduce_scalar(VR_SUMSQ, t0.get(), nullptr));
+        if (v0norm < kNear0)
+            throw Error(SB200_INVALID_ARGUMENT, "initial residual vector cannot be zero");
+        double* v = V.get();
+        spmv_plain(xfull, v);  // v = A * v0 (force v into the range of A)
+        const double vnorm = std::sqrt(reduce_scalar(VR_SUMSQ, v, nullptr));
+        if (vnorm < kNear0)
+            launch_vec_scale(t0.get(), v0norm, 1, v, nloc, stream());  // v = v0 / ||v0||   (:162-165)
+        else
+            launch_vec_scale(v, vnorm, 1, v, nloc, stream());  // v /= ||v||
+        prof.launches++;
+        const double* vfull = gather_full(v);
+        spmv_plain(vfull, w.get());  // w = A * v
+        const double h00 = reduce_scalar(VR_DOT, v, w.get());
+        launch_set_scalar(H.get(), h00, stream());
+        launch_vec_axpy(w.get(), v, h00, f.get(), nloc, stream());  // f = w - v * H(0,0)
+        prof.launches += 2;
+        const double fmax = reduce_scalar(VR_MAXABS, f.get(), nullptr);
+        if (fmax < kEps * std::fabs(h00))
+        {
+            f.zero(stream());
+            set_beta_host(0.0);
+        }
+        else
+        {
+            set_beta_host(std::sqrt(reduce_scalar(VR_SUMSQ, f.get(), nullptr)));
+        }
+        k = 1;
+        initialised = true;
+    }
+
+    // ---- Arnoldi::compress_V (Arnoldi.h:320-340) with the new subspace size knew ----
+    void compress_v(int knew)
+    {
+        stats.compress_launches++;
+        stats.compress_cols += knew + 1;
+        {
+            ScopedKernelTimer t(&prof, stream(), KC_COMPRESS);
+            launch_compress(V.get(), ld, nloc, m, Q.get(), knew + 1, V.get(), ld, f.get(), H.get(), ctl.get()->red_a + 2, rs, stream());
+        }
+        allreduce_sum(ctl.get()->red_a + 2, 1);
+        launch_set_beta(ctl.get(), ctl.get()->red_a + 2, 1, stream());
+        prof.launches++;
+        h_beta = read_status()->beta;
+        k = knew;
+    }
+
+    void finish_timing()
+    {
+        SB200_CUDA_CHECK(cudaEventRecord(ev_end, stream()));
+        SB200_CUDA_CHECK(cudaEventSynchronize(ev_end));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev_begin, ev_end);
+        stats.ms_total = ms;
+        stats.kernel_launches = prof.launches;
+        stats.ms_spmv = prof.ms[KC_SPMV];
+        stats.ms_panel = prof.ms[KC_PANEL];
+        stats.ms_compress = prof.ms[KC_COMPRESS];
+        stats.ms_small = prof.ms[KC_SMALL];
+        stats.ms_comm = prof.ms[KC_COMM];
+    }
+
+    void get_factorization(double* Vh, double* Hh, double* fh, double* beta, int64_t* kk)
+    {
+        cudaStream_t st = stream();
+        if (Vh && nloc > 0)
+            SB200_CUDA_CHECK(cudaMemcpy2DAsync(Vh, sizeof(double) * nloc, V.get(), sizeof(double) * ld, sizeof(double) * nloc, m, cudaMemcpyDeviceToHost, st));
+        if (Hh)
+            SB200_CUDA_CHECK(cudaMemcpyAsync(Hh, H.get(), sizeof(double) * m * m, cudaMemcpyDeviceToHost, st));
+        if (fh && nloc > 0)
+            SB200_CUDA_CHECK(cudaMemcpyAsync(fh, f.get(), sizeof(double) * nloc, cudaMemcpyDeviceToHost, st));
+        SB200_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (beta)
+            *beta = h_beta;
+        if (kk)
+            *kk = k;
+    }
+};
+
+}  // namespace sb200

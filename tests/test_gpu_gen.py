@@ -1,0 +1,157 @@
+"""GPU parity tests of the nonsymmetric (Arnoldi) path through the C ABI against the CPU oracle.
+Tiers and tolerances follow test/GenEigs.cpp (solver, ||AU-UD||_inf <= 1e-9, maxit 300),
+test/Arnoldi.cpp (factorisation, 1e-12), test/QR.cpp / test/Eigen.cpp / test/Schur.cpp (dense, 1e-12)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle as O
+from helpers import readme_banded, dense_as_csc
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_hess(rng, m):
+    return np.triu(rng.standard_normal((m, m)), -1)
+
+
+@pytest.mark.parametrize("m", [2, 3, 6, 20, 60, 64])
+def test_hessenberg_qr_device(gpu, m):
+    # test/QR.cpp:101-113
+    rng = np.random.default_rng(m)
+    H = _rand_hess(rng, m)
+    for shift in (0.0, 0.41):
+        D, Q = gpu.dense.shifted_qr(H, shift, "hess")
+        R0, D0, Q0 = O.shifted_qr(H, shift, "hess")
+        assert np.abs(Q.T @ Q - np.eye(m)).max() <= 1e-12
+        assert np.abs(Q.T @ H @ Q - D).max() <= 1e-12 * m
+        assert np.abs(Q - Q0).max() <= 1e-11 and np.abs(D - D0).max() <= 1e-11 * max(1, np.abs(D0).max())
+
+
+@pytest.mark.parametrize("m", [3, 4, 6, 20, 60, 64])
+def test_double_shift_qr_device(gpu, m):
+    # test/QR.cpp:131-175
+    rng = np.random.default_rng(10 + m)
+    H = _rand_hess(rng, m)
+    if m >= 20:
+        H[7, 6] = 0.0  # split into blocks (DoubleShiftQR.h:351-385)
+        H[12, 11] = 1e-300
+    s, t = 0.4, 1.3
+    D, Q = gpu.dense.double_shift_qr(H, s, t)
+    D0, Q0 = O.double_shift_qr(H, s, t)
+    assert np.abs(Q.T @ Q - np.eye(m)).max() <= 1e-12
+    assert np.abs(Q.T @ H @ Q - D).max() <= 1e-12 * m
+    R = Q.T @ (H @ H - s * H + t * np.eye(m))
+    assert np.abs(np.tril(R, -1)).max() <= 1e-11 * m
+    assert np.abs(Q - Q0).max() <= 1e-10 and np.abs(D - D0).max() <= 1e-10 * max(1, np.abs(D0).max())
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 6, 20, 50, 60, 64])
+def test_hessenberg_eigen_device(gpu, m):
+    # test/Eigen.cpp:26-42 (||HU - UD|| <= 1e-12 scaled), eigenvalues vs the oracle
+    rng = np.random.default_rng(20 + m)
+    H = _rand_hess(rng, m)
+    ev, V = gpu.dense.hess_eigen(H)
+    ev0, V0 = O.hess_eigen(H)
+    assert np.abs(H @ V - V * ev).max() <= 1e-12 * max(m, 4) * max(1, np.abs(H).max())
+    assert np.abs(np.linalg.norm(V, axis=0) - 1).max() <= 1e-12
+    assert np.abs(np.sort_complex(ev) - np.sort_complex(ev0)).max() <= 1e-10 * max(1, np.abs(ev0).max())
+    # exact conjugate pairs / exact zero imaginary parts (relied upon by GenEigsBase.h:200-201)
+    for z in ev:
+        if z.imag != 0:
+            assert np.any(ev == np.conj(z))
+
+
+@pytest.mark.parametrize("n,m", [(10, 6), (100, 30), (1000, 50), (3000, 64)])
+def test_arnoldi_factorization(gpu, n, m):
+    # test/Arnoldi.cpp:19-85
+    if n <= 1000:
+        A = O.gen_sparse_data(n, {10: 0.5, 100: 0.1, 1000: 0.01}[n])
+    else:
+        A = sp.random(n, n, density=0.003, random_state=5, format="csc")
+    op = gpu.SparseGenMatProd(A)
+    eigs = gpu.GenEigsSolver(op, min(3, n - 2), m)
+    v0 = O.simple_random(3, n)
+    eigs.init(v0)
+    eigs.factorize_from(1, m // 2)
+    eigs.factorize_from(m // 2, m)
+    fz = eigs.factorization()
+    V, H, f = fz["V"], fz["H"], fz["f"]
+    E = A @ V - V @ H
+    E[:, -1] -= f
+    scale = max(1.0, np.abs(H).max())
+    assert np.abs(E).max() <= 1e-12 * scale
+    assert np.abs(V.T @ V - np.eye(m)).max() <= 1e-12
+    assert np.abs(np.tril(H, -2)).max() == 0.0
+    ref = O.factorize(O.Csr.from_scipy(A), m, v0=v0, kind="arnoldi")
+    assert np.abs(H - ref["H"]).max() <= 1e-9 * scale
+
+
+GEN_CASES = [(10, 0.5, 3, 6), (100, 0.1, 10, 30), (1000, 0.01, 20, 50)]
+GEN_RULES = [("LargestMagn", False), ("LargestReal", False), ("LargestImag", False), ("SmallestMagn", True), ("SmallestReal", False), ("SmallestImag", True)]
+
+
+@pytest.mark.parametrize("n,prob,k,m", GEN_CASES)
+@pytest.mark.parametrize("rule,allow_fail", GEN_RULES)
+def test_gen_eigs_sparse_reference_cases(gpu, n, prob, k, m, rule, allow_fail):
+    # test/GenEigs.cpp:38-107,143-174
+    A = O.gen_sparse_data(n, prob)
+    eigs = gpu.GenEigsSolver(gpu.SparseGenMatProd(A), k, m)
+    eigs.init()
+    nconv = eigs.compute(gpu.SortRule[rule], 300)
+    ref = O.gen_eigs(O.Csr.from_scipy(A), k, m, int(gpu.SortRule[rule]), 300)
+    if allow_fail and eigs.info() != gpu.CompInfo.Successful:
+        assert ref.info != O.Successful  # the oracle fails on the same case
+        return
+    assert eigs.info() == gpu.CompInfo.Successful and nconv == k
+    evals, evecs = eigs.eigenvalues(), eigs.eigenvectors()
+    assert np.abs(A @ evecs - evecs * evals).max() <= 1e-9
+    assert ref.info == O.Successful
+    a = np.sort_complex(np.round(evals, 9))
+    b = np.sort_complex(np.round(ref.eigenvalues, 9))
+    assert np.abs(np.sort_complex(evals) - np.sort_complex(ref.eigenvalues)).max() <= 1e-9 * np.abs(ref.eigenvalues).max() or np.allclose(a, b)
+
+
+def test_readme_banded_nonsymmetric(gpu):
+    # README.md:146-178
+    M = readme_banded(10)
+    eigs = gpu.GenEigsSolver(gpu.SparseGenMatProd(sp.csc_matrix(M)), 3, 6)
+    eigs.init()
+    eigs.compute(gpu.SortRule.LargestMagn)
+    assert eigs.info() == gpu.CompInfo.Successful
+    true = sorted(np.linalg.eigvals(M), key=lambda z: -abs(z))[:3]
+    ev = eigs.eigenvalues()
+    assert np.allclose(ev.real, np.real(true), atol=1e-9) and np.abs(ev.imag).max() < 1e-9
+
+
+def test_gen_argument_checks(gpu):
+    op = gpu.SparseGenMatProd(sp.identity(10, format="csc"))
+    for nev, ncv in [(0, 5), (9, 12), (3, 4), (3, 11)]:
+        with pytest.raises(gpu.InvalidArgument):  # GenEigsBase.h:419-423
+            gpu.GenEigsSolver(op, nev, ncv)
+    eigs = gpu.GenEigsSolver(op, 3, 6)
+    with pytest.raises(gpu.InvalidArgument):
+        eigs.init(np.zeros(10))
+    eigs.init()
+    with pytest.raises(gpu.InvalidArgument):
+        eigs.compute(gpu.SortRule.LargestAlge)
+
+
+def test_gen_eigs_medium_vs_oracle(gpu):
+    # BASELINE config C3 shape at a size the oracle finishes in seconds: G_gen, k = 10, ncv = 30
+    from spectra_b200 import synth
+
+    n = 50000
+    rp, ci, v = synth.csr(n, 20, 1, False)
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    op = gpu.SparseGenMatProd.from_csr_slab(n, 0, rp, ci, v)
+    eigs = gpu.GenEigsSolver(op, 10, 30)
+    eigs.init()
+    nconv = eigs.compute(gpu.SortRule.LargestMagn)
+    assert eigs.info() == gpu.CompInfo.Successful and nconv == 10
+    evals, X = eigs.eigenvalues(), eigs.eigenvectors()
+    res = np.linalg.norm(A @ X - X * evals, axis=0) / np.abs(evals)
+    assert res.max() <= 1e-9
+    ref = O.gen_eigs(O.Csr.adopt(n, rp, ci, v), 10, 30, O.LargestMagn, want_vectors=False)
+    assert ref.info == O.Successful
+    assert np.abs(np.sort_complex(evals) - np.sort_complex(ref.eigenvalues)).max() <= 1e-9 * np.abs(ref.eigenvalues).max()

@@ -1,7 +1,10 @@
 """Developer probe (not the contract bench): SpMV + one full solve with per-kernel-class timing."""
 import json
+import os
 import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 
