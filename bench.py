@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: SymEigsSolver + SparseSymMatProd on a synthetic sparse matrix.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (sm_100a CUDA through the C ABI)
+    python bench.py --impl reference --gpus N ...            # the reference algorithm on the host CPU (oracle port)
+
+Workload (BASELINE.json `metric`): G_sym(n = 1e7, 20 nnz/row, seed 0), nev = 20, ncv = 60, tol 1e-10,
+selection LargestAlge, default SimpleRandom(0) initial residual.  One "step" = one complete solve
+(init() + compute()).  `value` = matrix operations (SpMV iterations) per second of device time with the
+operator already resident in HBM; `e2e` = the same metric through the reference-facing call sequence with
+HOST buffers (CSR upload + triangle expansion, solve, eigenvalues and eigenvectors copied back).
+Strong scaling: n stays 1e7 for every N; rows are sharded across the N ranks (one process per GPU).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=float, default=1e7)
+    ap.add_argument("--nnz-per-row", type=int, default=20)
+    ap.add_argument("--nev", type=int, default=20)
+    ap.add_argument("--ncv", type=int, default=60)
+    ap.add_argument("--tol", type=float, default=1e-10)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-sample-ops", type=int, default=12, help="matrix operations in the bounded CPU sample")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        if shutil.which("nvidia-smi"):
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(gpu_index)],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.th = threading.Thread(target=self._read, daemon=True)
+                self.th.start()
+            except Exception:
+                self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pinned_alloc():
+    """Host arrays in pinned memory (torch is only the allocator here)."""
+    import torch
+
+    keep = []
+
+    def alloc(count, dtype):
+        t = torch.empty(int(count), dtype={np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32, np.dtype(np.float64): torch.float64}[np.dtype(dtype)],
+                        pin_memory=True)
+        keep.append(t)
+        return t.numpy()
+
+    return alloc, keep
+
+
+def run_reference(args, n):
+    """The reference algorithm (CPU restatement in oracle/, all host threads) on bounded samples of the workload."""
+    from spectra_b200 import dist, synth
+    rank, _, world = dist.env_rank()
+    if rank != 0:
+        return
+    import oracle as O
+
+    threads = O.max_threads()
+    rp, ci, v = synth.csr(n, args.nnz_per_row, args.seed, True)
+    A = O.Csr.adopt(n, rp, ci, v)
+    times, ops = [], 0
+    for it in range(args.warmup + args.steps):
+        r = O.sym_eigs(A, args.nev, args.ncv, O.LargestAlge, 1000, args.tol, threads=threads, op_limit=args.cpu_sample_ops, want_vectors=False)
+        if it >= args.warmup:
+            times.append(r.seconds)
+            ops = r.nops
+    sec = float(np.mean(times))
+    value = ops / sec
+    sample = f"init + first {ops - 2} Lanczos steps (op_limit={args.cpu_sample_ops}) of the n={n} solve, {threads} OpenMP threads"
+    line = {
+        "impl": "reference", "metric": "spmv_iters_per_sec", "value": value, "unit": "SpMV-iters/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, n),
+        "cpu_baseline": {"value": value, "unit": "SpMV-iters/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "SpMV-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n):
+    return {"workload": f"SymEigsSolver<SparseSymMatProd<double>> G_sym n={n} nnz/row={args.nnz_per_row} nev={args.nev} ncv={args.ncv} tol={args.tol:g} "
+                        f"selection=LargestAlge init=SimpleRandom(0)", "n": n, "nnz_per_row": args.nnz_per_row, "nev": args.nev, "ncv": args.ncv,
+            "parallelism": f"row-sharded x{args.gpus}", "l2": "inputs larger than L2 (CSR + Krylov basis >> 126 MB); no flush needed"}
+
+
+def main():
+    args = parse_args()
+    n = int(args.n)
+    if args.impl == "reference":
+        run_reference(args, n)
+        return
+
+    import torch
+
+    import spectra_b200 as sb
+    from spectra_b200 import dist, synth
+
+    rank, local_rank, world = dist.env_rank()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} needs {args.gpus} ranks (launch with torch.distributed.run); WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    sb.set_device(local_rank)
+    dist.init_process_group("nccl" if world > 1 else None)
+    comm = dist.make_comm()
+    info = sb.device_info()
+    peak, peak_src = measured_peak()
+
+    # ---- synthetic input (host, pinned): this rank's row slab of G_sym ----
+    row0, nrows = dist.slab_range(n, rank, world)
+    alloc, _keep = pinned_alloc()
+    t0 = time.time()
+    rp, ci, v = synth.csr(n, args.nnz_per_row, args.seed, True, row0=row0, nrows=nrows, alloc=alloc)
+    gen_s = time.time() - t0
+    nnz_local = len(ci)
+    nnz_total = int(dist.sum_over_ranks(nnz_local))
+
+    def make_op():
+        if world == 1:
+            # the reference-facing call: Eigen-style compressed ColMajor matrix, lower triangle read and mirrored
+            return sb.SparseSymMatProd((n, rp, ci, v, "col"), uplo="lower")
+        return sb.SparseGenMatProd.from_csr_slab(n, row0, rp, ci, v, comm=comm)
+
+    # =========================== value arm: operator resident in HBM ===========================
+    op = make_op()
+    eigs = sb.SymEigsSolver(op, args.nev, args.ncv)
+    sampler = None
+    step_ms, step_wall, launches = [], [], 0
+    nops = nconv = niter = 0
+    for it in range(args.warmup + args.steps):
+        if it == args.warmup:
+            dist.barrier()
+            torch.cuda.synchronize()
+            sampler = ClockSampler(local_rank) if rank == 0 else None
+        tw = time.perf_counter()
+        eigs.init()
+        nconv = eigs.compute(sb.SortRule.LargestAlge, 1000, args.tol)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - tw
+        st = eigs.stats()
+        if it >= args.warmup:
+            step_ms.append(st["ms_total"])  # CUDA events on the solver stream around init()+compute()
+            step_wall.append(wall * 1e3)
+            launches += st["kernel_launches"]
+        nops, niter = eigs.num_operations(), eigs.num_iterations()
+    dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = dist.max_over_ranks(float(np.mean(step_ms)))
+    wall_per_step = dist.max_over_ranks(float(np.mean(step_wall)))
+    value = nops / (ms_per_step / 1e3)
+    info_ok = eigs.info() == sb.CompInfo.Successful
+    last_stats = eigs.stats()
+
+    # ---- accuracy of the returned eigenpairs (untimed): ||A x - lambda x|| / |lambda| ----
+    evals = eigs.eigenvalues()
+    X = eigs.eigenvectors(local=(world > 1))
+    Xfull = eigs.eigenvectors() if world > 1 else X
+    AX = op @ Xfull  # local rows
+    num = np.array([dist.sum_over_ranks(float(np.sum((AX[:, c] - X[:, c] * evals[c]) ** 2))) for c in range(len(evals))])
+    rel_res = np.sqrt(num) / np.abs(evals) if len(evals) else np.array([np.inf])
+    del AX, Xfull
+
+    # ---- per-kernel roofline (untimed extra solve with per-class CUDA events) ----
+    sb.set_profiling(1)
+    eigs.init()
+    eigs.compute(sb.SortRule.LargestAlge, 1000, args.tol)
+    ps = eigs.stats()
+    sb.set_profiling(0)
+    nl = nrows
+    spmv_bytes = 12.0 * nnz_local + 4.0 * (nl + 1) + 8.0 * n + 8.0 * nl + 16.0 * nl  # CSR + x + y, + v_i write and v_{i-1} read of the fused step head
+    panel_bytes_total = 8.0 * nl * (ps["panel_cols"] + 2 * ps["panel_launches"])
+    kern = {
+        "panel_pass": {"launches": ps["panel_launches"], "ms_total": ps["ms_panel"], "avg_ms": ps["ms_panel"] / max(ps["panel_launches"], 1),
+                       "algorithmic_bytes_per_launch": panel_bytes_total / max(ps["panel_launches"], 1),
+                       "gbs": panel_bytes_total / max(ps["ms_panel"], 1e-9) / 1e6},
+        "csr_spmv": {"launches": ps["spmv_launches"], "ms_total": ps["ms_spmv"], "avg_ms": ps["ms_spmv"] / max(ps["spmv_launches"], 1),
+                     "algorithmic_bytes_per_launch": spmv_bytes, "gbs": spmv_bytes * ps["spmv_launches"] / max(ps["ms_spmv"], 1e-9) / 1e6},
+        "restart_gemm": {"launches": ps["compress_launches"], "ms_total": ps["ms_compress"]},
+        "small_dense": {"ms_total": ps["ms_small"]},
+        "comm": {"ms_total": ps["ms_comm"]},
+    }
+    for kname in ("panel_pass", "csr_spmv"):
+        kern[kname]["frac_of_hbm_peak"] = kern[kname]["gbs"] / peak
+    dominant = "panel_pass" if ps["ms_panel"] >= ps["ms_spmv"] else "csr_spmv"
+    roofline = {"kernel": dominant, "bound": "hbm", "achieved": kern[dominant]["gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": kern[dominant]["gbs"] / peak, "traffic": None, "share_of_step": {"panel_pass": ps["ms_panel"] / ps["ms_total"],
+                                                                                          "csr_spmv": ps["ms_spmv"] / ps["ms_total"]}}
+
+    # =========================== e2e arm: host buffers in, host results out ===========================
+    e2e = None
+    if not args.skip_e2e:
+        del eigs
+        op.close()
+        e2e_wall = []
+        h2d = rp.nbytes + ci.nbytes + v.nbytes + 8 * n  # CSR arrays + the default initial residual
+        import torch as _t
+
+        xbuf = _t.empty((args.nev, nrows if world > 1 else n), dtype=_t.float64, pin_memory=True).numpy().T  # F-ordered (rows x nev)
+        d2h = 0
+        for it in range(args.warmup + args.steps):
+            dist.barrier()
+            torch.cuda.synchronize()
+            tw = time.perf_counter()
+            op2 = make_op()
+            e2 = sb.SymEigsSolver(op2, args.nev, args.ncv)
+            e2.init()
+            e2.compute(sb.SortRule.LargestAlge, 1000, args.tol)
+            ev2 = e2.eigenvalues()
+            xv = e2.eigenvectors(local=(world > 1), out=xbuf)
+            torch.cuda.synchronize()
+            dist.barrier()
+            wall = time.perf_counter() - tw
+            d2h = xv.nbytes + ev2.nbytes
+            ops2 = e2.num_operations()
+            if it >= args.warmup:
+                e2e_wall.append(wall)
+            del e2
+            op2.close()
+        e2e_s = dist.max_over_ranks(float(np.mean(e2e_wall)))
+        e2e = {"value": ops2 / e2e_s, "unit": "SpMV-iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "s_per_step": e2e_s,
+               "eigenpairs_per_sec": nconv / e2e_s}
+
+    # =========================== CPU baseline: oracle port, 1 thread, bounded sample ===========================
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        import oracle as O
+
+        A = O.Csr.adopt(n, rp, ci, v)
+        r = O.sym_eigs(A, args.nev, args.ncv, O.LargestAlge, 1000, args.tol, threads=1, op_limit=args.cpu_sample_ops, want_vectors=False)
+        cpu = {"value": r.nops / r.seconds, "unit": "SpMV-iters/s", "cores": 1, "kind": "port",
+               "sample": f"init + first {r.nops - 2} Lanczos steps (op_limit={args.cpu_sample_ops}) of the same n={n} solve, {r.seconds:.1f} s; early steps have "
+                         f"narrow panels, so this over-states the CPU's steady-state rate", "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": "spmv_iters_per_sec", "value": value, "unit": "SpMV-iters/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, n),
+            "eigenpairs_per_sec": nconv / (ms_per_step / 1e3), "nconv": int(nconv), "num_operations": int(nops), "num_iterations": int(niter),
+            "converged": bool(info_ok), "accuracy": {"max_rel_residual": float(np.max(rel_res)), "bound": 1e-10},
+            "wall_ms_per_step": wall_per_step, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kern, "cpu_baseline": cpu,
+            "clocks": clocks, "algo_counters": {k: last_stats[k] for k in ("lanczos_steps", "reorth_passes", "restarts", "expand_calls")},
+            "device": info, "nnz": nnz_total, "gen_seconds": gen_s,
+        }
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -337,10 +337,13 @@ class SymEigsSolver:
         _check(lib().sb200_sym_eigenvalues(self.h, _p(out), C.byref(cnt)))
         return out[:cnt.value].copy()
 
-    def eigenvectors(self, nvec: int | None = None, local: bool = False) -> np.ndarray:
+    def eigenvectors(self, nvec: int | None = None, local: bool = False, out: np.ndarray | None = None) -> np.ndarray:
+        """n x nconv column-major matrix (HermEigsBase.h:447-470).  `out` may supply a (pinned) F-ordered buffer."""
         nvec = self.nev if nvec is None else int(nvec)
         rows = self.op.nrows_local if local else self.op.n
-        out = np.empty((rows, max(nvec, 1)), order="F")
+        if out is None:
+            out = np.empty((rows, max(nvec, 1)), order="F")
+        assert out.flags.f_contiguous and out.shape[0] == rows and out.shape[1] >= max(nvec, 1) and out.dtype == np.float64
         cnt = C.c_int64()
         fn = lib().sb200_sym_eigenvectors_local if local else lib().sb200_sym_eigenvectors
         _check(fn(self.h, C.c_int64(nvec), _p(out), C.byref(cnt)))

@@ -30,15 +30,17 @@ def lib():
     return _lib
 
 
-def csr(n: int, d: int = 20, seed: int = 0, sym: bool = True, row0: int = 0, nrows: int | None = None):
-    """Rows [row0, row0+nrows) of G_sym / G_gen as (rowptr int64 (local offsets), col int32, val float64)."""
+def csr(n: int, d: int = 20, seed: int = 0, sym: bool = True, row0: int = 0, nrows: int | None = None, alloc=None):
+    """Rows [row0, row0+nrows) of G_sym / G_gen as (rowptr int64 (local offsets), col int32, val float64).
+    `alloc(count, dtype)` may supply the output arrays (e.g. pinned host memory)."""
     nrows = n - row0 if nrows is None else nrows
-    rowptr = np.empty(nrows + 1, np.int64)
+    alloc = alloc or (lambda count, dtype: np.empty(count, dtype))
+    rowptr = alloc(nrows + 1, np.int64)
     nnz = lib().synth_csr_count(C.c_int64(n), int(d), int(bool(sym)), C.c_uint64(seed), C.c_int64(row0), C.c_int64(nrows), rowptr.ctypes.data_as(C.c_void_p))
     if nnz < 0:
         raise ValueError("bad generator arguments")
-    col = np.empty(nnz, np.int32)
-    val = np.empty(nnz, np.float64)
+    col = alloc(nnz, np.int32)
+    val = alloc(nnz, np.float64)
     rc = lib().synth_csr_fill(C.c_int64(n), int(d), int(bool(sym)), C.c_uint64(seed), C.c_int64(row0), C.c_int64(nrows), rowptr.ctypes.data_as(C.c_void_p),
                               col.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p))
     assert rc == 0
