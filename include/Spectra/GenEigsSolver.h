@@ -1,0 +1,90 @@
+// B200 shim of Spectra/GenEigsSolver.h:158-186 (+ the public surface of GenEigsBase.h:409-611):
+// implicitly restarted Arnoldi for real nonsymmetric matrices; complex Ritz pairs.
+#ifndef SPECTRA_B200_GEN_EIGS_SOLVER_H
+#define SPECTRA_B200_GEN_EIGS_SOLVER_H
+
+#include <algorithm>
+
+#include "MatOp/SparseGenMatProd.h"
+#include "Util/CompInfo.h"
+#include "Util/SelectionRule.h"
+#include "b200/Common.h"
+
+namespace Spectra {
+
+template <typename OpType = SparseGenMatProd<double>>
+class GenEigsSolver
+{
+    static_assert(std::is_base_of<b200::SparseOpBase, OpType>::value, "the B200 solver runs with device-resident operators");
+    sb200_gen_solver* m_s = nullptr;
+    const OpType& m_op;
+    Index m_nev;
+
+public:
+    using Scalar = typename OpType::Scalar;
+    using ComplexVector = b200::ComplexVector;
+    using ComplexMatrix = b200::ComplexMatrix;
+
+    GenEigsSolver(OpType& op, Index nev, Index ncv) : m_op(op), m_nev(nev) { b200::check(sb200_gen_create(op.handle(), nev, ncv, &m_s)); }
+    GenEigsSolver(const GenEigsSolver&) = delete;
+    GenEigsSolver& operator=(const GenEigsSolver&) = delete;
+    virtual ~GenEigsSolver()
+    {
+        if (m_s)
+            sb200_gen_destroy(m_s);
+    }
+
+    void init(const Scalar* init_resid) { b200::check(sb200_gen_init(m_s, init_resid)); }
+    void init() { b200::check(sb200_gen_init(m_s, nullptr)); }
+
+    Index compute(SortRule selection = SortRule::LargestMagn, Index maxit = 1000, Scalar tol = 1e-10, SortRule sorting = SortRule::LargestMagn)
+    {
+        int64_t nconv = 0;
+        b200::check(sb200_gen_compute(m_s, static_cast<int>(selection), maxit, tol, static_cast<int>(sorting), &nconv));
+        return static_cast<Index>(nconv);
+    }
+    CompInfo info() const
+    {
+        int v = 0;
+        b200::check(sb200_gen_info(m_s, &v));
+        return static_cast<CompInfo>(v);
+    }
+    Index num_iterations() const
+    {
+        int64_t v = 0;
+        b200::check(sb200_gen_num_iterations(m_s, &v));
+        return static_cast<Index>(v);
+    }
+    Index num_operations() const
+    {
+        int64_t v = 0;
+        b200::check(sb200_gen_num_operations(m_s, &v));
+        return static_cast<Index>(v);
+    }
+
+    ComplexVector eigenvalues() const
+    {
+        std::vector<double> buf(static_cast<size_t>(2 * m_nev));
+        int64_t cnt = 0;
+        b200::check(sb200_gen_eigenvalues(m_s, buf.data(), &cnt));
+        ComplexVector res(static_cast<Index>(cnt));
+        for (int64_t i = 0; i < cnt; i++)
+            res[i] = std::complex<double>(buf[static_cast<size_t>(2 * i)], buf[static_cast<size_t>(2 * i + 1)]);
+        return res;
+    }
+
+    ComplexMatrix eigenvectors(Index nvec) const
+    {
+        nvec = (std::min)(nvec, m_nev);
+        ComplexMatrix res(m_op.rows(), (std::max)(nvec, Index(1)));
+        int64_t cnt = 0;
+        // std::complex<double> is layout-compatible with interleaved (re, im) pairs
+        b200::check(sb200_gen_eigenvectors(m_s, nvec, reinterpret_cast<double*>(res.data()), &cnt));
+        b200::shrink_cols(res, static_cast<Index>(cnt));
+        return res;
+    }
+    ComplexMatrix eigenvectors() const { return eigenvectors(m_nev); }
+};
+
+}  // namespace Spectra
+#endif

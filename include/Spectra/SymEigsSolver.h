@@ -1,0 +1,91 @@
+// B200 shim of Spectra/SymEigsSolver.h:133-160 (+ the public surface of HermEigsBase.h:257-478):
+// implicitly restarted Lanczos on the GPU behind the same constructor / init / compute / getters.
+#ifndef SPECTRA_B200_SYM_EIGS_SOLVER_H
+#define SPECTRA_B200_SYM_EIGS_SOLVER_H
+
+#include <algorithm>
+
+#include "MatOp/SparseSymMatProd.h"
+#include "Util/CompInfo.h"
+#include "Util/SelectionRule.h"
+#include "b200/Common.h"
+
+namespace Spectra {
+
+template <typename OpType = SparseSymMatProd<double>>
+class SymEigsSolver
+{
+    static_assert(std::is_base_of<b200::SparseOpBase, OpType>::value,
+                  "the B200 solver runs with device-resident operators (SparseSymMatProd / SparseGenMatProd); user-defined host OpTypes are not wired yet");
+    sb200_sym_solver* m_s = nullptr;
+    const OpType& m_op;  // the operator must outlive the solver (HermEigsBase.h:257-258)
+    Index m_nev;
+
+public:
+    using Scalar = typename OpType::Scalar;
+    using Vector = b200::Vector;
+    using Matrix = b200::Matrix;
+
+    SymEigsSolver(OpType& op, Index nev, Index ncv) : m_op(op), m_nev(nev) { b200::check(sb200_sym_create(op.handle(), nev, ncv, &m_s)); }
+    SymEigsSolver(const SymEigsSolver&) = delete;
+    SymEigsSolver& operator=(const SymEigsSolver&) = delete;
+    virtual ~SymEigsSolver()
+    {
+        if (m_s)
+            sb200_sym_destroy(m_s);
+    }
+
+    void init(const Scalar* init_resid) { b200::check(sb200_sym_init(m_s, init_resid)); }
+    void init() { b200::check(sb200_sym_init(m_s, nullptr)); }
+
+    Index compute(SortRule selection = SortRule::LargestMagn, Index maxit = 1000, Scalar tol = 1e-10, SortRule sorting = SortRule::LargestAlge)
+    {
+        int64_t nconv = 0;
+        b200::check(sb200_sym_compute(m_s, static_cast<int>(selection), maxit, tol, static_cast<int>(sorting), &nconv));
+        return static_cast<Index>(nconv);
+    }
+
+    CompInfo info() const
+    {
+        int v = 0;
+        b200::check(sb200_sym_info(m_s, &v));
+        return static_cast<CompInfo>(v);
+    }
+    Index num_iterations() const
+    {
+        int64_t v = 0;
+        b200::check(sb200_sym_num_iterations(m_s, &v));
+        return static_cast<Index>(v);
+    }
+    Index num_operations() const
+    {
+        int64_t v = 0;
+        b200::check(sb200_sym_num_operations(m_s, &v));
+        return static_cast<Index>(v);
+    }
+
+    Vector eigenvalues() const
+    {
+        std::vector<double> buf(static_cast<size_t>(m_nev));
+        int64_t cnt = 0;
+        b200::check(sb200_sym_eigenvalues(m_s, buf.data(), &cnt));
+        Vector res(static_cast<Index>(cnt));
+        for (int64_t i = 0; i < cnt; i++)
+            res[i] = buf[static_cast<size_t>(i)];
+        return res;
+    }
+
+    Matrix eigenvectors(Index nvec) const
+    {
+        nvec = (std::min)(nvec, m_nev);
+        Matrix res(m_op.rows(), (std::max)(nvec, Index(1)));
+        int64_t cnt = 0;
+        b200::check(sb200_sym_eigenvectors(m_s, nvec, res.data(), &cnt));
+        b200::shrink_cols(res, static_cast<Index>(cnt));
+        return res;
+    }
+    Matrix eigenvectors() const { return eigenvectors(m_nev); }
+};
+
+}  // namespace Spectra
+#endif

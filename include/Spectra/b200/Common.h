@@ -1,0 +1,203 @@
+// Shared pieces of the header-only C++ shim over the C ABI (include/spectra_b200.h).
+//
+// The shim keeps the reference's class and method names so that user code written against
+// yixuan/spectra compiles unchanged for the supported path:
+//     SparseSymMatProd<double> op(...);  SymEigsSolver<SparseSymMatProd<double>> eigs(op, nev, ncv);
+//     eigs.init();  eigs.compute(SortRule::LargestAlge);  eigs.info();  eigs.eigenvalues();  eigs.eigenvectors();
+// When Eigen is available (<Eigen/Core> on the include path) results are Eigen vectors / matrices and
+// the operator constructors accept Eigen::SparseMatrix; otherwise the light containers below are used
+// (same element access: v[i], M(i, j), .data(), .size(), .rows(), .cols()).
+#ifndef SPECTRA_B200_COMMON_H
+#define SPECTRA_B200_COMMON_H
+
+#include <complex>
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../spectra_b200.h"
+
+#if defined(__has_include)
+#if __has_include(<Eigen/Core>) && __has_include(<Eigen/SparseCore>) && !defined(SPECTRA_B200_NO_EIGEN)
+#define SPECTRA_B200_HAS_EIGEN 1
+#include <Eigen/Core>
+#include <Eigen/SparseCore>
+#endif
+#endif
+
+namespace Spectra {
+
+using Index = std::ptrdiff_t;
+
+namespace b200 {
+
+// status -> the exception type the reference throws
+inline void check(int status)
+{
+    if (status == SB200_OK)
+        return;
+    const std::string msg = sb200_last_error();
+    switch (status)
+    {
+        case SB200_INVALID_ARGUMENT: throw std::invalid_argument(msg);
+        case SB200_LOGIC: throw std::logic_error(msg);
+        default: throw std::runtime_error(msg);
+    }
+}
+
+#ifndef SPECTRA_B200_HAS_EIGEN
+template <typename T>
+class VectorT
+{
+    std::vector<T> m_v;
+
+public:
+    VectorT() {}
+    explicit VectorT(Index n) : m_v(static_cast<size_t>(n)) {}
+    Index size() const { return static_cast<Index>(m_v.size()); }
+    Index rows() const { return size(); }
+    Index cols() const { return 1; }
+    T& operator[](Index i) { return m_v[static_cast<size_t>(i)]; }
+    const T& operator[](Index i) const { return m_v[static_cast<size_t>(i)]; }
+    T& operator()(Index i) { return m_v[static_cast<size_t>(i)]; }
+    const T& operator()(Index i) const { return m_v[static_cast<size_t>(i)]; }
+    T* data() { return m_v.data(); }
+    const T* data() const { return m_v.data(); }
+    void resize(Index n) { m_v.resize(static_cast<size_t>(n)); }
+};
+
+// column-major dense matrix, element (i, j) at data()[i + j * rows()]
+template <typename T>
+class MatrixT
+{
+    Index m_r = 0, m_c = 0;
+    std::vector<T> m_v;
+
+public:
+    MatrixT() {}
+    MatrixT(Index r, Index c) : m_r(r), m_c(c), m_v(static_cast<size_t>(r * c)) {}
+    Index rows() const { return m_r; }
+    Index cols() const { return m_c; }
+    Index size() const { return m_r * m_c; }
+    T& operator()(Index i, Index j) { return m_v[static_cast<size_t>(i + j * m_r)]; }
+    const T& operator()(Index i, Index j) const { return m_v[static_cast<size_t>(i + j * m_r)]; }
+    T* data() { return m_v.data(); }
+    const T* data() const { return m_v.data(); }
+    void resize(Index r, Index c)
+    {
+        m_r = r;
+        m_c = c;
+        m_v.resize(static_cast<size_t>(r * c));
+    }
+    // keep the first c columns (column-major storage makes this a truncation)
+    void conservative_resize_cols(Index c)
+    {
+        m_c = c;
+        m_v.resize(static_cast<size_t>(m_r * c));
+    }
+};
+using Vector = VectorT<double>;
+using Matrix = MatrixT<double>;
+using ComplexVector = VectorT<std::complex<double>>;
+using ComplexMatrix = MatrixT<std::complex<double>>;
+inline void shrink_cols(Matrix& M, Index c) { M.conservative_resize_cols(c); }
+inline void shrink_cols(ComplexMatrix& M, Index c) { M.conservative_resize_cols(c); }
+#else
+using Vector = Eigen::VectorXd;
+using Matrix = Eigen::MatrixXd;
+using ComplexVector = Eigen::VectorXcd;
+using ComplexMatrix = Eigen::MatrixXcd;
+inline void shrink_cols(Matrix& M, Index c) { M.conservativeResize(M.rows(), c); }
+inline void shrink_cols(ComplexMatrix& M, Index c) { M.conservativeResize(M.rows(), c); }
+#endif
+
+// Device-resident sparse operator shared by SparseSymMatProd / SparseGenMatProd.
+// The user's compressed arrays must outlive the operator (the reference holds an Eigen::Ref to the
+// user's matrix, SparseSymMatProd.h:46-48); they are uploaded once at construction.
+class SparseOpBase
+{
+protected:
+    sb200_op* m_op = nullptr;
+    Index m_n = 0;
+    const void* m_outer = nullptr;
+    bool m_outer64 = false;
+    const int32_t* m_inner = nullptr;
+    const double* m_values = nullptr;
+    bool m_row_major = false;
+
+    void create(Index n, const void* outer, bool outer64, const int32_t* inner, const double* values, bool row_major, int mode)
+    {
+        m_n = n;
+        m_outer = outer;
+        m_outer64 = outer64;
+        m_inner = inner;
+        m_values = values;
+        m_row_major = row_major;
+        check(sb200_op_create_sparse(n, outer, outer64 ? 1 : 0, inner, values, row_major ? SB200_ROW_MAJOR : SB200_COL_MAJOR, mode, nullptr, &m_op));
+    }
+    int64_t outer_at(Index i) const
+    {
+        return m_outer64 ? static_cast<const int64_t*>(m_outer)[i] : static_cast<int64_t>(static_cast<const int32_t*>(m_outer)[i]);
+    }
+
+public:
+    SparseOpBase() {}
+    SparseOpBase(const SparseOpBase&) = delete;
+    SparseOpBase& operator=(const SparseOpBase&) = delete;
+    SparseOpBase(SparseOpBase&& o) noexcept { *this = std::move(o); }
+    SparseOpBase& operator=(SparseOpBase&& o) noexcept
+    {
+        if (this != &o)
+        {
+            if (m_op)
+                sb200_op_destroy(m_op);
+            m_op = o.m_op;
+            m_n = o.m_n;
+            m_outer = o.m_outer;
+            m_outer64 = o.m_outer64;
+            m_inner = o.m_inner;
+            m_values = o.m_values;
+            m_row_major = o.m_row_major;
+            o.m_op = nullptr;
+        }
+        return *this;
+    }
+    ~SparseOpBase()
+    {
+        if (m_op)
+            sb200_op_destroy(m_op);
+    }
+
+    Index rows() const { return m_n; }
+    Index cols() const { return m_n; }
+    sb200_op* handle() const { return m_op; }
+
+    // y_out = A * x_in, host pointers (SparseSymMatProd.h:83-88 / SparseGenMatProd.h:82-87)
+    void perform_op(const double* x_in, double* y_out) const { check(sb200_op_perform_op(m_op, x_in, y_out)); }
+
+    // operator*(Matrix) (SparseSymMatProd.h:93-96)
+    Matrix operator*(const Matrix& mat_in) const
+    {
+        Matrix res(m_n, mat_in.cols());
+        check(sb200_op_apply_matrix(m_op, mat_in.data(), mat_in.cols(), res.data()));
+        return res;
+    }
+
+    // operator()(i, j): the stored coefficient of the user's matrix (SparseSymMatProd.h:101-104)
+    double operator()(Index i, Index j) const
+    {
+        const Index o = m_row_major ? i : j, k = m_row_major ? j : i;
+        for (int64_t p = outer_at(o); p < outer_at(o + 1); p++)
+            if (m_inner[p] == k)
+                return m_values[p];
+        return 0.0;
+    }
+};
+
+inline int to_c(int rule) { return rule; }
+
+}  // namespace b200
+}  // namespace Spectra
+#endif

@@ -20,11 +20,11 @@ namespace {
 constexpr int kSpmvBlock = 256;
 
 template <int L>
-__device__ __forceinline__ double row_dot(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
-                                          const double* __restrict__ x, int64_t row, int lane, uint64_t pol_stream, uint64_t pol_keep)
+// All 32 lanes of a warp must call this together (sub-warp shuffle with a full mask); a sub-warp whose
+// row is out of range passes start == end.
+__device__ __forceinline__ double row_dot(int start, int end, const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
+                                          int lane, uint64_t pol_stream, uint64_t pol_keep)
 {
-    const int start = __ldg(rowptr + row);
-    const int end = __ldg(rowptr + row + 1);
     double acc = 0.0;
     int p = start + lane;
     // two independent gathers in flight per lane
@@ -57,10 +57,15 @@ __global__ void __launch_bounds__(kSpmvBlock) spmv_plain_kernel(const int* __res
     constexpr int RPB = kSpmvBlock / L;  // rows per CTA per iteration
     const int lane = threadIdx.x % L;
     const int sub = threadIdx.x / L;
-    for (int64_t row = (int64_t) blockIdx.x * RPB + sub; row < nrows; row += (int64_t) gridDim.x * RPB)
+    // the loop bound is CTA-uniform so that every warp executes the shuffles with all 32 lanes
+    for (int64_t rbase = (int64_t) blockIdx.x * RPB; rbase < nrows; rbase += (int64_t) gridDim.x * RPB)
     {
-        const double s = row_dot<L>(rowptr, col, val, x, row, lane, pol_stream, pol_keep);
-        if (lane == 0)
+        const int64_t row = rbase + sub;
+        const bool active = row < nrows;
+        const int start = active ? __ldg(rowptr + row) : 0;
+        const int end = active ? __ldg(rowptr + row + 1) : 0;
+        const double s = row_dot<L>(start, end, col, val, x, lane, pol_stream, pol_keep);
+        if (active && lane == 0)
             y[row] = s;
     }
 }
@@ -83,10 +88,14 @@ __global__ void __launch_bounds__(kSpmvBlock)
     const double* __restrict__ vp = V + (int64_t) (i - 1) * ldv;
 
     double part = 0.0;
-    for (int64_t row = (int64_t) blockIdx.x * RPB + sub; row < nrows; row += (int64_t) gridDim.x * RPB)
+    for (int64_t rbase = (int64_t) blockIdx.x * RPB; rbase < nrows; rbase += (int64_t) gridDim.x * RPB)
     {
-        const double s = row_dot<L>(rowptr, col, val, x_full, row, lane, pol_stream, pol_keep);
-        if (lane == 0)
+        const int64_t row = rbase + sub;
+        const bool active = row < nrows;
+        const int start = active ? __ldg(rowptr + row) : 0;
+        const int end = active ? __ldg(rowptr + row + 1) : 0;
+        const double s = row_dot<L>(start, end, col, val, x_full, lane, pol_stream, pol_keep);
+        if (active && lane == 0)
         {
             const double v = f_loc[row] / beta;  // v_i = f / ||f||      (Lanczos.h:106)
             vi[row] = v;

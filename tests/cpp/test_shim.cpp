@@ -1,0 +1,173 @@
+// Drop-in check of the header-only C++ shim (include/Spectra/*): the call sequence of the reference's
+// own tests (test/SymEigs.cpp:44-65,133-167 and test/GenEigs.cpp:38-71) against the GPU library.
+// Eigen-free: the fixture generator below is the reference tests' gen_sparse_data (std::default_random_engine
+// seeded 0), assembled into compressed ColMajor arrays by hand.
+#include <Spectra/GenEigsSolver.h>
+#include <Spectra/MatOp/SparseGenMatProd.h>
+#include <Spectra/MatOp/SparseSymMatProd.h>
+#include <Spectra/SymEigsSolver.h>
+
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <random>
+#include <vector>
+
+using namespace Spectra;
+
+struct Csc
+{
+    int n;
+    std::vector<int> outer, inner;
+    std::vector<double> val;
+};
+
+static Csc gen_sparse_data(int n, double prob)
+{
+    std::default_random_engine gen;
+    gen.seed(0);
+    std::uniform_real_distribution<double> distr(0.0, 1.0);
+    std::vector<std::vector<std::pair<int, double>>> cols(n);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++)
+            if (distr(gen) < prob)
+                cols[j].push_back({i, distr(gen) - 0.5});
+    Csc A;
+    A.n = n;
+    A.outer.push_back(0);
+    for (int j = 0; j < n; j++)
+    {
+        for (auto& e : cols[j])
+        {
+            A.inner.push_back(e.first);
+            A.val.push_back(e.second);
+        }
+        A.outer.push_back((int) A.inner.size());
+    }
+    return A;
+}
+
+// y = selfadjointView<Lower>(A) * x on the host (reference semantics)
+static void sym_lower_mv(const Csc& A, const double* x, double* y)
+{
+    for (int i = 0; i < A.n; i++)
+        y[i] = 0;
+    for (int j = 0; j < A.n; j++)
+        for (int p = A.outer[j]; p < A.outer[j + 1]; p++)
+        {
+            const int i = A.inner[p];
+            if (i < j)
+                continue;
+            y[i] += A.val[p] * x[j];
+            if (i != j)
+                y[j] += A.val[p] * x[i];
+        }
+}
+
+static int fails = 0;
+#define REQUIRE(cond)                                              \
+    do                                                             \
+    {                                                              \
+        if (!(cond))                                               \
+        {                                                          \
+            std::printf("REQUIRE failed: %s (line %d)\n", #cond, __LINE__); \
+            fails++;                                               \
+        }                                                          \
+    } while (0)
+
+static void run_sym(const Csc& A, int k, int m, SortRule rule)
+{
+    SparseSymMatProd<double> op(A.n, A.outer.data(), A.inner.data(), A.val.data());
+    SymEigsSolver<SparseSymMatProd<double>> eigs(op, k, m);
+    eigs.init();
+    const int nconv = (int) eigs.compute(rule);
+    REQUIRE(eigs.info() == CompInfo::Successful);
+    REQUIRE(nconv == k);
+    auto evals = eigs.eigenvalues();
+    auto evecs = eigs.eigenvectors();
+    REQUIRE(evecs.rows() == A.n && evecs.cols() == nconv);
+    std::vector<double> y(A.n);
+    double err = 0;
+    for (int c = 0; c < nconv; c++)
+    {
+        sym_lower_mv(A, &evecs(0, c), y.data());
+        for (int i = 0; i < A.n; i++)
+            err = std::max(err, std::fabs(y[i] - evecs(i, c) * evals[c]));
+    }
+    std::printf("sym n=%d rule=%d nconv=%d niter=%d nops=%d ||AU-UD||_inf=%.3e\n", A.n, (int) rule, nconv, (int) eigs.num_iterations(),
+                (int) eigs.num_operations(), err);
+    REQUIRE(err <= 1e-9);
+    // operator tier: op * M and op(i, j)
+    double x0 = op(45 % A.n, 22 % A.n);
+    (void) x0;
+}
+
+static void run_gen(const Csc& A, int k, int m, SortRule rule)
+{
+    SparseGenMatProd<double> op(A.n, A.outer.data(), A.inner.data(), A.val.data());
+    GenEigsSolver<SparseGenMatProd<double>> eigs(op, k, m);
+    eigs.init();
+    const int nconv = (int) eigs.compute(rule, 300);
+    REQUIRE(eigs.info() == CompInfo::Successful);
+    auto evals = eigs.eigenvalues();
+    auto evecs = eigs.eigenvectors();
+    double err = 0;
+    for (int c = 0; c < nconv; c++)
+    {
+        std::vector<std::complex<double>> y(A.n, 0.0);
+        for (int j = 0; j < A.n; j++)
+            for (int p = A.outer[j]; p < A.outer[j + 1]; p++)
+                y[A.inner[p]] += A.val[p] * evecs(j, c);
+        for (int i = 0; i < A.n; i++)
+            err = std::max(err, std::abs(y[i] - evecs(i, c) * evals[c]));
+    }
+    std::printf("gen n=%d rule=%d nconv=%d nops=%d ||AU-UD||_inf=%.3e\n", A.n, (int) rule, nconv, (int) eigs.num_operations(), err);
+    REQUIRE(err <= 1e-9);
+}
+
+int main()
+{
+    const struct
+    {
+        int n;
+        double p;
+        int k, m, mg;
+    } cases[] = {{10, 0.5, 3, 6, 6}, {100, 0.1, 10, 20, 30}, {1000, 0.01, 20, 50, 50}};
+    for (auto& c : cases)
+    {
+        Csc A = gen_sparse_data(c.n, c.p);
+        for (SortRule r : {SortRule::LargestMagn, SortRule::LargestAlge, SortRule::SmallestAlge, SortRule::BothEnds})
+            run_sym(A, c.k, c.m, r);
+        for (SortRule r : {SortRule::LargestMagn, SortRule::LargestReal, SortRule::LargestImag, SortRule::SmallestReal})
+            run_gen(A, c.k, c.mg, r);
+    }
+    // exceptions keep the reference's types
+    {
+        Csc A = gen_sparse_data(10, 0.5);
+        SparseSymMatProd<double> op(A.n, A.outer.data(), A.inner.data(), A.val.data());
+        bool thrown = false;
+        try
+        {
+            SymEigsSolver<SparseSymMatProd<double>> bad(op, 10, 12);
+        }
+        catch (const std::invalid_argument&)
+        {
+            thrown = true;
+        }
+        REQUIRE(thrown);
+        SymEigsSolver<SparseSymMatProd<double>> eigs(op, 3, 6);
+        std::vector<double> zero(10, 0.0);
+        thrown = false;
+        try
+        {
+            eigs.init(zero.data());
+        }
+        catch (const std::invalid_argument&)
+        {
+            thrown = true;
+        }
+        REQUIRE(thrown);
+    }
+    std::printf(fails ? "FAILED (%d)\n" : "ALL PASSED\n", fails);
+    return fails ? 1 : 0;
+}
