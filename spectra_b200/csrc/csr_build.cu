@@ -286,6 +286,125 @@ void build_device_csr(int64_t n, const void* outer, bool outer64, const int32_t*
         build_impl<int>(n, static_cast<const int*>(outer), inner, values, order, mode, row0, nrows, stream, out);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Column blocking: re-lay the (column-sorted) CSR out as nb sub-matrices over column ranges of width W
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct BlockPtrs
+{
+    int* rowptr[kMaxColBlocks];
+    int* col[kMaxColBlocks];
+    double* val[kMaxColBlocks];
+};
+
+// cnt[c * nrows + r] = number of entries of row r that fall into column block c
+__global__ void block_count_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int64_t nrows, int64_t W, int nb, int* __restrict__ cnt)
+{
+    for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int b = rowptr[r], e = rowptr[r + 1];
+        int c = 0, run = 0;
+        for (int p = b; p < e; p++)
+        {
+            const int cb = (int) (col[p] / W);
+            while (c < cb)
+            {
+                cnt[(int64_t) c * nrows + r] = run;
+                run = 0;
+                c++;
+            }
+            run++;
+        }
+        while (c < nb)
+        {
+            cnt[(int64_t) c * nrows + r] = run;
+            run = 0;
+            c++;
+        }
+    }
+}
+
+__global__ void block_fill_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, int64_t nrows, int64_t W,
+                                  BlockPtrs bp)
+{
+    for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int b = rowptr[r], e = rowptr[r + 1];
+        int c = -1, q = 0;
+        for (int p = b; p < e; p++)
+        {
+            const int cj = col[p];
+            const int cb = (int) (cj / W);
+            if (cb != c)
+            {
+                c = cb;
+                q = bp.rowptr[c][r];
+            }
+            bp.col[c][q] = cj;
+            bp.val[c][q] = val[p];
+            q++;
+        }
+    }
+}
+
+void exclusive_scan_to_rowptr(const int* cnt, int64_t nrows, int* rowptr, long long* h_total, cudaStream_t stream)
+{
+    const int nblocks = (int) ((nrows + (int64_t) kScanBlock * kScanItems - 1) / ((int64_t) kScanBlock * kScanItems));
+    DevBuf<long long> block_sums(std::max(nblocks, 1) + 1);
+    long long* d_total = block_sums.get() + std::max(nblocks, 1);
+    scan_block_sums_kernel<<<nblocks, kScanBlock, 0, stream>>>(cnt, nrows, block_sums.get());
+    scan_offsets_kernel<<<1, 1, 0, stream>>>(block_sums.get(), nblocks, d_total);
+    scan_write_kernel<<<nblocks, kScanBlock, 0, stream>>>(cnt, nrows, block_sums.get(), rowptr);
+    set_last_kernel<<<1, 1, 0, stream>>>(rowptr, nrows, d_total);
+    SB200_CUDA_CHECK(cudaGetLastError());
+    SB200_CUDA_CHECK(cudaMemcpyAsync(h_total, d_total, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+    SB200_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+}  // namespace
+
+void split_column_blocks(DeviceCsr& A, int nb, cudaStream_t stream)
+{
+    if (nb <= 1 || A.nrows == 0 || A.nnz == 0)
+        return;
+    nb = std::min(nb, kMaxColBlocks);
+    const int64_t W = (A.n + nb - 1) / nb;
+    DevBuf<int> cnt((size_t) nb * A.nrows);
+    block_count_kernel<<<grid_for(A.nrows, 128), 128, 0, stream>>>(A.rowptr.get(), A.col.get(), A.nrows, W, nb, cnt.get());
+    SB200_CUDA_CHECK(cudaGetLastError());
+    A.blocks.clear();
+    A.blocks.resize(nb);
+    BlockPtrs bp;
+    for (int c = 0; c < kMaxColBlocks; c++)
+    {
+        bp.rowptr[c] = nullptr;
+        bp.col[c] = nullptr;
+        bp.val[c] = nullptr;
+    }
+    for (int c = 0; c < nb; c++)
+    {
+        CsrBlock& B = A.blocks[c];
+        B.rowptr.alloc(A.nrows + 1);
+        long long total = 0;
+        exclusive_scan_to_rowptr(cnt.get() + (size_t) c * A.nrows, A.nrows, B.rowptr.get(), &total, stream);
+        B.nnz = total;
+        B.col.alloc(std::max<int64_t>(total, 1));
+        B.val.alloc(std::max<int64_t>(total, 1));
+        bp.rowptr[c] = B.rowptr.get();
+        bp.col[c] = B.col.get();
+        bp.val[c] = B.val.get();
+    }
+    block_fill_kernel<<<grid_for(A.nrows, 128), 128, 0, stream>>>(A.rowptr.get(), A.col.get(), A.val.get(), A.nrows, W, bp);
+    SB200_CUDA_CHECK(cudaGetLastError());
+    SB200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    A.col_block_width = W;
+    // the unblocked copy is no longer needed
+    A.rowptr.release();
+    A.col.release();
+    A.val.release();
+}
+
 void upload_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64_t* rowptr_local, const int32_t* col, const double* values, cudaStream_t stream,
                      DeviceCsr& out)
 {

@@ -5,11 +5,17 @@
 //                                  HermEigsBase.h:205-224, :158-175, :178-202, :105-147
 // so the whole restart decision stays on the device; the host reads back one 16-byte status.
 //
-// Parallelisation: the scalar recurrences (rotation generation on the tridiagonal) are inherently
-// sequential and run on thread 0; applying a sweep of rotations to the m x m eigenvector / Q
-// matrix is row-parallel (thread t owns row t, matrix column-major in shared memory so a warp
-// touches consecutive addresses).  The tridiagonal H is carried as (diag, subdiag) in shared
-// memory.
+// Parallelisation.  The scalar recurrences on the tridiagonal (rotation generation, deflation
+// tests, shift strategy) are inherently sequential: thread 0 runs them back to back WITHOUT block
+// synchronisation and appends every rotation to a log in shared memory.  Applying rotations to the
+// m x m eigenvector / Q matrix is row-local, so when the log fills up (or the sequence ends) all
+// threads replay it on their own row (matrix column-major in shared memory: a warp touches
+// consecutive addresses).  The tridiagonal H is carried as (diag, subdiag) in shared memory.
+//
+// Arithmetic notes: rotations on the max-scaled iteration matrix use one reciprocal square root
+// (c = p/r, s = -q/r, the closed form of Eigen's makeGivens); Givens<double>::compute_rotation keeps
+// the reference's Taylor branch for tiny ratios and uses the same rsqrt form otherwise, falling back
+// to the reference's hypot formulation outside the safe exponent range.
 #include "dense_common.cuh"
 #include "kernels.h"
 
@@ -20,17 +26,22 @@ namespace {
 using namespace dense;
 
 constexpr int kDenseBlock = 128;
+constexpr int kLogCap = 4096;   // rotations per log chunk
+constexpr int kSweepCap = 512;  // sweeps per log chunk
 
 struct TriShared
 {
     double* d;    // working diag        [m]
     double* e;    // working subdiag     [m]
-    double* rc;   // rotation cosines    [m]
-    double* rs;   // rotation sines      [m]
+    double* t1;   // scratch             [m]
+    double* t2;   // scratch             [m]
     double* ev;   // eigenvalues / keys  [m]
     double* aux;  // scratch             [m]
     int* idx;     // sort permutation    [m]
     double* Z;    // m x m
+    double* lc;   // rotation log: cosines [kLogCap]
+    double* ls;   // rotation log: sines   [kLogCap]
+    int* hdr;     // sweep log: (first column, count, offset) triples [3 * kSweepCap]
 };
 
 __device__ __forceinline__ TriShared carve(double* smem, int m)
@@ -38,19 +49,59 @@ __device__ __forceinline__ TriShared carve(double* smem, int m)
     TriShared s;
     s.d = smem;
     s.e = s.d + m;
-    s.rc = s.e + m;
-    s.rs = s.rc + m;
-    s.ev = s.rs + m;
+    s.t1 = s.e + m;
+    s.t2 = s.t1 + m;
+    s.ev = s.t2 + m;
     s.aux = s.ev + m;
-    s.idx = reinterpret_cast<int*>(s.aux + m);
-    s.Z = reinterpret_cast<double*>(s.idx + 2 * ((m + 1) / 2));
+    s.Z = s.aux + m;
+    s.lc = s.Z + m * m;
+    s.ls = s.lc + kLogCap;
+    s.idx = reinterpret_cast<int*>(s.ls + kLogCap);
+    s.hdr = s.idx + 2 * ((m + 1) / 2);
     return s;
 }
-size_t tri_smem_bytes(int m) { return sizeof(double) * (size_t) (6 * m + m * m) + sizeof(int) * (size_t) (2 * ((m + 1) / 2)); }
+size_t tri_smem_bytes(int m)
+{
+    return sizeof(double) * (size_t) (6 * m + m * m + 2 * kLogCap) + sizeof(int) * (size_t) (2 * ((m + 1) / 2) + 3 * kSweepCap);
+}
+
+// makeGivens for the scaled QR iteration: entries are <= 1 in magnitude (TridiagEigen.h:139-152), so
+// p^2 + q^2 cannot overflow; both branches of Eigen's makeGivens reduce to c = p/r, s = -q/r with
+// r = +sqrt(p^2 + q^2).
+__device__ __forceinline__ void make_givens_scaled(double p, double q, double& c, double& s)
+{
+    const double n2 = fma(p, p, q * q);
+    if (q == 0.0 || p == 0.0 || n2 < 1e-280)
+    {
+        make_givens(p, q, c, s);
+        return;
+    }
+    const double inv = rsqrt(n2);
+    c = p * inv;
+    s = -q * inv;
+}
+
+// Givens<double>::compute_rotation (Givens.h:166-205) with the rsqrt form for the regular case.
+__device__ __forceinline__ void givens_rotation_fast(double x, double y, double& r, double& c, double& s)
+{
+    const double xabs = fabs(x), yabs = fabs(y);
+    const double hi = fmax(xabs, yabs), lo = fmin(xabs, yabs);
+    const double cutoff = 0.1 * 1.220703125e-4;
+    if (x == 0.0 || y == 0.0 || lo < cutoff * hi || hi > 1e140 || hi < 1e-140)
+    {
+        givens_rotation(x, y, r, c, s);  // exact special cases, Taylor branch, extreme magnitudes
+        return;
+    }
+    const double n2 = fma(x, x, y * y);
+    const double inv = rsqrt(n2);
+    r = n2 * inv;  // sqrt(x^2 + y^2) >= 0
+    c = x * inv;   // c = x / r
+    s = -y * inv;  // s = -y / r
+}
 
 // One implicit Wilkinson-shift QR step on rows start..end of the (scaled) tridiagonal (thread 0).
-// Stores the rotations in rc/rs[start .. start+nrot) and returns nrot.   TridiagEigen.h:44-108
-__device__ int tridiagonal_qr_step(double* diag, double* subdiag, int start, int end, double* rc, double* rs)
+// Appends the rotations to (lc, ls) and returns their number.   TridiagEigen.h:44-108
+__device__ int tridiagonal_qr_step(double* diag, double* subdiag, int start, int end, double* lc, double* ls)
 {
     const double td = (diag[end - 1] - diag[end]) * 0.5;
     const double e = subdiag[end - 1];
@@ -68,36 +119,65 @@ __device__ int tridiagonal_qr_step(double* diag, double* subdiag, int start, int
     }
     double x = diag[start] - mu;
     double z = subdiag[start];
+    // running copies of the entries the next rotation touches
+    double dk = diag[start], ek = subdiag[start];
     int nrot = 0;
     for (int k = start; k < end && z != 0.0; ++k)
     {
         double c, s;
-        make_givens(x, z, c, s);
-        const double sdk = s * diag[k] + c * subdiag[k];
-        const double dkp1 = s * subdiag[k] + c * diag[k + 1];
-        diag[k] = c * (c * diag[k] - s * subdiag[k]) - s * (c * subdiag[k] - s * diag[k + 1]);
-        diag[k + 1] = s * sdk + c * dkp1;
-        subdiag[k] = c * sdk - s * dkp1;
+        make_givens_scaled(x, z, c, s);
+        const double dk1 = diag[k + 1];
+        const double sdk = s * dk + c * ek;
+        const double dkp1 = s * ek + c * dk1;
+        diag[k] = c * (c * dk - s * ek) - s * (c * ek - s * dk1);
+        const double ndk1 = s * sdk + c * dkp1;
+        const double nek = c * sdk - s * dkp1;
+        subdiag[k] = nek;
         if (k > start)
             subdiag[k - 1] = c * subdiag[k - 1] - s * z;
-        x = subdiag[k];
+        x = nek;
         if (k < end - 1)
         {
-            z = -s * subdiag[k + 1];
-            subdiag[k + 1] = c * subdiag[k + 1];
+            const double ek1 = subdiag[k + 1];
+            z = -s * ek1;
+            ek = c * ek1;
+            subdiag[k + 1] = ek;
         }
-        rc[k] = c;
-        rs[k] = s;
+        dk = ndk1;
+        diag[k + 1] = ndk1;
+        lc[nrot] = c;
+        ls[nrot] = s;
         nrot++;
     }
     return nrot;
+}
+
+// All threads: replay the logged sweeps on their row of Z (q.applyOnTheRight, TridiagEigen.h:106).
+__device__ void replay_sweeps(double* Z, int m, const double* lc, const double* ls, const int* hdr, int nsweeps)
+{
+    for (int t = threadIdx.x; t < m; t += kDenseBlock)
+    {
+        for (int sw = 0; sw < nsweeps; sw++)
+        {
+            const int st = hdr[3 * sw], nr = hdr[3 * sw + 1], off = hdr[3 * sw + 2];
+            double xk = Z[t + st * m];
+            for (int k = 0; k < nr; k++)
+            {
+                const double c = lc[off + k], s = ls[off + k];
+                const double yk = Z[t + (st + k + 1) * m];
+                Z[t + (st + k) * m] = c * xk - s * yk;
+                xk = s * xk + c * yk;
+            }
+            Z[t + (st + nr) * m] = xk;
+        }
+    }
 }
 
 // TridiagEigen::compute on (hd, he) = diag / subdiag of H.  On exit sh.ev = eigenvalues (unsorted),
 // sh.Z = eigenvectors.  Returns 0 on success, 1 when the 30*m sweep cap is hit.  Block-collective.
 __device__ int tridiag_eigen_block(const double* hd, const double* he, int m, TriShared& sh)
 {
-    __shared__ int s_state[4];  // 0: action (0 stop, 1 apply), 1: start, 2: nrot, 3: info
+    __shared__ int s_state[4];  // 0: more work after this chunk, 1: sweeps in chunk, 3: info
     __shared__ double s_scale;
     const int tid = threadIdx.x;
     for (int t = tid; t < m * m; t += kDenseBlock)
@@ -110,6 +190,7 @@ __device__ int tridiag_eigen_block(const double* hd, const double* he, int m, Tr
         for (int i = 0; i < m - 1; i++)
             scale = fmax(scale, fabs(he[i]));
         s_scale = scale;
+        s_state[3] = 0;
     }
     __syncthreads();
     const double scale = s_scale;
@@ -126,13 +207,9 @@ __device__ int tridiag_eigen_block(const double* hd, const double* he, int m, Tr
         if (t < m - 1)
             sh.e[t] = he[t] / scale;
     }
-    if (tid == 0)
-    {
-        s_state[3] = 0;
-    }
     __syncthreads();
 
-    // thread-0 loop state lives in registers of thread 0; other threads follow s_state
+    // loop state lives in registers of thread 0; the other threads follow s_state
     int end = m - 1, start = 0, iter = 0;
     const double considerAsZero = kMin;
     const double precision_inv = 1.0 / kEps;
@@ -140,16 +217,22 @@ __device__ int tridiag_eigen_block(const double* hd, const double* he, int m, Tr
     {
         if (tid == 0)
         {
-            int action = 0;
+            int nlog = 0, nsw = 0, more = 0;
             while (end > 0)
             {
+                if (nlog + m > kLogCap || nsw >= kSweepCap)
+                {
+                    more = 1;  // log full: replay, then continue
+                    break;
+                }
                 for (int i = start; i < end; i++)
                 {
-                    if (fabs(sh.e[i]) <= considerAsZero)
+                    const double ei = sh.e[i];
+                    if (fabs(ei) <= considerAsZero)
                         sh.e[i] = 0.0;
                     else
                     {
-                        const double scaled = precision_inv * sh.e[i];
+                        const double scaled = precision_inv * ei;
                         if (scaled * scaled <= (fabs(sh.d[i]) + fabs(sh.d[i + 1])))
                             sh.e[i] = 0.0;
                     }
@@ -167,35 +250,25 @@ __device__ int tridiag_eigen_block(const double* hd, const double* he, int m, Tr
                 start = end - 1;
                 while (start > 0 && sh.e[start - 1] != 0.0)
                     start--;
-                const int nrot = tridiagonal_qr_step(sh.d, sh.e, start, end, sh.rc, sh.rs);
+                const int nrot = tridiagonal_qr_step(sh.d, sh.e, start, end, sh.lc + nlog, sh.ls + nlog);
                 if (nrot > 0)
                 {
-                    s_state[1] = start;
-                    s_state[2] = nrot;
-                    action = 1;
-                    break;
+                    sh.hdr[3 * nsw] = start;
+                    sh.hdr[3 * nsw + 1] = nrot;
+                    sh.hdr[3 * nsw + 2] = nlog;
+                    nsw++;
+                    nlog += nrot;
                 }
             }
-            s_state[0] = action;
+            s_state[0] = more;
+            s_state[1] = nsw;
         }
         __syncthreads();
-        if (s_state[0] == 0)
+        replay_sweeps(sh.Z, m, sh.lc, sh.ls, sh.hdr, s_state[1]);
+        const int more = s_state[0];
+        __syncthreads();
+        if (!more)
             break;
-        const int st = s_state[1], nrot = s_state[2];
-        // q.applyOnTheRight(k, k+1, rot)  (TridiagEigen.h:106): row t of Z
-        for (int t = tid; t < m; t += kDenseBlock)
-        {
-            double xk = sh.Z[t + st * m];
-            for (int k = st; k < st + nrot; k++)
-            {
-                const double c = sh.rc[k], s = sh.rs[k];
-                const double yk = sh.Z[t + (k + 1) * m];
-                sh.Z[t + k * m] = c * xk - s * yk;
-                xk = s * xk + c * yk;
-            }
-            sh.Z[t + (st + nrot) * m] = xk;
-        }
-        __syncthreads();
     }
     const int info = s_state[3];
     for (int t = tid; t < m; t += kDenseBlock)
@@ -218,23 +291,21 @@ __device__ void tridiag_qr_step_scalar(double* d, double* e, int m, double mu, d
         rdiag[i] = d[i] - mu;
     for (int i = 0; i < n1; i++)
         rsupd[i] = e[i];
+    double rd = rdiag[0];
     for (int i = 0; i < n1; i++)
     {
         double r, c, s;
-        givens_rotation(rdiag[i], e[i], r, c, s);
+        givens_rotation_fast(rd, e[i], r, c, s);
         rc[i] = c;
         rs[i] = s;
-        rdiag[i] = r;
         const double Tii1 = rsupd[i];
         const double Ti1i1 = rdiag[i + 1];
-        rsupd[i] = c * Tii1 - s * Ti1i1;
-        rdiag[i + 1] = s * Tii1 + c * Ti1i1;
+        rd = s * Tii1 + c * Ti1i1;  // R[i+1, i+1]
         if (i < n2)
             rsupd[i + 1] *= c;
     }
-    // Q'TQ applied to T directly (:627-693).  dest(i+1,i) lives in e[i]; o' needs the ORIGINAL
+    // Q'TQ applied to T directly (:627-693).  dest(i+1,i) lives in e[i]; o' needs the original
     // (deflated) T_subd(i+1), which is read before e[i+1] is overwritten.
-    double e_next_orig = (n1 > 0) ? e[0] : 0.0;
     for (int i = 0; i < n1; i++)
     {
         const double c = rc[i], s = rs[i];
@@ -245,14 +316,13 @@ __device__ void tridiag_qr_step_scalar(double* d, double* e, int m, double mu, d
         d[i] = c2x - csy2 + s2z;
         e[i] = cs * (x - z) + (c2 - s2) * y;
         d[i + 1] = s2x + csy2 + c2z;
-        (void) e_next_orig;
         if (i < n2)
         {
             const double ci1 = rc[i + 1], si1 = rs[i + 1];
-            const double tsub = e[i + 1];      // m_T_subd[i+1] (still original here)
-            const double o = -s * tsub;        // o'
-            e[i + 1] = tsub * c;               // w' = dest(i+2,i+1) *= c
-            e[i] = ci1 * e[i] - si1 * o;       // y''
+            const double tsub = e[i + 1];  // m_T_subd[i+1] (still original here)
+            const double o = -s * tsub;    // o'
+            e[i + 1] = tsub * c;           // w' = dest(i+2,i+1) *= c
+            e[i] = ci1 * e[i] - si1 * o;   // y''
         }
     }
     for (int i = 0; i < n1; i++)
@@ -260,20 +330,25 @@ __device__ void tridiag_qr_step_scalar(double* d, double* e, int m, double mu, d
             e[i] = 0.0;
 }
 
-// Y <- Y Q for the rotation sequence rc/rs (UpperHessenbergQR.h:383-417), row-parallel.
-__device__ void apply_yq_block(double* Y, int m, const double* rc, const double* rs)
+// Y <- Y Q for nseq consecutive rotation sequences of m-1 rotations each (UpperHessenbergQR.h:383-417)
+__device__ void apply_yq_block(double* Y, int m, const double* lc, const double* ls, int nseq)
 {
     for (int t = threadIdx.x; t < m; t += kDenseBlock)
     {
-        double yi = Y[t];
-        for (int i = 0; i < m - 1; i++)
+        for (int q = 0; q < nseq; q++)
         {
-            const double c = rc[i], s = rs[i];
-            const double yi1 = Y[t + (i + 1) * m];
-            Y[t + i * m] = c * yi - s * yi1;
-            yi = s * yi + c * yi1;
+            const double* rc = lc + q * (m - 1);
+            const double* rs = ls + q * (m - 1);
+            double yi = Y[t];
+            for (int i = 0; i < m - 1; i++)
+            {
+                const double c = rc[i], s = rs[i];
+                const double yi1 = Y[t + (i + 1) * m];
+                Y[t + i * m] = c * yi - s * yi1;
+                yi = s * yi + c * yi1;
+            }
+            Y[t + (m - 1) * m] = yi;
         }
-        Y[t + (m - 1) * m] = yi;
     }
 }
 
@@ -303,7 +378,7 @@ __global__ void __launch_bounds__(kDenseBlock)
         argsort_keys(sh.aux, sh.idx, m);
         if (selection == SB200_BOTH_ENDS)  // SelectionRule.h:272-284
         {
-            int* tmp = reinterpret_cast<int*>(sh.rc);
+            int* tmp = reinterpret_cast<int*>(sh.t1);
             for (int i = 0; i < m; i++)
                 tmp[i] = sh.idx[i];
             for (int i = 0; i < m; i++)
@@ -318,7 +393,7 @@ __global__ void __launch_bounds__(kDenseBlock)
         const double re = sh.Z[(m - 1) + id * m];
         ritz_val[t] = rv;
         ritz_est[t] = re;
-        sh.d[t] = rv;   // keep sorted Ritz values / estimates for the scalar logic below
+        sh.d[t] = rv;  // keep sorted Ritz values / estimates for the scalar logic below
         sh.e[t] = re;
     }
     for (int t = tid; t < m * nev; t += kDenseBlock)
@@ -378,16 +453,19 @@ __global__ void __launch_bounds__(kDenseBlock)
         for (int i = 0; i < nshift; i++)
             shifts[i] = sh.d[k + sh.idx[i]];
     }
-    // Q = I in the (now free) Z buffer; working tridiagonal back to (s_hd, s_he)
+    // Q = I in the (now free) Z buffer; the working tridiagonal is (s_hd, s_he)
     for (int t = tid; t < m * m; t += kDenseBlock)
         sh.Z[t] = ((t % m) == (t / m)) ? 1.0 : 0.0;
     __syncthreads();
-    for (int ish = 0; ish < nshift; ish++)
+    const int per_chunk = max(1, kLogCap / (m - 1));  // shifts whose rotations fit into one log chunk
+    for (int ish0 = 0; ish0 < nshift; ish0 += per_chunk)
     {
+        const int cnt = min(per_chunk, nshift - ish0);
         if (tid == 0)
-            tridiag_qr_step_scalar(s_hd, s_he, m, shifts[ish], sh.rc, sh.rs, sh.d, sh.e);
+            for (int q = 0; q < cnt; q++)
+                tridiag_qr_step_scalar(s_hd, s_he, m, shifts[ish0 + q], sh.lc + q * (m - 1), sh.ls + q * (m - 1), sh.d, sh.e);
         __syncthreads();
-        apply_yq_block(sh.Z, m, sh.rc, sh.rs);
+        apply_yq_block(sh.Z, m, sh.lc, sh.ls, cnt);
         __syncthreads();
     }
     // write back Q and the (untrimmed) tridiagonal H
@@ -442,9 +520,9 @@ __global__ void __launch_bounds__(kDenseBlock) tridiag_qr_kernel(const double* H
         sh.Z[t] = ((t % m) == (t / m)) ? 1.0 : 0.0;
     __syncthreads();
     if (threadIdx.x == 0)
-        tridiag_qr_step_scalar(s_hd, s_he, m, shift, sh.rc, sh.rs, sh.d, sh.e);
+        tridiag_qr_step_scalar(s_hd, s_he, m, shift, sh.lc, sh.ls, sh.d, sh.e);
     __syncthreads();
-    apply_yq_block(sh.Z, m, sh.rc, sh.rs);
+    apply_yq_block(sh.Z, m, sh.lc, sh.ls, 1);
     __syncthreads();
     for (int t = threadIdx.x; t < m * m; t += kDenseBlock)
     {

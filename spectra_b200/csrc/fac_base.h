@@ -194,15 +194,21 @@ struct FacBase
         stats.spmv_launches++;
         nmatop++;
     }
-    void panel(int mode, int j, const double* x, double* fo, const double* coef)
+    void panel(int mode, int j, const double* x, double* fo, const double* coef, const int* pred = nullptr)
     {
         stats.panel_launches++;
         stats.panel_cols += j;
         {
             ScopedKernelTimer t(&prof, stream(), KC_PANEL);
-            launch_panel_pass(mode, V.get(), ld, nloc, j, x, fo, coef, ctl.get()->red, rs, stream());
+            launch_panel_pass(mode, V.get(), ld, nloc, j, x, fo, coef, ctl.get()->red, rs, stream(), pred);
         }
         allreduce_sum(ctl.get()->red, kRedNrm + 1);
+    }
+    // A speculatively enqueued pass turned out to be skipped on the device: undo its accounting.
+    void uncount_panel(int j)
+    {
+        stats.panel_launches--;
+        stats.panel_cols -= j;
     }
     // host copy of red[0..j) and red[kRedNrm]
     void fetch_red(int j, double& ortho_err, double& nrm2)

@@ -41,6 +41,15 @@ struct RedScratch
 };
 
 // ---- CSR build (csr_build.cu) -----------------------------------------------------------------
+constexpr int kMaxColBlocks = 16;
+// One column block of the operand: a CSR of its own over columns [c0, c1).
+struct CsrBlock
+{
+    int64_t nnz = 0;
+    DevBuf<int> rowptr;   // nrows + 1
+    DevBuf<int> col;      // nnz (global column ids)
+    DevBuf<double> val;   // nnz
+};
 struct DeviceCsr
 {
     int64_t n = 0;        // global order
@@ -50,7 +59,14 @@ struct DeviceCsr
     DevBuf<int> rowptr;   // nrows + 1
     DevBuf<int> col;      // nnz (global column ids)
     DevBuf<double> val;   // nnz
+    // Column blocking (large n): when the gathered operand x (8n bytes) does not fit in L2, the matrix is
+    // re-laid out as `blocks.size()` CSR sub-matrices of `col_block_width` columns each, processed one after
+    // the other so that each pass gathers from an L2-resident slice of x.  Empty => single block above.
+    std::vector<CsrBlock> blocks;
+    int64_t col_block_width = 0;
 };
+// Re-lays the CSR out in nblocks column blocks (frees the unblocked arrays).  No-op for nblocks <= 1.
+void split_column_blocks(DeviceCsr& A, int nblocks, cudaStream_t stream);
 // Builds the full CSR (columns ascending in each row, duplicates summed) from host compressed
 // arrays.  mode/order as in sb200_matrix_mode / sb200_storage_order.  Keeps rows [row0,row0+nrows).
 void build_device_csr(int64_t n, const void* outer, bool outer64, const int32_t* inner, const double* values, int order, int mode, int64_t row0, int64_t nrows,
@@ -65,6 +81,8 @@ struct SpmvPlan
     int grid = 0;
 };
 SpmvPlan make_spmv_plan(const DeviceCsr& A);
+// column blocks needed so that one slice of the gathered operand stays L2-resident (env SB200_XSLICE_MB)
+int choose_col_blocks(int64_t n);
 // y = A x   (x: full vector of A.n entries, y: A.nrows)
 void launch_spmv(const DeviceCsr& A, const SpmvPlan& plan, const double* x, double* y, cudaStream_t stream);
 // Fused Lanczos/Arnoldi step head (K-A):  V[:,i] = f_loc/beta;  w = (A x)/beta - hsub*V[:,i-1]
@@ -85,16 +103,17 @@ enum PanelMode
 // j = number of panel columns (<= kPanelMaxCols) is read from ctl->i + 1 when j_host < 0.
 // x: input vector (w for FORM, f or w for CORR/DOT), f_out: output residual (may alias x).
 // coef: device pointer to the coefficients (CORR) or to alpha (FORM).
+// pred (optional): device flag; the kernel is a no-op when *pred == 0 (speculatively enqueued correction pass).
 void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out,
-                       const RedScratch& rs, cudaStream_t stream);
+                       const RedScratch& rs, cudaStream_t stream, const int* pred = nullptr);
 
 // Decide kernels: consume ctl->red after a panel pass (and after the all-reduce when sharded).
 //  first = 1: after the FORM pass of a Lanczos step; first = 0: after a CORR pass (also applies
 //  the H update of Lanczos.h:172-175 with the coefficients that were just used).
-void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int first, cudaStream_t stream);
+void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int first, cudaStream_t stream, int predicated = 0);
 // Arnoldi flavours (Arnoldi.h:242-290): stage 0 = after h = V^T w (copies h into H(:,i) and c),
 // stage 1 = after f = w - V h (DGKS test), stage 2 = after a correction pass.
-void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream);
+void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated = 0);
 
 // ---- restart GEMM (panel.cu) ------------------------------------------------------------------------
 // Vout[:, c] = sum_j V[:, j] * Q[j, c]  for c < kk  (Q: m x m column-major on device, ldq = m).

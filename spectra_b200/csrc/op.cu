@@ -70,6 +70,7 @@ namespace sb200 {
 
 static void finish_op(sb200_op* op)
 {
+    split_column_blocks(op->A, choose_col_blocks(op->A.n), op->stream);
     op->plan = make_spmv_plan(op->A);
     const int P = op->nranks();
     op->slab = (op->A.n + P - 1) / P;

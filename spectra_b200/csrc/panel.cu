@@ -29,8 +29,11 @@ constexpr int kColsPerGroup = 16;
 template <int NG, int MODE>
 __global__ void __launch_bounds__(kPanelBlock, 2)
     panel_kernel(const double* __restrict__ V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* __restrict__ coef,
-                 double* red_out, double* partials, unsigned int* ticket)
+                 double* red_out, double* partials, unsigned int* ticket, const int* pred)
 {
+    // speculatively enqueued pass: skip when the device-side flag says no correction is needed
+    if (pred != nullptr && *pred == 0)
+        return;
     constexpr int RS = 8 / NG;        // row slices
     constexpr int RPI = RS * 64;      // rows per CTA iteration
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -168,14 +171,14 @@ __global__ void __launch_bounds__(kPanelBlock, 2)
 
 template <int MODE>
 void launch_panel_mode(const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out, int grid,
-                       const RedScratch& rs, cudaStream_t stream)
+                       const RedScratch& rs, const int* pred, cudaStream_t stream)
 {
     if (j <= 16)
-        panel_kernel<1, MODE><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket);
+        panel_kernel<1, MODE><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
     else if (j <= 32)
-        panel_kernel<2, MODE><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket);
+        panel_kernel<2, MODE><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
     else
-        panel_kernel<4, MODE><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket);
+        panel_kernel<4, MODE><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -197,8 +200,10 @@ __device__ __forceinline__ double panel_max_abs(const double* red, int j, int la
     return warp_max(mx);
 }
 
-__global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int first)
+__global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int first, int predicated)
 {
+    if (predicated && ctl->need_corr == 0)
+        return;  // the speculative correction pass was skipped
     const int lane = threadIdx.x;
     const int i = ctl->i, j = i + 1;
     int count = ctl->count;
@@ -242,8 +247,10 @@ __global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta
     }
 }
 
-__global__ void arnoldi_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int stage)
+__global__ void arnoldi_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, int predicated)
 {
+    if (predicated && ctl->need_corr == 0)
+        return;
     const int lane = threadIdx.x;
     const int i = ctl->i, j = i + 1;
     if (stage == 0)
@@ -374,7 +381,7 @@ __global__ void __launch_bounds__(kGemmBlock)
 }  // namespace
 
 void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out,
-                       const RedScratch& rs, cudaStream_t stream)
+                       const RedScratch& rs, cudaStream_t stream, const int* pred)
 {
     SB200_REQUIRE(j >= 1 && j <= kPanelMaxCols, SB200_INVALID_ARGUMENT, "panel width must be in [1, 64]");
     const int sms = device_info().sm_count;
@@ -385,23 +392,23 @@ void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, in
     SB200_REQUIRE(grid <= rs.max_grid, SB200_LOGIC, "panel: reduction scratch too small");
     switch (mode)
     {
-        case PANEL_DOT: launch_panel_mode<PANEL_DOT>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, stream); break;
-        case PANEL_FORM: launch_panel_mode<PANEL_FORM>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, stream); break;
-        case PANEL_CORR: launch_panel_mode<PANEL_CORR>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, stream); break;
+        case PANEL_DOT: launch_panel_mode<PANEL_DOT>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream); break;
+        case PANEL_FORM: launch_panel_mode<PANEL_FORM>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream); break;
+        case PANEL_CORR: launch_panel_mode<PANEL_CORR>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream); break;
         default: throw Error(SB200_LOGIC, "bad panel mode");
     }
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int first, cudaStream_t stream)
+void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int first, cudaStream_t stream, int predicated)
 {
-    lanczos_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, first);
+    lanczos_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, first, predicated);
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream)
+void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated)
 {
-    arnoldi_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage);
+    arnoldi_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage, predicated);
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -79,15 +79,21 @@ struct sb200_gen_solver : public FacBase
             panel(PANEL_CORR, j, w.get(), f.get(), ctl.get()->c);
             launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream());
             prof.launches += 2;
+            // correction passes (:266-290); the first one is enqueued speculatively (device-side predicate)
+            panel(PANEL_CORR, j, f.get(), f.get(), ctl.get()->c, &ctl.get()->need_corr);
+            launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 2, stream(), 1);
+            prof.launches++;
             const FacCtl* st = read_status();
+            if (st->count == 0)
+                uncount_panel(j);
             while (st->need_corr)
             {
-                stats.reorth_passes++;
                 panel(PANEL_CORR, j, f.get(), f.get(), ctl.get()->c);  // (:281-287)
                 launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 2, stream());
                 prof.launches++;
                 st = read_status();
             }
+            stats.reorth_passes += st->count;
             if (st->f_zeroed)
                 f.zero(stream());
             h_beta = st->beta;

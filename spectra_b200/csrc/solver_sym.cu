@@ -95,17 +95,22 @@ struct sb200_sym_solver : public FacBase
             const int j = i + 1;
             panel(PANEL_FORM, j, w.get(), f.get(), ctl.get()->red_a);
             launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream());
-            prof.launches++;
+            // K-C: iterative correction (Lanczos.h:156-182).  In practice exactly one pass is needed per step, so the
+            // first one is enqueued speculatively, predicated on the device-side flag, before the host looks at the status.
+            panel(PANEL_CORR, j, f.get(), f.get(), ctl.get()->c, &ctl.get()->need_corr);
+            launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 1);
+            prof.launches += 2;
             const FacCtl* st = read_status();
-            // K-C: iterative correction (Lanczos.h:156-182)
+            if (st->count == 0)
+                uncount_panel(j);
             while (st->need_corr)
             {
-                stats.reorth_passes++;
                 panel(PANEL_CORR, j, f.get(), f.get(), ctl.get()->c);
                 launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream());
                 prof.launches++;
                 st = read_status();
             }
+            stats.reorth_passes += st->count;
             if (st->f_zeroed)
                 f.zero(stream());
             h_beta = st->beta;

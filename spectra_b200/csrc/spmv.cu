@@ -8,9 +8,18 @@
 // Layout: full CSR in HBM, int32 row pointers / column ids, fp64 values, columns ascending in a
 // row.  A sub-warp of L lanes owns one row: the L lanes read consecutive (col, val) pairs, so a
 // warp reads one contiguous slab of the CSR arrays per iteration (coalesced), gathers x through
-// the read-only path and combines with log2(L) shuffles.  CSR streams are read with
-// L1::no_allocate + L2 evict_first so that the gathered vector x (8n bytes) stays L2-resident.
-// Algorithmic bytes per row at d nnz/row: 12 d + 4 + 8 (x once) + 8 (y)  (SURVEY §8d).
+// the read-only path and combines with log2(L) shuffles.  One warp owns 32 consecutive rows and
+// routes the row sums to lane (row - row0) so that the epilogue is coalesced.  CSR streams are
+// read with L1::no_allocate + L2 evict_first, the gathered vector x with evict_last.
+//
+// Column blocking: when x (8n bytes) exceeds the L2 budget the operand is stored as several CSR
+// sub-matrices over column ranges (csr_build.cu: split_column_blocks) and one launch per block
+// accumulates into y, so every pass gathers from an L2-resident slice of x instead of DRAM
+// (measured at n = 1e7 unblocked: 7.4 GB of DRAM reads per SpMV for 2.76 GB of algorithmic bytes).
+// Algorithmic bytes per row at d nnz/row: 12 d + 4 + 8 (x once) + 8 (y)  (SURVEY §8d); blocking adds
+// 4 (row pointer) + 16 (y read-modify-write) bytes per row per extra block.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace sb200 {
@@ -19,9 +28,9 @@ namespace {
 
 constexpr int kSpmvBlock = 256;
 
-template <int L>
 // All 32 lanes of a warp must call this together (sub-warp shuffle with a full mask); a sub-warp whose
 // row is out of range passes start == end.
+template <int L>
 __device__ __forceinline__ double row_dot(int start, int end, const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
                                           int lane, uint64_t pol_stream, uint64_t pol_keep)
 {
@@ -48,55 +57,87 @@ __device__ __forceinline__ double row_dot(int start, int end, const int* __restr
     return subwarp_sum<L>(acc);
 }
 
+// One warp owns 32 consecutive rows: L iterations of 32/L rows.  The row sums are routed by one
+// shuffle per iteration so that lane j ends up with the sum of row (row0 + j); the epilogue (stores,
+// the fused Lanczos head) then runs with all 32 lanes on consecutive rows, i.e. coalesced and without
+// the 4-of-32-lane divergence a per-sub-warp epilogue would have.
 template <int L>
+__device__ __forceinline__ double warp_rows_dot(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
+                                                const double* __restrict__ x, int64_t row0, int64_t nrows, int wlane, uint64_t pol_stream, uint64_t pol_keep)
+{
+    constexpr int RPW = 32 / L;  // rows per warp iteration
+    const int lane = wlane % L, sub = wlane / L;
+    // row pointers of the 32-row block: one coalesced load + one extra element
+    const int64_t rmine = row0 + wlane;
+    const int rp = __ldg(rowptr + (rmine <= nrows ? rmine : nrows));
+    const int64_t rlast = row0 + 32;
+    const int rp_hi = __ldg(rowptr + (rlast <= nrows ? rlast : nrows));
+    double mine = 0.0;
+#pragma unroll
+    for (int it = 0; it < L; it++)
+    {
+        const int j = it * RPW + sub;  // row index inside the block handled by this sub-warp
+        const int start = __shfl_sync(0xffffffffu, rp, j);
+        const int endn = __shfl_sync(0xffffffffu, rp, (j + 1) & 31);
+        const int end = (j == 31) ? rp_hi : endn;
+        const double sres = row_dot<L>(start, end, col, val, x, lane, pol_stream, pol_keep);
+        const double t = __shfl_sync(0xffffffffu, sres, (wlane % RPW) * L);
+        if (wlane / RPW == it)
+            mine = t;
+    }
+    return mine;
+}
+
+// y = (ACCUM ? y : 0) + A_block x
+template <int L, bool ACCUM>
 __global__ void __launch_bounds__(kSpmvBlock) spmv_plain_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
-                                                                const double* __restrict__ x, double* __restrict__ y, int64_t nrows)
+                                                                const double* __restrict__ x, double* y, int64_t nrows)
 {
     const uint64_t pol_stream = l2_policy_evict_first();
     const uint64_t pol_keep = l2_policy_evict_last();
-    constexpr int RPB = kSpmvBlock / L;  // rows per CTA per iteration
-    const int lane = threadIdx.x % L;
-    const int sub = threadIdx.x / L;
-    // the loop bound is CTA-uniform so that every warp executes the shuffles with all 32 lanes
-    for (int64_t rbase = (int64_t) blockIdx.x * RPB; rbase < nrows; rbase += (int64_t) gridDim.x * RPB)
+    const int wlane = threadIdx.x & 31;
+    const int64_t warp = (int64_t) blockIdx.x * (kSpmvBlock / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t) gridDim.x * (kSpmvBlock / 32);
+    for (int64_t row0 = warp * 32; row0 < nrows; row0 += nwarps * 32)
     {
-        const int64_t row = rbase + sub;
-        const bool active = row < nrows;
-        const int start = active ? __ldg(rowptr + row) : 0;
-        const int end = active ? __ldg(rowptr + row + 1) : 0;
-        const double s = row_dot<L>(start, end, col, val, x, lane, pol_stream, pol_keep);
-        if (active && lane == 0)
+        double s = warp_rows_dot<L>(rowptr, col, val, x, row0, nrows, wlane, pol_stream, pol_keep);
+        const int64_t row = row0 + wlane;
+        if (row < nrows)
+        {
+            if (ACCUM)
+                s += y[row];
             y[row] = s;
+        }
     }
 }
 
-// Fused step head.  x_full: un-normalised residual (all n entries), f_loc: this rank's rows of it.
-template <int L, bool SYM>
+// Fused step head on the LAST column block.  x_full: un-normalised residual (all n entries), f_loc: this
+// rank's rows of it.  ACCUM: w already holds the partial product of the previous column blocks.
+template <int L, bool SYM, bool ACCUM>
 __global__ void __launch_bounds__(kSpmvBlock)
     spmv_step_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x_full,
-                     const double* __restrict__ f_loc, double* __restrict__ V, int64_t ldv, double* __restrict__ w, int64_t nrows, FacCtl* ctl, double* H, int m,
-                     int i, int restarted, double* partials, unsigned int* ticket)
+                     const double* __restrict__ f_loc, double* __restrict__ V, int64_t ldv, double* w, int64_t nrows, FacCtl* ctl, double* H, int m, int i,
+                     int restarted, double* partials, unsigned int* ticket)
 {
     const uint64_t pol_stream = l2_policy_evict_first();
     const uint64_t pol_keep = l2_policy_evict_last();
-    constexpr int RPB = kSpmvBlock / L;
-    const int lane = threadIdx.x % L;
-    const int sub = threadIdx.x / L;
+    const int wlane = threadIdx.x & 31;
+    const int64_t warp = (int64_t) blockIdx.x * (kSpmvBlock / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t) gridDim.x * (kSpmvBlock / 32);
     const double beta = ctl->beta;
     const double hsub = restarted ? 0.0 : beta;
     double* __restrict__ vi = V + (int64_t) i * ldv;
     const double* __restrict__ vp = V + (int64_t) (i - 1) * ldv;
 
     double part = 0.0;
-    for (int64_t rbase = (int64_t) blockIdx.x * RPB; rbase < nrows; rbase += (int64_t) gridDim.x * RPB)
+    for (int64_t row0 = warp * 32; row0 < nrows; row0 += nwarps * 32)
     {
-        const int64_t row = rbase + sub;
-        const bool active = row < nrows;
-        const int start = active ? __ldg(rowptr + row) : 0;
-        const int end = active ? __ldg(rowptr + row + 1) : 0;
-        const double s = row_dot<L>(start, end, col, val, x_full, lane, pol_stream, pol_keep);
-        if (active && lane == 0)
+        double s = warp_rows_dot<L>(rowptr, col, val, x_full, row0, nrows, wlane, pol_stream, pol_keep);
+        const int64_t row = row0 + wlane;
+        if (row < nrows)
         {
+            if (ACCUM)
+                s += w[row];
             const double v = f_loc[row] / beta;  // v_i = f / ||f||      (Lanczos.h:106)
             vi[row] = v;
             double wr = s / beta;                // w = A v_i, with the scaling applied after the product
@@ -142,22 +183,74 @@ __global__ void __launch_bounds__(kSpmvBlock)
     }
 }
 
-template <int L>
-void launch_plain_t(const DeviceCsr& A, const SpmvPlan& plan, const double* x, double* y, cudaStream_t stream)
+struct BlockView
 {
-    spmv_plain_kernel<L><<<plan.grid, kSpmvBlock, 0, stream>>>(A.rowptr.get(), A.col.get(), A.val.get(), x, y, A.nrows);
+    const int* rowptr;
+    const int* col;
+    const double* val;
+    int64_t nnz;
+};
+
+int nblocks_of(const DeviceCsr& A) { return A.blocks.empty() ? 1 : (int) A.blocks.size(); }
+
+BlockView view_of(const DeviceCsr& A, int c)
+{
+    if (A.blocks.empty())
+        return {A.rowptr.get(), A.col.get(), A.val.get(), A.nnz};
+    const CsrBlock& B = A.blocks[c];
+    return {B.rowptr.get(), B.col.get(), B.val.get(), B.nnz};
+}
+
+int lanes_for(double avg)
+{
+    if (avg <= 3.0)
+        return 2;
+    if (avg <= 6.0)
+        return 4;
+    if (avg <= 28.0)
+        return 8;
+    if (avg <= 64.0)
+        return 16;
+    return 32;
 }
 
 template <int L>
-void launch_step_t(const DeviceCsr& A, const SpmvPlan& plan, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
-                   double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream)
+void launch_plain_t(const BlockView& b, int grid, int64_t nrows, const double* x, double* y, bool accum, cudaStream_t stream)
 {
-    if (symmetric)
-        spmv_step_kernel<L, true><<<plan.grid, kSpmvBlock, 0, stream>>>(A.rowptr.get(), A.col.get(), A.val.get(), x_full, f_loc, V, ldv, w, A.nrows, ctl, H, m, i,
-                                                                        restarted, rs.partials, rs.ticket);
+    if (accum)
+        spmv_plain_kernel<L, true><<<grid, kSpmvBlock, 0, stream>>>(b.rowptr, b.col, b.val, x, y, nrows);
     else
-        spmv_step_kernel<L, false><<<plan.grid, kSpmvBlock, 0, stream>>>(A.rowptr.get(), A.col.get(), A.val.get(), x_full, f_loc, V, ldv, w, A.nrows, ctl, H, m,
-                                                                         i, restarted, rs.partials, rs.ticket);
+        spmv_plain_kernel<L, false><<<grid, kSpmvBlock, 0, stream>>>(b.rowptr, b.col, b.val, x, y, nrows);
+}
+
+void launch_plain_block(int lanes, const BlockView& b, int grid, int64_t nrows, const double* x, double* y, bool accum, cudaStream_t stream)
+{
+    switch (lanes)
+    {
+        case 2: launch_plain_t<2>(b, grid, nrows, x, y, accum, stream); break;
+        case 4: launch_plain_t<4>(b, grid, nrows, x, y, accum, stream); break;
+        case 8: launch_plain_t<8>(b, grid, nrows, x, y, accum, stream); break;
+        case 16: launch_plain_t<16>(b, grid, nrows, x, y, accum, stream); break;
+        default: launch_plain_t<32>(b, grid, nrows, x, y, accum, stream); break;
+    }
+}
+
+template <int L>
+void launch_step_t(const BlockView& b, int grid, int64_t nrows, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl, double* H,
+                   int m, int i, int restarted, bool symmetric, bool accum, const RedScratch& rs, cudaStream_t stream)
+{
+#define SB200_STEP(SYM, ACC)                                                                                                                                     \
+    spmv_step_kernel<L, SYM, ACC><<<grid, kSpmvBlock, 0, stream>>>(b.rowptr, b.col, b.val, x_full, f_loc, V, ldv, w, nrows, ctl, H, m, i, restarted, rs.partials, \
+                                                                   rs.ticket)
+    if (symmetric && accum)
+        SB200_STEP(true, true);
+    else if (symmetric)
+        SB200_STEP(true, false);
+    else if (accum)
+        SB200_STEP(false, true);
+    else
+        SB200_STEP(false, false);
+#undef SB200_STEP
 }
 
 }  // namespace
@@ -165,37 +258,41 @@ void launch_step_t(const DeviceCsr& A, const SpmvPlan& plan, const double* x_ful
 SpmvPlan make_spmv_plan(const DeviceCsr& A)
 {
     SpmvPlan p;
-    const double avg = A.nrows > 0 ? double(A.nnz) / double(A.nrows) : 1.0;
-    if (avg <= 3.0)
-        p.lanes = 2;
-    else if (avg <= 6.0)
-        p.lanes = 4;
-    else if (avg <= 28.0)
-        p.lanes = 8;
-    else if (avg <= 64.0)
-        p.lanes = 16;
-    else
-        p.lanes = 32;
+    const int nb = nblocks_of(A);
+    const double avg = A.nrows > 0 ? double(A.nnz) / double(A.nrows) / nb : 1.0;
+    p.lanes = lanes_for(avg);
+    if (const char* e = std::getenv("SB200_SPMV_LANES"))
+    {
+        const int v = std::atoi(e);
+        if (v == 2 || v == 4 || v == 8 || v == 16 || v == 32)
+            p.lanes = v;
+    }
     const int sms = device_info().sm_count;
-    const int64_t rpb = kSpmvBlock / p.lanes;
+    const int64_t rpb = kSpmvBlock;  // 8 warps x 32 rows per CTA iteration
     const int64_t need = (A.nrows + rpb - 1) / rpb;
-    // persistent grid: 8 resident CTAs of 256 threads per SM (2048 threads/SM)
+    // persistent grid: up to 8 resident CTAs of 256 threads per SM
     p.grid = (int) std::max<int64_t>(1, std::min<int64_t>(need, (int64_t) sms * 8));
     return p;
+}
+
+// Number of column blocks for an operand of order n: slices of at most SB200_XSLICE_MB (default 24 MB) of x.
+int choose_col_blocks(int64_t n)
+{
+    double slice_mb = 24.0;
+    if (const char* e = std::getenv("SB200_XSLICE_MB"))
+        slice_mb = std::max(1.0, std::atof(e));
+    const double x_mb = 8.0 * double(n) / (1024.0 * 1024.0);
+    const int nb = (int) std::ceil(x_mb / slice_mb);
+    return std::max(1, std::min(nb, kMaxColBlocks));
 }
 
 void launch_spmv(const DeviceCsr& A, const SpmvPlan& plan, const double* x, double* y, cudaStream_t stream)
 {
     if (A.nrows == 0)
         return;
-    switch (plan.lanes)
-    {
-        case 2: launch_plain_t<2>(A, plan, x, y, stream); break;
-        case 4: launch_plain_t<4>(A, plan, x, y, stream); break;
-        case 8: launch_plain_t<8>(A, plan, x, y, stream); break;
-        case 16: launch_plain_t<16>(A, plan, x, y, stream); break;
-        default: launch_plain_t<32>(A, plan, x, y, stream); break;
-    }
+    const int nb = nblocks_of(A);
+    for (int c = 0; c < nb; c++)
+        launch_plain_block(plan.lanes, view_of(A, c), plan.grid, A.nrows, x, y, c > 0, stream);
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -203,13 +300,19 @@ void launch_spmv_step(const DeviceCsr& A, const SpmvPlan& plan, const double* x_
                       double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream)
 {
     SB200_REQUIRE(plan.grid <= rs.max_grid, SB200_LOGIC, "spmv: reduction scratch too small");
+    const int nb = nblocks_of(A);
+    // all but the last column block accumulate the raw product into w; the last one applies the step head
+    for (int c = 0; c + 1 < nb; c++)
+        launch_plain_block(plan.lanes, view_of(A, c), plan.grid, A.nrows, x_full, w, c > 0, stream);
+    const BlockView b = view_of(A, nb - 1);
+    const bool accum = nb > 1;
     switch (plan.lanes)
     {
-        case 2: launch_step_t<2>(A, plan, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, rs, stream); break;
-        case 4: launch_step_t<4>(A, plan, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, rs, stream); break;
-        case 8: launch_step_t<8>(A, plan, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, rs, stream); break;
-        case 16: launch_step_t<16>(A, plan, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, rs, stream); break;
-        default: launch_step_t<32>(A, plan, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, rs, stream); break;
+        case 2: launch_step_t<2>(b, plan.grid, A.nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
+        case 4: launch_step_t<4>(b, plan.grid, A.nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
+        case 8: launch_step_t<8>(b, plan.grid, A.nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
+        case 16: launch_step_t<16>(b, plan.grid, A.nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
+        default: launch_step_t<32>(b, plan.grid, A.nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
     }
     SB200_CUDA_CHECK(cudaGetLastError());
 }

@@ -365,3 +365,46 @@ def test_sym_eigs_full_size_properties(gpu):
     eigs.init()
     eigs.compute(gpu.SortRule.LargestAlge)
     assert np.array_equal(evals, eigs.eigenvalues())
+
+
+def test_column_blocked_operator_and_solver(gpu, monkeypatch):
+    # Large operands are stored as column blocks so that each SpMV pass gathers from an L2-resident slice of x
+    # (csr_build.cu: split_column_blocks).  Force the blocked layout at a small size and compare with the unblocked one.
+    from spectra_b200 import synth
+
+    n = 200_000
+    rp, ci, v = synth.csr(n, 20, 5, True)
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    x = O.simple_random(11, n)
+    y0 = A @ x
+    monkeypatch.setenv("SB200_XSLICE_MB", "0.25")  # 1.6 MB of x -> 7 column blocks
+    op = gpu.SparseGenMatProd.from_csr_slab(n, 0, rp, ci, v)
+    assert np.abs(op.perform_op(x) - y0).max() <= 1e-13 * np.abs(y0).max()
+    op_sym = gpu.SparseSymMatProd((n, rp, ci, v, "col"))
+    assert np.abs(op_sym.perform_op(x) - y0).max() <= 1e-13 * np.abs(y0).max()
+    eigs = gpu.SymEigsSolver(op, 10, 30)
+    eigs.init()
+    eigs.compute(gpu.SortRule.LargestAlge)
+    ev_blocked, nops_blocked = eigs.eigenvalues(), eigs.num_operations()
+    monkeypatch.setenv("SB200_XSLICE_MB", "1000")
+    op1 = gpu.SparseGenMatProd.from_csr_slab(n, 0, rp, ci, v)
+    e1 = gpu.SymEigsSolver(op1, 10, 30)
+    e1.init()
+    e1.compute(gpu.SortRule.LargestAlge)
+    assert eigs.info() == gpu.CompInfo.Successful and e1.info() == gpu.CompInfo.Successful
+    assert nops_blocked == e1.num_operations()
+    assert np.abs(ev_blocked - e1.eigenvalues()).max() <= 1e-12 * np.abs(ev_blocked).max()
+    # a nonsymmetric operator through the blocked Arnoldi step head
+    rpg, cig, vg = synth.csr(n, 20, 6, False)
+    G = sp.csr_matrix((vg, cig, rpg), shape=(n, n))
+    monkeypatch.setenv("SB200_XSLICE_MB", "0.25")
+    opg = gpu.SparseGenMatProd.from_csr_slab(n, 0, rpg, cig, vg)
+    yg = G @ x
+    assert np.abs(opg.perform_op(x) - yg).max() <= 1e-13 * np.abs(yg).max()
+    g = gpu.GenEigsSolver(opg, 3, 12)
+    g.init()
+    g.factorize_from(1, 12)
+    fz = g.factorization()
+    E = G @ fz["V"] - fz["V"] @ fz["H"]
+    E[:, -1] -= fz["f"]
+    assert np.abs(E).max() <= 1e-12 * max(1.0, np.abs(fz["H"]).max())
