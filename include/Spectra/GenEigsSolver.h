@@ -15,7 +15,7 @@ namespace Spectra {
 template <typename OpType = SparseGenMatProd<double>>
 class GenEigsSolver
 {
-    static_assert(std::is_base_of<b200::SparseOpBase, OpType>::value, "the B200 solver runs with device-resident operators");
+    b200::OpBinding<OpType> m_bind;
     sb200_gen_solver* m_s = nullptr;
     const OpType& m_op;
     Index m_nev;
@@ -25,7 +25,7 @@ public:
     using ComplexVector = b200::ComplexVector;
     using ComplexMatrix = b200::ComplexMatrix;
 
-    GenEigsSolver(OpType& op, Index nev, Index ncv) : m_op(op), m_nev(nev) { b200::check(sb200_gen_create(op.handle(), nev, ncv, &m_s)); }
+    GenEigsSolver(OpType& op, Index nev, Index ncv) : m_bind(op), m_op(op), m_nev(nev) { b200::check(sb200_gen_create(m_bind.handle(), nev, ncv, &m_s)); }
     GenEigsSolver(const GenEigsSolver&) = delete;
     GenEigsSolver& operator=(const GenEigsSolver&) = delete;
     virtual ~GenEigsSolver()

@@ -15,8 +15,7 @@ namespace Spectra {
 template <typename OpType = SparseSymMatProd<double>>
 class SymEigsSolver
 {
-    static_assert(std::is_base_of<b200::SparseOpBase, OpType>::value,
-                  "the B200 solver runs with device-resident operators (SparseSymMatProd / SparseGenMatProd); user-defined host OpTypes are not wired yet");
+    b200::OpBinding<OpType> m_bind;  // device-resident sparse operator, or a host-callback adapter for any other OpType
     sb200_sym_solver* m_s = nullptr;
     const OpType& m_op;  // the operator must outlive the solver (HermEigsBase.h:257-258)
     Index m_nev;
@@ -26,7 +25,7 @@ public:
     using Vector = b200::Vector;
     using Matrix = b200::Matrix;
 
-    SymEigsSolver(OpType& op, Index nev, Index ncv) : m_op(op), m_nev(nev) { b200::check(sb200_sym_create(op.handle(), nev, ncv, &m_s)); }
+    SymEigsSolver(OpType& op, Index nev, Index ncv) : m_bind(op), m_op(op), m_nev(nev) { b200::check(sb200_sym_create(m_bind.handle(), nev, ncv, &m_s)); }
     SymEigsSolver(const SymEigsSolver&) = delete;
     SymEigsSolver& operator=(const SymEigsSolver&) = delete;
     virtual ~SymEigsSolver()

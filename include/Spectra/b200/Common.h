@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../spectra_b200.h"
@@ -196,7 +197,46 @@ public:
     }
 };
 
-inline int to_c(int rule) { return rule; }
+// Adapter for user-defined operators (the OpType concept of the reference, SymEigsSolver.h:99-114): any class with
+// rows() and perform_op(const double* x_in, double* y_out) const.  The solver keeps the Krylov iteration on the GPU and
+// calls back into the user's host code once per matrix operation.
+template <typename OpType>
+class HostOpAdapter
+{
+    sb200_op* m_op = nullptr;
+    const OpType* m_user;
+    static void trampoline(const double* x, double* y, void* self) { static_cast<const OpType*>(self)->perform_op(x, y); }
+
+public:
+    explicit HostOpAdapter(const OpType& op) : m_user(&op)
+    {
+        check(sb200_op_create_callback(static_cast<int64_t>(op.rows()), &HostOpAdapter::trampoline, const_cast<OpType*>(m_user), &m_op));
+    }
+    HostOpAdapter(const HostOpAdapter&) = delete;
+    HostOpAdapter& operator=(const HostOpAdapter&) = delete;
+    ~HostOpAdapter()
+    {
+        if (m_op)
+            sb200_op_destroy(m_op);
+    }
+    sb200_op* handle() const { return m_op; }
+};
+
+// Picks the device handle of an operator: device-resident sparse wrappers expose it directly, anything else is wrapped.
+template <typename OpType, bool IsDevice = std::is_base_of<SparseOpBase, OpType>::value>
+struct OpBinding
+{
+    explicit OpBinding(OpType& op) : m_h(op.handle()) {}
+    sb200_op* handle() const { return m_h; }
+    sb200_op* m_h;
+};
+template <typename OpType>
+struct OpBinding<OpType, false>
+{
+    explicit OpBinding(OpType& op) : m_adapter(op) {}
+    sb200_op* handle() const { return m_adapter.handle(); }
+    HostOpAdapter<OpType> m_adapter;
+};
 
 }  // namespace b200
 }  // namespace Spectra

@@ -109,6 +109,12 @@ int sb200_op_create_sparse(int64_t n, const void* outer, int outer_is_64, const 
 /* Pre-partitioned form: this rank's rows [row0, row0 + nrows) of a full n x n CSR (general). */
 int sb200_op_create_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64_t* rowptr_local, const int32_t* col, const double* values, sb200_comm* comm,
                              sb200_op** out);
+/* User-defined operator: the reference's OpType concept (SymEigsSolver.h:99-114, MIGRATION.md:19-37) — any
+ * host function computing y_out = A * x_in on n-vectors.  The Krylov basis, the re-orthogonalisation and the
+ * restart still run on the GPU; each matrix operation copies v to pinned host memory, calls fn, and copies
+ * the product back.  Single-GPU only. */
+typedef void (*sb200_matvec_fn)(const double* x_in, double* y_out, void* user);
+int sb200_op_create_callback(int64_t n, sb200_matvec_fn fn, void* user, sb200_op** out);
 int sb200_op_rows(const sb200_op* op, int64_t* rows);      /* rows()  SparseSymMatProd.h:70 */
 int sb200_op_cols(const sb200_op* op, int64_t* cols);      /* cols()  SparseSymMatProd.h:74 */
 int sb200_op_local_rows(const sb200_op* op, int64_t* row0, int64_t* nrows);

@@ -21,12 +21,13 @@ import os
 import numpy as np
 
 __all__ = [
-    "SortRule", "CompInfo", "SparseSymMatProd", "SparseGenMatProd", "SymEigsSolver", "GenEigsSolver", "Comm", "Stats", "lib", "lib_path", "device_info",
+    "SortRule", "CompInfo", "SparseSymMatProd", "SparseGenMatProd", "UserOp", "SymEigsSolver", "GenEigsSolver", "Comm", "Stats", "lib", "lib_path", "device_info",
     "set_profiling", "set_device", "dense",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libspectra_b200.so")
+# SB200_LIB_SUFFIX selects an experimental build variant (developer knob, see _build.py); default: the product library
+_LIB_PATH = os.path.join(_HERE, "lib", "libspectra_b200" + os.environ.get("SB200_LIB_SUFFIX", "") + ".so")
 _lib = None
 
 
@@ -267,6 +268,67 @@ class _SparseOp:
         _check(lib().sb200_op_spmv_device(self.h, None, None, 3, C.byref(ms)))  # warm-up
         _check(lib().sb200_op_spmv_device(self.h, None, None, int(repeat), C.byref(ms)))
         return ms.value / repeat
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sb200_op_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_MATVEC_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+
+
+class UserOp:
+    """User-defined operator — the reference's OpType concept (SymEigsSolver.h:99-114): `op` is either a callable
+    y = op(x) on numpy vectors, or an object with rows() and perform_op(x_in, y_out).  The Krylov iteration still
+    runs on the GPU; every matrix operation round-trips one vector through pinned host memory."""
+
+    def __init__(self, op, n: int | None = None):
+        if hasattr(op, "perform_op"):
+            n = int(op.rows()) if n is None else int(n)
+
+            def apply(x, y):
+                op.perform_op(x, y)
+        else:
+            if n is None:
+                raise InvalidArgument(1, "n is required for a callable operator")
+            n = int(n)
+
+            def apply(x, y):
+                y[:] = op(x)
+
+        self.n = n
+        self.row0, self.nrows_local = 0, n
+        self.comm = None
+        self._exc = None
+
+        def tramp(xp, yp, _):
+            try:
+                apply(np.ctypeslib.as_array(xp, shape=(n,)), np.ctypeslib.as_array(yp, shape=(n,)))
+            except BaseException as e:  # noqa: BLE001 - re-raised on the Python side after the C call returns
+                self._exc = e
+
+        self._cb = _MATVEC_FN(tramp)  # must outlive the operator handle
+        self.h = C.c_void_p()
+        _check(lib().sb200_op_create_callback(C.c_int64(n), self._cb, None, C.byref(self.h)))
+
+    def rows(self):
+        return self.n
+
+    def cols(self):
+        return self.n
+
+    def perform_op(self, x_in, y_out=None):
+        x = np.ascontiguousarray(x_in, dtype=np.float64)
+        y = y_out if y_out is not None else np.empty(self.n)
+        _check(lib().sb200_op_perform_op(self.h, _p(x), _p(y)))
+        return y
 
     def close(self):
         if getattr(self, "h", None):

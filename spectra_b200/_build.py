@@ -32,9 +32,9 @@ def _headers_mtime():
     return max(os.path.getmtime(h) for h in hs)
 
 
-def _compile(src: str, verbose: bool):
-    obj = os.path.join(OBJ, src[:-3] + ".o")
-    cmd = [NVCC, *ARCH, *CFLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+def _compile(src: str, verbose: bool, objdir: str = OBJ, defines=()):
+    obj = os.path.join(objdir, src[:-3] + ".o")
+    cmd = [NVCC, *ARCH, *CFLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -44,29 +44,35 @@ def _compile(src: str, verbose: bool):
     return src, r.stderr
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(OBJ, exist_ok=True)
+def build(force: bool = False, verbose: bool = False, defines=(), suffix: str = "") -> str:
+    """suffix/defines build an experimental variant (lib/libspectra_b200<suffix>.so, selected at run time with
+    SB200_LIB_SUFFIX); the default build has neither."""
+    objdir = OBJ + suffix
+    lib = LIB if not suffix else os.path.join(LIBDIR, f"libspectra_b200{suffix}.so")
+    os.makedirs(objdir, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
     hm = _headers_mtime()
     todo = []
     for src in _sources():
-        obj = os.path.join(OBJ, src[:-3] + ".o")
+        obj = os.path.join(objdir, src[:-3] + ".o")
         sm = max(os.path.getmtime(os.path.join(CSRC, src)), hm)
         if force or verbose or not os.path.exists(obj) or os.path.getmtime(obj) < sm:
             todo.append(src)
     if todo:
         with ThreadPoolExecutor(max_workers=min(8, len(todo))) as ex:
-            for src, log in ex.map(lambda s: _compile(s, verbose), todo):
+            for src, log in ex.map(lambda s: _compile(s, verbose, objdir, defines), todo):
                 if verbose and log:
                     print(f"== {src}\n{log}")
-    objs = [os.path.join(OBJ, s[:-3] + ".o") for s in _sources()]
-    if todo or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-ldl", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
+    objs = [os.path.join(objdir, s[:-3] + ".o") for s in _sources()]
+    if todo or not os.path.exists(lib) or any(os.path.getmtime(o) > os.path.getmtime(lib) for o in objs):
+        cmd = [NVCC, *ARCH, "-shared", "-o", lib, *objs, "-ldl", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    suf = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--suffix=")), "")
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, suffix=suf))

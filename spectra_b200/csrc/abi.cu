@@ -12,6 +12,7 @@ sb200_op* op_create_sparse(int64_t n, const void* outer, int outer_is_64, const 
                            sb200_comm* comm);
 sb200_op* op_create_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64_t* rowptr_local, const int32_t* col, const double* values, sb200_comm* comm);
 void op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev);
+sb200_op* op_create_callback(int64_t n, void (*fn)(const double*, double*, void*), void* user);
 void op_perform_op_host(sb200_op* op, const double* x_host, double* y_host);
 
 sb200_sym_solver* sym_create(sb200_op* op, int64_t nev, int64_t ncv, bool shift_mode, double sigma);
@@ -172,6 +173,13 @@ int sb200_op_create_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64
     ABI_NONNULL(out);
     ABI_NONNULL(rowptr_local);
     *out = op_create_csr_slab(n, row0, nrows, rowptr_local, col, values, (comm && comm->nranks > 1) ? comm : nullptr);
+    ABI_CATCH
+}
+int sb200_op_create_callback(int64_t n, sb200_matvec_fn fn, void* user, sb200_op** out)
+{
+    ABI_TRY
+    ABI_NONNULL(out);
+    *out = op_create_callback(n, fn, user);
     ABI_CATCH
 }
 int sb200_op_rows(const sb200_op* op, int64_t* rows)

@@ -270,11 +270,22 @@ __device__ __forceinline__ void ld_stream_f64x4(const double* p, double (&v)[4])
 {
     asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
-// Gathered operand: keep in L2.
+// Gathered operand: keep in L2.  SB200_GATHER_MODE (build-time experiment knob): 0 = read-only path with the L2
+// evict_last hint (default), 1 = the same without allocating in L1, 2 = plain read-only load, no hints.
+#ifndef SB200_GATHER_MODE
+#define SB200_GATHER_MODE 0
+#endif
 __device__ __forceinline__ double ld_keep_f64(const double* p, uint64_t pol)
 {
     double v;
+#if SB200_GATHER_MODE == 0
     asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+#elif SB200_GATHER_MODE == 1
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+#else
+    (void) pol;
+    v = __ldg(p);
+#endif
     return v;
 }
 // L2-coherent load (skips the non-coherent L1) for data written by other CTAs of the same kernel.

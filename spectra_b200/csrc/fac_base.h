@@ -54,6 +54,7 @@ struct SimpleRandom
 };
 
 void launch_trim_h(double* H, int m, int from_k, cudaStream_t s);
+void op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev);
 
 struct FacBase
 {
@@ -179,13 +180,25 @@ struct FacBase
     {
         {
             ScopedKernelTimer t(&prof, stream(), KC_SPMV);
-            launch_spmv(op->A, op->plan, xfull, y, stream());
+            op_spmv_device(op, xfull, y);
         }
         stats.spmv_launches++;
         nmatop++;
     }
     void spmv_step(int i, bool restarted, bool symmetric)
     {
+        if (op->cb)
+        {
+            // user-defined host operator: v_i = f/beta on the device, w = op(v_i) on the host, epilogue on the device
+            ScopedKernelTimer t(&prof, stream(), KC_SPMV, 2);
+            double* vi = V.get() + (int64_t) i * ld;
+            launch_step_scale(f.get(), ctl.get(), vi, nloc, stream());
+            op_spmv_device(op, vi, w.get());
+            launch_step_epilogue(w.get(), V.get(), ld, nloc, ctl.get(), H.get(), m, i, restarted ? 1 : 0, symmetric, rs, stream());
+            stats.spmv_launches++;
+            nmatop++;
+            return;
+        }
         const double* xfull = gather_full(f.get());
         {
             ScopedKernelTimer t(&prof, stream(), KC_SPMV);

@@ -37,6 +37,10 @@ struct sb200_op
     sb200::DevBuf<double> x_stage;    // slab-sized send buffer for the all-gather
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool symmetric_hint = false;      // created through a SYM mode
+    // user-defined host operator (the reference's OpType concept, SymEigsSolver.h:99-114): y = fn(x) on host memory
+    void (*cb)(const double*, double*, void*) = nullptr;
+    void* cb_user = nullptr;
+    sb200::PinnedBuf<double> hx, hy;  // pinned staging of the callback path
 
     int nranks() const { return comm ? comm->nranks : 1; }
     int rank() const { return comm ? comm->rank : 0; }

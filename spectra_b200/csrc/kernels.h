@@ -134,6 +134,12 @@ void launch_vec_scale(const double* x, double s, int divide, double* y, int64_t 
 void launch_vec_axpy(const double* w, const double* v, double a, double* f, int64_t n, cudaStream_t stream);      // f = w - a*v
 void launch_set_beta(FacCtl* ctl, const double* red_slot, int take_sqrt, cudaStream_t stream);                      // ctl->beta = (sqrt) *red_slot
 void launch_set_scalar(double* dst, double v, cudaStream_t stream);
+// Host-operator path (user OpType): the two halves of the fused step head around the host call.
+//   scale:    V[:,i] = f / beta                                              (Lanczos.h:106, Arnoldi.h:236)
+//   epilogue: w -= hsub * V[:,i-1] (sym), red_a[0] = <V[:,i], w> (sym), step bookkeeping as in launch_spmv_step
+void launch_step_scale(const double* f, const FacCtl* ctl, double* vi, int64_t n, cudaStream_t stream);
+void launch_step_epilogue(double* w, const double* V, int64_t ldv, int64_t n, FacCtl* ctl, double* H, int m, int i, int restarted, bool symmetric,
+                          const RedScratch& rs, cudaStream_t stream);
 
 // ---- small dense restart kernels (dense_sym.cu) ----------------------------------------------------------
 struct SymRestartOut

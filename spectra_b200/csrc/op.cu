@@ -119,12 +119,55 @@ sb200_op* op_create_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64
     return op.release();
 }
 
+sb200_op* op_create_callback(int64_t n, void (*fn)(const double*, double*, void*), void* user)
+{
+    device_info();
+    SB200_REQUIRE(fn != nullptr, SB200_INVALID_ARGUMENT, "null operator callback");
+    SB200_REQUIRE(n >= 1 && n < (1LL << 31), SB200_INVALID_ARGUMENT, "matrix order out of range");
+    std::unique_ptr<sb200_op> op(new sb200_op());
+    SB200_CUDA_CHECK(cudaStreamCreateWithFlags(&op->stream, cudaStreamNonBlocking));
+    op->A.n = n;
+    op->A.row0 = 0;
+    op->A.nrows = n;
+    op->A.nnz = 0;
+    op->cb = fn;
+    op->cb_user = user;
+    op->hx.alloc((size_t) n);
+    op->hy.alloc((size_t) n);
+    op->slab = n;
+    op->plan.grid = 1;
+    SB200_CUDA_CHECK(cudaEventCreate(&op->ev0));
+    SB200_CUDA_CHECK(cudaEventCreate(&op->ev1));
+    return op.release();
+}
+
+// y_dev = A * x_dev through the user's host function (device pointers in, device pointers out)
+void op_callback_device(sb200_op* op, const double* x_dev, double* y_dev)
+{
+    const int64_t n = op->A.n;
+    SB200_CUDA_CHECK(cudaMemcpyAsync(op->hx.get(), x_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, op->stream));
+    SB200_CUDA_CHECK(cudaStreamSynchronize(op->stream));
+    op->cb(op->hx.get(), op->hy.get(), op->cb_user);
+    SB200_CUDA_CHECK(cudaMemcpyAsync(y_dev, op->hy.get(), sizeof(double) * n, cudaMemcpyHostToDevice, op->stream));
+}
+
 // y_dev (local rows) = A * x_dev (full vector).  Sharded: x_dev must already hold all n entries.
-void op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev) { launch_spmv(op->A, op->plan, x_dev, y_dev, op->stream); }
+void op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev)
+{
+    if (op->cb)
+        op_callback_device(op, x_dev, y_dev);
+    else
+        launch_spmv(op->A, op->plan, x_dev, y_dev, op->stream);
+}
 
 // Host-pointer perform_op (SparseSymMatProd.h:83-88): H2D x, kernel, D2H y (local rows).
 void op_perform_op_host(sb200_op* op, const double* x_host, double* y_host)
 {
+    if (op->cb)
+    {
+        op->cb(x_host, y_host, op->cb_user);
+        return;
+    }
     const int64_t n = op->A.n;
     if (op->x_full.n < (size_t) n)
         op->x_full.alloc((size_t) n);

@@ -90,7 +90,7 @@ __device__ __forceinline__ double warp_rows_dot(const int* __restrict__ rowptr, 
 
 // y = (ACCUM ? y : 0) + A_block x
 template <int L, bool ACCUM>
-__global__ void __launch_bounds__(kSpmvBlock) spmv_plain_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
+__global__ void __launch_bounds__(kSpmvBlock, 8) spmv_plain_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
                                                                 const double* __restrict__ x, double* y, int64_t nrows)
 {
     const uint64_t pol_stream = l2_policy_evict_first();
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kSpmvBlock) spmv_plain_kernel(const int* __res
 // Fused step head on the LAST column block.  x_full: un-normalised residual (all n entries), f_loc: this
 // rank's rows of it.  ACCUM: w already holds the partial product of the previous column blocks.
 template <int L, bool SYM, bool ACCUM>
-__global__ void __launch_bounds__(kSpmvBlock)
+__global__ void __launch_bounds__(kSpmvBlock, 8)
     spmv_step_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x_full,
                      const double* __restrict__ f_loc, double* __restrict__ V, int64_t ldv, double* w, int64_t nrows, FacCtl* ctl, double* H, int m, int i,
                      int restarted, double* partials, unsigned int* ticket)
@@ -275,10 +275,10 @@ SpmvPlan make_spmv_plan(const DeviceCsr& A)
     return p;
 }
 
-// Number of column blocks for an operand of order n: slices of at most SB200_XSLICE_MB (default 24 MB) of x.
+// Number of column blocks for an operand of order n: slices of at most SB200_XSLICE_MB (default 40 MB, measured best at n = 1e7) of x.
 int choose_col_blocks(int64_t n)
 {
-    double slice_mb = 24.0;
+    double slice_mb = 40.0;
     if (const char* e = std::getenv("SB200_XSLICE_MB"))
         slice_mb = std::max(1.0, std::atof(e));
     const double x_mb = 8.0 * double(n) / (1024.0 * 1024.0);

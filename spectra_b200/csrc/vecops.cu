@@ -103,6 +103,58 @@ __global__ void set_beta_kernel(FacCtl* ctl, const double* slot, int take_sqrt)
 
 __global__ void set_scalar_kernel(double* dst, double v) { *dst = v; }
 
+__global__ void step_scale_kernel(const double* __restrict__ f, const FacCtl* ctl, double* __restrict__ vi, int64_t n)
+{
+    const double beta = ctl->beta;
+    for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t) gridDim.x * blockDim.x)
+        vi[r] = f[r] / beta;
+}
+
+template <bool SYM>
+__global__ void __launch_bounds__(kVecBlock)
+    step_epilogue_kernel(double* __restrict__ w, const double* __restrict__ V, int64_t ldv, int64_t n, FacCtl* ctl, double* H, int m, int i, int restarted,
+                         double* partials, unsigned int* ticket)
+{
+    const double hsub = restarted ? 0.0 : ctl->beta;
+    const double* __restrict__ vi = V + (int64_t) i * ldv;
+    const double* __restrict__ vp = V + (int64_t) (i - 1) * ldv;
+    double part = 0.0;
+    if (SYM)
+    {
+        for (int64_t r = (int64_t) blockIdx.x * kVecBlock + threadIdx.x; r < n; r += (int64_t) gridDim.x * kVecBlock)
+        {
+            const double wr = w[r] - hsub * vp[r];  // Lanczos.h:139
+            w[r] = wr;
+            part = fma(vi[r], wr, part);            // Lanczos.h:142
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        ctl->i = i;
+        ctl->count = 0;
+        ctl->hsub = hsub;
+        ctl->need_corr = 0;
+        ctl->f_zeroed = 0;
+        ctl->dgks_skip = 0;
+        H[i + (int64_t) (i - 1) * m] = hsub;
+        if (SYM)
+            H[(i - 1) + (int64_t) i * m] = hsub;
+    }
+    if (SYM)
+    {
+        __shared__ double s_w[kVecBlock / 32];
+        part = warp_sum(part);
+        if ((threadIdx.x & 31) == 0)
+            s_w[threadIdx.x >> 5] = part;
+        __syncthreads();
+        double cta = 0.0;
+        if (threadIdx.x == 0)
+            for (int q = 0; q < kVecBlock / 32; q++)
+                cta += s_w[q];
+        grid_reduce_fixed_order<kVecBlock>(cta, 1, partials, ticket, ctl->red_a);
+    }
+}
+
 int vec_grid(int64_t n)
 {
     const int sms = device_info().sm_count;
@@ -135,6 +187,24 @@ void launch_vec_scale(const double* x, double s, int divide, double* y, int64_t 
 void launch_vec_axpy(const double* w, const double* v, double a, double* f, int64_t n, cudaStream_t stream)
 {
     vec_axpy_kernel<<<vec_grid(n), kVecBlock, 0, stream>>>(w, v, a, f, n);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_step_scale(const double* f, const FacCtl* ctl, double* vi, int64_t n, cudaStream_t stream)
+{
+    step_scale_kernel<<<vec_grid(n), kVecBlock, 0, stream>>>(f, ctl, vi, n);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_step_epilogue(double* w, const double* V, int64_t ldv, int64_t n, FacCtl* ctl, double* H, int m, int i, int restarted, bool symmetric,
+                          const RedScratch& rs, cudaStream_t stream)
+{
+    const int grid = symmetric ? vec_grid(n) : 1;
+    SB200_REQUIRE(grid <= rs.max_grid, SB200_LOGIC, "step epilogue: reduction scratch too small");
+    if (symmetric)
+        step_epilogue_kernel<true><<<grid, kVecBlock, 0, stream>>>(w, V, ldv, n, ctl, H, m, i, restarted, rs.partials, rs.ticket);
+    else
+        step_epilogue_kernel<false><<<grid, kVecBlock, 0, stream>>>(w, V, ldv, n, ctl, H, m, i, restarted, rs.partials, rs.ticket);
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -125,8 +125,33 @@ static void run_gen(const Csc& A, int k, int m, SortRule rule)
     REQUIRE(err <= 1e-9);
 }
 
+// The user-defined operator of the reference's documentation (SymEigsSolver.h:99-126): M = diag(1, 2, ..., 10)
+class MyDiagonalTen
+{
+public:
+    using Scalar = double;
+    Index rows() const { return 10; }
+    Index cols() const { return 10; }
+    void perform_op(const double* x_in, double* y_out) const
+    {
+        for (Index i = 0; i < rows(); i++)
+            y_out[i] = x_in[i] * (i + 1);
+    }
+};
+
 int main()
 {
+    {
+        MyDiagonalTen op;
+        SymEigsSolver<MyDiagonalTen> eigs(op, 3, 6);
+        eigs.init();
+        eigs.compute(SortRule::LargestAlge);
+        REQUIRE(eigs.info() == CompInfo::Successful);
+        auto ev = eigs.eigenvalues();
+        REQUIRE(ev.size() == 3);
+        REQUIRE(std::fabs(ev[0] - 10.0) < 1e-10 && std::fabs(ev[1] - 9.0) < 1e-10 && std::fabs(ev[2] - 8.0) < 1e-10);
+        std::printf("user op diag(1..10): %.12f %.12f %.12f nops=%d\n", ev[0], ev[1], ev[2], (int) eigs.num_operations());
+    }
     const struct
     {
         int n;

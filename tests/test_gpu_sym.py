@@ -408,3 +408,46 @@ def test_column_blocked_operator_and_solver(gpu, monkeypatch):
     E = G @ fz["V"] - fz["V"] @ fz["H"]
     E[:, -1] -= fz["f"]
     assert np.abs(E).max() <= 1e-12 * max(1.0, np.abs(fz["H"]).max())
+
+
+def test_user_defined_operator(gpu):
+    # the reference's OpType concept (SymEigsSolver.h:99-126): a user class with rows()/cols()/perform_op
+    class MyDiagonalTen:
+        def rows(self):
+            return 10
+
+        def cols(self):
+            return 10
+
+        def perform_op(self, x_in, y_out):
+            y_out[:] = x_in * np.arange(1, 11)
+
+    op = gpu.UserOp(MyDiagonalTen())
+    eigs = gpu.SymEigsSolver(op, 3, 6)
+    eigs.init()
+    eigs.compute(gpu.SortRule.LargestAlge)
+    assert eigs.info() == gpu.CompInfo.Successful
+    assert np.allclose(eigs.eigenvalues(), [10, 9, 8], atol=1e-10)
+    ref = O.sym_eigs_userop(10, lambda x: x * np.arange(1, 11), 3, 6, selection=O.LargestAlge)
+    assert eigs.num_operations() == ref.nops and eigs.num_iterations() == ref.niter
+    # a callable operator gives the same answer as the device-resident wrapper of the same matrix
+    A = O.gen_sparse_data(1000, 0.01)
+    Af = sym_full(A)
+    e1 = gpu.SymEigsSolver(gpu.UserOp(lambda x: Af @ x, n=1000), 20, 50)
+    e1.init()
+    e1.compute(gpu.SortRule.LargestAlge)
+    e2 = gpu.SymEigsSolver(gpu.SparseSymMatProd(A), 20, 50)
+    e2.init()
+    e2.compute(gpu.SortRule.LargestAlge)
+    assert e1.info() == gpu.CompInfo.Successful
+    assert np.abs(e1.eigenvalues() - e2.eigenvalues()).max() <= 1e-11 * np.abs(e2.eigenvalues()).max()
+    U = e1.eigenvectors()
+    assert np.abs(Af @ U - U * e1.eigenvalues()).max() <= 1e-9
+    # nonsymmetric user operator through GenEigsSolver
+    G = O.gen_sparse_data(100, 0.1).tocsr()
+    g = gpu.GenEigsSolver(gpu.UserOp(lambda x: G @ x, n=100), 10, 30)
+    g.init()
+    g.compute(gpu.SortRule.LargestMagn, 300)
+    assert g.info() == gpu.CompInfo.Successful
+    Z = g.eigenvectors()
+    assert np.abs(G @ Z - Z * g.eigenvalues()).max() <= 1e-9
