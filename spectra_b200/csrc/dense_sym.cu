@@ -119,14 +119,19 @@ __device__ int tridiagonal_qr_step(double* diag, double* subdiag, int start, int
     }
     double x = diag[start] - mu;
     double z = subdiag[start];
-    // running copies of the entries the next rotation touches
+    // Register-carried copies of every entry the recurrence reads, with the next column prefetched one iteration
+    // ahead, so that no shared-memory load sits on the dependent chain (stores are fire-and-forget).
     double dk = diag[start], ek = subdiag[start];
+    double dk1 = diag[start + 1];
+    double ek1 = (start + 1 < end) ? subdiag[start + 1] : 0.0;
+    double ekm1 = 0.0;
     int nrot = 0;
     for (int k = start; k < end && z != 0.0; ++k)
     {
+        const double dk2 = (k + 2 <= end) ? diag[k + 2] : 0.0;
+        const double ek2 = (k + 2 < end) ? subdiag[k + 2] : 0.0;
         double c, s;
         make_givens_scaled(x, z, c, s);
-        const double dk1 = diag[k + 1];
         const double sdk = s * dk + c * ek;
         const double dkp1 = s * ek + c * dk1;
         diag[k] = c * (c * dk - s * ek) - s * (c * ek - s * dk1);
@@ -134,17 +139,19 @@ __device__ int tridiagonal_qr_step(double* diag, double* subdiag, int start, int
         const double nek = c * sdk - s * dkp1;
         subdiag[k] = nek;
         if (k > start)
-            subdiag[k - 1] = c * subdiag[k - 1] - s * z;
+            subdiag[k - 1] = c * ekm1 - s * z;
         x = nek;
         if (k < end - 1)
         {
-            const double ek1 = subdiag[k + 1];
             z = -s * ek1;
             ek = c * ek1;
             subdiag[k + 1] = ek;
         }
+        ekm1 = nek;
         dk = ndk1;
         diag[k + 1] = ndk1;
+        dk1 = dk2;
+        ek1 = ek2;
         lc[nrot] = c;
         ls[nrot] = s;
         nrot++;
@@ -330,6 +337,94 @@ __device__ void tridiag_qr_step_scalar(double* d, double* e, int m, double mu, d
             e[i] = 0.0;
 }
 
+// The restart applies nshift shifted QR steps one after the other to the same tridiagonal (HermEigsBase.h:124-135).
+// A QR step is a forward sweep whose work at position i only touches entries i-2 .. i+2, so consecutive shifts can
+// chase each other down the band: lane q of warp 0 runs shift q, kLag positions behind lane q-1 (wavefront
+// pipelining).  Every lane performs exactly the operations of TridiagQR::compute (:515-598) + matrix_QtHQ (:627-693)
+// in the reference's order, on values that are final for the preceding shift, so the result is bit-identical to
+// the sequential chain; the critical path shrinks from nshift*(m-1) to (m-1) + kLag*(nshift-1) rotations.
+// Per shift, at local time t:  G(t) rotation t,  Q(t-1) similarity update of rows/cols t-1,t,  D(t-2) deflation test.
+constexpr int kLag = 5;
+__device__ void qr_chain_round(double* d, double* e, int m, const double* shifts, int nsh, double* lc, double* ls)
+{
+    const int lane = threadIdx.x;  // warp 0
+    const int n1 = m - 1, n2 = m - 2;
+    const bool has = lane < nsh;
+    const double mu = has ? shifts[lane] : 0.0;
+    double rd = 0.0, rsupd = 0.0, ed_cur = 0.0, x = 0.0, y = 0.0, c_prev = 1.0, s_prev = 0.0;
+    const int total = (n1 + 2) + kLag * (nsh - 1);
+    for (int g = 0; g < total; g++)
+    {
+        const int t = g - kLag * lane;
+        if (has && t >= 0 && t <= n1 + 1)
+        {
+            if (t == 0)
+            {
+                const double e0 = e[0];
+                ed_cur = (fabs(e0) <= kEps * (fabs(d[0]) + fabs(d[1]))) ? 0.0 : e0;  // pre-deflation (:533-539)
+                rd = d[0] - mu;
+                rsupd = ed_cur;
+                x = d[0];
+                y = ed_cur;
+            }
+            double c_t = 1.0, s_t = 0.0, ed_next = 0.0;
+            if (t <= n1 - 1)
+            {
+                // G(t): rotation from (R[t,t], T[t+1,t])  (:557-590)
+                if (t + 1 <= n1 - 1)
+                {
+                    const double a = e[t + 1];
+                    ed_next = (fabs(a) <= kEps * (fabs(d[t + 1]) + fabs(d[t + 2]))) ? 0.0 : a;
+                }
+                double r;
+                givens_rotation_fast(rd, ed_cur, r, c_t, s_t);
+                lc[lane * n1 + t] = c_t;
+                ls[lane * n1 + t] = s_t;
+                rd = s_t * rsupd + c_t * (d[t + 1] - mu);  // R[t+1, t+1]
+                rsupd = c_t * ed_next;                     // R[t+1, t+2]
+            }
+            if (t >= 1 && t <= n1)
+            {
+                // Q(i): Gi' T Gi on rows/cols i, i+1  (:650-679); (c_t, s_t) is rotation i+1
+                const int i = t - 1;
+                const double c = c_prev, s = s_prev;
+                const double z = d[i + 1];
+                const double cs = c * s, c2 = c * c, s2 = s * s;
+                const double c2x = c2 * x, s2x = s2 * x, c2z = c2 * z, s2z = s2 * z;
+                const double csy2 = 2.0 * c * s * y;
+                const double xn = c2x - csy2 + s2z;
+                double yn = cs * (x - z) + (c2 - s2) * y;
+                const double zn = s2x + csy2 + c2z;
+                double wn = 0.0;
+                if (i < n2)
+                {
+                    const double tsub = ed_cur;  // deflated T[i+2, i+1]
+                    const double o = -s * tsub;
+                    wn = tsub * c;
+                    yn = c_t * yn - s_t * o;
+                }
+                d[i] = xn;
+                e[i] = yn;
+                if (i == n1 - 1)
+                    d[i + 1] = zn;
+                x = zn;
+                y = wn;
+            }
+            if (t >= 2)
+            {
+                // D(i): post-deflation (:682-689); d[i] and d[i+1] are final by now
+                const int i = t - 2;
+                if (fabs(e[i]) <= kEps * (fabs(d[i]) + fabs(d[i + 1])))
+                    e[i] = 0.0;
+            }
+            c_prev = c_t;
+            s_prev = s_t;
+            ed_cur = ed_next;
+        }
+        __syncwarp();
+    }
+}
+
 // Y <- Y Q for nseq consecutive rotation sequences of m-1 rotations each (UpperHessenbergQR.h:383-417)
 __device__ void apply_yq_block(double* Y, int m, const double* lc, const double* ls, int nseq)
 {
@@ -457,13 +552,11 @@ __global__ void __launch_bounds__(kDenseBlock)
     for (int t = tid; t < m * m; t += kDenseBlock)
         sh.Z[t] = ((t % m) == (t / m)) ? 1.0 : 0.0;
     __syncthreads();
-    const int per_chunk = max(1, kLogCap / (m - 1));  // shifts whose rotations fit into one log chunk
-    for (int ish0 = 0; ish0 < nshift; ish0 += per_chunk)
+    for (int ish0 = 0; ish0 < nshift; ish0 += 32)
     {
-        const int cnt = min(per_chunk, nshift - ish0);
-        if (tid == 0)
-            for (int q = 0; q < cnt; q++)
-                tridiag_qr_step_scalar(s_hd, s_he, m, shifts[ish0 + q], sh.lc + q * (m - 1), sh.ls + q * (m - 1), sh.d, sh.e);
+        const int cnt = min(32, nshift - ish0);  // one warp-wide wavefront of shifts; 32 * (m - 1) <= kLogCap
+        if (tid < 32)
+            qr_chain_round(s_hd, s_he, m, shifts + ish0, cnt, sh.lc, sh.ls);
         __syncthreads();
         apply_yq_block(sh.Z, m, sh.lc, sh.ls, cnt);
         __syncthreads();
