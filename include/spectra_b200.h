@@ -217,6 +217,11 @@ int sb200_dense_hess_eigen(int64_t m, const double* H, double* evals_ri, double*
  * nev_adjusted :178-202, shift loop :118-147) on a tridiagonal H and beta. */
 int sb200_dense_sym_restart(int64_t m, const double* H, double beta, int64_t nev, int selection, double tol, double* ritz_val, double* ritz_est,
                             int32_t* conv, int64_t* nconv, int64_t* k, double* Q, double* Hnew);
+/* Restart GEMM of Arnoldi::compress_V (Arnoldi.h:320-340) on host buffers: Vout (n x kk) = V (n x m) * Q[:, :kk] (Q m x m,
+ * col-major).  If f != NULL (kk >= 2): f <- f*Q(m-1,kk-2) + Vout[:,kk-1]*H(kk-1,kk-2) (:337) and *fnorm2 = ||f||^2.
+ * impl 0 = DMMA/TMA kernel, 1 = FMA kernel (both are product kernels; the solvers use 0). */
+int sb200_dense_compress(int64_t n, int64_t m, int64_t kk, const double* V, const double* Q, const double* H, double* Vout, double* f, double* fnorm2,
+                         int impl);
 
 #ifdef __cplusplus
 }

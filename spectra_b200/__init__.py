@@ -572,3 +572,19 @@ class dense:
         _check(lib().sb200_dense_sym_restart(C.c_int64(m), _p(H), C.c_double(beta), C.c_int64(nev), int(selection), C.c_double(tol), _p(rv), _p(re), _p(conv),
                                              C.byref(nconv), C.byref(k), _p(Q), _p(Hn)))
         return dict(ritz_val=rv, ritz_est=re, conv=conv, nconv=nconv.value, k=k.value, Q=Q, H=Hn)
+
+    @staticmethod
+    def compress(V, Q, kk, f=None, H=None, impl=0):
+        """Restart GEMM (Arnoldi.h:320-340): returns V @ Q[:, :kk] and, when f is given, (Vnew, f_new, ||f_new||^2)."""
+        V = dense._cm(V)
+        Q = dense._cm(Q)
+        n, m = V.shape
+        out = np.empty((n, kk), order="F")
+        if f is None:
+            _check(lib().sb200_dense_compress(C.c_int64(n), C.c_int64(m), C.c_int64(kk), _p(V), _p(Q), None, _p(out), None, None, int(impl)))
+            return out
+        fb = np.array(f, dtype=np.float64, copy=True)
+        Hc = dense._cm(H)
+        nrm2 = C.c_double()
+        _check(lib().sb200_dense_compress(C.c_int64(n), C.c_int64(m), C.c_int64(kk), _p(V), _p(Q), _p(Hc), _p(out), _p(fb), C.byref(nrm2), int(impl)))
+        return out, fb, nrm2.value

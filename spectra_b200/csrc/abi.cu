@@ -539,6 +539,18 @@ int sb200_dense_sym_restart(int64_t m, const double* H, double beta, int64_t nev
     dense_sym_restart_host(m, H, beta, nev, selection, tol, ritz_val, ritz_est, conv, nconv, k, Q, Hnew);
     ABI_CATCH
 }
+int sb200_dense_compress(int64_t n, int64_t m, int64_t kk, const double* V, const double* Q, const double* H, double* Vout, double* f, double* fnorm2,
+                         int impl)
+{
+    ABI_TRY
+    ABI_NONNULL(V);
+    ABI_NONNULL(Q);
+    ABI_NONNULL(Vout);
+    SB200_REQUIRE(n >= 1 && m >= 1 && m <= kMaxNcv && kk >= 1 && kk <= m, SB200_INVALID_ARGUMENT, "bad dimensions");
+    SB200_REQUIRE(!f || (H && fnorm2 && kk >= 2), SB200_INVALID_ARGUMENT, "residual update needs H, fnorm2 and kk >= 2");
+    dense_compress_host(n, (int) m, (int) kk, V, Q, H, Vout, f, fnorm2, impl);
+    ABI_CATCH
+}
 
 }  // extern "C"
 #pragma GCC visibility pop

@@ -97,7 +97,7 @@ struct FacBase
         n = op->A.n;
         nloc = op->A.nrows;
         // leading dimension: multiple of 16 doubles (128 B) and at least the all-gather slab
-        ld = round_up(std::max<int64_t>(std::max<int64_t>(nloc, op->slab), 2), 16);
+        ld = round_up(std::max<int64_t>(std::max<int64_t>(nloc, op->slab), 2), 64);  // 64-row tiles of the restart GEMM
         nev = (int) nev_;
         m = (int) m_;
         V.alloc((size_t) ld * m);

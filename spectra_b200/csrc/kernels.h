@@ -119,6 +119,11 @@ void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, in
 // Vout[:, c] = sum_j V[:, j] * Q[j, c]  for c < kk  (Q: m x m column-major on device, ldq = m).
 // In place when Vout == V.  When f != nullptr also  f = f*Q(m-1,kk-2) + Vout[:,kk-1]*H(kk-1,kk-2)
 // and red_out[0] = ||f||^2   (Arnoldi.h:320-340).
+void launch_compress_fma(const double* V, int64_t ldv, int64_t nrows, int m, const double* Q, int kk, double* Vout, int64_t ldo, double* f, const double* H,
+                         double* red_out, const RedScratch& rs, cudaStream_t stream);
+void dense_compress_host(int64_t n, int m, int kk, const double* V, const double* Q, const double* H, double* Vout, double* f, double* fnorm2, int impl);
+void launch_compress_dmma(const double* V, int64_t ldv, int64_t nrows, int m, const double* Q, int kk, double* Vout, int64_t ldo, double* f, const double* H,
+                          double* red_out, const RedScratch& rs, cudaStream_t stream);
 void launch_compress(const double* V, int64_t ldv, int64_t nrows, int m, const double* Q, int kk, double* Vout, int64_t ldo, double* f, const double* H,
                      double* red_out, const RedScratch& rs, cudaStream_t stream);
 

@@ -17,6 +17,8 @@
 //
 // The restart GEMM  V[:, :kk] <- V Q  (Arnoldi.h:320-340) and  X = V S  (HermEigsBase.h:467) use
 // one thread per row with the whole row of V in registers and Q staged in shared memory.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace sb200 {
@@ -417,6 +419,19 @@ void launch_compress(const double* V, int64_t ldv, int64_t nrows, int m, const d
 {
     SB200_REQUIRE(m >= 1 && m <= kPanelMaxCols && kk >= 1 && kk <= m, SB200_INVALID_ARGUMENT, "compress: bad dimensions");
     SB200_REQUIRE(!f || kk >= 2, SB200_INVALID_ARGUMENT, "compress: residual update needs k >= 1");
+    // default: DMMA + TMA kernel (gemm_dmma.cu); SB200_COMPRESS_FMA=1 selects the plain FMA kernel below (A/B comparison)
+    static const bool force_fma = [] { const char* e = std::getenv("SB200_COMPRESS_FMA"); return e && e[0] == '1'; }();
+    if (!force_fma && ldv % 64 == 0 && ldo % 64 == 0)
+    {
+        launch_compress_dmma(V, ldv, nrows, m, Q, kk, Vout, ldo, f, H, red_out, rs, stream);
+        return;
+    }
+    launch_compress_fma(V, ldv, nrows, m, Q, kk, Vout, ldo, f, H, red_out, rs, stream);
+}
+
+void launch_compress_fma(const double* V, int64_t ldv, int64_t nrows, int m, const double* Q, int kk, double* Vout, int64_t ldo, double* f, const double* H,
+                         double* red_out, const RedScratch& rs, cudaStream_t stream)
+{
     const int sms = device_info().sm_count;
     const int64_t need = (nrows + kGemmBlock - 1) / kGemmBlock;
     const int grid = (int) std::max<int64_t>(1, std::min<int64_t>(need, (int64_t) sms * 3));
@@ -431,6 +446,39 @@ void launch_compress(const double* V, int64_t ldv, int64_t nrows, int m, const d
         default: compress_kernel<64><<<grid, kGemmBlock, smem, stream>>>(V, ldv, nrows, m, Q, kk, Vout, ldo, f, H, red_out, rs.partials, rs.ticket); break;
     }
     SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+// test hook: host buffers in / out, one launch of the selected product kernel
+void dense_compress_host(int64_t n, int m, int kk, const double* V, const double* Q, const double* H, double* Vout, double* f, double* fnorm2, int impl)
+{
+    const int64_t ld = round_up(std::max<int64_t>(n, 2), 64);
+    DevBuf<double> dV((size_t) ld * m), dQ((size_t) m * m), dH((size_t) m * m), dO((size_t) ld * kk), df((size_t) ld), dred(8);
+    const int max_grid = device_info().sm_count * 8;
+    DevBuf<double> partials((size_t) max_grid * 128);
+    DevBuf<unsigned int> ticket(1);
+    SB200_CUDA_CHECK(cudaMemset(dV.get(), 0, sizeof(double) * (size_t) ld * m));
+    SB200_CUDA_CHECK(cudaMemset(dO.get(), 0, sizeof(double) * (size_t) ld * kk));
+    SB200_CUDA_CHECK(cudaMemset(df.get(), 0, sizeof(double) * (size_t) ld));
+    SB200_CUDA_CHECK(cudaMemset(ticket.get(), 0, sizeof(unsigned int)));
+    SB200_CUDA_CHECK(cudaMemcpy2D(dV.get(), sizeof(double) * ld, V, sizeof(double) * n, sizeof(double) * n, m, cudaMemcpyHostToDevice));
+    SB200_CUDA_CHECK(cudaMemcpy(dQ.get(), Q, sizeof(double) * (size_t) m * m, cudaMemcpyHostToDevice));
+    if (f)
+    {
+        SB200_CUDA_CHECK(cudaMemcpy(dH.get(), H, sizeof(double) * (size_t) m * m, cudaMemcpyHostToDevice));
+        SB200_CUDA_CHECK(cudaMemcpy(df.get(), f, sizeof(double) * n, cudaMemcpyHostToDevice));
+    }
+    RedScratch rs{partials.get(), ticket.get(), max_grid};
+    if (impl == 0)
+        launch_compress_dmma(dV.get(), ld, n, m, dQ.get(), kk, dO.get(), ld, f ? df.get() : nullptr, dH.get(), dred.get(), rs, nullptr);
+    else
+        launch_compress_fma(dV.get(), ld, n, m, dQ.get(), kk, dO.get(), ld, f ? df.get() : nullptr, dH.get(), dred.get(), rs, nullptr);
+    SB200_CUDA_CHECK(cudaDeviceSynchronize());
+    SB200_CUDA_CHECK(cudaMemcpy2D(Vout, sizeof(double) * n, dO.get(), sizeof(double) * ld, sizeof(double) * n, kk, cudaMemcpyDeviceToHost));
+    if (f)
+    {
+        SB200_CUDA_CHECK(cudaMemcpy(f, df.get(), sizeof(double) * n, cudaMemcpyDeviceToHost));
+        SB200_CUDA_CHECK(cudaMemcpy(fnorm2, dred.get(), sizeof(double), cudaMemcpyDeviceToHost));
+    }
 }
 
 }  // namespace sb200

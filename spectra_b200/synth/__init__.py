@@ -27,6 +27,7 @@ def lib():
         build()
         _lib = C.CDLL(_LIB)
         _lib.synth_csr_count.restype = C.c_int64
+        _lib.synth_band_count.restype = C.c_int64
     return _lib
 
 
@@ -43,6 +44,21 @@ def csr(n: int, d: int = 20, seed: int = 0, sym: bool = True, row0: int = 0, nro
     val = alloc(nnz, np.float64)
     rc = lib().synth_csr_fill(C.c_int64(n), int(d), int(bool(sym)), C.c_uint64(seed), C.c_int64(row0), C.c_int64(nrows), rowptr.ctypes.data_as(C.c_void_p),
                               col.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return rowptr, col, val
+
+
+def band_csr(n: int, b: int = 15, seed: int = 0, diag_add: float = 0.0, row0: int = 0, nrows: int | None = None):
+    """Rows [row0, row0+nrows) of G_band: symmetric, half-bandwidth b, entries U(-0.5, 0.5), `diag_add` added on the diagonal."""
+    nrows = n - row0 if nrows is None else nrows
+    rowptr = np.empty(nrows + 1, np.int64)
+    nnz = lib().synth_band_count(C.c_int64(n), int(b), C.c_int64(row0), C.c_int64(nrows), rowptr.ctypes.data_as(C.c_void_p))
+    if nnz < 0:
+        raise ValueError("bad generator arguments")
+    col = np.empty(nnz, np.int32)
+    val = np.empty(nnz, np.float64)
+    rc = lib().synth_band_fill(C.c_int64(n), int(b), C.c_uint64(seed), C.c_double(diag_add), C.c_int64(row0), C.c_int64(nrows),
+                               rowptr.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p))
     assert rc == 0
     return rowptr, col, val
 

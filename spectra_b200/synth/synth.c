@@ -207,6 +207,43 @@ int synth_csr_fill(int64_t n, int d, int sym, uint64_t seed, int64_t row0, int64
     return 0;
 }
 
+/* G_band(n, b, seed, diag_add): symmetric band matrix, A(i,j) = u(min(i,j), |i-j|) in U(-0.5, 0.5) for |i-j| <= b, plus diag_add on the
+ * diagonal (SURVEY.md 8d "G_shift": symmetric banded, half-bandwidth 15, A - sigma I nonsingular).  Also the locality case of the SpMV
+ * roofline study: every gathered x entry lies within b rows of the diagonal. */
+int64_t synth_band_count(int64_t n, int b, int64_t row0, int64_t nrows, int64_t* rowptr)
+{
+    if (b < 0 || b > 127 || n < 2 || row0 < 0 || row0 + nrows > n)
+        return -1;
+    rowptr[0] = 0;
+    for (int64_t r = 0; r < nrows; r++)
+    {
+        const int64_t i = row0 + r;
+        const int64_t lo = i - b < 0 ? 0 : i - b, hi = i + b > n - 1 ? n - 1 : i + b;
+        rowptr[r + 1] = rowptr[r] + (hi - lo + 1);
+    }
+    return rowptr[nrows];
+}
+
+int synth_band_fill(int64_t n, int b, uint64_t seed, double diag_add, int64_t row0, int64_t nrows, const int64_t* rowptr, int32_t* col, double* val)
+{
+    if (b < 0 || b > 127 || n < 2 || row0 < 0 || row0 + nrows > n)
+        return -1;
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < nrows; r++)
+    {
+        const int64_t i = row0 + r;
+        const int64_t lo = i - b < 0 ? 0 : i - b, hi = i + b > n - 1 ? n - 1 : i + b;
+        int64_t p = rowptr[r];
+        for (int64_t j = lo; j <= hi; j++, p++)
+        {
+            const int64_t mn = i < j ? i : j, off = i < j ? j - i : i - j;
+            col[p] = (int32_t) j;
+            val[p] = uval(seed, 1000 + (int) off, (uint64_t) mn) + (off == 0 ? diag_add : 0.0);
+        }
+    }
+    return 0;
+}
+
 int synth_max_threads(void)
 {
 #ifdef _OPENMP

@@ -101,6 +101,29 @@ def test_tridiag_eigen_device(gpu, m):
     assert np.array_equal(ev, np.zeros(m)) and np.array_equal(Z, np.eye(m))
 
 
+@pytest.mark.parametrize("impl", [0, 1], ids=["dmma_tma", "fma"])
+@pytest.mark.parametrize("n,m,kk", [(1, 2, 2), (63, 6, 4), (64, 20, 11), (65, 30, 21), (1000, 60, 41), (4099, 64, 64), (300_001, 60, 37), (5000, 50, 1)])
+def test_restart_gemm_compress(gpu, impl, n, m, kk):
+    # Arnoldi::compress_V (Arnoldi.h:320-340): V[:, :kk] <- V Q[:, :kk]; f <- f Q(m-1,kk-2) + Vnew[:,kk-1] H(kk-1,kk-2); beta = ||f||
+    rng = np.random.default_rng(n + m + kk)
+    V = rng.standard_normal((n, m))
+    Q = np.linalg.qr(rng.standard_normal((m, m)))[0]
+    if n % 2:
+        Q = np.triu(Q, -(m - kk + 1))  # the band shape of a restart's Q (Arnoldi.h:330): exact zeros below
+    H = rng.standard_normal((m, m))
+    f = rng.standard_normal(n)
+    ref = V @ Q[:, :kk]
+    scale = np.abs(V).max() * m
+    out = gpu.dense.compress(V, Q, kk, impl=impl)
+    assert np.abs(out - ref).max() <= 4e-16 * scale * 4
+    if kk >= 2:
+        out2, f2, nrm2 = gpu.dense.compress(V, Q, kk, f=f, H=H, impl=impl)
+        assert np.array_equal(out2, out)  # deterministic
+        fref = f * Q[m - 1, kk - 2] + ref[:, kk - 1] * H[kk - 1, kk - 2]
+        assert np.abs(f2 - fref).max() <= 1e-14 * max(1.0, np.abs(fref).max()) * m
+        assert abs(nrm2 - fref @ fref) <= 1e-13 * (fref @ fref)
+
+
 @pytest.mark.parametrize("m", [2, 3, 6, 20, 60, 64])
 def test_tridiag_qr_device(gpu, m):
     # test/QR.cpp:115-129: Q orthogonal, Q'(T - sI) upper triangular, Q'TQ = D (1e-12, scaled)
