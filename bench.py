@@ -254,8 +254,20 @@ def main():
     for kname in ("panel_pass", "csr_spmv"):
         kern[kname]["frac_of_hbm_peak"] = kern[kname]["gbs"] / peak
     dominant = "panel_pass" if ps["ms_panel"] >= ps["ms_spmv"] else "csr_spmv"
+    # DRAM traffic per launch from the committed `ncu --set full` capture of this same workload (profiles/traffic.json;
+    # dram__bytes_read.sum + dram__bytes_write.sum, summed over the column-block kernels of one operator application)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tj = json.load(fh)
+        ent = tj.get(dominant)
+        if ent and int(ent["n"]) == n and int(ent.get("n_gpus", 1)) == world:
+            traffic, traffic_src = float(ent["dram_bytes_per_launch"]), ent.get("source")
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": kern[dominant]["gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": kern[dominant]["gbs"] / peak, "traffic": None, "share_of_step": {"panel_pass": ps["ms_panel"] / ps["ms_total"],
+                "frac": kern[dominant]["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": kern[dominant]["algorithmic_bytes_per_launch"], "share_of_step": {"panel_pass": ps["ms_panel"] / ps["ms_total"],
                                                                                           "csr_spmv": ps["ms_spmv"] / ps["ms_total"]}}
 
     # =========================== e2e arm: host buffers in, host results out ===========================

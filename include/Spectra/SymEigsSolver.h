@@ -20,6 +20,16 @@ class SymEigsSolver
     const OpType& m_op;  // the operator must outlive the solver (HermEigsBase.h:257-258)
     Index m_nev;
 
+protected:
+    // shift-and-invert construction used by SymEigsShiftSolver (SymEigsShiftSolver.h:190-195)
+    struct ShiftInvert
+    {
+    };
+    SymEigsSolver(OpType& op, Index nev, Index ncv, double sigma, ShiftInvert) : m_bind(op), m_op(op), m_nev(nev)
+    {
+        b200::check(sb200_sym_create_shift(m_bind.handle(), nev, ncv, sigma, &m_s));
+    }
+
 public:
     using Scalar = typename OpType::Scalar;
     using Vector = b200::Vector;

@@ -128,7 +128,7 @@ protected:
     const double* m_values = nullptr;
     bool m_row_major = false;
 
-    void create(Index n, const void* outer, bool outer64, const int32_t* inner, const double* values, bool row_major, int mode)
+    void create(Index n, const void* outer, bool outer64, const int32_t* inner, const double* values, bool row_major, int mode, bool shift_solve = false)
     {
         m_n = n;
         m_outer = outer;
@@ -136,7 +136,10 @@ protected:
         m_inner = inner;
         m_values = values;
         m_row_major = row_major;
-        check(sb200_op_create_sparse(n, outer, outer64 ? 1 : 0, inner, values, row_major ? SB200_ROW_MAJOR : SB200_COL_MAJOR, mode, nullptr, &m_op));
+        if (shift_solve)
+            check(sb200_op_create_shift_solve(n, outer, outer64 ? 1 : 0, inner, values, row_major ? SB200_ROW_MAJOR : SB200_COL_MAJOR, mode, &m_op));
+        else
+            check(sb200_op_create_sparse(n, outer, outer64 ? 1 : 0, inner, values, row_major ? SB200_ROW_MAJOR : SB200_COL_MAJOR, mode, nullptr, &m_op));
     }
     int64_t outer_at(Index i) const
     {

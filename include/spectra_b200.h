@@ -115,6 +115,20 @@ int sb200_op_create_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64
  * the product back.  Single-GPU only. */
 typedef void (*sb200_matvec_fn)(const double* x_in, double* y_out, void* user);
 int sb200_op_create_callback(int64_t n, sb200_matvec_fn fn, void* user, sb200_op** out);
+/* Shift-solve operator: replaces MatOp/SparseSymShiftSolve.h:30-110.  Same matrix arguments as sb200_op_create_sparse
+ * (matrix_mode SB200_SYM_LOWER / SB200_SYM_UPPER = the Uplo template argument).  perform_op then computes
+ * y = (A - sigma I)^{-1} x.  Device implementation: block cyclic reduction on the block-tridiagonal form, which needs a
+ * banded matrix (half-bandwidth <= 32, BASELINE config 5's class); wider patterns return SB200_INVALID_ARGUMENT.
+ * Single-GPU. */
+int sb200_op_create_shift_solve(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values, int storage_order, int matrix_mode,
+                                sb200_op** out);
+/* set_shift(sigma) (SparseSymShiftSolve.h:85-95): factorises A - sigma I on the device.  SB200_INVALID_ARGUMENT
+ * ("factorization failed with the given shift", :93-94) when a pivot block is singular or the verification solve fails. */
+int sb200_op_set_shift(sb200_op* op, double sigma);
+/* layout chosen for the factorisation: half-bandwidth found, block size B, number of block rows, reduction levels */
+int sb200_op_shift_solve_info(const sb200_op* op, int* half_bandwidth, int* block, int64_t* block_rows, int* levels);
+/* iterative-refinement steps per solve (0 or 1, default 1) */
+int sb200_op_shift_solve_refine(sb200_op* op, int steps);
 int sb200_op_rows(const sb200_op* op, int64_t* rows);      /* rows()  SparseSymMatProd.h:70 */
 int sb200_op_cols(const sb200_op* op, int64_t* cols);      /* cols()  SparseSymMatProd.h:74 */
 int sb200_op_local_rows(const sb200_op* op, int64_t* row0, int64_t* nrows);
@@ -138,6 +152,10 @@ int sb200_op_destroy(sb200_op* op);
  * shift-solve operator).
  * ------------------------------------------------------------------------------------------ */
 int sb200_sym_create(sb200_op* op, int64_t nev, int64_t ncv, sb200_sym_solver** out);      /* ctor, HermEigsBase.h:257-272 */
+/* SymEigsShiftSolver(op, nev, ncv, sigma) (SymEigsShiftSolver.h:190-195): calls set_shift(sigma) on a device shift-solve
+ * operator (a callback operator must already apply (A - sigma I)^{-1}); eigenvalues are mapped back by
+ * lambda = 1/nu + sigma before sorting (:163-169).  All other calls are the sb200_sym_* functions. */
+int sb200_sym_create_shift(sb200_op* op, int64_t nev, int64_t ncv, double sigma, sb200_sym_solver** out);
 int sb200_sym_init(sb200_sym_solver* s, const double* init_resid_or_null);                  /* init(), init(const Scalar*) :309-342 */
 int sb200_sym_compute(sb200_sym_solver* s, int selection, int64_t maxit, double tol, int sorting, int64_t* nconv); /* compute() :366-390 */
 int sb200_sym_info(const sb200_sym_solver* s, int* info);                                   /* info() :396 */

@@ -338,6 +338,43 @@ def sym_eigs(csr: Csr, nev, ncv, selection=LargestMagn, maxit=1000, tol=1e-10, s
     return _wrap(res, evals, evecs, nev)
 
 
+class BandLu:
+    """SparseSymShiftSolve on a banded matrix: set_shift at construction, perform_op = solve (oracle/band.hpp)."""
+
+    def __init__(self, csr: Csr, sigma: float):
+        self.n, self.sigma = csr.n, float(sigma)
+        h = C.c_void_p()
+        _check(lib().oracle_band_create(csr.h, C.c_double(sigma), C.byref(h)))
+        self.h = h
+        kl, ku = C.c_int64(), C.c_int64()
+        lib().oracle_band_info(self.h, C.byref(kl), C.byref(ku))
+        self.kl, self.ku = kl.value, ku.value
+
+    def perform_op(self, x):
+        x = _f64(x)
+        y = np.empty(self.n)
+        _check(lib().oracle_band_solve(self.h, _p(x), _p(y)))
+        return y
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_band_destroy(self.h)
+            self.h = None
+
+
+def sym_shift_eigs(op: BandLu, nev, ncv, selection=LargestMagn, maxit=1000, tol=1e-10, sorting=LargestAlge, init_resid=None, op_limit=-1,
+                   want_vectors=True) -> EigsResult:
+    """SymEigsShiftSolver<SparseSymShiftSolve> (SymEigsShiftSolver.h:148-196): Lanczos on (A - sigma I)^{-1}, eigenvalues mapped back by 1/nu + sigma."""
+    n = op.n
+    evals = np.zeros(nev)
+    evecs = np.zeros((n, nev), order="F") if want_vectors and op_limit < 0 else None
+    r0 = _f64(init_resid) if init_resid is not None else None
+    res = _Result()
+    _check(lib().oracle_sym_shift_eigs(op.h, C.c_double(op.sigma), C.c_int64(nev), C.c_int64(ncv), int(selection), C.c_int64(maxit), C.c_double(tol), int(sorting),
+                                       _p(r0), C.c_int64(op_limit), _p(evals), _p(evecs), C.byref(res)))
+    return _wrap(res, evals, evecs, nev)
+
+
 _USERFN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
 
 

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <random>
 
+#include "band.hpp"
 #include "solver.hpp"
 
 using namespace oracle;
@@ -404,6 +405,48 @@ int oracle_sym_eigs_userop(int64_t n, void (*fn)(const double*, double*, void*),
     ORACLE_TRY
     UserOp op{n, fn, user};
     run_sym(op, nev, ncv, selection, maxit, tol, sorting, init_resid, shift_mode, sigma, 1, -1, evals, evecs, res);
+    ORACLE_CATCH
+}
+
+// ---- shift-invert: SparseSymShiftSolve (band LU restatement, band.hpp) + SymEigsShiftSolver (SymEigsShiftSolver.h:148-196) ----
+int oracle_band_create(void* csr, double sigma, void** out)
+{
+    ORACLE_TRY
+    auto* A = static_cast<CsrOp*>(csr);
+    auto* op = new BandLuOp();
+    try
+    {
+        op->set_shift(*A, sigma);
+    }
+    catch (...)
+    {
+        delete op;
+        throw;
+    }
+    *out = op;
+    ORACLE_CATCH
+}
+int oracle_band_info(void* h, int64_t* kl, int64_t* ku)
+{
+    auto* op = static_cast<BandLuOp*>(h);
+    *kl = op->kl;
+    *ku = op->ku;
+    return 0;
+}
+int oracle_band_solve(void* h, const double* x, double* y)
+{
+    ORACLE_TRY
+    static_cast<BandLuOp*>(h)->perform_op(x, y);
+    ORACLE_CATCH
+}
+void oracle_band_destroy(void* h) { delete static_cast<BandLuOp*>(h); }
+
+int oracle_sym_shift_eigs(void* band, double sigma, int64_t nev, int64_t ncv, int selection, int64_t maxit, double tol, int sorting, const double* init_resid,
+                          int64_t op_limit, double* evals, double* evecs, OracleResult* res)
+{
+    ORACLE_TRY
+    auto* op = static_cast<BandLuOp*>(band);
+    run_sym(*op, nev, ncv, selection, maxit, tol, sorting, init_resid, 1, sigma, 1, op_limit, evals, evecs, res);
     ORACLE_CATCH
 }
 

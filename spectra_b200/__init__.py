@@ -166,6 +166,8 @@ class _SparseOp:
     (n, outer, inner, values, 'col'|'row') with Eigen's compressed layout."""
     _mode = 0
 
+    _shift_solve = False
+
     def __init__(self, mat, comm: Comm | None = None, uplo: str = "lower"):
         n, outer, inner, vals, order = self._unpack(mat)
         self.n = int(n)
@@ -177,8 +179,11 @@ class _SparseOp:
         outer64 = 1 if outer.dtype == np.int64 else 0
         self.h = C.c_void_p()
         self.comm = comm
-        _check(lib().sb200_op_create_sparse(C.c_int64(self.n), _p(outer), outer64, _p(inner), _p(vals), 0 if order == "col" else 1, mode,
-                                            comm.h if comm is not None else None, C.byref(self.h)))
+        if self._shift_solve:
+            _check(lib().sb200_op_create_shift_solve(C.c_int64(self.n), _p(outer), outer64, _p(inner), _p(vals), 0 if order == "col" else 1, mode, C.byref(self.h)))
+        else:
+            _check(lib().sb200_op_create_sparse(C.c_int64(self.n), _p(outer), outer64, _p(inner), _p(vals), 0 if order == "col" else 1, mode,
+                                                comm.h if comm is not None else None, C.byref(self.h)))
         r0, nr = C.c_int64(), C.c_int64()
         _check(lib().sb200_op_local_rows(self.h, C.byref(r0), C.byref(nr)))
         self.row0, self.nrows_local = r0.value, nr.value
@@ -307,6 +312,7 @@ class UserOp:
         self.row0, self.nrows_local = 0, n
         self.comm = None
         self._exc = None
+        self.user = op
 
         def tramp(xp, yp, _):
             try:
@@ -323,6 +329,11 @@ class UserOp:
 
     def cols(self):
         return self.n
+
+    def set_shift(self, sigma):
+        """Forwarded to the user's shift-solve operator (SymEigsShiftSolver.h:194 calls op.set_shift(sigma))."""
+        if hasattr(self.user, "set_shift"):
+            self.user.set_shift(sigma)
 
     def perform_op(self, x_in, y_out=None):
         x = np.ascontiguousarray(x_in, dtype=np.float64)
@@ -358,6 +369,31 @@ class SparseGenMatProd(_SparseOp):
         super().__init__(mat, comm=comm)
 
 
+class SparseSymShiftSolve(_SparseOp):
+    """MatOp/SparseSymShiftSolve.h — perform_op computes y = (A - sigma I)^{-1} x after set_shift(sigma).  Device
+    implementation: block cyclic reduction, banded matrices (half-bandwidth <= 32) only."""
+    _mode = 1
+    _shift_solve = True
+
+    def __init__(self, mat, uplo: str = "lower"):
+        super().__init__(mat, comm=None, uplo=uplo)
+
+    def set_shift(self, sigma: float):
+        _check(lib().sb200_op_set_shift(self.h, C.c_double(sigma)))
+
+    def set_refine(self, steps: int):
+        _check(lib().sb200_op_shift_solve_refine(self.h, int(steps)))
+
+    def layout(self) -> dict:
+        bw, blk, lev, rows = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        _check(lib().sb200_op_shift_solve_info(self.h, C.byref(bw), C.byref(blk), C.byref(rows), C.byref(lev)))
+        return dict(half_bandwidth=bw.value, block=blk.value, block_rows=rows.value, levels=lev.value)
+
+    def solve_device_time(self, repeat: int = 10) -> float:
+        """CUDA-event time (ms) of one device-resident solve."""
+        return self.spmv_device_time(repeat)
+
+
 class SymEigsSolver:
     """SymEigsSolver.h:133-160 / HermEigsBase.h — same call sequence as the reference."""
 
@@ -365,6 +401,9 @@ class SymEigsSolver:
         self.op = op
         self.nev, self.ncv = int(nev), int(ncv)
         self.h = C.c_void_p()
+        self._create(op, nev, ncv)
+
+    def _create(self, op, nev, ncv):
         _check(lib().sb200_sym_create(op.h, C.c_int64(nev), C.c_int64(ncv), C.byref(self.h)))
 
     def init(self, init_resid: np.ndarray | None = None):
@@ -439,6 +478,20 @@ class SymEigsSolver:
             self.close()
         except Exception:
             pass
+
+
+class SymEigsShiftSolver(SymEigsSolver):
+    """SymEigsShiftSolver.h:148-196 — shift-and-invert mode: `op` computes (A - sigma I)^{-1} x (SparseSymShiftSolve, or a
+    UserOp with a set_shift method); eigenvalues come back as lambda = 1/nu + sigma."""
+
+    def __init__(self, op, nev: int, ncv: int, sigma: float):
+        self.sigma = float(sigma)
+        super().__init__(op, nev, ncv)
+        if isinstance(op, UserOp):
+            op.set_shift(self.sigma)
+
+    def _create(self, op, nev, ncv):
+        _check(lib().sb200_sym_create_shift(op.h, C.c_int64(nev), C.c_int64(ncv), C.c_double(self.sigma), C.byref(self.h)))
 
 
 class GenEigsSolver:

@@ -13,6 +13,7 @@ sb200_op* op_create_sparse(int64_t n, const void* outer, int outer_is_64, const 
 sb200_op* op_create_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64_t* rowptr_local, const int32_t* col, const double* values, sb200_comm* comm);
 void op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev);
 sb200_op* op_create_callback(int64_t n, void (*fn)(const double*, double*, void*), void* user);
+sb200_op* op_create_shift_solve(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values, int storage_order, int matrix_mode);
 void op_perform_op_host(sb200_op* op, const double* x_host, double* y_host);
 
 sb200_sym_solver* sym_create(sb200_op* op, int64_t nev, int64_t ncv, bool shift_mode, double sigma);
@@ -182,6 +183,36 @@ int sb200_op_create_callback(int64_t n, sb200_matvec_fn fn, void* user, sb200_op
     *out = op_create_callback(n, fn, user);
     ABI_CATCH
 }
+int sb200_op_create_shift_solve(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values, int storage_order, int matrix_mode,
+                                sb200_op** out)
+{
+    ABI_TRY
+    ABI_NONNULL(out);
+    ABI_NONNULL(outer);
+    *out = op_create_shift_solve(n, outer, outer_is_64, inner, values, storage_order, matrix_mode);
+    ABI_CATCH
+}
+int sb200_op_set_shift(sb200_op* op, double sigma)
+{
+    ABI_TRY
+    ABI_NONNULL(op);
+    band_set_shift(op, sigma);
+    ABI_CATCH
+}
+int sb200_op_shift_solve_info(const sb200_op* op, int* half_bandwidth, int* block, int64_t* block_rows, int* levels)
+{
+    ABI_TRY
+    ABI_NONNULL(op);
+    band_info(op, half_bandwidth, block, block_rows, levels);
+    ABI_CATCH
+}
+int sb200_op_shift_solve_refine(sb200_op* op, int steps)
+{
+    ABI_TRY
+    ABI_NONNULL(op);
+    band_set_refine(op, steps);
+    ABI_CATCH
+}
 int sb200_op_rows(const sb200_op* op, int64_t* rows)
 {
     ABI_TRY
@@ -275,6 +306,28 @@ int sb200_sym_create(sb200_op* op, int64_t nev, int64_t ncv, sb200_sym_solver** 
     ABI_TRY
     ABI_NONNULL(out);
     *out = sym_create(op, nev, ncv, false, 0.0);
+    ABI_CATCH
+}
+int sb200_sym_create_shift(sb200_op* op, int64_t nev, int64_t ncv, double sigma, sb200_sym_solver** out)
+{
+    ABI_TRY
+    ABI_NONNULL(out);
+    ABI_NONNULL(op);
+    // Base(op, nev, ncv) argument checks first, then op.set_shift(sigma) (SymEigsShiftSolver.h:190-195)
+    sb200_sym_solver* s = sym_create(op, nev, ncv, true, sigma);
+    if (op->band)
+    {
+        try
+        {
+            band_set_shift(op, sigma);
+        }
+        catch (...)
+        {
+            sym_destroy(s);
+            throw;
+        }
+    }
+    *out = s;
     ABI_CATCH
 }
 int sb200_sym_init(sb200_sym_solver* s, const double* init_resid_or_null)

@@ -1,0 +1,848 @@
+// Device shift-solve operator  y = (A - sigma I)^{-1} x  for banded A          
+// Replaces SparseSymShiftSolve (MatOp/SparseSymShiftSolve.h:85-109: set_shift = Eigen::SparseLU factorisation,
+// perform_op = solve) for the matrix class of BASELINE config 5 (symmetric banded, half-bandwidth <= 32).
+//
+// B200 design.  A sequential band LU (what a CPU does, ~n dependent steps) would leave 147 SMs idle, so the
+// factorisation is block cyclic reduction (BCR) on the block-tridiagonal form of A - sigma I with B x B blocks,
+// B >= half-bandwidth: log2(n/B) levels, every level embarrassingly parallel over block rows, one warp per block row.
+//
+//   level l (stride s = 2^l), active rows i = k s - 1 (k = 1..floor(N/s)); odd k are eliminated, even k kept:
+//     eliminated j:  Dinv_j = D_j^{-1} (Gauss-Jordan, partial pivoting inside the block), GL_j = Dinv_j L_j, GU_j = Dinv_j U_j
+//     kept i (p = i - s, q = i + s):  ML_i = L_i Dinv_p, MU_i = U_i Dinv_q,
+//                                     D_i <- D_i - L_i GU_p - U_i GL_q,  L_i <- -L_i GL_p,  U_i <- -U_i GU_q
+//   solve:  forward  l = 0..L-1 : f_i -= ML_i f_p + MU_i f_q            (kept rows)
+//           top               : x_t = Dinv_t f_t
+//           backward l = L-1..0 : x_j = Dinv_j f_j - GL_j x_{j-s} - GU_j x_{j+s}   (eliminated rows)
+//   A solve is ~5 N B^2 doubles of streamed factors (120 MB at n = 2e5, B = 15: L2 resident on B200) in 2 L + 1 parallel
+//   sweeps; the levels with <= 64 active rows run inside one CTA.  One step of iterative refinement with the CSR
+//   operator (r = x - (A - sigma I) y) removes the growth BCR can show on an indefinite shifted matrix.
+//
+// Pivoting is confined to the diagonal blocks, so a shift for which some reduced diagonal block is singular is
+// rejected by set_shift (std::invalid_argument in the shim, like the reference's "factorization failed with the given
+// shift"); set_shift also verifies the factorisation with one random solve.
+#include <cmath>
+
+#include "host.h"
+
+namespace sb200 {
+
+namespace {
+
+constexpr int kTopRows = 64;  // levels with at most this many active rows are fused into one CTA
+constexpr int kTopThreads = 1024;
+
+__global__ void band_width_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int64_t nrows, int64_t row0, int* out_bw)
+{
+    int bw = 0;
+    for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int64_t i = row0 + r;
+        for (int p = rowptr[r]; p < rowptr[r + 1]; p++)
+        {
+            const int64_t d = i - col[p];
+            bw = max(bw, (int) (d < 0 ? -d : d));
+        }
+    }
+    if (bw > 0)
+        atomicMax(out_bw, bw);
+}
+
+// blocks of A - sigma I from the CSR: D (diagonal), Lo (coupling to block row i-1), Up (to i+1); column-major B x B each
+__global__ void band_scatter_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, int64_t n, int B, double* D,
+                                    double* Lo, double* Up, int* flag)
+{
+    const int64_t bb = (int64_t) B * B;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int64_t bi = i / B;
+        const int ri = (int) (i % B);
+        for (int p = rowptr[i]; p < rowptr[i + 1]; p++)
+        {
+            const int64_t j = col[p];
+            const int64_t bj = j / B;
+            const int cj = (int) (j % B);
+            double* dst = bj == bi ? D : (bj == bi - 1 ? Lo : (bj == bi + 1 ? Up : nullptr));
+            if (!dst)
+            {
+                *flag = 2;
+                continue;
+            }
+            atomicAdd(dst + bi * bb + ri + (int64_t) cj * B, val[p]);  // column blocks of the operator may split a row
+        }
+    }
+}
+
+__global__ void band_diag_kernel(double* D, int64_t n, int64_t N, int B, double sigma)
+{
+    const int64_t bb = (int64_t) B * B;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < N * B; i += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int64_t bi = i / B;
+        const int ri = (int) (i % B);
+        double* d = D + bi * bb + ri + (int64_t) ri * B;
+        if (i < n)
+            *d -= sigma;
+        else
+            *d = 1.0;  // identity padding of the last block
+    }
+}
+
+// element (r, c) of A * Bm, both B x B column-major in shared memory
+__device__ __forceinline__ double row_dot(const double* A, const double* Bm, int B, int r, int c)
+{
+    double acc = 0.0;
+    for (int k = 0; k < B; k++)
+        acc = fma(A[r + k * B], Bm[k + c * B], acc);
+    return acc;
+}
+
+__device__ __forceinline__ void load_block(double* dst_smem, const double* src, int bb, int lane)
+{
+    for (int e = lane; e < bb; e += 32)
+        dst_smem[e] = src[e];
+    __syncwarp();
+}
+
+// ---- factor, eliminated rows of one level: one warp (= one CTA) per row ----
+__global__ void __launch_bounds__(32) bcr_eliminate_kernel(const double* __restrict__ D, const double* __restrict__ Lo, const double* __restrict__ Up, double* Dinv,
+                                                           double* GL, double* GU, int64_t N, int B, int level, int64_t count, int* flag)
+{
+    extern __shared__ double sm[];
+    const int bb = B * B;
+    double* M = sm;            // working copy of D_j
+    double* Inv = sm + bb;     // becomes D_j^{-1}
+    double* T = sm + 2 * bb;   // operand
+    const int lane = threadIdx.x;
+    const int64_t s = (int64_t) 1 << level;
+    const int64_t k = 2 * (int64_t) blockIdx.x + 1;  // odd k
+    if (k > count)
+        return;
+    const int64_t j = k * s - 1;
+    (void) N;
+    load_block(M, D + j * bb, bb, lane);
+    for (int e = lane; e < bb; e += 32)
+        Inv[e] = (e % B == e / B) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int kk = 0; kk < B; kk++)
+    {
+        // partial pivoting inside the block
+        double best = (lane >= kk && lane < B) ? fabs(M[lane + kk * B]) : -1.0;
+        int arg = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ob > best || (ob == best && oa < arg))
+            {
+                best = ob;
+                arg = oa;
+            }
+        }
+        if (!(best > 0.0))
+        {
+            if (lane == 0)
+                *flag = 1;  // singular (or NaN) reduced diagonal block
+            return;
+        }
+        if (arg != kk && lane < B)
+        {
+            double t = M[kk + lane * B];
+            M[kk + lane * B] = M[arg + lane * B];
+            M[arg + lane * B] = t;
+            t = Inv[kk + lane * B];
+            Inv[kk + lane * B] = Inv[arg + lane * B];
+            Inv[arg + lane * B] = t;
+        }
+        __syncwarp();
+        const double piv = M[kk + kk * B];
+        __syncwarp();
+        if (lane < B)
+        {
+            M[kk + lane * B] /= piv;
+            Inv[kk + lane * B] /= piv;
+        }
+        __syncwarp();
+        if (lane < B && lane != kk)
+        {
+            const double fct = M[lane + kk * B];
+            if (fct != 0.0)
+                for (int c = 0; c < B; c++)
+                {
+                    M[lane + c * B] = fma(-fct, M[kk + c * B], M[lane + c * B]);
+                    Inv[lane + c * B] = fma(-fct, Inv[kk + c * B], Inv[lane + c * B]);
+                }
+        }
+        __syncwarp();
+    }
+    for (int e = lane; e < bb; e += 32)
+        Dinv[j * bb + e] = Inv[e];
+    // GL = Dinv * L_j, GU = Dinv * U_j
+    load_block(T, Lo + j * bb, bb, lane);
+    if (lane < B)
+        for (int c = 0; c < B; c++)
+            GL[j * bb + lane + c * B] = row_dot(Inv, T, B, lane, c);
+    __syncwarp();
+    load_block(T, Up + j * bb, bb, lane);
+    if (lane < B)
+        for (int c = 0; c < B; c++)
+            GU[j * bb + lane + c * B] = row_dot(Inv, T, B, lane, c);
+}
+
+// ---- factor, kept rows of one level ----
+__global__ void __launch_bounds__(32) bcr_update_kernel(double* D, double* Lo, double* Up, const double* __restrict__ Dinv, const double* __restrict__ GL,
+                                                        const double* __restrict__ GU, double* ML, double* MU, int64_t N, int B, int level, int64_t count)
+{
+    extern __shared__ double sm[];
+    const int bb = B * B;
+    double* Ls = sm;
+    double* Us = sm + bb;
+    double* T = sm + 2 * bb;
+    const int lane = threadIdx.x;
+    const int64_t s = (int64_t) 1 << level;
+    const int64_t k = 2 * ((int64_t) blockIdx.x + 1);  // even k
+    if (k > count)
+        return;
+    const int64_t i = k * s - 1, p = i - s, q = i + s;
+    const bool has_q = q < N;
+    double* ml = ML + (int64_t) blockIdx.x * bb;
+    double* mu = MU + (int64_t) blockIdx.x * bb;
+    load_block(Ls, Lo + i * bb, bb, lane);
+    load_block(Us, Up + i * bb, bb, lane);
+    double* Di = D + i * bb;
+    // --- left neighbour p ---
+    load_block(T, Dinv + p * bb, bb, lane);
+    if (lane < B)
+        for (int c = 0; c < B; c++)
+            ml[lane + c * B] = row_dot(Ls, T, B, lane, c);
+    __syncwarp();
+    load_block(T, GU + p * bb, bb, lane);
+    if (lane < B)
+        for (int c = 0; c < B; c++)
+            Di[lane + c * B] -= row_dot(Ls, T, B, lane, c);
+    __syncwarp();
+    load_block(T, GL + p * bb, bb, lane);
+    if (lane < B)
+        for (int c = 0; c < B; c++)
+            Lo[i * bb + lane + c * B] = -row_dot(Ls, T, B, lane, c);
+    __syncwarp();
+    // --- right neighbour q ---
+    if (has_q)
+    {
+        load_block(T, Dinv + q * bb, bb, lane);
+        if (lane < B)
+            for (int c = 0; c < B; c++)
+                mu[lane + c * B] = row_dot(Us, T, B, lane, c);
+        __syncwarp();
+        load_block(T, GL + q * bb, bb, lane);
+        if (lane < B)
+            for (int c = 0; c < B; c++)
+                Di[lane + c * B] -= row_dot(Us, T, B, lane, c);
+        __syncwarp();
+        load_block(T, GU + q * bb, bb, lane);
+        if (lane < B)
+            for (int c = 0; c < B; c++)
+                Up[i * bb + lane + c * B] = -row_dot(Us, T, B, lane, c);
+    }
+    else
+    {
+        for (int e = lane; e < bb; e += 32)
+        {
+            mu[e] = 0.0;
+            Up[i * bb + e] = 0.0;
+        }
+    }
+}
+
+// y_r = sum_c M[r + c B] * v[c], v held one entry per lane
+__device__ __forceinline__ double mat_vec_lane(const double* __restrict__ M, int B, int lane, double v_lane)
+{
+    double acc = 0.0;
+    for (int c = 0; c < B; c++)
+    {
+        const double vc = __shfl_sync(0xffffffffu, v_lane, c);
+        if (lane < B)
+            acc = fma(M[lane + c * B], vc, acc);
+    }
+    return acc;
+}
+
+struct BcrView
+{
+    const double* Dinv;
+    const double* GL;
+    const double* GU;
+    const double* ML;  // level-major: rows kept at level l start at ml_off[l] blocks
+    const double* MU;
+    int64_t N;
+    int B;
+    int levels;             // L: number of elimination levels; the top row is 2^L - 1
+    int64_t ml_off[40];
+};
+
+__device__ __forceinline__ void forward_row(const BcrView& v, double* f, int level, int64_t idx, int lane)
+{
+    const int bb = v.B * v.B;
+    const int64_t s = (int64_t) 1 << level;
+    const int64_t k = 2 * (idx + 1);
+    const int64_t i = k * s - 1, p = i - s, q = i + s;
+    const double* ml = v.ML + (v.ml_off[level] + idx) * bb;
+    const double* mu = v.MU + (v.ml_off[level] + idx) * bb;
+    const double fp = lane < v.B ? f[p * v.B + lane] : 0.0;
+    double acc = mat_vec_lane(ml, v.B, lane, fp);
+    if (q < v.N)
+    {
+        const double fq = lane < v.B ? f[q * v.B + lane] : 0.0;
+        acc += mat_vec_lane(mu, v.B, lane, fq);
+    }
+    if (lane < v.B)
+        f[i * v.B + lane] -= acc;
+}
+
+__device__ __forceinline__ void backward_row(const BcrView& v, double* f, int level, int64_t idx, int lane)
+{
+    const int bb = v.B * v.B;
+    const int64_t s = (int64_t) 1 << level;
+    const int64_t k = 2 * idx + 1;
+    const int64_t j = k * s - 1, p = j - s, q = j + s;
+    const double fj = lane < v.B ? f[j * v.B + lane] : 0.0;
+    double acc = mat_vec_lane(v.Dinv + j * bb, v.B, lane, fj);
+    if (p >= 0)
+    {
+        const double xp = lane < v.B ? f[p * v.B + lane] : 0.0;
+        acc -= mat_vec_lane(v.GL + j * bb, v.B, lane, xp);
+    }
+    if (q < v.N)
+    {
+        const double xq = lane < v.B ? f[q * v.B + lane] : 0.0;
+        acc -= mat_vec_lane(v.GU + j * bb, v.B, lane, xq);
+    }
+    if (lane < v.B)
+        f[j * v.B + lane] = acc;
+}
+
+__global__ void __launch_bounds__(128) bcr_forward_kernel(BcrView v, double* f, int level, int64_t nkept)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t) blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (w < nkept)
+        forward_row(v, f, level, w, lane);
+}
+
+__global__ void __launch_bounds__(128) bcr_backward_kernel(BcrView v, double* f, int level, int64_t nelim)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t) blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (w < nelim)
+        backward_row(v, f, level, w, lane);
+}
+
+// levels [first, L) forward, the top row, then backward L-1 .. first, inside one CTA
+__global__ void __launch_bounds__(kTopThreads) bcr_top_kernel(BcrView v, double* f, int first)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kTopThreads / 32;
+    for (int l = first; l < v.levels; l++)
+    {
+        const int64_t cnt = v.N >> l, nkept = cnt / 2;
+        for (int64_t w = warp; w < nkept; w += nw)
+            forward_row(v, f, l, w, lane);
+        __syncthreads();
+    }
+    if (warp == 0)
+    {
+        const int64_t t = ((int64_t) 1 << v.levels) - 1;
+        const double ft = lane < v.B ? f[t * v.B + lane] : 0.0;
+        const double xt = mat_vec_lane(v.Dinv + t * v.B * v.B, v.B, lane, ft);
+        if (lane < v.B)
+            f[t * v.B + lane] = xt;
+    }
+    __syncthreads();
+    for (int l = v.levels - 1; l >= first; l--)
+    {
+        const int64_t cnt = v.N >> l, nelim = (cnt + 1) / 2;
+        for (int64_t w = warp; w < nelim; w += nw)
+            backward_row(v, f, l, w, lane);
+        __syncthreads();
+    }
+}
+
+__global__ void pad_copy_kernel(const double* __restrict__ x, double* __restrict__ xb, int64_t n, int64_t npad)
+{
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < npad; i += (int64_t) gridDim.x * blockDim.x)
+        xb[i] = i < n ? x[i] : 0.0;
+}
+
+// r = x - (t - sigma y)   with t = A y
+__global__ void refine_residual_kernel(const double* __restrict__ x, const double* __restrict__ t, const double* __restrict__ y, double sigma, double* __restrict__ r,
+                                       int64_t n, int64_t npad)
+{
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < npad; i += (int64_t) gridDim.x * blockDim.x)
+        r[i] = i < n ? x[i] - (t[i] - sigma * y[i]) : 0.0;
+}
+
+__global__ void add_out_kernel(const double* __restrict__ y0, const double* __restrict__ dy, double* __restrict__ y, int64_t n)
+{
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+        y[i] = dy ? y0[i] + dy[i] : y0[i];
+}
+
+// ---- small matrices that are not banded (the reference's own fixtures, test/SymEigsShift.cpp:148-186: random sparse
+//      n <= 1000): explicit inverse by Gauss-Jordan with partial pivoting, one grid-wide rank-1 update per pivot;
+//      the solve is a dense GEMV.  n <= kDenseMax only.
+constexpr int kDenseMax = 2048;
+
+__global__ void dense_scatter_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, int64_t n, double* M)
+{
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+        for (int p = rowptr[i]; p < rowptr[i + 1]; p++)
+            atomicAdd(M + i + (int64_t) col[p] * n, val[p]);
+}
+
+__global__ void dense_init_kernel(double* M, double* Inv, int64_t n, double sigma)
+{
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+    {
+        M[i + i * n] -= sigma;
+        Inv[i + i * n] = 1.0;
+    }
+}
+
+// pivot row of column k among rows >= k (largest magnitude, lowest index on ties)
+__global__ void __launch_bounds__(1024) gj_pivot_kernel(const double* __restrict__ M, int64_t n, int k, int* piv_row, double* piv_val, int* flag)
+{
+    __shared__ double s_best[32];
+    __shared__ int s_arg[32];
+    double best = -1.0;
+    int arg = k;
+    for (int r = k + threadIdx.x; r < n; r += blockDim.x)
+    {
+        const double a = fabs(M[r + (int64_t) k * n]);
+        if (a > best)
+        {
+            best = a;
+            arg = r;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ob > best || (ob == best && oa < arg))
+        {
+            best = ob;
+            arg = oa;
+        }
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        s_best[threadIdx.x >> 5] = best;
+        s_arg[threadIdx.x >> 5] = arg;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int w = 1; w < (int) (blockDim.x >> 5); w++)
+            if (s_best[w] > best || (s_best[w] == best && s_arg[w] < arg))
+            {
+                best = s_best[w];
+                arg = s_arg[w];
+            }
+        *piv_row = arg;
+        *piv_val = M[arg + (int64_t) k * n];
+        if (!(best > 0.0))
+            *flag = 1;
+    }
+}
+
+// swap rows k and p, scale the new row k by 1/pivot, save column k (after the swap) for the update
+__global__ void gj_swap_scale_kernel(double* M, double* Inv, int64_t n, int k, const int* piv_row, const double* piv_val, double* colk)
+{
+    const int p = *piv_row;
+    const double piv = *piv_val;
+    const double inv_piv = piv != 0.0 ? 1.0 / piv : 0.0;
+    for (int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; c < 2 * n; c += (int64_t) gridDim.x * blockDim.x)
+    {
+        double* X = c < n ? M : Inv;
+        const int64_t cc = c < n ? c : c - n;
+        const double a = X[k + cc * n], b = X[p + cc * n];
+        X[p + cc * n] = a;
+        X[k + cc * n] = b * inv_piv;
+    }
+    for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t) gridDim.x * blockDim.x)
+    {
+        // column k after the row swap, read from the pre-swap values (this kernel only rewrites rows k and p)
+        double v;
+        if (r == k)
+            v = 0.0;  // row k itself is not updated
+        else if (r == p)
+            v = M[k + (int64_t) k * n];  // old row k lands in row p; may race with the swap above: see gj_colk_fix
+        else
+            v = M[r + (int64_t) k * n];
+        colk[r] = v;
+    }
+}
+
+// colk[p] must be the pre-swap M(k,k); it is saved by the pivot step instead of being read during the swap
+__global__ void gj_save_kk_kernel(const double* __restrict__ M, int64_t n, int k, double* save) { *save = M[k + (int64_t) k * n]; }
+
+__global__ void gj_fix_colk_kernel(double* colk, int k, const int* piv_row, const double* save)
+{
+    const int p = *piv_row;
+    if (p != k)
+        colk[p] = *save;
+}
+
+__global__ void gj_eliminate_kernel(double* M, double* Inv, int64_t n, int k, const double* __restrict__ colk)
+{
+    const int64_t total = 2 * n * n;
+    for (int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x)
+    {
+        double* X = e < n * n ? M : Inv;
+        const int64_t ee = e < n * n ? e : e - n * n;
+        const int64_t r = ee % n, c = ee / n;
+        const double f = colk[r];
+        if (f != 0.0)
+            X[ee] = fma(-f, X[k + c * n], X[ee]);
+    }
+}
+
+// y = Inv * x  (column-major n x n): one warp per 32 rows, lanes along rows
+__global__ void __launch_bounds__(256) dense_gemv_kernel(const double* __restrict__ Inv, const double* __restrict__ x, double* __restrict__ y, int64_t n)
+{
+    __shared__ double s_part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = (int64_t) blockIdx.x * 32 + lane;
+    double acc = 0.0;
+    if (r < n)
+        for (int64_t c = warp; c < n; c += 8)
+            acc = fma(Inv[r + c * n], x[c], acc);
+    s_part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && r < n)
+    {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++)
+            t += s_part[w][lane];
+        y[r] = t;
+    }
+}
+
+int grid_for(int64_t n, int block = 256)
+{
+    const int sms = device_info().sm_count;
+    return (int) std::max<int64_t>(1, std::min<int64_t>((n + block - 1) / block, (int64_t) sms * 8));
+}
+
+}  // namespace
+
+struct BandSolve
+{
+    int64_t n = 0, N = 0;
+    int B = 0, levels = 0, first_top = 0, bw = 0;
+    bool factored = false;
+    double sigma = 0.0;
+    int refine = 1;
+    DevBuf<double> D, Lo, Up, Dinv, GL, GU, ML, MU;
+    DevBuf<double> xb, rb, t;
+    DevBuf<int> flag;
+    BcrView view;
+    int64_t solves = 0, launches = 0;
+    // dense fallback (small non-banded matrices)
+    bool dense = false;
+    DevBuf<double> Mden, Iden, colk, scal;
+    DevBuf<int> ipiv;
+};
+
+void band_destroy(BandSolve* b) { delete b; }
+
+// half-bandwidth of the operator's CSR and the block layout; no factorisation yet
+BandSolve* band_create(sb200_op* op)
+{
+    const DeviceCsr& A = op->A;
+    SB200_REQUIRE(A.row0 == 0 && A.nrows == A.n, SB200_INVALID_ARGUMENT, "the shift-solve operator is single-GPU (whole matrix on one device)");
+    std::unique_ptr<BandSolve> b(new BandSolve());
+    b->n = A.n;
+    b->flag.alloc(2);
+    SB200_CUDA_CHECK(cudaMemsetAsync(b->flag.get(), 0, sizeof(int) * 2, op->stream));
+    auto scan = [&](const int* rp, const int* ci) { band_width_kernel<<<grid_for(A.n), 256, 0, op->stream>>>(rp, ci, A.nrows, A.row0, b->flag.get() + 1); };
+    if (A.blocks.empty())
+        scan(A.rowptr.get(), A.col.get());
+    else
+        for (const CsrBlock& blk : A.blocks)
+            scan(blk.rowptr.get(), blk.col.get());
+    SB200_CUDA_CHECK(cudaGetLastError());
+    int h[2];
+    SB200_CUDA_CHECK(cudaMemcpyAsync(h, b->flag.get(), sizeof(h), cudaMemcpyDeviceToHost, op->stream));
+    SB200_CUDA_CHECK(cudaStreamSynchronize(op->stream));
+    b->bw = h[1];
+    if (b->bw > 32)
+    {
+        SB200_REQUIRE(A.n <= kDenseMax, SB200_INVALID_ARGUMENT,
+                      "SparseSymShiftSolve: half-bandwidth " + std::to_string(b->bw) + " exceeds 32 and n exceeds " + std::to_string(kDenseMax) +
+                          "; the device shift-solve handles banded matrices (and small general ones) only");
+        b->dense = true;
+        b->B = 0;
+        b->N = 0;
+        const size_t nn = (size_t) A.n * A.n;
+        b->Mden.alloc(nn);
+        b->Iden.alloc(nn);
+        b->colk.alloc((size_t) A.n);
+        b->scal.alloc(2);
+        b->ipiv.alloc(1);
+        b->xb.alloc((size_t) A.n);
+        b->rb.alloc((size_t) A.n);
+        b->t.alloc((size_t) A.n);
+        return b.release();
+    }
+    b->B = std::max(b->bw, 4);
+    b->N = (A.n + b->B - 1) / b->B;
+    b->levels = 0;
+    while ((b->N >> (b->levels + 1)) >= 1)
+        b->levels++;
+    SB200_REQUIRE(b->levels < 40, SB200_LOGIC, "too many BCR levels");
+    b->first_top = 0;
+    while (b->first_top < b->levels && (b->N >> b->first_top) > kTopRows)
+        b->first_top++;
+    const size_t bb = (size_t) b->B * b->B;
+    const size_t tot = (size_t) b->N * bb;
+    b->D.alloc(tot);
+    b->Lo.alloc(tot);
+    b->Up.alloc(tot);
+    b->Dinv.alloc(tot);
+    b->GL.alloc(tot);
+    b->GU.alloc(tot);
+    int64_t kept_total = 0;
+    for (int l = 0; l < b->levels; l++)
+    {
+        b->view.ml_off[l] = kept_total;
+        kept_total += (b->N >> l) / 2;
+    }
+    b->ML.alloc((size_t) std::max<int64_t>(kept_total, 1) * bb);
+    b->MU.alloc((size_t) std::max<int64_t>(kept_total, 1) * bb);
+    const size_t npad = (size_t) b->N * b->B;
+    b->xb.alloc(npad);
+    b->rb.alloc(npad);
+    b->t.alloc(npad);
+    b->view.Dinv = b->Dinv.get();
+    b->view.GL = b->GL.get();
+    b->view.GU = b->GU.get();
+    b->view.ML = b->ML.get();
+    b->view.MU = b->MU.get();
+    b->view.N = b->N;
+    b->view.B = b->B;
+    b->view.levels = b->levels;
+    return b.release();
+}
+
+// one BCR solve in place on the padded vector f (N*B entries)
+static void bcr_solve_inplace(BandSolve* b, double* f, cudaStream_t st)
+{
+    for (int l = 0; l < b->first_top; l++)
+    {
+        const int64_t nkept = (b->N >> l) / 2;
+        bcr_forward_kernel<<<(unsigned) ((nkept + 3) / 4), 128, 0, st>>>(b->view, f, l, nkept);
+        b->launches++;
+    }
+    bcr_top_kernel<<<1, kTopThreads, 0, st>>>(b->view, f, b->first_top);
+    b->launches++;
+    for (int l = b->first_top - 1; l >= 0; l--)
+    {
+        const int64_t nelim = ((b->N >> l) + 1) / 2;
+        bcr_backward_kernel<<<(unsigned) ((nelim + 3) / 4), 128, 0, st>>>(b->view, f, l, nelim);
+        b->launches++;
+    }
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+// y = (A - sigma I)^{-1} x, device pointers (n entries each; x == y allowed)
+void band_solve_device(sb200_op* op, const double* x, double* y)
+{
+    BandSolve* b = op->band;
+    SB200_REQUIRE(b && b->factored, SB200_LOGIC, "SparseSymShiftSolve: set_shift() has not been called");
+    cudaStream_t st = op->stream;
+    if (b->dense)
+    {
+        const int64_t n = b->n;
+        const unsigned g = (unsigned) ((n + 31) / 32);
+        dense_gemv_kernel<<<g, 256, 0, st>>>(b->Iden.get(), x, b->xb.get(), n);
+        if (b->refine > 0)
+        {
+            launch_spmv(op->A, op->plan, b->xb.get(), b->t.get(), st);
+            refine_residual_kernel<<<grid_for(n), 256, 0, st>>>(x, b->t.get(), b->xb.get(), b->sigma, b->rb.get(), n, n);
+            dense_gemv_kernel<<<g, 256, 0, st>>>(b->Iden.get(), b->rb.get(), b->t.get(), n);
+            add_out_kernel<<<grid_for(n), 256, 0, st>>>(b->xb.get(), b->t.get(), y, n);
+            b->launches += 5;
+        }
+        else
+        {
+            add_out_kernel<<<grid_for(n), 256, 0, st>>>(b->xb.get(), nullptr, y, n);
+            b->launches += 2;
+        }
+        SB200_CUDA_CHECK(cudaGetLastError());
+        b->solves++;
+        return;
+    }
+    const int64_t n = b->n, npad = b->N * b->B;
+    pad_copy_kernel<<<grid_for(npad), 256, 0, st>>>(x, b->xb.get(), n, npad);
+    bcr_solve_inplace(b, b->xb.get(), st);
+    b->launches++;
+    if (b->refine > 0)
+    {
+        // r = x - (A - sigma I) y0 ; y = y0 + solve(r)
+        launch_spmv(op->A, op->plan, b->xb.get(), b->t.get(), st);
+        refine_residual_kernel<<<grid_for(npad), 256, 0, st>>>(x, b->t.get(), b->xb.get(), b->sigma, b->rb.get(), n, npad);
+        bcr_solve_inplace(b, b->rb.get(), st);
+        add_out_kernel<<<grid_for(n), 256, 0, st>>>(b->xb.get(), b->rb.get(), y, n);
+        b->launches += 3;
+    }
+    else
+    {
+        add_out_kernel<<<grid_for(n), 256, 0, st>>>(b->xb.get(), nullptr, y, n);
+        b->launches++;
+    }
+    SB200_CUDA_CHECK(cudaGetLastError());
+    b->solves++;
+}
+
+static void factor_dense(sb200_op* op, BandSolve* b, double sigma)
+{
+    const DeviceCsr& A = op->A;
+    cudaStream_t st = op->stream;
+    const int64_t n = A.n;
+    b->Mden.zero(st);
+    b->Iden.zero(st);
+    auto scat = [&](const int* rp, const int* ci, const double* v) { dense_scatter_kernel<<<grid_for(n), 256, 0, st>>>(rp, ci, v, n, b->Mden.get()); };
+    if (A.blocks.empty())
+        scat(A.rowptr.get(), A.col.get(), A.val.get());
+    else
+        for (const CsrBlock& blk : A.blocks)
+            scat(blk.rowptr.get(), blk.col.get(), blk.val.get());
+    dense_init_kernel<<<grid_for(n), 256, 0, st>>>(b->Mden.get(), b->Iden.get(), n, sigma);
+    const int ge = grid_for(2 * n * n);
+    for (int k = 0; k < (int) n; k++)
+    {
+        gj_pivot_kernel<<<1, 1024, 0, st>>>(b->Mden.get(), n, k, b->ipiv.get(), b->scal.get(), b->flag.get());
+        gj_save_kk_kernel<<<1, 1, 0, st>>>(b->Mden.get(), n, k, b->scal.get() + 1);
+        gj_swap_scale_kernel<<<grid_for(2 * n), 256, 0, st>>>(b->Mden.get(), b->Iden.get(), n, k, b->ipiv.get(), b->scal.get(), b->colk.get());
+        gj_fix_colk_kernel<<<1, 1, 0, st>>>(b->colk.get(), k, b->ipiv.get(), b->scal.get() + 1);
+        gj_eliminate_kernel<<<ge, 256, 0, st>>>(b->Mden.get(), b->Iden.get(), n, k, b->colk.get());
+    }
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+static void factor_band(sb200_op* op, BandSolve* b, double sigma)
+{
+    const DeviceCsr& A = op->A;
+    cudaStream_t st = op->stream;
+    const int B = b->B;
+    const size_t bb = (size_t) B * B;
+    b->D.zero(st);
+    b->Lo.zero(st);
+    b->Up.zero(st);
+    auto scatter = [&](const int* rp, const int* ci, const double* v) {
+        band_scatter_kernel<<<grid_for(A.n), 256, 0, st>>>(rp, ci, v, A.n, B, b->D.get(), b->Lo.get(), b->Up.get(), b->flag.get());
+    };
+    if (A.blocks.empty())
+        scatter(A.rowptr.get(), A.col.get(), A.val.get());
+    else
+        for (const CsrBlock& blk : A.blocks)
+            scatter(blk.rowptr.get(), blk.col.get(), blk.val.get());
+    band_diag_kernel<<<grid_for(b->N * B), 256, 0, st>>>(b->D.get(), A.n, b->N, B, sigma);
+    SB200_CUDA_CHECK(cudaGetLastError());
+    const size_t smem = 3 * bb * sizeof(double);
+    SB200_CUDA_CHECK(cudaFuncSetAttribute((const void*) bcr_eliminate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    SB200_CUDA_CHECK(cudaFuncSetAttribute((const void*) bcr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    for (int l = 0; l < b->levels; l++)
+    {
+        const int64_t cnt = b->N >> l, nelim = (cnt + 1) / 2, nkept = cnt / 2;
+        bcr_eliminate_kernel<<<(unsigned) nelim, 32, smem, st>>>(b->D.get(), b->Lo.get(), b->Up.get(), b->Dinv.get(), b->GL.get(), b->GU.get(), b->N, B, l, cnt,
+                                                                  b->flag.get());
+        if (nkept > 0)
+            bcr_update_kernel<<<(unsigned) nkept, 32, smem, st>>>(b->D.get(), b->Lo.get(), b->Up.get(), b->Dinv.get(), b->GL.get(), b->GU.get(),
+                                                                   b->ML.get() + (size_t) b->view.ml_off[l] * bb, b->MU.get() + (size_t) b->view.ml_off[l] * bb, b->N,
+                                                                   B, l, cnt);
+    }
+    // top row: the eliminate kernel at level `levels` with a single active row (k = 1)
+    bcr_eliminate_kernel<<<1, 32, smem, st>>>(b->D.get(), b->Lo.get(), b->Up.get(), b->Dinv.get(), b->GL.get(), b->GU.get(), b->N, B, b->levels, 1, b->flag.get());
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+// set_shift (SparseSymShiftSolve.h:85-95)
+void band_set_shift(sb200_op* op, double sigma)
+{
+    BandSolve* b = op->band;
+    SB200_REQUIRE(b != nullptr, SB200_INVALID_ARGUMENT, "operator is not a shift-solve operator");
+    const DeviceCsr& A = op->A;
+    cudaStream_t st = op->stream;
+    const int B = b->B;
+    b->factored = false;
+    b->sigma = sigma;
+    SB200_CUDA_CHECK(cudaMemsetAsync(b->flag.get(), 0, sizeof(int), st));
+    if (b->dense)
+        factor_dense(op, b, sigma);
+    else
+        factor_band(op, b, sigma);
+    int h = 0;
+    SB200_CUDA_CHECK(cudaMemcpyAsync(&h, b->flag.get(), sizeof(int), cudaMemcpyDeviceToHost, st));
+    SB200_CUDA_CHECK(cudaStreamSynchronize(st));
+    SB200_REQUIRE(h != 2, SB200_LOGIC, "band scatter met an entry outside the block tridiagonal");
+    SB200_REQUIRE(h == 0, SB200_INVALID_ARGUMENT, "SparseSymShiftSolve: factorization failed with the given shift");
+    b->factored = true;
+    // verification solve: relative residual of one deterministic right-hand side
+    {
+        std::vector<double> hx((size_t) A.n), hy((size_t) A.n), ht((size_t) A.n);
+        uint64_t sstate = 0x9E3779B97F4A7C15ULL;
+        for (int64_t i = 0; i < A.n; i++)
+        {
+            sstate = sstate * 6364136223846793005ULL + 1442695040888963407ULL;
+            hx[(size_t) i] = (double) (sstate >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+        }
+        const size_t npad_v = std::max<size_t>((size_t) b->N * B, (size_t) A.n);
+        DevBuf<double> dx((size_t) A.n), dy(npad_v), dt(npad_v);
+        dy.zero(st);
+        SB200_CUDA_CHECK(cudaMemcpyAsync(dx.get(), hx.data(), sizeof(double) * A.n, cudaMemcpyHostToDevice, st));
+        band_solve_device(op, dx.get(), dy.get());
+        launch_spmv(op->A, op->plan, dy.get(), dt.get(), st);
+        SB200_CUDA_CHECK(cudaMemcpyAsync(hy.data(), dy.get(), sizeof(double) * A.n, cudaMemcpyDeviceToHost, st));
+        SB200_CUDA_CHECK(cudaMemcpyAsync(ht.data(), dt.get(), sizeof(double) * A.n, cudaMemcpyDeviceToHost, st));
+        SB200_CUDA_CHECK(cudaStreamSynchronize(st));
+        double rn = 0.0, xn = 0.0;
+        for (int64_t i = 0; i < A.n; i++)
+        {
+            const double r = hx[(size_t) i] - (ht[(size_t) i] - sigma * hy[(size_t) i]);
+            rn += r * r;
+            xn += hx[(size_t) i] * hx[(size_t) i];
+        }
+        const double rel = std::sqrt(rn / xn);
+        if (!(rel <= 1e-8))
+        {
+            b->factored = false;
+            throw Error(SB200_INVALID_ARGUMENT, "SparseSymShiftSolve: factorization failed with the given shift (verification residual " + std::to_string(rel) + ")");
+        }
+        b->solves = 0;
+        b->launches = 0;
+    }
+}
+
+void band_info(const sb200_op* op, int* half_bandwidth, int* block, int64_t* block_rows, int* levels)
+{
+    const BandSolve* b = op->band;
+    SB200_REQUIRE(b != nullptr, SB200_INVALID_ARGUMENT, "operator is not a shift-solve operator");
+    if (half_bandwidth)
+        *half_bandwidth = b->bw;
+    if (block)
+        *block = b->B;
+    if (block_rows)
+        *block_rows = b->N;
+    if (levels)
+        *levels = b->levels;
+}
+
+void band_set_refine(sb200_op* op, int steps)
+{
+    SB200_REQUIRE(op->band != nullptr, SB200_INVALID_ARGUMENT, "operator is not a shift-solve operator");
+    op->band->refine = steps > 0 ? 1 : 0;
+}
+
+}  // namespace sb200

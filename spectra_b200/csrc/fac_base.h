@@ -187,9 +187,9 @@ struct FacBase
     }
     void spmv_step(int i, bool restarted, bool symmetric)
     {
-        if (op->cb)
+        if (op->indirect())
         {
-            // user-defined host operator: v_i = f/beta on the device, w = op(v_i) on the host, epilogue on the device
+            // user-defined host operator / device shift-solve: v_i = f/beta on the device, w = op(v_i), epilogue on the device
             ScopedKernelTimer t(&prof, stream(), KC_SPMV, 2);
             double* vi = V.get() + (int64_t) i * ld;
             launch_step_scale(f.get(), ctl.get(), vi, nloc, stream());

@@ -22,6 +22,15 @@ void nccl_allreduce_sum(sb200_comm* c, double* buf, size_t count, cudaStream_t s
 void nccl_allreduce_max(sb200_comm* c, double* buf, size_t count, cudaStream_t s);
 void nccl_allgather(sb200_comm* c, const double* send, double* recv, size_t count_per_rank, cudaStream_t s);
 
+// ---- banded shift-solve operator (band_solve.cu; SparseSymShiftSolve.h:85-109) ----
+struct BandSolve;
+BandSolve* band_create(sb200_op* op);
+void band_destroy(BandSolve* b);
+void band_set_shift(sb200_op* op, double sigma);
+void band_solve_device(sb200_op* op, const double* x_dev, double* y_dev);
+void band_info(const sb200_op* op, int* half_bandwidth, int* block, int64_t* block_rows, int* levels);
+void band_set_refine(sb200_op* op, int steps);
+
 }  // namespace sb200
 
 // Device-resident operator: full CSR rows [row0, row0+nrows) of an n x n matrix.
@@ -41,6 +50,10 @@ struct sb200_op
     void (*cb)(const double*, double*, void*) = nullptr;
     void* cb_user = nullptr;
     sb200::PinnedBuf<double> hx, hy;  // pinned staging of the callback path
+    // shift-solve operator: perform_op is y = (A - sigma I)^{-1} x instead of y = A x (A stays available for refinement)
+    sb200::BandSolve* band = nullptr;
+    // true when perform_op is not the fused CSR SpMV (user callback or shift-solve): the solvers take the unfused step path
+    bool indirect() const { return cb != nullptr || band != nullptr; }
 
     int nranks() const { return comm ? comm->nranks : 1; }
     int rank() const { return comm ? comm->rank : 0; }

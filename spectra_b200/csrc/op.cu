@@ -58,6 +58,8 @@ using namespace sb200;
 
 sb200_op::~sb200_op()
 {
+    if (band)
+        band_destroy(band);
     if (ev0)
         cudaEventDestroy(ev0);
     if (ev1)
@@ -101,6 +103,14 @@ sb200_op* op_create_sparse(int64_t n, const void* outer, int outer_is_64, const 
     build_device_csr(n, outer, outer_is_64 != 0, inner, values, storage_order, matrix_mode, row0, nrows, op->stream, op->A);
     op->symmetric_hint = (matrix_mode != SB200_GENERAL);
     finish_op(op.get());
+    return op.release();
+}
+
+// SparseSymShiftSolve(mat) (SparseSymShiftSolve.h:57-68): the matrix is uploaded like SparseSymMatProd's; set_shift() factorises
+sb200_op* op_create_shift_solve(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values, int storage_order, int matrix_mode)
+{
+    std::unique_ptr<sb200_op> op(op_create_sparse(n, outer, outer_is_64, inner, values, storage_order, matrix_mode, nullptr));
+    op->band = band_create(op.get());
     return op.release();
 }
 
@@ -156,6 +166,8 @@ void op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev)
 {
     if (op->cb)
         op_callback_device(op, x_dev, y_dev);
+    else if (op->band)
+        band_solve_device(op, x_dev, y_dev);
     else
         launch_spmv(op->A, op->plan, x_dev, y_dev, op->stream);
 }

@@ -5,6 +5,8 @@
 #include <Spectra/GenEigsSolver.h>
 #include <Spectra/MatOp/SparseGenMatProd.h>
 #include <Spectra/MatOp/SparseSymMatProd.h>
+#include <Spectra/MatOp/SparseSymShiftSolve.h>
+#include <Spectra/SymEigsShiftSolver.h>
 #include <Spectra/SymEigsSolver.h>
 
 #include <cmath>
@@ -139,8 +141,109 @@ public:
     }
 };
 
+// The user-defined shift-solve operator of the reference's documentation (SymEigsShiftSolver.h:104-146)
+class MyDiagonalTenShiftSolve
+{
+    double sigma_ = 0.0;
+
+public:
+    using Scalar = double;
+    Index rows() const { return 10; }
+    Index cols() const { return 10; }
+    void set_shift(double sigma) { sigma_ = sigma; }
+    void perform_op(const double* x_in, double* y_out) const
+    {
+        for (Index i = 0; i < rows(); i++)
+            y_out[i] = x_in[i] / (i + 1 - sigma_);
+    }
+};
+
+// symmetric band matrix (half-bandwidth b) in compressed ColMajor, lower triangle only; a(i,j) = cos-hash, strong diagonal i
+static Csc band_lower(int n, int b)
+{
+    Csc A;
+    A.n = n;
+    A.outer.push_back(0);
+    for (int j = 0; j < n; j++)
+    {
+        for (int i = j; i < n && i <= j + b; i++)
+        {
+            A.inner.push_back(i);
+            A.val.push_back(i == j ? 0.01 * (j + 1) : 0.3 * std::cos(1.7 * i + 0.3 * j) / (1 + i - j));
+        }
+        A.outer.push_back((int) A.inner.size());
+    }
+    return A;
+}
+
+static void run_shift(int n, int b, int k, int m, double sigma)
+{
+    Csc A = band_lower(n, b);
+    SparseSymShiftSolve<double> op(A.n, A.outer.data(), A.inner.data(), A.val.data());
+    SymEigsShiftSolver<SparseSymShiftSolve<double>> eigs(op, k, m, sigma);
+    eigs.init();
+    const Index nconv = eigs.compute(SortRule::LargestMagn);
+    REQUIRE(eigs.info() == CompInfo::Successful);
+    REQUIRE(nconv == k);
+    auto ev = eigs.eigenvalues();
+    auto U = eigs.eigenvectors();
+    // test/SymEigsShift.cpp:72-76: ||A U - U D||_inf <= 1e-9
+    double err = 0.0;
+    std::vector<double> y(n);
+    for (Index c = 0; c < U.cols(); c++)
+    {
+        sym_lower_mv(A, &U(0, c), y.data());
+        for (int i = 0; i < n; i++)
+            err = std::max(err, std::fabs(y[i] - ev[c] * U(i, c)));
+    }
+    REQUIRE(err <= 1e-9);
+    // the solve itself: (A - sigma I) y = x
+    std::vector<double> x(n), z(n), t(n);
+    for (int i = 0; i < n; i++)
+        x[i] = std::sin(0.1 * i) + 0.5;
+    op.perform_op(x.data(), z.data());
+    sym_lower_mv(A, z.data(), t.data());
+    double rs = 0.0, xs = 0.0;
+    for (int i = 0; i < n; i++)
+    {
+        const double r = t[i] - sigma * z[i] - x[i];
+        rs += r * r;
+        xs += x[i] * x[i];
+    }
+    REQUIRE(std::sqrt(rs / xs) <= 1e-11);
+    std::printf("shift-invert n=%d b=%d sigma=%g: nconv=%d nops=%d ev0=%.12f residual=%.2e solve=%.2e\n", n, b, sigma, (int) nconv, (int) eigs.num_operations(),
+                ev[0], err, std::sqrt(rs / xs));
+}
+
 int main()
 {
+    {
+        MyDiagonalTenShiftSolve op;
+        SymEigsShiftSolver<MyDiagonalTenShiftSolve> eigs(op, 3, 6, 3.14);
+        eigs.init();
+        eigs.compute(SortRule::LargestMagn);
+        REQUIRE(eigs.info() == CompInfo::Successful);
+        auto ev = eigs.eigenvalues();
+        REQUIRE(ev.size() == 3);
+        REQUIRE(std::fabs(ev[0] - 4.0) < 1e-10 && std::fabs(ev[1] - 3.0) < 1e-10 && std::fabs(ev[2] - 2.0) < 1e-10);
+        std::printf("user shift-solve op diag(1..10), sigma 3.14: %.12f %.12f %.12f\n", ev[0], ev[1], ev[2]);
+    }
+    run_shift(500, 3, 5, 20, 1.0);
+    run_shift(20000, 15, 10, 30, 100.005);
+    {
+        // a pattern that is not banded is rejected with the reference's exception type
+        Csc A = gen_sparse_data(200, 0.2);
+        bool thrown = false;
+        try
+        {
+            SparseSymShiftSolve<double> bad(A.n, A.outer.data(), A.inner.data(), A.val.data());
+        }
+        catch (const std::invalid_argument&)
+        {
+            thrown = true;
+        }
+        REQUIRE(thrown);
+    }
     {
         MyDiagonalTen op;
         SymEigsSolver<MyDiagonalTen> eigs(op, 3, 6);

@@ -164,3 +164,33 @@ def test_gen_eigs_medium_vs_oracle(gpu):
         assert ref.info == O.Successful
         assert np.abs(np.sort_complex(evals) - np.sort_complex(ref.eigenvalues)).max() <= 1e-9 * np.abs(ref.eigenvalues).max()
         assert abs(eigs.num_operations() - ref.nops) <= max(60, ref.nops // 5)
+
+
+def test_gen_eigs_full_size_properties(gpu):
+    # BASELINE config C3: nonsymmetric CSR n = 1e6, nnz/row = 20, k = 10, ncv = 30, LargestMagn (planted separated eigenvalues, see above).
+    # Size-independent properties: relative residuals, conjugate-closed spectrum, sortedness, run-to-run reproducibility.
+    from spectra_b200 import synth
+
+    n = 1_000_000
+    rp, ci, v = synth.csr(n, 20, 1, False)
+    d = np.zeros(n)
+    d[:20] = 3.0 + 0.35 * np.arange(20)
+    A = (sp.csr_matrix((v, ci, rp), shape=(n, n)) + sp.diags(d)).tocsr()
+    A.sort_indices()
+    op = gpu.SparseGenMatProd(A)
+    runs = []
+    for _ in range(2):
+        eigs = gpu.GenEigsSolver(op, 10, 30)
+        eigs.init()
+        nconv = eigs.compute(gpu.SortRule.LargestMagn)
+        assert eigs.info() == gpu.CompInfo.Successful and nconv == 10
+        runs.append((eigs.eigenvalues(), eigs.num_operations(), eigs.num_iterations()))
+    evals, X = eigs.eigenvalues(), eigs.eigenvectors()
+    assert X.shape == (n, 10)
+    res = np.linalg.norm(A @ X - X * evals, axis=0) / np.abs(evals)
+    assert res.max() <= 1e-10
+    assert np.all(np.diff(np.abs(evals)) <= 1e-12 * np.abs(evals).max())  # LargestMagn ordering (GenEigsBase.h:501-502 default sorting)
+    assert np.abs(np.linalg.norm(X, axis=0) - 1).max() <= 1e-12
+    # the planted eigenvalues are real up to the perturbation: the top 10 lie near 3 + 0.35 j, j = 19..10
+    assert np.abs(np.sort(evals.real)[::-1] - (3.0 + 0.35 * np.arange(19, 9, -1))).max() < 0.5
+    assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1:] == runs[1][1:]

@@ -1,0 +1,171 @@
+"""GPU parity tests of the shift-and-invert path (BASELINE config 5):
+SparseSymShiftSolve (MatOp/SparseSymShiftSolve.h:30-110) + SymEigsShiftSolver (SymEigsShiftSolver.h:148-196),
+against the oracle's band LU (oracle/band.hpp), SciPy SuperLU / ARPACK shift-invert, and the reference's own
+fixtures and thresholds (test/SymEigsShift.cpp)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from scipy.sparse.linalg import eigsh, splu
+
+import oracle as O
+from helpers import sym_full
+
+pytestmark = pytest.mark.gpu
+
+
+def _band(n, b, seed=0, diag_add=0.0):
+    from spectra_b200 import synth
+
+    rp, ci, v = synth.band_csr(n, b, seed, diag_add)
+    return sp.csr_matrix((v, ci, rp), shape=(n, n))
+
+
+@pytest.mark.parametrize("n,b", [(5, 2), (50, 15), (64, 1), (777, 7), (1000, 32), (20_000, 15), (200_000, 15)])
+def test_shift_solve_operator_banded(gpu, n, b):
+    # perform_op = (A - sigma I)^{-1} x (SparseSymShiftSolve.h:104-109); factors are not observable, the solve result is
+    A = _band(n, b, seed=n)
+    sigma = 0.5
+    op = gpu.SparseSymShiftSolve(sp.tril(A).tocsc())
+    lay = op.layout()
+    assert lay["half_bandwidth"] == min(b, n - 1) and lay["block"] >= lay["half_bandwidth"]
+    op.set_shift(sigma)
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n)
+    y = op.perform_op(x)
+    M = (A - sigma * sp.identity(n)).tocsc()
+    y_ref = splu(M).solve(x)
+    assert np.linalg.norm(M @ y - x) <= 1e-12 * np.linalg.norm(x) * max(1.0, np.abs(y).max())
+    assert np.abs(y - y_ref).max() <= 1e-9 * np.abs(y_ref).max()
+    # the oracle's band LU (LAPACK dgbtrf/dgbtrs restatement) agrees as well
+    rp, ci, v = A.indptr.astype(np.int64), A.indices, A.data
+    y_or = O.BandLu(O.Csr.adopt(n, rp, ci, v), sigma).perform_op(x)
+    assert np.abs(y - y_or).max() <= 1e-9 * np.abs(y_or).max()
+    # without the refinement step block cyclic reduction alone is still a usable solve
+    op.set_refine(0)
+    y0 = op.perform_op(x)
+    assert np.linalg.norm(M @ y0 - x) <= 1e-7 * np.linalg.norm(x) * max(1.0, np.abs(y0).max())
+    # a second shift re-factorises the same operator
+    op.set_refine(1)
+    op.set_shift(-1.25)
+    y2 = op.perform_op(x)
+    M2 = (A + 1.25 * sp.identity(n)).tocsc()
+    assert np.linalg.norm(M2 @ y2 - x) <= 1e-12 * np.linalg.norm(x) * max(1.0, np.abs(y2).max())
+
+
+def test_shift_solve_errors(gpu):
+    n = 300
+    A = _band(n, 5)
+    op = gpu.SparseSymShiftSolve(sp.tril(A).tocsc())
+    with pytest.raises(gpu.LogicError):
+        op.perform_op(np.ones(n))  # set_shift has not been called
+    # singular shift: diag(1..n), sigma = 7 exactly (reference: "factorization failed with the given shift", :93-94)
+    D = sp.diags(np.arange(1.0, n + 1)).tocsc()
+    opd = gpu.SparseSymShiftSolve(D)
+    with pytest.raises(gpu.InvalidArgument):
+        opd.set_shift(7.0)
+    opd.set_shift(7.5)
+    y = opd.perform_op(np.ones(n))
+    assert np.abs(y - 1.0 / (np.arange(1.0, n + 1) - 7.5)).max() <= 1e-13 * np.abs(y).max()
+    # large and not banded: rejected at construction
+    rng = np.random.default_rng(0)
+    R = sp.random(5000, 5000, density=0.002, random_state=rng, format="csc")
+    with pytest.raises(gpu.InvalidArgument):
+        gpu.SparseSymShiftSolve(sp.tril(R + R.T).tocsc())
+    # a non-shift operator cannot take set_shift
+    plain = gpu.SparseSymMatProd(sp.tril(A).tocsc())
+    with pytest.raises(gpu.InvalidArgument):
+        gpu._check(gpu.lib().sb200_op_set_shift(plain.h, gpu.C.c_double(1.0)))
+
+
+RULES = ["LargestMagn", "LargestAlge", "SmallestMagn", "SmallestAlge", "BothEnds"]
+
+
+@pytest.mark.parametrize("rule", RULES)
+@pytest.mark.parametrize("n,prob,k,m,sigma", [(10, 0.5, 3, 6, 1.0), (100, 0.1, 10, 20, 10.0), (1000, 0.01, 20, 50, 100.0)])
+def test_sym_shift_eigs_reference_cases(gpu, n, prob, k, m, sigma, rule):
+    # test/SymEigsShift.cpp:148-186: gen_sparse_data(n, prob), lower triangle, maxit = 500, ||AU - UD||_inf <= 1e-9.
+    # These small matrices are not banded: the operator takes its dense (explicit inverse) route.
+    A = O.gen_sparse_data(n, prob)
+    Afull = sym_full(A)
+    op = gpu.SparseSymShiftSolve(A)
+    eigs = gpu.SymEigsShiftSolver(op, k, m, sigma)
+    eigs.init()
+    nconv = eigs.compute(getattr(gpu.SortRule, rule), 500)
+    if rule == "SmallestMagn" and eigs.info() != gpu.CompInfo.Successful:
+        pytest.skip("allowed failure in the reference test (allow_fail = true)")
+    assert eigs.info() == gpu.CompInfo.Successful and nconv == k
+    evals, U = eigs.eigenvalues(), eigs.eigenvectors()
+    assert np.abs(Afull @ U - U * evals).max() <= 1e-9
+    # oracle: same driver on the host with SuperLU as the shift-solve operator
+    lu = splu((Afull - sigma * sp.identity(n)).tocsc())
+    ref = O.sym_eigs_userop(n, lu.solve, k, m, getattr(O, rule), 500, sigma=sigma)
+    if ref.info == O.Successful:
+        assert np.abs(np.sort(evals) - np.sort(ref.eigenvalues)).max() <= 1e-9 * max(1.0, np.abs(ref.eigenvalues).max())
+
+
+def test_shift_solver_doc_example_user_op(gpu):
+    # SymEigsShiftSolver.h:104-146: M = diag(1..10), sigma = 3.14 -> (4, 3, 2)
+    class MyDiagonalTenShiftSolve:
+        def rows(self):
+            return 10
+
+        def set_shift(self, sigma):
+            self.sigma = sigma
+
+        def perform_op(self, x, y):
+            y[:] = x / (np.arange(1.0, 11.0) - self.sigma)
+
+    user = MyDiagonalTenShiftSolve()
+    op = gpu.UserOp(user)
+    eigs = gpu.SymEigsShiftSolver(op, 3, 6, 3.14)
+    eigs.init()
+    eigs.compute(gpu.SortRule.LargestMagn)
+    assert eigs.info() == gpu.CompInfo.Successful
+    assert np.abs(eigs.eigenvalues() - np.array([4.0, 3.0, 2.0])).max() <= 1e-10
+
+
+def test_sym_shift_eigs_banded_vs_oracle_and_arpack(gpu):
+    # BASELINE config 5 at a size the oracle finishes in a blink: banded, 31 nnz/row, k = 10, sigma = 0.5
+    n, b, sigma = 20_000, 15, 0.5
+    A = _band(n, b)
+    op = gpu.SparseSymShiftSolve(sp.tril(A).tocsc())
+    eigs = gpu.SymEigsShiftSolver(op, 10, 30, sigma)
+    eigs.init()
+    nconv = eigs.compute(gpu.SortRule.LargestMagn)
+    assert eigs.info() == gpu.CompInfo.Successful and nconv == 10
+    evals, X = eigs.eigenvalues(), eigs.eigenvectors()
+    res = np.linalg.norm(A @ X - X * evals, axis=0) / np.abs(evals)
+    assert res.max() <= 1e-10
+    csr = O.Csr.adopt(n, A.indptr.astype(np.int64), A.indices, A.data)
+    ref = O.sym_shift_eigs(O.BandLu(csr, sigma), 10, 30, O.LargestMagn)
+    assert ref.info == O.Successful
+    assert np.abs(np.sort(evals) - np.sort(ref.eigenvalues)).max() <= 1e-10 * np.abs(ref.eigenvalues).max()
+    assert abs(eigs.num_operations() - ref.nops) <= max(30, ref.nops // 5)
+    w = eigsh(A.tocsc(), k=10, sigma=sigma, which="LM", ncv=30, tol=1e-12, return_eigenvectors=False)
+    assert np.abs(np.sort(evals) - np.sort(w)).max() <= 1e-10 * np.abs(w).max()
+    # default sorting is LargestAlge on the back-transformed values (HermEigsBase.h:366-367 with SymEigsShiftSolver.h:163-169)
+    assert np.all(np.diff(evals) <= 0)
+
+
+def test_sym_shift_eigs_full_size_properties(gpu):
+    # BASELINE config 5: n = 2e5, 31 nnz/row (half-bandwidth 15), k = 10, sigma = 0.5.  Size-independent properties.
+    n, b, sigma = 200_000, 15, 0.5
+    A = _band(n, b)
+    op = gpu.SparseSymShiftSolve(sp.tril(A).tocsc())
+    runs = []
+    for _ in range(2):
+        eigs = gpu.SymEigsShiftSolver(op, 10, 30, sigma)
+        eigs.init()
+        nconv = eigs.compute(gpu.SortRule.LargestMagn)
+        assert eigs.info() == gpu.CompInfo.Successful and nconv == 10
+        runs.append((eigs.eigenvalues(), eigs.num_operations()))
+    evals, X = eigs.eigenvalues(), eigs.eigenvectors()
+    res = np.linalg.norm(A @ X - X * evals, axis=0) / np.abs(evals)
+    assert res.max() <= 1e-10
+    assert np.abs(X.T @ X - np.eye(10)).max() <= 1e-10
+    # they are the 10 eigenvalues closest to sigma: Sylvester inertia count through SuperLU is too slow here; use the
+    # oracle's independent band LU + the same driver instead
+    csr = O.Csr.adopt(n, A.indptr.astype(np.int64), A.indices, A.data)
+    ref = O.sym_shift_eigs(O.BandLu(csr, sigma), 10, 30, O.LargestMagn, want_vectors=False)
+    assert np.abs(np.sort(evals) - np.sort(ref.eigenvalues)).max() <= 1e-10 * np.abs(ref.eigenvalues).max()
+    assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1] == runs[1][1]

@@ -207,3 +207,48 @@ def test_argument_checks():
     with pytest.raises(O.OracleError) as e:
         O.sym_eigs(A, 3, 6, init_resid=np.zeros(10))
     assert e.value.code == 1  # Arnoldi.h:147-148
+
+
+# ---------------------------------------------------------------- shift-invert
+@pytest.mark.parametrize("n,b", [(5, 2), (200, 1), (777, 7), (5000, 15)])
+def test_band_lu_shift_solve_vs_superlu(n, b):
+    # SparseSymShiftSolve::perform_op (SparseSymShiftSolve.h:104-109): only the solve result is observable
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import splu
+    from spectra_b200 import synth
+
+    rp, ci, v = synth.band_csr(n, b, n, 0.0)
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    op = O.BandLu(O.Csr.adopt(n, rp, ci, v), 0.5)
+    assert op.kl == min(b, n - 1) and op.ku == min(b, n - 1)
+    x = np.random.default_rng(n).standard_normal(n)
+    y = op.perform_op(x)
+    M = (A - 0.5 * sp.identity(n)).tocsc()
+    assert np.linalg.norm(M @ y - x) <= 1e-12 * np.linalg.norm(x) * max(1.0, np.abs(y).max())
+    assert np.abs(y - splu(M).solve(x)).max() <= 1e-9 * np.abs(y).max()
+
+
+def test_band_lu_singular_shift_throws():
+    import scipy.sparse as sp
+
+    D = sp.diags(np.arange(1.0, 11.0)).tocsr()
+    csr = O.Csr.from_scipy(D)
+    with pytest.raises(O.OracleError) as e:
+        O.BandLu(csr, 3.0)
+    assert e.value.code == 1  # std::invalid_argument (SparseSymShiftSolve.h:93-94)
+
+
+def test_sym_shift_eigs_banded_vs_arpack():
+    # SymEigsShiftSolver (SymEigsShiftSolver.h:148-196) on the matrix class of BASELINE config 5
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import eigsh
+    from spectra_b200 import synth
+
+    n = 20000
+    rp, ci, v = synth.band_csr(n, 15, 0, 0.0)
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    r = O.sym_shift_eigs(O.BandLu(O.Csr.adopt(n, rp, ci, v), 0.5), 10, 30, O.LargestMagn)
+    assert r.info == O.Successful and r.nconv == 10
+    w = eigsh(A.tocsc(), k=10, sigma=0.5, which="LM", ncv=30, tol=1e-12, return_eigenvectors=False)
+    assert np.abs(np.sort(r.eigenvalues) - np.sort(w)).max() <= 1e-10
+    assert np.abs(A @ r.eigenvectors - r.eigenvectors * r.eigenvalues).max() <= 1e-9
