@@ -12,14 +12,13 @@ template <typename Scalar_, int Flags = SPECTRA_B200_COLMAJOR, typename StorageI
 class SparseGenMatProd : public b200::SparseOpBase
 {
     static_assert(std::is_same<Scalar_, double>::value, "the B200 path implements Scalar = double");
-    static_assert(sizeof(StorageIndex) == 4, "inner indices must be 32-bit (Eigen's default StorageIndex = int)");
 
 public:
     using Scalar = Scalar_;
 
     SparseGenMatProd(Index n, const StorageIndex* outer, const StorageIndex* inner, const Scalar* values)
     {
-        create(n, outer, false, reinterpret_cast<const int32_t*>(inner), values, Flags == SPECTRA_B200_ROWMAJOR, SB200_GENERAL);
+        create_any(n, outer, inner, values, Flags == SPECTRA_B200_ROWMAJOR, SB200_GENERAL);
     }
 #ifdef SPECTRA_B200_HAS_EIGEN
     explicit SparseGenMatProd(const Eigen::SparseMatrix<Scalar, Flags, StorageIndex>& mat)
@@ -28,7 +27,7 @@ public:
             throw std::invalid_argument("SparseGenMatProd: matrix must be in compressed mode (call makeCompressed())");
         if (mat.rows() != mat.cols())
             throw std::invalid_argument("SparseGenMatProd: matrix must be square");
-        create(mat.rows(), mat.outerIndexPtr(), false, reinterpret_cast<const int32_t*>(mat.innerIndexPtr()), mat.valuePtr(), Flags == Eigen::RowMajor,
+        create_any(mat.rows(), mat.outerIndexPtr(), mat.innerIndexPtr(), mat.valuePtr(), Flags == Eigen::RowMajor,
                SB200_GENERAL);
     }
 #endif

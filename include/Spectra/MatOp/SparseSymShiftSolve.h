@@ -12,7 +12,6 @@ template <typename Scalar_, int Uplo = SPECTRA_B200_LOWER, int Flags = SPECTRA_B
 class SparseSymShiftSolve : public b200::SparseOpBase
 {
     static_assert(std::is_same<Scalar_, double>::value, "the B200 path implements Scalar = double");
-    static_assert(sizeof(StorageIndex) == 4, "inner indices must be 32-bit (Eigen's default StorageIndex = int)");
 
 public:
     using Scalar = Scalar_;
@@ -20,7 +19,7 @@ public:
     // Raw compressed arrays with Eigen's layout: outer[n + 1], inner[nnz], values[nnz].
     SparseSymShiftSolve(Index n, const StorageIndex* outer, const StorageIndex* inner, const Scalar* values)
     {
-        create(n, outer, false, reinterpret_cast<const int32_t*>(inner), values, Flags == SPECTRA_B200_ROWMAJOR,
+        create_any(n, outer, inner, values, Flags == SPECTRA_B200_ROWMAJOR,
                Uplo == SPECTRA_B200_LOWER ? SB200_SYM_LOWER : SB200_SYM_UPPER, true);
     }
 #ifdef SPECTRA_B200_HAS_EIGEN
@@ -31,7 +30,7 @@ public:
             throw std::invalid_argument("SparseSymShiftSolve: matrix must be square");
         if (!mat.isCompressed())
             throw std::invalid_argument("SparseSymShiftSolve: matrix must be in compressed mode (call makeCompressed())");
-        create(mat.rows(), mat.outerIndexPtr(), false, reinterpret_cast<const int32_t*>(mat.innerIndexPtr()), mat.valuePtr(), Flags == Eigen::RowMajor,
+        create_any(mat.rows(), mat.outerIndexPtr(), mat.innerIndexPtr(), mat.valuePtr(), Flags == Eigen::RowMajor,
                Uplo == Eigen::Lower ? SB200_SYM_LOWER : SB200_SYM_UPPER, true);
     }
 #endif

@@ -141,6 +141,26 @@ protected:
         else
             check(sb200_op_create_sparse(n, outer, outer64 ? 1 : 0, inner, values, row_major ? SB200_ROW_MAJOR : SB200_COL_MAJOR, mode, nullptr, &m_op));
     }
+    // StorageIndex = int (Eigen's default) is passed through; 64-bit StorageIndex keeps its 64-bit outer offsets and has its
+    // inner indices narrowed once (the device CSR addresses n < 2^31 columns with 32-bit ids)
+    std::vector<int32_t> m_inner32;
+    template <typename StorageIndex>
+    void create_any(Index n, const StorageIndex* outer, const StorageIndex* inner, const double* values, bool row_major, int mode, bool shift_solve = false)
+    {
+        static_assert(std::is_integral<StorageIndex>::value && (sizeof(StorageIndex) == 4 || sizeof(StorageIndex) == 8), "StorageIndex must be a 32- or 64-bit integer");
+        if (sizeof(StorageIndex) == 4)
+        {
+            create(n, outer, false, reinterpret_cast<const int32_t*>(inner), values, row_major, mode, shift_solve);
+            return;
+        }
+        if (n >= (Index(1) << 31))
+            throw std::invalid_argument("matrix order must be below 2^31");
+        const int64_t nnz = static_cast<int64_t>(outer[n]);
+        m_inner32.resize(static_cast<size_t>(nnz));
+        for (int64_t p = 0; p < nnz; p++)
+            m_inner32[static_cast<size_t>(p)] = static_cast<int32_t>(inner[p]);
+        create(n, outer, true, m_inner32.data(), values, row_major, mode, shift_solve);
+    }
     int64_t outer_at(Index i) const
     {
         return m_outer64 ? static_cast<const int64_t*>(m_outer)[i] : static_cast<int64_t>(static_cast<const int32_t*>(m_outer)[i]);
@@ -164,6 +184,10 @@ public:
             m_inner = o.m_inner;
             m_values = o.m_values;
             m_row_major = o.m_row_major;
+            const bool own_inner = !o.m_inner32.empty();
+            m_inner32 = std::move(o.m_inner32);
+            if (own_inner)
+                m_inner = m_inner32.data();
             o.m_op = nullptr;
         }
         return *this;

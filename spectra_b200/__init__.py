@@ -118,6 +118,16 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+def _check_op(op, rc: int):
+    """_check for calls that may run a Python operator callback: an exception raised inside the callback cannot cross
+    the C frames, so it is parked on the operator and re-raised here once the C call has returned."""
+    exc = getattr(op, "_exc", None)
+    if exc is not None:
+        op._exc = None
+        raise exc
+    _check(rc)
+
+
 def device_info() -> dict:
     dev, sms, maj, mnr, mem = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int64()
     _check(lib().sb200_device_info(C.byref(dev), C.byref(sms), C.byref(maj), C.byref(mnr), C.byref(mem)))
@@ -338,7 +348,7 @@ class UserOp:
     def perform_op(self, x_in, y_out=None):
         x = np.ascontiguousarray(x_in, dtype=np.float64)
         y = y_out if y_out is not None else np.empty(self.n)
-        _check(lib().sb200_op_perform_op(self.h, _p(x), _p(y)))
+        _check_op(self, lib().sb200_op_perform_op(self.h, _p(x), _p(y)))
         return y
 
     def close(self):
@@ -410,11 +420,11 @@ class SymEigsSolver:
         r = np.ascontiguousarray(init_resid, dtype=np.float64) if init_resid is not None else None
         if r is not None and r.shape != (self.op.n,):
             raise InvalidArgument(1, "init_resid has the wrong length")
-        _check(lib().sb200_sym_init(self.h, _p(r)))
+        _check_op(self.op, lib().sb200_sym_init(self.h, _p(r)))
 
     def compute(self, selection=SortRule.LargestMagn, maxit: int = 1000, tol: float = 1e-10, sorting=SortRule.LargestAlge) -> int:
         nconv = C.c_int64()
-        _check(lib().sb200_sym_compute(self.h, int(selection), C.c_int64(maxit), C.c_double(tol), int(sorting), C.byref(nconv)))
+        _check_op(self.op, lib().sb200_sym_compute(self.h, int(selection), C.c_int64(maxit), C.c_double(tol), int(sorting), C.byref(nconv)))
         return nconv.value
 
     def info(self) -> CompInfo:
@@ -507,11 +517,11 @@ class GenEigsSolver:
         r = np.ascontiguousarray(init_resid, dtype=np.float64) if init_resid is not None else None
         if r is not None and r.shape != (self.op.n,):
             raise InvalidArgument(1, "init_resid has the wrong length")
-        _check(lib().sb200_gen_init(self.h, _p(r)))
+        _check_op(self.op, lib().sb200_gen_init(self.h, _p(r)))
 
     def compute(self, selection=SortRule.LargestMagn, maxit: int = 1000, tol: float = 1e-10, sorting=SortRule.LargestMagn) -> int:
         nconv = C.c_int64()
-        _check(lib().sb200_gen_compute(self.h, int(selection), C.c_int64(maxit), C.c_double(tol), int(sorting), C.byref(nconv)))
+        _check_op(self.op, lib().sb200_gen_compute(self.h, int(selection), C.c_int64(maxit), C.c_double(tol), int(sorting), C.byref(nconv)))
         return nconv.value
 
     def info(self) -> CompInfo:

@@ -29,7 +29,7 @@ namespace sb200 {
 namespace {
 
 constexpr int kTopRows = 64;  // levels with at most this many active rows are fused into one CTA
-constexpr int kTopThreads = 1024;
+constexpr int kTopThreads = 512;
 
 __global__ void band_width_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int64_t nrows, int64_t row0, int* out_bw)
 {
@@ -254,16 +254,19 @@ __global__ void __launch_bounds__(32) bcr_update_kernel(double* D, double* Lo, d
     }
 }
 
-// y_r = sum_c M[r + c B] * v[c], v held one entry per lane
+// y_r = sum_c M[r + c B] * v[c], v held one entry per lane.  All (<= BMAX) loads of the lane's row are issued before
+// the first use so that one block row costs one memory latency, not B of them.
+template <int BMAX>
 __device__ __forceinline__ double mat_vec_lane(const double* __restrict__ M, int B, int lane, double v_lane)
 {
+    double m[BMAX];
+#pragma unroll
+    for (int c = 0; c < BMAX; c++)
+        m[c] = (c < B && lane < B) ? __ldg(M + lane + c * B) : 0.0;
     double acc = 0.0;
-    for (int c = 0; c < B; c++)
-    {
-        const double vc = __shfl_sync(0xffffffffu, v_lane, c);
-        if (lane < B)
-            acc = fma(M[lane + c * B], vc, acc);
-    }
+#pragma unroll
+    for (int c = 0; c < BMAX; c++)
+        acc = fma(m[c], __shfl_sync(0xffffffffu, v_lane, c), acc);
     return acc;
 }
 
@@ -280,6 +283,7 @@ struct BcrView
     int64_t ml_off[40];
 };
 
+template <int BMAX>
 __device__ __forceinline__ void forward_row(const BcrView& v, double* f, int level, int64_t idx, int lane)
 {
     const int bb = v.B * v.B;
@@ -289,16 +293,17 @@ __device__ __forceinline__ void forward_row(const BcrView& v, double* f, int lev
     const double* ml = v.ML + (v.ml_off[level] + idx) * bb;
     const double* mu = v.MU + (v.ml_off[level] + idx) * bb;
     const double fp = lane < v.B ? f[p * v.B + lane] : 0.0;
-    double acc = mat_vec_lane(ml, v.B, lane, fp);
+    double acc = mat_vec_lane<BMAX>(ml, v.B, lane, fp);
     if (q < v.N)
     {
         const double fq = lane < v.B ? f[q * v.B + lane] : 0.0;
-        acc += mat_vec_lane(mu, v.B, lane, fq);
+        acc += mat_vec_lane<BMAX>(mu, v.B, lane, fq);
     }
     if (lane < v.B)
         f[i * v.B + lane] -= acc;
 }
 
+template <int BMAX>
 __device__ __forceinline__ void backward_row(const BcrView& v, double* f, int level, int64_t idx, int lane)
 {
     const int bb = v.B * v.B;
@@ -306,38 +311,41 @@ __device__ __forceinline__ void backward_row(const BcrView& v, double* f, int le
     const int64_t k = 2 * idx + 1;
     const int64_t j = k * s - 1, p = j - s, q = j + s;
     const double fj = lane < v.B ? f[j * v.B + lane] : 0.0;
-    double acc = mat_vec_lane(v.Dinv + j * bb, v.B, lane, fj);
+    double acc = mat_vec_lane<BMAX>(v.Dinv + j * bb, v.B, lane, fj);
     if (p >= 0)
     {
         const double xp = lane < v.B ? f[p * v.B + lane] : 0.0;
-        acc -= mat_vec_lane(v.GL + j * bb, v.B, lane, xp);
+        acc -= mat_vec_lane<BMAX>(v.GL + j * bb, v.B, lane, xp);
     }
     if (q < v.N)
     {
         const double xq = lane < v.B ? f[q * v.B + lane] : 0.0;
-        acc -= mat_vec_lane(v.GU + j * bb, v.B, lane, xq);
+        acc -= mat_vec_lane<BMAX>(v.GU + j * bb, v.B, lane, xq);
     }
     if (lane < v.B)
         f[j * v.B + lane] = acc;
 }
 
+template <int BMAX>
 __global__ void __launch_bounds__(128) bcr_forward_kernel(BcrView v, double* f, int level, int64_t nkept)
 {
     const int lane = threadIdx.x & 31;
     const int64_t w = (int64_t) blockIdx.x * 4 + (threadIdx.x >> 5);
     if (w < nkept)
-        forward_row(v, f, level, w, lane);
+        forward_row<BMAX>(v, f, level, w, lane);
 }
 
+template <int BMAX>
 __global__ void __launch_bounds__(128) bcr_backward_kernel(BcrView v, double* f, int level, int64_t nelim)
 {
     const int lane = threadIdx.x & 31;
     const int64_t w = (int64_t) blockIdx.x * 4 + (threadIdx.x >> 5);
     if (w < nelim)
-        backward_row(v, f, level, w, lane);
+        backward_row<BMAX>(v, f, level, w, lane);
 }
 
 // levels [first, L) forward, the top row, then backward L-1 .. first, inside one CTA
+template <int BMAX>
 __global__ void __launch_bounds__(kTopThreads) bcr_top_kernel(BcrView v, double* f, int first)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kTopThreads / 32;
@@ -345,14 +353,14 @@ __global__ void __launch_bounds__(kTopThreads) bcr_top_kernel(BcrView v, double*
     {
         const int64_t cnt = v.N >> l, nkept = cnt / 2;
         for (int64_t w = warp; w < nkept; w += nw)
-            forward_row(v, f, l, w, lane);
+            forward_row<BMAX>(v, f, l, w, lane);
         __syncthreads();
     }
     if (warp == 0)
     {
         const int64_t t = ((int64_t) 1 << v.levels) - 1;
         const double ft = lane < v.B ? f[t * v.B + lane] : 0.0;
-        const double xt = mat_vec_lane(v.Dinv + t * v.B * v.B, v.B, lane, ft);
+        const double xt = mat_vec_lane<BMAX>(v.Dinv + t * v.B * v.B, v.B, lane, ft);
         if (lane < v.B)
             f[t * v.B + lane] = xt;
     }
@@ -361,7 +369,7 @@ __global__ void __launch_bounds__(kTopThreads) bcr_top_kernel(BcrView v, double*
     {
         const int64_t cnt = v.N >> l, nelim = (cnt + 1) / 2;
         for (int64_t w = warp; w < nelim; w += nw)
-            backward_row(v, f, l, w, lane);
+            backward_row<BMAX>(v, f, l, w, lane);
         __syncthreads();
     }
 }
@@ -641,15 +649,24 @@ static void bcr_solve_inplace(BandSolve* b, double* f, cudaStream_t st)
     for (int l = 0; l < b->first_top; l++)
     {
         const int64_t nkept = (b->N >> l) / 2;
-        bcr_forward_kernel<<<(unsigned) ((nkept + 3) / 4), 128, 0, st>>>(b->view, f, l, nkept);
+        if (b->B <= 16)
+            bcr_forward_kernel<16><<<(unsigned) ((nkept + 3) / 4), 128, 0, st>>>(b->view, f, l, nkept);
+        else
+            bcr_forward_kernel<32><<<(unsigned) ((nkept + 3) / 4), 128, 0, st>>>(b->view, f, l, nkept);
         b->launches++;
     }
-    bcr_top_kernel<<<1, kTopThreads, 0, st>>>(b->view, f, b->first_top);
+    if (b->B <= 16)
+        bcr_top_kernel<16><<<1, kTopThreads, 0, st>>>(b->view, f, b->first_top);
+    else
+        bcr_top_kernel<32><<<1, kTopThreads, 0, st>>>(b->view, f, b->first_top);
     b->launches++;
     for (int l = b->first_top - 1; l >= 0; l--)
     {
         const int64_t nelim = ((b->N >> l) + 1) / 2;
-        bcr_backward_kernel<<<(unsigned) ((nelim + 3) / 4), 128, 0, st>>>(b->view, f, l, nelim);
+        if (b->B <= 16)
+            bcr_backward_kernel<16><<<(unsigned) ((nelim + 3) / 4), 128, 0, st>>>(b->view, f, l, nelim);
+        else
+            bcr_backward_kernel<32><<<(unsigned) ((nelim + 3) / 4), 128, 0, st>>>(b->view, f, l, nelim);
         b->launches++;
     }
     SB200_CUDA_CHECK(cudaGetLastError());

@@ -102,6 +102,20 @@ static void run_sym(const Csc& A, int k, int m, SortRule rule)
     // operator tier: op * M and op(i, j)
     double x0 = op(45 % A.n, 22 % A.n);
     (void) x0;
+    // template-argument variants (SparseSymMatProd.h:30): the same compressed arrays read as RowMajor hold the transpose, whose
+    // Upper triangle is this matrix' Lower one; 64-bit StorageIndex.  Same symmetric matrix => same eigenvalues and op counts.
+    std::vector<long long> outer64(A.outer.begin(), A.outer.end()), inner64(A.inner.begin(), A.inner.end());
+    using OpV = SparseSymMatProd<double, SPECTRA_B200_UPPER, SPECTRA_B200_ROWMAJOR, long long>;
+    OpV opv(A.n, outer64.data(), inner64.data(), A.val.data());
+    SymEigsSolver<OpV> eigv(opv, k, m);
+    eigv.init();
+    eigv.compute(rule);
+    REQUIRE(eigv.info() == CompInfo::Successful);
+    REQUIRE(eigv.num_operations() == eigs.num_operations());
+    auto ev2 = eigv.eigenvalues();
+    for (int c = 0; c < nconv; c++)
+        REQUIRE(ev2[c] == evals[c]);
+    REQUIRE(opv(22 % A.n, 45 % A.n) == x0);
 }
 
 static void run_gen(const Csc& A, int k, int m, SortRule rule)
@@ -231,8 +245,8 @@ int main()
     run_shift(500, 3, 5, 20, 1.0);
     run_shift(20000, 15, 10, 30, 100.005);
     {
-        // a pattern that is not banded is rejected with the reference's exception type
-        Csc A = gen_sparse_data(200, 0.2);
+        // a large pattern that is not banded is rejected with the reference's exception type
+        Csc A = gen_sparse_data(3000, 0.002);
         bool thrown = false;
         try
         {

@@ -474,3 +474,16 @@ def test_user_defined_operator(gpu):
     assert g.info() == gpu.CompInfo.Successful
     Z = g.eigenvectors()
     assert np.abs(G @ Z - Z * g.eigenvalues()).max() <= 1e-9
+    # an exception raised inside the Python operator surfaces from the call that ran it
+    calls = {"n": 0}
+
+    def failing(x):
+        calls["n"] += 1
+        if calls["n"] == 4:
+            raise KeyError("operator failed")
+        return x * np.arange(1, 11)
+
+    bad = gpu.SymEigsSolver(gpu.UserOp(failing, n=10), 3, 6)
+    with pytest.raises(KeyError):
+        bad.init()
+        bad.compute(gpu.SortRule.LargestAlge)
