@@ -390,6 +390,33 @@ def test_sym_eigs_full_size_properties(gpu):
     assert np.array_equal(evals, eigs.eigenvalues())
 
 
+def test_sym_eigs_c4_size_properties(gpu):
+    # BASELINE config C4 on one GPU (the bench workload): n = 1e7, nnz/row = 20, k = 20, ncv = 60.  Size-independent properties:
+    # north_star's ||Ax - lambda x|| / |lambda| <= 1e-10, orthonormality, ordering; the operator is checked through linearity and
+    # symmetry (x'Ay = y'Ax) on the device result.
+    from spectra_b200 import synth
+
+    n = 10_000_000
+    rp, ci, v = synth.csr(n, 20, 0, True)
+    op = gpu.SparseGenMatProd.from_csr_slab(n, 0, rp, ci, v)
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    rng = np.random.default_rng(7)
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    Ax, Ay = op.perform_op(x), op.perform_op(y)
+    assert abs(y @ Ax - x @ Ay) <= 1e-10 * np.linalg.norm(x) * np.linalg.norm(Ay)
+    assert np.abs(op.perform_op(2.0 * x - 3.0 * y) - (2.0 * Ax - 3.0 * Ay)).max() <= 1e-12 * np.abs(Ax).max() * 10
+    assert np.abs(Ax[:: n // 1000] - (A @ x)[:: n // 1000]).max() <= 1e-12 * np.abs(Ax).max()
+    eigs = gpu.SymEigsSolver(op, 20, 60)
+    eigs.init()
+    nconv = eigs.compute(gpu.SortRule.LargestAlge)
+    assert eigs.info() == gpu.CompInfo.Successful and nconv == 20
+    evals, X = eigs.eigenvalues(), eigs.eigenvectors()
+    assert np.all(np.diff(evals) <= 0)
+    res = np.linalg.norm(A @ X - X * evals, axis=0) / np.abs(evals)
+    assert res.max() <= 1e-10
+    assert np.abs(X.T @ X - np.eye(20)).max() <= 1e-10
+
+
 def test_column_blocked_operator_and_solver(gpu, monkeypatch):
     # Large operands are stored as column blocks so that each SpMV pass gathers from an L2-resident slice of x
     # (csr_build.cu: split_column_blocks).  Force the blocked layout at a small size and compare with the unblocked one.
