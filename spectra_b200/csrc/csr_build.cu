@@ -298,53 +298,63 @@ struct BlockPtrs
     double* val[kMaxColBlocks];
 };
 
+// Column -> (block, id inside the block's operand slice).  RANGE: contiguous column ranges of width W, ids stay global.
+// CHUNK: block = which 1/K-th of its owner rank's slab the column lies in, id = position in that partial all-gather.
+struct ColMap
+{
+    int chunked;
+    int64_t W, slab, len;
+    __device__ __forceinline__ int block(int col) const { return chunked ? (int) (((int64_t) col % slab) / len) : (int) (col / W); }
+    __device__ __forceinline__ int remap(int col) const
+    {
+        return chunked ? (int) (((int64_t) col / slab) * len + ((int64_t) col % slab) % len) : col;
+    }
+};
+
 // cnt[c * nrows + r] = number of entries of row r that fall into column block c
-__global__ void block_count_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int64_t nrows, int64_t W, int nb, int* __restrict__ cnt)
+__global__ void block_count_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int64_t nrows, ColMap map, int nb, int* __restrict__ cnt)
 {
     for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t) gridDim.x * blockDim.x)
     {
-        const int b = rowptr[r], e = rowptr[r + 1];
-        int c = 0, run = 0;
-        for (int p = b; p < e; p++)
-        {
-            const int cb = (int) (col[p] / W);
-            while (c < cb)
-            {
-                cnt[(int64_t) c * nrows + r] = run;
-                run = 0;
-                c++;
-            }
-            run++;
-        }
-        while (c < nb)
-        {
-            cnt[(int64_t) c * nrows + r] = run;
-            run = 0;
-            c++;
-        }
+        int run[kMaxColBlocks];
+#pragma unroll
+        for (int c = 0; c < kMaxColBlocks; c++)
+            run[c] = 0;
+        for (int p = rowptr[r]; p < rowptr[r + 1]; p++)
+            run[map.block(col[p])]++;
+        for (int c = 0; c < nb; c++)
+            cnt[(int64_t) c * nrows + r] = run[c];
     }
 }
 
-__global__ void block_fill_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, int64_t nrows, int64_t W,
+// Entries keep their order inside each block; for both maps ascending global columns give ascending remapped ids.
+__global__ void block_fill_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, int64_t nrows, ColMap map, int nb,
                                   BlockPtrs bp)
 {
     for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t) gridDim.x * blockDim.x)
     {
-        const int b = rowptr[r], e = rowptr[r + 1];
-        int c = -1, q = 0;
-        for (int p = b; p < e; p++)
+        int q[kMaxColBlocks];
+        for (int c = 0; c < nb; c++)
+            q[c] = bp.rowptr[c][r];
+        for (int p = rowptr[r]; p < rowptr[r + 1]; p++)
         {
             const int cj = col[p];
-            const int cb = (int) (cj / W);
-            if (cb != c)
-            {
-                c = cb;
-                q = bp.rowptr[c][r];
-            }
-            bp.col[c][q] = cj;
-            bp.val[c][q] = val[p];
-            q++;
+            const int c = map.block(cj);
+            bp.col[c][q[c]] = map.remap(cj);
+            bp.val[c][q[c]] = val[p];
+            q[c]++;
         }
+    }
+}
+
+__global__ void permute_to_chunks_kernel(const double* __restrict__ x, double* __restrict__ xc, int64_t n, int64_t slab, int64_t len, int ranks, int nchunks)
+{
+    const int64_t stride = (int64_t) ranks * len, total = stride * nchunks;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int64_t c = i / stride, rem = i % stride, r = rem / len, ii = rem % len;
+        const int64_t local = c * len + ii, colg = r * slab + local;
+        xc[i] = (local < slab && colg < n) ? x[colg] : 0.0;
     }
 }
 
@@ -364,14 +374,10 @@ void exclusive_scan_to_rowptr(const int* cnt, int64_t nrows, int* rowptr, long l
 
 }  // namespace
 
-void split_column_blocks(DeviceCsr& A, int nb, cudaStream_t stream)
+static void split_by_map(DeviceCsr& A, int nb, const ColMap& map, cudaStream_t stream)
 {
-    if (nb <= 1 || A.nrows == 0 || A.nnz == 0)
-        return;
-    nb = std::min(nb, kMaxColBlocks);
-    const int64_t W = (A.n + nb - 1) / nb;
     DevBuf<int> cnt((size_t) nb * A.nrows);
-    block_count_kernel<<<grid_for(A.nrows, 128), 128, 0, stream>>>(A.rowptr.get(), A.col.get(), A.nrows, W, nb, cnt.get());
+    block_count_kernel<<<grid_for(A.nrows, 128), 128, 0, stream>>>(A.rowptr.get(), A.col.get(), A.nrows, map, nb, cnt.get());
     SB200_CUDA_CHECK(cudaGetLastError());
     A.blocks.clear();
     A.blocks.resize(nb);
@@ -395,14 +401,60 @@ void split_column_blocks(DeviceCsr& A, int nb, cudaStream_t stream)
         bp.col[c] = B.col.get();
         bp.val[c] = B.val.get();
     }
-    block_fill_kernel<<<grid_for(A.nrows, 128), 128, 0, stream>>>(A.rowptr.get(), A.col.get(), A.val.get(), A.nrows, W, bp);
+    block_fill_kernel<<<grid_for(A.nrows, 128), 128, 0, stream>>>(A.rowptr.get(), A.col.get(), A.val.get(), A.nrows, map, nb, bp);
     SB200_CUDA_CHECK(cudaGetLastError());
     SB200_CUDA_CHECK(cudaStreamSynchronize(stream));
-    A.col_block_width = W;
     // the unblocked copy is no longer needed
     A.rowptr.release();
     A.col.release();
     A.val.release();
+}
+
+void split_column_blocks(DeviceCsr& A, int nb, cudaStream_t stream)
+{
+    if (nb <= 1 || A.nrows == 0 || A.nnz == 0)
+        return;
+    nb = std::min(nb, kMaxColBlocks);
+    const int64_t W = (A.n + nb - 1) / nb;
+    split_by_map(A, nb, ColMap{0, W, 0, 0}, stream);
+    A.col_block_width = W;
+}
+
+void split_column_chunks(DeviceCsr& A, int nchunks, int64_t slab, int nranks, cudaStream_t stream)
+{
+    SB200_REQUIRE(nchunks >= 1 && nchunks <= kMaxColBlocks && slab >= 1 && nranks >= 1, SB200_LOGIC, "bad chunk layout");
+    const int64_t len = round_up((slab + nchunks - 1) / nchunks, 16);
+    SB200_REQUIRE((int64_t) nranks * len < (1LL << 31), SB200_LOGIC, "chunk ids exceed the int32 range");
+    A.chunk_slab = slab;
+    A.chunk_len = len;
+    A.chunk_ranks = nranks;
+    if (A.nrows == 0 || A.nnz == 0)
+    {
+        // keep nchunks (empty) blocks so that every rank issues the same sequence of collectives and launches
+        A.blocks.clear();
+        A.blocks.resize(nchunks);
+        for (CsrBlock& B : A.blocks)
+        {
+            B.rowptr.alloc(A.nrows + 1);
+            B.rowptr.zero(stream);
+            B.col.alloc(1);
+            B.val.alloc(1);
+        }
+        A.rowptr.release();
+        A.col.release();
+        A.val.release();
+        SB200_CUDA_CHECK(cudaStreamSynchronize(stream));
+        return;
+    }
+    split_by_map(A, nchunks, ColMap{1, 0, slab, len}, stream);
+}
+
+void launch_permute_to_chunks(const DeviceCsr& A, const double* x_nat, double* x_chunked, cudaStream_t stream)
+{
+    const int nb = (int) A.blocks.size();
+    const int64_t total = A.chunk_stride() * nb;
+    permute_to_chunks_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x_nat, x_chunked, A.n, A.chunk_slab, A.chunk_len, A.chunk_ranks, nb);
+    SB200_CUDA_CHECK(cudaGetLastError());
 }
 
 void upload_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64_t* rowptr_local, const int32_t* col, const double* values, cudaStream_t stream,

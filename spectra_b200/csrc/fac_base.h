@@ -97,7 +97,9 @@ struct FacBase
         n = op->A.n;
         nloc = op->A.nrows;
         // leading dimension: multiple of 16 doubles (128 B) and at least the all-gather slab
-        ld = round_up(std::max<int64_t>(std::max<int64_t>(nloc, op->slab), 2), 64);  // 64-row tiles of the restart GEMM
+        // (64-row tiles of the restart GEMM; chunked all-gathers read nchunks * chunk_len local entries)
+        const int64_t chunk_rows = (op->A.chunk_len && op->nranks() > 1) ? op->A.chunk_len * (int64_t) op->A.blocks.size() : 0;
+        ld = round_up(std::max<int64_t>(std::max<int64_t>(std::max<int64_t>(nloc, op->slab), chunk_rows), 2), 64);
         nev = (int) nev_;
         m = (int) m_;
         V.alloc((size_t) ld * m);
@@ -199,6 +201,24 @@ struct FacBase
             nmatop++;
             return;
         }
+        if (op->A.chunk_len && P() > 1)
+        {
+            spmv_step_chunked(i, restarted, symmetric);
+            stats.spmv_launches++;
+            nmatop++;
+            return;
+        }
+        if (op->A.chunk_len)
+        {
+            // single-GPU test layout (SB200_FORCE_CHUNK_RANKS): permute instead of gathering
+            ScopedKernelTimer t(&prof, stream(), KC_SPMV, 1 + (int) op->A.blocks.size());
+            launch_permute_to_chunks(op->A, f.get(), op->x_chunks.get(), stream());
+            launch_spmv_step(op->A, op->plan, op->x_chunks.get(), f.get(), V.get(), ld, w.get(), ctl.get(), H.get(), m, i, restarted ? 1 : 0, symmetric, rs,
+                             stream());
+            stats.spmv_launches++;
+            nmatop++;
+            return;
+        }
         const double* xfull = gather_full(f.get());
         {
             ScopedKernelTimer t(&prof, stream(), KC_SPMV);
@@ -206,6 +226,33 @@ struct FacBase
         }
         stats.spmv_launches++;
         nmatop++;
+    }
+    // Sharded operator: the operand is all-gathered in chunks on the communication stream; the SpMV of column block c (the
+    // columns that chunk c delivers) starts as soon as chunk c has landed, while chunk c+1 is still on the wire.
+    void spmv_step_chunked(int i, bool restarted, bool symmetric)
+    {
+        const DeviceCsr& A = op->A;
+        const int nb = (int) A.blocks.size();
+        const int64_t len = A.chunk_len, stride = A.chunk_stride();
+        SB200_CUDA_CHECK(cudaEventRecord(op->ev_ready, stream()));  // f is final on the compute stream
+        SB200_CUDA_CHECK(cudaStreamWaitEvent(op->comm_stream, op->ev_ready, 0));
+        for (int c = 0; c < nb; c++)
+        {
+            nccl_allgather(op->comm, f.get() + (int64_t) c * len, op->x_chunks.get() + (int64_t) c * stride, (size_t) len, op->comm_stream);
+            SB200_CUDA_CHECK(cudaEventRecord(op->ev_chunk[(size_t) c], op->comm_stream));
+        }
+        prof.launches += nb;
+        for (int c = 0; c < nb; c++)
+        {
+            {
+                // the wait for the chunk is what remains visible of the collective
+                ScopedKernelTimer t(&prof, stream(), KC_COMM, 0);
+                SB200_CUDA_CHECK(cudaStreamWaitEvent(stream(), op->ev_chunk[(size_t) c], 0));
+            }
+            ScopedKernelTimer t(&prof, stream(), KC_SPMV);
+            launch_spmv_step_block(A, op->plan, c, op->x_chunks.get() + (int64_t) c * stride, f.get(), V.get(), ld, w.get(), ctl.get(), H.get(), m, i,
+                                   restarted ? 1 : 0, symmetric, rs, stream());
+        }
     }
     void panel(int mode, int j, const double* x, double* fo, const double* coef, const int* pred = nullptr)
     {

@@ -44,6 +44,12 @@ struct sb200_op
     sb200::DevBuf<double> x_full;     // n_pad = slab * nranks entries (sharded), else n
     sb200::DevBuf<double> y_loc;      // host-pointer perform_op staging
     sb200::DevBuf<double> x_stage;    // slab-sized send buffer for the all-gather
+    // chunked all-gather / SpMV overlap (sharded operators, DeviceCsr::chunk_len): operand in chunk-major layout, a second
+    // stream for the collectives, one event per chunk
+    sb200::DevBuf<double> x_chunks;   // nchunks * nranks * chunk_len
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_ready = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool symmetric_hint = false;      // created through a SYM mode
     // user-defined host operator (the reference's OpType concept, SymEigsSolver.h:99-114): y = fn(x) on host memory

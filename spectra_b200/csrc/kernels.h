@@ -64,9 +64,22 @@ struct DeviceCsr
     // the other so that each pass gathers from an L2-resident slice of x.  Empty => single block above.
     std::vector<CsrBlock> blocks;
     int64_t col_block_width = 0;
+    // Chunked column layout (row-sharded operators; chunk_len == 0 means the natural layout above).  Column block c holds, for
+    // every rank r, the columns [r*chunk_slab + c*chunk_len, +chunk_len) with their ids REMAPPED to r*chunk_len + i, i.e. to
+    // positions inside the result of the c-th partial all-gather (chunk_ranks*chunk_len doubles).  The SpMV of block c can
+    // therefore start as soon as all-gather c has landed while all-gather c+1 is still in flight.
+    int64_t chunk_slab = 0, chunk_len = 0;
+    int chunk_ranks = 0;
+    int64_t chunk_stride() const { return (int64_t) chunk_ranks * chunk_len; }
+    const double* x_of_block(const double* x, int c) const { return chunk_len ? x + (int64_t) c * chunk_stride() : x; }
 };
 // Re-lays the CSR out in nblocks column blocks (frees the unblocked arrays).  No-op for nblocks <= 1.
 void split_column_blocks(DeviceCsr& A, int nblocks, cudaStream_t stream);
+// Chunked variant for row-sharded operators (see DeviceCsr::chunk_len): nchunks blocks, chunk_len = ceil(slab / nchunks) rounded
+// up to 16 entries.
+void split_column_chunks(DeviceCsr& A, int nchunks, int64_t slab, int nranks, cudaStream_t stream);
+// x_chunked (nchunks * nranks * chunk_len) <- natural-layout x_nat (A.n entries); padding positions are zeroed
+void launch_permute_to_chunks(const DeviceCsr& A, const double* x_nat, double* x_chunked, cudaStream_t stream);
 // Builds the full CSR (columns ascending in each row, duplicates summed) from host compressed
 // arrays.  mode/order as in sb200_matrix_mode / sb200_storage_order.  Keeps rows [row0,row0+nrows).
 void build_device_csr(int64_t n, const void* outer, bool outer64, const int32_t* inner, const double* values, int order, int mode, int64_t row0, int64_t nrows,
@@ -90,6 +103,11 @@ void launch_spmv(const DeviceCsr& A, const SpmvPlan& plan, const double* x, doub
 // V points at column 0 (ld = ldv).  Reads i, beta, hsub from ctl.
 // Also performs the step bookkeeping (block 0): ctl->i = i, count = 0, hsub = restarted ? 0 : beta,
 // H(i,i-1) = hsub (and H(i-1,i) when symmetric)      (Lanczos.h:127-128, Arnoldi.h:239).
+// One column block of the fused step: c < nblocks-1 accumulates the raw product into w, the last block applies the step head.
+// x_block points at the operand slice of block c (DeviceCsr::x_of_block).
+int spmv_num_blocks(const DeviceCsr& A);
+void launch_spmv_step_block(const DeviceCsr& A, const SpmvPlan& plan, int c, const double* x_block, const double* f_loc, double* V, int64_t ldv, double* w,
+                            FacCtl* ctl, double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream);
 void launch_spmv_step(const DeviceCsr& A, const SpmvPlan& plan, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
                       double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream);
 

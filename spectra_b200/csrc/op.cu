@@ -1,4 +1,5 @@
 // Device-resident operator behind sb200_op (replaces Sparse{Sym,Gen}MatProd).
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -64,18 +65,62 @@ sb200_op::~sb200_op()
         cudaEventDestroy(ev0);
     if (ev1)
         cudaEventDestroy(ev1);
+    for (cudaEvent_t e : ev_chunk)
+        cudaEventDestroy(e);
+    if (ev_ready)
+        cudaEventDestroy(ev_ready);
+    if (comm_stream)
+        cudaStreamDestroy(comm_stream);
     if (stream)
         cudaStreamDestroy(stream);
 }
 
 namespace sb200 {
 
+// Number of partial all-gathers per operator application on a sharded operator: enough that one slice of the operand is
+// L2-resident (choose_col_blocks), and at least 2 so that the second collective hides behind the SpMV of the first chunk.
+// Measured on 4 GPUs at n = 1e7 (tools/mgpu_chunks.py): 1 chunk 571 ms, 2 chunks 519 ms, 4 chunks 550 ms, 8 chunks 618 ms
+// per 541 operations -- more chunks shorten the exposed collective but split the rows into ever shorter pieces.
+// SB200_AG_CHUNKS overrides.
+static int choose_chunks(int64_t n)
+{
+    int k = std::max(choose_col_blocks(n), 2);
+    if (const char* e = std::getenv("SB200_AG_CHUNKS"))
+        k = std::atoi(e);
+    return std::max(1, std::min(k, kMaxColBlocks));
+}
+
 static void finish_op(sb200_op* op)
 {
-    split_column_blocks(op->A, choose_col_blocks(op->A.n), op->stream);
-    op->plan = make_spmv_plan(op->A);
     const int P = op->nranks();
     op->slab = (op->A.n + P - 1) / P;
+    // test hook: SB200_FORCE_CHUNK_RANKS=R lays a single-GPU operator out as if it were one of R ranks' (chunk-major operand,
+    // remapped column ids), so that the chunked split / permutation / per-block SpMV are covered without a second GPU
+    int virt = 0;
+    if (P == 1 && !op->cb)
+        if (const char* e = std::getenv("SB200_FORCE_CHUNK_RANKS"))
+            virt = std::max(0, std::atoi(e));
+    if (P > 1 || virt > 0)
+    {
+        const int ranks = P > 1 ? P : virt;
+        const int64_t slab = (op->A.n + ranks - 1) / ranks;
+        split_column_chunks(op->A, choose_chunks(op->A.n), slab, ranks, op->stream);
+        const int nb = (int) op->A.blocks.size();
+        op->x_chunks.alloc((size_t) (op->A.chunk_stride() * nb));
+        op->x_chunks.zero(op->stream);
+    }
+    if (P > 1)
+    {
+        const int nb = (int) op->A.blocks.size();
+        SB200_CUDA_CHECK(cudaStreamCreateWithFlags(&op->comm_stream, cudaStreamNonBlocking));
+        SB200_CUDA_CHECK(cudaEventCreateWithFlags(&op->ev_ready, cudaEventDisableTiming));
+        op->ev_chunk.resize((size_t) nb);
+        for (cudaEvent_t& e : op->ev_chunk)
+            SB200_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    else
+        split_column_blocks(op->A, choose_col_blocks(op->A.n), op->stream);
+    op->plan = make_spmv_plan(op->A);
     if (P > 1)
     {
         op->x_full.alloc((size_t) op->slab * P);
@@ -168,6 +213,12 @@ void op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev)
         op_callback_device(op, x_dev, y_dev);
     else if (op->band)
         band_solve_device(op, x_dev, y_dev);
+    else if (op->A.chunk_len)
+    {
+        // natural-layout operand -> chunk-major operand of the sharded operator (cold paths only: init, perform_op)
+        launch_permute_to_chunks(op->A, x_dev, op->x_chunks.get(), op->stream);
+        launch_spmv(op->A, op->plan, op->x_chunks.get(), y_dev, op->stream);
+    }
     else
         launch_spmv(op->A, op->plan, x_dev, y_dev, op->stream);
 }

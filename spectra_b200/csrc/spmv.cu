@@ -292,29 +292,43 @@ void launch_spmv(const DeviceCsr& A, const SpmvPlan& plan, const double* x, doub
         return;
     const int nb = nblocks_of(A);
     for (int c = 0; c < nb; c++)
-        launch_plain_block(plan.lanes, view_of(A, c), plan.grid, A.nrows, x, y, c > 0, stream);
+        launch_plain_block(plan.lanes, view_of(A, c), plan.grid, A.nrows, A.x_of_block(x, c), y, c > 0, stream);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+int spmv_num_blocks(const DeviceCsr& A) { return nblocks_of(A); }
+
+void launch_spmv_step_block(const DeviceCsr& A, const SpmvPlan& plan, int c, const double* x_block, const double* f_loc, double* V, int64_t ldv, double* w,
+                            FacCtl* ctl, double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream)
+{
+    SB200_REQUIRE(plan.grid <= rs.max_grid, SB200_LOGIC, "spmv: reduction scratch too small");
+    const int nb = nblocks_of(A);
+    if (c + 1 < nb)
+    {
+        // all but the last column block accumulate the raw product into w
+        launch_plain_block(plan.lanes, view_of(A, c), plan.grid, A.nrows, x_block, w, c > 0, stream);
+        SB200_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
+    const BlockView b = view_of(A, nb - 1);
+    const bool accum = nb > 1;
+    switch (plan.lanes)
+    {
+        case 2: launch_step_t<2>(b, plan.grid, A.nrows, x_block, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
+        case 4: launch_step_t<4>(b, plan.grid, A.nrows, x_block, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
+        case 8: launch_step_t<8>(b, plan.grid, A.nrows, x_block, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
+        case 16: launch_step_t<16>(b, plan.grid, A.nrows, x_block, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
+        default: launch_step_t<32>(b, plan.grid, A.nrows, x_block, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
+    }
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_spmv_step(const DeviceCsr& A, const SpmvPlan& plan, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
                       double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream)
 {
-    SB200_REQUIRE(plan.grid <= rs.max_grid, SB200_LOGIC, "spmv: reduction scratch too small");
     const int nb = nblocks_of(A);
-    // all but the last column block accumulate the raw product into w; the last one applies the step head
-    for (int c = 0; c + 1 < nb; c++)
-        launch_plain_block(plan.lanes, view_of(A, c), plan.grid, A.nrows, x_full, w, c > 0, stream);
-    const BlockView b = view_of(A, nb - 1);
-    const bool accum = nb > 1;
-    switch (plan.lanes)
-    {
-        case 2: launch_step_t<2>(b, plan.grid, A.nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
-        case 4: launch_step_t<4>(b, plan.grid, A.nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
-        case 8: launch_step_t<8>(b, plan.grid, A.nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
-        case 16: launch_step_t<16>(b, plan.grid, A.nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
-        default: launch_step_t<32>(b, plan.grid, A.nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
-    }
-    SB200_CUDA_CHECK(cudaGetLastError());
+    for (int c = 0; c < nb; c++)
+        launch_spmv_step_block(A, plan, c, A.x_of_block(x_full, c), f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, rs, stream);
 }
 
 }  // namespace sb200

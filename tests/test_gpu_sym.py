@@ -460,6 +460,42 @@ def test_column_blocked_operator_and_solver(gpu, monkeypatch):
     assert np.abs(E).max() <= 1e-12 * max(1.0, np.abs(fz["H"]).max())
 
 
+@pytest.mark.parametrize("n,ranks,chunks", [(200_003, 3, 4), (1000, 8, 2), (10, 4, 2), (65_537, 2, 5)])
+def test_chunked_operand_layout(gpu, monkeypatch, n, ranks, chunks):
+    # Row-sharded operators keep their columns in "chunk-major" order (column block c = the c-th part of every rank's slab,
+    # ids remapped to positions in the c-th partial all-gather) so that SpMV block c overlaps all-gather c+1.  The test hook
+    # SB200_FORCE_CHUNK_RANKS lays a single-GPU operator out the same way; results must not change.
+    if n >= 1000:
+        from spectra_b200 import synth
+
+        rp, ci, v = synth.csr(n, 20, 3, True)
+        A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+        k, m = 10, 30
+    else:
+        A = sym_full(O.gen_sparse_data(n, 0.5)).tocsr()
+        A.sort_indices()
+        rp, ci, v = A.indptr.astype(np.int64), A.indices, A.data
+        k, m = 3, 6
+    x = O.simple_random(5, n)
+    y0 = A @ x
+    monkeypatch.delenv("SB200_FORCE_CHUNK_RANKS", raising=False)
+    e0 = gpu.SymEigsSolver(gpu.SparseGenMatProd.from_csr_slab(n, 0, rp, ci, v), k, m)
+    e0.init()
+    e0.compute(gpu.SortRule.LargestAlge)
+    monkeypatch.setenv("SB200_FORCE_CHUNK_RANKS", str(ranks))
+    monkeypatch.setenv("SB200_AG_CHUNKS", str(chunks))
+    op = gpu.SparseGenMatProd.from_csr_slab(n, 0, rp, ci, v)
+    assert np.abs(op.perform_op(x) - y0).max() <= 1e-13 * max(1.0, np.abs(y0).max())
+    e1 = gpu.SymEigsSolver(op, k, m)
+    e1.init()
+    e1.compute(gpu.SortRule.LargestAlge)
+    assert e0.info() == gpu.CompInfo.Successful and e1.info() == gpu.CompInfo.Successful
+    assert e1.num_operations() == e0.num_operations()
+    assert np.abs(e1.eigenvalues() - e0.eigenvalues()).max() <= 1e-12 * np.abs(e0.eigenvalues()).max()
+    U = e1.eigenvectors()
+    assert np.abs(A @ U - U * e1.eigenvalues()).max() <= 1e-9
+
+
 def test_user_defined_operator(gpu):
     # the reference's OpType concept (SymEigsSolver.h:99-126): a user class with rows()/cols()/perform_op
     class MyDiagonalTen:
