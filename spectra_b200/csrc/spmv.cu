@@ -113,8 +113,13 @@ __global__ void __launch_bounds__(kSpmvBlock, 8) spmv_plain_kernel(const int* __
 
 // Fused step head on the LAST column block.  x_full: un-normalised residual (all n entries), f_loc: this
 // rank's rows of it.  ACCUM: w already holds the partial product of the previous column blocks.
+// Resident CTAs per SM requested for the fused kernel: 8 (32 registers, a few spilled loop invariants) keeps the gather
+// rate of the plain kernel; SB200_STEP_MINBLOCKS is a build-time knob for A/B runs.
+#ifndef SB200_STEP_MINBLOCKS
+#define SB200_STEP_MINBLOCKS 8
+#endif
 template <int L, bool SYM, bool ACCUM>
-__global__ void __launch_bounds__(kSpmvBlock, 8)
+__global__ void __launch_bounds__(kSpmvBlock, SB200_STEP_MINBLOCKS)
     spmv_step_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x_full,
                      const double* __restrict__ f_loc, double* __restrict__ V, int64_t ldv, double* w, int64_t nrows, FacCtl* ctl, double* H, int m, int i,
                      int restarted, double* partials, unsigned int* ticket)
