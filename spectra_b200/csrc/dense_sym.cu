@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(kDenseBlock)
     extern __shared__ double smem[];
     TriShared sh = carve(smem, m);
     __shared__ double s_hd[kMaxNcv], s_he[kMaxNcv];
-    __shared__ int s_k, s_nconv, s_go;
+    __shared__ int s_k, s_go;
     const int tid = threadIdx.x;
     for (int t = tid; t < m; t += kDenseBlock)
     {
@@ -525,7 +525,6 @@ __global__ void __launch_bounds__(kDenseBlock)
         if (nev_new > m - 1)
             nev_new = m - 1;
         s_k = nev_new;
-        s_nconv = nconv;
         s_go = (do_restart && nconv < nev && info == 0 && nev_new < m) ? 1 : 0;
         out->nconv = nconv;
         out->k = nev_new;
