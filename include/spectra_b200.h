@@ -145,6 +145,14 @@ int sb200_op_apply_matrix(sb200_op* op, const double* X_host, int64_t k, double*
  * vector of ones / scratch output (benchmark convenience). */
 int sb200_op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev, int repeat, float* elapsed_ms);
 int sb200_op_destroy(sb200_op* op);
+/* Device layout of a sparse operator (new surface, for tests and benchmarks): *format = 0 CSR (sub-warp per row kernels), 1 sliced
+ * CSR (one lane per row; experimental, selected with SB200_SPMV_FORMAT=sell at creation); *col_blocks = column blocks the operand is
+ * split into; *stored_entries = matrix entries held on the device including padding. */
+int sb200_op_layout_info(const sb200_op* op, int* format, int* col_blocks, int64_t* stored_entries);
+/* Roofline microbenchmark (tools/gather_roof.py; not on the product path): average time of `gathers` independent, uniformly random
+ * 8-byte read-only loads from a device vector of n doubles -- the operand access of a CSR SpMV with random column ids, without the
+ * matrix stream.  *checksum = mean of the loaded values (1.0). */
+int sb200_bench_gather(int64_t n, int64_t gathers, int repeat, float* elapsed_ms, double* checksum);
 
 /* ------------------------------------------------------------------------------------------
  * SymEigsSolver — replaces SymEigsSolver.h:133-160 + HermEigsBase.h:43-479 (+ the

@@ -284,6 +284,12 @@ class _SparseOp:
         _check(lib().sb200_op_spmv_device(self.h, None, None, int(repeat), C.byref(ms)))
         return ms.value / repeat
 
+    def spmv_layout(self) -> dict:
+        """Device layout: format ('csr' | 'sell'), column blocks, stored entries (incl. padding of the sliced layout)."""
+        fmt, nb, stored = C.c_int(), C.c_int(), C.c_int64()
+        _check(lib().sb200_op_layout_info(self.h, C.byref(fmt), C.byref(nb), C.byref(stored)))
+        return dict(format="sell" if fmt.value == 1 else "csr", col_blocks=nb.value, stored_entries=stored.value)
+
     def close(self):
         if getattr(self, "h", None):
             lib().sb200_op_destroy(self.h)
@@ -294,6 +300,13 @@ class _SparseOp:
             self.close()
         except Exception:
             pass
+
+
+def bench_gather(n: int, gathers: int, repeat: int = 5) -> dict:
+    """Roofline microbenchmark (tools/gather_roof.py): time of `gathers` uniformly random 8-byte loads from n doubles."""
+    ms, chk = C.c_float(), C.c_double()
+    _check(lib().sb200_bench_gather(C.c_int64(int(n)), C.c_int64(int(gathers)), int(repeat), C.byref(ms), C.byref(chk)))
+    return dict(ms=ms.value, checksum=chk.value)
 
 
 _MATVEC_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)

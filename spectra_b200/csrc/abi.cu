@@ -15,6 +15,7 @@ void op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev);
 sb200_op* op_create_callback(int64_t n, void (*fn)(const double*, double*, void*), void* user);
 sb200_op* op_create_shift_solve(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values, int storage_order, int matrix_mode);
 void op_perform_op_host(sb200_op* op, const double* x_host, double* y_host);
+float bench_gather(int64_t n, int64_t gathers, int repeat, double* checksum);
 
 sb200_sym_solver* sym_create(sb200_op* op, int64_t nev, int64_t ncv, bool shift_mode, double sigma);
 void sym_init(sb200_sym_solver* s, const double* resid);
@@ -242,6 +243,35 @@ int sb200_op_nnz(const sb200_op* op, int64_t* nnz_local)
     ABI_TRY
     ABI_NONNULL(op);
     *nnz_local = op->A.nnz;
+    ABI_CATCH
+}
+int sb200_op_layout_info(const sb200_op* op, int* format, int* col_blocks, int64_t* stored_entries)
+{
+    ABI_TRY
+    ABI_NONNULL(op);
+    const DeviceCsr& A = op->A;
+    int64_t stored = 0;
+    bool sell = op->plan.sell_threads > 0;
+    if (A.blocks.empty())
+        stored = sell ? A.sell.padded : A.nnz;
+    else
+        for (const CsrBlock& B : A.blocks)
+            stored += sell ? B.sell.padded : B.nnz;
+    if (format)
+        *format = sell ? 1 : 0;
+    if (col_blocks)
+        *col_blocks = A.blocks.empty() ? 1 : (int) A.blocks.size();
+    if (stored_entries)
+        *stored_entries = stored;
+    ABI_CATCH
+}
+int sb200_bench_gather(int64_t n, int64_t gathers, int repeat, float* elapsed_ms, double* checksum)
+{
+    ABI_TRY
+    device_info();
+    const float ms = bench_gather(n, gathers, repeat, checksum);
+    if (elapsed_ms)
+        *elapsed_ms = ms;
     ABI_CATCH
 }
 int sb200_op_perform_op(sb200_op* op, const double* x_host, double* y_host)

@@ -1,7 +1,12 @@
 // Shared host/device helpers for the sm_100a eigensolver library.
 #pragma once
 
+#ifdef SB200_EMU
+// kernel-logic emulation build (tools/cuda_emu/, test infrastructure only): the CUDA execution model on CPU fibers
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include <cmath>
@@ -232,6 +237,21 @@ __device__ __forceinline__ double subwarp_sum(double v)
     return v;
 }
 
+#ifdef SB200_EMU
+// emulation: cache hints have no meaning on the CPU; the loads are plain loads
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { return 0; }
+__device__ __forceinline__ uint64_t l2_policy_evict_last() { return 0; }
+__device__ __forceinline__ double ld_stream_f64(const double* p, uint64_t) { return *p; }
+__device__ __forceinline__ int ld_stream_s32(const int* p, uint64_t) { return *p; }
+__device__ __forceinline__ double2 ld_stream_f64x2(const double* p, uint64_t) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void ld_stream_f64x4(const double* p, double (&v)[4])
+{
+    for (int q = 0; q < 4; q++)
+        v[q] = p[q];
+}
+__device__ __forceinline__ double ld_keep_f64(const double* p, uint64_t) { return *p; }
+__device__ __forceinline__ double ld_cg_f64(const double* p) { return *p; }
+#else
 // L2 cache policies (createpolicy): streamed-once data is marked evict_first so that the gathered
 // operand vector / small reused vectors keep their L2 residency (evict_last).
 __device__ __forceinline__ uint64_t l2_policy_evict_first()
@@ -295,6 +315,7 @@ __device__ __forceinline__ double ld_cg_f64(const double* p)
     asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
+#endif  // SB200_EMU
 
 // Grid-wide deterministic reduction of K (<= 128) per-CTA partial values.
 //   partials : gridDim.x * 128 doubles (scratch);  ticket : zero-initialised counter, left at zero.

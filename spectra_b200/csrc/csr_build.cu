@@ -457,6 +457,135 @@ void launch_permute_to_chunks(const DeviceCsr& A, const double* x_nat, double* x
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sliced layout (SellBlock, kernels.h): window sort -> slice widths -> scan -> step-major fill
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// One CTA per window of kSellWindow rows, one thread per row: stable rank of the row by descending length.
+// perm[win * W + rank] = row inside the window; cnt[slice] = 32 * (longest row of the slice) = stored entries of the slice.
+__global__ void __launch_bounds__(kSellWindow) sell_sort_kernel(const int* __restrict__ rowptr, int64_t nrows, unsigned short* __restrict__ perm, int* __restrict__ cnt)
+{
+    __shared__ __align__(16) int s_len[kSellWindow];
+    const int r = threadIdx.x;
+    const int64_t row = (int64_t) blockIdx.x * kSellWindow + r;
+    const int len = (row < nrows) ? rowptr[row + 1] - rowptr[row] : 0;
+    s_len[r] = len;
+    __syncthreads();
+    int rank = 0;
+    const int4* s4 = reinterpret_cast<const int4*>(s_len);
+    for (int q = 0; q < kSellWindow / 4; q++)
+    {
+        const int4 l = s4[q];  // broadcast read
+        const int j = 4 * q;
+        rank += (l.x > len || (l.x == len && j + 0 < r)) ? 1 : 0;
+        rank += (l.y > len || (l.y == len && j + 1 < r)) ? 1 : 0;
+        rank += (l.z > len || (l.z == len && j + 2 < r)) ? 1 : 0;
+        rank += (l.w > len || (l.w == len && j + 3 < r)) ? 1 : 0;
+    }
+    perm[(int64_t) blockIdx.x * kSellWindow + rank] = (unsigned short) r;
+    if ((rank & (kSellSlice - 1)) == 0)
+        cnt[(int64_t) blockIdx.x * (kSellWindow / kSellSlice) + rank / kSellSlice] = (len < (1 << 25)) ? len * kSellSlice : 0x7fffffe0;  // absurd rows: forces rejection
+}
+
+// One warp per slice: lane = row of the slice; writes the slice step-major, padding with (col -1, val 0).
+__global__ void sell_fill_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, int64_t nrows, int64_t nslices,
+                                 const unsigned short* __restrict__ perm, const int* __restrict__ slice_ptr, int* __restrict__ scol, double* __restrict__ sval)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t) gridDim.x * blockDim.x) >> 5;
+    constexpr int SPW = kSellWindow / kSellSlice;  // slices per window
+    for (int64_t s = gw; s < nslices; s += nw)
+    {
+        const int64_t win = s / SPW;
+        const int pos = (int) (s % SPW) * kSellSlice + lane;
+        const int64_t row = win * kSellWindow + perm[win * kSellWindow + pos];
+        int b = 0, len = 0;
+        if (row < nrows)
+        {
+            b = rowptr[row];
+            len = rowptr[row + 1] - b;
+        }
+        const int base = slice_ptr[s];
+        const int width = (slice_ptr[s + 1] - base) / kSellSlice;
+        for (int t = 0; t < width; t++)
+        {
+            const int dst = base + t * kSellSlice + lane;
+            const bool real = t < len;
+            scol[dst] = real ? col[b + t] : -1;
+            sval[dst] = real ? val[b + t] : 0.0;
+        }
+    }
+}
+
+// Stored entries of the sliced layout of one CSR (device rowptr), without building it.
+void sell_prepare(const int* rowptr, int64_t nrows, SellBlock& S, long long* padded, cudaStream_t stream)
+{
+    const int64_t nwin = (nrows + kSellWindow - 1) / kSellWindow;
+    const int64_t nslices = nwin * (kSellWindow / kSellSlice);
+    S.nwin = nwin;
+    S.perm.alloc((size_t) (nwin * kSellWindow));
+    S.slice_ptr.alloc((size_t) (nslices + 1));
+    DevBuf<int> cnt((size_t) nslices);
+    sell_sort_kernel<<<(unsigned) nwin, kSellWindow, 0, stream>>>(rowptr, nrows, S.perm.get(), cnt.get());
+    SB200_CUDA_CHECK(cudaGetLastError());
+    exclusive_scan_to_rowptr(cnt.get(), nslices, S.slice_ptr.get(), padded, stream);
+    S.padded = *padded;
+}
+
+void sell_fill(const int* rowptr, const int* col, const double* val, int64_t nrows, SellBlock& S, cudaStream_t stream)
+{
+    const int64_t nslices = S.nwin * (kSellWindow / kSellSlice);
+    S.col.alloc((size_t) std::max<int64_t>(S.padded, 1));
+    S.val.alloc((size_t) std::max<int64_t>(S.padded, 1));
+    sell_fill_kernel<<<grid_for(nslices * 32, 256), 256, 0, stream>>>(rowptr, col, val, nrows, nslices, S.perm.get(), S.slice_ptr.get(), S.col.get(), S.val.get());
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+bool build_sell_layout(DeviceCsr& A, double max_fill, cudaStream_t stream)
+{
+    if (A.nrows == 0)
+        return false;
+    struct Part
+    {
+        const int* rowptr;
+        const int* col;
+        const double* val;
+        int64_t nnz;
+        SellBlock* S;
+    };
+    std::vector<Part> parts;
+    if (A.blocks.empty())
+        parts.push_back({A.rowptr.get(), A.col.get(), A.val.get(), A.nnz, &A.sell});
+    else
+        for (CsrBlock& B : A.blocks)
+            parts.push_back({B.rowptr.get(), B.col.get(), B.val.get(), B.nnz, &B.sell});
+    bool ok = true;
+    long long total_padded = 0, total_nnz = 0;
+    for (Part& p : parts)
+    {
+        long long padded = 0;
+        sell_prepare(p.rowptr, A.nrows, *p.S, &padded, stream);
+        ok = ok && padded < (1LL << 31) - 64;
+        total_padded += padded;
+        total_nnz += p.nnz;
+    }
+    // padding of at most one 32-row step per window is always accepted (tiny operands)
+    ok = ok && double(total_padded) <= max_fill * double(total_nnz) + 32.0 * double(kSellWindow) * double(parts.size());
+    if (!ok)
+    {
+        for (Part& p : parts)
+            p.S->release();
+        return false;
+    }
+    for (Part& p : parts)
+        sell_fill(p.rowptr, p.col, p.val, A.nrows, *p.S, stream);
+    SB200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return true;
+}
+
 void upload_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64_t* rowptr_local, const int32_t* col, const double* values, cudaStream_t stream,
                      DeviceCsr& out)
 {

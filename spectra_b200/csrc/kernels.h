@@ -42,6 +42,38 @@ struct RedScratch
 
 // ---- CSR build (csr_build.cu) -----------------------------------------------------------------
 constexpr int kMaxColBlocks = 16;
+
+// Sliced layout of one CSR (block) for the lane-per-row SpMV kernels (spmv.cu, "sliced CSR" / SELL-32-sigma):
+// rows are grouped in windows of kSellWindow consecutive rows; inside a window the rows are ordered by
+// descending length (stable) and cut into slices of 32 rows; a slice stores its entries step-major
+// (entry t of the 32 rows side by side), padded to the longest row of the slice with column id -1.
+// Lane r of a warp therefore owns one row and reads col / val with fully coalesced 128 B / 256 B warp
+// loads, sums its row sequentially in ascending column order (the order a scalar CSR loop uses) and needs
+// no cross-lane reduction.  perm maps (window, position after sorting) -> row inside the window, so that the
+// kernels can hand their results back in natural row order through shared memory.
+// Experimental in round 1 (SB200_SPMV_FORMAT=sell): built next to the CSR arrays, which stay authoritative.
+constexpr int kSellWindow = 1024;
+constexpr int kSellSlice = 32;
+struct SellBlock
+{
+    int64_t nwin = 0;              // windows = ceil(nrows / kSellWindow)
+    int64_t padded = 0;            // stored entries including padding (multiple of 32)
+    DevBuf<int> slice_ptr;         // nwin * 32 + 1 entry offsets
+    DevBuf<int> col;               // padded; -1 marks padding
+    DevBuf<double> val;            // padded
+    DevBuf<unsigned short> perm;   // nwin * kSellWindow
+    bool built() const { return nwin > 0; }
+    void release()
+    {
+        nwin = 0;
+        padded = 0;
+        slice_ptr.release();
+        col.release();
+        val.release();
+        perm.release();
+    }
+};
+
 // One column block of the operand: a CSR of its own over columns [c0, c1).
 struct CsrBlock
 {
@@ -49,6 +81,7 @@ struct CsrBlock
     DevBuf<int> rowptr;   // nrows + 1
     DevBuf<int> col;      // nnz (global column ids)
     DevBuf<double> val;   // nnz
+    SellBlock sell;       // optional sliced copy (build_sell_layout)
 };
 struct DeviceCsr
 {
@@ -64,6 +97,7 @@ struct DeviceCsr
     // the other so that each pass gathers from an L2-resident slice of x.  Empty => single block above.
     std::vector<CsrBlock> blocks;
     int64_t col_block_width = 0;
+    SellBlock sell;       // optional sliced copy of the unblocked CSR (build_sell_layout)
     // Chunked column layout (row-sharded operators; chunk_len == 0 means the natural layout above).  Column block c holds, for
     // every rank r, the columns [r*chunk_slab + c*chunk_len, +chunk_len) with their ids REMAPPED to r*chunk_len + i, i.e. to
     // positions inside the result of the c-th partial all-gather (chunk_ranks*chunk_len doubles).  The SpMV of block c can
@@ -80,6 +114,9 @@ void split_column_blocks(DeviceCsr& A, int nblocks, cudaStream_t stream);
 void split_column_chunks(DeviceCsr& A, int nchunks, int64_t slab, int nranks, cudaStream_t stream);
 // x_chunked (nchunks * nranks * chunk_len) <- natural-layout x_nat (A.n entries); padding positions are zeroed
 void launch_permute_to_chunks(const DeviceCsr& A, const double* x_nat, double* x_chunked, cudaStream_t stream);
+// Adds the sliced layout (SellBlock) to the CSR / to every column block.  Returns false (and builds nothing) when padding
+// would store more than max_fill times the nonzeros (very uneven row lengths: the CSR-vector kernels stay in charge).
+bool build_sell_layout(DeviceCsr& A, double max_fill, cudaStream_t stream);
 // Builds the full CSR (columns ascending in each row, duplicates summed) from host compressed
 // arrays.  mode/order as in sb200_matrix_mode / sb200_storage_order.  Keeps rows [row0,row0+nrows).
 void build_device_csr(int64_t n, const void* outer, bool outer64, const int32_t* inner, const double* values, int order, int mode, int64_t row0, int64_t nrows,
@@ -92,6 +129,8 @@ struct SpmvPlan
 {
     int lanes = 8;  // lanes per row
     int grid = 0;
+    int sell_threads = 0;  // > 0: the operand carries the sliced layout and the lane-per-row kernels run (CTA size)
+    int sell_grid = 0;
 };
 SpmvPlan make_spmv_plan(const DeviceCsr& A);
 // column blocks needed so that one slice of the gathered operand stays L2-resident (env SB200_XSLICE_MB)

@@ -120,6 +120,15 @@ static void finish_op(sb200_op* op)
     }
     else
         split_column_blocks(op->A, choose_col_blocks(op->A.n), op->stream);
+    // experimental (round 1: written, not yet measured on a GPU): sliced layout + lane-per-row kernels, see spmv.cu
+    if (const char* e = std::getenv("SB200_SPMV_FORMAT"))
+        if (std::strcmp(e, "sell") == 0)
+        {
+            double max_fill = 1.3;
+            if (const char* f = std::getenv("SB200_SELL_MAX_FILL"))
+                max_fill = std::max(1.0, std::atof(f));
+            build_sell_layout(op->A, max_fill, op->stream);
+        }
     op->plan = make_spmv_plan(op->A);
     if (P > 1)
     {

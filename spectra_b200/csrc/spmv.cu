@@ -18,6 +18,12 @@
 // (measured at n = 1e7 unblocked: 7.4 GB of DRAM reads per SpMV for 2.76 GB of algorithmic bytes).
 // Algorithmic bytes per row at d nnz/row: 12 d + 4 + 8 (x once) + 8 (y)  (SURVEY §8d); blocking adds
 // 4 (row pointer) + 16 (y read-modify-write) bytes per row per extra block.
+//
+// Sliced layout (SellBlock, kernels.h; SB200_SPMV_FORMAT=sell, experimental): the same column blocks stored as 32-row slices,
+// step-major, rows sorted by length inside 1024-row windows.  One lane owns one row: no shuffles, every CSR byte arrives in a
+// fully coalesced warp load, the row sum runs in ascending column order.  A CTA owns one window at a time and returns the sums
+// to natural row order through 8 KB of shared memory, so the epilogues (accumulate, fused step head) are the coalesced ones of
+// the CSR-vector kernels.  Traffic per row at d nnz/row and padding p: 12 d (1 + p) + 2 (perm) + 0.25 (slice_ptr) + x + y.
 #include <cstdlib>
 
 #include "kernels.h"
@@ -188,12 +194,174 @@ __global__ void __launch_bounds__(kSpmvBlock, SB200_STEP_MINBLOCKS)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sliced-layout kernels: one lane per row, one CTA per 1024-row window at a time
+// ---------------------------------------------------------------------------------------------
+constexpr int sell_min_blocks(int threads) { return 1536 / threads; }  // 48 resident warps per SM (32 at 1024 threads)
+
+// Row sums of window `win` into s_y (natural row order inside the window).  Warp w handles slices w, w + WARPS, ...: the slices of
+// a window are sorted by length, so every warp gets long and short ones.
+template <int THREADS>
+__device__ __forceinline__ void sell_window_dot(const int* __restrict__ slice_ptr, const int* __restrict__ scol, const double* __restrict__ sval,
+                                                const unsigned short* __restrict__ perm, const double* __restrict__ x, int64_t win, double* s_y,
+                                                uint64_t pol_stream, uint64_t pol_keep)
+{
+    constexpr int WARPS = THREADS / 32;
+    constexpr int SPW = kSellWindow / kSellSlice;
+    static_assert(SPW % WARPS == 0, "warps must divide the slices of a window");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int q = 0; q < SPW / WARPS; q++)
+    {
+        const int sl = q * WARPS + warp;
+        const int64_t s = win * SPW + sl;
+        const int base = __ldg(slice_ptr + s);
+        const int steps = (__ldg(slice_ptr + s + 1) - base) >> 5;
+        const int* cp = scol + base + lane;
+        const double* vp = sval + base + lane;
+        double acc = 0.0;
+        int t = 0;
+        // four steps (= four independent gathers per lane) in flight; padding carries col -1 / val 0
+        for (; t + 4 <= steps; t += 4)
+        {
+            const int c0 = ld_stream_s32(cp + (t + 0) * 32, pol_stream);
+            const int c1 = ld_stream_s32(cp + (t + 1) * 32, pol_stream);
+            const int c2 = ld_stream_s32(cp + (t + 2) * 32, pol_stream);
+            const int c3 = ld_stream_s32(cp + (t + 3) * 32, pol_stream);
+            const double v0 = ld_stream_f64(vp + (t + 0) * 32, pol_stream);
+            const double v1 = ld_stream_f64(vp + (t + 1) * 32, pol_stream);
+            const double v2 = ld_stream_f64(vp + (t + 2) * 32, pol_stream);
+            const double v3 = ld_stream_f64(vp + (t + 3) * 32, pol_stream);
+            const double x0 = (c0 >= 0) ? ld_keep_f64(x + c0, pol_keep) : 0.0;
+            const double x1 = (c1 >= 0) ? ld_keep_f64(x + c1, pol_keep) : 0.0;
+            const double x2 = (c2 >= 0) ? ld_keep_f64(x + c2, pol_keep) : 0.0;
+            const double x3 = (c3 >= 0) ? ld_keep_f64(x + c3, pol_keep) : 0.0;
+            acc = fma(v0, x0, acc);
+            acc = fma(v1, x1, acc);
+            acc = fma(v2, x2, acc);
+            acc = fma(v3, x3, acc);
+        }
+        for (; t < steps; t++)
+        {
+            const int c0 = ld_stream_s32(cp + t * 32, pol_stream);
+            const double v0 = ld_stream_f64(vp + t * 32, pol_stream);
+            const double x0 = (c0 >= 0) ? ld_keep_f64(x + c0, pol_keep) : 0.0;
+            acc = fma(v0, x0, acc);
+        }
+        s_y[__ldg(perm + win * kSellWindow + sl * kSellSlice + lane)] = acc;
+    }
+}
+
+// y = (ACCUM ? y : 0) + A_block x
+template <int THREADS, bool ACCUM>
+__global__ void __launch_bounds__(THREADS, sell_min_blocks(THREADS))
+    sell_plain_kernel(const int* __restrict__ slice_ptr, const int* __restrict__ scol, const double* __restrict__ sval, const unsigned short* __restrict__ perm,
+                      const double* __restrict__ x, double* y, int64_t nrows, int64_t nwin)
+{
+    __shared__ double s_y[kSellWindow];
+    const uint64_t pol_stream = l2_policy_evict_first();
+    const uint64_t pol_keep = l2_policy_evict_last();
+    for (int64_t win = blockIdx.x; win < nwin; win += gridDim.x)
+    {
+        sell_window_dot<THREADS>(slice_ptr, scol, sval, perm, x, win, s_y, pol_stream, pol_keep);
+        __syncthreads();
+        for (int r = threadIdx.x; r < kSellWindow; r += THREADS)
+        {
+            const int64_t row = win * kSellWindow + r;
+            if (row < nrows)
+            {
+                double s = s_y[r];
+                if (ACCUM)
+                    s += y[row];
+                y[row] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Fused step head on the last column block; same contract as spmv_step_kernel.
+template <int THREADS, bool SYM, bool ACCUM>
+__global__ void __launch_bounds__(THREADS, sell_min_blocks(THREADS))
+    sell_step_kernel(const int* __restrict__ slice_ptr, const int* __restrict__ scol, const double* __restrict__ sval, const unsigned short* __restrict__ perm,
+                     const double* __restrict__ x_full, const double* __restrict__ f_loc, double* __restrict__ V, int64_t ldv, double* w, int64_t nrows,
+                     int64_t nwin, FacCtl* ctl, double* H, int m, int i, int restarted, double* partials, unsigned int* ticket)
+{
+    __shared__ double s_y[kSellWindow];
+    const uint64_t pol_stream = l2_policy_evict_first();
+    const uint64_t pol_keep = l2_policy_evict_last();
+    const double beta = ctl->beta;
+    const double hsub = restarted ? 0.0 : beta;
+    double* __restrict__ vi = V + (int64_t) i * ldv;
+    const double* __restrict__ vp = V + (int64_t) (i - 1) * ldv;
+
+    double part = 0.0;
+    for (int64_t win = blockIdx.x; win < nwin; win += gridDim.x)
+    {
+        sell_window_dot<THREADS>(slice_ptr, scol, sval, perm, x_full, win, s_y, pol_stream, pol_keep);
+        __syncthreads();
+        for (int r = threadIdx.x; r < kSellWindow; r += THREADS)
+        {
+            const int64_t row = win * kSellWindow + r;
+            if (row < nrows)
+            {
+                double s = s_y[r];
+                if (ACCUM)
+                    s += w[row];
+                const double v = f_loc[row] / beta;  // v_i = f / ||f||      (Lanczos.h:106)
+                vi[row] = v;
+                double wr = s / beta;                // w = A v_i, with the scaling applied after the product
+                if (SYM)
+                {
+                    wr -= hsub * vp[row];            // w -= H(i,i-1) v_{i-1}  (Lanczos.h:139)
+                    part = fma(v, wr, part);         // <v_i, w>               (Lanczos.h:142)
+                }
+                w[row] = wr;
+            }
+        }
+        __syncthreads();
+    }
+
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        // step bookkeeping (Lanczos.h:127-128, Arnoldi.h:239)
+        ctl->i = i;
+        ctl->count = 0;
+        ctl->hsub = hsub;
+        ctl->need_corr = 0;
+        ctl->f_zeroed = 0;
+        ctl->dgks_skip = 0;
+        H[i + (int64_t) (i - 1) * m] = hsub;
+        if (SYM)
+            H[(i - 1) + (int64_t) i * m] = hsub;
+    }
+
+    if (SYM)
+    {
+        // CTA partial in a fixed order: warp shuffle tree, then the warps sequentially
+        __shared__ double s_w[THREADS / 32];
+        part = warp_sum(part);
+        if ((threadIdx.x & 31) == 0)
+            s_w[threadIdx.x >> 5] = part;
+        __syncthreads();
+        double cta = 0.0;
+        if (threadIdx.x == 0)
+        {
+#pragma unroll
+            for (int q = 0; q < THREADS / 32; q++)
+                cta += s_w[q];
+        }
+        grid_reduce_fixed_order<THREADS>(cta, 1, partials, ticket, ctl->red_a);
+    }
+}
+
 struct BlockView
 {
     const int* rowptr;
     const int* col;
     const double* val;
     int64_t nnz;
+    const SellBlock* sell;  // non-null when the sliced layout was built
 };
 
 int nblocks_of(const DeviceCsr& A) { return A.blocks.empty() ? 1 : (int) A.blocks.size(); }
@@ -201,9 +369,9 @@ int nblocks_of(const DeviceCsr& A) { return A.blocks.empty() ? 1 : (int) A.block
 BlockView view_of(const DeviceCsr& A, int c)
 {
     if (A.blocks.empty())
-        return {A.rowptr.get(), A.col.get(), A.val.get(), A.nnz};
+        return {A.rowptr.get(), A.col.get(), A.val.get(), A.nnz, A.sell.built() ? &A.sell : nullptr};
     const CsrBlock& B = A.blocks[c];
-    return {B.rowptr.get(), B.col.get(), B.val.get(), B.nnz};
+    return {B.rowptr.get(), B.col.get(), B.val.get(), B.nnz, B.sell.built() ? &B.sell : nullptr};
 }
 
 int lanes_for(double avg)
@@ -228,9 +396,29 @@ void launch_plain_t(const BlockView& b, int grid, int64_t nrows, const double* x
         spmv_plain_kernel<L, false><<<grid, kSpmvBlock, 0, stream>>>(b.rowptr, b.col, b.val, x, y, nrows);
 }
 
-void launch_plain_block(int lanes, const BlockView& b, int grid, int64_t nrows, const double* x, double* y, bool accum, cudaStream_t stream)
+template <int THREADS>
+void launch_sell_plain_t(const SellBlock& S, int grid, int64_t nrows, const double* x, double* y, bool accum, cudaStream_t stream)
 {
-    switch (lanes)
+    if (accum)
+        sell_plain_kernel<THREADS, true><<<grid, THREADS, 0, stream>>>(S.slice_ptr.get(), S.col.get(), S.val.get(), S.perm.get(), x, y, nrows, S.nwin);
+    else
+        sell_plain_kernel<THREADS, false><<<grid, THREADS, 0, stream>>>(S.slice_ptr.get(), S.col.get(), S.val.get(), S.perm.get(), x, y, nrows, S.nwin);
+}
+
+void launch_plain_block(const SpmvPlan& plan, const BlockView& b, int64_t nrows, const double* x, double* y, bool accum, cudaStream_t stream)
+{
+    if (b.sell && plan.sell_threads)
+    {
+        switch (plan.sell_threads)
+        {
+            case 256: launch_sell_plain_t<256>(*b.sell, plan.sell_grid, nrows, x, y, accum, stream); break;
+            case 1024: launch_sell_plain_t<1024>(*b.sell, plan.sell_grid, nrows, x, y, accum, stream); break;
+            default: launch_sell_plain_t<512>(*b.sell, plan.sell_grid, nrows, x, y, accum, stream); break;
+        }
+        return;
+    }
+    const int grid = plan.grid;
+    switch (plan.lanes)
     {
         case 2: launch_plain_t<2>(b, grid, nrows, x, y, accum, stream); break;
         case 4: launch_plain_t<4>(b, grid, nrows, x, y, accum, stream); break;
@@ -238,6 +426,24 @@ void launch_plain_block(int lanes, const BlockView& b, int grid, int64_t nrows, 
         case 16: launch_plain_t<16>(b, grid, nrows, x, y, accum, stream); break;
         default: launch_plain_t<32>(b, grid, nrows, x, y, accum, stream); break;
     }
+}
+
+template <int THREADS>
+void launch_sell_step_t(const SellBlock& S, int grid, int64_t nrows, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
+                        double* H, int m, int i, int restarted, bool symmetric, bool accum, const RedScratch& rs, cudaStream_t stream)
+{
+#define SB200_SELL_STEP(SYM, ACC)                                                                                                                              \
+    sell_step_kernel<THREADS, SYM, ACC><<<grid, THREADS, 0, stream>>>(S.slice_ptr.get(), S.col.get(), S.val.get(), S.perm.get(), x_full, f_loc, V, ldv, w, nrows, \
+                                                                      S.nwin, ctl, H, m, i, restarted, rs.partials, rs.ticket)
+    if (symmetric && accum)
+        SB200_SELL_STEP(true, true);
+    else if (symmetric)
+        SB200_SELL_STEP(true, false);
+    else if (accum)
+        SB200_SELL_STEP(false, true);
+    else
+        SB200_SELL_STEP(false, false);
+#undef SB200_SELL_STEP
 }
 
 template <int L>
@@ -277,6 +483,19 @@ SpmvPlan make_spmv_plan(const DeviceCsr& A)
     const int64_t need = (A.nrows + rpb - 1) / rpb;
     // persistent grid: up to 8 resident CTAs of 256 threads per SM
     p.grid = (int) std::max<int64_t>(1, std::min<int64_t>(need, (int64_t) sms * 8));
+    // sliced layout present (build_sell_layout): lane-per-row kernels, persistent grid of one window per CTA iteration
+    const SellBlock& S0 = A.blocks.empty() ? A.sell : A.blocks[0].sell;
+    if (S0.built())
+    {
+        p.sell_threads = 512;
+        if (const char* e = std::getenv("SB200_SELL_THREADS"))
+        {
+            const int v = std::atoi(e);
+            if (v == 256 || v == 512 || v == 1024)
+                p.sell_threads = v;
+        }
+        p.sell_grid = (int) std::max<int64_t>(1, std::min<int64_t>(S0.nwin, (int64_t) sms * sell_min_blocks(p.sell_threads)));
+    }
     return p;
 }
 
@@ -297,7 +516,7 @@ void launch_spmv(const DeviceCsr& A, const SpmvPlan& plan, const double* x, doub
         return;
     const int nb = nblocks_of(A);
     for (int c = 0; c < nb; c++)
-        launch_plain_block(plan.lanes, view_of(A, c), plan.grid, A.nrows, A.x_of_block(x, c), y, c > 0, stream);
+        launch_plain_block(plan, view_of(A, c), A.nrows, A.x_of_block(x, c), y, c > 0, stream);
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -311,12 +530,24 @@ void launch_spmv_step_block(const DeviceCsr& A, const SpmvPlan& plan, int c, con
     if (c + 1 < nb)
     {
         // all but the last column block accumulate the raw product into w
-        launch_plain_block(plan.lanes, view_of(A, c), plan.grid, A.nrows, x_block, w, c > 0, stream);
+        launch_plain_block(plan, view_of(A, c), A.nrows, x_block, w, c > 0, stream);
         SB200_CUDA_CHECK(cudaGetLastError());
         return;
     }
     const BlockView b = view_of(A, nb - 1);
     const bool accum = nb > 1;
+    if (b.sell && plan.sell_threads)
+    {
+        SB200_REQUIRE(plan.sell_grid <= rs.max_grid, SB200_LOGIC, "spmv: reduction scratch too small");
+        switch (plan.sell_threads)
+        {
+            case 256: launch_sell_step_t<256>(*b.sell, plan.sell_grid, A.nrows, x_block, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
+            case 1024: launch_sell_step_t<1024>(*b.sell, plan.sell_grid, A.nrows, x_block, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
+            default: launch_sell_step_t<512>(*b.sell, plan.sell_grid, A.nrows, x_block, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
+        }
+        SB200_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     switch (plan.lanes)
     {
         case 2: launch_step_t<2>(b, plan.grid, A.nrows, x_block, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;

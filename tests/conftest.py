@@ -33,7 +33,20 @@ def _build_cpu_side():
 
 
 @pytest.fixture(scope="session")
+def emu():
+    """The product's kernels compiled for the CPU against the CUDA execution model of tools/cuda_emu (logic checks without a GPU)."""
+    import emu_loader
+
+    return emu_loader.load()
+
+
+@pytest.fixture(scope="session")
 def gpu():
+    if os.environ.get("SB200_TEST_BACKEND") == "emu":
+        # developer mode: run the gpu-marked tests against the kernel-logic emulator (python -m pytest tests -m gpu with this variable set)
+        import emu_loader
+
+        return emu_loader.load()
     if not _has_gpu():
         pytest.fail("a test marked `gpu` ran without a usable CUDA device / built library (no CPU fallback exists)")
     import spectra_b200 as sb

@@ -1,0 +1,521 @@
+// cuda_emu.h -- a small CUDA-on-CPU execution model, TEST INFRASTRUCTURE ONLY.
+//
+// Purpose: run the *source* of the sm_100a kernels (spectra_b200/csrc/*.cu) on the CPU to check their logic (indexing, barriers,
+// shuffles, reductions, host sequencing) when no GPU is at hand.  tools/cuda_emu/emu_build.py rewrites the `<<< >>>` launches and
+// `extern __shared__` declarations, compiles the sources with g++ against this header and links tests/_emu/libspectra_b200_emu.so.
+// Nothing in spectra_b200/ loads that library; it is used by `tests/test_emu_*.py` (-m "not gpu") only, exactly like the oracle.
+// It is NOT a fallback of the product (the product has none), it says nothing about performance, and it cannot run the kernels that
+// are written in PTX (TMA / mbarrier / DMMA in gemm_dmma.cu).
+//
+// Model: one OS thread; the threads of ONE CTA are ucontext fibers that run round-robin and switch only at synchronisation points
+// (__syncthreads, __syncwarp, warp shuffles).  CTAs of a grid run one after the other, so `__shared__` can be a plain static and
+// atomics are trivially atomic.  Threads that have returned count as arrived at every later barrier (CUDA semantics).  A round in
+// which no fiber makes progress aborts with a message (deadlock = a barrier some thread never reaches).
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <functional>
+#include <vector>
+
+#define __CUDACC__ 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __constant__ static
+#define __align__(n) __attribute__((aligned(n)))
+#ifndef __restrict__
+#define __restrict__ __restrict
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// vector types
+// ---------------------------------------------------------------------------------------------
+struct uint3
+{
+    unsigned int x, y, z;
+};
+struct dim3
+{
+    unsigned int x, y, z;
+    dim3(unsigned int x_ = 1, unsigned int y_ = 1, unsigned int z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct alignas(16) double2
+{
+    double x, y;
+};
+struct alignas(16) int4
+{
+    int x, y, z, w;
+};
+struct alignas(8) int2
+{
+    int x, y;
+};
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
+
+namespace emu {
+
+struct Warp
+{
+    uint32_t live = 0;      // lanes that have not returned
+    uint32_t mask = 0;      // mask of the collective in progress
+    int gen = 0;            // completed collectives
+    int arrived = 0;
+    uint64_t buf[2][32];
+};
+
+struct State
+{
+    // current thread / CTA
+    uint3 tid{0, 0, 0}, bid{0, 0, 0};
+    dim3 bdim, gdim;
+    // CTA barrier
+    int live = 0, bar_count = 0, bar_gen = 0;
+    std::vector<Warp> warps;
+    unsigned char* dyn_smem = nullptr;
+    // fibers
+    ucontext_t main_ctx;
+    std::vector<ucontext_t> ctx;
+    std::vector<char*> stacks;
+    std::vector<char> done;
+    int cur = -1;
+    uint64_t progress = 0;
+    const std::function<void()>* body = nullptr;
+    int64_t launches = 0;
+};
+inline State g;
+
+constexpr size_t kStackBytes = 256 * 1024;
+
+inline void yield_to_main() { swapcontext(&g.ctx[(size_t) g.cur], &g.main_ctx); }
+
+inline void warp_try_release(Warp& w)
+{
+    if (w.arrived > 0 && w.arrived == __builtin_popcount(w.mask & w.live))
+    {
+        w.arrived = 0;
+        w.gen++;
+        g.progress++;
+    }
+}
+
+inline void cta_try_release()
+{
+    if (g.bar_count > 0 && g.bar_count >= g.live)
+    {
+        g.bar_count = 0;
+        g.bar_gen++;
+        g.progress++;
+    }
+}
+
+inline void fiber_entry()
+{
+    (*g.body)();
+    // thread exit: counts as arrived everywhere from now on
+    const int t = g.cur;
+    g.done[(size_t) t] = 1;
+    g.live--;
+    Warp& w = g.warps[(size_t) t / 32];
+    w.live &= ~(1u << (t & 31));
+    g.progress++;
+    warp_try_release(w);
+    cta_try_release();
+    swapcontext(&g.ctx[(size_t) t], &g.main_ctx);
+}
+
+inline void syncthreads()
+{
+    const int my = g.bar_gen;
+    g.bar_count++;
+    g.progress++;
+    cta_try_release();
+    while (g.bar_gen == my)
+        yield_to_main();
+}
+
+// all lanes in (mask & live) deposit `bits`; returns the generation the values were written in
+inline int warp_collective(uint32_t mask, uint64_t bits)
+{
+    const int t = g.cur, lane = t & 31;
+    Warp& w = g.warps[(size_t) t / 32];
+    const int my = w.gen;
+    w.buf[my & 1][lane] = bits;
+    w.mask = mask;
+    w.arrived++;
+    g.progress++;
+    warp_try_release(w);
+    while (w.gen == my)
+        yield_to_main();
+    return my;
+}
+
+template <typename T>
+inline uint64_t to_bits(T v)
+{
+    static_assert(sizeof(T) <= 8, "shuffle of a type wider than 64 bits");
+    uint64_t b = 0;
+    memcpy(&b, &v, sizeof(T));
+    return b;
+}
+template <typename T>
+inline T from_bits(uint64_t b)
+{
+    T v;
+    memcpy(&v, &b, sizeof(T));
+    return v;
+}
+
+template <typename T>
+inline T shfl_from(uint32_t mask, T v, int src_lane)
+{
+    const int my = warp_collective(mask, to_bits(v));
+    const Warp& w = g.warps[(size_t) g.cur / 32];
+    return from_bits<T>(w.buf[my & 1][src_lane & 31]);
+}
+
+struct Launch
+{
+    dim3 grid, block;
+    size_t smem;
+};
+
+inline void run_cta(const std::function<void()>& body, const Launch& L)
+{
+    const int nthreads = (int) (L.block.x * L.block.y * L.block.z);
+    g.bdim = L.block;
+    g.gdim = L.grid;
+    g.live = nthreads;
+    g.bar_count = 0;
+    g.bar_gen = 0;
+    g.warps.assign((size_t) (nthreads + 31) / 32, Warp());
+    for (int t = 0; t < nthreads; t++)
+        g.warps[(size_t) t / 32].live |= 1u << (t & 31);
+    if ((int) g.ctx.size() < nthreads)
+    {
+        g.ctx.resize((size_t) nthreads);
+        while ((int) g.stacks.size() < nthreads)
+            g.stacks.push_back((char*) malloc(kStackBytes));
+    }
+    g.done.assign((size_t) nthreads, 0);
+    g.body = &body;
+    for (int t = 0; t < nthreads; t++)
+    {
+        getcontext(&g.ctx[(size_t) t]);
+        g.ctx[(size_t) t].uc_stack.ss_sp = g.stacks[(size_t) t];
+        g.ctx[(size_t) t].uc_stack.ss_size = kStackBytes;
+        g.ctx[(size_t) t].uc_link = &g.main_ctx;
+        makecontext(&g.ctx[(size_t) t], (void (*)()) fiber_entry, 0);
+    }
+    int remaining = nthreads;
+    while (remaining > 0)
+    {
+        const uint64_t before = g.progress;
+        remaining = 0;
+        for (int t = 0; t < nthreads; t++)
+        {
+            if (g.done[(size_t) t])
+                continue;
+            g.cur = t;
+            g.tid.x = (unsigned) t % L.block.x;
+            g.tid.y = ((unsigned) t / L.block.x) % L.block.y;
+            g.tid.z = (unsigned) t / (L.block.x * L.block.y);
+            swapcontext(&g.main_ctx, &g.ctx[(size_t) t]);
+            if (!g.done[(size_t) t])
+                remaining++;
+        }
+        if (remaining > 0 && g.progress == before)
+        {
+            fprintf(stderr, "cuda_emu: deadlock in CTA (%u,%u,%u): %d threads wait at a barrier/shuffle nobody else reaches\n", g.bid.x, g.bid.y, g.bid.z, remaining);
+            abort();
+        }
+    }
+    g.cur = -1;
+}
+
+inline void launch_impl(const Launch& L, const std::function<void()>& body)
+{
+    g.launches++;
+    std::vector<unsigned char> smem(L.smem + 128);
+    unsigned char* sp = smem.data();
+    sp += (128 - ((uintptr_t) sp & 127)) & 127;
+    g.dyn_smem = sp;
+    for (unsigned bz = 0; bz < L.grid.z; bz++)
+        for (unsigned by = 0; by < L.grid.y; by++)
+            for (unsigned bx = 0; bx < L.grid.x; bx++)
+            {
+                g.bid = uint3{bx, by, bz};
+                run_cta(body, L);
+            }
+    g.dyn_smem = nullptr;
+}
+
+template <typename F>
+inline void launch(dim3 grid, dim3 block, F&& f)
+{
+    launch_impl(Launch{grid, block, 0}, std::function<void()>(f));
+}
+template <typename F>
+inline void launch(dim3 grid, dim3 block, size_t smem, F&& f)
+{
+    launch_impl(Launch{grid, block, smem}, std::function<void()>(f));
+}
+template <typename S, typename F>
+inline void launch(dim3 grid, dim3 block, size_t smem, S /*stream*/, F&& f)
+{
+    launch_impl(Launch{grid, block, smem}, std::function<void()>(f));
+}
+
+}  // namespace emu
+
+#define threadIdx (::emu::g.tid)
+#define blockIdx (::emu::g.bid)
+#define blockDim (::emu::g.bdim)
+#define gridDim (::emu::g.gdim)
+
+// ---------------------------------------------------------------------------------------------
+// device builtins
+// ---------------------------------------------------------------------------------------------
+inline void __syncthreads() { ::emu::syncthreads(); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) { ::emu::warp_collective(mask, 0); }
+inline void __threadfence() {}
+inline void __threadfence_block() {}
+
+template <typename T>
+inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)
+{
+    const int lane = ::emu::g.cur & 31;
+    const int base = lane & ~(width - 1);
+    return ::emu::shfl_from<T>(mask, v, base + (src & (width - 1)));
+}
+template <typename T>
+inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask, int width = 32)
+{
+    const int lane = ::emu::g.cur & 31;
+    const int src = lane ^ lane_mask;
+    const int base = lane & ~(width - 1);
+    // a source outside the lane's own segment returns the lane's own value
+    const T r = ::emu::shfl_from<T>(mask, v, (src >= base && src < base + width) ? src : lane);
+    return r;
+}
+template <typename T>
+inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32)
+{
+    const int lane = ::emu::g.cur & 31;
+    const int base = lane & ~(width - 1);
+    const int src = lane - (int) delta;
+    return ::emu::shfl_from<T>(mask, v, src >= base ? src : lane);
+}
+template <typename T>
+inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32)
+{
+    const int lane = ::emu::g.cur & 31;
+    const int base = lane & ~(width - 1);
+    const int src = lane + (int) delta;
+    return ::emu::shfl_from<T>(mask, v, src < base + width ? src : lane);
+}
+
+template <typename T>
+inline T __ldg(const T* p)
+{
+    return *p;
+}
+inline unsigned int __umulhi(unsigned int a, unsigned int b) { return (unsigned int) (((uint64_t) a * (uint64_t) b) >> 32); }
+inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+// CUDA's global min / max overloads
+#define EMU_MINMAX(T)                               \
+    inline T min(T a, T b) { return b < a ? b : a; } \
+    inline T max(T a, T b) { return a < b ? b : a; }
+EMU_MINMAX(int)
+EMU_MINMAX(unsigned int)
+EMU_MINMAX(long)
+EMU_MINMAX(unsigned long)
+EMU_MINMAX(long long)
+EMU_MINMAX(unsigned long long)
+EMU_MINMAX(float)
+EMU_MINMAX(double)
+#undef EMU_MINMAX
+inline int __popc(unsigned int x) { return __builtin_popcount(x); }
+
+template <typename T>
+inline T atomicAdd(T* p, T v)
+{
+    const T old = *p;
+    *p = old + v;
+    return old;
+}
+inline unsigned int atomicAdd(unsigned int* p, int v) { return atomicAdd<unsigned int>(p, (unsigned int) v); }
+template <typename T>
+inline T atomicMax(T* p, T v)
+{
+    const T old = *p;
+    if (v > old)
+        *p = v;
+    return old;
+}
+
+// ---------------------------------------------------------------------------------------------
+// runtime API subset (synchronous; "device memory" is host memory filled with 0xFF = NaN doubles / -1 ints)
+// ---------------------------------------------------------------------------------------------
+typedef int cudaError_t;
+constexpr cudaError_t cudaSuccess = 0;
+constexpr cudaError_t cudaErrorMemoryAllocation = 2;
+struct CUstream_st
+{
+    int dummy;
+};
+typedef CUstream_st* cudaStream_t;
+struct CUevent_st
+{
+    std::chrono::steady_clock::time_point t;
+};
+typedef CUevent_st* cudaEvent_t;
+enum cudaMemcpyKind
+{
+    cudaMemcpyHostToHost = 0,
+    cudaMemcpyHostToDevice = 1,
+    cudaMemcpyDeviceToHost = 2,
+    cudaMemcpyDeviceToDevice = 3,
+    cudaMemcpyDefault = 4
+};
+constexpr unsigned int cudaStreamNonBlocking = 1;
+constexpr unsigned int cudaEventDisableTiming = 2;
+enum cudaFuncAttribute
+{
+    cudaFuncAttributeMaxDynamicSharedMemorySize = 8
+};
+struct cudaDeviceProp
+{
+    char name[256];
+    int multiProcessorCount, major, minor, l2CacheSize;
+    size_t totalGlobalMem;
+};
+
+inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "cuda_emu error"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n)
+{
+    *n = 1;
+    return cudaSuccess;
+}
+inline cudaError_t cudaGetDevice(int* d)
+{
+    *d = 0;
+    return cudaSuccess;
+}
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int)
+{
+    memset(p, 0, sizeof(*p));
+    strcpy(p->name, "cuda_emu (CPU, test infrastructure)");
+    const char* e = getenv("CUDA_EMU_SMS");
+    p->multiProcessorCount = e ? atoi(e) : 2;
+    p->major = 10;
+    p->minor = 0;
+    p->l2CacheSize = 126 << 20;
+    p->totalGlobalMem = (size_t) 8 << 30;
+    return cudaSuccess;
+}
+template <typename T>
+inline cudaError_t cudaMalloc(T** p, size_t bytes)
+{
+    void* q = malloc(bytes ? bytes : 1);
+    if (!q)
+        return cudaErrorMemoryAllocation;
+    memset(q, 0xFF, bytes);
+    *p = (T*) q;
+    return cudaSuccess;
+}
+inline cudaError_t cudaFree(void* p)
+{
+    free(p);
+    return cudaSuccess;
+}
+template <typename T>
+inline cudaError_t cudaMallocHost(T** p, size_t bytes)
+{
+    *p = (T*) malloc(bytes ? bytes : 1);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+inline cudaError_t cudaFreeHost(void* p)
+{
+    free(p);
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind)
+{
+    memmove(d, s, n);
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t = nullptr) { return cudaMemcpy(d, s, n, k); }
+inline cudaError_t cudaMemcpy2D(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind)
+{
+    for (size_t r = 0; r < h; r++)
+        memmove((char*) d + r * dp, (const char*) s + r * sp, w);
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind k, cudaStream_t = nullptr)
+{
+    return cudaMemcpy2D(d, dp, s, sp, w, h, k);
+}
+inline cudaError_t cudaMemset(void* p, int v, size_t n)
+{
+    memset(p, v, n);
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t = nullptr) { return cudaMemset(p, v, n); }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned int)
+{
+    *s = new CUstream_st{0};
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamDestroy(cudaStream_t s)
+{
+    delete s;
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e)
+{
+    *e = new CUevent_st{std::chrono::steady_clock::now()};
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned int) { return cudaEventCreate(e); }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e)
+{
+    delete e;
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr)
+{
+    e->t = std::chrono::steady_clock::now();
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
+{
+    *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned int = 0) { return cudaSuccess; }
+template <typename F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int)
+{
+    return cudaSuccess;
+}

@@ -1,0 +1,140 @@
+"""Builds tests/_emu/libspectra_b200_emu.so: the library's CUDA sources compiled for the CPU against tools/cuda_emu/cuda_emu.h.
+
+TEST INFRASTRUCTURE ONLY (see cuda_emu.h).  The sources are the product's own .cu files, rewritten textually in two places that
+are not C++:  `kernel<<<grid, block[, smem[, stream]]>>>(args)`  ->  `::emu::launch(grid, block[, smem[, stream]], [&]() { kernel(args); })`
+and  `extern __shared__ T name[];`  ->  `T* name = reinterpret_cast<T*>(::emu::g.dyn_smem);`.
+gemm_dmma.cu (TMA / mbarrier / DMMA in PTX) cannot be emulated; its entry point is replaced by the FMA restart GEMM of panel.cu.
+
+    python tools/cuda_emu/emu_build.py [--force]
+"""
+from __future__ import annotations
+
+import os
+import re
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "spectra_b200", "csrc")
+OUT = os.path.join(ROOT, "tests", "_emu")
+SRC_OUT = os.path.join(OUT, "src")
+LIB = os.path.join(OUT, "libspectra_b200_emu.so")
+SKIP = {"gemm_dmma.cu"}
+CXX = os.environ.get("CXX", "g++")
+CXXFLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-DSB200_EMU", "-w", f"-I{HERE}", f"-I{CSRC}"]
+
+STUBS = r'''
+// emulation stub for gemm_dmma.cu (PTX kernels cannot run under cuda_emu): the FMA restart GEMM of panel.cu stands in
+#include "kernels.h"
+namespace sb200 {
+void launch_compress_dmma(const double* V, int64_t ldv, int64_t nrows, int m, const double* Q, int kk, double* Vout, int64_t ldo, double* f, const double* H,
+                          double* red_out, const RedScratch& rs, cudaStream_t stream)
+{
+    launch_compress_fma(V, ldv, nrows, m, Q, kk, Vout, ldo, f, H, red_out, rs, stream);
+}
+}  // namespace sb200
+'''
+
+
+def _match_back_angle(s: str, i: int) -> int:
+    """s[i] == '>': index of the matching '<' (balanced), scanning backwards."""
+    depth = 0
+    while i >= 0:
+        if s[i] == ">":
+            depth += 1
+        elif s[i] == "<":
+            depth -= 1
+            if depth == 0:
+                return i
+        i -= 1
+    raise ValueError("unbalanced template brackets before <<<")
+
+
+def _match_paren(s: str, i: int) -> int:
+    """s[i] == '(': index of the matching ')'."""
+    depth = 0
+    while i < len(s):
+        if s[i] == "(":
+            depth += 1
+        elif s[i] == ")":
+            depth -= 1
+            if depth == 0:
+                return i
+        i += 1
+    raise ValueError("unbalanced parentheses after >>>")
+
+
+def rewrite_launches(s: str) -> str:
+    out = []
+    pos = 0
+    while True:
+        k = s.find("<<<", pos)
+        if k < 0:
+            out.append(s[pos:])
+            break
+        # kernel expression before <<<
+        j = k - 1
+        while s[j].isspace():
+            j -= 1
+        if s[j] == ">":
+            j = _match_back_angle(s, j) - 1
+        while j >= 0 and (s[j].isalnum() or s[j] in "_:"):
+            j -= 1
+        kern = s[j + 1:k].strip()
+        e = s.find(">>>", k)
+        cfg = s[k + 3:e].strip()
+        a0 = e + 3
+        while s[a0].isspace() or s[a0] == "\\":
+            a0 += 1
+        assert s[a0] == "(", f"expected '(' after >>> near: {s[k - 40:k + 80]!r}"
+        a1 = _match_paren(s, a0)
+        args = s[a0 + 1:a1]
+        out.append(s[pos:j + 1])
+        out.append(f"::emu::launch({cfg}, [&]() {{ {kern}({args}); }})")
+        pos = a1 + 1
+    return "".join(out)
+
+
+_EXT_SH = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w:]+(?:\s+[\w:]+)*?)\s+(\w+)\s*\[\s*\]\s*;")
+
+
+def rewrite(s: str) -> str:
+    s = _EXT_SH.sub(lambda m: f"{m.group(1)}* {m.group(2)} = reinterpret_cast<{m.group(1)}*>(::emu::g.dyn_smem);", s)
+    return rewrite_launches(s)
+
+
+def _compile(name: str, text: str, force: bool) -> str:
+    src = os.path.join(SRC_OUT, name + ".cpp")
+    obj = os.path.join(SRC_OUT, name + ".o")
+    old = open(src).read() if os.path.exists(src) else None
+    if old != text:
+        with open(src, "w") as f:
+            f.write(text)
+    deps = [src, os.path.join(HERE, "cuda_emu.h")] + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".h", ".cuh"))]
+    deps.append(os.path.join(ROOT, "include", "spectra_b200.h"))
+    if force or old != text or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(d) for d in deps):
+        r = subprocess.run([CXX, *CXXFLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"emu compile failed for {name}:\n{r.stderr[:6000]}")
+    return obj
+
+
+def build(force: bool = False) -> str:
+    os.makedirs(SRC_OUT, exist_ok=True)
+    jobs = [("emu_stubs", STUBS)]
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith(".cu") and f not in SKIP:
+            jobs.append((f[:-3], f'#line 1 "{os.path.join(CSRC, f)}"\n' + rewrite(open(os.path.join(CSRC, f)).read())))
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(lambda j: _compile(j[0], j[1], force), jobs))
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+        r = subprocess.run([CXX, "-shared", "-o", LIB, *objs, "-ldl", "-lpthread"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"emu link failed:\n{r.stderr[:4000]}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))
