@@ -69,7 +69,9 @@ typedef enum
 {
     SB200_GENERAL = 0,   /* SparseGenMatProd: every stored entry is used          (SparseGenMatProd.h:82-87) */
     SB200_SYM_LOWER = 1, /* SparseSymMatProd<.., Eigen::Lower>: selfadjointView   (SparseSymMatProd.h:83-88) */
-    SB200_SYM_UPPER = 2  /* SparseSymMatProd<.., Eigen::Upper> */
+    SB200_SYM_UPPER = 2, /* SparseSymMatProd<.., Eigen::Upper> */
+    SB200_HERM_LOWER = 3, /* SparseHermMatProd<std::complex<double>, Eigen::Lower> (SparseHermMatProd.h:83-88); complex operators only */
+    SB200_HERM_UPPER = 4  /* SparseHermMatProd<std::complex<double>, Eigen::Upper> */
 } sb200_matrix_mode;
 
 typedef struct sb200_comm sb200_comm;
@@ -115,6 +117,14 @@ int sb200_op_create_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64
  * the product back.  Single-GPU only. */
 typedef void (*sb200_matvec_fn)(const double* x_in, double* y_out, void* user);
 int sb200_op_create_callback(int64_t n, sb200_matvec_fn fn, void* user, sb200_op** out);
+/* Complex Hermitian operator: replaces MatOp/SparseHermMatProd.h:21-89 (Scalar = std::complex<double>).  values_ri holds the
+ * nnz complex values interleaved (re, im) -- the memory layout of std::complex<double> --, matrix_mode is SB200_HERM_LOWER /
+ * SB200_HERM_UPPER (the Uplo template argument: only that triangle is read, mirrored conjugated, the diagonal taken as real) or
+ * SB200_GENERAL.  Every vector the operator or its solver exchanges is interleaved complex too: perform_op / apply_matrix take
+ * and return 2 n doubles per column.  Single GPU.  (experimental in round 1: verified on the kernel-logic
+ * emulator, not yet on a device.) */
+int sb200_op_create_sparse_herm(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values_ri, int storage_order, int matrix_mode,
+                                sb200_op** out);
 /* Shift-solve operator: replaces MatOp/SparseSymShiftSolve.h:30-110.  Same matrix arguments as sb200_op_create_sparse
  * (matrix_mode SB200_SYM_LOWER / SB200_SYM_UPPER = the Uplo template argument).  perform_op then computes
  * y = (A - sigma I)^{-1} x.  Device implementation: block cyclic reduction on the block-tridiagonal form, which needs a
@@ -164,6 +174,10 @@ int sb200_sym_create(sb200_op* op, int64_t nev, int64_t ncv, sb200_sym_solver** 
  * operator (a callback operator must already apply (A - sigma I)^{-1}); eigenvalues are mapped back by
  * lambda = 1/nu + sigma before sorting (:163-169).  All other calls are the sb200_sym_* functions. */
 int sb200_sym_create_shift(sb200_op* op, int64_t nev, int64_t ncv, double sigma, sb200_sym_solver** out);
+/* HermEigsSolver(op, nev, ncv) (HermEigsSolver.h:121-122 + HermEigsBase.h with a complex Scalar) on an operator made by
+ * sb200_op_create_sparse_herm; ncv <= 63.  The handle is used with the sb200_sym_* calls: eigenvalues are real, init() takes and
+ * eigenvectors() returns interleaved complex data (2 n doubles per vector / column). */
+int sb200_herm_create(sb200_op* op, int64_t nev, int64_t ncv, sb200_sym_solver** out);
 int sb200_sym_init(sb200_sym_solver* s, const double* init_resid_or_null);                  /* init(), init(const Scalar*) :309-342 */
 int sb200_sym_compute(sb200_sym_solver* s, int selection, int64_t maxit, double tol, int sorting, int64_t* nconv); /* compute() :366-390 */
 int sb200_sym_info(const sb200_sym_solver* s, int* info);                                   /* info() :396 */

@@ -21,7 +21,7 @@ import os
 import numpy as np
 
 __all__ = [
-    "SortRule", "CompInfo", "SparseSymMatProd", "SparseGenMatProd", "UserOp", "SymEigsSolver", "GenEigsSolver", "Comm", "Stats", "lib", "lib_path", "device_info",
+    "SortRule", "CompInfo", "SparseSymMatProd", "SparseGenMatProd", "SparseHermMatProd", "UserOp", "SymEigsSolver", "HermEigsSolver", "GenEigsSolver", "Comm", "Stats", "lib", "lib_path", "device_info",
     "set_profiling", "set_device", "dense",
 ]
 
@@ -392,6 +392,82 @@ class SparseGenMatProd(_SparseOp):
         super().__init__(mat, comm=comm)
 
 
+class SparseHermMatProd:
+    """MatOp/SparseHermMatProd.h with Scalar = std::complex<double>: y = A.selfadjointView<Uplo>() * x for a complex sparse
+    matrix of which only one triangle is read (mirrored conjugated; the diagonal is taken as real).  `mat` is a complex
+    scipy.sparse CSC/CSR matrix or a tuple (n, outer, inner, values[complex128], 'col'|'row').  Vectors are complex128.
+    Experimental in round 1: verified on the kernel-logic emulator, not yet on a device."""
+
+    def __init__(self, mat, uplo: str = "lower"):
+        if isinstance(mat, tuple):
+            n, outer, inner, vals, order = mat
+        else:
+            import scipy.sparse as sp
+
+            if sp.isspmatrix_csr(mat):
+                order = "row"
+            else:
+                mat = sp.csc_matrix(mat)
+                order = "col"
+            if mat.shape[0] != mat.shape[1]:
+                raise InvalidArgument(1, "matrix must be square")
+            mat.sort_indices()
+            n, outer, inner, vals = mat.shape[0], mat.indptr, mat.indices, mat.data
+        outer = np.ascontiguousarray(outer)
+        if outer.dtype not in (np.int32, np.int64):
+            outer = outer.astype(np.int64)
+        inner = np.ascontiguousarray(inner, dtype=np.int32)
+        vals = np.ascontiguousarray(vals, dtype=np.complex128)
+        self.n = int(n)
+        self._keep = (outer, inner, vals)
+        self._order = order
+        self.comm = None
+        self.row0, self.nrows_local = 0, self.n
+        mode = {"lower": 3, "upper": 4, "general": 0}[uplo]
+        self.h = C.c_void_p()
+        _check(lib().sb200_op_create_sparse_herm(C.c_int64(self.n), _p(outer), 1 if outer.dtype == np.int64 else 0, _p(inner), _p(vals),
+                                                 0 if order == "col" else 1, mode, C.byref(self.h)))
+
+    def rows(self):
+        return self.n
+
+    def cols(self):
+        return self.n
+
+    @property
+    def nnz(self):
+        v = C.c_int64()
+        _check(lib().sb200_op_nnz(self.h, C.byref(v)))
+        return v.value
+
+    def perform_op(self, x_in: np.ndarray, y_out: np.ndarray | None = None) -> np.ndarray:
+        x = np.ascontiguousarray(x_in, dtype=np.complex128)
+        if x.shape != (self.n,):
+            raise InvalidArgument(1, "x has the wrong length")
+        y = y_out if y_out is not None else np.empty(self.n, dtype=np.complex128)
+        _check(lib().sb200_op_perform_op(self.h, _p(x), _p(y)))
+        return y
+
+    def __matmul__(self, X):
+        X = np.asfortranarray(X, dtype=np.complex128)
+        if X.ndim == 1:
+            return self.perform_op(X)
+        Y = np.empty((self.n, X.shape[1]), dtype=np.complex128, order="F")
+        _check(lib().sb200_op_apply_matrix(self.h, _p(X), C.c_int64(X.shape[1]), _p(Y)))
+        return Y
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sb200_op_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class SparseSymShiftSolve(_SparseOp):
     """MatOp/SparseSymShiftSolve.h — perform_op computes y = (A - sigma I)^{-1} x after set_shift(sigma).  Device
     implementation: block cyclic reduction, banded matrices (half-bandwidth <= 32) only."""
@@ -501,6 +577,35 @@ class SymEigsSolver:
             self.close()
         except Exception:
             pass
+
+
+class HermEigsSolver(SymEigsSolver):
+    """HermEigsSolver.h:121-122 (HermEigsBase with a complex Scalar) on a SparseHermMatProd: real eigenvalues, complex vectors."""
+
+    def _create(self, op, nev, ncv):
+        _check(lib().sb200_herm_create(op.h, C.c_int64(nev), C.c_int64(ncv), C.byref(self.h)))
+
+    def init(self, init_resid: np.ndarray | None = None):
+        r = np.ascontiguousarray(init_resid, dtype=np.complex128) if init_resid is not None else None
+        if r is not None and r.shape != (self.op.n,):
+            raise InvalidArgument(1, "init_resid has the wrong length")
+        _check(lib().sb200_sym_init(self.h, _p(r)))
+
+    def eigenvectors(self, nvec: int | None = None) -> np.ndarray:
+        nvec = self.nev if nvec is None else int(nvec)
+        out = np.empty((self.op.n, max(nvec, 1)), dtype=np.complex128, order="F")
+        cnt = C.c_int64()
+        _check(lib().sb200_sym_eigenvectors(self.h, C.c_int64(nvec), _p(out), C.byref(cnt)))
+        return out[:, :cnt.value]
+
+    def factorization(self):
+        n, m = self.op.n, min(self.ncv, self.op.n)
+        V = np.empty((n, m), dtype=np.complex128, order="F")
+        H = np.empty((m, m), order="F")
+        f = np.empty(n, dtype=np.complex128)
+        beta, k = C.c_double(), C.c_int64()
+        _check(lib().sb200_sym_get_factorization(self.h, _p(V), _p(H), _p(f), C.byref(beta), C.byref(k)))
+        return dict(V=V, H=H, f=f, beta=beta.value, k=k.value)
 
 
 class SymEigsShiftSolver(SymEigsSolver):

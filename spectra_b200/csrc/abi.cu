@@ -15,6 +15,7 @@ void op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev);
 sb200_op* op_create_callback(int64_t n, void (*fn)(const double*, double*, void*), void* user);
 sb200_op* op_create_shift_solve(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values, int storage_order, int matrix_mode);
 void op_perform_op_host(sb200_op* op, const double* x_host, double* y_host);
+sb200_op* op_create_sparse_herm(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values_ri, int storage_order, int matrix_mode);
 float bench_gather(int64_t n, int64_t gathers, int repeat, double* checksum);
 
 sb200_sym_solver* sym_create(sb200_op* op, int64_t nev, int64_t ncv, bool shift_mode, double sigma);
@@ -168,6 +169,15 @@ int sb200_op_create_sparse(int64_t n, const void* outer, int outer_is_64, const 
     *out = op_create_sparse(n, outer, outer_is_64, inner, values, storage_order, matrix_mode, (comm && comm->nranks > 1) ? comm : nullptr);
     ABI_CATCH
 }
+int sb200_op_create_sparse_herm(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values_ri, int storage_order, int matrix_mode,
+                                sb200_op** out)
+{
+    ABI_TRY
+    ABI_NONNULL(out);
+    ABI_NONNULL(outer);
+    *out = op_create_sparse_herm(n, outer, outer_is_64, inner, values_ri, storage_order, matrix_mode);
+    ABI_CATCH
+}
 int sb200_op_create_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64_t* rowptr_local, const int32_t* col, const double* values, sb200_comm* comm,
                              sb200_op** out)
 {
@@ -289,8 +299,9 @@ int sb200_op_apply_matrix(sb200_op* op, const double* X_host, int64_t k, double*
     ABI_NONNULL(op);
     ABI_NONNULL(X_host);
     ABI_NONNULL(Y_host);
+    const int cw = op->cplx ? 2 : 1;  // complex operators: interleaved (re, im) columns
     for (int64_t c = 0; c < k; c++)
-        op_perform_op_host(op, X_host + c * op->A.n, Y_host + c * op->A.nrows);
+        op_perform_op_host(op, X_host + c * op->A.n * cw, Y_host + c * op->A.nrows * cw);
     ABI_CATCH
 }
 int sb200_op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev, int repeat, float* elapsed_ms)
@@ -335,6 +346,17 @@ int sb200_sym_create(sb200_op* op, int64_t nev, int64_t ncv, sb200_sym_solver** 
 {
     ABI_TRY
     ABI_NONNULL(out);
+    ABI_NONNULL(op);
+    SB200_REQUIRE(!op->cplx, SB200_INVALID_ARGUMENT, "SymEigsSolver needs a real operator; use sb200_herm_create for a complex Hermitian one");
+    *out = sym_create(op, nev, ncv, false, 0.0);
+    ABI_CATCH
+}
+int sb200_herm_create(sb200_op* op, int64_t nev, int64_t ncv, sb200_sym_solver** out)
+{
+    ABI_TRY
+    ABI_NONNULL(out);
+    ABI_NONNULL(op);
+    SB200_REQUIRE(op->cplx, SB200_INVALID_ARGUMENT, "HermEigsSolver needs a complex Hermitian operator (sb200_op_create_sparse_herm)");
     *out = sym_create(op, nev, ncv, false, 0.0);
     ABI_CATCH
 }

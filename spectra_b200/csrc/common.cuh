@@ -250,6 +250,7 @@ __device__ __forceinline__ void ld_stream_f64x4(const double* p, double (&v)[4])
         v[q] = p[q];
 }
 __device__ __forceinline__ double ld_keep_f64(const double* p, uint64_t) { return *p; }
+__device__ __forceinline__ double2 ld_keep_f64x2(const double* p, uint64_t) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ double ld_cg_f64(const double* p) { return *p; }
 #else
 // L2 cache policies (createpolicy): streamed-once data is marked evict_first so that the gathered
@@ -306,6 +307,13 @@ __device__ __forceinline__ double ld_keep_f64(const double* p, uint64_t pol)
     (void) pol;
     v = __ldg(p);
 #endif
+    return v;
+}
+// 16-byte gather (one complex operand entry), kept in L2
+__device__ __forceinline__ double2 ld_keep_f64x2(const double* p, uint64_t pol)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
     return v;
 }
 // L2-coherent load (skips the non-coherent L1) for data written by other CTAs of the same kernel.

@@ -36,7 +36,7 @@ __global__ void count_kernel(const OuterT* __restrict__ outer, const int* __rest
             }
             else
             {
-                const bool used = (mode == SB200_SYM_LOWER) ? (i >= j) : (i <= j);
+                const bool used = (mode == SB200_SYM_LOWER || mode == SB200_HERM_LOWER) ? (i >= j) : (i <= j);
                 if (!used)
                     continue;
                 if (i >= row0 && i < row0 + nrows)
@@ -48,10 +48,20 @@ __global__ void count_kernel(const OuterT* __restrict__ outer, const int* __rest
     }
 }
 
-template <typename OuterT>
-__global__ void fill_kernel(const OuterT* __restrict__ outer, const int* __restrict__ inner, const double* __restrict__ values, int64_t n, int order, int mode,
-                            int64_t row0, int64_t nrows, const int* __restrict__ rowptr, int* __restrict__ cursor, int* __restrict__ col, double* __restrict__ val)
+// Value handling of the mirrored / diagonal entries: real symmetric entries are copied; Hermitian ones (complex values stored as
+// double2 = (re, im), selfadjointView<Uplo> of a complex matrix, MatOp/SparseHermMatProd.h:83-88) are conjugated when mirrored and
+// their diagonal is taken as real.
+__device__ __forceinline__ double mirror_value(double v, bool) { return v; }
+__device__ __forceinline__ double2 mirror_value(double2 v, bool herm) { return herm ? make_double2(v.x, -v.y) : v; }
+__device__ __forceinline__ double diag_value(double v, bool) { return v; }
+__device__ __forceinline__ double2 diag_value(double2 v, bool herm) { return herm ? make_double2(v.x, 0.0) : v; }
+
+template <typename OuterT, typename VT>
+__global__ void fill_kernel(const OuterT* __restrict__ outer, const int* __restrict__ inner, const VT* __restrict__ values, int64_t n, int order, int mode,
+                            int64_t row0, int64_t nrows, const int* __restrict__ rowptr, int* __restrict__ cursor, int* __restrict__ col, VT* __restrict__ val)
 {
+    const bool herm = (mode == SB200_HERM_LOWER || mode == SB200_HERM_UPPER);
+    const bool lower = (mode == SB200_SYM_LOWER || mode == SB200_HERM_LOWER);
     for (int64_t o = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t) gridDim.x * blockDim.x)
     {
         const int64_t pb = outer[o], pe = outer[o + 1];
@@ -60,13 +70,13 @@ __global__ void fill_kernel(const OuterT* __restrict__ outer, const int* __restr
             const int64_t in = inner[p];
             const int64_t i = (order == SB200_COL_MAJOR) ? in : o;
             const int64_t j = (order == SB200_COL_MAJOR) ? o : in;
-            const double v = values[p];
+            const VT v = values[p];
             bool put_ij = false, put_ji = false;
             if (mode == SB200_GENERAL)
                 put_ij = true;
             else
             {
-                const bool used = (mode == SB200_SYM_LOWER) ? (i >= j) : (i <= j);
+                const bool used = lower ? (i >= j) : (i <= j);
                 put_ij = used;
                 put_ji = used && (i != j);
             }
@@ -75,21 +85,22 @@ __global__ void fill_kernel(const OuterT* __restrict__ outer, const int* __restr
                 const int li = (int) (i - row0);
                 const int q = rowptr[li] + atomicAdd(cursor + li, 1);
                 col[q] = (int) j;
-                val[q] = v;
+                val[q] = (i == j && mode != SB200_GENERAL) ? diag_value(v, herm) : v;
             }
             if (put_ji && j >= row0 && j < row0 + nrows)
             {
                 const int lj = (int) (j - row0);
                 const int q = rowptr[lj] + atomicAdd(cursor + lj, 1);
                 col[q] = (int) i;
-                val[q] = v;
+                val[q] = mirror_value(v, herm);
             }
         }
     }
 }
 
 // Per-row insertion sort by column id (rows are short; long rows only appear in small test inputs).
-__global__ void sort_rows_kernel(const int* __restrict__ rowptr, int* __restrict__ col, double* __restrict__ val, int64_t nrows)
+template <typename VT>
+__global__ void sort_rows_kernel(const int* __restrict__ rowptr, int* __restrict__ col, VT* __restrict__ val, int64_t nrows)
 {
     for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t) gridDim.x * blockDim.x)
     {
@@ -97,7 +108,7 @@ __global__ void sort_rows_kernel(const int* __restrict__ rowptr, int* __restrict
         for (int p = b + 1; p < e; p++)
         {
             const int c = col[p];
-            const double v = val[p];
+            const VT v = val[p];
             int q = p - 1;
             while (q >= b && col[q] > c)
             {
@@ -215,25 +226,32 @@ int grid_for(int64_t n, int block)
     return (int) std::max<int64_t>(1, std::min<int64_t>(need, (int64_t) sms * 16));
 }
 
-template <typename OuterT>
-void build_impl(int64_t n, const OuterT* h_outer, const int32_t* h_inner, const double* h_values, int order, int mode, int64_t row0, int64_t nrows,
-                cudaStream_t stream, DeviceCsr& out)
+// Destination arrays of one build (real DeviceCsr or complex DeviceCsrZ)
+template <typename VT>
+struct CsrDest
+{
+    int64_t& nnz;
+    DevBuf<int>& rowptr;
+    DevBuf<int>& col;
+    DevBuf<VT>& val;
+};
+
+template <typename OuterT, typename VT>
+void build_impl(int64_t n, const OuterT* h_outer, const int32_t* h_inner, const VT* h_values, int order, int mode, int64_t row0, int64_t nrows,
+                cudaStream_t stream, CsrDest<VT> out)
 {
     const int64_t nnz_in = (int64_t) h_outer[n] - (int64_t) h_outer[0];
     SB200_REQUIRE(h_outer[0] == 0, SB200_INVALID_ARGUMENT, "sparse matrix must be in compressed form (outer[0] == 0)");
     DevBuf<OuterT> d_outer(n + 1);
     DevBuf<int> d_inner(std::max<int64_t>(nnz_in, 1));
-    DevBuf<double> d_values(std::max<int64_t>(nnz_in, 1));
+    DevBuf<VT> d_values(std::max<int64_t>(nnz_in, 1));
     SB200_CUDA_CHECK(cudaMemcpyAsync(d_outer.get(), h_outer, sizeof(OuterT) * (n + 1), cudaMemcpyHostToDevice, stream));
     if (nnz_in > 0)
     {
         SB200_CUDA_CHECK(cudaMemcpyAsync(d_inner.get(), h_inner, sizeof(int) * nnz_in, cudaMemcpyHostToDevice, stream));
-        SB200_CUDA_CHECK(cudaMemcpyAsync(d_values.get(), h_values, sizeof(double) * nnz_in, cudaMemcpyHostToDevice, stream));
+        SB200_CUDA_CHECK(cudaMemcpyAsync(d_values.get(), h_values, sizeof(VT) * nnz_in, cudaMemcpyHostToDevice, stream));
     }
 
-    out.n = n;
-    out.row0 = row0;
-    out.nrows = nrows;
     out.rowptr.alloc(nrows + 1);
     DevBuf<int> cnt(std::max<int64_t>(nrows, 1));
     cnt.zero(stream);
@@ -263,9 +281,9 @@ void build_impl(int64_t n, const OuterT* h_outer, const int32_t* h_inner, const 
     if (total > 0)
     {
         cnt.zero(stream);  // reuse as the per-row cursor
-        fill_kernel<OuterT><<<g, 256, 0, stream>>>(d_outer.get(), d_inner.get(), d_values.get(), n, order, mode, row0, nrows, out.rowptr.get(), cnt.get(),
-                                                   out.col.get(), out.val.get());
-        sort_rows_kernel<<<grid_for(nrows, 128), 128, 0, stream>>>(out.rowptr.get(), out.col.get(), out.val.get(), nrows);
+        fill_kernel<OuterT, VT><<<g, 256, 0, stream>>>(d_outer.get(), d_inner.get(), d_values.get(), n, order, mode, row0, nrows, out.rowptr.get(), cnt.get(),
+                                                       out.col.get(), out.val.get());
+        sort_rows_kernel<VT><<<grid_for(nrows, 128), 128, 0, stream>>>(out.rowptr.get(), out.col.get(), out.val.get(), nrows);
         SB200_CUDA_CHECK(cudaGetLastError());
     }
     SB200_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -280,10 +298,32 @@ void build_device_csr(int64_t n, const void* outer, bool outer64, const int32_t*
     SB200_REQUIRE(n < (1LL << 31), SB200_INVALID_ARGUMENT, "matrix order exceeds the int32 index range");
     SB200_REQUIRE(order == SB200_COL_MAJOR || order == SB200_ROW_MAJOR, SB200_INVALID_ARGUMENT, "bad storage order");
     SB200_REQUIRE(mode >= SB200_GENERAL && mode <= SB200_SYM_UPPER, SB200_INVALID_ARGUMENT, "bad matrix mode");
+    out.n = n;
+    out.row0 = row0;
+    out.nrows = nrows;
+    CsrDest<double> dest{out.nnz, out.rowptr, out.col, out.val};
     if (outer64)
-        build_impl<long long>(n, static_cast<const long long*>(outer), inner, values, order, mode, row0, nrows, stream, out);
+        build_impl<long long, double>(n, static_cast<const long long*>(outer), inner, values, order, mode, row0, nrows, stream, dest);
     else
-        build_impl<int>(n, static_cast<const int*>(outer), inner, values, order, mode, row0, nrows, stream, out);
+        build_impl<int, double>(n, static_cast<const int*>(outer), inner, values, order, mode, row0, nrows, stream, dest);
+}
+
+// Complex operand (interleaved (re, im) values): SB200_HERM_LOWER / SB200_HERM_UPPER read one triangle and mirror it conjugated
+// (selfadjointView<Uplo> of a complex matrix, MatOp/SparseHermMatProd.h:83-88); SB200_GENERAL keeps every stored entry.
+void build_device_csr_z(int64_t n, const void* outer, bool outer64, const int32_t* inner, const double* values_ri, int order, int mode, cudaStream_t stream,
+                        DeviceCsrZ& out)
+{
+    SB200_REQUIRE(n >= 1, SB200_INVALID_ARGUMENT, "matrix order must be positive");
+    SB200_REQUIRE(n < (1LL << 30), SB200_INVALID_ARGUMENT, "matrix order exceeds the index range of the complex operator");
+    SB200_REQUIRE(order == SB200_COL_MAJOR || order == SB200_ROW_MAJOR, SB200_INVALID_ARGUMENT, "bad storage order");
+    SB200_REQUIRE(mode == SB200_GENERAL || mode == SB200_HERM_LOWER || mode == SB200_HERM_UPPER, SB200_INVALID_ARGUMENT, "bad matrix mode for a complex operator");
+    out.n = n;
+    CsrDest<double2> dest{out.nnz, out.rowptr, out.col, out.val};
+    const double2* v2 = reinterpret_cast<const double2*>(values_ri);
+    if (outer64)
+        build_impl<long long, double2>(n, static_cast<const long long*>(outer), inner, v2, order, mode, 0, n, stream, dest);
+    else
+        build_impl<int, double2>(n, static_cast<const int*>(outer), inner, v2, order, mode, 0, n, stream, dest);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -59,7 +59,11 @@ void op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev);
 struct FacBase
 {
     sb200_op* op = nullptr;
+    // n / nloc / ld count DOUBLES: for a complex (Hermitian) operator every vector holds interleaved (re, im) pairs and is handled
+    // as a real vector of twice the length by every kernel except the operator itself and the panel passes (cw = 2).
     int64_t n = 0, nloc = 0, ld = 0;
+    int cw = 1;
+    bool is_cplx() const { return cw == 2; }
     int nev = 0, m = 0;
 
     DevBuf<double> V, f, w, t0, H, Q, S, X;
@@ -94,12 +98,14 @@ struct FacBase
     void alloc_common(sb200_op* op_, int64_t nev_, int64_t m_)
     {
         op = op_;
-        n = op->A.n;
-        nloc = op->A.nrows;
+        cw = op->cplx ? 2 : 1;
+        SB200_REQUIRE(cw == 1 || op->nranks() == 1, SB200_INVALID_ARGUMENT, "complex operators are single-GPU in this build");
+        n = op->A.n * cw;
+        nloc = op->A.nrows * cw;
         // leading dimension: multiple of 16 doubles (128 B) and at least the all-gather slab
         // (64-row tiles of the restart GEMM; chunked all-gathers read nchunks * chunk_len local entries)
         const int64_t chunk_rows = (op->A.chunk_len && op->nranks() > 1) ? op->A.chunk_len * (int64_t) op->A.blocks.size() : 0;
-        ld = round_up(std::max<int64_t>(std::max<int64_t>(std::max<int64_t>(nloc, op->slab), chunk_rows), 2), 64);
+        ld = round_up(std::max<int64_t>(std::max<int64_t>(std::max<int64_t>(nloc, op->slab * cw), chunk_rows), 2), 64);
         nev = (int) nev_;
         m = (int) m_;
         V.alloc((size_t) ld * m);
@@ -164,7 +170,7 @@ struct FacBase
             ScopedKernelTimer t(&prof, stream(), KC_PANEL);
             launch_vec_reduce(opk, x, y, nloc, slot, rs, stream());
         }
-        if (opk == VR_MAXABS)
+        if (opk == VR_MAXABS || opk == VR_CMAXABS)
             allreduce_max(slot, 1);
         else
             allreduce_sum(slot, 1);
@@ -260,7 +266,7 @@ struct FacBase
         stats.panel_cols += j;
         {
             ScopedKernelTimer t(&prof, stream(), KC_PANEL);
-            launch_panel_pass(mode, V.get(), ld, nloc, j, x, fo, coef, ctl.get()->red, rs, stream(), pred);
+            launch_panel_pass(mode, V.get(), ld, nloc, j, x, fo, coef, ctl.get()->red, rs, stream(), pred, is_cplx());
         }
         allreduce_sum(ctl.get()->red, kRedNrm + 1);
     }
@@ -273,12 +279,18 @@ struct FacBase
     // host copy of red[0..j) and red[kRedNrm]
     void fetch_red(int j, double& ortho_err, double& nrm2)
     {
-        SB200_CUDA_CHECK(cudaMemcpyAsync(hred.get(), ctl.get()->red, sizeof(double) * (kRedNrm + 1), cudaMemcpyDeviceToHost, stream()));
+        SB200_CUDA_CHECK(cudaMemcpyAsync(hred.get(), ctl.get()->red, sizeof(double) * (is_cplx() ? kRedStride : kRedNrm + 1), cudaMemcpyDeviceToHost, stream()));
         SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
         ortho_err = 0.0;
         for (int q = 0; q < j; q++)
-            ortho_err = std::max(ortho_err, std::fabs(hred.get()[q]));
+            ortho_err = std::max(ortho_err, is_cplx() ? std::hypot(hred.get()[q], hred.get()[kRedNrm + 1 + q]) : std::fabs(hred.get()[q]));
         nrm2 = hred.get()[kRedNrm];
+    }
+
+    // coefficients of the next correction pass <- result of the last panel reduction (complex: Re and Im halves, see panel.cu)
+    void copy_red_to_c(int i)
+    {
+        SB200_CUDA_CHECK(cudaMemcpyAsync(ctl.get()->c, ctl.get()->red, sizeof(double) * (is_cplx() ? kRedStride : i), cudaMemcpyDeviceToDevice, stream()));
     }
 
     // ---- Arnoldi::expand_basis (Arnoldi.h:66-115), V = first i columns ----
@@ -304,7 +316,7 @@ struct FacBase
             }
             // Vf = V^T f ; f -= V Vf ; fnorm ; Vf = V^T f   (:88-95) — the last three in one fused pass
             panel(PANEL_DOT, i, f.get(), nullptr, nullptr);
-            SB200_CUDA_CHECK(cudaMemcpyAsync(ctl.get()->c, ctl.get()->red, sizeof(double) * i, cudaMemcpyDeviceToDevice, stream()));
+            copy_red_to_c(i);
             panel(PANEL_CORR, i, f.get(), f.get(), ctl.get()->c);
             double ortho_err, nrm2;
             fetch_red(i, ortho_err, nrm2);
@@ -312,7 +324,7 @@ struct FacBase
             int count = 0;
             while (count < 3 && ortho_err >= kEps * fnorm)
             {
-                SB200_CUDA_CHECK(cudaMemcpyAsync(ctl.get()->c, ctl.get()->red, sizeof(double) * i, cudaMemcpyDeviceToDevice, stream()));
+                copy_red_to_c(i);
                 panel(PANEL_CORR, i, f.get(), f.get(), ctl.get()->c);
                 fetch_red(i, ortho_err, nrm2);
                 fnorm = std::sqrt(nrm2);
@@ -373,7 +385,7 @@ struct FacBase
         launch_set_scalar(H.get(), h00, stream());
         launch_vec_axpy(w.get(), v, h00, f.get(), nloc, stream());  // f = w - v * H(0,0)
         prof.launches += 2;
-        const double fmax = reduce_scalar(VR_MAXABS, f.get(), nullptr);
+        const double fmax = reduce_scalar(is_cplx() ? VR_CMAXABS : VR_MAXABS, f.get(), nullptr);  // m_fac_f.cwiseAbs().maxCoeff()
         if (fmax < kEps * std::fabs(h00))
         {
             f.zero(stream());

@@ -58,8 +58,12 @@ struct sb200_op
     sb200::PinnedBuf<double> hx, hy;  // pinned staging of the callback path
     // shift-solve operator: perform_op is y = (A - sigma I)^{-1} x instead of y = A x (A stays available for refinement)
     sb200::BandSolve* band = nullptr;
-    // true when perform_op is not the fused CSR SpMV (user callback or shift-solve): the solvers take the unfused step path
-    bool indirect() const { return cb != nullptr || band != nullptr; }
+    // complex Hermitian operator (SparseHermMatProd): the matrix lives in Az; A only carries n / nrows / nnz.
+    // Vectors are interleaved complex, i.e. 2 n doubles; single GPU.
+    bool cplx = false;
+    sb200::DeviceCsrZ Az;
+    // true when perform_op is not the fused CSR SpMV (user callback, shift-solve, complex operand): the solvers take the unfused step path
+    bool indirect() const { return cb != nullptr || band != nullptr || cplx; }
 
     int nranks() const { return comm ? comm->nranks : 1; }
     int rank() const { return comm ? comm->rank : 0; }

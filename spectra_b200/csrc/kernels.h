@@ -107,6 +107,19 @@ struct DeviceCsr
     int64_t chunk_stride() const { return (int64_t) chunk_ranks * chunk_len; }
     const double* x_of_block(const double* x, int c) const { return chunk_len ? x + (int64_t) c * chunk_stride() : x; }
 };
+// Complex operand of the Hermitian path: full CSR with interleaved complex values, single GPU, one column block.
+struct DeviceCsrZ
+{
+    int64_t n = 0;
+    int64_t nnz = 0;
+    DevBuf<int> rowptr;      // n + 1
+    DevBuf<int> col;         // nnz
+    DevBuf<double2> val;     // nnz, (re, im)
+};
+void build_device_csr_z(int64_t n, const void* outer, bool outer64, const int32_t* inner, const double* values_ri, int order, int mode, cudaStream_t stream,
+                        DeviceCsrZ& out);
+// y (n complex, interleaved) = A x   (MatOp/SparseHermMatProd.h:83-88)
+void launch_spmv_z(const DeviceCsrZ& A, const double* x_ri, double* y_ri, cudaStream_t stream);
 // Re-lays the CSR out in nblocks column blocks (frees the unblocked arrays).  No-op for nblocks <= 1.
 void split_column_blocks(DeviceCsr& A, int nblocks, cudaStream_t stream);
 // Chunked variant for row-sharded operators (see DeviceCsr::chunk_len): nchunks blocks, chunk_len = ceil(slab / nchunks) rounded
@@ -161,13 +174,15 @@ enum PanelMode
 // x: input vector (w for FORM, f or w for CORR/DOT), f_out: output residual (may alias x).
 // coef: device pointer to the coefficients (CORR) or to alpha (FORM).
 // pred (optional): device flag; the kernel is a no-op when *pred == 0 (speculatively enqueued correction pass).
+// cplx: the vectors hold interleaved complex entries and nrows / ldv count doubles (Hermitian path); red_out / coef then use the
+// layout [0, j) = Re, [kRedNrm] = ||f||^2, [kRedNrm + 1, kRedNrm + 1 + j) = Im and j <= 63.
 void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out,
-                       const RedScratch& rs, cudaStream_t stream, const int* pred = nullptr);
+                       const RedScratch& rs, cudaStream_t stream, const int* pred = nullptr, bool cplx = false);
 
 // Decide kernels: consume ctl->red after a panel pass (and after the all-reduce when sharded).
 //  first = 1: after the FORM pass of a Lanczos step; first = 0: after a CORR pass (also applies
 //  the H update of Lanczos.h:172-175 with the coefficients that were just used).
-void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int first, cudaStream_t stream, int predicated = 0);
+void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int first, cudaStream_t stream, int predicated = 0, bool cplx = false);
 // Arnoldi flavours (Arnoldi.h:242-290): stage 0 = after h = V^T w (copies h into H(:,i) and c),
 // stage 1 = after f = w - V h (DGKS test), stage 2 = after a correction pass.
 void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated = 0);
@@ -189,7 +204,10 @@ enum VecReduceOp
 {
     VR_SUMSQ = 0,
     VR_DOT = 1,
-    VR_MAXABS = 2
+    VR_MAXABS = 2,
+    // interleaved complex vectors of n doubles (Hermitian path): Im <x, y> = sum x_re y_im - x_im y_re, max |x_k| (modulus)
+    VR_CDOT_IM = 3,
+    VR_CMAXABS = 4
 };
 void launch_vec_reduce(int op, const double* x, const double* y, int64_t n, double* out, const RedScratch& rs, cudaStream_t stream);
 void launch_vec_scale(const double* x, double s, int divide, double* y, int64_t n, cudaStream_t stream);          // y = x*s or x/s

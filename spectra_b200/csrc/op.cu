@@ -183,6 +183,27 @@ sb200_op* op_create_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64
     return op.release();
 }
 
+// SparseHermMatProd<std::complex<double>, Uplo, Flags>(mat) (MatOp/SparseHermMatProd.h:46-54): values are interleaved (re, im)
+sb200_op* op_create_sparse_herm(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values_ri, int storage_order, int matrix_mode)
+{
+    device_info();
+    SB200_REQUIRE(outer != nullptr, SB200_INVALID_ARGUMENT, "null matrix arrays");
+    std::unique_ptr<sb200_op> op(new sb200_op());
+    SB200_CUDA_CHECK(cudaStreamCreateWithFlags(&op->stream, cudaStreamNonBlocking));
+    build_device_csr_z(n, outer, outer_is_64 != 0, inner, values_ri, storage_order, matrix_mode, op->stream, op->Az);
+    op->cplx = true;
+    op->A.n = n;
+    op->A.row0 = 0;
+    op->A.nrows = n;
+    op->A.nnz = op->Az.nnz;
+    op->slab = n;
+    op->plan.grid = 1;
+    op->symmetric_hint = (matrix_mode != SB200_GENERAL);
+    SB200_CUDA_CHECK(cudaEventCreate(&op->ev0));
+    SB200_CUDA_CHECK(cudaEventCreate(&op->ev1));
+    return op.release();
+}
+
 sb200_op* op_create_callback(int64_t n, void (*fn)(const double*, double*, void*), void* user)
 {
     device_info();
@@ -220,6 +241,8 @@ void op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev)
 {
     if (op->cb)
         op_callback_device(op, x_dev, y_dev);
+    else if (op->cplx)
+        launch_spmv_z(op->Az, x_dev, y_dev, op->stream);
     else if (op->band)
         band_solve_device(op, x_dev, y_dev);
     else if (op->A.chunk_len)
@@ -240,15 +263,16 @@ void op_perform_op_host(sb200_op* op, const double* x_host, double* y_host)
         op->cb(x_host, y_host, op->cb_user);
         return;
     }
-    const int64_t n = op->A.n;
+    const int cw = op->cplx ? 2 : 1;  // doubles per scalar
+    const int64_t n = op->A.n * cw, nloc = op->A.nrows * cw;
     if (op->x_full.n < (size_t) n)
         op->x_full.alloc((size_t) n);
-    if (op->y_loc.n < (size_t) std::max<int64_t>(op->A.nrows, 1))
-        op->y_loc.alloc((size_t) std::max<int64_t>(op->A.nrows, 1));
+    if (op->y_loc.n < (size_t) std::max<int64_t>(nloc, 1))
+        op->y_loc.alloc((size_t) std::max<int64_t>(nloc, 1));
     SB200_CUDA_CHECK(cudaMemcpyAsync(op->x_full.get(), x_host, sizeof(double) * n, cudaMemcpyHostToDevice, op->stream));
     op_spmv_device(op, op->x_full.get(), op->y_loc.get());
-    if (op->A.nrows > 0)
-        SB200_CUDA_CHECK(cudaMemcpyAsync(y_host, op->y_loc.get(), sizeof(double) * op->A.nrows, cudaMemcpyDeviceToHost, op->stream));
+    if (nloc > 0)
+        SB200_CUDA_CHECK(cudaMemcpyAsync(y_host, op->y_loc.get(), sizeof(double) * nloc, cudaMemcpyDeviceToHost, op->stream));
     SB200_CUDA_CHECK(cudaStreamSynchronize(op->stream));
 }
 

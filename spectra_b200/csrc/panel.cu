@@ -28,7 +28,12 @@ namespace {
 constexpr int kPanelBlock = 256;
 constexpr int kColsPerGroup = 16;
 
-template <int NG, int MODE>
+// CPLX (Hermitian path): V, x, f hold interleaved complex numbers and are addressed as real arrays of twice the
+// length (nrows, ldv in doubles), so the double2 a lane loads per column IS one complex entry; the products become
+// c = V^H f (conjugated, ArnoldiOp.h:144-148 with Scalar = complex) and f -= V c with complex c.  A column group then holds 8
+// columns (16 accumulators: Re and Im).  Reduction layout: red[k] = Re c_k, red[kRedNrm] = ||f||^2, red[kRedNrm + 1 + k] = Im c_k
+// (the same layout is read from `coef` by the CORR mode), which limits the complex panel to 63 columns.
+template <int NG, int MODE, bool CPLX>
 __global__ void __launch_bounds__(kPanelBlock, 2)
     panel_kernel(const double* __restrict__ V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* __restrict__ coef,
                  double* red_out, double* partials, unsigned int* ticket, const int* pred)
@@ -36,31 +41,41 @@ __global__ void __launch_bounds__(kPanelBlock, 2)
     // speculatively enqueued pass: skip when the device-side flag says no correction is needed
     if (pred != nullptr && *pred == 0)
         return;
+    constexpr int CPG = CPLX ? 8 : kColsPerGroup;  // columns per group
+    constexpr int NCOEF = CPLX ? 2 * kPanelMaxCols : kPanelMaxCols;
     constexpr int RS = 8 / NG;        // row slices
     constexpr int RPI = RS * 64;      // rows per CTA iteration
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = warp % NG, rs = warp / NG;
     const uint64_t pol = l2_policy_evict_first();
 
-    __shared__ double s_c[kPanelMaxCols];
+    __shared__ double s_c[NCOEF];               // CPLX: Re c_k at [k], Im c_k at [kPanelMaxCols + k]
     __shared__ double2 s_p[2][NG][RS * 32];     // CORR: per-group partial  sum_k c_k V[r,k]
-    __shared__ double s_part[RS][kPanelMaxCols + 1];
+    __shared__ double s_part[RS][NCOEF + 1];    // CPLX: Re at [k], Im at [kPanelMaxCols + k], ||f||^2 at [NCOEF]
     __shared__ double s_out[kRedStride];
 
     if (MODE == PANEL_CORR)
     {
         if (threadIdx.x < kPanelMaxCols)
+        {
             s_c[threadIdx.x] = (threadIdx.x < j) ? coef[threadIdx.x] : 0.0;
+            if (CPLX)
+                s_c[kPanelMaxCols + threadIdx.x] = (threadIdx.x < j) ? coef[kRedNrm + 1 + threadIdx.x] : 0.0;
+        }
         __syncthreads();
     }
     const double alpha = (MODE == PANEL_FORM) ? coef[0] : 0.0;
 
-    double acc[kColsPerGroup];
+    double acc[CPG];
+    double acci[CPLX ? CPG : 1];
 #pragma unroll
-    for (int kk = 0; kk < kColsPerGroup; kk++)
+    for (int kk = 0; kk < CPG; kk++)
         acc[kk] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < (CPLX ? CPG : 1); kk++)
+        acci[kk] = 0.0;
     double nrm = 0.0;
-    const double* cg = s_c + g * kColsPerGroup;  // CORR coefficients of this group (shared-memory broadcast)
+    const double* cg = s_c + g * CPG;  // CORR coefficients of this group (shared-memory broadcast)
 
     const double* __restrict__ vi = V + (int64_t) (j - 1) * ldv;  // FORM: v_i is the last panel column
     int buf = 0;
@@ -68,11 +83,11 @@ __global__ void __launch_bounds__(kPanelBlock, 2)
     {
         const int64_t r0 = base + rs * 64 + lane * 2;
         const bool valid = r0 < ldv;  // padding rows [nrows, ldv) hold zeros
-        double2 v[kColsPerGroup];
+        double2 v[CPG];
 #pragma unroll
-        for (int kk = 0; kk < kColsPerGroup; kk++)
+        for (int kk = 0; kk < CPG; kk++)
         {
-            const int k = g * kColsPerGroup + kk;
+            const int k = g * CPG + kk;
             v[kk] = (valid && k < j) ? ld_stream_f64x2(V + r0 + (int64_t) k * ldv, pol) : make_double2(0.0, 0.0);
         }
         double2 xv = valid ? *reinterpret_cast<const double2*>(x + r0) : make_double2(0.0, 0.0);
@@ -87,10 +102,16 @@ __global__ void __launch_bounds__(kPanelBlock, 2)
         {
             double2 p = make_double2(0.0, 0.0);
 #pragma unroll
-            for (int kk = 0; kk < kColsPerGroup; kk++)
+            for (int kk = 0; kk < CPG; kk++)
             {
                 p.x = fma(cg[kk], v[kk].x, p.x);
                 p.y = fma(cg[kk], v[kk].y, p.y);
+                if (CPLX)
+                {
+                    // (cr + i ci) (vx + i vy)
+                    p.x = fma(-cg[kPanelMaxCols + kk], v[kk].y, p.x);
+                    p.y = fma(cg[kPanelMaxCols + kk], v[kk].x, p.y);
+                }
             }
             if (NG > 1)
             {
@@ -116,10 +137,16 @@ __global__ void __launch_bounds__(kPanelBlock, 2)
         if (MODE != PANEL_DOT && g == 0 && valid)
             *reinterpret_cast<double2*>(f_out + r0) = fn;
 #pragma unroll
-        for (int kk = 0; kk < kColsPerGroup; kk++)
+        for (int kk = 0; kk < CPG; kk++)
         {
             acc[kk] = fma(v[kk].x, fn.x, acc[kk]);
             acc[kk] = fma(v[kk].y, fn.y, acc[kk]);
+            if (CPLX)
+            {
+                // conj(v) f = (vx fx + vy fy) + i (vx fy - vy fx)
+                acci[kk] = fma(v[kk].x, fn.y, acci[kk]);
+                acci[kk] = fma(-v[kk].y, fn.x, acci[kk]);
+            }
         }
         if (g == 0)
         {
@@ -130,44 +157,53 @@ __global__ void __launch_bounds__(kPanelBlock, 2)
 
     // ---- CTA-level combine (fixed order) ----
 #pragma unroll
-    for (int kk = 0; kk < kColsPerGroup; kk++)
+    for (int kk = 0; kk < CPG; kk++)
     {
         const double s = warp_sum(acc[kk]);
         if (lane == 0)
-            s_part[rs][g * kColsPerGroup + kk] = s;
+            s_part[rs][g * CPG + kk] = s;
+        if (CPLX)
+        {
+            const double si = warp_sum(acci[kk]);
+            if (lane == 0)
+                s_part[rs][kPanelMaxCols + g * CPG + kk] = si;
+        }
     }
     if (g == 0)
     {
         const double s = warp_sum(nrm);
         if (lane == 0)
-            s_part[rs][kPanelMaxCols] = s;
+            s_part[rs][NCOEF] = s;
     }
-    if (NG < 4)
+    if (NG * CPG < kPanelMaxCols)
     {
         // columns of the unused groups
-        for (int t = threadIdx.x; t < RS * kPanelMaxCols; t += kPanelBlock)
+        for (int t = threadIdx.x; t < RS * NCOEF; t += kPanelBlock)
         {
-            const int c = t % kPanelMaxCols, r = t / kPanelMaxCols;
-            if (c >= NG * kColsPerGroup)
+            const int c = t % NCOEF, r = t / NCOEF;
+            if ((c % kPanelMaxCols) >= NG * CPG)
                 s_part[r][c] = 0.0;
         }
     }
     __syncthreads();
     double cta = 0.0;
     const int t = threadIdx.x;
-    if (t <= j)
+    const int K = CPLX ? 2 * j + 1 : j + 1;  // reduced values: [0, j) Re c (or c), slot j = ||f||^2, (j, 2j] Im c
+    if (t < K)
     {
-        const int src = (t == j) ? kPanelMaxCols : t;  // slot j carries ||f||^2
+        const int src = CPLX ? ((t < j) ? t : ((t == j) ? NCOEF : kPanelMaxCols + (t - j - 1))) : ((t == j) ? kPanelMaxCols : t);  // slot j carries ||f||^2
 #pragma unroll
         for (int q = 0; q < RS; q++)
             cta += s_part[q][src];
     }
-    if (grid_reduce_fixed_order<kPanelBlock>(cta, j + 1, partials, ticket, s_out))
+    if (grid_reduce_fixed_order<kPanelBlock>(cta, K, partials, ticket, s_out))
     {
         if (t < j)
             red_out[t] = s_out[t];
         if (t == 0)
             red_out[kRedNrm] = s_out[j];
+        if (CPLX && t > j && t < K)
+            red_out[kRedNrm + 1 + (t - j - 1)] = s_out[t];
     }
 }
 
@@ -176,11 +212,26 @@ void launch_panel_mode(const double* V, int64_t ldv, int64_t nrows, int j, const
                        const RedScratch& rs, const int* pred, cudaStream_t stream)
 {
     if (j <= 16)
-        panel_kernel<1, MODE><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
+        panel_kernel<1, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
     else if (j <= 32)
-        panel_kernel<2, MODE><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
+        panel_kernel<2, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
     else
-        panel_kernel<4, MODE><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
+        panel_kernel<4, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
+}
+
+// complex panel: 8 columns per group
+template <int MODE>
+void launch_panel_mode_z(const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out, int grid,
+                         const RedScratch& rs, const int* pred, cudaStream_t stream)
+{
+    if (j <= 8)
+        panel_kernel<1, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
+    else if (j <= 16)
+        panel_kernel<2, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
+    else if (j <= 32)
+        panel_kernel<4, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
+    else
+        panel_kernel<8, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -231,6 +282,61 @@ __global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta
     __syncwarp();
     for (int k = lane; k < j; k += 32)
         ctl->c[k] = ctl->red[k];
+    int need = (count < 5) && (ortho_err > kEps * beta);  // Lanczos.h:156
+    int zeroed = 0;
+    if (need && beta < beta_thresh)  // Lanczos.h:163-168
+    {
+        zeroed = 1;
+        beta = 0.0;
+        need = 0;
+    }
+    if (lane == 0)
+    {
+        ctl->beta = beta;
+        ctl->ortho_err = ortho_err;
+        ctl->count = count;
+        ctl->need_corr = need;
+        ctl->f_zeroed = zeroed;
+    }
+}
+
+// Complex (Hermitian) flavour of lanczos_decide_kernel: ctl->red / ctl->c carry Re at [k] and Im at [kRedNrm + 1 + k]; the
+// orthogonality error is the largest complex modulus (Vf.cwiseAbs().maxCoeff(), Lanczos.h:153); H is kept real -- the restart
+// reads m_fac_H.real() (HermEigsBase.h:131, 207) -- so only the real parts of the corrections enter it (Lanczos.h:172-175).
+__global__ void lanczos_decide_z_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int first, int predicated)
+{
+    if (predicated && ctl->need_corr == 0)
+        return;
+    const int lane = threadIdx.x;
+    const int i = ctl->i, j = i + 1;
+    int count = ctl->count;
+    if (lane == 0)
+    {
+        if (first)
+        {
+            H[i + (int64_t) i * m] = ctl->red_a[0];  // H(i,i) = Re <v, w>   (Lanczos.h:142)
+        }
+        else
+        {
+            const double hu = H[(i - 1) + (int64_t) i * m] + ctl->c[i - 1];
+            H[(i - 1) + (int64_t) i * m] = hu;
+            H[i + (int64_t) (i - 1) * m] = hu;
+            H[i + (int64_t) i * m] += ctl->c[i];
+        }
+    }
+    if (!first)
+        count += 1;
+    double mx = 0.0;
+    for (int k = lane; k < j; k += 32)
+        mx = fmax(mx, hypot(ctl->red[k], ctl->red[kRedNrm + 1 + k]));
+    const double ortho_err = warp_max(mx);
+    double beta = sqrt(ctl->red[kRedNrm]);
+    __syncwarp();
+    for (int k = lane; k < j; k += 32)
+    {
+        ctl->c[k] = ctl->red[k];
+        ctl->c[kRedNrm + 1 + k] = ctl->red[kRedNrm + 1 + k];
+    }
     int need = (count < 5) && (ortho_err > kEps * beta);  // Lanczos.h:156
     int zeroed = 0;
     if (need && beta < beta_thresh)  // Lanczos.h:163-168
@@ -383,10 +489,28 @@ __global__ void __launch_bounds__(kGemmBlock)
 }  // namespace
 
 void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out,
-                       const RedScratch& rs, cudaStream_t stream, const int* pred)
+                       const RedScratch& rs, cudaStream_t stream, const int* pred, bool cplx)
 {
     SB200_REQUIRE(j >= 1 && j <= kPanelMaxCols, SB200_INVALID_ARGUMENT, "panel width must be in [1, 64]");
     const int sms = device_info().sm_count;
+    if (cplx)
+    {
+        // nrows / ldv count doubles (two per complex entry); see panel_kernel
+        SB200_REQUIRE(j < kPanelMaxCols, SB200_INVALID_ARGUMENT, "complex panel width must be in [1, 63]");
+        const int ngz = j <= 8 ? 1 : (j <= 16 ? 2 : (j <= 32 ? 4 : 8));
+        const int64_t rpiz = (8 / ngz) * 64;
+        const int gridz = (int) std::max<int64_t>(1, std::min<int64_t>((nrows + rpiz - 1) / rpiz, (int64_t) sms * 2));
+        SB200_REQUIRE(gridz <= rs.max_grid, SB200_LOGIC, "panel: reduction scratch too small");
+        switch (mode)
+        {
+            case PANEL_DOT: launch_panel_mode_z<PANEL_DOT>(V, ldv, nrows, j, x, f_out, coef, red_out, gridz, rs, pred, stream); break;
+            case PANEL_FORM: launch_panel_mode_z<PANEL_FORM>(V, ldv, nrows, j, x, f_out, coef, red_out, gridz, rs, pred, stream); break;
+            case PANEL_CORR: launch_panel_mode_z<PANEL_CORR>(V, ldv, nrows, j, x, f_out, coef, red_out, gridz, rs, pred, stream); break;
+            default: throw Error(SB200_LOGIC, "bad panel mode");
+        }
+        SB200_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     const int ng = j <= 16 ? 1 : (j <= 32 ? 2 : 4);
     const int64_t rpi = (8 / ng) * 64;
     const int64_t need = (nrows + rpi - 1) / rpi;
@@ -402,9 +526,12 @@ void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, in
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int first, cudaStream_t stream, int predicated)
+void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int first, cudaStream_t stream, int predicated, bool cplx)
 {
-    lanczos_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, first, predicated);
+    if (cplx)
+        lanczos_decide_z_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, first, predicated);
+    else
+        lanczos_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, first, predicated);
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -69,7 +69,7 @@ struct sb200_sym_solver : public FacBase
         if (from_k > k)
             throw Error(SB200_INVALID_ARGUMENT, "Lanczos: from_k (= " + std::to_string(from_k) + ") is larger than the current subspace dimension (= " +
                                                     std::to_string(k) + ")");
-        const double beta_thresh = kEps * std::sqrt(double(n));
+        const double beta_thresh = kEps * std::sqrt(double(n / cw));  // m_n counts scalars
         const double eps_sqrt = std::sqrt(kEps);
         launch_trim_h(H.get(), m, (int) from_k, stream());
         prof.launches++;
@@ -81,7 +81,9 @@ struct sb200_sym_solver : public FacBase
             if (!restart && h_beta < eps_sqrt)
             {
                 // (V_{i-1}^H) v with v = f / beta   (Lanczos.h:107-113)
-                const double viv = reduce_scalar(VR_DOT, V.get() + (int64_t) (i - 1) * ld, f.get()) / h_beta;
+                double viv = reduce_scalar(VR_DOT, V.get() + (int64_t) (i - 1) * ld, f.get()) / h_beta;
+                if (is_cplx())
+                    viv = std::hypot(viv, reduce_scalar(VR_CDOT_IM, V.get() + (int64_t) (i - 1) * ld, f.get()) / h_beta);  // |Viv|, complex
                 restart = (std::fabs(viv) > eps_sqrt);
             }
             if (restart)
@@ -94,11 +96,11 @@ struct sb200_sym_solver : public FacBase
             // K-B: f = w - H(i,i) v_i, beta, Vf = V^T f   (Lanczos.h:145-153)
             const int j = i + 1;
             panel(PANEL_FORM, j, w.get(), f.get(), ctl.get()->red_a);
-            launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream());
+            launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream(), 0, is_cplx());
             // K-C: iterative correction (Lanczos.h:156-182).  In practice exactly one pass is needed per step, so the
             // first one is enqueued speculatively, predicated on the device-side flag, before the host looks at the status.
             panel(PANEL_CORR, j, f.get(), f.get(), ctl.get()->c, &ctl.get()->need_corr);
-            launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 1);
+            launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 1, is_cplx());
             prof.launches += 2;
             const FacCtl* st = read_status();
             if (st->count == 0)
@@ -106,7 +108,7 @@ struct sb200_sym_solver : public FacBase
             while (st->need_corr)
             {
                 panel(PANEL_CORR, j, f.get(), f.get(), ctl.get()->c);
-                launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream());
+                launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 0, is_cplx());
                 prof.launches++;
                 st = read_status();
             }
@@ -267,6 +269,7 @@ sb200_sym_solver* sym_create(sb200_op* op, int64_t nev, int64_t ncv, bool shift_
     if (ncv <= nev || ncv > n)
         throw Error(SB200_INVALID_ARGUMENT, "ncv must satisfy nev < ncv <= n, n is the size of matrix");
     SB200_REQUIRE(m <= kPanelMaxCols, SB200_INVALID_ARGUMENT, "this build supports ncv <= 64");
+    SB200_REQUIRE(!op->cplx || m < kPanelMaxCols, SB200_INVALID_ARGUMENT, "this build supports ncv <= 63 for complex Hermitian operators");
     std::unique_ptr<sb200_sym_solver> s(new sb200_sym_solver());
     s->alloc_common(op, nev, m);
     s->shift_mode = shift_mode;

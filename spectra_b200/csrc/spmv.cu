@@ -355,6 +355,49 @@ __global__ void __launch_bounds__(THREADS, sell_min_blocks(THREADS))
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Complex Hermitian operand (SparseHermMatProd::perform_op, MatOp/SparseHermMatProd.h:83-88): the full CSR carries
+// interleaved complex values; x and y are interleaved complex vectors.  Sub-warp of L lanes per row as in the real kernel;
+// one 16-byte gather per entry (a complex operand entry is half a sector, so the gather is twice as sector-efficient as the
+// real one).  Algorithmic bytes per row at d nnz/row: 20 d + 4 + 16 (x) + 16 (y).
+// ---------------------------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(kSpmvBlock, 4) spmv_z_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double2* __restrict__ val,
+                                                                const double* __restrict__ x, double* __restrict__ y, int64_t nrows)
+{
+    const uint64_t pol_stream = l2_policy_evict_first();
+    const uint64_t pol_keep = l2_policy_evict_last();
+    const int lane = threadIdx.x % L;
+    const int64_t sub = ((int64_t) blockIdx.x * kSpmvBlock + threadIdx.x) / L, nsub = (int64_t) gridDim.x * kSpmvBlock / L;
+    // every lane of a warp runs the same number of rounds: subwarp_sum shuffles with the full mask
+    const int64_t rounds = (nrows + nsub - 1) / nsub;
+    for (int64_t it = 0; it < rounds; it++)
+    {
+        const int64_t row = sub + it * nsub;
+        int start = 0, end = 0;
+        if (row < nrows)
+        {
+            start = __ldg(rowptr + row);
+            end = __ldg(rowptr + row + 1);
+        }
+        double ar = 0.0, ai = 0.0;
+        for (int p = start + lane; p < end; p += L)
+        {
+            const int c = ld_stream_s32(col + p, pol_stream);
+            const double2 a = ld_stream_f64x2(reinterpret_cast<const double*>(val + p), pol_stream);
+            const double2 xv = ld_keep_f64x2(x + 2 * (int64_t) c, pol_keep);
+            ar = fma(a.x, xv.x, ar);
+            ar = fma(-a.y, xv.y, ar);
+            ai = fma(a.x, xv.y, ai);
+            ai = fma(a.y, xv.x, ai);
+        }
+        ar = subwarp_sum<L>(ar);
+        ai = subwarp_sum<L>(ai);
+        if (lane == 0 && row < nrows)
+            *reinterpret_cast<double2*>(y + 2 * row) = make_double2(ar, ai);
+    }
+}
+
 struct BlockView
 {
     const int* rowptr;
@@ -521,6 +564,25 @@ void launch_spmv(const DeviceCsr& A, const SpmvPlan& plan, const double* x, doub
 }
 
 int spmv_num_blocks(const DeviceCsr& A) { return nblocks_of(A); }
+
+void launch_spmv_z(const DeviceCsrZ& A, const double* x_ri, double* y_ri, cudaStream_t stream)
+{
+    if (A.n == 0)
+        return;
+    const int lanes = lanes_for(double(A.nnz) / double(A.n));
+    const int sms = device_info().sm_count;
+    const int64_t need = (A.n * lanes + kSpmvBlock - 1) / kSpmvBlock;
+    const int grid = (int) std::max<int64_t>(1, std::min<int64_t>(need, (int64_t) sms * 4));
+    switch (lanes)
+    {
+        case 2: spmv_z_kernel<2><<<grid, kSpmvBlock, 0, stream>>>(A.rowptr.get(), A.col.get(), A.val.get(), x_ri, y_ri, A.n); break;
+        case 4: spmv_z_kernel<4><<<grid, kSpmvBlock, 0, stream>>>(A.rowptr.get(), A.col.get(), A.val.get(), x_ri, y_ri, A.n); break;
+        case 8: spmv_z_kernel<8><<<grid, kSpmvBlock, 0, stream>>>(A.rowptr.get(), A.col.get(), A.val.get(), x_ri, y_ri, A.n); break;
+        case 16: spmv_z_kernel<16><<<grid, kSpmvBlock, 0, stream>>>(A.rowptr.get(), A.col.get(), A.val.get(), x_ri, y_ri, A.n); break;
+        default: spmv_z_kernel<32><<<grid, kSpmvBlock, 0, stream>>>(A.rowptr.get(), A.col.get(), A.val.get(), x_ri, y_ri, A.n); break;
+    }
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
 
 void launch_spmv_step_block(const DeviceCsr& A, const SpmvPlan& plan, int c, const double* x_block, const double* f_loc, double* V, int64_t ldv, double* w,
                             FacCtl* ctl, double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream)

@@ -21,11 +21,15 @@ __global__ void __launch_bounds__(kVecBlock) vec_reduce_kernel(const double* __r
             acc = fma(a, a, acc);
         else if (OP == VR_DOT)
             acc = fma(a, y[i], acc);
+        else if (OP == VR_CDOT_IM)
+            acc = (i & 1) ? fma(-a, y[i - 1], acc) : fma(a, y[i + 1], acc);  // Im conj(x) y = x_re y_im - x_im y_re (n even)
+        else if (OP == VR_CMAXABS)
+            acc = (i & 1) ? acc : fmax(acc, hypot(a, x[i + 1]));
         else
             acc = fmax(acc, fabs(a));
     }
     __shared__ double s_w[kVecBlock / 32];
-    if (OP == VR_MAXABS)
+    if (OP == VR_MAXABS || OP == VR_CMAXABS)
     {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
@@ -40,9 +44,9 @@ __global__ void __launch_bounds__(kVecBlock) vec_reduce_kernel(const double* __r
     if (threadIdx.x == 0)
     {
         for (int q = 0; q < kVecBlock / 32; q++)
-            cta = (OP == VR_MAXABS) ? fmax(cta, s_w[q]) : cta + s_w[q];
+            cta = (OP == VR_MAXABS || OP == VR_CMAXABS) ? fmax(cta, s_w[q]) : cta + s_w[q];
     }
-    if (OP == VR_MAXABS)
+    if (OP == VR_MAXABS || OP == VR_CMAXABS)
     {
         // max is order independent: reuse the ticket scheme with a max combine
         __shared__ bool s_last;
@@ -173,6 +177,8 @@ void launch_vec_reduce(int op, const double* x, const double* y, int64_t n, doub
         case VR_SUMSQ: vec_reduce_kernel<VR_SUMSQ><<<grid, kVecBlock, 0, stream>>>(x, y, n, out, rs.partials, rs.ticket); break;
         case VR_DOT: vec_reduce_kernel<VR_DOT><<<grid, kVecBlock, 0, stream>>>(x, y, n, out, rs.partials, rs.ticket); break;
         case VR_MAXABS: vec_reduce_kernel<VR_MAXABS><<<grid, kVecBlock, 0, stream>>>(x, y, n, out, rs.partials, rs.ticket); break;
+        case VR_CDOT_IM: vec_reduce_kernel<VR_CDOT_IM><<<grid, kVecBlock, 0, stream>>>(x, y, n, out, rs.partials, rs.ticket); break;
+        case VR_CMAXABS: vec_reduce_kernel<VR_CMAXABS><<<grid, kVecBlock, 0, stream>>>(x, y, n, out, rs.partials, rs.ticket); break;
         default: throw Error(SB200_LOGIC, "bad reduce op");
     }
     SB200_CUDA_CHECK(cudaGetLastError());

@@ -1,0 +1,105 @@
+"""Parity cases of the complex Hermitian path, written against a backend module `sb` with the API of spectra_b200:
+run on a device by tests/test_gpu_experimental.py and on the kernel-logic emulator by tests/test_emu_kernels.py.
+Tolerances: operator 1e-13 relative; factorisation identities 1e-12 (test/Arnoldi.cpp); solver ||AU - UD||_inf <= 1e-9
+(test/HermEigs.cpp:66-70) and eigenvalues within 1e-10 relative of the oracle (oracle/herm.py)."""
+import numpy as np
+import scipy.sparse as sp
+
+import oracle as O
+from oracle import herm as OH
+
+FIXTURES = {10: (0.5, 3, 6), 100: (0.1, 10, 20), 1000: (0.01, 20, 50)}  # test/HermEigs.cpp:140-174
+
+
+def operator_case(sb, n=100, fmt="csc", uplo="lower"):
+    # SparseHermMatProd::perform_op (MatOp/SparseHermMatProd.h:83-88): one triangle, mirrored conjugated
+    rng = np.random.default_rng(n)
+    A = OH.gen_sparse_data_herm(n, FIXTURES.get(n, (0.1,))[0])
+    A = A.tocsc() if fmt == "csc" else A.tocsr()
+    Af = OH.herm_full(A, uplo)
+    op = sb.SparseHermMatProd(A, uplo=uplo)
+    assert op.rows() == n and op.cols() == n
+    for _ in range(2):
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        y, y0 = op.perform_op(x), Af @ x
+        assert np.abs(y - y0).max() <= 1e-13 * max(1.0, np.abs(y0).max())
+    M = rng.standard_normal((n, 3)) + 1j * rng.standard_normal((n, 3))
+    assert np.abs(op @ M - Af @ M).max() <= 1e-13 * max(1.0, np.abs(Af @ M).max())
+    assert np.array_equal(op.perform_op(x), op.perform_op(x))
+    # Hermitian: <x, A x> is real
+    assert abs(np.vdot(x, op.perform_op(x)).imag) <= 1e-12 * abs(np.vdot(x, op.perform_op(x)))
+
+
+def factorization_case(sb, n=200, m=24):
+    # test/Arnoldi.cpp:19-85 with a complex Scalar: A V - V H = f e_m', V^H V = I, H real symmetric tridiagonal
+    A = sp.random(n, n, density=0.05, random_state=7, format="csc") + 1j * sp.random(n, n, density=0.05, random_state=8, format="csc")
+    A = sp.csc_matrix(A)
+    Af = OH.herm_full(A)
+    op = sb.SparseHermMatProd(A)
+    eigs = sb.HermEigsSolver(op, 3, m)
+    v0 = OH.simple_random_complex(3, n)
+    eigs.init(v0)
+    eigs.factorize_from(1, m // 2)
+    eigs.factorize_from(m // 2, m)
+    fz = eigs.factorization()
+    V, H, f = fz["V"], fz["H"], fz["f"]
+    E = Af @ V - V @ H
+    E[:, -1] -= f
+    scale = max(1.0, np.abs(H).max())
+    assert np.abs(E).max() <= 1e-12 * scale
+    assert np.abs(V.conj().T @ V - np.eye(m)).max() <= 1e-12
+    assert abs(np.linalg.norm(f) - fz["beta"]) <= 1e-12 * scale
+    assert np.abs(H - H.T).max() == 0.0 and np.abs(np.triu(H, 2)).max() == 0.0
+    ref = OH.herm_factorize(Af.dot, n, m, v0=v0)
+    assert np.abs(H - ref["H"].real).max() <= 1e-9 * scale
+
+
+def solver_case(sb, n, selection, check_history=True):
+    # test/HermEigs.cpp:52-71, 118-174 (sparse cases)
+    prob, k, m = FIXTURES[n]
+    A = OH.gen_sparse_data_herm(n, prob)
+    Af = OH.herm_full(A)
+    op = sb.SparseHermMatProd(A)
+    eigs = sb.HermEigsSolver(op, k, m)
+    eigs.init()
+    nconv = eigs.compute(selection)
+    assert eigs.info() == sb.CompInfo.Successful and nconv == k
+    ev, U = eigs.eigenvalues(), eigs.eigenvectors()
+    assert U.dtype == np.complex128 and U.shape == (n, k)
+    assert np.abs(Af @ U - U * ev).max() <= 1e-9
+    ref = OH.herm_eigs(Af.dot, n, k, m, selection)
+    assert ref.nconv == k
+    assert np.abs(ev - ref.eigenvalues).max() <= 1e-10 * np.abs(ref.eigenvalues).max()
+    if check_history:
+        assert eigs.num_operations() == ref.nops and eigs.num_iterations() == ref.niter
+    assert np.abs(U.conj().T @ U - np.eye(k)).max() <= 1e-9
+
+
+def argument_checks(sb):
+    A = OH.gen_sparse_data_herm(10, 0.5)
+    op = sb.SparseHermMatProd(A)
+    for nev, ncv in ((0, 6), (10, 11), (3, 3), (3, 11)):  # HermEigsBase.h:267-271
+        try:
+            sb.HermEigsSolver(op, nev, ncv)
+        except sb.InvalidArgument:
+            continue
+        raise AssertionError((nev, ncv))
+    # SymEigsSolver needs a real operator, HermEigsSolver a complex one
+    try:
+        sb.SymEigsSolver(op, 3, 6)
+        raise AssertionError("SymEigsSolver accepted a complex operator")
+    except sb.InvalidArgument:
+        pass
+    real_op = sb.SparseSymMatProd(O.gen_sparse_data(10, 0.5))
+    try:
+        sb.HermEigsSolver(real_op, 3, 6)
+        raise AssertionError("HermEigsSolver accepted a real operator")
+    except sb.InvalidArgument:
+        pass
+    # a zero initial residual is rejected (Arnoldi.h:147-148)
+    e = sb.HermEigsSolver(op, 3, 6)
+    try:
+        e.init(np.zeros(10, dtype=np.complex128))
+        raise AssertionError("zero residual accepted")
+    except sb.InvalidArgument:
+        pass

@@ -1,0 +1,110 @@
+"""Kernel-logic checks WITHOUT a GPU: the product's own .cu sources compiled for the CPU against the CUDA execution model of
+tools/cuda_emu (fibers for the threads of a CTA, real barriers / shuffles / shared memory / atomics; see cuda_emu.h), driven through
+the same C ABI and Python mirror as on a device and compared with the CPU oracle.
+
+What this does and does not show: indexing, barrier placement, shuffle patterns, reduction orders, host sequencing and the
+reference's control flow are exercised statement by statement; hardware behaviour (memory model, PTX paths such as the TMA/DMMA
+restart GEMM, performance) is not -- the `-m gpu` suite remains the parity gate.  The emulator is test infrastructure like oracle/:
+nothing in spectra_b200/ can load it.
+
+The cases are small twins of the GPU tests (sizes chosen so that the file runs in a couple of minutes)."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import herm_cases as HC
+import oracle as O
+import test_gpu_experimental as X
+from helpers import sym_full
+
+
+# ---------------------------------------------------------------- default product path (verified on a B200 in round 1)
+def test_emu_default_operator_and_solver(emu):
+    A = O.gen_sparse_data(100, 0.1)
+    op = emu.SparseSymMatProd(A)
+    ref = O.Csr.from_scipy(A, "lower")
+    x = np.random.default_rng(0).standard_normal(100)
+    assert np.abs(op.perform_op(x) - ref.spmv(x)).max() <= 1e-13 * np.abs(ref.spmv(x)).max()
+    eigs = emu.SymEigsSolver(op, 10, 20)
+    eigs.init()
+    assert eigs.compute(emu.SortRule.LargestAlge) == 10 and eigs.info() == emu.CompInfo.Successful
+    r = O.sym_eigs(ref, 10, 20, O.LargestAlge)
+    assert np.abs(eigs.eigenvalues() - r.eigenvalues).max() <= 1e-10 * np.abs(r.eigenvalues).max()
+    assert eigs.num_operations() == r.nops and eigs.num_iterations() == r.niter
+    U = eigs.eigenvectors()
+    assert np.abs(ref.to_scipy() @ U - U * eigs.eigenvalues()).max() <= 1e-9
+
+
+def test_emu_default_gen_solver(emu):
+    A = O.gen_sparse_data(100, 0.1)
+    g = emu.GenEigsSolver(emu.SparseGenMatProd(A), 6, 20)
+    g.init()
+    g.compute(emu.SortRule.LargestMagn, 300)
+    assert g.info() == emu.CompInfo.Successful
+    ev, Z = g.eigenvalues(), g.eigenvectors()
+    assert np.abs(A @ Z - Z * ev).max() <= 1e-9
+    r = O.gen_eigs(O.Csr.from_scipy(A, "gen"), 6, 20, O.LargestMagn, 300)
+    assert g.num_operations() == r.nops
+
+
+# ---------------------------------------------------------------- sliced layout (SB200_SPMV_FORMAT=sell)
+@pytest.mark.parametrize("threads", [256, 512, 1024])
+@pytest.mark.parametrize("n,density", [(1, 1.0), (33, 0.3), (1025, 0.02), (5000, 0.004)])
+def test_emu_sell_spmv(emu, threads, n, density):
+    X.test_sell_spmv_matches_csr_and_scipy(emu, threads, n, density)
+
+
+def test_emu_sell_padding_and_empty_rows(emu):
+    X.test_sell_rejects_wasteful_padding(emu)
+    X.test_sell_empty_rows_and_empty_matrix(emu)
+
+
+def test_emu_sell_chunk_layout(emu):
+    X.test_sell_with_column_blocks_and_chunk_layout(emu, 65_537, 3, 4)
+
+
+@pytest.mark.parametrize("threads", [256, 1024])
+def test_emu_sell_fused_step_factorization(emu, threads):
+    X.test_sell_lanczos_factorization(emu, threads)
+
+
+def test_emu_sell_solver(emu):
+    X.test_sell_solver_matches_oracle(emu, "sym")
+    # a nonsymmetric operator through the sliced Arnoldi step head
+    A = O.gen_sparse_data(100, 0.1)
+    with X.env(SB200_SPMV_FORMAT="sell", SB200_SELL_MAX_FILL=100):
+        op = emu.SparseGenMatProd(A)
+    assert op.spmv_layout()["format"] == "sell"
+    g = emu.GenEigsSolver(op, 6, 20)
+    g.init()
+    g.compute(emu.SortRule.LargestMagn, 300)
+    assert g.info() == emu.CompInfo.Successful
+    ev, Z = g.eigenvalues(), g.eigenvectors()
+    assert np.abs(A @ Z - Z * ev).max() <= 1e-9
+
+
+# ---------------------------------------------------------------- complex Hermitian path
+@pytest.mark.parametrize("fmt,uplo", [("csc", "lower"), ("csr", "upper")])
+def test_emu_herm_operator(emu, fmt, uplo):
+    HC.operator_case(emu, 100, fmt, uplo)
+    HC.operator_case(emu, 10, fmt, uplo)
+
+
+def test_emu_herm_factorization(emu):
+    HC.factorization_case(emu)
+
+
+@pytest.mark.parametrize("selection", [O.LargestMagn, O.LargestAlge, O.SmallestAlge, O.BothEnds])
+@pytest.mark.parametrize("n", [10, 100])
+def test_emu_herm_solver(emu, n, selection):
+    HC.solver_case(emu, n, selection)
+
+
+def test_emu_herm_solver_smallest_magnitude(emu):
+    HC.solver_case(emu, 10, O.SmallestMagn)
+
+
+def test_emu_herm_argument_checks(emu):
+    HC.argument_checks(emu)

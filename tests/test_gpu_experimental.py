@@ -192,3 +192,29 @@ def test_sell_mid_size_solve_against_oracle(gpu):
 def test_gather_microbenchmark_runs(gpu):
     r = gpu.bench_gather(1_000_000, 10_000_000, 2)
     assert r["ms"] > 0 and abs(r["checksum"] - 1.0) < 1e-12
+
+
+# ---------------------------------------------------------------- complex Hermitian path
+import herm_cases as HC  # noqa: E402
+
+
+@pytest.mark.parametrize("fmt,uplo", [("csc", "lower"), ("csr", "lower"), ("csc", "upper"), ("csr", "upper")])
+@pytest.mark.parametrize("n", [10, 100, 1000])
+def test_sparse_herm_mat_prod(gpu, n, fmt, uplo):
+    HC.operator_case(gpu, n, fmt, uplo)
+
+
+def test_herm_lanczos_factorization(gpu):
+    HC.factorization_case(gpu)
+    HC.factorization_case(gpu, n=5000, m=63)
+
+
+@pytest.mark.parametrize("selection", [O.LargestMagn, O.LargestAlge, O.SmallestMagn, O.SmallestAlge, O.BothEnds])
+@pytest.mark.parametrize("n", [10, 100, 1000])
+def test_herm_eigs_reference_cases(gpu, n, selection):
+    # test/HermEigs.cpp:140-174
+    HC.solver_case(gpu, n, selection)
+
+
+def test_herm_argument_checks(gpu):
+    HC.argument_checks(gpu)
