@@ -114,10 +114,16 @@ inline void shrink_cols(Matrix& M, Index c) { M.conservativeResize(M.rows(), c);
 inline void shrink_cols(ComplexMatrix& M, Index c) { M.conservativeResize(M.rows(), c); }
 #endif
 
+// Marks operator wrappers that own a device-resident sb200_op (exposed through handle()); any other OpType is treated as a
+// user-defined host operator and wrapped in a callback adapter.
+struct DeviceOpTag
+{
+};
+
 // Device-resident sparse operator shared by SparseSymMatProd / SparseGenMatProd.
 // The user's compressed arrays must outlive the operator (the reference holds an Eigen::Ref to the
 // user's matrix, SparseSymMatProd.h:46-48); they are uploaded once at construction.
-class SparseOpBase
+class SparseOpBase : public DeviceOpTag
 {
 protected:
     sb200_op* m_op = nullptr;
@@ -250,7 +256,7 @@ public:
 };
 
 // Picks the device handle of an operator: device-resident sparse wrappers expose it directly, anything else is wrapped.
-template <typename OpType, bool IsDevice = std::is_base_of<SparseOpBase, OpType>::value>
+template <typename OpType, bool IsDevice = std::is_base_of<DeviceOpTag, OpType>::value>
 struct OpBinding
 {
     explicit OpBinding(OpType& op) : m_h(op.handle()) {}

@@ -36,3 +36,27 @@ def test_shim_reference_flow_on_gpu(gpu):
     print(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "ALL PASSED" in r.stdout
+
+
+# ---- complex Hermitian shim: compiled on the CPU, run against the kernel-logic emulator (tests/emu_loader.py) ----
+HERM_EXE = os.path.join(ROOT, "tests", "_build", "test_shim_herm")
+
+
+def _compile_herm(libdir, libname):
+    os.makedirs(os.path.dirname(HERM_EXE), exist_ok=True)
+    exe = HERM_EXE + "_" + libname
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_shim_herm.cpp"),
+           "-L", libdir, "-l" + libname, f"-Wl,-rpath,{libdir}", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_herm_shim_reference_flow_on_emulator(emu):
+    # test/HermEigs.cpp's sparse flow through include/Spectra/HermEigsSolver.h; the kernels run on the CPU execution model
+    libdir = os.path.join(ROOT, "tests", "_emu")
+    exe = _compile_herm(libdir, "spectra_b200_emu")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "ALL PASSED" in r.stdout

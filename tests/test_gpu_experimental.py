@@ -218,3 +218,14 @@ def test_herm_eigs_reference_cases(gpu, n, selection):
 
 def test_herm_argument_checks(gpu):
     HC.argument_checks(gpu)
+
+
+def test_herm_shim_reference_flow_on_gpu(gpu):
+    # test/HermEigs.cpp's sparse flow through the C++ shim headers against the CUDA library
+    import subprocess
+
+    import test_cpp_shim as TS
+
+    exe = TS._compile_herm(os.path.dirname(gpu.lib_path()), "spectra_b200")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ALL PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -252,3 +252,49 @@ def test_sym_shift_eigs_banded_vs_arpack():
     w = eigsh(A.tocsc(), k=10, sigma=0.5, which="LM", ncv=30, tol=1e-12, return_eigenvectors=False)
     assert np.abs(np.sort(r.eigenvalues) - np.sort(w)).max() <= 1e-10
     assert np.abs(A @ r.eigenvectors - r.eigenvectors * r.eigenvalues).max() <= 1e-9
+
+
+# ---------------------------------------------------------------- complex Hermitian oracle (oracle/herm.py)
+@pytest.mark.parametrize("n", [10, 100, 1000])
+def test_herm_oracle_reference_cases(n):
+    # test/HermEigs.cpp:140-174 (sparse cases): every selection rule converges, ||AU - UD||_inf <= 1e-9 (:66-70);
+    # independent truth: the dense spectrum from numpy.linalg.eigvalsh
+    from oracle import herm as OH
+
+    prob, k, m = {10: (0.5, 3, 6), 100: (0.1, 10, 20), 1000: (0.01, 20, 50)}[n]
+    A = OH.gen_sparse_data_herm(n, prob)
+    assert np.all(A.diagonal().imag == 0.0)  # "diagonal elements must have a zero imaginary part" (:29-31)
+    Af = OH.herm_full(A)
+    assert abs(Af - Af.conj().T).max() == 0.0
+    w = np.linalg.eigvalsh(Af.toarray())
+    picks = {O.LargestAlge: w[::-1][:k], O.SmallestAlge: w[:k], O.LargestMagn: w[np.argsort(-np.abs(w))][:k], O.SmallestMagn: w[np.argsort(np.abs(w))][:k]}
+    for sel in (O.LargestMagn, O.LargestAlge, O.SmallestMagn, O.SmallestAlge, O.BothEnds):
+        r = OH.herm_eigs(Af.dot, n, k, m, sel)
+        assert r.info == 0 and r.nconv == k
+        assert np.abs(Af @ r.eigenvectors - r.eigenvectors * r.eigenvalues).max() <= 1e-9
+        assert np.abs(r.eigenvectors.conj().T @ r.eigenvectors - np.eye(k)).max() <= 1e-9
+        if sel in picks:
+            assert np.abs(np.sort(r.eigenvalues) - np.sort(picks[sel])).max() <= 1e-10 * np.abs(w).max()
+        else:
+            assert max(np.abs(w - e).min() for e in r.eigenvalues) <= 1e-10 * np.abs(w).max()
+        assert np.all(np.diff(r.eigenvalues) <= 0)  # default sorting LargestAlge
+
+
+def test_herm_oracle_factorization_and_random_stream():
+    from oracle import herm as OH
+
+    # SimpleRandom<complex>: re, im drawn consecutively from the MINSTD stream (Util/SimpleRandom.h:68-77)
+    z = OH.simple_random_complex(0, 4)
+    r = O.simple_random(0, 8)
+    assert np.array_equal(z.real, r[0::2]) and np.array_equal(z.imag, r[1::2])
+    # Lanczos identities with a complex Scalar (test/Arnoldi.cpp:19-85 thresholds)
+    n, m = 120, 16
+    A = OH.gen_sparse_data_herm(n, 0.1)
+    Af = OH.herm_full(A)
+    fz = OH.herm_factorize(Af.dot, n, m)
+    V, H, f = fz["V"], fz["H"], fz["f"]
+    E = Af @ V - V @ H
+    E[:, -1] -= f
+    assert np.abs(E).max() <= 1e-12 * max(1.0, np.abs(H).max())
+    assert np.abs(V.conj().T @ V - np.eye(m)).max() <= 1e-12
+    assert np.abs(H.imag).max() <= 1e-14 * np.abs(H).max()  # the restart may use H.real() (HermEigsBase.h:131)
