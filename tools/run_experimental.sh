@@ -8,3 +8,5 @@ timeout 300 python tools/gather_roof.py 2>&1 | tee gpurun_out/gather_roof.log
 timeout 600 python tools/spmv_roofline.py 1e7 2>&1 | tee gpurun_out/spmv_variants_n1e7.log
 timeout 300 python tools/spmv_roofline.py 1e6 2>&1 | tee gpurun_out/spmv_variants_n1e6.log
 SB200_SPMV_FORMAT=sell timeout 600 python tools/quick_bench.py 1e7 2>&1 | tee gpurun_out/quick_sell_n1e7.log
+# complex Hermitian path: one mid-size solve for a first timing (SparseHermMatProd + HermEigsSolver)
+timeout 300 python tools/herm_probe.py 2>&1 | tee gpurun_out/herm_probe.log
