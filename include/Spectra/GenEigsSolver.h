@@ -21,9 +21,9 @@ class GenEigsSolver
     Index m_nev;
 
 public:
-    using Scalar = typename OpType::Scalar;
-    using ComplexVector = b200::ComplexVector;
-    using ComplexMatrix = b200::ComplexMatrix;
+    using Scalar = typename OpType::Scalar;  // double, or float (float storage at the boundary, fp64 arithmetic on the device)
+    using ComplexVector = b200::VectorOf<std::complex<Scalar>>;
+    using ComplexMatrix = b200::MatrixOf<std::complex<Scalar>>;
 
     GenEigsSolver(OpType& op, Index nev, Index ncv) : m_bind(op), m_op(op), m_nev(nev) { b200::check(sb200_gen_create(m_bind.handle(), nev, ncv, &m_s)); }
     GenEigsSolver(const GenEigsSolver&) = delete;
@@ -34,13 +34,17 @@ public:
             sb200_gen_destroy(m_s);
     }
 
-    void init(const Scalar* init_resid) { b200::check(sb200_gen_init(m_s, init_resid)); }
+    void init(const Scalar* init_resid)
+    {
+        std::vector<double> buf;
+        b200::check(sb200_gen_init(m_s, b200::widen(init_resid, m_op.rows(), buf)));
+    }
     void init() { b200::check(sb200_gen_init(m_s, nullptr)); }
 
     Index compute(SortRule selection = SortRule::LargestMagn, Index maxit = 1000, Scalar tol = 1e-10, SortRule sorting = SortRule::LargestMagn)
     {
         int64_t nconv = 0;
-        b200::check(sb200_gen_compute(m_s, static_cast<int>(selection), maxit, tol, static_cast<int>(sorting), &nconv));
+        b200::check(sb200_gen_compute(m_s, static_cast<int>(selection), maxit, static_cast<double>(tol), static_cast<int>(sorting), &nconv));
         return static_cast<Index>(nconv);
     }
     CompInfo info() const
@@ -69,21 +73,31 @@ public:
         b200::check(sb200_gen_eigenvalues(m_s, buf.data(), &cnt));
         ComplexVector res(static_cast<Index>(cnt));
         for (int64_t i = 0; i < cnt; i++)
-            res[i] = std::complex<double>(buf[static_cast<size_t>(2 * i)], buf[static_cast<size_t>(2 * i + 1)]);
+            res[i] = std::complex<Scalar>(static_cast<Scalar>(buf[static_cast<size_t>(2 * i)]), static_cast<Scalar>(buf[static_cast<size_t>(2 * i + 1)]));
         return res;
     }
 
     ComplexMatrix eigenvectors(Index nvec) const
     {
         nvec = (std::min)(nvec, m_nev);
-        ComplexMatrix res(m_op.rows(), (std::max)(nvec, Index(1)));
+        b200::ComplexMatrix buf(m_op.rows(), (std::max)(nvec, Index(1)));
         int64_t cnt = 0;
         // std::complex<double> is layout-compatible with interleaved (re, im) pairs
-        b200::check(sb200_gen_eigenvectors(m_s, nvec, reinterpret_cast<double*>(res.data()), &cnt));
-        b200::shrink_cols(res, static_cast<Index>(cnt));
-        return res;
+        b200::check(sb200_gen_eigenvectors(m_s, nvec, reinterpret_cast<double*>(buf.data()), &cnt));
+        b200::shrink_cols(buf, static_cast<Index>(cnt));
+        return narrow(std::move(buf), std::is_same<Scalar, double>());
     }
     ComplexMatrix eigenvectors() const { return eigenvectors(m_nev); }
+
+private:
+    static ComplexMatrix narrow(b200::ComplexMatrix&& M, std::true_type) { return std::move(M); }
+    static ComplexMatrix narrow(b200::ComplexMatrix&& M, std::false_type)
+    {
+        ComplexMatrix res(M.rows(), M.cols());
+        for (Index q = 0; q < M.rows() * M.cols(); q++)
+            res.data()[q] = std::complex<Scalar>(static_cast<Scalar>(M.data()[q].real()), static_cast<Scalar>(M.data()[q].imag()));
+        return res;
+    }
 };
 
 }  // namespace Spectra

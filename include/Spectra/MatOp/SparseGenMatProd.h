@@ -11,7 +11,7 @@ namespace Spectra {
 template <typename Scalar_, int Flags = SPECTRA_B200_COLMAJOR, typename StorageIndex = int>
 class SparseGenMatProd : public b200::SparseOpBase
 {
-    static_assert(std::is_same<Scalar_, double>::value, "the B200 path implements Scalar = double");
+    static_assert(b200::IsSupportedScalar<Scalar_>::value, "the B200 path implements Scalar = double, and float with fp64 device arithmetic");
 
 public:
     using Scalar = Scalar_;

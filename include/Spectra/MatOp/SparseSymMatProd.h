@@ -28,7 +28,7 @@ enum { Lower = 1, Upper = 2, ColMajor = 0, RowMajor = 1 };
 template <typename Scalar_, int Uplo = SPECTRA_B200_LOWER, int Flags = SPECTRA_B200_COLMAJOR, typename StorageIndex = int>
 class SparseSymMatProd : public b200::SparseOpBase
 {
-    static_assert(std::is_same<Scalar_, double>::value, "the B200 path implements Scalar = double");
+    static_assert(b200::IsSupportedScalar<Scalar_>::value, "the B200 path implements Scalar = double, and float with fp64 device arithmetic");
 
 public:
     using Scalar = Scalar_;

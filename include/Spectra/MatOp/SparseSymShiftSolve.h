@@ -11,7 +11,7 @@ namespace Spectra {
 template <typename Scalar_, int Uplo = SPECTRA_B200_LOWER, int Flags = SPECTRA_B200_COLMAJOR, typename StorageIndex = int>
 class SparseSymShiftSolve : public b200::SparseOpBase
 {
-    static_assert(std::is_same<Scalar_, double>::value, "the B200 path implements Scalar = double");
+    static_assert(b200::IsSupportedScalar<Scalar_>::value, "the B200 path implements Scalar = double, and float with fp64 device arithmetic");
 
 public:
     using Scalar = Scalar_;
@@ -36,7 +36,7 @@ public:
 #endif
 
     // set_shift(sigma) (SparseSymShiftSolve.h:85-95); throws std::invalid_argument when the factorisation fails
-    void set_shift(const Scalar& sigma) { b200::check(sb200_op_set_shift(m_op, sigma)); }
+    void set_shift(const Scalar& sigma) { b200::check(sb200_op_set_shift(m_op, static_cast<double>(sigma))); }
     // perform_op(x_in, y_out) = solve (:104-109) is SparseOpBase::perform_op
 };
 

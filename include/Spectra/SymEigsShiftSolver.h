@@ -14,14 +14,14 @@ class SymEigsShiftSolver : public SymEigsSolver<OpType>
     using Base = SymEigsSolver<OpType>;
     // device operators are shifted inside sb200_sym_create_shift; user-defined host operators through their own set_shift
     static void shift_host_op(OpType&, double, std::true_type) {}
-    static void shift_host_op(OpType& op, double sigma, std::false_type) { op.set_shift(sigma); }
+    static void shift_host_op(OpType& op, double sigma, std::false_type) { op.set_shift(static_cast<typename OpType::Scalar>(sigma)); }
 
 public:
     using Scalar = typename OpType::Scalar;
 
-    SymEigsShiftSolver(OpType& op, Index nev, Index ncv, const Scalar& sigma) : Base(op, nev, ncv, sigma, typename Base::ShiftInvert())
+    SymEigsShiftSolver(OpType& op, Index nev, Index ncv, const Scalar& sigma) : Base(op, nev, ncv, static_cast<double>(sigma), typename Base::ShiftInvert())
     {
-        shift_host_op(op, sigma, std::is_base_of<b200::SparseOpBase, OpType>());
+        shift_host_op(op, static_cast<double>(sigma), std::is_base_of<b200::SparseOpBase, OpType>());
     }
 };
 

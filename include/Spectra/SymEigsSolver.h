@@ -31,9 +31,9 @@ protected:
     }
 
 public:
-    using Scalar = typename OpType::Scalar;
-    using Vector = b200::Vector;
-    using Matrix = b200::Matrix;
+    using Scalar = typename OpType::Scalar;  // double, or float (float storage at the boundary, fp64 arithmetic on the device)
+    using Vector = b200::VectorOf<Scalar>;
+    using Matrix = b200::MatrixOf<Scalar>;
 
     SymEigsSolver(OpType& op, Index nev, Index ncv) : m_bind(op), m_op(op), m_nev(nev) { b200::check(sb200_sym_create(m_bind.handle(), nev, ncv, &m_s)); }
     SymEigsSolver(const SymEigsSolver&) = delete;
@@ -44,13 +44,17 @@ public:
             sb200_sym_destroy(m_s);
     }
 
-    void init(const Scalar* init_resid) { b200::check(sb200_sym_init(m_s, init_resid)); }
+    void init(const Scalar* init_resid)
+    {
+        std::vector<double> buf;
+        b200::check(sb200_sym_init(m_s, b200::widen(init_resid, m_op.rows(), buf)));
+    }
     void init() { b200::check(sb200_sym_init(m_s, nullptr)); }
 
     Index compute(SortRule selection = SortRule::LargestMagn, Index maxit = 1000, Scalar tol = 1e-10, SortRule sorting = SortRule::LargestAlge)
     {
         int64_t nconv = 0;
-        b200::check(sb200_sym_compute(m_s, static_cast<int>(selection), maxit, tol, static_cast<int>(sorting), &nconv));
+        b200::check(sb200_sym_compute(m_s, static_cast<int>(selection), maxit, static_cast<double>(tol), static_cast<int>(sorting), &nconv));
         return static_cast<Index>(nconv);
     }
 
@@ -80,20 +84,30 @@ public:
         b200::check(sb200_sym_eigenvalues(m_s, buf.data(), &cnt));
         Vector res(static_cast<Index>(cnt));
         for (int64_t i = 0; i < cnt; i++)
-            res[i] = buf[static_cast<size_t>(i)];
+            res[i] = static_cast<Scalar>(buf[static_cast<size_t>(i)]);
         return res;
     }
 
     Matrix eigenvectors(Index nvec) const
     {
         nvec = (std::min)(nvec, m_nev);
-        Matrix res(m_op.rows(), (std::max)(nvec, Index(1)));
+        b200::Matrix buf(m_op.rows(), (std::max)(nvec, Index(1)));
         int64_t cnt = 0;
-        b200::check(sb200_sym_eigenvectors(m_s, nvec, res.data(), &cnt));
-        b200::shrink_cols(res, static_cast<Index>(cnt));
-        return res;
+        b200::check(sb200_sym_eigenvectors(m_s, nvec, buf.data(), &cnt));
+        b200::shrink_cols(buf, static_cast<Index>(cnt));
+        return narrow(std::move(buf), std::is_same<Scalar, double>());
     }
     Matrix eigenvectors() const { return eigenvectors(m_nev); }
+
+private:
+    static Matrix narrow(b200::Matrix&& M, std::true_type) { return std::move(M); }
+    static Matrix narrow(b200::Matrix&& M, std::false_type)
+    {
+        Matrix res(M.rows(), M.cols());
+        for (Index q = 0; q < M.rows() * M.cols(); q++)
+            res.data()[q] = static_cast<Scalar>(M.data()[q]);
+        return res;
+    }
 };
 
 }  // namespace Spectra

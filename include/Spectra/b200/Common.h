@@ -99,20 +99,46 @@ public:
         m_v.resize(static_cast<size_t>(m_r * c));
     }
 };
-using Vector = VectorT<double>;
-using Matrix = MatrixT<double>;
-using ComplexVector = VectorT<std::complex<double>>;
-using ComplexMatrix = MatrixT<std::complex<double>>;
-inline void shrink_cols(Matrix& M, Index c) { M.conservative_resize_cols(c); }
-inline void shrink_cols(ComplexMatrix& M, Index c) { M.conservative_resize_cols(c); }
+template <typename T>
+using VectorOf = VectorT<T>;
+template <typename T>
+using MatrixOf = MatrixT<T>;
+template <typename T>
+inline void shrink_cols(MatrixT<T>& M, Index c)
+{
+    M.conservative_resize_cols(c);
+}
 #else
-using Vector = Eigen::VectorXd;
-using Matrix = Eigen::MatrixXd;
-using ComplexVector = Eigen::VectorXcd;
-using ComplexMatrix = Eigen::MatrixXcd;
-inline void shrink_cols(Matrix& M, Index c) { M.conservativeResize(M.rows(), c); }
-inline void shrink_cols(ComplexMatrix& M, Index c) { M.conservativeResize(M.rows(), c); }
+template <typename T>
+using VectorOf = Eigen::Matrix<T, Eigen::Dynamic, 1>;
+template <typename T>
+using MatrixOf = Eigen::Matrix<T, Eigen::Dynamic, Eigen::Dynamic>;
+template <typename T>
+inline void shrink_cols(MatrixOf<T>& M, Index c)
+{
+    M.conservativeResize(M.rows(), c);
+}
 #endif
+using Vector = VectorOf<double>;
+using Matrix = MatrixOf<double>;
+using ComplexVector = VectorOf<std::complex<double>>;
+using ComplexMatrix = MatrixOf<std::complex<double>>;
+
+// Scalar = float (the reference's wrappers are templated on Scalar, SparseSymMatProd.h:30): the shim keeps the user's float
+// storage and float results, the device path computes in fp64 -- values are widened once at upload, vectors at the boundary.
+// (The path is HBM-bound; fp32 device storage would halve its bytes and is not implemented.)
+template <typename T>
+struct IsSupportedScalar : std::integral_constant<bool, std::is_same<T, double>::value || std::is_same<T, float>::value>
+{
+};
+inline const double* widen(const double* p, Index, std::vector<double>&) { return p; }
+inline const double* widen(const float* p, Index n, std::vector<double>& buf)
+{
+    buf.resize(static_cast<size_t>(n));
+    for (Index i = 0; i < n; i++)
+        buf[static_cast<size_t>(i)] = static_cast<double>(p[i]);
+    return buf.data();
+}
 
 // Marks operator wrappers that own a device-resident sb200_op (exposed through handle()); any other OpType is treated as a
 // user-defined host operator and wrapped in a callback adapter.
@@ -150,6 +176,12 @@ protected:
     // StorageIndex = int (Eigen's default) is passed through; 64-bit StorageIndex keeps its 64-bit outer offsets and has its
     // inner indices narrowed once (the device CSR addresses n < 2^31 columns with 32-bit ids)
     std::vector<int32_t> m_inner32;
+    std::vector<double> m_values64;  // Scalar = float: the widened copy of the user's values
+    template <typename StorageIndex>
+    void create_any(Index n, const StorageIndex* outer, const StorageIndex* inner, const float* values, bool row_major, int mode, bool shift_solve = false)
+    {
+        create_any(n, outer, inner, widen(values, static_cast<Index>(outer[n]), m_values64), row_major, mode, shift_solve);
+    }
     template <typename StorageIndex>
     void create_any(Index n, const StorageIndex* outer, const StorageIndex* inner, const double* values, bool row_major, int mode, bool shift_solve = false)
     {
@@ -194,6 +226,10 @@ public:
             m_inner32 = std::move(o.m_inner32);
             if (own_inner)
                 m_inner = m_inner32.data();
+            const bool own_values = !o.m_values64.empty();
+            m_values64 = std::move(o.m_values64);
+            if (own_values)
+                m_values = m_values64.data();
             o.m_op = nullptr;
         }
         return *this;
@@ -210,12 +246,28 @@ public:
 
     // y_out = A * x_in, host pointers (SparseSymMatProd.h:83-88 / SparseGenMatProd.h:82-87)
     void perform_op(const double* x_in, double* y_out) const { check(sb200_op_perform_op(m_op, x_in, y_out)); }
+    void perform_op(const float* x_in, float* y_out) const
+    {
+        std::vector<double> x(static_cast<size_t>(m_n)), y(static_cast<size_t>(m_n));
+        for (Index i = 0; i < m_n; i++)
+            x[static_cast<size_t>(i)] = x_in[i];
+        check(sb200_op_perform_op(m_op, x.data(), y.data()));
+        for (Index i = 0; i < m_n; i++)
+            y_out[i] = static_cast<float>(y[static_cast<size_t>(i)]);
+    }
 
     // operator*(Matrix) (SparseSymMatProd.h:93-96)
     Matrix operator*(const Matrix& mat_in) const
     {
         Matrix res(m_n, mat_in.cols());
         check(sb200_op_apply_matrix(m_op, mat_in.data(), mat_in.cols(), res.data()));
+        return res;
+    }
+    MatrixOf<float> operator*(const MatrixOf<float>& mat_in) const
+    {
+        MatrixOf<float> res(m_n, mat_in.cols());
+        for (Index c = 0; c < mat_in.cols(); c++)
+            perform_op(mat_in.data() + c * m_n, res.data() + c * m_n);
         return res;
     }
 
@@ -238,12 +290,32 @@ class HostOpAdapter
 {
     sb200_op* m_op = nullptr;
     const OpType* m_user;
-    static void trampoline(const double* x, double* y, void* self) { static_cast<const OpType*>(self)->perform_op(x, y); }
+    Index m_rows = 0;
+    mutable std::vector<typename OpType::Scalar> m_x, m_y;  // Scalar = float: narrowed operand / result of the user's perform_op
+    static void call(const OpType* op, const double* x, double* y, const HostOpAdapter*, std::true_type) { op->perform_op(x, y); }
+    static void call(const OpType* op, const double* x, double* y, const HostOpAdapter* self, std::false_type)
+    {
+        using S = typename OpType::Scalar;
+        const size_t n = static_cast<size_t>(self->m_rows);
+        self->m_x.resize(n);
+        self->m_y.resize(n);
+        for (size_t i = 0; i < n; i++)
+            self->m_x[i] = static_cast<S>(x[i]);
+        op->perform_op(self->m_x.data(), self->m_y.data());
+        for (size_t i = 0; i < n; i++)
+            y[i] = static_cast<double>(self->m_y[i]);
+    }
+    static void trampoline(const double* x, double* y, void* self)
+    {
+        const HostOpAdapter* a = static_cast<const HostOpAdapter*>(self);
+        call(a->m_user, x, y, a, std::is_same<typename OpType::Scalar, double>());
+    }
 
 public:
-    explicit HostOpAdapter(const OpType& op) : m_user(&op)
+    explicit HostOpAdapter(const OpType& op) : m_user(&op), m_rows(static_cast<Index>(op.rows()))
     {
-        check(sb200_op_create_callback(static_cast<int64_t>(op.rows()), &HostOpAdapter::trampoline, const_cast<OpType*>(m_user), &m_op));
+        static_assert(IsSupportedScalar<typename OpType::Scalar>::value, "user-defined operators must use Scalar = double or float");
+        check(sb200_op_create_callback(static_cast<int64_t>(op.rows()), &HostOpAdapter::trampoline, this, &m_op));
     }
     HostOpAdapter(const HostOpAdapter&) = delete;
     HostOpAdapter& operator=(const HostOpAdapter&) = delete;

@@ -42,10 +42,10 @@ def test_shim_reference_flow_on_gpu(gpu):
 HERM_EXE = os.path.join(ROOT, "tests", "_build", "test_shim_herm")
 
 
-def _compile_herm(libdir, libname):
+def _compile_herm(libdir, libname, src="test_shim_herm.cpp"):
     os.makedirs(os.path.dirname(HERM_EXE), exist_ok=True)
-    exe = HERM_EXE + "_" + libname
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_shim_herm.cpp"),
+    exe = os.path.join(ROOT, "tests", "_build", src[:-4] + "_" + libname)
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", src),
            "-L", libdir, "-l" + libname, f"-Wl,-rpath,{libdir}", "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
@@ -56,6 +56,15 @@ def test_herm_shim_reference_flow_on_emulator(emu):
     # test/HermEigs.cpp's sparse flow through include/Spectra/HermEigsSolver.h; the kernels run on the CPU execution model
     libdir = os.path.join(ROOT, "tests", "_emu")
     exe = _compile_herm(libdir, "spectra_b200_emu")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "ALL PASSED" in r.stdout
+
+
+def test_float_shim_flow_on_emulator(emu):
+    # Scalar = float wrappers / solvers / user operator (float at the boundary, fp64 on the device)
+    exe = _compile_herm(os.path.join(ROOT, "tests", "_emu"), "spectra_b200_emu", "test_shim_float.cpp")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     print(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
