@@ -751,6 +751,7 @@ __device__ void hess_eigen_real(double* T, double* U, int m, double* ev_re, doub
                     }
                     __syncwarp();
                     const double t = fabs(M_(T, i, n));
+                    __syncwarp();  // every lane must have read t before the lane that owns row i rescales T(i, n)
                     if ((eps * t) * t > 1.0)
                     {
                         FOR_LANES(k, i, m) M_(T, k, n) /= t;
@@ -841,6 +842,7 @@ __device__ void hess_eigen_real(double* T, double* U, int m, double* ev_re, doub
                     }
                     __syncwarp();
                     const double t = fmax(fabs(M_(T, i, n - 1)), fabs(M_(T, i, n)));
+                    __syncwarp();  // as above: t is read by all lanes before row i is rescaled
                     if ((eps * t) * t > 1.0)
                     {
                         FOR_LANES(k, i, m)

@@ -40,6 +40,16 @@ def emu():
     return emu_loader.load()
 
 
+@pytest.fixture(params=["forward", "reverse"])
+def emu_order(request, emu):
+    """Runs a test twice: with the fibers of a CTA scheduled in ascending and in descending thread order.  A result that depends on
+    the order means code that relies on warp-lockstep execution between two synchronisation points -- a data race under independent
+    thread scheduling (this is how the missing __syncwarp() of dense_gen.cu's overflow rescaling was found)."""
+    emu.lib().cuda_emu_set_reverse(1 if request.param == "reverse" else 0)
+    yield emu
+    emu.lib().cuda_emu_set_reverse(0)
+
+
 @pytest.fixture(scope="session")
 def gpu():
     if os.environ.get("SB200_TEST_BACKEND") == "emu":

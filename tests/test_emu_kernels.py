@@ -108,3 +108,25 @@ def test_emu_herm_solver_smallest_magnitude(emu):
 
 def test_emu_herm_argument_checks(emu):
     HC.argument_checks(emu)
+
+
+# ---------------------------------------------------------------- scheduling-order independence (race detection)
+def test_emu_order_dense_kernels(emu_order):
+    # the small dense device kernels in both fiber orders; m = 61, 62, 64 of the Hessenberg eigen-decomposition exercise the
+    # overflow-rescaling branch whose missing __syncwarp() this check uncovered
+    import test_gpu_gen as G
+    import test_gpu_sym as S
+
+    for m in (6, 50, 61, 62, 64):
+        G.test_hessenberg_eigen_device(emu_order, m)
+    for m in (6, 60):
+        G.test_hessenberg_qr_device(emu_order, m)
+        G.test_double_shift_qr_device(emu_order, m)
+        S.test_tridiag_eigen_device(emu_order, m)
+        S.test_tridiag_qr_device(emu_order, m)
+
+
+def test_emu_order_solvers(emu_order):
+    test_emu_default_operator_and_solver(emu_order)
+    HC.solver_case(emu_order, 10, O.LargestAlge)
+    X.test_sell_lanczos_factorization(emu_order, 512)

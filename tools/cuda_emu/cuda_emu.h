@@ -97,6 +97,7 @@ struct State
     uint64_t progress = 0;
     const std::function<void()>* body = nullptr;
     int64_t launches = 0;
+    bool reverse_order = [] { const char* e = getenv("CUDA_EMU_ORDER"); return e && e[0] == 'r'; }();
 };
 inline State g;
 
@@ -227,8 +228,11 @@ inline void run_cta(const std::function<void()>& body, const Launch& L)
     {
         const uint64_t before = g.progress;
         remaining = 0;
-        for (int t = 0; t < nthreads; t++)
+        for (int tt = 0; tt < nthreads; tt++)
         {
+            // CUDA_EMU_ORDER=reverse runs the fibers of a CTA in descending thread order: results that change with the order expose
+            // code that relies on warp-lockstep execution between two synchronisation points (a race under independent thread scheduling)
+            const int t = g.reverse_order ? nthreads - 1 - tt : tt;
             if (g.done[(size_t) t])
                 continue;
             g.cur = t;
@@ -251,9 +255,13 @@ inline void run_cta(const std::function<void()>& body, const Launch& L)
 inline void launch_impl(const Launch& L, const std::function<void()>& body)
 {
     g.launches++;
-    std::vector<unsigned char> smem(L.smem + 128);
+    // dynamic shared memory: 128-byte aligned, NaN-filled (like device memory here), followed by a guard zone that must stay intact
+    constexpr size_t kGuard = 4096;
+    std::vector<unsigned char> smem(L.smem + 128 + kGuard);
     unsigned char* sp = smem.data();
     sp += (128 - ((uintptr_t) sp & 127)) & 127;
+    memset(sp, 0xFF, L.smem);
+    memset(sp + L.smem, 0xA5, kGuard);
     g.dyn_smem = sp;
     for (unsigned bz = 0; bz < L.grid.z; bz++)
         for (unsigned by = 0; by < L.grid.y; by++)
@@ -262,6 +270,12 @@ inline void launch_impl(const Launch& L, const std::function<void()>& body)
                 g.bid = uint3{bx, by, bz};
                 run_cta(body, L);
             }
+    for (size_t q = 0; q < kGuard; q++)
+        if (sp[L.smem + q] != 0xA5)
+        {
+            fprintf(stderr, "cuda_emu: a kernel wrote %zu bytes past its %zu bytes of dynamic shared memory\n", q + 1, L.smem);
+            abort();
+        }
     g.dyn_smem = nullptr;
 }
 

@@ -35,6 +35,9 @@ void launch_compress_dmma(const double* V, int64_t ldv, int64_t nrows, int m, co
     launch_compress_fma(V, ldv, nrows, m, Q, kk, Vout, ldo, f, H, red_out, rs, stream);
 }
 }  // namespace sb200
+
+// test control: run the fibers of every CTA in descending thread order (see cuda_emu.h, CUDA_EMU_ORDER)
+extern "C" __attribute__((visibility("default"))) void cuda_emu_set_reverse(int on) { ::emu::g.reverse_order = (on != 0); }
 '''
 
 
