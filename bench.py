@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-ops", type=int, default=12, help="matrix operations in the bounded CPU sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-experimental", action="store_true", help="do not run tools/experimental_probe.py (opt-in code paths) after the timed work")
     return ap.parse_args()
 
 
@@ -330,6 +331,21 @@ def main():
                "sample": f"init + first {r.nops - 2} Lanczos steps (op_limit={args.cpu_sample_ops}) of the same n={n} solve, {r.seconds:.1f} s; early steps have "
                          f"narrow panels, so this over-states the CPU's steady-state rate", "host_cores_available": os.cpu_count()}
 
+    # ---- opt-in code paths (sliced-CSR SpMV, Hermitian solver, gather-roof microbenchmark): probed in a SEPARATE process with a hard
+    # timeout, after every timed region is over; reported under "experimental", never part of value / e2e / roofline ----
+    experimental = None
+    if rank == 0 and world == 1 and not args.skip_experimental:
+        import subprocess
+
+        try:
+            pr = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "experimental_probe.py"), str(n)], capture_output=True, text=True, timeout=420)
+            last = [ln for ln in pr.stdout.splitlines() if ln.startswith("{")]
+            experimental = json.loads(last[-1]) if last else {"error": f"no output (exit {pr.returncode}): {pr.stderr[-400:]}"}
+        except subprocess.TimeoutExpired:
+            experimental = {"error": "probe timed out after 420 s"}
+        except Exception as e:  # noqa: BLE001
+            experimental = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         line = {
             "metric": "spmv_iters_per_sec", "value": value, "unit": "SpMV-iters/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -339,7 +355,7 @@ def main():
             "converged": bool(info_ok), "accuracy": {"max_rel_residual": float(np.max(rel_res)), "bound": 1e-10},
             "wall_ms_per_step": wall_per_step, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kern, "cpu_baseline": cpu,
             "clocks": clocks, "algo_counters": {k: last_stats[k] for k in ("lanczos_steps", "reorth_passes", "restarts", "expand_calls")},
-            "device": info, "nnz": nnz_total, "gen_seconds": gen_s,
+            "device": info, "nnz": nnz_total, "gen_seconds": gen_s, "experimental": experimental,
         }
         print(json.dumps(line), flush=True)
 

@@ -10,3 +10,5 @@ timeout 300 python tools/spmv_roofline.py 1e6 2>&1 | tee gpurun_out/spmv_variant
 SB200_SPMV_FORMAT=sell timeout 600 python tools/quick_bench.py 1e7 2>&1 | tee gpurun_out/quick_sell_n1e7.log
 # complex Hermitian path: one mid-size solve for a first timing (SparseHermMatProd + HermEigsSolver)
 timeout 300 python tools/herm_probe.py 2>&1 | tee gpurun_out/herm_probe.log
+# everything above in one JSON line (what bench.py attaches under "experimental")
+timeout 600 python tools/experimental_probe.py 1e7 2>&1 | tail -1 | tee gpurun_out/experimental_probe.json
