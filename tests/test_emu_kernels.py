@@ -130,3 +130,23 @@ def test_emu_order_solvers(emu_order):
     test_emu_default_operator_and_solver(emu_order)
     HC.solver_case(emu_order, 10, O.LargestAlge)
     X.test_sell_lanczos_factorization(emu_order, 512)
+
+
+# ---------------------------------------------------------------- golden known-answer spectra through the kernels
+@pytest.mark.parametrize("n", [10, 100])
+def test_emu_against_golden_spectra(emu, n):
+    import golden_cases as GC
+    from oracle import herm as OH
+
+    prob = {10: 0.5, 100: 0.1}[n]
+    k, m = GC.KM[n]
+    A = O.gen_sparse_data(n, prob)
+    for rule, srule in ((O.LargestAlge, emu.SortRule.LargestAlge), (O.SmallestAlge, emu.SortRule.SmallestAlge)):
+        e = emu.SymEigsSolver(emu.SparseSymMatProd(A), k, m)
+        e.init()
+        e.compute(srule)
+        GC.check_sym_values("sym", n, rule, e.eigenvalues())
+        h = emu.HermEigsSolver(emu.SparseHermMatProd(OH.gen_sparse_data_herm(n, prob)), k, m)
+        h.init()
+        h.compute(srule)
+        GC.check_sym_values("herm", n, rule, h.eigenvalues())

@@ -194,3 +194,14 @@ def test_gen_eigs_full_size_properties(gpu):
     # the planted eigenvalues are real up to the perturbation: the top 10 lie near 3 + 0.35 j, j = 19..10
     assert np.abs(np.sort(evals.real)[::-1] - (3.0 + 0.35 * np.arange(19, 9, -1))).max() < 0.5
     assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1:] == runs[1][1:]
+
+
+@pytest.mark.parametrize("n,k,m", [(100, 10, 30), (1000, 20, 50)])
+def test_gen_eigs_against_golden_spectra(gpu, n, k, m):
+    import golden_cases as GC
+
+    A = O.gen_sparse_data(n, {100: 0.1, 1000: 0.01}[n])
+    g = gpu.GenEigsSolver(gpu.SparseGenMatProd(A), k, m)
+    g.init()
+    assert g.compute(gpu.SortRule.LargestMagn) == k
+    GC.check_gen_values(n, g.eigenvalues(), k)

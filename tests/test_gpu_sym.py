@@ -550,3 +550,19 @@ def test_user_defined_operator(gpu):
     with pytest.raises(KeyError):
         bad.init()
         bad.compute(gpu.SortRule.LargestAlge)
+
+
+@pytest.mark.parametrize("n", [10, 100, 1000])
+def test_sym_eigs_against_golden_spectra(gpu, n):
+    # tests/golden/kat_spectra.json: dense-LAPACK spectra of the reference's own fixtures (make_golden.py)
+    import golden_cases as GC
+
+    prob = {10: 0.5, 100: 0.1, 1000: 0.01}[n]
+    k, m = GC.KM[n]
+    A = O.gen_sparse_data(n, prob)
+    op = gpu.SparseSymMatProd(A)
+    for rule, srule in ((O.LargestAlge, gpu.SortRule.LargestAlge), (O.SmallestAlge, gpu.SortRule.SmallestAlge), (O.LargestMagn, gpu.SortRule.LargestMagn)):
+        e = gpu.SymEigsSolver(op, k, m)
+        e.init()
+        assert e.compute(srule) == k
+        GC.check_sym_values("sym", n, rule, e.eigenvalues())

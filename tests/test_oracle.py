@@ -298,3 +298,24 @@ def test_herm_oracle_factorization_and_random_stream():
     assert np.abs(E).max() <= 1e-12 * max(1.0, np.abs(H).max())
     assert np.abs(V.conj().T @ V - np.eye(m)).max() <= 1e-12
     assert np.abs(H.imag).max() <= 1e-14 * np.abs(H).max()  # the restart may use H.real() (HermEigsBase.h:131)
+
+
+# ---------------------------------------------------------------- golden known-answer spectra (tests/golden/kat_spectra.json)
+@pytest.mark.parametrize("n", [10, 100, 1000])
+def test_oracle_against_golden_spectra(n):
+    import golden_cases as GC
+    from oracle import herm as OH
+
+    prob = {10: 0.5, 100: 0.1, 1000: 0.01}[n]
+    k, m = GC.KM[n]
+    A = O.gen_sparse_data(n, prob)
+    csr = O.Csr.from_scipy(A, "lower")
+    Hf = OH.herm_full(OH.gen_sparse_data_herm(n, prob))
+    for rule in (O.LargestAlge, O.SmallestAlge, O.LargestMagn):
+        GC.check_sym_values("sym", n, rule, O.sym_eigs(csr, k, m, rule).eigenvalues)
+        GC.check_sym_values("herm", n, rule, OH.herm_eigs(Hf.dot, n, k, m, rule).eigenvalues)
+    kg, mg = {10: (3, 6), 100: (10, 30), 1000: (20, 50)}[n]
+    r = O.gen_eigs(O.Csr.from_scipy(A, "gen"), kg, mg, O.LargestMagn)
+    if r.nconv == kg:  # the reference tolerates non-convergence of this fixture at n = 10 (test/GenEigs.cpp:143-150)
+        GC.check_gen_values(n, r.eigenvalues, kg)
+    assert np.allclose(O.sym_eigs(O.Csr.from_dense(np.diag(np.arange(1.0, 11.0)), "lower"), 3, 6, O.LargestAlge).eigenvalues, GC.golden()["diag10"]["largest"], atol=1e-12)
