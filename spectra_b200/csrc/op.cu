@@ -146,7 +146,7 @@ sb200_op* op_create_sparse(int64_t n, const void* outer, int outer_is_64, const 
                            sb200_comm* comm)
 {
     device_info();
-    SB200_REQUIRE(outer && (inner || true), SB200_INVALID_ARGUMENT, "null matrix arrays");
+    SB200_REQUIRE(outer != nullptr, SB200_INVALID_ARGUMENT, "null matrix arrays");  // inner / values may be null for an empty matrix
     std::unique_ptr<sb200_op> op(new sb200_op());
     op->comm = comm;
     SB200_CUDA_CHECK(cudaStreamCreateWithFlags(&op->stream, cudaStreamNonBlocking));

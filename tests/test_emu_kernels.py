@@ -150,3 +150,81 @@ def test_emu_against_golden_spectra(emu, n):
         h.init()
         h.compute(srule)
         GC.check_sym_values("herm", n, rule, h.eigenvalues())
+
+
+# ---------------------------------------------------------------- row-sharded solver: ranks emulated as threads of one process
+def _sharded_solve(emu, n, P, rp, ci, v, k, m, kind="sym", fmt_env=None):
+    """One thread per rank; the emulated communicator (emu_build.py, comm.cu stand-in) rendezvouses the collectives in-process."""
+    import threading
+
+    from spectra_b200_emu import dist
+
+    uid = emu.Comm.unique_id()
+    out, errs = [None] * P, []
+
+    def worker(rank):
+        try:
+            comm = emu.Comm(rank, P, uid)
+            row0, nrows = dist.slab_range(n, rank, P)
+            # global row pointers of the slab + the full col / value arrays (upload_csr_slab reads them from rowptr_local[0] on)
+            op = emu.SparseGenMatProd.from_csr_slab(n, row0, rp[row0:row0 + nrows + 1], ci, v, comm=comm)
+            if kind == "sym":
+                e = emu.SymEigsSolver(op, k, m)
+                e.init()
+                nconv = e.compute(emu.SortRule.LargestAlge)
+                out[rank] = dict(nconv=nconv, ev=e.eigenvalues(), nops=e.num_operations(), niter=e.num_iterations(), U=e.eigenvectors(local=True).copy(),
+                                 Ufull=e.eigenvectors().copy(), row0=row0, nrows=nrows, layout=op.spmv_layout())
+            else:
+                g = emu.GenEigsSolver(op, k, m)
+                g.init()
+                nconv = g.compute(emu.SortRule.LargestMagn, 300)
+                out[rank] = dict(nconv=nconv, ev=g.eigenvalues(), nops=g.num_operations())
+        except BaseException as ex:  # noqa: BLE001
+            import traceback
+
+            errs.append((rank, traceback.format_exc()))
+
+    with X.env(**(fmt_env or {})):
+        ts = [threading.Thread(target=worker, args=(r,)) for r in range(P)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(timeout=900)
+    assert not errs, errs
+    assert all(o is not None for o in out), "a rank did not finish (deadlocked collective?)"
+    return out
+
+
+@pytest.mark.parametrize("P,fmt", [(2, "csr"), (3, "csr"), (2, "sell")])
+def test_emu_row_sharded_sym_solver(emu, P, fmt):
+    # SURVEY §8e: 1-D row partition, all-gather of the SpMV operand in chunks, all-reduce of the dot products; every rank must run the
+    # same iteration (identical operation counts), reproduce the single-rank eigenvalues, and hold its rows of the eigenvectors
+    from spectra_b200_emu import synth
+
+    n, k, m = 701, 4, 12
+    rp, ci, v = synth.csr(n, 12, 3, True)
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    fmt_env = dict(SB200_SPMV_FORMAT="sell", SB200_SELL_MAX_FILL=100) if fmt == "sell" else dict(SB200_SPMV_FORMAT="csr")
+    res = _sharded_solve(emu, n, P, rp, ci, v, k, m, "sym", fmt_env)
+    ref = O.sym_eigs(O.Csr.adopt(n, rp, ci, v), k, m, O.LargestAlge, want_vectors=False)
+    for r, o in enumerate(res):
+        assert o["layout"]["format"] == fmt
+        assert o["nconv"] == k and o["nops"] == res[0]["nops"] and o["niter"] == res[0]["niter"]
+        assert np.array_equal(o["ev"], res[0]["ev"])  # bitwise identical across ranks (deterministic collectives + redundant restart kernel)
+        assert np.abs(o["ev"] - ref.eigenvalues).max() <= 1e-10 * np.abs(ref.eigenvalues).max()
+        assert np.array_equal(o["Ufull"][o["row0"]:o["row0"] + o["nrows"]], o["U"])
+    U = res[0]["Ufull"]
+    assert np.abs(A @ U - U * res[0]["ev"]).max() <= 1e-9
+    assert res[0]["nops"] == ref.nops
+
+
+def test_emu_row_sharded_gen_solver(emu):
+    from spectra_b200_emu import synth
+
+    n, k, m = 500, 3, 12
+    rp, ci, v = synth.csr(n, 12, 4, False)
+    res = _sharded_solve(emu, n, 2, rp, ci, v, k, m, "gen")
+    ref = O.gen_eigs(O.Csr.adopt(n, rp, ci, v), k, m, O.LargestMagn, 300)
+    assert res[0]["nconv"] == k and res[1]["nops"] == res[0]["nops"] == ref.nops
+    assert np.array_equal(res[0]["ev"], res[1]["ev"])
+    assert np.abs(np.sort_complex(res[0]["ev"]) - np.sort_complex(ref.eigenvalues)).max() <= 1e-9 * np.abs(ref.eigenvalues).max()

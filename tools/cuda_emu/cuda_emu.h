@@ -24,6 +24,7 @@
 #include <chrono>
 #include <cmath>
 #include <functional>
+#include <mutex>
 #include <vector>
 
 #define __CUDACC__ 1
@@ -99,7 +100,10 @@ struct State
     int64_t launches = 0;
     bool reverse_order = [] { const char* e = getenv("CUDA_EMU_ORDER"); return e && e[0] == 'r'; }();
 };
-inline State g;
+// One State per OS thread: the ranks of an emulated multi-GPU run are threads of one process (emu_comm.cpp).  Kernel launches of
+// different ranks are serialised by launch_mutex because `__shared__` variables are process-wide statics.
+inline thread_local State g;
+inline std::mutex launch_mutex;
 
 constexpr size_t kStackBytes = 256 * 1024;
 
@@ -254,6 +258,7 @@ inline void run_cta(const std::function<void()>& body, const Launch& L)
 
 inline void launch_impl(const Launch& L, const std::function<void()>& body)
 {
+    std::lock_guard<std::mutex> lock(launch_mutex);
     g.launches++;
     // dynamic shared memory: 128-byte aligned, NaN-filled (like device memory here), followed by a guard zone that must stay intact
     constexpr size_t kGuard = 4096;

@@ -21,7 +21,7 @@ CSRC = os.path.join(ROOT, "spectra_b200", "csrc")
 OUT = os.path.join(ROOT, "tests", "_emu")
 SRC_OUT = os.path.join(OUT, "src")
 LIB = os.path.join(OUT, "libspectra_b200_emu.so")
-SKIP = {"gemm_dmma.cu"}
+SKIP = {"gemm_dmma.cu", "comm.cu"}
 CXX = os.environ.get("CXX", "g++")
 CXXFLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-DSB200_EMU", "-w", f"-I{HERE}", f"-I{CSRC}"]
 
@@ -33,6 +33,105 @@ void launch_compress_dmma(const double* V, int64_t ldv, int64_t nrows, int m, co
                           double* red_out, const RedScratch& rs, cudaStream_t stream)
 {
     launch_compress_fma(V, ldv, nrows, m, Q, kk, Vout, ldo, f, H, red_out, rs, stream);
+}
+}  // namespace sb200
+
+// ---- emulation of comm.cu (NCCL binding): the ranks of a communicator are OS threads of this process -------------------------
+// Collectives rendezvous on a shared "world" keyed by the 128-byte unique id: publish the send pointer, barrier, every rank computes its
+// result from all ranks' buffers in rank order (so results are bitwise identical on every rank, like NCCL's), barrier, write back.
+#include <condition_variable>
+#include <cstring>
+#include <map>
+#include <memory>
+#include "host.h"
+namespace sb200 {
+namespace {
+struct EmuWorld
+{
+    int nranks = 0, arrived = 0, gen = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<const double*> send;
+    void barrier()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        const int my = gen;
+        if (++arrived == nranks)
+        {
+            arrived = 0;
+            gen++;
+            cv.notify_all();
+        }
+        else
+            cv.wait(lk, [&] { return gen != my; });
+    }
+};
+std::mutex g_worlds_mu;
+std::map<uint64_t, std::shared_ptr<EmuWorld>> g_worlds;
+uint64_t g_next_id = 1;
+struct EmuComm
+{
+    std::shared_ptr<EmuWorld> w;
+};
+EmuWorld& world_of(sb200_comm* c) { return *static_cast<EmuComm*>(c->nccl)->w; }
+}  // namespace
+
+void nccl_unique_id(void* id128)
+{
+    std::lock_guard<std::mutex> lk(g_worlds_mu);
+    memset(id128, 0, 128);
+    const uint64_t id = g_next_id++;
+    memcpy(id128, &id, sizeof(id));
+}
+void nccl_comm_init(sb200_comm* c, const void* id128)
+{
+    uint64_t id = 0;
+    memcpy(&id, id128, sizeof(id));
+    std::lock_guard<std::mutex> lk(g_worlds_mu);
+    std::shared_ptr<EmuWorld>& w = g_worlds[id];
+    if (!w)
+    {
+        w = std::make_shared<EmuWorld>();
+        w->nranks = c->nranks;
+        w->send.assign((size_t) c->nranks, nullptr);
+    }
+    SB200_REQUIRE(w->nranks == c->nranks, SB200_NCCL, "emulated communicator: rank count mismatch");
+    c->nccl = new EmuComm{w};
+}
+void nccl_comm_destroy(sb200_comm* c)
+{
+    delete static_cast<EmuComm*>(c->nccl);
+    c->nccl = nullptr;
+}
+static void allreduce(sb200_comm* c, double* buf, size_t count, bool is_max)
+{
+    EmuWorld& w = world_of(c);
+    w.send[(size_t) c->rank] = buf;
+    w.barrier();
+    std::vector<double> tmp(count);
+    for (size_t i = 0; i < count; i++)
+    {
+        double a = w.send[0][i];
+        for (int r = 1; r < w.nranks; r++)
+            a = is_max ? std::max(a, w.send[(size_t) r][i]) : a + w.send[(size_t) r][i];
+        tmp[i] = a;
+    }
+    w.barrier();
+    memcpy(buf, tmp.data(), sizeof(double) * count);
+    w.barrier();
+}
+void nccl_allreduce_sum(sb200_comm* c, double* buf, size_t count, cudaStream_t) { allreduce(c, buf, count, false); }
+void nccl_allreduce_max(sb200_comm* c, double* buf, size_t count, cudaStream_t) { allreduce(c, buf, count, true); }
+void nccl_allgather(sb200_comm* c, const double* send, double* recv, size_t count_per_rank, cudaStream_t)
+{
+    EmuWorld& w = world_of(c);
+    w.send[(size_t) c->rank] = send;
+    w.barrier();
+    // send may alias a slice of recv on the calling rank only; other ranks' send buffers are disjoint from this recv
+    for (int r = 0; r < w.nranks; r++)
+        if (w.send[(size_t) r] != recv + (size_t) r * count_per_rank)
+            memmove(recv + (size_t) r * count_per_rank, w.send[(size_t) r], sizeof(double) * count_per_rank);
+    w.barrier();
 }
 }  // namespace sb200
 
