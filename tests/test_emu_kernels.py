@@ -71,7 +71,16 @@ def test_emu_sell_fused_step_factorization(emu, threads):
 
 
 def test_emu_sell_solver(emu):
-    X.test_sell_solver_matches_oracle(emu, "sym")
+    A = O.gen_sparse_data(300, 0.03)
+    with X.env(SB200_SPMV_FORMAT="sell", SB200_SELL_MAX_FILL=100):
+        ops = emu.SparseSymMatProd(A)
+    assert ops.spmv_layout()["format"] == "sell"
+    e = emu.SymEigsSolver(ops, 8, 24)
+    e.init()
+    assert e.compute(emu.SortRule.LargestAlge) == 8
+    r = O.sym_eigs(O.Csr.from_scipy(A, "lower"), 8, 24, O.LargestAlge)
+    assert np.abs(e.eigenvalues() - r.eigenvalues).max() <= 1e-10 * np.abs(r.eigenvalues).max()
+    assert e.num_operations() == r.nops
     # a nonsymmetric operator through the sliced Arnoldi step head
     A = O.gen_sparse_data(100, 0.1)
     with X.env(SB200_SPMV_FORMAT="sell", SB200_SELL_MAX_FILL=100):
@@ -175,10 +184,12 @@ def _sharded_solve(emu, n, P, rp, ci, v, k, m, kind="sym", fmt_env=None):
                 out[rank] = dict(nconv=nconv, ev=e.eigenvalues(), nops=e.num_operations(), niter=e.num_iterations(), U=e.eigenvectors(local=True).copy(),
                                  Ufull=e.eigenvectors().copy(), row0=row0, nrows=nrows, layout=op.spmv_layout())
             else:
+                # Arnoldi factorisation tier (test/Arnoldi.cpp) on the sharded operator: no restart, so the emulated run stays short
                 g = emu.GenEigsSolver(op, k, m)
                 g.init()
-                nconv = g.compute(emu.SortRule.LargestMagn, 300)
-                out[rank] = dict(nconv=nconv, ev=g.eigenvalues(), nops=g.num_operations())
+                g.factorize_from(1, m)
+                fz = g.factorization()
+                out[rank] = dict(V=fz["V"].copy(), H=fz["H"].copy(), f=fz["f"].copy(), beta=fz["beta"], nops=g.num_operations(), row0=row0, nrows=nrows)
         except BaseException as ex:  # noqa: BLE001
             import traceback
 
@@ -218,13 +229,21 @@ def test_emu_row_sharded_sym_solver(emu, P, fmt):
     assert res[0]["nops"] == ref.nops
 
 
-def test_emu_row_sharded_gen_solver(emu):
+def test_emu_row_sharded_arnoldi_factorization(emu):
     from spectra_b200_emu import synth
 
-    n, k, m = 500, 3, 12
+    n, k, m = 400, 3, 12
     rp, ci, v = synth.csr(n, 12, 4, False)
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
     res = _sharded_solve(emu, n, 2, rp, ci, v, k, m, "gen")
-    ref = O.gen_eigs(O.Csr.adopt(n, rp, ci, v), k, m, O.LargestMagn, 300)
-    assert res[0]["nconv"] == k and res[1]["nops"] == res[0]["nops"] == ref.nops
-    assert np.array_equal(res[0]["ev"], res[1]["ev"])
-    assert np.abs(np.sort_complex(res[0]["ev"]) - np.sort_complex(ref.eigenvalues)).max() <= 1e-9 * np.abs(ref.eigenvalues).max()
+    assert np.array_equal(res[0]["H"], res[1]["H"]) and res[0]["beta"] == res[1]["beta"] and res[0]["nops"] == res[1]["nops"]
+    V = np.vstack([o["V"] for o in res])
+    f = np.concatenate([o["f"] for o in res])
+    H = res[0]["H"]
+    E = A @ V - V @ H
+    E[:, -1] -= f
+    scale = max(1.0, np.abs(H).max())
+    assert np.abs(E).max() <= 1e-12 * scale                      # A V - V H = f e_m'   (test/Arnoldi.cpp:60-75)
+    assert np.abs(V.T @ V - np.eye(m)).max() <= 1e-12
+    ref = O.factorize(O.Csr.adopt(n, rp, ci, v), m, kind="arnoldi")
+    assert np.abs(H - ref["H"]).max() <= 1e-9 * scale
