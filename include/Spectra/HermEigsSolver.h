@@ -17,8 +17,7 @@ namespace Spectra {
 template <typename OpType = SparseHermMatProd<std::complex<double>>>
 class HermEigsSolver
 {
-    static_assert(std::is_base_of<b200::DeviceOpTag, OpType>::value,
-                  "HermEigsSolver: this build runs device-resident complex operators (SparseHermMatProd); user-defined complex host operators are not wired yet");
+    b200::OpBindingZ<OpType> m_bind;  // device-resident SparseHermMatProd, or a host-callback adapter for any other complex OpType
     sb200_sym_solver* m_s = nullptr;
     const OpType& m_op;  // the operator must outlive the solver (HermEigsBase.h:257-258)
     Index m_nev;
@@ -29,7 +28,7 @@ public:
     using RealVector = b200::Vector;
     using Matrix = b200::ComplexMatrix;
 
-    HermEigsSolver(OpType& op, Index nev, Index ncv) : m_op(op), m_nev(nev) { b200::check(sb200_herm_create(op.handle(), nev, ncv, &m_s)); }
+    HermEigsSolver(OpType& op, Index nev, Index ncv) : m_bind(op), m_op(op), m_nev(nev) { b200::check(sb200_herm_create(m_bind.handle(), nev, ncv, &m_s)); }
     HermEigsSolver(const HermEigsSolver&) = delete;
     HermEigsSolver& operator=(const HermEigsSolver&) = delete;
     ~HermEigsSolver()

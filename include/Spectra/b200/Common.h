@@ -327,6 +327,48 @@ public:
     sb200_op* handle() const { return m_op; }
 };
 
+// The same for user-defined COMPLEX operators (OpType::Scalar = std::complex<double>, HermEigsSolver): vectors cross the C ABI as
+// interleaved (re, im) doubles, which is the memory layout of std::complex<double>.
+template <typename OpType>
+class HostOpAdapterZ
+{
+    sb200_op* m_op = nullptr;
+    const OpType* m_user;
+    static void trampoline(const double* x, double* y, void* self)
+    {
+        static_cast<const OpType*>(self)->perform_op(reinterpret_cast<const std::complex<double>*>(x), reinterpret_cast<std::complex<double>*>(y));
+    }
+
+public:
+    explicit HostOpAdapterZ(const OpType& op) : m_user(&op)
+    {
+        static_assert(std::is_same<typename OpType::Scalar, std::complex<double>>::value, "complex user-defined operators must use Scalar = std::complex<double>");
+        check(sb200_op_create_callback_z(static_cast<int64_t>(op.rows()), &HostOpAdapterZ::trampoline, const_cast<OpType*>(m_user), &m_op));
+    }
+    HostOpAdapterZ(const HostOpAdapterZ&) = delete;
+    HostOpAdapterZ& operator=(const HostOpAdapterZ&) = delete;
+    ~HostOpAdapterZ()
+    {
+        if (m_op)
+            sb200_op_destroy(m_op);
+    }
+    sb200_op* handle() const { return m_op; }
+};
+template <typename OpType, bool IsDevice = std::is_base_of<DeviceOpTag, OpType>::value>
+struct OpBindingZ
+{
+    explicit OpBindingZ(OpType& op) : m_h(op.handle()) {}
+    sb200_op* handle() const { return m_h; }
+    sb200_op* m_h;
+};
+template <typename OpType>
+struct OpBindingZ<OpType, false>
+{
+    explicit OpBindingZ(OpType& op) : m_adapter(op) {}
+    sb200_op* handle() const { return m_adapter.handle(); }
+    HostOpAdapterZ<OpType> m_adapter;
+};
+
 // Picks the device handle of an operator: device-resident sparse wrappers expose it directly, anything else is wrapped.
 template <typename OpType, bool IsDevice = std::is_base_of<DeviceOpTag, OpType>::value>
 struct OpBinding

@@ -117,6 +117,9 @@ int sb200_op_create_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64
  * the product back.  Single-GPU only. */
 typedef void (*sb200_matvec_fn)(const double* x_in, double* y_out, void* user);
 int sb200_op_create_callback(int64_t n, sb200_matvec_fn fn, void* user, sb200_op** out);
+/* The same for a user-defined COMPLEX operator (OpType::Scalar = std::complex<double>, for sb200_herm_create): fn receives and fills
+ * interleaved (re, im) vectors of 2 n doubles. */
+int sb200_op_create_callback_z(int64_t n, sb200_matvec_fn fn, void* user, sb200_op** out);
 /* Complex Hermitian operator: replaces MatOp/SparseHermMatProd.h:21-89 (Scalar = std::complex<double>).  values_ri holds the
  * nnz complex values interleaved (re, im) -- the memory layout of std::complex<double> --, matrix_mode is SB200_HERM_LOWER /
  * SB200_HERM_UPPER (the Uplo template argument: only that triangle is read, mirrored conjugated, the diagonal taken as real) or

@@ -317,7 +317,10 @@ class UserOp:
     y = op(x) on numpy vectors, or an object with rows() and perform_op(x_in, y_out).  The Krylov iteration still
     runs on the GPU; every matrix operation round-trips one vector through pinned host memory."""
 
-    def __init__(self, op, n: int | None = None):
+    def __init__(self, op, n: int | None = None, complex_scalar: bool = False):
+        """complex_scalar=True: the operator works on complex128 vectors (Scalar = std::complex<double>, for HermEigsSolver)."""
+        dt = np.complex128 if complex_scalar else np.float64
+        self._dtype = dt
         if hasattr(op, "perform_op"):
             n = int(op.rows()) if n is None else int(n)
 
@@ -337,15 +340,19 @@ class UserOp:
         self._exc = None
         self.user = op
 
+        cw = 2 if complex_scalar else 1
+
         def tramp(xp, yp, _):
             try:
-                apply(np.ctypeslib.as_array(xp, shape=(n,)), np.ctypeslib.as_array(yp, shape=(n,)))
+                # complex vectors cross the boundary as interleaved (re, im) doubles: view them as complex128 without copying
+                apply(np.ctypeslib.as_array(xp, shape=(cw * n,)).view(dt), np.ctypeslib.as_array(yp, shape=(cw * n,)).view(dt))
             except BaseException as e:  # noqa: BLE001 - re-raised on the Python side after the C call returns
                 self._exc = e
 
         self._cb = _MATVEC_FN(tramp)  # must outlive the operator handle
         self.h = C.c_void_p()
-        _check(lib().sb200_op_create_callback(C.c_int64(n), self._cb, None, C.byref(self.h)))
+        create = lib().sb200_op_create_callback_z if complex_scalar else lib().sb200_op_create_callback
+        _check(create(C.c_int64(n), self._cb, None, C.byref(self.h)))
 
     def rows(self):
         return self.n
@@ -359,8 +366,8 @@ class UserOp:
             self.user.set_shift(sigma)
 
     def perform_op(self, x_in, y_out=None):
-        x = np.ascontiguousarray(x_in, dtype=np.float64)
-        y = y_out if y_out is not None else np.empty(self.n)
+        x = np.ascontiguousarray(x_in, dtype=self._dtype)
+        y = y_out if y_out is not None else np.empty(self.n, dtype=self._dtype)
         _check_op(self, lib().sb200_op_perform_op(self.h, _p(x), _p(y)))
         return y
 
@@ -589,7 +596,7 @@ class HermEigsSolver(SymEigsSolver):
         r = np.ascontiguousarray(init_resid, dtype=np.complex128) if init_resid is not None else None
         if r is not None and r.shape != (self.op.n,):
             raise InvalidArgument(1, "init_resid has the wrong length")
-        _check(lib().sb200_sym_init(self.h, _p(r)))
+        _check_op(self.op, lib().sb200_sym_init(self.h, _p(r)))
 
     def eigenvectors(self, nvec: int | None = None) -> np.ndarray:
         nvec = self.nev if nvec is None else int(nvec)

@@ -12,7 +12,7 @@ sb200_op* op_create_sparse(int64_t n, const void* outer, int outer_is_64, const 
                            sb200_comm* comm);
 sb200_op* op_create_csr_slab(int64_t n, int64_t row0, int64_t nrows, const int64_t* rowptr_local, const int32_t* col, const double* values, sb200_comm* comm);
 void op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev);
-sb200_op* op_create_callback(int64_t n, void (*fn)(const double*, double*, void*), void* user);
+sb200_op* op_create_callback(int64_t n, void (*fn)(const double*, double*, void*), void* user, bool is_complex);
 sb200_op* op_create_shift_solve(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values, int storage_order, int matrix_mode);
 void op_perform_op_host(sb200_op* op, const double* x_host, double* y_host);
 sb200_op* op_create_sparse_herm(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values_ri, int storage_order, int matrix_mode);
@@ -191,7 +191,14 @@ int sb200_op_create_callback(int64_t n, sb200_matvec_fn fn, void* user, sb200_op
 {
     ABI_TRY
     ABI_NONNULL(out);
-    *out = op_create_callback(n, fn, user);
+    *out = op_create_callback(n, fn, user, false);
+    ABI_CATCH
+}
+int sb200_op_create_callback_z(int64_t n, sb200_matvec_fn fn, void* user, sb200_op** out)
+{
+    ABI_TRY
+    ABI_NONNULL(out);
+    *out = op_create_callback(n, fn, user, true);
     ABI_CATCH
 }
 int sb200_op_create_shift_solve(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values, int storage_order, int matrix_mode,

@@ -204,11 +204,12 @@ sb200_op* op_create_sparse_herm(int64_t n, const void* outer, int outer_is_64, c
     return op.release();
 }
 
-sb200_op* op_create_callback(int64_t n, void (*fn)(const double*, double*, void*), void* user)
+// complex = true: the user's function works on interleaved complex vectors (2 n doubles), for HermEigsSolver
+sb200_op* op_create_callback(int64_t n, void (*fn)(const double*, double*, void*), void* user, bool is_complex)
 {
     device_info();
     SB200_REQUIRE(fn != nullptr, SB200_INVALID_ARGUMENT, "null operator callback");
-    SB200_REQUIRE(n >= 1 && n < (1LL << 31), SB200_INVALID_ARGUMENT, "matrix order out of range");
+    SB200_REQUIRE(n >= 1 && n < (1LL << (is_complex ? 30 : 31)), SB200_INVALID_ARGUMENT, "matrix order out of range");
     std::unique_ptr<sb200_op> op(new sb200_op());
     SB200_CUDA_CHECK(cudaStreamCreateWithFlags(&op->stream, cudaStreamNonBlocking));
     op->A.n = n;
@@ -217,8 +218,9 @@ sb200_op* op_create_callback(int64_t n, void (*fn)(const double*, double*, void*
     op->A.nnz = 0;
     op->cb = fn;
     op->cb_user = user;
-    op->hx.alloc((size_t) n);
-    op->hy.alloc((size_t) n);
+    op->cplx = is_complex;
+    op->hx.alloc((size_t) n * (is_complex ? 2 : 1));
+    op->hy.alloc((size_t) n * (is_complex ? 2 : 1));
     op->slab = n;
     op->plan.grid = 1;
     SB200_CUDA_CHECK(cudaEventCreate(&op->ev0));
@@ -229,7 +231,7 @@ sb200_op* op_create_callback(int64_t n, void (*fn)(const double*, double*, void*
 // y_dev = A * x_dev through the user's host function (device pointers in, device pointers out)
 void op_callback_device(sb200_op* op, const double* x_dev, double* y_dev)
 {
-    const int64_t n = op->A.n;
+    const int64_t n = op->A.n * (op->cplx ? 2 : 1);
     SB200_CUDA_CHECK(cudaMemcpyAsync(op->hx.get(), x_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, op->stream));
     SB200_CUDA_CHECK(cudaStreamSynchronize(op->stream));
     op->cb(op->hx.get(), op->hy.get(), op->cb_user);

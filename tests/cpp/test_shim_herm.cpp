@@ -112,8 +112,52 @@ static void run_case(int n, double prob, int k, int m)
     }
 }
 
+// user-defined complex operator (the OpType concept, SymEigsSolver.h:99-114, with Scalar = std::complex<double>):
+// A = D + u u^H with D = diag(1..n) real and a fixed complex u -- Hermitian, applied without forming the matrix
+struct RankOneUpdateOp
+{
+    using Scalar = cd;
+    int n;
+    std::vector<cd> u;
+    explicit RankOneUpdateOp(int n_) : n(n_), u(n_)
+    {
+        for (int i = 0; i < n; i++)
+            u[i] = cd(std::cos(0.7 * i), std::sin(1.3 * i)) / std::sqrt((double) n);
+    }
+    int rows() const { return n; }
+    int cols() const { return n; }
+    void perform_op(const cd* x, cd* y) const
+    {
+        cd dot = 0;
+        for (int i = 0; i < n; i++)
+            dot += std::conj(u[i]) * x[i];
+        for (int i = 0; i < n; i++)
+            y[i] = (double) (i + 1) * x[i] + u[i] * dot;
+    }
+};
+
 int main()
 {
+    {
+        RankOneUpdateOp op(40);
+        HermEigsSolver<RankOneUpdateOp> eigs(op, 4, 12);
+        eigs.init();
+        const Index nconv = eigs.compute(SortRule::LargestAlge);
+        CHECK(eigs.info() == CompInfo::Successful && nconv == 4);
+        const auto evals = eigs.eigenvalues();
+        const auto evecs = eigs.eigenvectors();
+        double err = 0.0;
+        std::vector<cd> y(40);
+        for (Index c = 0; c < evecs.cols(); c++)
+        {
+            op.perform_op(evecs.data() + c * 40, y.data());
+            for (int i = 0; i < 40; i++)
+                err = std::max(err, std::abs(y[i] - evecs(i, c) * evals[c]));
+        }
+        std::printf("user complex op D + uu^H: lambda_max=%.12f ||AU-UD||_inf=%.3e\n", evals[0], err);
+        CHECK(err <= 1e-9);
+        CHECK(evals[0] > 40.0 && evals[0] < 41.0 + 1e-9);  // interlacing: lambda_max(D) <= lambda_max(D + uu^H) <= lambda_max(D) + |u|^2
+    }
     run_case(10, 0.5, 3, 6);
     run_case(100, 0.1, 10, 20);
     bool threw = false;

@@ -103,3 +103,30 @@ def argument_checks(sb):
         raise AssertionError("zero residual accepted")
     except sb.InvalidArgument:
         pass
+
+
+def user_operator_case(sb, n=60):
+    # a user-defined complex operator (the OpType concept with Scalar = std::complex<double>) behind HermEigsSolver
+    rng = np.random.default_rng(5)
+    B = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    A = (B + B.conj().T) / 2
+
+    class MyOp:
+        def rows(self):
+            return n
+
+        def perform_op(self, x_in, y_out):
+            y_out[:] = A @ x_in
+
+    op = sb.UserOp(MyOp(), complex_scalar=True)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    assert np.abs(op.perform_op(x) - A @ x).max() <= 1e-13 * np.abs(A @ x).max()
+    eigs = sb.HermEigsSolver(op, 5, 20)
+    eigs.init()
+    assert eigs.compute(sb.SortRule.LargestAlge) == 5
+    ev, U = eigs.eigenvalues(), eigs.eigenvectors()
+    w = np.linalg.eigvalsh(A)[::-1][:5]
+    assert np.abs(ev - w).max() <= 1e-10 * np.abs(w).max()
+    assert np.abs(A @ U - U * ev).max() <= 1e-9
+    ref = OH.herm_eigs(lambda v: A @ v, n, 5, 20, O.LargestAlge)
+    assert eigs.num_operations() == ref.nops

@@ -220,6 +220,10 @@ def test_herm_argument_checks(gpu):
     HC.argument_checks(gpu)
 
 
+def test_herm_user_operator(gpu):
+    HC.user_operator_case(gpu)
+
+
 def test_herm_shim_reference_flow_on_gpu(gpu):
     # test/HermEigs.cpp's sparse flow through the C++ shim headers against the CUDA library
     import subprocess
