@@ -8,5 +8,5 @@ export SB200_SPMV_FORMAT=sell
 export QB_MAXIT=3 QB_NOPROF=1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/sell_launches.csv python tools/quick_bench.py 1e7 > gpurun_out/sell_quick.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:sell_ -c 6 -o gpurun_out/sell_full python tools/quick_bench.py 1e7 > gpurun_out/sell_full.log 2>&1
-ncu -i gpurun_out/sell_full.ncu-rep --page raw --csv > gpurun_out/sell_full_raw.csv 2>/dev/null
-python tools/ncu_summary.py gpurun_out/sell_full_raw.csv > gpurun_out/sell_full_summary.md 2>&1 || true
+python tools/ncu_summary.py launches gpurun_out/sell_launches.csv gpurun_out/sell_launches.md || true
+python tools/ncu_summary.py full gpurun_out/sell_full.ncu-rep gpurun_out/sell_full.md || true
