@@ -143,7 +143,8 @@ struct SpmvPlan
     int lanes = 8;  // lanes per row
     int grid = 0;
     int sell_threads = 0;  // > 0: the operand carries the sliced layout and the lane-per-row kernels run (CTA size)
-    int sell_grid = 0;
+    int sell_grid = 0;        // fused step kernel (bounded by the reduction scratch)
+    int sell_grid_plain = 0;  // plain / accumulate kernels: one CTA per window
 };
 SpmvPlan make_spmv_plan(const DeviceCsr& A);
 // column blocks needed so that one slice of the gathered operand stays L2-resident (env SB200_XSLICE_MB)

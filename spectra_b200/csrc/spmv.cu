@@ -199,8 +199,9 @@ __global__ void __launch_bounds__(kSpmvBlock, SB200_STEP_MINBLOCKS)
 // ---------------------------------------------------------------------------------------------
 constexpr int sell_min_blocks(int threads) { return 1536 / threads; }  // 48 resident warps per SM (32 at 1024 threads)
 
-// Row sums of window `win` into s_y (natural row order inside the window).  Warp w handles slices w, w + WARPS, ...: the slices of
-// a window are sorted by length, so every warp gets long and short ones.
+// Row sums of window `win` into s_y (natural row order inside the window).  The slices of a window are sorted by length (longest
+// first); warp w takes them in serpentine order -- w, 2 WARPS - 1 - w, 2 WARPS + w, ... -- so that every warp of the CTA gets about
+// the same number of steps before the barrier (w, w + WARPS, ... would give warp 0 the longest slice of every group).
 template <int THREADS>
 __device__ __forceinline__ void sell_window_dot(const int* __restrict__ slice_ptr, const int* __restrict__ scol, const double* __restrict__ sval,
                                                 const unsigned short* __restrict__ perm, const double* __restrict__ x, int64_t win, double* s_y,
@@ -213,7 +214,7 @@ __device__ __forceinline__ void sell_window_dot(const int* __restrict__ slice_pt
 #pragma unroll 1
     for (int q = 0; q < SPW / WARPS; q++)
     {
-        const int sl = q * WARPS + warp;
+        const int sl = (q & 1) ? (q + 1) * WARPS - 1 - warp : q * WARPS + warp;
         const int64_t s = win * SPW + sl;
         const int base = __ldg(slice_ptr + s);
         const int steps = (__ldg(slice_ptr + s + 1) - base) >> 5;
@@ -454,9 +455,9 @@ void launch_plain_block(const SpmvPlan& plan, const BlockView& b, int64_t nrows,
     {
         switch (plan.sell_threads)
         {
-            case 256: launch_sell_plain_t<256>(*b.sell, plan.sell_grid, nrows, x, y, accum, stream); break;
-            case 1024: launch_sell_plain_t<1024>(*b.sell, plan.sell_grid, nrows, x, y, accum, stream); break;
-            default: launch_sell_plain_t<512>(*b.sell, plan.sell_grid, nrows, x, y, accum, stream); break;
+            case 256: launch_sell_plain_t<256>(*b.sell, plan.sell_grid_plain, nrows, x, y, accum, stream); break;
+            case 1024: launch_sell_plain_t<1024>(*b.sell, plan.sell_grid_plain, nrows, x, y, accum, stream); break;
+            default: launch_sell_plain_t<512>(*b.sell, plan.sell_grid_plain, nrows, x, y, accum, stream); break;
         }
         return;
     }
@@ -537,7 +538,12 @@ SpmvPlan make_spmv_plan(const DeviceCsr& A)
             if (v == 256 || v == 512 || v == 1024)
                 p.sell_threads = v;
         }
-        p.sell_grid = (int) std::max<int64_t>(1, std::min<int64_t>(S0.nwin, (int64_t) sms * sell_min_blocks(p.sell_threads)));
+        // One CTA per window while the grid fits the reduction scratch of the fused step kernel (sms * 16 CTAs, FacBase::alloc_common):
+        // the hardware then balances the windows over the SMs as CTAs retire.  Larger operands use a persistent grid of resident
+        // CTAs that stride over the windows (>= 20 windows per CTA at that size, so the last round costs little).
+        const int64_t resident = (int64_t) sms * sell_min_blocks(p.sell_threads);
+        p.sell_grid = (int) std::max<int64_t>(1, (S0.nwin <= (int64_t) sms * 16) ? S0.nwin : resident);
+        p.sell_grid_plain = (int) std::max<int64_t>(1, std::min<int64_t>(S0.nwin, 1 << 30));  // no reduction: always one CTA per window
     }
     return p;
 }
