@@ -116,7 +116,7 @@ struct FacBase
         Q.alloc((size_t) m * m);
         S.alloc((size_t) 2 * m * m);
         ctl.alloc(1);
-        const int max_grid = device_info().sm_count * 16;
+        const int max_grid = reduction_max_grid(device_info().sm_count);  // 16 MB of partials
         partials.alloc((size_t) max_grid * kRedStride);
         ticket.alloc(1);
         ticket.zero(op->stream);

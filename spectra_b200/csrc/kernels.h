@@ -32,6 +32,10 @@ struct FacCtl
 };
 constexpr size_t kFacCtlStatusBytes = 64;
 
+// Largest grid a solver's reduction scratch serves: the persistent kernels use at most sm_count * 16 CTAs; the sliced-layout step
+// kernel runs one CTA per 1024-row window up to this bound (16384 windows = 16.7 M rows per rank) and turns persistent beyond it.
+inline int reduction_max_grid(int sm_count) { return sm_count * 16 > 16384 ? sm_count * 16 : 16384; }
+
 // Reduction scratch shared by all kernels of one solver (one stream => no overlap).
 struct RedScratch
 {

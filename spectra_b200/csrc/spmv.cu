@@ -538,12 +538,14 @@ SpmvPlan make_spmv_plan(const DeviceCsr& A)
             if (v == 256 || v == 512 || v == 1024)
                 p.sell_threads = v;
         }
-        // One CTA per window while the grid fits the reduction scratch of the fused step kernel (sms * 16 CTAs, FacBase::alloc_common):
+        // One CTA per window while the grid fits the reduction scratch of the fused step kernel (reduction_max_grid, FacBase::alloc_common):
         // the hardware then balances the windows over the SMs as CTAs retire.  Larger operands use a persistent grid of resident
         // CTAs that stride over the windows (>= 20 windows per CTA at that size, so the last round costs little).
         const int64_t resident = (int64_t) sms * sell_min_blocks(p.sell_threads);
-        p.sell_grid = (int) std::max<int64_t>(1, (S0.nwin <= (int64_t) sms * 16) ? S0.nwin : resident);
-        p.sell_grid_plain = (int) std::max<int64_t>(1, std::min<int64_t>(S0.nwin, 1 << 30));  // no reduction: always one CTA per window
+        const char* force = std::getenv("SB200_SELL_PERSISTENT");  // test / A-B knob: always use the persistent strided grid
+        const bool persistent = (force && force[0] == '1') || S0.nwin > (int64_t) reduction_max_grid(sms);
+        p.sell_grid = (int) std::max<int64_t>(1, persistent ? std::min<int64_t>(S0.nwin, resident) : S0.nwin);
+        p.sell_grid_plain = persistent && force ? p.sell_grid : (int) std::max<int64_t>(1, std::min<int64_t>(S0.nwin, 1 << 30));  // no reduction: one CTA per window
     }
     return p;
 }

@@ -70,6 +70,13 @@ def test_emu_sell_fused_step_factorization(emu, threads):
     X.test_sell_lanczos_factorization(emu, threads)
 
 
+def test_emu_sell_persistent_grid(emu):
+    # operands beyond 16384 windows per rank use a persistent grid that strides over the windows; forced here at a small size
+    with X.env(SB200_SELL_PERSISTENT=1):
+        X.test_sell_lanczos_factorization(emu, 512)
+        X.test_sell_spmv_matches_csr_and_scipy(emu, 256, 40_000, 0.0005)
+
+
 def test_emu_sell_solver(emu):
     A = O.gen_sparse_data(300, 0.03)
     with X.env(SB200_SPMV_FORMAT="sell", SB200_SELL_MAX_FILL=100):
