@@ -74,7 +74,7 @@ def test_emu_sell_persistent_grid(emu):
     # operands beyond 16384 windows per rank use a persistent grid that strides over the windows; forced here at a small size
     with X.env(SB200_SELL_PERSISTENT=1):
         X.test_sell_lanczos_factorization(emu, 512)
-        X.test_sell_spmv_matches_csr_and_scipy(emu, 256, 40_000, 0.0005)
+        X.test_sell_spmv_matches_csr_and_scipy(emu, 256, 13_000, 0.0008)  # 13 windows > 12 resident CTAs on the 2 emulated SMs
 
 
 def test_emu_sell_solver(emu):
