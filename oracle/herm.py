@@ -256,3 +256,54 @@ def herm_factorize(op, n, m, v0=None, mid=None):
     fac.factorize_from(1, mid)
     fac.factorize_from(mid, m)
     return dict(V=fac.V, H=fac.H, f=fac.f, beta=fac.beta, nops=fac.nops)
+
+
+def arnoldi_factorize_complex(op, n, m, v0=None, mid=None):
+    """Arnoldi<complex>::init + factorize_from(1, mid) + factorize_from(mid, m) (LinAlg/Arnoldi.h:136-195, 198-295), the complex case of
+    test/Arnoldi.cpp:19-85.  `op` maps a complex128 vector to A x for a general complex A."""
+    fac = _Lanczos(op, n, m)  # shares init / expand_basis / state with the Hermitian oracle
+    fac.init(simple_random_complex(0, n) if v0 is None else np.asarray(v0, dtype=np.complex128))
+    mid = m // 2 if mid is None else mid
+    beta_thresh = EPS * np.sqrt(n)
+
+    def factorize_from(from_k, to_m):
+        if to_m <= from_k:
+            return
+        fac.H[:, from_k:] = 0
+        fac.H[from_k:, :from_k] = 0
+        for i in range(from_k, to_m):
+            restart = False
+            if fac.beta < NEAR0:
+                fac.expand_basis(i, 2 * i)
+                restart = True
+            v = fac.f / fac.beta
+            fac.V[:, i] = v
+            fac.H[i, i - 1] = 0.0 if restart else fac.beta
+            w = fac.matvec(v)
+            Vs = fac.V[:, :i + 1]
+            h = Vs.conj().T @ w
+            fac.H[:i + 1, i] = h
+            fac.f = w - Vs @ h
+            fac.beta = float(np.linalg.norm(fac.f))
+            if fac.beta > 0.717 * np.linalg.norm(h):
+                continue
+            Vf = Vs.conj().T @ fac.f
+            err = np.abs(Vf).max()
+            count = 0
+            while count < 5 and err > EPS * fac.beta:
+                if fac.beta < beta_thresh:
+                    fac.f[:] = 0
+                    fac.beta = 0.0
+                    break
+                fac.f = fac.f - Vs @ Vf
+                fac.H[:i + 1, i] += Vf
+                fac.beta = float(np.linalg.norm(fac.f))
+                Vf = Vs.conj().T @ fac.f
+                err = np.abs(Vf).max()
+                count += 1
+                fac.reorth += 1
+        fac.k = to_m
+
+    factorize_from(1, mid)
+    factorize_from(mid, m)
+    return dict(V=fac.V, H=fac.H, f=fac.f, beta=fac.beta, nops=fac.nops)

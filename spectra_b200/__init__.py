@@ -638,8 +638,13 @@ class GenEigsSolver:
         self.h = C.c_void_p()
         _check(lib().sb200_gen_create(op.h, C.c_int64(nev), C.c_int64(ncv), C.byref(self.h)))
 
+    def _complex_op(self) -> bool:
+        """True for complex operators (SparseHermMatProd in 'general' mode, UserOp(complex_scalar=True)): only init() and the
+        factorisation tier run for them in this build (the complex restart kernels are not built yet)."""
+        return isinstance(self.op, SparseHermMatProd) or getattr(self.op, "_dtype", np.float64) == np.complex128
+
     def init(self, init_resid: np.ndarray | None = None):
-        r = np.ascontiguousarray(init_resid, dtype=np.float64) if init_resid is not None else None
+        r = np.ascontiguousarray(init_resid, dtype=np.complex128 if self._complex_op() else np.float64) if init_resid is not None else None
         if r is not None and r.shape != (self.op.n,):
             raise InvalidArgument(1, "init_resid has the wrong length")
         _check_op(self.op, lib().sb200_gen_init(self.h, _p(r)))
@@ -689,9 +694,10 @@ class GenEigsSolver:
 
     def factorization(self):
         n, m = self.op.nrows_local, min(self.ncv, self.op.n)
-        V = np.empty((n, m), order="F")
-        H = np.empty((m, m), order="F")
-        f = np.empty(n)
+        dt = np.complex128 if self._complex_op() else np.float64
+        V = np.empty((n, m), dtype=dt, order="F")
+        H = np.empty((m, m), dtype=dt, order="F")
+        f = np.empty(n, dtype=dt)
         beta, k = C.c_double(), C.c_int64()
         _check(lib().sb200_gen_get_factorization(self.h, _p(V), _p(H), _p(f), C.byref(beta), C.byref(k)))
         return dict(V=V, H=H, f=f, beta=beta.value, k=k.value)

@@ -67,6 +67,8 @@ struct FacBase
     int nev = 0, m = 0;
 
     DevBuf<double> V, f, w, t0, H, Q, S, X;
+    DevBuf<double> Hi;        // complex Arnoldi only: imaginary parts of the Hessenberg matrix (H holds the real parts)
+    bool complex_h = false;   // keep the imaginary parts of the projected matrix (general complex operator; Hermitian ones drop them)
     DevBuf<FacCtl> ctl;
     DevBuf<double> partials;
     DevBuf<unsigned int> ticket;
@@ -113,6 +115,8 @@ struct FacBase
         w.alloc((size_t) ld);
         t0.alloc((size_t) std::max<int64_t>(ld, n));
         H.alloc((size_t) m * m);
+        if (complex_h)
+            Hi.alloc((size_t) m * m);
         Q.alloc((size_t) m * m);
         S.alloc((size_t) 2 * m * m);
         ctl.alloc(1);
@@ -356,6 +360,8 @@ struct FacBase
         w.zero(stream());
         t0.zero(stream());
         H.zero(stream());
+        if (complex_h)
+            Hi.zero(stream());
         ctl.zero(stream());
         nmatop = 0;
         niter = 0;
@@ -383,10 +389,20 @@ struct FacBase
         spmv_plain(vfull, w.get());  // w = A * v
         const double h00 = reduce_scalar(VR_DOT, v, w.get());
         launch_set_scalar(H.get(), h00, stream());
-        launch_vec_axpy(w.get(), v, h00, f.get(), nloc, stream());  // f = w - v * H(0,0)
+        double h00_im = 0.0;
+        if (complex_h)
+        {
+            // H(0,0) = v^H w is genuinely complex for a general complex operator (Arnoldi.h:176-177)
+            h00_im = reduce_scalar(VR_CDOT_IM, v, w.get());
+            launch_set_scalar(Hi.get(), h00_im, stream());
+            launch_vec_caxpy(w.get(), v, h00, h00_im, f.get(), nloc, stream());
+            prof.launches++;
+        }
+        else
+            launch_vec_axpy(w.get(), v, h00, f.get(), nloc, stream());  // f = w - v * H(0,0)
         prof.launches += 2;
         const double fmax = reduce_scalar(is_cplx() ? VR_CMAXABS : VR_MAXABS, f.get(), nullptr);  // m_fac_f.cwiseAbs().maxCoeff()
-        if (fmax < kEps * std::fabs(h00))
+        if (fmax < kEps * std::hypot(h00, h00_im))
         {
             f.zero(stream());
             set_beta_host(0.0);
@@ -435,11 +451,25 @@ struct FacBase
         cudaStream_t st = stream();
         if (Vh && nloc > 0)
             SB200_CUDA_CHECK(cudaMemcpy2DAsync(Vh, sizeof(double) * nloc, V.get(), sizeof(double) * ld, sizeof(double) * nloc, m, cudaMemcpyDeviceToHost, st));
-        if (Hh)
+        std::vector<double> hre, him;
+        if (Hh && complex_h)
+        {
+            // complex Arnoldi: Hh receives m x m interleaved (re, im) values
+            hre.resize((size_t) m * m);
+            him.resize((size_t) m * m);
+            SB200_CUDA_CHECK(cudaMemcpyAsync(hre.data(), H.get(), sizeof(double) * m * m, cudaMemcpyDeviceToHost, st));
+            SB200_CUDA_CHECK(cudaMemcpyAsync(him.data(), Hi.get(), sizeof(double) * m * m, cudaMemcpyDeviceToHost, st));
+        }
+        else if (Hh)
             SB200_CUDA_CHECK(cudaMemcpyAsync(Hh, H.get(), sizeof(double) * m * m, cudaMemcpyDeviceToHost, st));
         if (fh && nloc > 0)
             SB200_CUDA_CHECK(cudaMemcpyAsync(fh, f.get(), sizeof(double) * nloc, cudaMemcpyDeviceToHost, st));
         SB200_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (size_t q = 0; q < hre.size(); q++)
+        {
+            Hh[2 * q] = hre[q];
+            Hh[2 * q + 1] = him[q];
+        }
         if (beta)
             *beta = h_beta;
         if (kk)

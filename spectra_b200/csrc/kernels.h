@@ -190,7 +190,8 @@ void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, in
 void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int first, cudaStream_t stream, int predicated = 0, bool cplx = false);
 // Arnoldi flavours (Arnoldi.h:242-290): stage 0 = after h = V^T w (copies h into H(:,i) and c),
 // stage 1 = after f = w - V h (DGKS test), stage 2 = after a correction pass.
-void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated = 0);
+// Hi != nullptr: complex Arnoldi (Hermitian-path layout of ctl->red / ctl->c); H receives the real and Hi the imaginary parts of H(:, i)
+void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated = 0, double* Hi = nullptr);
 
 // ---- restart GEMM (panel.cu) ------------------------------------------------------------------------
 // Vout[:, c] = sum_j V[:, j] * Q[j, c]  for c < kk  (Q: m x m column-major on device, ldq = m).
@@ -217,6 +218,7 @@ enum VecReduceOp
 void launch_vec_reduce(int op, const double* x, const double* y, int64_t n, double* out, const RedScratch& rs, cudaStream_t stream);
 void launch_vec_scale(const double* x, double s, int divide, double* y, int64_t n, cudaStream_t stream);          // y = x*s or x/s
 void launch_vec_axpy(const double* w, const double* v, double a, double* f, int64_t n, cudaStream_t stream);      // f = w - a*v
+void launch_vec_caxpy(const double* w, const double* v, double ar, double ai, double* f, int64_t n, cudaStream_t stream);  // complex f = w - (ar + i ai) v, n doubles
 void launch_set_beta(FacCtl* ctl, const double* red_slot, int take_sqrt, cudaStream_t stream);                      // ctl->beta = (sqrt) *red_slot
 void launch_set_scalar(double* dst, double v, cudaStream_t stream);
 // Host-operator path (user OpType): the two halves of the fused step head around the host call.

@@ -418,6 +418,81 @@ __global__ void arnoldi_decide_kernel(FacCtl* ctl, double* H, int m, double beta
     }
 }
 
+// Complex flavour of arnoldi_decide_kernel (Arnoldi.h:242-290 with Scalar = std::complex<double>): ctl->red / ctl->c carry Re at [k]
+// and Im at [kRedNrm + 1 + k]; column i of the Hessenberg matrix is kept as H (real parts) and Hi (imaginary parts).
+__global__ void arnoldi_decide_z_kernel(FacCtl* ctl, double* H, double* Hi, int m, double beta_thresh, int stage, int predicated)
+{
+    if (predicated && ctl->need_corr == 0)
+        return;
+    const int lane = threadIdx.x;
+    const int i = ctl->i, j = i + 1;
+    if (stage == 0)
+    {
+        for (int k = lane; k < j; k += 32)
+        {
+            const double hr = ctl->red[k], hi = ctl->red[kRedNrm + 1 + k];
+            H[k + (int64_t) i * m] = hr;
+            Hi[k + (int64_t) i * m] = hi;
+            ctl->c[k] = hr;
+            ctl->c[kRedNrm + 1 + k] = hi;
+        }
+        if (lane == 0)
+        {
+            double s = 0.0;
+            for (int k = 0; k < j; k++)
+                s += ctl->red[k] * ctl->red[k] + ctl->red[kRedNrm + 1 + k] * ctl->red[kRedNrm + 1 + k];
+            ctl->hnorm = sqrt(s);  // ||h||   (Arnoldi.h:257)
+        }
+        return;
+    }
+    int count = ctl->count;
+    if (stage == 2)
+    {
+        for (int k = lane; k < j; k += 32)
+        {
+            H[k + (int64_t) i * m] += ctl->c[k];  // h += Vf   (Arnoldi.h:283)
+            Hi[k + (int64_t) i * m] += ctl->c[kRedNrm + 1 + k];
+        }
+        count += 1;
+    }
+    double beta = sqrt(ctl->red[kRedNrm]);
+    double mx = 0.0;
+    for (int k = lane; k < j; k += 32)
+        mx = fmax(mx, hypot(ctl->red[k], ctl->red[kRedNrm + 1 + k]));
+    const double ortho_err = warp_max(mx);
+    __syncwarp();
+    int need, skip = 0, zeroed = 0;
+    if (stage == 1 && beta > 0.717 * ctl->hnorm)  // DGKS   (Arnoldi.h:257)
+    {
+        skip = 1;
+        need = 0;
+    }
+    else
+    {
+        for (int k = lane; k < j; k += 32)
+        {
+            ctl->c[k] = ctl->red[k];
+            ctl->c[kRedNrm + 1 + k] = ctl->red[kRedNrm + 1 + k];
+        }
+        need = (count < 5) && (ortho_err > kEps * beta);  // Arnoldi.h:266
+        if (need && beta < beta_thresh)                    // Arnoldi.h:273-278
+        {
+            zeroed = 1;
+            beta = 0.0;
+            need = 0;
+        }
+    }
+    if (lane == 0)
+    {
+        ctl->beta = beta;
+        ctl->ortho_err = ortho_err;
+        ctl->count = count;
+        ctl->need_corr = need;
+        ctl->f_zeroed = zeroed;
+        ctl->dgks_skip = skip;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Restart GEMM: one thread per row, row of V in registers (MP = padded panel width), Q in smem.
 // ---------------------------------------------------------------------------------------------
@@ -535,9 +610,12 @@ void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, in
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated)
+void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated, double* Hi)
 {
-    arnoldi_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage, predicated);
+    if (Hi)
+        arnoldi_decide_z_kernel<<<1, 32, 0, stream>>>(ctl, H, Hi, m, beta_thresh, stage, predicated);
+    else
+        arnoldi_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage, predicated);
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 

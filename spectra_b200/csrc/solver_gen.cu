@@ -56,9 +56,12 @@ struct sb200_gen_solver : public FacBase
         if (from_k > k)
             throw Error(SB200_INVALID_ARGUMENT, "Arnoldi: from_k (= " + std::to_string(from_k) + ") is larger than the current subspace dimension (= " +
                                                     std::to_string(k) + ")");
-        const double beta_thresh = kEps * std::sqrt(double(n));
+        const double beta_thresh = kEps * std::sqrt(double(n / cw));  // m_n counts scalars
         launch_trim_h(H.get(), m, (int) from_k, stream());
+        if (complex_h)
+            launch_trim_h(Hi.get(), m, (int) from_k, stream());
         prof.launches++;
+        double* hi = complex_h ? Hi.get() : nullptr;
 
         for (int i = (int) from_k; i <= (int) to_m - 1; i++)
         {
@@ -74,14 +77,14 @@ struct sb200_gen_solver : public FacBase
             const int j = i + 1;
             // h = V^T w  (:251)
             panel(PANEL_DOT, j, w.get(), nullptr, nullptr);
-            launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream());
+            launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 0, hi);
             // f = w - V h, beta, and V^T f for the DGKS test in the same pass  (:254-262)
             panel(PANEL_CORR, j, w.get(), f.get(), ctl.get()->c);
-            launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream());
+            launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream(), 0, hi);
             prof.launches += 2;
             // correction passes (:266-290); the first one is enqueued speculatively (device-side predicate)
             panel(PANEL_CORR, j, f.get(), f.get(), ctl.get()->c, &ctl.get()->need_corr);
-            launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 2, stream(), 1);
+            launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 2, stream(), 1, hi);
             prof.launches++;
             const FacCtl* st = read_status();
             if (st->count == 0)
@@ -89,7 +92,7 @@ struct sb200_gen_solver : public FacBase
             while (st->need_corr)
             {
                 panel(PANEL_CORR, j, f.get(), f.get(), ctl.get()->c);  // (:281-287)
-                launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 2, stream());
+                launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 2, stream(), 0, hi);
                 prof.launches++;
                 st = read_status();
             }
@@ -133,6 +136,10 @@ struct sb200_gen_solver : public FacBase
     // ---- GenEigsBase::compute (GenEigsBase.h:501-525) ----
     int64_t compute(int selection, int64_t maxit, double tol, int sorting)
     {
+        // complex GenEigsSolver (GenEigsBase.h:111-140, UpperHessenbergEigen.h:328-454): the data-parallel part -- the complex Arnoldi
+        // factorisation -- runs (sb200_gen_factorize_from); the small dense complex restart kernels are not built yet
+        SB200_REQUIRE(!is_cplx(), SB200_LOGIC, "complex GenEigsSolver: the complex restart (Hessenberg QR / Schur) kernels are not implemented in this build; "
+                                               "only init() and the factorisation tier are available for complex operators");
         SB200_REQUIRE(initialised, SB200_LOGIC, "init() must be called before compute()");
         check_rule(selection, "unsupported selection rule");
         factorize_from(1, m);
@@ -261,7 +268,9 @@ sb200_gen_solver* gen_create(sb200_op* op, int64_t nev, int64_t ncv)
     if (ncv < nev + 2 || ncv > n)
         throw Error(SB200_INVALID_ARGUMENT, "ncv must satisfy nev + 2 <= ncv <= n, n is the size of matrix");
     SB200_REQUIRE(m <= kPanelMaxCols, SB200_INVALID_ARGUMENT, "this build supports ncv <= 64");
+    SB200_REQUIRE(!op->cplx || m < kPanelMaxCols, SB200_INVALID_ARGUMENT, "this build supports ncv <= 63 for complex operators");
     std::unique_ptr<sb200_gen_solver> s(new sb200_gen_solver());
+    s->complex_h = op->cplx;
     s->alloc_common(op, nev, m);
     s->ritz_val.alloc(2 * m);
     s->ritz_est.alloc(2 * m);

@@ -99,6 +99,17 @@ __global__ void vec_axpy_kernel(const double* __restrict__ w, const double* __re
         f[i] = w[i] - v[i] * a;  // f = w - v * H(0,0)   (Arnoldi.h:177)
 }
 
+// interleaved complex vectors of n doubles: f = w - v * (ar + i ai)   (Arnoldi.h:177 with a complex Scalar)
+__global__ void vec_caxpy_kernel(const double* __restrict__ w, const double* __restrict__ v, double ar, double ai, double* __restrict__ f, int64_t n)
+{
+    for (int64_t i = 2 * ((int64_t) blockIdx.x * blockDim.x + threadIdx.x); i + 1 < n; i += 2 * (int64_t) gridDim.x * blockDim.x)
+    {
+        const double vr = v[i], vi = v[i + 1];
+        f[i] = w[i] - (vr * ar - vi * ai);
+        f[i + 1] = w[i + 1] - (vr * ai + vi * ar);
+    }
+}
+
 __global__ void set_beta_kernel(FacCtl* ctl, const double* slot, int take_sqrt)
 {
     const double v = *slot;
@@ -193,6 +204,12 @@ void launch_vec_scale(const double* x, double s, int divide, double* y, int64_t 
 void launch_vec_axpy(const double* w, const double* v, double a, double* f, int64_t n, cudaStream_t stream)
 {
     vec_axpy_kernel<<<vec_grid(n), kVecBlock, 0, stream>>>(w, v, a, f, n);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_vec_caxpy(const double* w, const double* v, double ar, double ai, double* f, int64_t n, cudaStream_t stream)
+{
+    vec_caxpy_kernel<<<vec_grid(n / 2), kVecBlock, 0, stream>>>(w, v, ar, ai, f, n);
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -130,6 +130,10 @@ def test_emu_herm_user_operator(emu):
     HC.user_operator_case(emu)
 
 
+def test_emu_complex_arnoldi_factorization(emu_order):
+    HC.complex_arnoldi_factorization_case(emu_order)
+
+
 # ---------------------------------------------------------------- scheduling-order independence (race detection)
 def test_emu_order_dense_kernels(emu_order):
     # the small dense device kernels in both fiber orders; m = 61, 62, 64 of the Hessenberg eigen-decomposition exercise the

@@ -224,6 +224,11 @@ def test_herm_user_operator(gpu):
     HC.user_operator_case(gpu)
 
 
+def test_complex_arnoldi_factorization(gpu):
+    HC.complex_arnoldi_factorization_case(gpu)
+    HC.complex_arnoldi_factorization_case(gpu, n=20_000, m=40)
+
+
 def test_herm_shim_reference_flow_on_gpu(gpu):
     # test/HermEigs.cpp's sparse flow through the C++ shim headers against the CUDA library
     import subprocess
