@@ -149,6 +149,26 @@ int64_t oracle_gen_sparse_data_herm(int64_t n, double prob, int32_t* rows, int32
     return cnt;
 }
 
+// gen_sparse_data(n, prob) of test/ComplexEigs.cpp:20-39: same engine and visiting order; every accepted position draws re and im
+int64_t oracle_gen_sparse_data_complex(int64_t n, double prob, int32_t* rows, int32_t* cols, double* vals_ri)
+{
+    std::default_random_engine gen;
+    gen.seed(0);
+    std::uniform_real_distribution<double> distr(0.0, 1.0);
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t j = 0; j < n; j++)
+            if (distr(gen) < prob)
+            {
+                rows[cnt] = int32_t(i);
+                cols[cnt] = int32_t(j);
+                vals_ri[2 * cnt] = distr(gen) - 0.5;
+                vals_ri[2 * cnt + 1] = distr(gen) - 0.5;
+                cnt++;
+            }
+    return cnt;
+}
+
 // ---- small dense kernels --------------------------------------------------------------------
 void oracle_givens(double x, double y, double* r, double* c, double* s) { givens_rotation(x, y, *r, *c, *s); }
 

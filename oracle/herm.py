@@ -307,3 +307,237 @@ def arnoldi_factorize_complex(op, n, m, v0=None, mid=None):
     factorize_from(1, mid)
     factorize_from(mid, m)
     return dict(V=fac.V, H=fac.H, f=fac.f, beta=fac.beta, nops=fac.nops)
+
+
+# =============================================================================================================================
+# Complex GenEigsSolver: GenEigsBase.h with Scalar = std::complex<double>
+#   Givens<complex>::compute_rotation     LinAlg/Givens.h:218-335 (Algorithm 1 branches) + StableScaling :28-86, real Givens :166-205
+#   UpperHessenbergQR<complex>            LinAlg/UpperHessenbergQR.h:136-195 compute, :219-255 matrix_QtHQ (RQ + sI), :383-417 apply_YQ
+#   RestartArnoldi<complex>::run          GenEigsBase.h:122-139 (one complex shift at a time)
+#   restart / num_converged / nev_adjusted / retrieve_ritzpair / sort_ritzpair / compute   GenEigsBase.h:204-277, 280-404, 501-525
+#   compress_V                            LinAlg/Arnoldi.h:320-340 (complex Q)
+# The Ritz pairs of the m x m complex Hessenberg matrix come from LAPACK (numpy.linalg.eig) instead of a restatement of
+# Eigen::ComplexSchur (third party, UpperHessenbergEigen.h:328-454): same eigenvalues; eigenvectors normalised to unit 2-norm as in
+# :383-387, their phase is irrelevant to everything downstream (|last component| enters the convergence test, V*s the result).
+# =============================================================================================================================
+def _stable_scaling(a, b):
+    """StableScaling::run (Givens.h:28-62): a >= b > 0 -> (r, c, s) = (sqrt(a^2 + b^2), a / r, b / r), Taylor branch for tiny b / a"""
+    t = b / a
+    if t >= 0.1 * EPS ** 0.25:
+        r = float(np.hypot(a, b))
+        return r, a / r, b / r
+    t2 = t * t
+    c = 1.0 - t2 * (0.5 - t2 * (0.375 - 0.3125 * t2))
+    return a + 0.5 * b * t * (1.0 - t2 * (0.25 - 0.125 * t2)), c, t * c
+
+
+def _stable_scaling_complex(a, b):
+    """StableScaling::run(Complex a, Complex b, a2, tc1, tc2) (Givens.h:64-92): a2 = |a|^2, tc1 = sqrt(1 + t2), tc2 = 1 / tc1, t2 = |b|^2 / |a|^2"""
+    b2 = b.real * b.real + b.imag * b.imag
+    a2 = a.real * a.real + a.imag * a.imag
+    t2 = b2 / a2
+    if t2 >= 0.1 * np.sqrt(EPS):
+        return a2, float(np.sqrt(1.0 + t2)), float(np.sqrt(a2 / (a2 + b2)))
+    return a2, 1.0 + t2 * (0.5 - t2 * (0.125 - 0.0625 * t2)), 1.0 - t2 * (0.5 - t2 * (0.375 - 0.3125 * t2))
+
+
+def givens_real(x, y):
+    """Givens<double>::compute_rotation (Givens.h:166-205): c*x - s*y = r >= 0, s*x + c*y = 0"""
+    xs, ys = (1.0 if x >= 0 else -1.0), (1.0 if y >= 0 else -1.0)
+    xa, ya = abs(x), abs(y)
+    if xa > ya:
+        if ya == 0.0:
+            return xa, xs, 0.0
+        r, c, s = _stable_scaling(xa, ya)
+        return r, xs * c, -ys * s
+    if xa == 0.0 and ya == 0.0:
+        return 0.0, 1.0, 0.0
+    if xa == 0.0:
+        return ya, 0.0, -ys
+    r, s, c = _stable_scaling(ya, xa)
+    return r, xs * c, -ys * s
+
+
+def givens_complex(x, y):
+    """Givens<complex>::compute_rotation (Givens.h:218-335): real c, complex s, r with  c*x - s*y = r,  conj(s)*x + c*y = 0"""
+    if y == 0:
+        return x, 1.0, 0j
+    if x == 0:
+        rr, sr, si = givens_real(-y.real, -y.imag)
+        return complex(rr, 0.0), 0.0, complex(sr, si)
+    xn1, yn1 = abs(x.real) + abs(x.imag), abs(y.real) + abs(y.imag)
+    if xn1 > yn1:
+        x2, tc1, tc2 = _stable_scaling_complex(x, y)
+        c = tc2
+        return tc1 * x, c, -(c / x2) * (x * np.conj(y))
+    rho = np.sqrt(abs(x) ** 2 + abs(y) ** 2)
+    xnorm, zr, zi = givens_real(x.real, -x.imag)
+    z = complex(zr, zi)
+    return rho * z, xnorm / rho, -(z * np.conj(y)) / rho
+
+
+def hess_qr_complex(H, shift):
+    """UpperHessenbergQR<complex>: returns (RQ + shift*I, cos[], sin[]) of H - shift*I = QR"""
+    n = H.shape[0]
+    R = H.astype(np.complex128).copy()
+    R[np.diag_indices(n)] -= shift
+    cs, sn = np.zeros(n - 1), np.zeros(n - 1, dtype=np.complex128)
+    for i in range(n - 1):
+        R[i + 2:, i] = 0
+        r, c, s = givens_complex(complex(R[i, i]), complex(R[i + 1, i]))
+        cs[i], sn[i] = c, s
+        R[i, i], R[i + 1, i] = r, 0
+        t0, t1 = R[i, i + 1:].copy(), R[i + 1, i + 1:].copy()
+        R[i, i + 1:] = c * t0 - s * t1
+        R[i + 1, i + 1:] = np.conj(s) * t0 + c * t1
+    RQ = R
+    for i in range(n - 1):
+        c, s = cs[i], sn[i]
+        a, b = RQ[:i + 2, i].copy(), RQ[:i + 2, i + 1].copy()
+        RQ[:i + 2, i] = c * a - np.conj(s) * b
+        RQ[:i + 2, i + 1] = s * a + c * b
+    RQ[np.diag_indices(n)] += shift
+    return RQ, cs, sn
+
+
+def apply_yq_complex(Y, cs, sn):
+    for i in range(len(cs)):
+        c, s = cs[i], sn[i]
+        a, b = Y[:, i].copy(), Y[:, i + 1].copy()
+        Y[:, i] = c * a - np.conj(s) * b
+        Y[:, i + 1] = s * a + c * b
+
+
+def _sort_key_complex(rule, v):
+    from . import LargestImag, LargestReal, SmallestImag, SmallestReal  # noqa: PLC0415
+
+    return {LargestMagn: -np.abs(v), LargestReal: -v.real, LargestImag: -np.abs(v.imag), SmallestMagn: np.abs(v), SmallestReal: v.real,
+            SmallestImag: np.abs(v.imag)}[rule]
+
+
+@dataclass
+class GenResultZ:
+    nconv: int
+    niter: int
+    nops: int
+    info: int
+    eigenvalues: np.ndarray
+    eigenvectors: np.ndarray | None
+
+
+class _ArnoldiZ(_Lanczos):
+    def factorize_from(self, from_k, to_m):  # Arnoldi.h:198-295
+        if to_m <= from_k:
+            return
+        beta_thresh = EPS * np.sqrt(self.n)
+        self.H[:, from_k:] = 0
+        self.H[from_k:, :from_k] = 0
+        for i in range(from_k, to_m):
+            restart = False
+            if self.beta < NEAR0:
+                self.expand_basis(i, 2 * i)
+                restart = True
+            v = self.f / self.beta
+            self.V[:, i] = v
+            self.H[i, i - 1] = 0.0 if restart else self.beta
+            w = self.matvec(v)
+            Vs = self.V[:, :i + 1]
+            h = Vs.conj().T @ w
+            self.H[:i + 1, i] = h
+            self.f = w - Vs @ h
+            self.beta = float(np.linalg.norm(self.f))
+            if self.beta > 0.717 * np.linalg.norm(h):
+                continue
+            Vf = Vs.conj().T @ self.f
+            err = np.abs(Vf).max()
+            count = 0
+            while count < 5 and err > EPS * self.beta:
+                if self.beta < beta_thresh:
+                    self.f[:] = 0
+                    self.beta = 0.0
+                    break
+                self.f = self.f - Vs @ Vf
+                self.H[:i + 1, i] += Vf
+                self.beta = float(np.linalg.norm(self.f))
+                Vf = Vs.conj().T @ self.f
+                err = np.abs(Vf).max()
+                count += 1
+                self.reorth += 1
+        self.k = to_m
+
+
+def gen_eigs_complex(op, n, nev, ncv, selection=LargestMagn, maxit=1000, tol=1e-10, sorting=LargestMagn, init_resid=None) -> GenResultZ:
+    """GenEigsSolver<complex op>(op, nev, ncv): init() + compute(selection, maxit, tol, sorting)   (GenEigsBase.h:409-525)"""
+    if nev < 1 or nev > n - 2:
+        raise ValueError("nev must satisfy 1 <= nev <= n - 2, n is the size of matrix")
+    if ncv < nev + 2 or ncv > n:
+        raise ValueError("ncv must satisfy nev + 2 <= ncv <= n, n is the size of matrix")
+    m = ncv
+    fac = _ArnoldiZ(op, n, m)
+    fac.init(simple_random_complex(0, n) if init_resid is None else np.asarray(init_resid, dtype=np.complex128))
+    fac.factorize_from(1, m)
+    eps23 = EPS ** (2.0 / 3.0)
+
+    def retrieve():
+        ev, Z = np.linalg.eig(fac.H)
+        Z = Z / np.linalg.norm(Z, axis=0)
+        # UpperHessenbergEigen<complex>::sortEigenvalues (:389-404): ascending modulus, then the selection rule (stable here)
+        o = np.argsort(np.abs(ev), kind="stable")
+        ev, Z = ev[o], Z[:, o]
+        ind = np.argsort(_sort_key_complex(selection, ev), kind="stable")
+        return ev[ind], Z[m - 1, ind], Z[:, ind[:nev]]
+
+    ritz_val, ritz_est, ritz_vec = retrieve()
+    nconv, i = 0, 0
+    conv = np.zeros(nev, dtype=bool)
+    for i in range(maxit):
+        thresh = tol * np.maximum(np.abs(ritz_val[:nev]), eps23)
+        conv = np.abs(ritz_est[:nev]) * fac.beta < thresh
+        nconv = int(conv.sum())
+        if nconv >= nev:
+            break
+        # nev_adjusted (GenEigsBase.h:245-277)
+        k = nev + int(np.sum(np.abs(ritz_est[nev:]) < NEAR0))
+        k += min(nconv, (m - k) // 2)
+        if k == 1 and m >= 6:
+            k = m // 2
+        elif k == 1 and m > 3:
+            k = 2
+        k = min(k, m - 2)
+        if ritz_val[k - 1].imag != 0 and ritz_val[k - 1] == np.conj(ritz_val[k]):
+            k += 1
+        # restart(k): one complex shift per unwanted Ritz value, V <- V Q, expand again
+        if k < m:
+            Q = np.eye(m, dtype=np.complex128)
+            for j in range(k, m):
+                fac.H, cs, sn = hess_qr_complex(fac.H, ritz_val[j])
+                apply_yq_complex(Q, cs, sn)
+            Vs = np.empty((n, k + 1), dtype=np.complex128, order="F")
+            for c in range(k):
+                nnz = m - k + c + 1
+                Vs[:, c] = fac.V[:, :nnz] @ Q[:nnz, c]
+            Vs[:, k] = fac.V @ Q[:, k]
+            fac.V[:, :k + 1] = Vs
+            fac.f = fac.f * Q[m - 1, k - 1] + fac.V[:, k] * fac.H[k, k - 1]
+            fac.beta = float(np.linalg.norm(fac.f))
+            fac.k = k
+            fac.factorize_from(k, m)
+            ritz_val, ritz_est, ritz_vec = retrieve()
+    else:
+        i = maxit
+    niter = i + 1
+    ind = np.argsort(_sort_key_complex(sorting, ritz_val[:nev]), kind="stable")
+    rv, rvec, conv = ritz_val[:nev][ind], ritz_vec[:, ind], conv[ind]
+    return GenResultZ(int(min(nev, nconv)), niter, fac.nops, 0 if nconv >= nev else 2, rv[conv], fac.V @ rvec[:, conv])
+
+
+def gen_sparse_data_complex(n: int, prob: float = 0.5):
+    """test/ComplexEigs.cpp:20-39: general complex sparse matrix, same engine; real and imaginary part drawn for every entry.  CSC."""
+    import scipy.sparse as sp
+
+    r = np.empty(n * n, np.int32)
+    c = np.empty(n * n, np.int32)
+    v = np.empty(2 * n * n, np.float64)
+    cnt = lib().oracle_gen_sparse_data_complex(C.c_int64(n), C.c_double(prob), _p(r), _p(c), _p(v))
+    vals = v[0:2 * cnt:2] + 1j * v[1:2 * cnt:2]
+    return sp.csc_matrix((vals, (r[:cnt], c[:cnt])), shape=(n, n))

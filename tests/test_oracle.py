@@ -319,3 +319,48 @@ def test_oracle_against_golden_spectra(n):
     if r.nconv == kg:  # the reference tolerates non-convergence of this fixture at n = 10 (test/GenEigs.cpp:143-150)
         GC.check_gen_values(n, r.eigenvalues, kg)
     assert np.allclose(O.sym_eigs(O.Csr.from_dense(np.diag(np.arange(1.0, 11.0)), "lower"), 3, 6, O.LargestAlge).eigenvalues, GC.golden()["diag10"]["largest"], atol=1e-12)
+
+
+# ---------------------------------------------------------------- complex GenEigsSolver oracle (oracle/herm.py)
+def test_complex_givens_and_hessenberg_qr_oracle():
+    # test/Givens.cpp:64-99 (complex case): c x - s y = r, conj(s) x + c y = 0 to 1e-12; test/QR.cpp:177-189: Q unitary, Q^H H Q = RQ + sI
+    from oracle import herm as OH
+
+    rng = np.random.default_rng(0)
+    for _ in range(5000):
+        x = complex(*rng.standard_normal(2)) * 10 ** rng.uniform(-8, 8)
+        y = complex(*rng.standard_normal(2)) * 10 ** rng.uniform(-8, 8)
+        if rng.random() < 0.1:
+            x = 0j
+        if rng.random() < 0.1:
+            y = 0j
+        r, c, s = OH.givens_complex(x, y)
+        sc = max(abs(x), abs(y), 1e-300)
+        assert abs(c * x - s * y - r) <= 1e-12 * sc and abs(np.conj(s) * x + c * y) <= 1e-12 * sc
+        assert np.imag(c) == 0
+    for m in (2, 6, 30):
+        H = np.triu(rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m)), -1)
+        mu = complex(*rng.standard_normal(2))
+        RQ, cs, sn = OH.hess_qr_complex(H, mu)
+        Q = np.eye(m, dtype=complex)
+        OH.apply_yq_complex(Q, cs, sn)
+        assert np.abs(Q.conj().T @ Q - np.eye(m)).max() <= 1e-12
+        assert np.abs(Q.conj().T @ H @ Q - RQ).max() <= 1e-12 * max(1.0, np.abs(H).max()) * m
+        assert np.abs(np.tril(RQ, -2)).max() == 0.0
+
+
+@pytest.mark.parametrize("n", [10, 100, 1000])
+def test_complex_gen_oracle_reference_cases(n):
+    # test/ComplexEigs.cpp:112-192 (sparse cases, maxit = 300): ||AU - UD||_inf <= 1e-9; every value is an eigenvalue of the dense matrix
+    from oracle import herm as OH
+
+    prob, k, m = {10: (0.5, 3, 6), 100: (0.1, 10, 30), 1000: (0.01, 20, 50)}[n]
+    A = OH.gen_sparse_data_complex(n, prob).tocsr()
+    w = np.linalg.eigvals(A.toarray())
+    for sel in (O.LargestMagn, O.LargestReal, O.LargestImag, O.SmallestReal):
+        if n == 1000 and sel != O.LargestReal:
+            continue  # keep the CPU suite short: one rule at the largest size
+        r = OH.gen_eigs_complex(A.dot, n, k, m, sel, 300)
+        assert r.info == 0 and r.nconv == k
+        assert np.abs(A @ r.eigenvectors - r.eigenvectors * r.eigenvalues).max() <= 1e-9
+        assert max(np.abs(w - e).min() for e in r.eigenvalues) <= 1e-9 * np.abs(w).max()
