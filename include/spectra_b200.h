@@ -259,6 +259,11 @@ int sb200_dense_shifted_qr(int kind, int64_t m, const double* H, double shift, d
 int sb200_dense_double_shift_qr(int64_t m, const double* H, double s, double t, double* QtHQ, double* Q);
 /* UpperHessenbergEigen (UpperHessenbergEigen.h:32-321): interleaved complex evals (m) and evecs (m x m). */
 int sb200_dense_hess_eigen(int64_t m, const double* H, double* evals_ri, double* evecs_ri);
+/* Complex counterparts (interleaved (re, im) m x m matrices, m <= 63) for the complex GenEigsSolver:
+ * UpperHessenbergQR<std::complex<double>> (UpperHessenbergQR.h:136-255, 383-417 with the complex Givens of Givens.h:218-335) and
+ * UpperHessenbergEigen<std::complex<double>> (UpperHessenbergEigen.h:328-454; unit-norm eigenvectors, unsorted). */
+int sb200_dense_shifted_qr_z(int64_t m, const double* H_ri, double shift_re, double shift_im, double* QtHQ_ri, double* Q_ri);
+int sb200_dense_hess_eigen_z(int64_t m, const double* H_ri, double* evals_ri, double* evecs_ri);
 /* One restart "prepare" step of HermEigsBase (retrieve_ritzpair :205-224, num_converged :158-175,
  * nev_adjusted :178-202, shift loop :118-147) on a tridiagonal H and beta. */
 int sb200_dense_sym_restart(int64_t m, const double* H, double beta, int64_t nev, int selection, double tol, double* ritz_val, double* ritz_est,

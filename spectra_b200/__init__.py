@@ -756,6 +756,24 @@ class dense:
         return ev[0::2] + 1j * ev[1::2], (V[0::2] + 1j * V[1::2]).reshape((m, m), order="F")
 
     @staticmethod
+    def shifted_qr_z(H, shift):
+        """UpperHessenbergQR<complex>: (Q^H H Q, Q) for H - shift I = Q R, complex m x m (m <= 63)"""
+        H = np.asfortranarray(H, dtype=np.complex128)
+        m = H.shape[0]
+        D, Q = np.empty((m, m), dtype=np.complex128, order="F"), np.empty((m, m), dtype=np.complex128, order="F")
+        _check(lib().sb200_dense_shifted_qr_z(C.c_int64(m), _p(H), C.c_double(complex(shift).real), C.c_double(complex(shift).imag), _p(D), _p(Q)))
+        return D, Q
+
+    @staticmethod
+    def hess_eigen_z(H):
+        """UpperHessenbergEigen<complex>: eigenvalues (m) and unit-norm eigenvectors (m x m) of a complex Hessenberg matrix"""
+        H = np.asfortranarray(H, dtype=np.complex128)
+        m = H.shape[0]
+        ev, Z = np.empty(m, dtype=np.complex128), np.empty((m, m), dtype=np.complex128, order="F")
+        _check(lib().sb200_dense_hess_eigen_z(C.c_int64(m), _p(H), _p(ev), _p(Z)))
+        return ev, Z
+
+    @staticmethod
     def sym_restart(H, beta, nev, selection, tol):
         H = dense._cm(H)
         m = H.shape[0]

@@ -51,6 +51,9 @@ void gen_destroy(sb200_gen_solver* s);
 void dense_hess_qr_host(int64_t m, const double* H, double shift, double* QtHQ, double* Q);
 void dense_double_shift_qr_host(int64_t m, const double* H, double s, double t, double* QtHQ, double* Q);
 void dense_hess_eigen_host(int64_t m, const double* H, double* evals_ri, double* evecs_ri);
+// dense_gen_z.cu
+void dense_hess_qr_z_host(int64_t m, const double* H_ri, double mu_re, double mu_im, double* QtHQ_ri, double* Q_ri);
+void dense_hess_eigen_z_host(int64_t m, const double* H_ri, double* evals_ri, double* evecs_ri);
 }  // namespace sb200
 
 using namespace sb200;
@@ -640,6 +643,24 @@ int sb200_dense_hess_eigen(int64_t m, const double* H, double* evals_ri, double*
     ABI_NONNULL(evals_ri);
     ABI_NONNULL(evecs_ri);
     dense_hess_eigen_host(m, H, evals_ri, evecs_ri);
+    ABI_CATCH
+}
+int sb200_dense_shifted_qr_z(int64_t m, const double* H_ri, double shift_re, double shift_im, double* QtHQ_ri, double* Q_ri)
+{
+    ABI_TRY
+    ABI_NONNULL(H_ri);
+    ABI_NONNULL(QtHQ_ri);
+    ABI_NONNULL(Q_ri);
+    dense_hess_qr_z_host(m, H_ri, shift_re, shift_im, QtHQ_ri, Q_ri);
+    ABI_CATCH
+}
+int sb200_dense_hess_eigen_z(int64_t m, const double* H_ri, double* evals_ri, double* evecs_ri)
+{
+    ABI_TRY
+    ABI_NONNULL(H_ri);
+    ABI_NONNULL(evals_ri);
+    ABI_NONNULL(evecs_ri);
+    dense_hess_eigen_z_host(m, H_ri, evals_ri, evecs_ri);
     ABI_CATCH
 }
 int sb200_dense_sym_restart(int64_t m, const double* H, double beta, int64_t nev, int selection, double tol, double* ritz_val, double* ritz_est,
