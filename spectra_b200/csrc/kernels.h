@@ -219,6 +219,10 @@ void launch_vec_reduce(int op, const double* x, const double* y, int64_t n, doub
 void launch_vec_scale(const double* x, double s, int divide, double* y, int64_t n, cudaStream_t stream);          // y = x*s or x/s
 void launch_vec_axpy(const double* w, const double* v, double a, double* f, int64_t n, cudaStream_t stream);      // f = w - a*v
 void launch_vec_caxpy(const double* w, const double* v, double ar, double ai, double* f, int64_t n, cudaStream_t stream);  // complex f = w - (ar + i ai) v, n doubles
+// complex restart (complex Q): V(:, c) = A(:, c) + i B(:, c) for c < kk on interleaved data; f <- f Q(m-1,kk-2) + V(:,kk-1) H(kk-1,kk-2)
+void launch_zcombine(const double* A, const double* B, int64_t ldab, double* V, int64_t ldv, int64_t n, int kk, cudaStream_t stream);
+void launch_zf_update(double* f, const double* vk, const double* Qr, const double* Qi, const double* Hr, const double* Hi, int m, int kk, int64_t n,
+                      cudaStream_t stream);
 void launch_set_beta(FacCtl* ctl, const double* red_slot, int take_sqrt, cudaStream_t stream);                      // ctl->beta = (sqrt) *red_slot
 void launch_set_scalar(double* dst, double v, cudaStream_t stream);
 // Host-operator path (user OpType): the two halves of the fused step head around the host call.

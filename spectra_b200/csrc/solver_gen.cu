@@ -22,6 +22,10 @@ struct GenRestartOut
 };
 void launch_gen_restart(double* H, int m, int nev, const FacCtl* ctl, double beta, int use_beta, int selection, double tol, double* ritz_val_ri,
                         double* ritz_est_ri, double* ritz_vec_ri, int* ritz_conv, double* Q, GenRestartOut* out, int do_restart, cudaStream_t stream);
+// dense_gen_z.cu: the complex restart kernel (H and Q as separate real / imaginary m x m arrays)
+void launch_gen_restart_z(double* Hr, double* Hi, int m, int nev, const FacCtl* ctl, double beta, int use_beta, int selection, double tol, double* ritz_val_ri,
+                          double* ritz_est_ri, double* ritz_vec_ri, int* ritz_conv, double* Qr, double* Qi, GenRestartOut* out, int do_restart,
+                          cudaStream_t stream);
 
 }  // namespace sb200
 
@@ -108,8 +112,13 @@ struct sb200_gen_solver : public FacBase
     {
         {
             ScopedKernelTimer t(&prof, stream(), KC_SMALL);
-            launch_gen_restart(H.get(), m, nev, ctl.get(), 0.0, 0, selection, tol, ritz_val.get(), ritz_est.get(), ritz_vec.get(), ritz_conv.get(), Q.get(),
-                               rout.get(), do_restart, stream());
+            if (complex_h)
+                // complex Hessenberg matrix: Q comes back as Q (real parts) and S (imaginary parts; S is free between eigenvector calls)
+                launch_gen_restart_z(H.get(), Hi.get(), m, nev, ctl.get(), 0.0, 0, selection, tol, ritz_val.get(), ritz_est.get(), ritz_vec.get(), ritz_conv.get(),
+                                     Q.get(), S.get(), rout.get(), do_restart, stream());
+            else
+                launch_gen_restart(H.get(), m, nev, ctl.get(), 0.0, 0, selection, tol, ritz_val.get(), ritz_est.get(), ritz_vec.get(), ritz_conv.get(), Q.get(),
+                                   rout.get(), do_restart, stream());
         }
         SB200_CUDA_CHECK(cudaMemcpyAsync(hstat.get(), rout.get(), sizeof(GenRestartOut), cudaMemcpyDeviceToHost, stream()));
         SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
@@ -117,6 +126,32 @@ struct sb200_gen_solver : public FacBase
         if (o.info != 0)
             throw Error(SB200_RUNTIME, "UpperHessenbergSchur: Schur decomposition failed");
         return o;
+    }
+
+    // ---- Arnoldi::compress_V with a complex Q (Arnoldi.h:320-340): V Q = V Re(Q) + i V Im(Q) -- two runs of the real restart GEMM on
+    // the interleaved basis (its rows are the real and imaginary parts), one combine pass, then the complex residual update ----
+    DevBuf<double> Xz;
+    void compress_v_z(int knew)
+    {
+        const int kk = knew + 1;
+        stats.compress_launches++;
+        stats.compress_cols += kk;
+        if (Xz.n < (size_t) 2 * ld * m)
+            Xz.alloc((size_t) 2 * ld * m);
+        double* A = Xz.get();
+        double* B = Xz.get() + (size_t) ld * m;
+        {
+            ScopedKernelTimer t(&prof, stream(), KC_COMPRESS, 4);
+            launch_compress(V.get(), ld, nloc, m, Q.get(), kk, A, ld, nullptr, nullptr, nullptr, rs, stream());
+            launch_compress(V.get(), ld, nloc, m, S.get(), kk, B, ld, nullptr, nullptr, nullptr, rs, stream());
+            launch_zcombine(A, B, ld, V.get(), ld, nloc, kk, stream());
+            launch_zf_update(f.get(), V.get() + (int64_t) knew * ld, Q.get(), S.get(), H.get(), Hi.get(), m, kk, nloc, stream());
+        }
+        launch_vec_reduce(VR_SUMSQ, f.get(), nullptr, nloc, ctl.get()->red_a + 2, rs, stream());
+        launch_set_beta(ctl.get(), ctl.get()->red_a + 2, 1, stream());
+        prof.launches += 2;
+        h_beta = read_status()->beta;
+        k = knew;
     }
 
     static void check_rule(int rule, const char* what)
@@ -136,10 +171,8 @@ struct sb200_gen_solver : public FacBase
     // ---- GenEigsBase::compute (GenEigsBase.h:501-525) ----
     int64_t compute(int selection, int64_t maxit, double tol, int sorting)
     {
-        // complex GenEigsSolver (GenEigsBase.h:111-140, UpperHessenbergEigen.h:328-454): the data-parallel part -- the complex Arnoldi
-        // factorisation -- runs (sb200_gen_factorize_from); the small dense complex restart kernels are not built yet
-        SB200_REQUIRE(!is_cplx(), SB200_LOGIC, "complex GenEigsSolver: the complex restart (Hessenberg QR / Schur) kernels are not implemented in this build; "
-                                               "only init() and the factorisation tier are available for complex operators");
+        // complex operators: GenEigsBase with Scalar = std::complex<double> (:111-140 restart, :204-277, :280-404) -- the same loop with the
+        // complex restart kernel (dense_gen_z.cu) and the complex restart GEMM (compress_v_z)
         SB200_REQUIRE(initialised, SB200_LOGIC, "init() must be called before compute()");
         check_rule(selection, "unsupported selection rule");
         factorize_from(1, m);
@@ -153,7 +186,10 @@ struct sb200_gen_solver : public FacBase
             stats.restarts++;
             if (o.k < m)
             {
-                compress_v(o.k);
+                if (complex_h)
+                    compress_v_z(o.k);
+                else
+                    compress_v(o.k);
                 factorize_from(o.k, m);
             }
         }
@@ -320,6 +356,20 @@ int64_t gen_eigenvectors(sb200_gen_solver* s, int64_t nvec, double* out_ri)
         SB200_CUDA_CHECK(cudaMemcpy2DAsync(im.data(), sizeof(double) * nloc, s->X.get() + (size_t) nc * s->ld, sizeof(double) * s->ld, sizeof(double) * nloc, nc,
                                            cudaMemcpyDeviceToHost, st));
         SB200_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (s->complex_h)
+        {
+            // complex basis: `re` holds V Re(S) and `im` holds V Im(S), both as interleaved complex columns of n = 2 n_c doubles;
+            // X = V Re(S) + i V Im(S)
+            for (int64_t c = 0; c < nc; c++)
+                for (int64_t r = 0; r + 1 < n; r += 2)
+                {
+                    const double pr = re[(size_t) (r + c * nloc)], pi = re[(size_t) (r + 1 + c * nloc)];
+                    const double qr = im[(size_t) (r + c * nloc)], qi = im[(size_t) (r + 1 + c * nloc)];
+                    out_ri[r + c * n] = pr - qi;
+                    out_ri[r + 1 + c * n] = pi + qr;
+                }
+            return nc;
+        }
         for (int64_t c = 0; c < nc; c++)
             for (int64_t r = 0; r < n; r++)
             {

@@ -110,6 +110,34 @@ __global__ void vec_caxpy_kernel(const double* __restrict__ w, const double* __r
     }
 }
 
+// Complex restart GEMM, last step: A = V Re(Q), B = V Im(Q) were formed by two real GEMMs on the interleaved basis (rows = 2 x complex
+// rows); V(:, c) = A(:, c) + i B(:, c), i.e. (a_re - b_im) + i (a_im + b_re), for c < kk.   (Arnoldi.h:320-335 with a complex Q)
+__global__ void zcombine_kernel(const double* __restrict__ A, const double* __restrict__ B, int64_t ldab, double* __restrict__ V, int64_t ldv, int64_t n, int kk)
+{
+    const int64_t pairs = n / 2;
+    for (int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < pairs * kk; t += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int64_t c = t / pairs, i = 2 * (t % pairs);
+        const double ar = A[i + c * ldab], ai = A[i + 1 + c * ldab], br = B[i + c * ldab], bi = B[i + 1 + c * ldab];
+        V[i + c * ldv] = ar - bi;
+        V[i + 1 + c * ldv] = ai + br;
+    }
+}
+
+// f <- f * Q(m-1, kk-2) + V(:, kk-1) * H(kk-1, kk-2) with complex coefficients read on the device   (Arnoldi.h:337)
+__global__ void zf_update_kernel(double* __restrict__ f, const double* __restrict__ vk, const double* __restrict__ Qr, const double* __restrict__ Qi,
+                                 const double* __restrict__ Hr, const double* __restrict__ Hi, int m, int kk, int64_t n)
+{
+    const double qr = Qr[(m - 1) + (int64_t) (kk - 2) * m], qi = Qi[(m - 1) + (int64_t) (kk - 2) * m];
+    const double hr = Hr[(kk - 1) + (int64_t) (kk - 2) * m], hi = Hi[(kk - 1) + (int64_t) (kk - 2) * m];
+    for (int64_t i = 2 * ((int64_t) blockIdx.x * blockDim.x + threadIdx.x); i + 1 < n; i += 2 * (int64_t) gridDim.x * blockDim.x)
+    {
+        const double fr = f[i], fi = f[i + 1], vr = vk[i], vi = vk[i + 1];
+        f[i] = (fr * qr - fi * qi) + (vr * hr - vi * hi);
+        f[i + 1] = (fr * qi + fi * qr) + (vr * hi + vi * hr);
+    }
+}
+
 __global__ void set_beta_kernel(FacCtl* ctl, const double* slot, int take_sqrt)
 {
     const double v = *slot;
@@ -210,6 +238,19 @@ void launch_vec_axpy(const double* w, const double* v, double a, double* f, int6
 void launch_vec_caxpy(const double* w, const double* v, double ar, double ai, double* f, int64_t n, cudaStream_t stream)
 {
     vec_caxpy_kernel<<<vec_grid(n / 2), kVecBlock, 0, stream>>>(w, v, ar, ai, f, n);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_zcombine(const double* A, const double* B, int64_t ldab, double* V, int64_t ldv, int64_t n, int kk, cudaStream_t stream)
+{
+    zcombine_kernel<<<vec_grid((n / 2) * kk), kVecBlock, 0, stream>>>(A, B, ldab, V, ldv, n, kk);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_zf_update(double* f, const double* vk, const double* Qr, const double* Qi, const double* Hr, const double* Hi, int m, int kk, int64_t n,
+                      cudaStream_t stream)
+{
+    zf_update_kernel<<<vec_grid(n / 2), kVecBlock, 0, stream>>>(f, vk, Qr, Qi, Hr, Hi, m, kk, n);
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 

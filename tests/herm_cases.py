@@ -155,9 +155,43 @@ def complex_arnoldi_factorization_case(sb, n=150, m=20):
     assert np.abs(np.tril(H, -2)).max() == 0.0 and np.abs(np.diag(H, -1).imag).max() == 0.0  # Hessenberg, real positive sub-diagonal
     ref = OH.arnoldi_factorize_complex(lambda v: A @ v, n, m, v0=v0)
     assert np.abs(H - ref["H"]).max() <= 1e-9 * scale and g.num_operations() == ref["nops"]
-    # the restart of the complex solver is not built yet: compute() says so with the reference's exception type for "not computed"
-    try:
-        g.compute()
-        raise AssertionError("complex GenEigsSolver.compute() unexpectedly ran")
-    except sb.LogicError:
-        pass
+
+
+COMPLEX_FIXTURES = {10: (0.5, 3, 6), 100: (0.1, 10, 30), 1000: (0.01, 20, 50)}  # test/ComplexEigs.cpp:151-192
+
+
+def complex_dense_kernels_case(sb, m):
+    # test/QR.cpp:177-189 and test/Eigen.cpp with a complex Hessenberg matrix: Q unitary, Q^H H Q = RQ + sI, H Z = Z D to 1e-12
+    rng = np.random.default_rng(100 + m)
+    H = np.triu(rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m)), -1)
+    mu = complex(*rng.standard_normal(2))
+    D, Q = sb.dense.shifted_qr_z(H, mu)
+    assert np.abs(Q.conj().T @ Q - np.eye(m)).max() <= 1e-12
+    assert np.abs(Q.conj().T @ H @ Q - D).max() <= 1e-12 * m * max(1.0, np.abs(H).max())
+    assert np.abs(np.tril(D, -2)).max() == 0.0
+    D0, cs, sn = OH.hess_qr_complex(H, mu)
+    assert np.abs(D - D0).max() <= 1e-12 * m * max(1.0, np.abs(H).max())
+    ev, Z = sb.dense.hess_eigen_z(H)
+    assert np.abs(H @ Z - Z * ev).max() <= 1e-12 * m * max(1.0, np.abs(H).max())
+    assert np.abs(np.linalg.norm(Z, axis=0) - 1.0).max() <= 1e-12
+    w = np.linalg.eigvals(H)
+    assert max(np.abs(w - e).min() for e in ev) <= 1e-11 * max(1.0, np.abs(w).max())
+
+
+def complex_gen_solver_case(sb, n, rule_name, check_history=True):
+    # test/ComplexEigs.cpp:41-110 (sparse cases, maxit = 300): ||AU - UD||_inf <= 1e-9; eigenvalues within 1e-10 relative of the oracle
+    prob, k, m = COMPLEX_FIXTURES[n]
+    A = OH.gen_sparse_data_complex(n, prob)
+    op = sb.SparseHermMatProd(A, uplo="general")
+    g = sb.GenEigsSolver(op, k, m)
+    g.init()
+    nconv = g.compute(getattr(sb.SortRule, rule_name), 300)
+    assert g.info() == sb.CompInfo.Successful and nconv == k
+    ev, Z = g.eigenvalues(), g.eigenvectors()
+    assert Z.dtype == np.complex128 and Z.shape == (n, k)
+    assert np.abs(A @ Z - Z * ev).max() <= 1e-9
+    ref = OH.gen_eigs_complex(A.tocsr().dot, n, k, m, getattr(O, rule_name), 300)
+    assert ref.nconv == k
+    assert np.abs(np.sort_complex(ev) - np.sort_complex(ref.eigenvalues)).max() <= 1e-10 * np.abs(ref.eigenvalues).max()
+    if check_history:
+        assert g.num_operations() == ref.nops and g.num_iterations() == ref.niter

@@ -134,6 +134,20 @@ def test_emu_complex_arnoldi_factorization(emu_order):
     HC.complex_arnoldi_factorization_case(emu_order)
 
 
+@pytest.mark.parametrize("m", [2, 3, 6, 20, 50, 63])
+def test_emu_complex_dense_kernels(emu_order, m):
+    HC.complex_dense_kernels_case(emu_order, m)
+
+
+@pytest.mark.parametrize("rule", ["LargestMagn", "LargestReal", "LargestImag", "SmallestReal"])
+def test_emu_complex_gen_solver(emu, rule):
+    HC.complex_gen_solver_case(emu, 10, rule)
+
+
+def test_emu_complex_gen_solver_n100(emu_order):
+    HC.complex_gen_solver_case(emu_order, 100, "LargestReal")
+
+
 # ---------------------------------------------------------------- scheduling-order independence (race detection)
 def test_emu_order_dense_kernels(emu_order):
     # the small dense device kernels in both fiber orders; m = 61, 62, 64 of the Hessenberg eigen-decomposition exercise the

@@ -229,6 +229,18 @@ def test_complex_arnoldi_factorization(gpu):
     HC.complex_arnoldi_factorization_case(gpu, n=20_000, m=40)
 
 
+@pytest.mark.parametrize("m", [2, 3, 6, 20, 50, 63])
+def test_complex_dense_kernels(gpu, m):
+    HC.complex_dense_kernels_case(gpu, m)
+
+
+@pytest.mark.parametrize("rule", ["LargestMagn", "LargestReal", "LargestImag", "SmallestReal"])
+@pytest.mark.parametrize("n", [10, 100, 1000])
+def test_complex_gen_eigs_reference_cases(gpu, n, rule):
+    # test/ComplexEigs.cpp:151-192
+    HC.complex_gen_solver_case(gpu, n, rule)
+
+
 def test_herm_shim_reference_flow_on_gpu(gpu):
     # test/HermEigs.cpp's sparse flow through the C++ shim headers against the CUDA library
     import subprocess
