@@ -2,7 +2,9 @@
 #ifndef SPECTRA_B200_SPARSE_GEN_MAT_PROD_H
 #define SPECTRA_B200_SPARSE_GEN_MAT_PROD_H
 
+#include <complex>
 #include <type_traits>
+#include <vector>
 
 #include "SparseSymMatProd.h"
 
@@ -31,6 +33,62 @@ public:
                SB200_GENERAL);
     }
 #endif
+};
+
+// Scalar = std::complex<double> (the reference's wrapper is templated on Scalar; test/ComplexEigs.cpp:77-79 uses this instantiation):
+// a general complex sparse matrix behind the complex CSR SpMV kernel, for GenEigsSolver.  (experimental in round 1.)
+template <int Flags, typename StorageIndex>
+class SparseGenMatProd<std::complex<double>, Flags, StorageIndex> : public b200::DeviceOpTag
+{
+    static_assert(std::is_integral<StorageIndex>::value && (sizeof(StorageIndex) == 4 || sizeof(StorageIndex) == 8), "StorageIndex must be a 32- or 64-bit integer");
+    sb200_op* m_op = nullptr;
+    Index m_n = 0;
+    std::vector<int32_t> m_inner32;
+
+    void create(Index n, const StorageIndex* outer, const StorageIndex* inner, const std::complex<double>* values)
+    {
+        m_n = n;
+        const int32_t* in32 = reinterpret_cast<const int32_t*>(inner);
+        if (sizeof(StorageIndex) == 8)
+        {
+            const int64_t nnz = static_cast<int64_t>(outer[n]);
+            m_inner32.resize(static_cast<size_t>(nnz));
+            for (int64_t p = 0; p < nnz; p++)
+                m_inner32[static_cast<size_t>(p)] = static_cast<int32_t>(inner[p]);
+            in32 = m_inner32.data();
+        }
+        b200::check(sb200_op_create_sparse_herm(n, outer, sizeof(StorageIndex) == 8 ? 1 : 0, in32, reinterpret_cast<const double*>(values),
+                                                Flags == SPECTRA_B200_ROWMAJOR ? SB200_ROW_MAJOR : SB200_COL_MAJOR, SB200_GENERAL, &m_op));
+    }
+
+public:
+    using Scalar = std::complex<double>;
+
+    SparseGenMatProd(Index n, const StorageIndex* outer, const StorageIndex* inner, const Scalar* values) { create(n, outer, inner, values); }
+#ifdef SPECTRA_B200_HAS_EIGEN
+    explicit SparseGenMatProd(const Eigen::SparseMatrix<Scalar, Flags, StorageIndex>& mat)
+    {
+        if (!mat.isCompressed())
+            throw std::invalid_argument("SparseGenMatProd: matrix must be in compressed mode (call makeCompressed())");
+        if (mat.rows() != mat.cols())
+            throw std::invalid_argument("SparseGenMatProd: matrix must be square");
+        create(mat.rows(), mat.outerIndexPtr(), mat.innerIndexPtr(), mat.valuePtr());
+    }
+#endif
+    SparseGenMatProd(const SparseGenMatProd&) = delete;
+    SparseGenMatProd& operator=(const SparseGenMatProd&) = delete;
+    ~SparseGenMatProd()
+    {
+        if (m_op)
+            sb200_op_destroy(m_op);
+    }
+    Index rows() const { return m_n; }
+    Index cols() const { return m_n; }
+    sb200_op* handle() const { return m_op; }
+    void perform_op(const Scalar* x_in, Scalar* y_out) const
+    {
+        b200::check(sb200_op_perform_op(m_op, reinterpret_cast<const double*>(x_in), reinterpret_cast<double*>(y_out)));
+    }
 };
 
 }  // namespace Spectra

@@ -229,9 +229,10 @@ int sb200_sym_get_factorization(sb200_sym_solver* s, double* V, double* H, doubl
  * GenEigsSolver — replaces GenEigsSolver.h:158-186 + GenEigsBase.h:43-612 (real double).
  * Complex results are returned as interleaved (re, im) pairs.
  * ------------------------------------------------------------------------------------------ */
-/* With a COMPLEX operator (sb200_op_create_sparse_herm in SB200_GENERAL mode, sb200_op_create_callback_z; ncv <= 63) the handle runs
- * init() and the factorisation tier only -- sb200_gen_factorize_from / sb200_gen_get_factorization with interleaved complex V, H, f
- * (complex Arnoldi, Arnoldi.h:136-295) -- and sb200_gen_compute returns SB200_LOGIC: the complex restart kernels are not built yet. */
+/* With a COMPLEX operator (sb200_op_create_sparse_herm in SB200_GENERAL mode, sb200_op_create_callback_z; ncv <= 63) this is
+ * GenEigsSolver with Scalar = std::complex<double> (GenEigsBase.h:111-140, test/ComplexEigs.cpp): the initial residual, the
+ * factorisation (sb200_gen_get_factorization: V, H, f) and the eigenvectors are interleaved complex.  Experimental in round 1:
+ * verified on the kernel-logic emulator, not yet on a device. */
 int sb200_gen_create(sb200_op* op, int64_t nev, int64_t ncv, sb200_gen_solver** out);      /* GenEigsBase.h:409-424 */
 int sb200_gen_init(sb200_gen_solver* s, const double* init_resid_or_null);                  /* :442-475 */
 int sb200_gen_compute(sb200_gen_solver* s, int selection, int64_t maxit, double tol, int sorting, int64_t* nconv); /* :501-525 */

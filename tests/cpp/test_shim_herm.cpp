@@ -1,7 +1,9 @@
 // The flow of the reference's test/HermEigs.cpp (sparse cases, :27-71, :140-163) written against the B200 shim headers:
 // the same gen_sparse_data (std::default_random_engine seeded 0), SparseHermMatProd + HermEigsSolver, every selection rule,
 // acceptance ||AU - UD||_inf <= 1e-9.  No Eigen: the fixture is assembled into CSC arrays by hand.
+#include <Spectra/GenEigsSolver.h>
 #include <Spectra/HermEigsSolver.h>
+#include <Spectra/MatOp/SparseGenMatProd.h>
 #include <Spectra/MatOp/SparseHermMatProd.h>
 
 #include <cmath>
@@ -70,6 +72,36 @@ static void herm_matvec(const Csc& A, const cd* x, cd* y)
         }
 }
 
+// test/ComplexEigs.cpp:20-39: general complex sparse matrix (re and im drawn for every entry)
+static Csc gen_sparse_data_complex(int n, double prob)
+{
+    std::vector<std::vector<std::pair<int, cd>>> cols(n);
+    std::default_random_engine gen;
+    gen.seed(0);
+    std::uniform_real_distribution<double> distr(0.0, 1.0);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++)
+            if (distr(gen) < prob)
+            {
+                const double re = distr(gen) - 0.5;
+                const double im = distr(gen) - 0.5;
+                cols[j].push_back({i, cd(re, im)});
+            }
+    Csc A;
+    A.n = n;
+    A.outer.assign(n + 1, 0);
+    for (int j = 0; j < n; j++)
+    {
+        A.outer[j + 1] = A.outer[j] + (int) cols[j].size();
+        for (auto& e : cols[j])
+        {
+            A.inner.push_back(e.first);
+            A.val.push_back(e.second);
+        }
+    }
+    return A;
+}
+
 static int failures = 0;
 #define CHECK(cond)                                                  \
     do                                                               \
@@ -136,8 +168,37 @@ struct RankOneUpdateOp
     }
 };
 
+// the flow of test/ComplexEigs.cpp:41-110 (sparse case): GenEigsSolver<SparseGenMatProd<std::complex<double>>>, maxit = 300
+static void run_complex_gen(int n, double prob, int k, int m)
+{
+    const Csc A = gen_sparse_data_complex(n, prob);
+    SparseGenMatProd<cd> op(n, A.outer.data(), A.inner.data(), A.val.data());
+    for (SortRule rule : {SortRule::LargestMagn, SortRule::LargestReal, SortRule::SmallestReal})
+    {
+        GenEigsSolver<SparseGenMatProd<cd>> eigs(op, k, m);
+        eigs.init();
+        const Index nconv = eigs.compute(rule, 300);
+        CHECK(eigs.info() == CompInfo::Successful && nconv == k);
+        const auto evals = eigs.eigenvalues();
+        const auto evecs = eigs.eigenvectors();
+        double err = 0.0;
+        for (Index c = 0; c < evecs.cols(); c++)
+        {
+            std::vector<cd> y(n, cd(0));
+            for (int j = 0; j < n; j++)
+                for (int p = A.outer[j]; p < A.outer[j + 1]; p++)
+                    y[A.inner[p]] += A.val[p] * evecs(j, c);
+            for (int i = 0; i < n; i++)
+                err = std::max(err, std::abs(y[i] - evecs(i, c) * evals[c]));
+        }
+        std::printf("complex gen n=%d rule=%d nconv=%d nops=%d ||AU-UD||_inf=%.3e\n", n, (int) rule, (int) nconv, (int) eigs.num_operations(), err);
+        CHECK(err <= 1e-9);
+    }
+}
+
 int main()
 {
+    run_complex_gen(10, 0.5, 3, 6);
     {
         RankOneUpdateOp op(40);
         HermEigsSolver<RankOneUpdateOp> eigs(op, 4, 12);

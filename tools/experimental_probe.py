@@ -8,6 +8,7 @@ under "experimental"; nothing here enters `value`, `e2e` or `roofline`.  Every b
                 on a band matrix: ms, fraction of the HBM roof (algorithmic bytes), fill, difference of the result to the CSR kernel's
   sell_solve    a truncated Lanczos run (first restarts) through the fused sliced step kernel: operations / s next to the default path
   herm          SparseHermMatProd + HermEigsSolver on a random sparse Hermitian matrix: residuals and time
+  complex_gen   complex GenEigsSolver (complex Arnoldi + the one-warp complex restart kernel) on a random sparse complex matrix
 
 usage: python tools/experimental_probe.py [n]
 """
@@ -133,10 +134,30 @@ def main():
         return {"n": m, "nnz": int(Af.nnz), "spmv_rel_err": err, "nconv": int(nconv), "nops": eigs.num_operations(), "wall_s": round(wall, 3),
                 "ms_total": round(st["ms_total"], 1), "max_rel_residual": resid}
 
+    def complex_gen():
+        import scipy.sparse as sp
+
+        m = min(n, 200_000)
+        rng = np.random.default_rng(1)
+        cnt = 20 * m
+        A = sp.csc_matrix(((rng.random(cnt) - 0.5) + 1j * (rng.random(cnt) - 0.5), (rng.integers(0, m, cnt), rng.integers(0, m, cnt))), shape=(m, m))
+        A.sum_duplicates()
+        op = sb.SparseHermMatProd(A, uplo="general")
+        g = sb.GenEigsSolver(op, 6, 30)
+        t = time.time()
+        g.init()
+        nconv = g.compute(sb.SortRule.LargestMagn, 300)
+        wall = time.time() - t
+        ev, Z = g.eigenvalues(), g.eigenvectors()
+        resid = float((np.linalg.norm(A @ Z - Z * ev, axis=0) / np.abs(ev)).max()) if len(ev) else None
+        return {"n": m, "nnz": int(A.nnz), "nconv": int(nconv), "nops": g.num_operations(), "niter": g.num_iterations(), "wall_s": round(wall, 3),
+                "max_rel_residual": resid}
+
     block("gather_roof", gather_roof)
     block("spmv", spmv_variants)
     block("sell_solve", sell_solve)
     block("herm", herm)
+    block("complex_gen", complex_gen)
     print(json.dumps(out), flush=True)
 
 
