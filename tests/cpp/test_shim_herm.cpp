@@ -121,8 +121,12 @@ static void run_case(int n, double prob, int k, int m)
     const SortRule rules[] = {SortRule::LargestMagn, SortRule::LargestAlge, SortRule::SmallestMagn, SortRule::SmallestAlge, SortRule::BothEnds};
     for (SortRule rule : rules)
     {
+#ifdef SB200_SHIM_TEST_SMALL
+        if (n >= 100 && rule != SortRule::LargestAlge && rule != SortRule::BothEnds)
+            continue;  // the emulated CPU run keeps two rules at n = 100; the device run (tests/test_gpu_experimental.py) takes all
+#endif
         if (n >= 100 && rule == SortRule::SmallestMagn)
-            continue;  // converges after > 1000 matrix operations: too slow for the emulated run, covered on the device
+            continue;  // converges after > 1000 matrix operations
         HermEigsSolver<SparseHermMatProd<cd>> eigs(op, k, m);
         eigs.init();
         const Index nconv = eigs.compute(rule);

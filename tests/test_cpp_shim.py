@@ -55,7 +55,7 @@ def _compile_herm(libdir, libname, src="test_shim_herm.cpp", defines=()):
 def test_herm_shim_reference_flow_on_emulator(emu):
     # test/HermEigs.cpp's sparse flow through include/Spectra/HermEigsSolver.h; the kernels run on the CPU execution model
     libdir = os.path.join(ROOT, "tests", "_emu")
-    exe = _compile_herm(libdir, "spectra_b200_emu")
+    exe = _compile_herm(libdir, "spectra_b200_emu", defines=("SB200_SHIM_TEST_SMALL",))
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     print(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
