@@ -195,3 +195,33 @@ def complex_gen_solver_case(sb, n, rule_name, check_history=True):
     assert np.abs(np.sort_complex(ev) - np.sort_complex(ref.eigenvalues)).max() <= 1e-10 * np.abs(ref.eigenvalues).max()
     if check_history:
         assert g.num_operations() == ref.nops and g.num_iterations() == ref.niter
+
+
+def complex_gen_user_operator_case(sb, n=50):
+    # a user-defined general complex operator (OpType concept with Scalar = std::complex<double>) behind GenEigsSolver
+    rng = np.random.default_rng(9)
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+
+    class MyOp:
+        def rows(self):
+            return n
+
+        def perform_op(self, x_in, y_out):
+            y_out[:] = A @ x_in
+
+    op = sb.UserOp(MyOp(), complex_scalar=True)
+    g = sb.GenEigsSolver(op, 4, 16)
+    g.init()
+    assert g.compute(sb.SortRule.LargestMagn, 300) == 4 and g.info() == sb.CompInfo.Successful
+    ev, Z = g.eigenvalues(), g.eigenvectors()
+    assert np.abs(A @ Z - Z * ev).max() <= 1e-9
+    ref = OH.gen_eigs_complex(lambda v: A @ v, n, 4, 16, O.LargestMagn, 300)
+    assert g.num_operations() == ref.nops
+    assert np.abs(np.sort_complex(ev) - np.sort_complex(ref.eigenvalues)).max() <= 1e-10 * np.abs(ref.eigenvalues).max()
+    # argument checks of GenEigsBase.h:419-423 hold for complex operators too
+    for nev, ncv in ((0, 6), (n - 1, n), (3, 4), (3, n + 1)):
+        try:
+            sb.GenEigsSolver(op, nev, ncv)
+        except sb.InvalidArgument:
+            continue
+        raise AssertionError((nev, ncv))

@@ -144,6 +144,10 @@ def test_emu_complex_gen_solver(emu, rule):
     HC.complex_gen_solver_case(emu, 10, rule)
 
 
+def test_emu_complex_gen_user_operator(emu):
+    HC.complex_gen_user_operator_case(emu)
+
+
 def test_emu_complex_gen_solver_n100(emu_order):
     HC.complex_gen_solver_case(emu_order, 100, "LargestReal")
 

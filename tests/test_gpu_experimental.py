@@ -3,7 +3,10 @@ They are skipped unless SB200_EXPERIMENTAL=1 so that the verified suite stays me
 runs them (tools/run_experimental.sh).  Everything here is opt-in at run time as well: the default product path is unchanged.
 
 Covered: the sliced-CSR layout + lane-per-row SpMV kernels (SB200_SPMV_FORMAT=sell; csr_build.cu build_sell_layout, spmv.cu
-sell_plain_kernel / sell_step_kernel) at the operator, factorisation and solver tiers, and the gather microbenchmark."""
+sell_plain_kernel / sell_step_kernel) at the operator, factorisation and solver tiers; the gather microbenchmark; the complex Hermitian
+path (SparseHermMatProd / HermEigsSolver, user-defined complex operators); the complex GenEigsSolver (complex Arnoldi, the one-warp
+complex restart kernel of dense_gen_z.cu, complex restart GEMM); the C++ shim flows for complex and float scalars.  All of them pass on
+the kernel-logic emulator (tests/test_emu_kernels.py, tests/test_cpp_shim.py) in both fiber orders."""
 import contextlib
 import os
 
@@ -227,6 +230,10 @@ def test_herm_user_operator(gpu):
 def test_complex_arnoldi_factorization(gpu):
     HC.complex_arnoldi_factorization_case(gpu)
     HC.complex_arnoldi_factorization_case(gpu, n=20_000, m=40)
+
+
+def test_complex_gen_user_operator(gpu):
+    HC.complex_gen_user_operator_case(gpu)
 
 
 @pytest.mark.parametrize("m", [2, 3, 6, 20, 50, 63])
