@@ -25,6 +25,7 @@
 // to natural row order through 8 KB of shared memory, so the epilogues (accumulate, fused step head) are the coalesced ones of
 // the CSR-vector kernels.  Traffic per row at d nnz/row and padding p: 12 d (1 + p) + 2 (perm) + 0.25 (slice_ptr) + x + y.
 #include <cstdlib>
+#include <cstring>
 
 #include "kernels.h"
 
@@ -527,6 +528,12 @@ SpmvPlan make_spmv_plan(const DeviceCsr& A)
     const int64_t need = (A.nrows + rpb - 1) / rpb;
     // persistent grid: up to 8 resident CTAs of 256 threads per SM
     p.grid = (int) std::max<int64_t>(1, std::min<int64_t>(need, (int64_t) sms * 8));
+    // A/B knob for the next round (profiles/README.md, "grid quantisation"): SB200_SPMV_GRID=blocks launches one CTA per 256-row block
+    // when that fits the reduction scratch, so that the hardware balances a small number of rounds instead of leaving part of the last
+    // persistent round idle.  Default: unchanged (the GPU-verified persistent grid).
+    if (const char* e = std::getenv("SB200_SPMV_GRID"))
+        if (std::strcmp(e, "blocks") == 0 && need <= (int64_t) reduction_max_grid(sms))
+            p.grid = (int) std::max<int64_t>(1, need);
     // sliced layout present (build_sell_layout): lane-per-row kernels, persistent grid of one window per CTA iteration
     const SellBlock& S0 = A.blocks.empty() ? A.sell : A.blocks[0].sell;
     if (S0.built())

@@ -62,8 +62,11 @@ def main():
             alg = 12 * nnz + 4 * (n + 1) + 16 * n
             x = np.random.default_rng(0).standard_normal(n)
             y_ref = None
-            for var in ("csr", "sell256", "sell512", "sell1024"):
+            for var in ("csr", "csr_blocks", "sell256", "sell512", "sell1024"):
                 os.environ.pop("SB200_SPMV_FORMAT", None)
+                os.environ.pop("SB200_SPMV_GRID", None)
+                if var == "csr_blocks":
+                    os.environ["SB200_SPMV_GRID"] = "blocks"  # one CTA per 256-row block instead of the persistent grid
                 if var.startswith("sell"):
                     os.environ["SB200_SPMV_FORMAT"] = "sell"
                     os.environ["SB200_SELL_THREADS"] = var[4:]
@@ -81,7 +84,30 @@ def main():
                 except Exception as e:  # noqa: BLE001
                     res.append({"case": case, "variant": var, "error": f"{type(e).__name__}: {e}"})
             os.environ.pop("SB200_SPMV_FORMAT", None)
+            os.environ.pop("SB200_SPMV_GRID", None)
             del rp, ci, v
+        # the same comparison at BASELINE config C2's size, where the persistent grid has only 3.3 rounds
+        if n > 1_000_000:
+            n2 = 1_000_000
+            rp, ci, v = synth.csr(n2, 20, 0, True)
+            alg = 12 * len(ci) + 4 * (n2 + 1) + 16 * n2
+            for var in ("csr", "csr_blocks", "sell512"):
+                os.environ.pop("SB200_SPMV_FORMAT", None)
+                os.environ.pop("SB200_SPMV_GRID", None)
+                if var == "csr_blocks":
+                    os.environ["SB200_SPMV_GRID"] = "blocks"
+                if var.startswith("sell"):
+                    os.environ["SB200_SPMV_FORMAT"] = "sell"
+                    os.environ["SB200_SELL_THREADS"] = var[4:]
+                try:
+                    op = sb.SparseGenMatProd.from_csr_slab(n2, 0, rp, ci, v)
+                    ms = op.spmv_device_time(50)
+                    res.append({"case": "uniform_G_sym_d20_n1e6", "variant": var, "ms": round(ms, 4), "frac_of_hbm_roof": round(alg / ms / 1e6 / peak, 3)})
+                    op.close()
+                except Exception as e:  # noqa: BLE001
+                    res.append({"case": "uniform_G_sym_d20_n1e6", "variant": var, "error": f"{type(e).__name__}: {e}"})
+            os.environ.pop("SB200_SPMV_FORMAT", None)
+            os.environ.pop("SB200_SPMV_GRID", None)
         return res
 
     def sell_solve():
