@@ -242,7 +242,11 @@ int main()
         REQUIRE(std::fabs(ev[0] - 4.0) < 1e-10 && std::fabs(ev[1] - 3.0) < 1e-10 && std::fabs(ev[2] - 2.0) < 1e-10);
         std::printf("user shift-solve op diag(1..10), sigma 3.14: %.12f %.12f %.12f\n", ev[0], ev[1], ev[2]);
     }
+#ifdef SB200_SHIM_TEST_SMALL
+    run_shift(120, 3, 4, 12, 1.0);
+#else
     run_shift(500, 3, 5, 20, 1.0);
+#endif
 #ifndef SB200_SHIM_TEST_SMALL  // the emulated CPU run (tests/test_cpp_shim.py) keeps the small cases only
     run_shift(20000, 15, 10, 30, 100.005);
 #endif

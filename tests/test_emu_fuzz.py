@@ -109,7 +109,7 @@ def small_sym_problem(draw):
     return M, k, m, rule, kind
 
 
-@settings(max_examples=16, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@settings(max_examples=8, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(prob=small_sym_problem())
 def test_fuzz_sym_solver_follows_oracle(emu, prob):
     # whole pipeline (init, factorisation with its restart heuristics, device restart kernel, compress) against the CPU oracle on random and

@@ -73,7 +73,6 @@ def test_emu_sell_fused_step_factorization(emu, threads):
 def test_emu_sell_persistent_grid(emu):
     # operands beyond 16384 windows per rank use a persistent grid that strides over the windows; forced here at a small size
     with X.env(SB200_SELL_PERSISTENT=1):
-        X.test_sell_lanczos_factorization(emu, 512)
         X.test_sell_spmv_matches_csr_and_scipy(emu, 256, 13_000, 0.0008)  # 13 windows > 12 resident CTAs on the 2 emulated SMs
 
 
@@ -148,8 +147,12 @@ def test_emu_complex_gen_user_operator(emu):
     HC.complex_gen_user_operator_case(emu)
 
 
-def test_emu_complex_gen_solver_n100(emu_order):
-    HC.complex_gen_solver_case(emu_order, 100, "LargestReal")
+def test_emu_complex_gen_solver_n100(emu):
+    HC.complex_gen_solver_case(emu, 100, "LargestReal")
+
+
+def test_emu_complex_gen_solver_reverse_order(emu_order):
+    HC.complex_gen_solver_case(emu_order, 10, "LargestMagn")
 
 
 # ---------------------------------------------------------------- scheduling-order independence (race detection)
@@ -183,7 +186,7 @@ def test_emu_against_golden_spectra(emu, n):
     prob = {10: 0.5, 100: 0.1}[n]
     k, m = GC.KM[n]
     A = O.gen_sparse_data(n, prob)
-    for rule, srule in ((O.LargestAlge, emu.SortRule.LargestAlge), (O.SmallestAlge, emu.SortRule.SmallestAlge)):
+    for rule, srule in ((O.LargestAlge, emu.SortRule.LargestAlge), (O.SmallestAlge, emu.SortRule.SmallestAlge))[:2 if n == 10 else 1]:
         e = emu.SymEigsSolver(emu.SparseSymMatProd(A), k, m)
         e.init()
         e.compute(srule)
@@ -245,7 +248,7 @@ def test_emu_row_sharded_sym_solver(emu, P, fmt):
     # same iteration (identical operation counts), reproduce the single-rank eigenvalues, and hold its rows of the eigenvectors
     from spectra_b200_emu import synth
 
-    n, k, m = 701, 4, 12
+    n, k, m = 401, 4, 12
     rp, ci, v = synth.csr(n, 12, 3, True)
     A = sp.csr_matrix((v, ci, rp), shape=(n, n))
     fmt_env = dict(SB200_SPMV_FORMAT="sell", SB200_SELL_MAX_FILL=100) if fmt == "sell" else dict(SB200_SPMV_FORMAT="csr")
