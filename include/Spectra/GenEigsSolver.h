@@ -5,6 +5,7 @@
 
 #include <algorithm>
 
+#include "MatOp/DenseGenMatProd.h"
 #include "MatOp/SparseGenMatProd.h"
 #include "Util/CompInfo.h"
 #include "Util/SelectionRule.h"
@@ -36,7 +37,7 @@ struct GenBinding<OpType, true> : OpBindingZ<OpType>
 
 // Scalar = double / float: real nonsymmetric problems (complex Ritz pairs).  Scalar = std::complex<double>: GenEigsBase with a complex
 // Scalar (GenEigsBase.h:111-140, test/ComplexEigs.cpp); experimental in round 1, see DESIGN.md.
-template <typename OpType = SparseGenMatProd<double>>
+template <typename OpType = DenseGenMatProd<double>>  // the reference's default (GenEigsSolver.h:157)
 class GenEigsSolver
 {
     b200::GenBinding<OpType> m_bind;

@@ -1,0 +1,84 @@
+// B200 shim of Spectra/MatOp/DenseSymMatProd.h:20-105 (the reference's default OpType of SymEigsSolver) and of
+// MatOp/DenseGenMatProd.h: the dense matrix is uploaded once as a full compressed matrix (every entry stored) and multiplied by the
+// same sm_100a CSR SpMV kernel as the sparse wrappers -- a dense n x n operand is simply a CSR with n entries per row (one warp per
+// row).  Dense operators are outside the hot-path scope of this build; they are provided so that code written
+// against the reference's defaults compiles and runs.  Only the `Uplo` triangle is read by DenseSymMatProd (selfadjointView<Uplo>).
+#ifndef SPECTRA_B200_DENSE_SYM_MAT_PROD_H
+#define SPECTRA_B200_DENSE_SYM_MAT_PROD_H
+
+#include <vector>
+
+#include "SparseSymMatProd.h"
+
+namespace Spectra {
+
+namespace b200 {
+// dense column-/row-major n x n matrix -> compressed arrays with every entry present
+template <typename Scalar>
+struct DenseAsCompressed
+{
+    std::vector<int32_t> outer, inner;
+    std::vector<Scalar> values;
+    DenseAsCompressed(Index n, const Scalar* data)
+    {
+        outer.resize(static_cast<size_t>(n) + 1);
+        inner.resize(static_cast<size_t>(n * n));
+        values.assign(data, data + n * n);
+        for (Index o = 0; o <= n; o++)
+            outer[static_cast<size_t>(o)] = static_cast<int32_t>(o * n);
+        for (Index o = 0; o < n; o++)
+            for (Index k = 0; k < n; k++)
+                inner[static_cast<size_t>(o * n + k)] = static_cast<int32_t>(k);
+    }
+};
+}  // namespace b200
+
+template <typename Scalar_, int Uplo = SPECTRA_B200_LOWER, int Flags = SPECTRA_B200_COLMAJOR>
+class DenseSymMatProd : public b200::SparseOpBase
+{
+    static_assert(b200::IsSupportedScalar<Scalar_>::value, "the B200 path implements Scalar = double, and float with fp64 device arithmetic");
+    b200::DenseAsCompressed<Scalar_> m_c;
+
+public:
+    using Scalar = Scalar_;
+
+    // n x n matrix in `Flags` storage order (ColMajor: data[i + j * n])
+    DenseSymMatProd(Index n, const Scalar* data) : m_c(n, data)
+    {
+        create_any(n, m_c.outer.data(), m_c.inner.data(), m_c.values.data(), Flags == SPECTRA_B200_ROWMAJOR,
+                   Uplo == SPECTRA_B200_LOWER ? SB200_SYM_LOWER : SB200_SYM_UPPER);
+    }
+#ifdef SPECTRA_B200_HAS_EIGEN
+    // Same constructor as the reference (DenseSymMatProd.h:45-53)
+    explicit DenseSymMatProd(const Eigen::Matrix<Scalar, Eigen::Dynamic, Eigen::Dynamic, Flags>& mat) : DenseSymMatProd(mat.rows(), mat.data())
+    {
+        if (mat.rows() != mat.cols())
+            throw std::invalid_argument("DenseSymMatProd: matrix must be square");
+    }
+#endif
+};
+
+template <typename Scalar_, int Flags = SPECTRA_B200_COLMAJOR>
+class DenseGenMatProd : public b200::SparseOpBase
+{
+    static_assert(b200::IsSupportedScalar<Scalar_>::value, "the B200 path implements Scalar = double, and float with fp64 device arithmetic");
+    b200::DenseAsCompressed<Scalar_> m_c;
+
+public:
+    using Scalar = Scalar_;
+
+    DenseGenMatProd(Index n, const Scalar* data) : m_c(n, data)
+    {
+        create_any(n, m_c.outer.data(), m_c.inner.data(), m_c.values.data(), Flags == SPECTRA_B200_ROWMAJOR, SB200_GENERAL);
+    }
+#ifdef SPECTRA_B200_HAS_EIGEN
+    explicit DenseGenMatProd(const Eigen::Matrix<Scalar, Eigen::Dynamic, Eigen::Dynamic, Flags>& mat) : DenseGenMatProd(mat.rows(), mat.data())
+    {
+        if (mat.rows() != mat.cols())
+            throw std::invalid_argument("DenseGenMatProd: matrix must be square");
+    }
+#endif
+};
+
+}  // namespace Spectra
+#endif

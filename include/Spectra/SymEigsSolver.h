@@ -5,6 +5,7 @@
 
 #include <algorithm>
 
+#include "MatOp/DenseSymMatProd.h"
 #include "MatOp/SparseSymMatProd.h"
 #include "Util/CompInfo.h"
 #include "Util/SelectionRule.h"
@@ -12,7 +13,7 @@
 
 namespace Spectra {
 
-template <typename OpType = SparseSymMatProd<double>>
+template <typename OpType = DenseSymMatProd<double>>  // the reference's default (SymEigsSolver.h:132)
 class SymEigsSolver
 {
     b200::OpBinding<OpType> m_bind;  // device-resident sparse operator, or a host-callback adapter for any other OpType

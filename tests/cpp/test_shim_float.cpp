@@ -2,6 +2,8 @@
 // float matrices / vectors at the boundary, fp64 arithmetic on the device.  Flow of test/SymEigs.cpp / test/GenEigs.cpp on the
 // reference's gen_sparse_data fixture (n = 100), plus a user-defined float operator (SymEigsSolver.h:99-126).
 #include <Spectra/GenEigsSolver.h>
+#include <Spectra/MatOp/DenseGenMatProd.h>
+#include <Spectra/MatOp/DenseSymMatProd.h>
 #include <Spectra/MatOp/SparseGenMatProd.h>
 #include <Spectra/MatOp/SparseSymMatProd.h>
 #include <Spectra/SymEigsSolver.h>
@@ -158,6 +160,43 @@ int main()
         CHECK(eigs.info() == CompInfo::Successful && nconv == 3);
         const auto evals = eigs.eigenvalues();
         CHECK(std::fabs(evals[0] - 10.f) < 1e-4f && std::fabs(evals[1] - 9.f) < 1e-4f && std::fabs(evals[2] - 8.f) < 1e-4f);  // SymEigsSolver.h:99-126
+    }
+    {
+        // the reference's first README example (README.md:90-125): dense symmetric M = A + A', DenseSymMatProd, 3 largest eigenvalues
+        const int nd = 10;
+        std::vector<double> M(nd * nd);
+        std::default_random_engine gen(7);
+        std::uniform_real_distribution<double> distr(-1.0, 1.0);
+        std::vector<double> Ar(nd * nd);
+        for (double& a : Ar)
+            a = distr(gen);
+        for (int i = 0; i < nd; i++)
+            for (int j = 0; j < nd; j++)
+                M[i + j * nd] = Ar[i + j * nd] + Ar[j + i * nd];
+        DenseSymMatProd<double> op(nd, M.data());
+        SymEigsSolver<DenseSymMatProd<double>> eigs(op, 3, 6);
+        eigs.init();
+        const Index nconv = eigs.compute(SortRule::LargestAlge);
+        CHECK(eigs.info() == CompInfo::Successful && nconv == 3);
+        const auto evals = eigs.eigenvalues();
+        const auto evecs = eigs.eigenvectors();
+        double res = 0;
+        for (Index c = 0; c < 3; c++)
+            for (int i = 0; i < nd; i++)
+            {
+                double y = 0;
+                for (int j = 0; j < nd; j++)
+                    y += M[i + j * nd] * evecs(j, c);
+                res = std::max(res, std::fabs(y - evecs(i, c) * evals[c]));
+            }
+        std::printf("dense sym README example: %.10f %.10f %.10f ||AU-UD||_inf=%.3e\n", evals[0], evals[1], evals[2], res);
+        CHECK(res <= 1e-9);
+        CHECK(std::fabs(op(2, 5) - M[2 + 5 * nd]) == 0.0);
+        DenseGenMatProd<double> gop(nd, Ar.data());
+        GenEigsSolver<DenseGenMatProd<double>> geigs(gop, 2, 6);
+        geigs.init();
+        geigs.compute(SortRule::LargestMagn, 300);
+        CHECK(geigs.info() == CompInfo::Successful);
     }
     std::printf(failures ? "FAILED (%d)\n" : "ALL PASSED\n", failures);
     return failures ? 1 : 0;
