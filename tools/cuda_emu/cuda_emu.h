@@ -450,19 +450,38 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int)
     p->totalGlobalMem = (size_t) 8 << 30;
     return cudaSuccess;
 }
+// "Device" allocations carry a 64-byte guard zone on either side (0xA5) that cudaFree verifies: an out-of-bounds WRITE of any kernel
+// or copy aborts the test run with the size of the block (reads are not detected).  Layout: [size_t size | pad][guard][user bytes][guard]
+constexpr size_t kMemGuard = 64;
 template <typename T>
 inline cudaError_t cudaMalloc(T** p, size_t bytes)
 {
-    void* q = malloc(bytes ? bytes : 1);
-    if (!q)
+    unsigned char* raw = (unsigned char*) malloc(bytes + 3 * kMemGuard);
+    if (!raw)
         return cudaErrorMemoryAllocation;
-    memset(q, 0xFF, bytes);
-    *p = (T*) q;
+    memcpy(raw, &bytes, sizeof(size_t));
+    memset(raw + kMemGuard, 0xA5, kMemGuard);
+    memset(raw + 2 * kMemGuard, 0xFF, bytes);
+    memset(raw + 2 * kMemGuard + bytes, 0xA5, kMemGuard);
+    *p = (T*) (raw + 2 * kMemGuard);
     return cudaSuccess;
 }
 inline cudaError_t cudaFree(void* p)
 {
-    free(p);
+    if (!p)
+        return cudaSuccess;
+    unsigned char* user = (unsigned char*) p;
+    unsigned char* raw = user - 2 * kMemGuard;
+    size_t bytes = 0;
+    memcpy(&bytes, raw, sizeof(size_t));
+    for (size_t q = 0; q < kMemGuard; q++)
+        if (raw[kMemGuard + q] != 0xA5 || user[bytes + q] != 0xA5)
+        {
+            fprintf(stderr, "cuda_emu: out-of-bounds write detected around a device allocation of %zu bytes (%s the block)\n", bytes,
+                    raw[kMemGuard + q] != 0xA5 ? "before" : "after");
+            abort();
+        }
+    free(raw);
     return cudaSuccess;
 }
 template <typename T>
