@@ -250,6 +250,7 @@ int main()
 #ifndef SB200_SHIM_TEST_SMALL  // the emulated CPU run (tests/test_cpp_shim.py) keeps the small cases only
     run_shift(20000, 15, 10, 30, 100.005);
 #endif
+#ifndef SB200_SHIM_TEST_SMALL
     {
         // a large pattern that is not banded is rejected with the reference's exception type
         Csc A = gen_sparse_data(3000, 0.002);
@@ -264,6 +265,7 @@ int main()
         }
         REQUIRE(thrown);
     }
+#endif
     {
         MyDiagonalTen op;
         SymEigsSolver<MyDiagonalTen> eigs(op, 3, 6);
