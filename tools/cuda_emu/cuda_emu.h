@@ -69,7 +69,50 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 inline int2 make_int2(int x, int y) { return int2{x, y}; }
 
+// Fiber switch.  x86-64: a 12-instruction register switch (callee-saved registers + stack pointer; defined once in the emu_stubs
+// translation unit) -- glibc's swapcontext costs two rt_sigprocmask system calls per switch, which dominated the emulated run time.
+// Elsewhere: ucontext.
+#if defined(__x86_64__) && !defined(CUDA_EMU_USE_UCONTEXT)
+#define CUDA_EMU_ASM_SWITCH 1
+extern "C" void cuda_emu_ctx_switch(void** save_sp, void* load_sp);
+#endif
+
 namespace emu {
+
+#ifdef CUDA_EMU_ASM_SWITCH
+struct Ctx
+{
+    void* sp = nullptr;
+};
+inline void ctx_switch(Ctx* from, Ctx* to) { cuda_emu_ctx_switch(&from->sp, to->sp); }
+inline void ctx_make(Ctx* c, char* stack, size_t bytes, void (*entry)())
+{
+    // initial frame: six callee-saved register slots, the entry address that `ret` pops, one fake return-address slot;
+    // at entry %rsp must be 8 modulo 16 (as after a call)
+    uintptr_t top = ((uintptr_t) stack + bytes) & ~(uintptr_t) 15;
+    void** slot = (void**) (top - 16);
+    slot[0] = (void*) entry;
+    slot[1] = nullptr;
+    void** sp = slot - 6;
+    for (int q = 0; q < 6; q++)
+        sp[q] = nullptr;
+    c->sp = sp;
+}
+#else
+struct Ctx
+{
+    ucontext_t uc;
+};
+inline void ctx_switch(Ctx* from, Ctx* to) { swapcontext(&from->uc, &to->uc); }
+inline void ctx_make(Ctx* c, char* stack, size_t bytes, void (*entry)())
+{
+    getcontext(&c->uc);
+    c->uc.uc_stack.ss_sp = stack;
+    c->uc.uc_stack.ss_size = bytes;
+    c->uc.uc_link = nullptr;
+    makecontext(&c->uc, entry, 0);
+}
+#endif
 
 struct Warp
 {
@@ -90,8 +133,8 @@ struct State
     std::vector<Warp> warps;
     unsigned char* dyn_smem = nullptr;
     // fibers
-    ucontext_t main_ctx;
-    std::vector<ucontext_t> ctx;
+    Ctx main_ctx;
+    std::vector<Ctx> ctx;
     std::vector<char*> stacks;
     std::vector<char> done;
     int cur = -1;
@@ -107,7 +150,7 @@ inline std::mutex launch_mutex;
 
 constexpr size_t kStackBytes = 256 * 1024;
 
-inline void yield_to_main() { swapcontext(&g.ctx[(size_t) g.cur], &g.main_ctx); }
+inline void yield_to_main() { ctx_switch(&g.ctx[(size_t) g.cur], &g.main_ctx); }
 
 inline void warp_try_release(Warp& w)
 {
@@ -141,7 +184,8 @@ inline void fiber_entry()
     g.progress++;
     warp_try_release(w);
     cta_try_release();
-    swapcontext(&g.ctx[(size_t) t], &g.main_ctx);
+    ctx_switch(&g.ctx[(size_t) t], &g.main_ctx);
+    abort();  // a finished fiber is never resumed
 }
 
 inline void syncthreads()
@@ -221,11 +265,7 @@ inline void run_cta(const std::function<void()>& body, const Launch& L)
     g.body = &body;
     for (int t = 0; t < nthreads; t++)
     {
-        getcontext(&g.ctx[(size_t) t]);
-        g.ctx[(size_t) t].uc_stack.ss_sp = g.stacks[(size_t) t];
-        g.ctx[(size_t) t].uc_stack.ss_size = kStackBytes;
-        g.ctx[(size_t) t].uc_link = &g.main_ctx;
-        makecontext(&g.ctx[(size_t) t], (void (*)()) fiber_entry, 0);
+        ctx_make(&g.ctx[(size_t) t], g.stacks[(size_t) t], kStackBytes, fiber_entry);
     }
     int remaining = nthreads;
     while (remaining > 0)
@@ -243,7 +283,7 @@ inline void run_cta(const std::function<void()>& body, const Launch& L)
             g.tid.x = (unsigned) t % L.block.x;
             g.tid.y = ((unsigned) t / L.block.x) % L.block.y;
             g.tid.z = (unsigned) t / (L.block.x * L.block.y);
-            swapcontext(&g.main_ctx, &g.ctx[(size_t) t]);
+            ctx_switch(&g.main_ctx, &g.ctx[(size_t) t]);
             if (!g.done[(size_t) t])
                 remaining++;
         }

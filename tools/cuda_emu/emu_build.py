@@ -135,6 +135,36 @@ void nccl_allgather(sb200_comm* c, const double* send, double* recv, size_t coun
 }
 }  // namespace sb200
 
+// fiber switch for x86-64 (cuda_emu.h, CUDA_EMU_ASM_SWITCH): save the callee-saved registers and the stack pointer of the running fiber,
+// load the other one's.  void cuda_emu_ctx_switch(void** save_sp, void* load_sp)
+#ifdef CUDA_EMU_ASM_SWITCH
+asm(R"(
+    .text
+    .globl cuda_emu_ctx_switch
+    .hidden cuda_emu_ctx_switch
+    .type cuda_emu_ctx_switch,@function
+cuda_emu_ctx_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+    .size cuda_emu_ctx_switch,.-cuda_emu_ctx_switch
+    .section .note.GNU-stack,"",@progbits
+    .text
+)");
+#endif
+
 // test control: run the fibers of every CTA in descending thread order (see cuda_emu.h, CUDA_EMU_ORDER)
 extern "C" __attribute__((visibility("default"))) void cuda_emu_set_reverse(int on) { ::emu::g.reverse_order = (on != 0); }
 '''
