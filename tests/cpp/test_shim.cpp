@@ -286,7 +286,7 @@ int main()
     for (auto& c : cases)
     {
 #ifdef SB200_SHIM_TEST_SMALL
-        if (c.n > 10)
+        if (c.n > 100)
             continue;
 #endif
         Csc A = gen_sparse_data(c.n, c.p);

@@ -121,10 +121,6 @@ static void run_case(int n, double prob, int k, int m)
     const SortRule rules[] = {SortRule::LargestMagn, SortRule::LargestAlge, SortRule::SmallestMagn, SortRule::SmallestAlge, SortRule::BothEnds};
     for (SortRule rule : rules)
     {
-#ifdef SB200_SHIM_TEST_SMALL
-        if (n >= 100 && rule != SortRule::LargestAlge)
-            continue;  // the emulated CPU run keeps one rule at n = 100; the device run (tests/test_gpu_experimental.py) takes all
-#endif
         if (n >= 100 && rule == SortRule::SmallestMagn)
             continue;  // converges after > 1000 matrix operations
         HermEigsSolver<SparseHermMatProd<cd>> eigs(op, k, m);
@@ -203,6 +199,7 @@ static void run_complex_gen(int n, double prob, int k, int m)
 int main()
 {
     run_complex_gen(10, 0.5, 3, 6);
+    run_complex_gen(100, 0.1, 10, 30);
     {
         RankOneUpdateOp op(40);
         HermEigsSolver<RankOneUpdateOp> eigs(op, 4, 12);

@@ -46,7 +46,7 @@ def compressed_matrix(draw, complex_values=False):
 
 FMT = st.sampled_from([{}, {"SB200_SPMV_FORMAT": "sell", "SB200_SELL_MAX_FILL": "1000"}, {"SB200_FORCE_CHUNK_RANKS": "2", "SB200_AG_CHUNKS": "3"},
                        {"SB200_SPMV_FORMAT": "sell", "SB200_SELL_MAX_FILL": "1000", "SB200_FORCE_CHUNK_RANKS": "3", "SB200_AG_CHUNKS": "2"}])
-SETTINGS = dict(max_examples=120, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+SETTINGS = dict(max_examples=200, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 
 
 @settings(**SETTINGS)
@@ -109,7 +109,7 @@ def small_sym_problem(draw):
     return M, k, m, rule, kind
 
 
-@settings(max_examples=8, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(prob=small_sym_problem())
 def test_fuzz_sym_solver_follows_oracle(emu, prob):
     # whole pipeline (init, factorisation with its restart heuristics, device restart kernel, compress) against the CPU oracle on random and

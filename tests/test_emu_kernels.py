@@ -72,8 +72,14 @@ def test_emu_sell_fused_step_factorization(emu, threads):
 
 def test_emu_sell_persistent_grid(emu):
     # operands beyond 16384 windows per rank use a persistent grid that strides over the windows; forced here at a small size
-    with X.env(SB200_SELL_PERSISTENT=1):
-        X.test_sell_spmv_matches_csr_and_scipy(emu, 256, 13_000, 0.0008)  # 13 windows > 12 resident CTAs on the 2 emulated SMs
+    n = 13_000  # 13 windows > 12 resident CTAs of 256 threads on the 2 emulated SMs
+    A = sp.random(n, n, density=0.0008, random_state=4, format="csr")
+    x = np.random.default_rng(4).standard_normal(n)
+    with X.env(SB200_SELL_PERSISTENT=1, SB200_SPMV_FORMAT="sell", SB200_SELL_THREADS=256, SB200_SELL_MAX_FILL=100):
+        op = emu.SparseGenMatProd(A)
+        assert op.spmv_layout()["format"] == "sell"
+        assert np.abs(op.perform_op(x) - A @ x).max() <= 1e-13 * np.abs(A @ x).max()
+        X.test_sell_lanczos_factorization(emu, 512)
 
 
 def test_emu_sell_solver(emu):
@@ -113,8 +119,8 @@ def test_emu_herm_factorization(emu):
 
 @pytest.mark.parametrize("selection", [O.LargestMagn, O.LargestAlge, O.SmallestAlge, O.BothEnds])
 @pytest.mark.parametrize("n", [10, 100])
-def test_emu_herm_solver(emu, n, selection):
-    HC.solver_case(emu, n, selection)
+def test_emu_herm_solver(emu_order, n, selection):
+    HC.solver_case(emu_order, n, selection)
 
 
 def test_emu_herm_solver_smallest_magnitude(emu):
@@ -147,8 +153,9 @@ def test_emu_complex_gen_user_operator(emu):
     HC.complex_gen_user_operator_case(emu)
 
 
-def test_emu_complex_gen_solver_n100(emu):
-    HC.complex_gen_solver_case(emu, 100, "LargestReal")
+@pytest.mark.parametrize("rule", ["LargestMagn", "LargestReal", "LargestImag", "SmallestReal"])
+def test_emu_complex_gen_solver_n100(emu_order, rule):
+    HC.complex_gen_solver_case(emu_order, 100, rule)
 
 
 def test_emu_complex_gen_solver_reverse_order(emu_order):
@@ -242,13 +249,13 @@ def _sharded_solve(emu, n, P, rp, ci, v, k, m, kind="sym", fmt_env=None):
     return out
 
 
-@pytest.mark.parametrize("P,fmt", [(3, "csr"), (2, "sell")])
+@pytest.mark.parametrize("P,fmt", [(2, "csr"), (3, "csr"), (2, "sell"), (3, "sell")])
 def test_emu_row_sharded_sym_solver(emu, P, fmt):
     # 1-D row partition, all-gather of the SpMV operand in chunks, all-reduce of the dot products; every rank must run the
     # same iteration (identical operation counts), reproduce the single-rank eigenvalues, and hold its rows of the eigenvectors
     from spectra_b200_emu import synth
 
-    n, k, m = 401, 4, 12
+    n, k, m = 901, 5, 16
     rp, ci, v = synth.csr(n, 12, 3, True)
     A = sp.csr_matrix((v, ci, rp), shape=(n, n))
     fmt_env = dict(SB200_SPMV_FORMAT="sell", SB200_SELL_MAX_FILL=100) if fmt == "sell" else dict(SB200_SPMV_FORMAT="csr")
