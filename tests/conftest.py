@@ -40,12 +40,13 @@ def emu():
     return emu_loader.load()
 
 
-@pytest.fixture(params=["forward", "reverse"])
+@pytest.fixture(params=["forward", "reverse", "rotate"])
 def emu_order(request, emu):
-    """Runs a test twice: with the fibers of a CTA scheduled in ascending and in descending thread order.  A result that depends on
+    """Runs a test three times: with the fibers of a CTA scheduled in ascending order, in descending order, and ascending from a start
+    thread that rotates every scheduling round.  A result that depends on
     the order means code that relies on warp-lockstep execution between two synchronisation points -- a data race under independent
     thread scheduling (this is how the missing __syncwarp() of dense_gen.cu's overflow rescaling was found)."""
-    emu.lib().cuda_emu_set_reverse(1 if request.param == "reverse" else 0)
+    emu.lib().cuda_emu_set_reverse({"forward": 0, "reverse": 1, "rotate": 2}[request.param])
     yield emu
     emu.lib().cuda_emu_set_reverse(0)
 

@@ -141,7 +141,9 @@ struct State
     uint64_t progress = 0;
     const std::function<void()>* body = nullptr;
     int64_t launches = 0;
-    bool reverse_order = [] { const char* e = getenv("CUDA_EMU_ORDER"); return e && e[0] == 'r'; }();
+    bool reverse_order = [] { const char* e = getenv("CUDA_EMU_ORDER"); return e && e[0] == 'r' && e[1] == 'e'; }();
+    int order_mode = [] { const char* e = getenv("CUDA_EMU_ORDER"); return (e && e[0] == 'r' && e[1] == 'o') ? 2 : 0; }();  // "rotate"
+    uint64_t round = 0;
 };
 // One State per OS thread: the ranks of an emulated multi-GPU run are threads of one process (emu_comm.cpp).  Kernel launches of
 // different ranks are serialised by launch_mutex because `__shared__` variables are process-wide statics.
@@ -271,12 +273,14 @@ inline void run_cta(const std::function<void()>& body, const Launch& L)
     while (remaining > 0)
     {
         const uint64_t before = g.progress;
+        g.round++;
         remaining = 0;
         for (int tt = 0; tt < nthreads; tt++)
         {
             // CUDA_EMU_ORDER=reverse runs the fibers of a CTA in descending thread order: results that change with the order expose
             // code that relies on warp-lockstep execution between two synchronisation points (a race under independent thread scheduling)
-            const int t = g.reverse_order ? nthreads - 1 - tt : tt;
+            // order 2 ("rotate"): ascending from a start thread that moves every scheduling round, so that neither end is always first
+            const int t = g.order_mode == 2 ? (tt + (int) ((g.round * 13) % (uint64_t) nthreads)) % nthreads : (g.reverse_order ? nthreads - 1 - tt : tt);
             if (g.done[(size_t) t])
                 continue;
             g.cur = t;

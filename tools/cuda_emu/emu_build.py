@@ -166,7 +166,12 @@ cuda_emu_ctx_switch:
 #endif
 
 // test control: run the fibers of every CTA in descending thread order (see cuda_emu.h, CUDA_EMU_ORDER)
-extern "C" __attribute__((visibility("default"))) void cuda_emu_set_reverse(int on) { ::emu::g.reverse_order = (on != 0); }
+// mode 0: ascending thread order, 1: descending, 2: ascending from a start thread that rotates every scheduling round
+extern "C" __attribute__((visibility("default"))) void cuda_emu_set_reverse(int mode)
+{
+    ::emu::g.reverse_order = (mode == 1);
+    ::emu::g.order_mode = (mode == 2) ? 2 : 0;
+}
 '''
 
 
