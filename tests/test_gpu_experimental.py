@@ -254,7 +254,7 @@ def test_herm_shim_reference_flow_on_gpu(gpu):
 
     import test_cpp_shim as TS
 
-    exe = TS._compile_herm(os.path.dirname(gpu.lib_path()), "spectra_b200")
+    exe = TS._compile_herm(os.path.dirname(gpu.lib_path()), os.path.basename(gpu.lib_path())[3:-3])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ALL PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
@@ -264,6 +264,6 @@ def test_float_shim_flow_on_gpu(gpu):
 
     import test_cpp_shim as TS
 
-    exe = TS._compile_herm(os.path.dirname(gpu.lib_path()), "spectra_b200", "test_shim_float.cpp")
+    exe = TS._compile_herm(os.path.dirname(gpu.lib_path()), os.path.basename(gpu.lib_path())[3:-3], "test_shim_float.cpp")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ALL PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
