@@ -6,6 +6,7 @@
 #ifndef SPECTRA_B200_DENSE_SYM_MAT_PROD_H
 #define SPECTRA_B200_DENSE_SYM_MAT_PROD_H
 
+#include <stdexcept>
 #include <vector>
 
 #include "SparseSymMatProd.h"
@@ -17,15 +18,25 @@ namespace b200 {
 template <typename Scalar>
 struct DenseAsCompressed
 {
-    std::vector<int32_t> outer, inner;
+    std::vector<int64_t> outer;  // 64-bit offsets: n * n passes 2^31 at n = 46341
+    std::vector<int32_t> inner;
     std::vector<Scalar> values;
+    // rows != cols is rejected before a single element is read (the Eigen constructors delegate here)
+    static Index checked_square(Index rows, Index cols, const char* what)
+    {
+        if (rows != cols)
+            throw std::invalid_argument(what);
+        return rows;
+    }
     DenseAsCompressed(Index n, const Scalar* data)
     {
+        if (n < 0 || data == nullptr)
+            throw std::invalid_argument("dense operator: bad matrix");
         outer.resize(static_cast<size_t>(n) + 1);
         inner.resize(static_cast<size_t>(n * n));
         values.assign(data, data + n * n);
         for (Index o = 0; o <= n; o++)
-            outer[static_cast<size_t>(o)] = static_cast<int32_t>(o * n);
+            outer[static_cast<size_t>(o)] = static_cast<int64_t>(o) * n;
         for (Index o = 0; o < n; o++)
             for (Index k = 0; k < n; k++)
                 inner[static_cast<size_t>(o * n + k)] = static_cast<int32_t>(k);
@@ -50,10 +61,9 @@ public:
     }
 #ifdef SPECTRA_B200_HAS_EIGEN
     // Same constructor as the reference (DenseSymMatProd.h:45-53)
-    explicit DenseSymMatProd(const Eigen::Matrix<Scalar, Eigen::Dynamic, Eigen::Dynamic, Flags>& mat) : DenseSymMatProd(mat.rows(), mat.data())
+    explicit DenseSymMatProd(const Eigen::Matrix<Scalar, Eigen::Dynamic, Eigen::Dynamic, Flags>& mat) :
+        DenseSymMatProd(b200::DenseAsCompressed<Scalar>::checked_square(mat.rows(), mat.cols(), "DenseSymMatProd: matrix must be square"), mat.data())
     {
-        if (mat.rows() != mat.cols())
-            throw std::invalid_argument("DenseSymMatProd: matrix must be square");
     }
 #endif
 };
@@ -72,10 +82,9 @@ public:
         create_any(n, m_c.outer.data(), m_c.inner.data(), m_c.values.data(), Flags == SPECTRA_B200_ROWMAJOR, SB200_GENERAL);
     }
 #ifdef SPECTRA_B200_HAS_EIGEN
-    explicit DenseGenMatProd(const Eigen::Matrix<Scalar, Eigen::Dynamic, Eigen::Dynamic, Flags>& mat) : DenseGenMatProd(mat.rows(), mat.data())
+    explicit DenseGenMatProd(const Eigen::Matrix<Scalar, Eigen::Dynamic, Eigen::Dynamic, Flags>& mat) :
+        DenseGenMatProd(b200::DenseAsCompressed<Scalar>::checked_square(mat.rows(), mat.cols(), "DenseGenMatProd: matrix must be square"), mat.data())
     {
-        if (mat.rows() != mat.cols())
-            throw std::invalid_argument("DenseGenMatProd: matrix must be square");
     }
 #endif
 };

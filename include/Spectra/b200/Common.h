@@ -199,6 +199,17 @@ protected:
             m_inner32[static_cast<size_t>(p)] = static_cast<int32_t>(inner[p]);
         create(n, outer, true, m_inner32.data(), values, row_major, mode, shift_solve);
     }
+    // 64-bit offsets with 32-bit inner indices (the dense wrappers: n * n entries can pass 2^31 while every index stays below n)
+    void create_any(Index n, const int64_t* outer, const int32_t* inner, const double* values, bool row_major, int mode, bool shift_solve = false)
+    {
+        if (n >= (Index(1) << 31))
+            throw std::invalid_argument("matrix order must be below 2^31");
+        create(n, outer, true, inner, values, row_major, mode, shift_solve);
+    }
+    void create_any(Index n, const int64_t* outer, const int32_t* inner, const float* values, bool row_major, int mode, bool shift_solve = false)
+    {
+        create_any(n, outer, inner, widen(values, static_cast<Index>(outer[n]), m_values64), row_major, mode, shift_solve);
+    }
     int64_t outer_at(Index i) const
     {
         return m_outer64 ? static_cast<const int64_t*>(m_outer)[i] : static_cast<int64_t>(static_cast<const int32_t*>(m_outer)[i]);

@@ -253,6 +253,10 @@ int sb200_gen_destroy(sb200_gen_solver* s);
  * ------------------------------------------------------------------------------------------ */
 /* TridiagEigen::compute (TridiagEigen.h:121-210): evals (m, unsorted) and evecs (m x m). */
 int sb200_dense_tridiag_eigen(int64_t m, const double* H, double* evals, double* evecs);
+/* Givens<double>::compute_rotation (Givens.h:166-205, StableScaling :28-86; sign convention test/Givens.cpp:82-95): `count` independent
+ * rotations, (r, c, s) with c*x - s*y = r, s*x + c*y = 0.  variant 0 = the reference's formulas (Taylor branch included),
+ * 1 = the rsqrt form the device QR kernels call, 2 = Eigen's JacobiRotation::makeGivens (TridiagEigen.h:79-80). */
+int sb200_dense_givens(int variant, int64_t count, const double* x, const double* y, double* r, double* c, double* s);
 /* TridiagQR (kind 0, UpperHessenbergQR.h:459-709) / UpperHessenbergQR (kind 1, :46-447):
  * QtHQ = Q'HQ and Q = G1*G2*... for H - shift*I = QR. */
 int sb200_dense_shifted_qr(int kind, int64_t m, const double* H, double shift, double* QtHQ, double* Q);

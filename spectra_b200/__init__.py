@@ -171,6 +171,20 @@ class Comm:
             pass
 
 
+def _result_buffer(y_out, count, dtype):
+    """(array handed to the C ABI, user array to copy back into or None).  A caller-supplied y_out is written in place only when it
+    is a C-contiguous array of exactly the element type and length the library writes; anything else (float32, strided, a list) gets
+    the result through a temporary so that a wrong buffer can never be overrun."""
+    if y_out is None:
+        return np.empty(count, dtype=dtype), None
+    if not isinstance(y_out, np.ndarray) or y_out.size != count:
+        raise InvalidArgument(1, "y_out has the wrong length")
+    if y_out.dtype == np.dtype(dtype) and y_out.flags.c_contiguous and y_out.flags.writeable:
+        return y_out, None
+    return np.empty(count, dtype=dtype), y_out
+
+
+
 class _SparseOp:
     """Device-resident CSR operator.  `mat` is a scipy.sparse CSC/CSR matrix or a tuple
     (n, outer, inner, values, 'col'|'row') with Eigen's compressed layout."""
@@ -212,7 +226,6 @@ class _SparseOp:
                 order = "col"
             if mat.shape[0] != mat.shape[1]:
                 raise InvalidArgument(1, "matrix must be square")
-            mat.sort_indices()
             n, outer, inner, vals = mat.shape[0], mat.indptr, mat.indices, mat.data
         outer = np.ascontiguousarray(outer)
         if outer.dtype not in (np.int32, np.int64):
@@ -256,8 +269,11 @@ class _SparseOp:
         x = np.ascontiguousarray(x_in, dtype=np.float64)
         if x.shape != (self.n,):
             raise InvalidArgument(1, "x has the wrong length")
-        y = y_out if y_out is not None else np.empty(self.nrows_local)
+        y, user = _result_buffer(y_out, self.nrows_local, np.float64)
         _check(lib().sb200_op_perform_op(self.h, _p(x), _p(y)))
+        if user is not None:
+            user.reshape(-1)[:] = y
+            return user
         return y
 
     def __matmul__(self, X):
@@ -367,8 +383,11 @@ class UserOp:
 
     def perform_op(self, x_in, y_out=None):
         x = np.ascontiguousarray(x_in, dtype=self._dtype)
-        y = y_out if y_out is not None else np.empty(self.n, dtype=self._dtype)
+        y, user = _result_buffer(y_out, self.n, self._dtype)
         _check_op(self, lib().sb200_op_perform_op(self.h, _p(x), _p(y)))
+        if user is not None:
+            user.reshape(-1)[:] = y
+            return user
         return y
 
     def close(self):
@@ -418,7 +437,6 @@ class SparseHermMatProd:
                 order = "col"
             if mat.shape[0] != mat.shape[1]:
                 raise InvalidArgument(1, "matrix must be square")
-            mat.sort_indices()
             n, outer, inner, vals = mat.shape[0], mat.indptr, mat.indices, mat.data
         outer = np.ascontiguousarray(outer)
         if outer.dtype not in (np.int32, np.int64):
@@ -451,8 +469,11 @@ class SparseHermMatProd:
         x = np.ascontiguousarray(x_in, dtype=np.complex128)
         if x.shape != (self.n,):
             raise InvalidArgument(1, "x has the wrong length")
-        y = y_out if y_out is not None else np.empty(self.n, dtype=np.complex128)
+        y, user = _result_buffer(y_out, self.n, np.complex128)
         _check(lib().sb200_op_perform_op(self.h, _p(x), _p(y)))
+        if user is not None:
+            user.reshape(-1)[:] = y
+            return user
         return y
 
     def __matmul__(self, X):
@@ -729,6 +750,17 @@ class dense:
         Z = np.empty((m, m), order="F")
         _check(lib().sb200_dense_tridiag_eigen(C.c_int64(m), _p(H), _p(ev), _p(Z)))
         return ev, Z
+
+    @staticmethod
+    def givens(x, y, variant=0):
+        """(r, c, s) arrays of Givens<double>::compute_rotation (Givens.h:166-205) evaluated on the device, one rotation per entry."""
+        x = np.ascontiguousarray(np.atleast_1d(x), dtype=np.float64)
+        y = np.ascontiguousarray(np.atleast_1d(y), dtype=np.float64)
+        if x.shape != y.shape:
+            raise InvalidArgument(1, "x and y must have the same length")
+        r, c, s = (np.empty(x.size) for _ in range(3))
+        _check(lib().sb200_dense_givens(int(variant), C.c_int64(x.size), _p(x), _p(y), _p(r), _p(c), _p(s)))
+        return r, c, s
 
     @staticmethod
     def shifted_qr(H, shift, kind="tridiag"):

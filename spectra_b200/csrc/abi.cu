@@ -71,6 +71,17 @@ using namespace sb200;
         sb200::set_last_error("host out of memory"); \
         return SB200_RUNTIME;                      \
     }                                              \
+    catch (const std::invalid_argument& e)         \
+    {                                              \
+        /* thrown by a user-defined C++ OpType inside the callback trampoline: keep its type across the C boundary */ \
+        sb200::set_last_error(e.what());           \
+        return SB200_INVALID_ARGUMENT;             \
+    }                                              \
+    catch (const std::logic_error& e)              \
+    {                                              \
+        sb200::set_last_error(e.what());           \
+        return SB200_LOGIC;                        \
+    }                                              \
     catch (const std::exception& e)                \
     {                                              \
         sb200::set_last_error(e.what());           \
@@ -324,7 +335,7 @@ int sb200_op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev, int r
     if (!x_dev)
     {
         // benchmark convenience: x = ones, y = scratch
-        std::vector<double> ones((size_t) op->A.n, 1.0);
+        std::vector<double> ones((size_t) op->A.n * (op->cplx ? 2 : 1), 1.0);  // complex operators: interleaved (re, im)
         xb.alloc(ones.size());
         SB200_CUDA_CHECK(cudaMemcpyAsync(xb.get(), ones.data(), sizeof(double) * ones.size(), cudaMemcpyHostToDevice, op->stream));
         SB200_CUDA_CHECK(cudaStreamSynchronize(op->stream));
@@ -332,7 +343,7 @@ int sb200_op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev, int r
     }
     if (!y_dev)
     {
-        yb.alloc((size_t) std::max<int64_t>(op->A.nrows, 1));
+        yb.alloc((size_t) std::max<int64_t>(op->A.nrows, 1) * (op->cplx ? 2 : 1));
         y_dev = yb.get();
     }
     SB200_CUDA_CHECK(cudaEventRecord(op->ev0, op->stream));
@@ -375,6 +386,10 @@ int sb200_sym_create_shift(sb200_op* op, int64_t nev, int64_t ncv, double sigma,
     ABI_TRY
     ABI_NONNULL(out);
     ABI_NONNULL(op);
+    // The reference makes a missing set_shift() a compile error (SymEigsShiftSolver.h:193); here the operator must be a shift-solve
+    // operator (sb200_op_create_shift_solve) or a user callback that applies (A - sigma I)^{-1} itself, and it must be real.
+    SB200_REQUIRE(!op->cplx, SB200_INVALID_ARGUMENT, "SymEigsShiftSolver needs a real operator");
+    SB200_REQUIRE(op->band || op->cb, SB200_INVALID_ARGUMENT, "SymEigsShiftSolver needs a shift-solve operator (sb200_op_create_shift_solve) or a user-defined one");
     // Base(op, nev, ncv) argument checks first, then op.set_shift(sigma) (SymEigsShiftSolver.h:190-195)
     sb200_sym_solver* s = sym_create(op, nev, ncv, true, sigma);
     if (op->band)
@@ -604,6 +619,29 @@ int sb200_dense_tridiag_eigen(int64_t m, const double* H, double* evals, double*
         throw Error(SB200_RUNTIME, "TridiagEigen: eigen decomposition failed");
     SB200_CUDA_CHECK(cudaMemcpy(evals, dE.get(), sizeof(double) * m, cudaMemcpyDeviceToHost));
     SB200_CUDA_CHECK(cudaMemcpy(evecs, dZ.get(), sizeof(double) * m * m, cudaMemcpyDeviceToHost));
+    ABI_CATCH
+}
+int sb200_dense_givens(int variant, int64_t count, const double* x, const double* y, double* r, double* c, double* s)
+{
+    ABI_TRY
+    ABI_NONNULL(x);
+    ABI_NONNULL(y);
+    ABI_NONNULL(r);
+    ABI_NONNULL(c);
+    ABI_NONNULL(s);
+    device_info();
+    SB200_REQUIRE(variant >= 0 && variant <= 2 && count >= 0, SB200_INVALID_ARGUMENT, "givens: bad arguments");
+    if (count > 0)
+    {
+        DevBuf<double> dx(count), dy(count), dr(count), dc(count), ds(count);
+        SB200_CUDA_CHECK(cudaMemcpy(dx.get(), x, sizeof(double) * count, cudaMemcpyHostToDevice));
+        SB200_CUDA_CHECK(cudaMemcpy(dy.get(), y, sizeof(double) * count, cudaMemcpyHostToDevice));
+        launch_givens_batch(variant, count, dx.get(), dy.get(), dr.get(), dc.get(), ds.get(), 0);
+        SB200_CUDA_CHECK(cudaDeviceSynchronize());
+        SB200_CUDA_CHECK(cudaMemcpy(r, dr.get(), sizeof(double) * count, cudaMemcpyDeviceToHost));
+        SB200_CUDA_CHECK(cudaMemcpy(c, dc.get(), sizeof(double) * count, cudaMemcpyDeviceToHost));
+        SB200_CUDA_CHECK(cudaMemcpy(s, ds.get(), sizeof(double) * count, cudaMemcpyDeviceToHost));
+    }
     ABI_CATCH
 }
 int sb200_dense_shifted_qr(int kind, int64_t m, const double* H, double shift, double* QtHQ, double* Q)

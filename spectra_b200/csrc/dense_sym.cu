@@ -637,7 +637,36 @@ void ensure_smem(const void* fn, size_t bytes)
         SB200_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes));
 }
 
+// Unit-tier hook for Givens<double>::compute_rotation (Givens.h:166-205; StableScaling :28-86): one rotation per thread.
+// variant 0 = givens_rotation (the reference's formulas, Taylor branch included), 1 = givens_rotation_fast (the form the QR
+// kernels of this file call: rsqrt + fallback to variant 0), 2 = make_givens (Eigen's JacobiRotation::makeGivens as used by
+// TridiagEigen.h:79-80, r returned through its third argument).
+__global__ void givens_batch_kernel(int variant, int64_t count, const double* x, const double* y, double* r, double* c, double* s)
+{
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count)
+        return;
+    double rr = 0.0, cc = 0.0, ss = 0.0;
+    if (variant == 0)
+        givens_rotation(x[t], y[t], rr, cc, ss);
+    else if (variant == 1)
+        givens_rotation_fast(x[t], y[t], rr, cc, ss);
+    else
+        make_givens(x[t], y[t], cc, ss, &rr);
+    r[t] = rr;
+    c[t] = cc;
+    s[t] = ss;
+}
+
 }  // namespace
+
+void launch_givens_batch(int variant, int64_t count, const double* x, const double* y, double* r, double* c, double* s, cudaStream_t stream)
+{
+    if (count <= 0)
+        return;
+    givens_batch_kernel<<<(unsigned) ((count + 127) / 128), 128, 0, stream>>>(variant, count, x, y, r, c, s);
+    SB200_CUDA_CHECK(cudaGetLastError());
+}
 
 void launch_sym_restart(double* H, int m, int nev, const FacCtl* ctl, int selection, double tol, double* ritz_val, double* ritz_est, double* ritz_vec,
                         int* ritz_conv, double* Q, SymRestartOut* out, int do_restart, cudaStream_t stream)

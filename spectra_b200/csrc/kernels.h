@@ -247,6 +247,7 @@ void launch_sym_restart(double* H, int m, int nev, const FacCtl* ctl, int select
                         int* ritz_conv, double* Q, SymRestartOut* out, int do_restart, cudaStream_t stream);
 // standalone pieces for the unit tier
 void launch_tridiag_eigen(const double* H, int m, double* evals, double* evecs, int* info, cudaStream_t stream);
+void launch_givens_batch(int variant, int64_t count, const double* x, const double* y, double* r, double* c, double* s, cudaStream_t stream);
 void launch_tridiag_qr(const double* H, int m, double shift, double* QtHQ, double* Q, cudaStream_t stream);
 
 }  // namespace sb200

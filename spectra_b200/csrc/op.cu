@@ -120,15 +120,22 @@ static void finish_op(sb200_op* op)
     }
     else
         split_column_blocks(op->A, choose_col_blocks(op->A.n), op->stream);
-    // experimental (round 1: written, not yet measured on a GPU): sliced layout + lane-per-row kernels, see spmv.cu
-    if (const char* e = std::getenv("SB200_SPMV_FORMAT"))
-        if (std::strcmp(e, "sell") == 0)
+    // Device layout of the column blocks.  Default ("auto"): the sliced layout (SELL-32 in 1024-row windows, lane-per-row kernels, spmv.cu)
+    // whenever its padding stays below SB200_SELL_MAX_FILL (1.3) -- measured on a B200 at n = 1e7, 20 nnz/row: 0.884 ms vs 1.051 ms for
+    // the CSR-vector kernels on uniformly random columns, 0.505 vs 0.698 ms on band columns (profiles/r2_spmv_variants_n1e7.log).
+    // Operands with very uneven rows (fill above the limit) keep the CSR-vector kernels; SB200_SPMV_FORMAT=csr forces them.
+    {
+        const char* e = std::getenv("SB200_SPMV_FORMAT");
+        const bool want_sell = (e == nullptr) || std::strcmp(e, "sell") == 0 || std::strcmp(e, "auto") == 0;
+        SB200_REQUIRE(want_sell || std::strcmp(e, "csr") == 0, SB200_INVALID_ARGUMENT, "SB200_SPMV_FORMAT must be auto, sell or csr");
+        if (want_sell)
         {
             double max_fill = 1.3;
             if (const char* f = std::getenv("SB200_SELL_MAX_FILL"))
                 max_fill = std::max(1.0, std::atof(f));
             build_sell_layout(op->A, max_fill, op->stream);
         }
+    }
     op->plan = make_spmv_plan(op->A);
     if (P > 1)
     {

@@ -1,5 +1,5 @@
 """Parity cases of the complex Hermitian path, written against a backend module `sb` with the API of spectra_b200:
-run on a device by tests/test_gpu_experimental.py and on the kernel-logic emulator by tests/test_emu_kernels.py.
+run on a device by tests/test_gpu_layouts_complex.py and on the kernel-logic emulator by tests/test_emu_kernels.py.
 Tolerances: operator 1e-13 relative; factorisation identities 1e-12 (test/Arnoldi.cpp); solver ||AU - UD||_inf <= 1e-9
 (test/HermEigs.cpp:66-70) and eigenvalues within 1e-10 relative of the oracle (oracle/herm.py)."""
 import numpy as np

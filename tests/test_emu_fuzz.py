@@ -10,7 +10,7 @@ import pytest
 from hypothesis import HealthCheck, given, settings
 from hypothesis import strategies as st
 
-import test_gpu_experimental as X
+import test_gpu_layouts_complex as X
 
 
 def _dense_model(n, outer, inner, vals, order, mode):

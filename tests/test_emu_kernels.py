@@ -16,7 +16,7 @@ import scipy.sparse as sp
 
 import herm_cases as HC
 import oracle as O
-import test_gpu_experimental as X
+import test_gpu_layouts_complex as X
 from helpers import sym_full
 
 

@@ -196,6 +196,48 @@ def test_gen_eigs_full_size_properties(gpu):
     assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1:] == runs[1][1:]
 
 
+def test_gen_eigs_c3_unplanted_history(gpu):
+    # BASELINE config C3 as stated: G_gen(n = 1e6, 20 nnz/row, seed 1), k = 10, ncv = 30, LargestMagn -- NO planted eigenvalues.  The
+    # spectrum fills a disc (circular law) whose rim is packed with eigenvalues of nearly equal modulus, so neither the reference nor
+    # this solver converges within the default 1000 restarts; what can be pinned is (1) the Arnoldi factorisation itself against the
+    # oracle's at full size and (2) the maxit-bounded run: status NotConverging and the oracle's operation / iteration counts
+    # (tests/golden/baseline_C3.json, maxit = 40).
+    import json
+    import os
+
+    from spectra_b200 import synth
+
+    n, k, m = 1_000_000, 10, 30
+    rp, ci, v = synth.csr(n, 20, 1, False)
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    op = gpu.SparseGenMatProd.from_csr_slab(n, 0, rp, ci, v)
+    g = gpu.GenEigsSolver(op, k, m)
+    g.init()
+    g.factorize_from(1, m)
+    fz = g.factorization()
+    V, H, f = fz["V"], fz["H"], fz["f"]
+    E = A @ V - V @ H
+    E[:, -1] -= f
+    hs = np.abs(H).max()
+    assert np.abs(E).max() <= 1e-12 * max(1.0, hs)                     # A V = V H + f e'   (test/Arnoldi.cpp:70-76)
+    assert np.abs(V.T @ V - np.eye(m)).max() <= 1e-12                  # V'V = I
+    assert np.abs(V.T @ f).max() <= 1e-12 * max(1.0, np.linalg.norm(f))
+    ref = O.factorize(O.Csr.adopt(n, rp, ci, v), m, kind="arnoldi")
+    assert np.abs(H - ref["H"]).max() <= 1e-9 * hs                      # same Hessenberg matrix as the CPU oracle from the same start
+    assert abs(fz["beta"] - ref["beta"]) <= 1e-9 * max(1.0, ref["beta"])
+    del V, E, fz
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "baseline_C3.json")
+    with open(path) as fh:
+        gold = json.load(fh)
+    g2 = gpu.GenEigsSolver(op, k, m)
+    g2.init()
+    nconv = g2.compute(gpu.SortRule.LargestMagn, gold["maxit"])
+    assert g2.info() == gpu.CompInfo.NotConverging and gold["info"] == O.NotConverging
+    assert nconv == gold["nconv"] and len(g2.eigenvalues()) == nconv
+    assert g2.num_iterations() == gold["niter"]
+    assert abs(g2.num_operations() - gold["nops"]) <= 20
+
+
 @pytest.mark.parametrize("n,k,m", [(100, 10, 30), (1000, 20, 50)])
 def test_gen_eigs_against_golden_spectra(gpu, n, k, m):
     import golden_cases as GC

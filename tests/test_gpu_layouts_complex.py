@@ -1,12 +1,11 @@
-"""GPU tests of code paths that were written after round 1's GPU budget was spent and have therefore NOT run on a device yet.
-They are skipped unless SB200_EXPERIMENTAL=1 so that the verified suite stays meaningful; the first GPU call of the next round
-runs them (tools/run_experimental.sh).  Everything here is opt-in at run time as well: the default product path is unchanged.
+"""GPU tests of the sliced (SELL-32) operand layout and of the complex scalar paths.  First device run: round 2, call 1
+(profiles/r2_layout_complex_tests.log, 94 passed); since then part of the default `-m gpu` suite.
 
-Covered: the sliced-CSR layout + lane-per-row SpMV kernels (SB200_SPMV_FORMAT=sell; csr_build.cu build_sell_layout, spmv.cu
-sell_plain_kernel / sell_step_kernel) at the operator, factorisation and solver tiers; the gather microbenchmark; the complex Hermitian
-path (SparseHermMatProd / HermEigsSolver, user-defined complex operators); the complex GenEigsSolver (complex Arnoldi, the one-warp
-complex restart kernel of dense_gen_z.cu, complex restart GEMM); the C++ shim flows for complex and float scalars.  All of them pass on
-the kernel-logic emulator (tests/test_emu_kernels.py, tests/test_cpp_shim.py) in both fiber orders."""
+Covered: the sliced layout + lane-per-row SpMV kernels (the default layout; csr_build.cu build_sell_layout, spmv.cu sell_plain_kernel /
+sell_step_kernel) against the CSR-vector kernels (SB200_SPMV_FORMAT=csr) and SciPy at the operator, factorisation and solver tiers; the
+gather microbenchmark; the complex Hermitian path (SparseHermMatProd / HermEigsSolver, user-defined complex operators); the complex
+GenEigsSolver (complex Arnoldi, the one-warp complex restart kernel of dense_gen_z.cu, complex restart GEMM); the C++ shim flows for
+complex and float scalars."""
 import contextlib
 import os
 
@@ -17,8 +16,7 @@ import scipy.sparse as sp
 import oracle as O
 from helpers import sym_full
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SB200_EXPERIMENTAL") != "1", reason="not yet verified on a GPU (round-1 budget spent); set SB200_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 @contextlib.contextmanager
@@ -49,7 +47,8 @@ def test_sell_spmv_matches_csr_and_scipy(gpu, threads, n, density):
     A = _rand_csr(n, density, n)
     x = rng.standard_normal(n)
     y0 = A @ x
-    op_csr = gpu.SparseGenMatProd(A)
+    with env(SB200_SPMV_FORMAT="csr"):
+        op_csr = gpu.SparseGenMatProd(A)
     assert op_csr.spmv_layout()["format"] == "csr"
     y_csr = op_csr.perform_op(x)
     with env(SB200_SPMV_FORMAT="sell", SB200_SELL_THREADS=threads, SB200_SELL_MAX_FILL=100):

@@ -124,6 +124,41 @@ def test_restart_gemm_compress(gpu, impl, n, m, kk):
         assert abs(nrm2 - fref @ fref) <= 1e-13 * (fref @ fref)
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_givens_rotation_device(gpu, variant):
+    # Givens<double>::compute_rotation on the device (Givens.h:166-205, StableScaling :28-86), the reference's own test
+    # (test/Givens.cpp:64-99: c x - s y = r and s x + c y = 0 to 1e-12 on 100000 draws from U(-100, 100) with 10 % exact zeros), plus the
+    # branches that test never reaches: the Taylor branch (ratio < 0.1 eps^(1/4) = 1.22e-5), both orderings |x| >< |y|, every sign
+    # combination, extreme magnitudes.  variant 0 = the reference's formulas, 1 = the rsqrt form the QR kernels call, 2 = makeGivens.
+    rng = np.random.default_rng(0)
+    nsim = 100_000
+    x = np.where(rng.random(nsim) < 0.1, 0.0, rng.uniform(-100, 100, nsim))
+    y = np.where(rng.random(nsim) < 0.1, 0.0, rng.uniform(-100, 100, nsim))
+    # Taylor branch: ratios from 1e-5 down to 1e-17, both orderings, all signs
+    big = rng.uniform(0.5, 2.0, 4000) * rng.choice([-1.0, 1.0], 4000)
+    small = big * 10.0 ** rng.uniform(-17, -4.9, 4000) * rng.choice([-1.0, 1.0], 4000)
+    x = np.concatenate([x, big, small, [3.0, -3.0, 0.0, 0.0, 0.0, 1e200, 1e-200, -1e150, 5e-324, 1.0]])
+    y = np.concatenate([y, small, big, [0.0, 0.0, 4.0, -4.0, 0.0, 1e200, 1e-200, 1e150, 1.0, 5e-324]])
+    r, c, s = gpu.dense.givens(x, y, variant)
+    scale = np.maximum(1.0, np.hypot(x, y))
+    assert np.abs(c * x - s * y - r)[:nsim].max() <= 1e-12 and np.abs((c * x - s * y - r) / scale).max() <= 4e-16 * 4
+    assert np.abs((s * x + c * y) / scale).max() <= 4e-16 * 4 and np.abs(s * x + c * y)[:nsim].max() <= 1e-12
+    assert np.all(r >= 0.0) and np.abs(c * c + s * s - 1.0).max() <= 1e-15 * 4
+    # sign convention of the special cases (Givens.h:176-192; makeGivens: c = sign(p), s = 0 / c = 0, s = -sign(q))
+    k = len(x) - 10
+    assert (c[k], s[k], r[k]) == (1.0, 0.0, 3.0) and (c[k + 1], s[k + 1], r[k + 1]) == (-1.0, 0.0, 3.0)
+    assert (c[k + 2], s[k + 2], r[k + 2]) == (0.0, -1.0, 4.0) and (c[k + 3], s[k + 3], r[k + 3]) == (0.0, 1.0, 4.0)
+    assert (c[k + 4], s[k + 4], r[k + 4]) == (1.0, 0.0, 0.0)
+    # agreement with the CPU oracle's restatement of Givens.h (variants 0 and 1 implement it, to a few ulp)
+    if variant < 2:
+        ref = np.array([O.givens(a, b) for a, b in zip(x[nsim:], y[nsim:])])
+        ref_main = np.array([O.givens(a, b) for a, b in zip(x[:2000], y[:2000])])
+        tol = 4.5e-16 if variant == 0 else 1e-15  # device hypot / rsqrt are within 1 ulp of the correctly rounded host functions
+        for got, want in ((r[nsim:], ref[:, 0]), (c[nsim:], ref[:, 1]), (s[nsim:], ref[:, 2]), (r[:2000], ref_main[:, 0]), (c[:2000], ref_main[:, 1]),
+                          (s[:2000], ref_main[:, 2])):
+            assert np.all(np.abs(got - want) <= tol * np.maximum(np.abs(want), 1e-300)), variant
+
+
 @pytest.mark.parametrize("m", [2, 3, 6, 20, 60, 64])
 def test_tridiag_qr_device(gpu, m):
     # test/QR.cpp:115-129: Q orthogonal, Q'(T - sI) upper triangular, Q'TQ = D (1e-12, scaled)
@@ -367,6 +402,17 @@ def test_sym_eigs_medium_vs_oracle_and_arpack(gpu):
     assert np.abs(np.sort(evals) - np.sort(w)).max() <= 1e-10 * np.abs(w).max()
 
 
+def baseline_golden(name):
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"baseline_{name}.json")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated (tests/golden/make_baseline_golden.py {name})")
+    with open(path) as f:
+        return json.load(f)
+
+
 def test_sym_eigs_full_size_properties(gpu):
     # BASELINE config C2: n = 1e6, nnz/row = 20, k = 20, ncv = 60.  Size-independent properties only.
     from spectra_b200 import synth
@@ -384,6 +430,14 @@ def test_sym_eigs_full_size_properties(gpu):
     res = np.linalg.norm(A @ X - X * evals, axis=0) / np.abs(evals)
     assert res.max() <= 1e-10
     assert np.abs(X.T @ X - np.eye(20)).max() <= 1e-10
+    # parity with the CPU oracle's full solve of the same problem (tests/golden/baseline_C2.json, make_baseline_golden.py):
+    # north_star's "eigenvalues within 1e-10 relative", equal nconv, and the same restart history up to rounding-level decisions
+    g = baseline_golden("C2")
+    ref = np.array(g["eigenvalues"])
+    assert nconv == g["nconv"] and len(evals) == len(ref)
+    assert np.abs(evals - ref).max() <= 1e-10 * np.abs(ref).max()
+    assert np.abs(evals - ref).max() / np.abs(ref).min() <= 1e-10
+    assert abs(eigs.num_iterations() - g["niter"]) <= 2 and abs(eigs.num_operations() - g["nops"]) <= 2 * 40
     # run-to-run bit reproducibility (fixed-order reductions)
     eigs.init()
     eigs.compute(gpu.SortRule.LargestAlge)
@@ -415,6 +469,12 @@ def test_sym_eigs_c4_size_properties(gpu):
     res = np.linalg.norm(A @ X - X * evals, axis=0) / np.abs(evals)
     assert res.max() <= 1e-10
     assert np.abs(X.T @ X - np.eye(20)).max() <= 1e-10
+    # parity with the CPU oracle's full solve of the bench workload (tests/golden/baseline_C4.json; hours of CPU time, generated once)
+    g = baseline_golden("C4")
+    ref = np.array(g["eigenvalues"])
+    assert nconv == g["nconv"] and len(evals) == len(ref)
+    assert np.abs(evals - ref).max() / np.abs(ref).min() <= 1e-10
+    assert abs(eigs.num_iterations() - g["niter"]) <= 3 and abs(eigs.num_operations() - g["nops"]) <= 3 * 40
 
 
 def test_column_blocked_operator_and_solver(gpu, monkeypatch):
