@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-ops", type=int, default=12, help="matrix operations in the bounded CPU sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--skip-experimental", action="store_true", help="do not run tools/experimental_probe.py (opt-in code paths) after the timed work")
+    ap.add_argument("--skip-configs", action="store_true", help="do not run the other BASELINE configurations (C2, C3, C5) after the timed work")
     return ap.parse_args()
 
 
@@ -119,8 +119,34 @@ def pinned_alloc():
     return alloc, keep
 
 
+def host_threads():
+    """Hardware threads this process may use.  Deliberately NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1, which would
+    silently shrink the CPU arm at N > 1; the oracle takes its team size as an explicit num_threads() clause."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def golden_full_solves():
+    """Full CPU solves of the BASELINE configurations, run once with tests/golden/make_baseline_golden.py and committed (the n = 1e7
+    solve takes hours): operations, seconds, thread count and the host they were timed on."""
+    out = {}
+    for name in ("C2", "C4"):
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", f"baseline_{name}.json")) as fh:
+                g = json.load(fh)
+            out[name] = {"nops": g["nops"], "niter": g["niter"], "nconv": g["nconv"], "seconds": g["seconds"], "threads": g["threads"],
+                         "spmv_iters_per_sec": g["nops"] / g["seconds"], "host": "development container, 8 vCPU (not the GPU box)"}
+        except (OSError, KeyError, ValueError):
+            pass
+    return out
+
+
 def run_reference(args, n):
-    """The reference algorithm (CPU restatement in oracle/, all host threads) on bounded samples of the workload."""
+    """The reference algorithm (CPU restatement in oracle/) on bounded samples of the workload: once single-threaded -- what the
+    reference, a single-threaded header library, does as shipped -- and once with the fastest OpenMP team of this host.  `value` is the
+    team figure (the stronger baseline); both are in the line so that ratios at different N compare like with like."""
     from spectra_b200 import dist, synth
     rank, _, world = dist.env_rank()
     if rank != 0:
@@ -129,9 +155,7 @@ def run_reference(args, n):
 
     rp, ci, v = synth.csr(n, args.nnz_per_row, args.seed, True)
     A = O.Csr.adopt(n, rp, ci, v)
-    # "all the host threads it can use": the OpenMP team size is calibrated on the operator itself, because on a
-    # multi-socket or CPU-quota'd box the largest team is not the fastest one
-    avail = max(1, min(O.max_threads(), len(os.sched_getaffinity(0))))
+    avail = host_threads()
     cands = sorted({t for t in (1, 4, 8, 16, 32, 64, 128, avail) if t <= avail})
     xcal = np.ones(n)
     calib = {}
@@ -143,22 +167,29 @@ def run_reference(args, n):
         calib[t] = time.perf_counter() - t0
     threads = min(calib, key=calib.get)
     del xcal
-    times, ops = [], 0
-    for it in range(args.warmup + args.steps):
-        r = O.sym_eigs(A, args.nev, args.ncv, O.LargestAlge, 1000, args.tol, threads=threads, op_limit=args.cpu_sample_ops, want_vectors=False)
-        if it >= args.warmup:
-            times.append(r.seconds)
-            ops = r.nops
-    sec = float(np.mean(times))
+
+    def sample(nthreads, reps, warm):
+        times, ops = [], 0
+        for it in range(warm + reps):
+            r = O.sym_eigs(A, args.nev, args.ncv, O.LargestAlge, 1000, args.tol, threads=nthreads, op_limit=args.cpu_sample_ops, want_vectors=False)
+            if it >= warm:
+                times.append(r.seconds)
+                ops = r.nops
+        return ops, float(np.mean(times))
+
+    ops, sec = sample(threads, args.steps, args.warmup)
+    ops1, sec1 = sample(1, 1, 0)
     value = ops / sec
-    sample = (f"init + first {ops - 2} Lanczos steps (op_limit={args.cpu_sample_ops}) of the n={n} solve, {threads} OpenMP threads "
-              f"(fastest team of {cands} on the SpMV; {avail} hardware threads available)")
+    what = (f"init + first {ops - 2} Lanczos steps (op_limit={args.cpu_sample_ops}) of the n={n} solve, {threads} OpenMP threads "
+            f"(fastest team of {cands} on the SpMV; {avail} hardware threads available, OMP_NUM_THREADS ignored)")
     line = {
         "impl": "reference", "metric": "spmv_iters_per_sec", "value": value, "unit": "SpMV-iters/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, n),
-        "cpu_baseline": {"value": value, "unit": "SpMV-iters/s", "cores": threads, "kind": "port", "sample": sample,
-                         "spmv_seconds_by_team": {str(k): round(val, 4) for k, val in calib.items()}},
+        "cpu_baseline": {"value": value, "unit": "SpMV-iters/s", "cores": threads, "kind": "port", "sample": what,
+                         "single_thread_value": ops1 / sec1, "single_thread_note": "the reference as shipped is single-threaded; same sample, 1 thread",
+                         "spmv_seconds_by_team": {str(k): round(val, 4) for k, val in calib.items()},
+                         "full_solves_cached": golden_full_solves()},
         "e2e": {"value": value, "unit": "SpMV-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -169,6 +200,45 @@ def workload_config(args, n):
     return {"workload": f"SymEigsSolver<SparseSymMatProd<double>> G_sym n={n} nnz/row={args.nnz_per_row} nev={args.nev} ncv={args.ncv} tol={args.tol:g} "
                         f"selection=LargestAlge init=SimpleRandom(0)", "n": n, "nnz_per_row": args.nnz_per_row, "nev": args.nev, "ncv": args.ncv,
             "parallelism": f"row-sharded x{args.gpus}", "l2": "inputs larger than L2 (CSR + Krylov basis >> 126 MB); no flush needed"}
+
+
+def run_other_configs(sb, synth):
+    """BASELINE.json configs[1], [2], [4] on one GPU: SpMV-iters/s of one complete solve (device time of init() + compute())."""
+    import scipy.sparse as sp
+
+    out = {}
+
+    def solve(make, sel, maxit=1000):
+        best = None
+        for _ in range(2):  # first solve warms up (allocation, clocks); the second is reported
+            e = make()
+            e.init()
+            nconv = e.compute(sel, maxit)
+            st = e.stats()
+            best = {"nconv": int(nconv), "num_operations": int(e.num_operations()), "num_iterations": int(e.num_iterations()), "info": int(e.info()),
+                    "ms": st["ms_total"], "spmv_iters_per_sec": e.num_operations() / (st["ms_total"] / 1e3), "eigenpairs_per_sec": nconv / (st["ms_total"] / 1e3),
+                    "host_syncs": st["host_syncs"], "kernel_launches": st["kernel_launches"]}
+            e.close()
+        return best
+
+    n2 = 1_000_000
+    rp, ci, v = synth.csr(n2, 20, 0, True)
+    op = sb.SparseGenMatProd.from_csr_slab(n2, 0, rp, ci, v)
+    out["C2_sym_n1e6_k20_ncv60_LargestAlge"] = solve(lambda: sb.SymEigsSolver(op, 20, 60), sb.SortRule.LargestAlge)
+    op.close()
+    rp, ci, v = synth.csr(n2, 20, 1, False)
+    op = sb.SparseGenMatProd.from_csr_slab(n2, 0, rp, ci, v)
+    r = solve(lambda: sb.GenEigsSolver(op, 10, 30), sb.SortRule.LargestMagn, 40)
+    r["note"] = "G_gen unplanted, maxit = 40 (the circular-law spectrum does not converge within the default 1000 restarts either); throughput of the Arnoldi loop"
+    out["C3_gen_n1e6_k10_ncv30_LargestMagn_maxit40"] = r
+    op.close()
+    n5 = 200_000
+    rp, ci, v = synth.band_csr(n5, 15, 0, 0.0)
+    A = sp.csr_matrix((v, ci, rp), shape=(n5, n5))
+    ops = sb.SparseSymShiftSolve(sp.tril(A).tocsc())
+    out["C5_shift_invert_n2e5_band15_k10_ncv30_sigma0.5"] = solve(lambda: sb.SymEigsShiftSolver(ops, 10, 30, 0.5), sb.SortRule.LargestMagn)
+    ops.close()
+    return out
 
 
 def main():
@@ -255,36 +325,67 @@ def main():
     ps = eigs.stats()
     sb.set_profiling(0)
     nl = nrows
-    spmv_bytes = 12.0 * nnz_local + 4.0 * (nl + 1) + 8.0 * n + 8.0 * nl + 16.0 * nl  # CSR + x + y, + v_i write and v_{i-1} read of the fused step head
+    # one operator application = 12 nnz + 4 (n + 1) + 8 n (x) + 8 n (y); the fused step head adds the v_i write and the
+    # v_{i-1} read (16 B/row); an application whose last kernel also carries the first panel pass (sell_step_dot_kernel) additionally
+    # streams 8 nl i bytes of V (8(d) "GEMV-T": 8 n j + 8 n, the w values stay on chip)
+    spmv_only_bytes = 12.0 * nnz_local + 4.0 * (nl + 1) + 8.0 * n + 8.0 * nl
+    spmv_bytes = spmv_only_bytes + 16.0 * nl
+    fused_bytes_total = 8.0 * nl * ps["fused_dot_cols"]
+    op_bytes_total = spmv_bytes * ps["spmv_launches"] + fused_bytes_total
     panel_bytes_total = 8.0 * nl * (ps["panel_cols"] + 2 * ps["panel_launches"])
+    # the plain operator kernels alone (no step head, no panel): what BASELINE's "SpMV at >= 70 % of the HBM roofline" is quoted on
+    plain_ms = op.spmv_device_time(20)
     kern = {
         "panel_pass": {"launches": ps["panel_launches"], "ms_total": ps["ms_panel"], "avg_ms": ps["ms_panel"] / max(ps["panel_launches"], 1),
                        "algorithmic_bytes_per_launch": panel_bytes_total / max(ps["panel_launches"], 1),
                        "gbs": panel_bytes_total / max(ps["ms_panel"], 1e-9) / 1e6},
-        "csr_spmv": {"launches": ps["spmv_launches"], "ms_total": ps["ms_spmv"], "avg_ms": ps["ms_spmv"] / max(ps["spmv_launches"], 1),
-                     "algorithmic_bytes_per_launch": spmv_bytes, "gbs": spmv_bytes * ps["spmv_launches"] / max(ps["ms_spmv"], 1e-9) / 1e6},
+        "operator_step": {"launches": ps["spmv_launches"], "ms_total": ps["ms_spmv"], "avg_ms": ps["ms_spmv"] / max(ps["spmv_launches"], 1),
+                          "algorithmic_bytes_per_launch": op_bytes_total / max(ps["spmv_launches"], 1), "gbs": op_bytes_total / max(ps["ms_spmv"], 1e-9) / 1e6,
+                          "fused_first_panel_pass": {"launches": ps["fused_dot_launches"], "avg_cols": ps["fused_dot_cols"] / max(ps["fused_dot_launches"], 1)},
+                          "layout": op.spmv_layout(),
+                          "note": "all column-block kernels of one operator application inside the solver, incl. the fused step head and (sliced layout) "
+                                  "the first panel pass V^T w streamed in the same kernel"},
+        "spmv_plain": {"avg_ms": plain_ms, "algorithmic_bytes_per_launch": spmv_only_bytes, "gbs": spmv_only_bytes / plain_ms / 1e6,
+                       "note": "y = A x alone (sb200_op_spmv_device, 20 launches back to back): SURVEY 8(d) bytes of the SpMV itself"},
         "restart_gemm": {"launches": ps["compress_launches"], "ms_total": ps["ms_compress"]},
         "small_dense": {"ms_total": ps["ms_small"]},
         "comm": {"ms_total": ps["ms_comm"]},
     }
-    for kname in ("panel_pass", "csr_spmv"):
+    for kname in ("panel_pass", "operator_step", "spmv_plain"):
         kern[kname]["frac_of_hbm_peak"] = kern[kname]["gbs"] / peak
-    dominant = "panel_pass" if ps["ms_panel"] >= ps["ms_spmv"] else "csr_spmv"
-    # DRAM traffic per launch from the committed `ncu --set full` capture of this same workload (profiles/traffic.json;
+    dominant = "panel_pass" if ps["ms_panel"] >= ps["ms_spmv"] else "operator_step"
+    # roofs of the gather phase measured live (csrc/microbench.cu): 1e8 uniformly random 8-byte gathers from one 40 MB operand slice, alone and
+    # with the (index, value) stream a sliced SpMV reads -- two slices of that make one n = 1e7 operator application
+    roofs = None
+    if rank == 0 and world == 1:
+        try:
+            sl = min(n, 5_000_000)
+            g_only = sb.bench_gather(sl, 100_000_000, 5)["ms"]
+            g_stream = sb.bench_stream_gather(sl, 100_000_000, False, 5)["ms"]
+            scale = nnz_total / 1e8
+            roofs = {"slice_doubles": sl, "gathers": 100_000_000, "gather_only_ms": g_only, "stream_gather_ms": g_stream,
+                     "spmv_floor_ms_gather_only": g_only * scale, "spmv_floor_ms_stream_gather": g_stream * scale,
+                     "spmv_frac_ceiling_stream_gather": spmv_only_bytes / (g_stream * scale) / 1e6 / peak,
+                     "note": "uniformly random columns: every gathered operand is its own 32 B sector; the L1TEX wavefront rate (1 per clock per SM) and the "
+                             "L2 sector throughput bound the SpMV below the HBM roof"}
+        except Exception as e:  # noqa: BLE001
+            roofs = {"error": f"{type(e).__name__}: {e}"}
+    # DRAM traffic per launch from the committed `ncu --set full` capture of this same workload and device layout (profiles/traffic.json;
     # dram__bytes_read.sum + dram__bytes_write.sum, summed over the column-block kernels of one operator application)
     traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             tj = json.load(fh)
         ent = tj.get(dominant)
-        if ent and int(ent["n"]) == n and int(ent.get("n_gpus", 1)) == world:
+        if ent and int(ent["n"]) == n and int(ent.get("n_gpus", 1)) == world and ent.get("layout") == kern["operator_step"]["layout"]["format"]:
             traffic, traffic_src = float(ent["dram_bytes_per_launch"]), ent.get("source")
     except (OSError, ValueError, KeyError):
         pass
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": kern[dominant]["gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": kern[dominant]["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": kern[dominant]["algorithmic_bytes_per_launch"], "share_of_step": {"panel_pass": ps["ms_panel"] / ps["ms_total"],
-                                                                                          "csr_spmv": ps["ms_spmv"] / ps["ms_total"]}}
+                "algorithmic_bytes_per_launch": kern[dominant]["algorithmic_bytes_per_launch"],
+                "spmv_plain_frac": kern["spmv_plain"]["frac_of_hbm_peak"], "gather_roofs": roofs,
+                "share_of_step": {"panel_pass": ps["ms_panel"] / ps["ms_total"], "operator_step": ps["ms_spmv"] / ps["ms_total"]}}
 
     # =========================== e2e arm: host buffers in, host results out ===========================
     e2e = None
@@ -329,22 +430,18 @@ def main():
         r = O.sym_eigs(A, args.nev, args.ncv, O.LargestAlge, 1000, args.tol, threads=1, op_limit=args.cpu_sample_ops, want_vectors=False)
         cpu = {"value": r.nops / r.seconds, "unit": "SpMV-iters/s", "cores": 1, "kind": "port",
                "sample": f"init + first {r.nops - 2} Lanczos steps (op_limit={args.cpu_sample_ops}) of the same n={n} solve, {r.seconds:.1f} s; early steps have "
-                         f"narrow panels, so this over-states the CPU's steady-state rate", "host_cores_available": os.cpu_count()}
+                         f"narrow panels, so this over-states the CPU's steady-state rate", "host_cores_available": host_threads(),
+               "full_solves_cached": golden_full_solves()}
 
-    # ---- opt-in code paths (sliced-CSR SpMV, Hermitian solver, gather-roof microbenchmark): probed in a SEPARATE process with a hard
-    # timeout, after every timed region is over; reported under "experimental", never part of value / e2e / roofline ----
-    experimental = None
-    if rank == 0 and world == 1 and not args.skip_experimental:
-        import subprocess
-
+    # ---- the other BASELINE configurations on one GPU (C2, C3, C5): one solve each after a warm-up solve, device time; parity of
+    # these configurations is the job of tests/ (test_sym_eigs_full_size_properties, test_gen_eigs_c3_unplanted_history, test_gpu_shift) ----
+    configs = None
+    if rank == 0 and world == 1 and not args.skip_configs:
+        configs = {}
         try:
-            pr = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "experimental_probe.py"), str(n)], capture_output=True, text=True, timeout=420)
-            last = [ln for ln in pr.stdout.splitlines() if ln.startswith("{")]
-            experimental = json.loads(last[-1]) if last else {"error": f"no output (exit {pr.returncode}): {pr.stderr[-400:]}"}
-        except subprocess.TimeoutExpired:
-            experimental = {"error": "probe timed out after 420 s"}
+            configs.update(run_other_configs(sb, synth))
         except Exception as e:  # noqa: BLE001
-            experimental = {"error": f"{type(e).__name__}: {e}"}
+            configs["error"] = f"{type(e).__name__}: {e}"
 
     if rank == 0:
         line = {
@@ -354,8 +451,8 @@ def main():
             "eigenpairs_per_sec": nconv / (ms_per_step / 1e3), "nconv": int(nconv), "num_operations": int(nops), "num_iterations": int(niter),
             "converged": bool(info_ok), "accuracy": {"max_rel_residual": float(np.max(rel_res)), "bound": 1e-10},
             "wall_ms_per_step": wall_per_step, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kern, "cpu_baseline": cpu,
-            "clocks": clocks, "algo_counters": {k: last_stats[k] for k in ("lanczos_steps", "reorth_passes", "restarts", "expand_calls")},
-            "device": info, "nnz": nnz_total, "gen_seconds": gen_s, "experimental": experimental,
+            "clocks": clocks, "algo_counters": {k: last_stats[k] for k in ("lanczos_steps", "reorth_passes", "restarts", "expand_calls", "host_syncs", "fused_dot_launches")},
+            "device": info, "nnz": nnz_total, "gen_seconds": gen_s, "configs": configs,
         }
         print(json.dumps(line), flush=True)
 

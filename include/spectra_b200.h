@@ -159,13 +159,17 @@ int sb200_op_apply_matrix(sb200_op* op, const double* X_host, int64_t k, double*
 int sb200_op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev, int repeat, float* elapsed_ms);
 int sb200_op_destroy(sb200_op* op);
 /* Device layout of a sparse operator (new surface, for tests and benchmarks): *format = 0 CSR (sub-warp per row kernels), 1 sliced
- * CSR (one lane per row; experimental, selected with SB200_SPMV_FORMAT=sell at creation); *col_blocks = column blocks the operand is
+ * CSR (one lane per row; the default whenever its padding is below SB200_SELL_MAX_FILL, SB200_SPMV_FORMAT=csr forces the CSR-vector kernels); *col_blocks = column blocks the operand is
  * split into; *stored_entries = matrix entries held on the device including padding. */
 int sb200_op_layout_info(const sb200_op* op, int* format, int* col_blocks, int64_t* stored_entries);
 /* Roofline microbenchmark (tools/gather_roof.py; not on the product path): average time of `gathers` independent, uniformly random
  * 8-byte read-only loads from a device vector of n doubles -- the operand access of a CSR SpMV with random column ids, without the
  * matrix stream.  *checksum = mean of the loaded values (1.0). */
 int sb200_bench_gather(int64_t n, int64_t gathers, int repeat, float* elapsed_ms, double* checksum);
+/* The same with the indices and one coefficient per gather STREAMED from HBM (12 B per gather, coalesced, four steps in flight) and
+ * each gather dependent on its index load: acc += val[k] * x[col[k]] without rows, padding or output -- the floor of any SpMV on this
+ * access pattern.  band = 0: uniformly random columns; band = 1: neighbouring columns (coalesced gathers). */
+int sb200_bench_stream_gather(int64_t n, int64_t gathers, int band, int repeat, float* elapsed_ms, double* checksum);
 
 /* ------------------------------------------------------------------------------------------
  * SymEigsSolver — replaces SymEigsSolver.h:133-160 + HermEigsBase.h:43-479 (+ the
@@ -213,7 +217,10 @@ typedef struct
     double ms_panel;        /* fused re-orthogonalisation panel kernels */
     double ms_compress;     /* compress_V GEMM */
     double ms_small;        /* small dense restart kernels */
-    double ms_comm;         /* NCCL collectives */
+    double ms_comm;         /* collectives (NCCL or peer-memory kernels) */
+    int64_t fused_dot_launches; /* operator applications whose last kernel also carried the first panel pass (sell_step_dot_kernel) */
+    int64_t fused_dot_cols;     /* sum of the panel widths i streamed by those kernels: their extra algorithmic bytes are 8 n fused_dot_cols */
+    int64_t host_syncs;         /* stream synchronisations issued by init()+compute() */
 } sb200_stats;
 int sb200_sym_stats(const sb200_sym_solver* s, sb200_stats* out);
 /* 0 = off (default, no extra events), 1 = per-kernel-class CUDA-event timing (adds syncs). */

@@ -57,7 +57,7 @@ class Stats(C.Structure):
         ("lanczos_steps", C.c_int64), ("reorth_passes", C.c_int64), ("restarts", C.c_int64), ("expand_calls", C.c_int64), ("kernel_launches", C.c_int64),
         ("spmv_launches", C.c_int64), ("panel_launches", C.c_int64), ("panel_cols", C.c_int64), ("compress_launches", C.c_int64), ("compress_cols", C.c_int64),
         ("ms_total", C.c_double), ("ms_spmv", C.c_double), ("ms_panel", C.c_double), ("ms_compress", C.c_double), ("ms_small", C.c_double),
-        ("ms_comm", C.c_double),
+        ("ms_comm", C.c_double), ("fused_dot_launches", C.c_int64), ("fused_dot_cols", C.c_int64), ("host_syncs", C.c_int64),
     ]
 
     def as_dict(self):
@@ -322,6 +322,13 @@ def bench_gather(n: int, gathers: int, repeat: int = 5) -> dict:
     """Roofline microbenchmark (tools/gather_roof.py): time of `gathers` uniformly random 8-byte loads from n doubles."""
     ms, chk = C.c_float(), C.c_double()
     _check(lib().sb200_bench_gather(C.c_int64(int(n)), C.c_int64(int(gathers)), int(repeat), C.byref(ms), C.byref(chk)))
+    return dict(ms=ms.value, checksum=chk.value)
+
+
+def bench_stream_gather(n: int, gathers: int, band: bool = False, repeat: int = 5) -> dict:
+    """Roofline microbenchmark: streamed (index, coefficient) pairs + dependent gathers, the floor of any SpMV on this access pattern."""
+    ms, chk = C.c_float(), C.c_double()
+    _check(lib().sb200_bench_stream_gather(C.c_int64(int(n)), C.c_int64(int(gathers)), int(bool(band)), int(repeat), C.byref(ms), C.byref(chk)))
     return dict(ms=ms.value, checksum=chk.value)
 
 

@@ -17,6 +17,7 @@ sb200_op* op_create_shift_solve(int64_t n, const void* outer, int outer_is_64, c
 void op_perform_op_host(sb200_op* op, const double* x_host, double* y_host);
 sb200_op* op_create_sparse_herm(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values_ri, int storage_order, int matrix_mode);
 float bench_gather(int64_t n, int64_t gathers, int repeat, double* checksum);
+float bench_stream_gather(int64_t n, int64_t gathers, int band, int repeat, double* checksum);
 
 sb200_sym_solver* sym_create(sb200_op* op, int64_t nev, int64_t ncv, bool shift_mode, double sigma);
 void sym_init(sb200_sym_solver* s, const double* resid);
@@ -301,6 +302,15 @@ int sb200_bench_gather(int64_t n, int64_t gathers, int repeat, float* elapsed_ms
     ABI_TRY
     device_info();
     const float ms = bench_gather(n, gathers, repeat, checksum);
+    if (elapsed_ms)
+        *elapsed_ms = ms;
+    ABI_CATCH
+}
+int sb200_bench_stream_gather(int64_t n, int64_t gathers, int band, int repeat, float* elapsed_ms, double* checksum)
+{
+    ABI_TRY
+    device_info();
+    const float ms = bench_stream_gather(n, gathers, band, repeat, checksum);
     if (elapsed_ms)
         *elapsed_ms = ms;
     ABI_CATCH

@@ -252,6 +252,31 @@ __device__ __forceinline__ void ld_stream_f64x4(const double* p, double (&v)[4])
 __device__ __forceinline__ double ld_keep_f64(const double* p, uint64_t) { return *p; }
 __device__ __forceinline__ double2 ld_keep_f64x2(const double* p, uint64_t) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ double ld_cg_f64(const double* p) { return *p; }
+// system-scope accesses of the peer-memory kernels: the emulated ranks are OS threads of one process
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void st_sys_f64(double* p, double v)
+{
+    unsigned long long b;
+    memcpy(&b, &v, sizeof(b));
+    __atomic_store_n(reinterpret_cast<unsigned long long*>(p), b, __ATOMIC_RELAXED);
+}
+__device__ __forceinline__ double ld_sys_f64(const double* p)
+{
+    const unsigned long long b = __atomic_load_n(reinterpret_cast<const unsigned long long*>(p), __ATOMIC_RELAXED);
+    double v;
+    memcpy(&v, &b, sizeof(v));
+    return v;
+}
+__device__ __forceinline__ void st_peer_f64x2(double* p, double2 v) { p[0] = v.x; p[1] = v.y; }
+// mbarrier / bulk-copy (TMA) helpers: under emulation the copy is performed synchronously at issue, so the barriers have nothing to wait for
+__device__ __forceinline__ void mbar_init(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void mbar_init_fence() {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t*) { memcpy(dst_smem, src_gmem, bytes); }
+__device__ __forceinline__ void tma_load_1d_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t*, uint64_t) { memcpy(dst_smem, src_gmem, bytes); }
+__device__ __forceinline__ void fence_proxy_async_smem() {}
 #else
 // L2 cache policies (createpolicy): streamed-once data is marked evict_first so that the gathered
 // operand vector / small reused vectors keep their L2 residency (evict_last).
@@ -323,6 +348,74 @@ __device__ __forceinline__ double ld_cg_f64(const double* p)
     asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
+// System-scope accesses used on peer (NVLink-mapped) memory: release / acquire flags, relaxed data.
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys_f64(double* p, double v) { asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ double ld_sys_f64(const double* p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// 16-byte store of two consecutive rows into a (possibly remote) operand buffer; ordered for the peers by the kernel boundary and the
+// system-scope release of the all-reduce that follows
+__device__ __forceinline__ void st_peer_f64x2(double* p, double2 v) { asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory"); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    int spins = 0;
+    while (!done)
+    {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1 << 26))
+            __trap();  // never hang the device on a lost transaction
+    }
+}
+// 1-D bulk TMA copy global -> shared, completion signalled on an mbarrier (bytes: multiple of 16, both addresses 16 B aligned)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+// the same with an L2 cache policy (createpolicy) for read-once streams
+__device__ __forceinline__ void tma_load_1d_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// orders generic-proxy accesses of shared memory before later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif  // SB200_EMU
 
 // Grid-wide deterministic reduction of K (<= 128) per-CTA partial values.

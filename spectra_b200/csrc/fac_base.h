@@ -82,6 +82,13 @@ struct FacBase
     double h_beta = 0.0;
     bool initialised = false;
 
+    // peer mode (row-sharded runs with NVLink-mapped windows, peer.cu): mailboxes of the one-shot all-reduce, destinations of the residual
+    // rows in every rank's operand buffer, and whether those buffers currently hold f
+    PeerCtl pctl{};
+    PeerX px{};
+    bool peer = false;
+    bool x_published = false;
+
     Profiler prof;
     sb200_stats stats;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -129,6 +136,25 @@ struct FacBase
         rs.max_grid = max_grid;
         hstat.alloc(256);
         hred.alloc(kRedStride + 8);
+        peer = op->peer_mode();
+        if (peer)
+        {
+            const int Pn = op->nranks();
+            for (int r = 0; r < Pn; r++)
+            {
+                pctl.slots[r] = static_cast<double*>(op->win_ctl.peer[r]);
+                pctl.flags[r] = reinterpret_cast<unsigned long long*>(static_cast<double*>(op->win_ctl.peer[r]) + (size_t) 2 * Pn * kRedStride);
+                px.dst[r] = static_cast<double*>(op->win_x.peer[r]);
+            }
+            pctl.seq = op->peer_seq.get();
+            pctl.rank = op->rank();
+            pctl.nranks = Pn;
+            px.np = Pn;
+            px.rank = op->rank();
+            px.len = op->A.chunk_len;
+            px.stride = op->A.chunk_stride();
+            px.rows = op->A.chunk_len * (int64_t) op->A.blocks.size();
+        }
         SB200_CUDA_CHECK(cudaEventCreate(&ev_begin));
         SB200_CUDA_CHECK(cudaEventCreate(&ev_end));
         std::memset(&stats, 0, sizeof(stats));
@@ -139,23 +165,39 @@ struct FacBase
     {
         SB200_CUDA_CHECK(cudaMemcpyAsync(hstat.get(), ctl.get(), kFacCtlStatusBytes, cudaMemcpyDeviceToHost, stream()));
         SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+        stats.host_syncs++;
         return reinterpret_cast<const FacCtl*>(hstat.get());
     }
     void allreduce_sum(double* buf, size_t count)
     {
         if (P() > 1)
         {
-            ScopedKernelTimer t(&prof, stream(), KC_COMM, 0);
-            nccl_allreduce_sum(op->comm, buf, count, stream());
+            ScopedKernelTimer t(&prof, stream(), KC_COMM, peer ? 1 : 0);
+            if (peer)
+                launch_peer_allreduce(pctl, buf, (int) count, 0, stream());
+            else
+                nccl_allreduce_sum(op->comm, buf, count, stream());
         }
     }
     void allreduce_max(double* buf, size_t count)
     {
         if (P() > 1)
         {
-            ScopedKernelTimer t(&prof, stream(), KC_COMM, 0);
-            nccl_allreduce_max(op->comm, buf, count, stream());
+            ScopedKernelTimer t(&prof, stream(), KC_COMM, peer ? 1 : 0);
+            if (peer)
+                launch_peer_allreduce(pctl, buf, (int) count, 1, stream());
+            else
+                nccl_allreduce_max(op->comm, buf, count, stream());
         }
+    }
+    // peer mode: make every rank's operand buffer hold the current residual f (cold paths -- after init, a restart, expand_basis or a
+    // zeroed residual; on the hot path the correction pass has already written it).  The all-reduce is the barrier for the peer writes.
+    void publish_f()
+    {
+        ScopedKernelTimer t(&prof, stream(), KC_COMM, 2);
+        launch_peer_push(px, f.get(), ld, stream());
+        launch_peer_allreduce(pctl, ctl.get()->red_a + 3, 1, 0, stream());
+        x_published = true;
     }
     // x_full <- all-gather of a local vector (sharded); returns the pointer the SpMV must read
     const double* gather_full(const double* local)
@@ -197,8 +239,11 @@ struct FacBase
         stats.spmv_launches++;
         nmatop++;
     }
-    void spmv_step(int i, bool restarted, bool symmetric)
+    // K-A of one step.  want_dot: ask the operator kernel to also deliver ctl->red[0..i] = V[:, :i+1]^T w (the first panel pass);
+    // returns true when it did (sliced layout), false when the caller has to run the panel pass itself.
+    bool spmv_step(int i, bool restarted, bool symmetric, bool want_dot = false)
     {
+        double* dot_out = want_dot ? ctl.get()->red : nullptr;
         if (op->indirect())
         {
             // user-defined host operator / device shift-solve: v_i = f/beta on the device, w = op(v_i), epilogue on the device
@@ -209,49 +254,84 @@ struct FacBase
             launch_step_epilogue(w.get(), V.get(), ld, nloc, ctl.get(), H.get(), m, i, restarted ? 1 : 0, symmetric, rs, stream());
             stats.spmv_launches++;
             nmatop++;
-            return;
+            return false;
         }
         if (op->A.chunk_len && P() > 1)
         {
-            spmv_step_chunked(i, restarted, symmetric);
+            const bool fused = spmv_step_chunked(i, restarted, symmetric, dot_out);
             stats.spmv_launches++;
             nmatop++;
-            return;
+            return count_fused(fused, i);
         }
         if (op->A.chunk_len)
         {
             // single-GPU test layout (SB200_FORCE_CHUNK_RANKS): permute instead of gathering
             ScopedKernelTimer t(&prof, stream(), KC_SPMV, 1 + (int) op->A.blocks.size());
-            launch_permute_to_chunks(op->A, f.get(), op->x_chunks.get(), stream());
-            launch_spmv_step(op->A, op->plan, op->x_chunks.get(), f.get(), V.get(), ld, w.get(), ctl.get(), H.get(), m, i, restarted ? 1 : 0, symmetric, rs,
-                             stream());
+            launch_permute_to_chunks(op->A, f.get(), op->xc, stream());
+            const bool fused = launch_spmv_step(op->A, op->plan, op->xc, f.get(), V.get(), ld, w.get(), ctl.get(), H.get(), m, i, restarted ? 1 : 0,
+                                                symmetric, rs, stream(), dot_out);
             stats.spmv_launches++;
             nmatop++;
-            return;
+            return count_fused(fused, i);
         }
         const double* xfull = gather_full(f.get());
+        bool fused;
         {
             ScopedKernelTimer t(&prof, stream(), KC_SPMV);
-            launch_spmv_step(op->A, op->plan, xfull, f.get(), V.get(), ld, w.get(), ctl.get(), H.get(), m, i, restarted ? 1 : 0, symmetric, rs, stream());
+            fused = launch_spmv_step(op->A, op->plan, xfull, f.get(), V.get(), ld, w.get(), ctl.get(), H.get(), m, i, restarted ? 1 : 0, symmetric, rs, stream(),
+                                     dot_out);
         }
         stats.spmv_launches++;
         nmatop++;
+        return count_fused(fused, i);
+    }
+    bool count_fused(bool fused, int i)
+    {
+        if (fused)
+        {
+            stats.fused_dot_launches++;
+            stats.fused_dot_cols += i;
+        }
+        return fused;
+    }
+    // first panel pass of a step: red[0..j) = V[:, :j]^T w, either already delivered by the operator kernel (fused) or run here
+    void step_dot(int i, bool restarted, bool symmetric)
+    {
+        const int j = i + 1;
+        if (spmv_step(i, restarted, symmetric, !is_cplx()))
+            allreduce_sum(ctl.get()->red, (size_t) j);
+        else
+            panel(PANEL_DOT, j, w.get(), nullptr, nullptr);
     }
     // Sharded operator: the operand is all-gathered in chunks on the communication stream; the SpMV of column block c (the
     // columns that chunk c delivers) starts as soon as chunk c has landed, while chunk c+1 is still on the wire.
-    void spmv_step_chunked(int i, bool restarted, bool symmetric)
+    bool spmv_step_chunked(int i, bool restarted, bool symmetric, double* dot_out)
     {
         const DeviceCsr& A = op->A;
         const int nb = (int) A.blocks.size();
         const int64_t len = A.chunk_len, stride = A.chunk_stride();
+        if (peer)
+        {
+            // the operand is already in place: the last correction pass (or publish_f) wrote every rank's rows into all operand buffers
+            if (!x_published)
+                publish_f();
+            bool fused_p = false;
+            ScopedKernelTimer t(&prof, stream(), KC_SPMV, nb);
+            for (int c = 0; c < nb; c++)
+                fused_p = launch_spmv_step_block(A, op->plan, c, op->xc + (int64_t) c * stride, f.get(), V.get(), ld, w.get(), ctl.get(), H.get(), m, i,
+                                                 restarted ? 1 : 0, symmetric, rs, stream(), dot_out);
+            x_published = false;  // w / f move on; the next correction pass republishes
+            return fused_p;
+        }
         SB200_CUDA_CHECK(cudaEventRecord(op->ev_ready, stream()));  // f is final on the compute stream
         SB200_CUDA_CHECK(cudaStreamWaitEvent(op->comm_stream, op->ev_ready, 0));
         for (int c = 0; c < nb; c++)
         {
-            nccl_allgather(op->comm, f.get() + (int64_t) c * len, op->x_chunks.get() + (int64_t) c * stride, (size_t) len, op->comm_stream);
+            nccl_allgather(op->comm, f.get() + (int64_t) c * len, op->xc + (int64_t) c * stride, (size_t) len, op->comm_stream);
             SB200_CUDA_CHECK(cudaEventRecord(op->ev_chunk[(size_t) c], op->comm_stream));
         }
         prof.launches += nb;
+        bool fused = false;
         for (int c = 0; c < nb; c++)
         {
             {
@@ -260,19 +340,23 @@ struct FacBase
                 SB200_CUDA_CHECK(cudaStreamWaitEvent(stream(), op->ev_chunk[(size_t) c], 0));
             }
             ScopedKernelTimer t(&prof, stream(), KC_SPMV);
-            launch_spmv_step_block(A, op->plan, c, op->x_chunks.get() + (int64_t) c * stride, f.get(), V.get(), ld, w.get(), ctl.get(), H.get(), m, i,
-                                   restarted ? 1 : 0, symmetric, rs, stream());
+            fused = launch_spmv_step_block(A, op->plan, c, op->xc + (int64_t) c * stride, f.get(), V.get(), ld, w.get(), ctl.get(), H.get(), m, i,
+                                           restarted ? 1 : 0, symmetric, rs, stream(), dot_out);
         }
+        return fused;
     }
     void panel(int mode, int j, const double* x, double* fo, const double* coef, const int* pred = nullptr)
     {
         stats.panel_launches++;
         stats.panel_cols += j;
+        const bool push = peer && mode == PANEL_CORR && fo == f.get();
         {
             ScopedKernelTimer t(&prof, stream(), KC_PANEL);
-            launch_panel_pass(mode, V.get(), ld, nloc, j, x, fo, coef, ctl.get()->red, rs, stream(), pred, is_cplx());
+            launch_panel_pass(mode, V.get(), ld, nloc, j, x, fo, coef, ctl.get()->red, rs, stream(), pred, is_cplx(), push ? &px : nullptr);
         }
         allreduce_sum(ctl.get()->red, kRedNrm + 1);
+        if (push && pred == nullptr)
+            x_published = true;  // the all-reduce above is the barrier for the rows just written into the peers' operand buffers
     }
     // A speculatively enqueued pass turned out to be skipped on the device: undo its accounting.
     void uncount_panel(int j)
@@ -413,6 +497,7 @@ struct FacBase
         }
         k = 1;
         initialised = true;
+        x_published = false;
     }
 
     // ---- Arnoldi::compress_V (Arnoldi.h:320-340) with the new subspace size knew ----
@@ -429,6 +514,7 @@ struct FacBase
         prof.launches++;
         h_beta = read_status()->beta;
         k = knew;
+        x_published = false;  // the restart GEMM rewrote f
     }
 
     void finish_timing()

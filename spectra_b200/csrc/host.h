@@ -22,6 +22,23 @@ void nccl_allreduce_sum(sb200_comm* c, double* buf, size_t count, cudaStream_t s
 void nccl_allreduce_max(sb200_comm* c, double* buf, size_t count, cudaStream_t s);
 void nccl_allgather(sb200_comm* c, const double* send, double* recv, size_t count_per_rank, cudaStream_t s);
 
+// ---- peer memory over NVLink (row-sharded runs on one node): symmetric device allocations mapped into every rank's address space
+// (CUDA IPC handles exchanged through the NCCL communicator), used by the peer kernels of peer.cu -- one-shot all-reduce of the
+// dot products and the direct write of each rank's new residual slice into every peer's SpMV operand buffer ----
+constexpr int kMaxPeers = 16;
+struct PeerWindow
+{
+    void* local = nullptr;
+    size_t bytes = 0;
+    void* peer[kMaxPeers] = {};   // peer[r] = rank r's allocation as mapped here; peer[own rank] == local
+    int nranks = 0;
+    bool ok() const { return local != nullptr; }
+};
+// Collective over the communicator.  Returns false on every rank (and allocates nothing) when any rank cannot map its peers
+// (no IPC / peer access): the caller then stays on the NCCL collectives.
+bool peer_window_create(sb200_comm* c, size_t bytes, PeerWindow& w, cudaStream_t s);
+void peer_window_destroy(sb200_comm* c, PeerWindow& w);
+
 // ---- banded shift-solve operator (band_solve.cu; SparseSymShiftSolve.h:85-109) ----
 struct BandSolve;
 BandSolve* band_create(sb200_op* op);
@@ -46,7 +63,12 @@ struct sb200_op
     sb200::DevBuf<double> x_stage;    // slab-sized send buffer for the all-gather
     // chunked all-gather / SpMV overlap (sharded operators, DeviceCsr::chunk_len): operand in chunk-major layout, a second
     // stream for the collectives, one event per chunk
-    sb200::DevBuf<double> x_chunks;   // nchunks * nranks * chunk_len
+    sb200::DevBuf<double> x_chunks;   // nchunks * nranks * chunk_len (NCCL path / single-GPU test layout)
+    double* xc = nullptr;             // the chunk-major operand buffer in use: x_chunks, or the local part of win_x in peer mode
+    // peer mode (peer.cu): operand buffer and reduction mailboxes live in symmetric windows every rank can write
+    sb200::PeerWindow win_x, win_ctl;
+    sb200::DevBuf<unsigned long long> peer_seq;  // round counter of the one-shot all-reduce (identical on every rank)
+    bool peer_mode() const { return win_x.ok() && win_ctl.ok(); }
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_ready = nullptr;
     std::vector<cudaEvent_t> ev_chunk;

@@ -149,6 +149,7 @@ struct SpmvPlan
     int sell_threads = 0;  // > 0: the operand carries the sliced layout and the lane-per-row kernels run (CTA size)
     int sell_grid = 0;        // fused step kernel (bounded by the reduction scratch)
     int sell_grid_plain = 0;  // plain / accumulate kernels: one CTA per window
+    int sell_grid_fused = 0;  // fused step head + first panel pass (sell_step_dot_kernel); 0 = not used
 };
 SpmvPlan make_spmv_plan(const DeviceCsr& A);
 // column blocks needed so that one slice of the gathered operand stays L2-resident (env SB200_XSLICE_MB)
@@ -163,10 +164,41 @@ void launch_spmv(const DeviceCsr& A, const SpmvPlan& plan, const double* x, doub
 // One column block of the fused step: c < nblocks-1 accumulates the raw product into w, the last block applies the step head.
 // x_block points at the operand slice of block c (DeviceCsr::x_of_block).
 int spmv_num_blocks(const DeviceCsr& A);
-void launch_spmv_step_block(const DeviceCsr& A, const SpmvPlan& plan, int c, const double* x_block, const double* f_loc, double* V, int64_t ldv, double* w,
-                            FacCtl* ctl, double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream);
-void launch_spmv_step(const DeviceCsr& A, const SpmvPlan& plan, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
-                      double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream);
+// dot_out != nullptr asks the last block to also deliver dot_out[0..i] = V[:, :i+1]^T w (the first panel pass of the step, fused into the
+// operator kernel -- sliced layout only); the return value says whether it did (false: the caller runs the panel pass itself).
+bool launch_spmv_step_block(const DeviceCsr& A, const SpmvPlan& plan, int c, const double* x_block, const double* f_loc, double* V, int64_t ldv, double* w,
+                            FacCtl* ctl, double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream,
+                            double* dot_out = nullptr);
+bool launch_spmv_step(const DeviceCsr& A, const SpmvPlan& plan, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
+                      double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream, double* dot_out = nullptr);
+
+// ---- peer-memory kernels (peer.cu; row-sharded runs over NVLink) --------------------------------------------------------
+constexpr int kPeerMax = 16;
+// Mailboxes of the one-shot all-reduce inside each rank's control window: 2 (round parity) x nranks x kRedStride doubles of data
+// followed by 2 x nranks 64-bit flags.
+struct PeerCtl
+{
+    double* slots[kPeerMax];                 // slots[r] = rank r's mailbox area (mapped peer pointer; slots[rank] is local)
+    unsigned long long* flags[kPeerMax];     // flags[r] = rank r's flag area
+    unsigned long long* seq;                 // local round counter
+    int rank, nranks;
+};
+inline size_t peer_ctl_bytes(int nranks) { return sizeof(double) * 2 * (size_t) nranks * kRedStride + sizeof(unsigned long long) * 2 * (size_t) nranks; }
+// in-place all-reduce (op 0 = sum in rank order, 1 = max) of count <= kRedStride doubles in buf: every rank writes its values into every
+// peer's mailbox, releases a flag per peer, waits for the flags of all peers and combines the mailboxes in rank order (bitwise identical
+// results on every rank).  One launch, no host involvement; doubles as a barrier for peer writes issued by earlier kernels of the stream.
+void launch_peer_allreduce(const PeerCtl& pc, double* buf, int count, int op, cudaStream_t stream);
+// Destination of this rank's residual rows in the chunk-major operand buffer of every rank (DeviceCsr::chunk_len): local row r goes to
+// x[(r / len) * stride + rank * len + r % len] on all ranks.
+struct PeerX
+{
+    double* dst[kPeerMax];   // operand buffers of all ranks (own included); np == 0: no peer writes
+    int np;
+    int rank;
+    int64_t len, stride, rows;  // rows = chunk rows (len * number of chunks): rows at or beyond it have no destination
+};
+// x (all ranks) <- f_loc rows of this rank (cold paths: after init / restart / expand_basis; the hot path writes from the panel pass)
+void launch_peer_push(const PeerX& px, const double* f_loc, int64_t nrows_ld, cudaStream_t stream);
 
 // ---- fused Krylov-panel passes (panel.cu) ---------------------------------------------------------
 enum PanelMode
@@ -181,13 +213,14 @@ enum PanelMode
 // pred (optional): device flag; the kernel is a no-op when *pred == 0 (speculatively enqueued correction pass).
 // cplx: the vectors hold interleaved complex entries and nrows / ldv count doubles (Hermitian path); red_out / coef then use the
 // layout [0, j) = Re, [kRedNrm] = ||f||^2, [kRedNrm + 1, kRedNrm + 1 + j) = Im and j <= 63.
+// push (optional, CORR mode, real path): also write the new residual rows into every rank's SpMV operand buffer (peer memory).
 void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out,
-                       const RedScratch& rs, cudaStream_t stream, const int* pred = nullptr, bool cplx = false);
+                       const RedScratch& rs, cudaStream_t stream, const int* pred = nullptr, bool cplx = false, const PeerX* push = nullptr);
 
 // Decide kernels: consume ctl->red after a panel pass (and after the all-reduce when sharded).
-//  first = 1: after the FORM pass of a Lanczos step; first = 0: after a CORR pass (also applies
-//  the H update of Lanczos.h:172-175 with the coefficients that were just used).
-void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int first, cudaStream_t stream, int predicated = 0, bool cplx = false);
+//  stage 0: after c = V^T w (fills H(i,i), H(i-1,i), the coefficients of the first pass f = w - V c); stage 1: after that pass;
+//  stage 2: after a further correction pass (also applies the H update of Lanczos.h:172-175 with the coefficients just used).
+void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated = 0, bool cplx = false);
 // Arnoldi flavours (Arnoldi.h:242-290): stage 0 = after h = V^T w (copies h into H(:,i) and c),
 // stage 1 = after f = w - V h (DGKS test), stage 2 = after a correction pass.
 // Hi != nullptr: complex Arnoldi (Hermitian-path layout of ctl->red / ctl->c); H receives the real and Hi the imaginary parts of H(:, i)

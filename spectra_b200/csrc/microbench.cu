@@ -41,6 +41,61 @@ __global__ void __launch_bounds__(256, 8) gather_bench_kernel(const double* __re
     out[tid] = (a0 + a1) + (a2 + a3);
 }
 
+// stream_gather_bench_kernel: the same gathers, but the indices and a coefficient per gather are STREAMED from HBM exactly as a sliced
+// (ELL-like) SpMV streams its (col, val) arrays -- 12 bytes per gather in fully coalesced 128 B / 256 B warp loads, four steps in flight
+// -- and each gather depends on its index load.  No rows, no padding, no reduction tree, no output vector: acc += val[k] * x[col[k]].
+// This is the floor of ANY SpMV kernel on this access pattern (stream + dependent gather through one L1TEX and the L2), i.e. the
+// practical roof the product kernels are compared with.
+__global__ void __launch_bounds__(512, 3) stream_gather_bench_kernel(const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
+                                                                    int64_t count, double* __restrict__ out)
+{
+    const uint64_t pol_stream = l2_policy_evict_first();
+    const uint64_t pol_keep = l2_policy_evict_last();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+    // each warp owns contiguous runs of 32 * 20 entries (one "slice" of a 20-per-row matrix), strided over the grid like the windows of the product kernel
+    constexpr int RUN = 20;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const int64_t nruns = count / (32 * RUN);
+    for (int64_t r = warp; r < nruns; r += nwarps)
+    {
+        const int* cp = col + r * (32 * RUN) + lane;
+        const double* vp = val + r * (32 * RUN) + lane;
+#pragma unroll
+        for (int t = 0; t < RUN; t += 4)
+        {
+            const int c0 = ld_stream_s32(cp + (t + 0) * 32, pol_stream), c1 = ld_stream_s32(cp + (t + 1) * 32, pol_stream);
+            const int c2 = ld_stream_s32(cp + (t + 2) * 32, pol_stream), c3 = ld_stream_s32(cp + (t + 3) * 32, pol_stream);
+            const double v0 = ld_stream_f64(vp + (t + 0) * 32, pol_stream), v1 = ld_stream_f64(vp + (t + 1) * 32, pol_stream);
+            const double v2 = ld_stream_f64(vp + (t + 2) * 32, pol_stream), v3 = ld_stream_f64(vp + (t + 3) * 32, pol_stream);
+            a0 = fma(v0, ld_keep_f64(x + c0, pol_keep), a0);
+            a1 = fma(v1, ld_keep_f64(x + c1, pol_keep), a1);
+            a2 = fma(v2, ld_keep_f64(x + c2, pol_keep), a2);
+            a3 = fma(v3, ld_keep_f64(x + c3, pol_keep), a3);
+        }
+    }
+    out[(int64_t) blockIdx.x * blockDim.x + threadIdx.x] = (a0 + a1) + (a2 + a3);
+}
+
+// col[k] = uniform pseudo-random index below n (band == 0) or k / 20 + (k % 20) - 10 clamped (band != 0: neighbouring columns, coalesced gathers)
+__global__ void fill_stream_kernel(int* col, double* val, int64_t count, unsigned int n, int band)
+{
+    for (int64_t k = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (int64_t) gridDim.x * blockDim.x)
+    {
+        if (band)
+        {
+            // entry k of the step-major slice layout: run r = k / 640, step t = (k % 640) / 32, lane = k % 32  ->  row = 32 r + lane, column = row + t - 10
+            const int64_t r = k / 640, t = (k % 640) / 32, lane = k % 32;
+            int64_t c = (32 * r + lane) % n + t - 10;
+            c = c < 0 ? 0 : (c >= (int64_t) n ? (int64_t) n - 1 : c);
+            col[k] = (int) c;
+        }
+        else
+            col[k] = (int) __umulhi(mix32((unsigned int) k * 2654435761u + (unsigned int) (k >> 32)), n);
+        val[k] = 1.0;
+    }
+}
+
 __global__ void fill_ones_kernel(double* x, int64_t n)
 {
     for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
@@ -81,6 +136,46 @@ float bench_gather(int64_t n, int64_t gathers, int repeat, double* checksum)
         s += v;
     if (checksum)
         *checksum = s / (double(per_thread) * double(threads));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaStreamDestroy(st);
+    return ms / float(std::max(repeat, 1));
+}
+
+// `gathers` streamed (index, coefficient) pairs + dependent gathers from a vector of n doubles (see stream_gather_bench_kernel);
+// band != 0 uses neighbouring columns instead of uniformly random ones.  Returns the average time of `repeat` launches (ms).
+float bench_stream_gather(int64_t n, int64_t gathers, int band, int repeat, double* checksum)
+{
+    SB200_REQUIRE(n >= 1 && n < (1LL << 31) && gathers >= 640, SB200_INVALID_ARGUMENT, "bench_stream_gather: bad sizes");
+    const int sms = device_info().sm_count;
+    const int grid = sms * 3, block = 512;
+    const int64_t threads = (int64_t) grid * block;
+    const int64_t count = gathers / 640 * 640;
+    DevBuf<double> x((size_t) n), out((size_t) threads), val((size_t) count);
+    DevBuf<int> col((size_t) count);
+    cudaStream_t st;
+    SB200_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1;
+    SB200_CUDA_CHECK(cudaEventCreate(&e0));
+    SB200_CUDA_CHECK(cudaEventCreate(&e1));
+    fill_ones_kernel<<<sms * 8, 256, 0, st>>>(x.get(), n);
+    fill_stream_kernel<<<sms * 8, 256, 0, st>>>(col.get(), val.get(), count, (unsigned int) n, band);
+    stream_gather_bench_kernel<<<grid, block, 0, st>>>(col.get(), val.get(), x.get(), count, out.get());  // warm-up
+    SB200_CUDA_CHECK(cudaEventRecord(e0, st));
+    for (int r = 0; r < std::max(repeat, 1); r++)
+        stream_gather_bench_kernel<<<grid, block, 0, st>>>(col.get(), val.get(), x.get(), count, out.get());
+    SB200_CUDA_CHECK(cudaEventRecord(e1, st));
+    SB200_CUDA_CHECK(cudaEventSynchronize(e1));
+    SB200_CUDA_CHECK(cudaGetLastError());
+    float ms = 0.f;
+    SB200_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    std::vector<double> h((size_t) threads);
+    SB200_CUDA_CHECK(cudaMemcpy(h.data(), out.get(), sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+    double sum = 0.0;
+    for (double v : h)
+        sum += v;
+    if (checksum)
+        *checksum = sum / double(count);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaStreamDestroy(st);

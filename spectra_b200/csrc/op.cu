@@ -71,6 +71,8 @@ sb200_op::~sb200_op()
         cudaEventDestroy(ev_ready);
     if (comm_stream)
         cudaStreamDestroy(comm_stream);
+    sb200::peer_window_destroy(comm, win_x);
+    sb200::peer_window_destroy(comm, win_ctl);
     if (stream)
         cudaStreamDestroy(stream);
 }
@@ -106,8 +108,30 @@ static void finish_op(sb200_op* op)
         const int64_t slab = (op->A.n + ranks - 1) / ranks;
         split_column_chunks(op->A, choose_chunks(op->A.n), slab, ranks, op->stream);
         const int nb = (int) op->A.blocks.size();
-        op->x_chunks.alloc((size_t) (op->A.chunk_stride() * nb));
-        op->x_chunks.zero(op->stream);
+        const size_t xcount = (size_t) (op->A.chunk_stride() * nb);
+        // Peer mode (default on a multi-rank communicator, SB200_PEER=0 keeps the NCCL collectives): the operand buffer and the mailboxes
+        // of the one-shot all-reduce are symmetric windows that every rank maps (peer.cu); falls back when the mapping is refused.
+        const char* pe = std::getenv("SB200_PEER");
+        if (P > 1 && !(pe && pe[0] == '0'))
+        {
+            if (peer_window_create(op->comm, sizeof(double) * xcount, op->win_x, op->stream))
+            {
+                if (!peer_window_create(op->comm, peer_ctl_bytes(P), op->win_ctl, op->stream))
+                    peer_window_destroy(op->comm, op->win_x);
+            }
+        }
+        if (op->peer_mode())
+        {
+            op->xc = static_cast<double*>(op->win_x.local);
+            op->peer_seq.alloc(1);
+            op->peer_seq.zero(op->stream);
+        }
+        else
+        {
+            op->x_chunks.alloc(xcount);
+            op->x_chunks.zero(op->stream);
+            op->xc = op->x_chunks.get();
+        }
     }
     if (P > 1)
     {
@@ -257,8 +281,8 @@ void op_spmv_device(sb200_op* op, const double* x_dev, double* y_dev)
     else if (op->A.chunk_len)
     {
         // natural-layout operand -> chunk-major operand of the sharded operator (cold paths only: init, perform_op)
-        launch_permute_to_chunks(op->A, x_dev, op->x_chunks.get(), op->stream);
-        launch_spmv(op->A, op->plan, op->x_chunks.get(), y_dev, op->stream);
+        launch_permute_to_chunks(op->A, x_dev, op->xc, op->stream);
+        launch_spmv(op->A, op->plan, op->xc, y_dev, op->stream);
     }
     else
         launch_spmv(op->A, op->plan, x_dev, y_dev, op->stream);

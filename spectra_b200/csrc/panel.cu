@@ -36,7 +36,7 @@ constexpr int kColsPerGroup = 16;
 template <int NG, int MODE, bool CPLX>
 __global__ void __launch_bounds__(kPanelBlock, 2)
     panel_kernel(const double* __restrict__ V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* __restrict__ coef,
-                 double* red_out, double* partials, unsigned int* ticket, const int* pred)
+                 double* red_out, double* partials, unsigned int* ticket, const int* pred, const PeerX push)
 {
     // speculatively enqueued pass: skip when the device-side flag says no correction is needed
     if (pred != nullptr && *pred == 0)
@@ -136,6 +136,15 @@ __global__ void __launch_bounds__(kPanelBlock, 2)
         }
         if (MODE != PANEL_DOT && g == 0 && valid)
             *reinterpret_cast<double2*>(f_out + r0) = fn;
+        if (MODE == PANEL_CORR && !CPLX && push.np > 0 && g == 0 && r0 < push.rows)
+        {
+            // row-sharded runs: the new residual is the next SpMV operand of EVERY rank -- store this rank's rows straight into all
+            // operand buffers (peer memory over NVLink, chunk-major layout) instead of all-gathering them afterwards
+            const int64_t c = r0 / push.len;
+            const int64_t dst = c * push.stride + (int64_t) push.rank * push.len + (r0 - c * push.len);
+            for (int p = 0; p < push.np; p++)
+                st_peer_f64x2(push.dst[p] + dst, fn);
+        }
 #pragma unroll
         for (int kk = 0; kk < CPG; kk++)
         {
@@ -209,14 +218,14 @@ __global__ void __launch_bounds__(kPanelBlock, 2)
 
 template <int MODE>
 void launch_panel_mode(const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out, int grid,
-                       const RedScratch& rs, const int* pred, cudaStream_t stream)
+                       const RedScratch& rs, const int* pred, cudaStream_t stream, const PeerX& push)
 {
     if (j <= 16)
-        panel_kernel<1, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
+        panel_kernel<1, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, push);
     else if (j <= 32)
-        panel_kernel<2, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
+        panel_kernel<2, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, push);
     else
-        panel_kernel<4, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
+        panel_kernel<4, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, push);
 }
 
 // complex panel: 8 columns per group
@@ -224,14 +233,15 @@ template <int MODE>
 void launch_panel_mode_z(const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out, int grid,
                          const RedScratch& rs, const int* pred, cudaStream_t stream)
 {
+    const PeerX none{};
     if (j <= 8)
-        panel_kernel<1, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
+        panel_kernel<1, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none);
     else if (j <= 16)
-        panel_kernel<2, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
+        panel_kernel<2, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none);
     else if (j <= 32)
-        panel_kernel<4, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
+        panel_kernel<4, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none);
     else
-        panel_kernel<8, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred);
+        panel_kernel<8, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -253,30 +263,45 @@ __device__ __forceinline__ double panel_max_abs(const double* red, int j, int la
     return warp_max(mx);
 }
 
-__global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int first, int predicated)
+// Lanczos step, decisions after a panel pass.  The device schedule is classical Gram-Schmidt with re-orthogonalisation checks:
+//   stage 0, after  c = V[:, :j]^T w  (fused into the operator kernel or PANEL_DOT):
+//            H(i,i) = c_i (= <v_i, w>, Lanczos.h:142), H(i-1,i) = H(i,i-1) = hsub + c_{i-1}; c becomes the coefficient vector of the first
+//            pass  f = w - V c.  In exact arithmetic this is the reference's  f = w - H(i,i) v_i  followed by its first correction
+//            f -= V (V^T f), h += Vf  (Lanczos.h:145-175: Vf = c - H(i,i) e_i up to |H(i,i)| O(eps) terms) -- the correction the
+//            reference applies on all but a fraction of a percent of the steps -- done in one pass over V instead of two.
+//   stage 1, after that pass (red = V^T f, ||f||^2): count = 1, beta = ||f||, the test of Lanczos.h:156 on the new f.
+//   stage 2, after a further correction pass  f -= V c  (Lanczos.h:171-179): h += c with the coefficients just applied, count += 1, test.
+__global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, int predicated)
 {
     if (predicated && ctl->need_corr == 0)
         return;  // the speculative correction pass was skipped
     const int lane = threadIdx.x;
     const int i = ctl->i, j = i + 1;
-    int count = ctl->count;
-    if (lane == 0)
+    if (stage == 0)
     {
-        if (first)
+        for (int k = lane; k < j; k += 32)
+            ctl->c[k] = ctl->red[k];
+        if (lane == 0)
         {
-            H[i + (int64_t) i * m] = ctl->red_a[0];  // H(i,i) = <v, w>   (Lanczos.h:142)
-        }
-        else
-        {
-            // h <- h + Vf   (Lanczos.h:172-175) with the coefficients the pass just applied
-            const double hu = H[(i - 1) + (int64_t) i * m] + ctl->c[i - 1];
+            H[i + (int64_t) i * m] = ctl->red[i];
+            const double hu = ctl->hsub + ctl->red[i - 1];
             H[(i - 1) + (int64_t) i * m] = hu;
             H[i + (int64_t) (i - 1) * m] = hu;
-            H[i + (int64_t) i * m] += ctl->c[i];
+            ctl->count = 0;
+            ctl->need_corr = 1;
         }
+        return;
     }
-    if (!first)
-        count += 1;
+    int count = ctl->count;
+    if (lane == 0 && stage == 2)
+    {
+        // h <- h + Vf   (Lanczos.h:172-175) with the coefficients the pass just applied
+        const double hu = H[(i - 1) + (int64_t) i * m] + ctl->c[i - 1];
+        H[(i - 1) + (int64_t) i * m] = hu;
+        H[i + (int64_t) (i - 1) * m] = hu;
+        H[i + (int64_t) i * m] += ctl->c[i];
+    }
+    count += 1;
     const double ortho_err = panel_max_abs(ctl->red, j, lane);
     double beta = sqrt(ctl->red[kRedNrm]);  // ||f||   (Lanczos.h:146,177)
     __syncwarp();
@@ -303,29 +328,39 @@ __global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta
 // Complex (Hermitian) flavour of lanczos_decide_kernel: ctl->red / ctl->c carry Re at [k] and Im at [kRedNrm + 1 + k]; the
 // orthogonality error is the largest complex modulus (Vf.cwiseAbs().maxCoeff(), Lanczos.h:153); H is kept real -- the restart
 // reads m_fac_H.real() (HermEigsBase.h:131, 207) -- so only the real parts of the corrections enter it (Lanczos.h:172-175).
-__global__ void lanczos_decide_z_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int first, int predicated)
+__global__ void lanczos_decide_z_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, int predicated)
 {
     if (predicated && ctl->need_corr == 0)
         return;
     const int lane = threadIdx.x;
     const int i = ctl->i, j = i + 1;
-    int count = ctl->count;
-    if (lane == 0)
+    if (stage == 0)
     {
-        if (first)
+        for (int k = lane; k < j; k += 32)
         {
-            H[i + (int64_t) i * m] = ctl->red_a[0];  // H(i,i) = Re <v, w>   (Lanczos.h:142)
+            ctl->c[k] = ctl->red[k];
+            ctl->c[kRedNrm + 1 + k] = ctl->red[kRedNrm + 1 + k];
         }
-        else
+        if (lane == 0)
         {
-            const double hu = H[(i - 1) + (int64_t) i * m] + ctl->c[i - 1];
+            H[i + (int64_t) i * m] = ctl->red[i];  // H(i,i) = Re <v, w>   (Lanczos.h:142)
+            const double hu = ctl->hsub + ctl->red[i - 1];
             H[(i - 1) + (int64_t) i * m] = hu;
             H[i + (int64_t) (i - 1) * m] = hu;
-            H[i + (int64_t) i * m] += ctl->c[i];
+            ctl->count = 0;
+            ctl->need_corr = 1;
         }
+        return;
     }
-    if (!first)
-        count += 1;
+    int count = ctl->count;
+    if (lane == 0 && stage == 2)
+    {
+        const double hu = H[(i - 1) + (int64_t) i * m] + ctl->c[i - 1];
+        H[(i - 1) + (int64_t) i * m] = hu;
+        H[i + (int64_t) (i - 1) * m] = hu;
+        H[i + (int64_t) i * m] += ctl->c[i];
+    }
+    count += 1;
     double mx = 0.0;
     for (int k = lane; k < j; k += 32)
         mx = fmax(mx, hypot(ctl->red[k], ctl->red[kRedNrm + 1 + k]));
@@ -564,8 +599,10 @@ __global__ void __launch_bounds__(kGemmBlock)
 }  // namespace
 
 void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out,
-                       const RedScratch& rs, cudaStream_t stream, const int* pred, bool cplx)
+                       const RedScratch& rs, cudaStream_t stream, const int* pred, bool cplx, const PeerX* push_or_null)
 {
+    const PeerX none{};
+    const PeerX& push = (push_or_null && mode == PANEL_CORR && !cplx) ? *push_or_null : none;
     SB200_REQUIRE(j >= 1 && j <= kPanelMaxCols, SB200_INVALID_ARGUMENT, "panel width must be in [1, 64]");
     const int sms = device_info().sm_count;
     if (cplx)
@@ -593,20 +630,20 @@ void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, in
     SB200_REQUIRE(grid <= rs.max_grid, SB200_LOGIC, "panel: reduction scratch too small");
     switch (mode)
     {
-        case PANEL_DOT: launch_panel_mode<PANEL_DOT>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream); break;
-        case PANEL_FORM: launch_panel_mode<PANEL_FORM>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream); break;
-        case PANEL_CORR: launch_panel_mode<PANEL_CORR>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream); break;
+        case PANEL_DOT: launch_panel_mode<PANEL_DOT>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream, none); break;
+        case PANEL_FORM: launch_panel_mode<PANEL_FORM>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream, none); break;
+        case PANEL_CORR: launch_panel_mode<PANEL_CORR>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream, push); break;
         default: throw Error(SB200_LOGIC, "bad panel mode");
     }
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int first, cudaStream_t stream, int predicated, bool cplx)
+void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated, bool cplx)
 {
     if (cplx)
-        lanczos_decide_z_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, first, predicated);
+        lanczos_decide_z_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage, predicated);
     else
-        lanczos_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, first, predicated);
+        lanczos_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage, predicated);
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -77,10 +77,9 @@ struct sb200_gen_solver : public FacBase
                 restart = true;
             }
             // K-A: v_i = f/beta, H(i,i-1) = beta (or 0), w = A v_i   (Arnoldi.h:236-243)
-            spmv_step(i, restart, false);
+            // and h = V^T w  (:251), in the same kernel when the operand carries the sliced layout
             const int j = i + 1;
-            // h = V^T w  (:251)
-            panel(PANEL_DOT, j, w.get(), nullptr, nullptr);
+            step_dot(i, restart, false);
             launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 0, hi);
             // f = w - V h, beta, and V^T f for the DGKS test in the same pass  (:254-262)
             panel(PANEL_CORR, j, w.get(), f.get(), ctl.get()->c);
@@ -102,7 +101,10 @@ struct sb200_gen_solver : public FacBase
             }
             stats.reorth_passes += st->count;
             if (st->f_zeroed)
+            {
                 f.zero(stream());
+                x_published = false;
+            }
             h_beta = st->beta;
         }
         k = to_m;

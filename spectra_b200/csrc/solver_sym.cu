@@ -89,32 +89,31 @@ struct sb200_sym_solver : public FacBase
             if (restart)
                 expand_basis(i, 2 * (int64_t) i);
 
-            // K-A: v_i = f/beta, w = A v_i - H(i,i-1) v_{i-1}, partial <v_i, w>   (Lanczos.h:106,127-142)
-            spmv_step(i, restart, true);
-            allreduce_sum(ctl.get()->red_a, 1);
-
-            // K-B: f = w - H(i,i) v_i, beta, Vf = V^T f   (Lanczos.h:145-153)
+            // K-A+B: v_i = f/beta, w = A v_i - H(i,i-1) v_{i-1} (Lanczos.h:106,127-139) and c = V[:, :i+1]^T w in the operator kernel
+            // (sliced layout; otherwise a separate PANEL_DOT pass); c_i = <v_i, w> = H(i,i) (:142)
             const int j = i + 1;
-            panel(PANEL_FORM, j, w.get(), f.get(), ctl.get()->red_a);
+            step_dot(i, restart, true);
+            launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 0, is_cplx());
+            // K-C: f = w - V c, beta = ||f||, Vf = V^T f in one pass (Lanczos.h:145-153 and the first correction :171-179, see
+            // lanczos_decide_kernel); then the test of :156 on the device
+            panel(PANEL_CORR, j, w.get(), f.get(), ctl.get()->c);
             launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream(), 0, is_cplx());
-            // K-C: iterative correction (Lanczos.h:156-182).  In practice exactly one pass is needed per step, so the
-            // first one is enqueued speculatively, predicated on the device-side flag, before the host looks at the status.
-            panel(PANEL_CORR, j, f.get(), f.get(), ctl.get()->c, &ctl.get()->need_corr);
-            launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 1, is_cplx());
             prof.launches += 2;
             const FacCtl* st = read_status();
-            if (st->count == 0)
-                uncount_panel(j);
             while (st->need_corr)
             {
+                // further corrections f -= V Vf (Lanczos.h:156-182): rare, host sequenced
                 panel(PANEL_CORR, j, f.get(), f.get(), ctl.get()->c);
-                launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 0, is_cplx());
+                launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 2, stream(), 0, is_cplx());
                 prof.launches++;
                 st = read_status();
             }
             stats.reorth_passes += st->count;
             if (st->f_zeroed)
+            {
                 f.zero(stream());
+                x_published = false;
+            }
             h_beta = st->beta;
         }
         k = to_m;

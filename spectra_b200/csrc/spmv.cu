@@ -358,6 +358,196 @@ __global__ void __launch_bounds__(THREADS, sell_min_blocks(THREADS))
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused step head + first panel pass ("K-A+B"): the last column block of the operator application, the step head
+//   v_i = f/beta (Lanczos.h:106), w = A v_i - H(i,i-1) v_{i-1} (:131-139)
+// and the Gram-Schmidt coefficients  c = V[:, :i+1]^T w  (the adjoint_product of Lanczos.h:152 / Arnoldi.h:251) in ONE kernel.
+// Why: on uniformly random columns the gather phase is bound by the L1TEX wavefront / L2 sector rate and leaves HBM more than half
+// idle, while the panel pass is a pure HBM stream.  A CTA alternates, window by window, between the two (gather the window's row sums ->
+// step head -> stream the window's 1024 x i tile of V against the fresh w values held in shared memory), and the two resident CTAs of
+// an SM are in different phases most of the time, so the V stream fills the memory pipe the gathers cannot use.
+// Phase C is fed by TMA: warp q owns the columns k = q (mod 16) of the panel and walks them in tasks of 256 rows (2 KB, contiguous in
+// the column-major basis); one lane brings each task in with a 1-D bulk copy (cp.async.bulk + mbarrier complete_tx, L2 evict_first) into
+// the warp's private ring of kFusedSlots slots in shared memory, so the bytes in flight per SM (2 CTAs x 16 warps x 3 x 2 KB = 192 KB)
+// do not cost registers; the lanes then read 16-byte row pairs from the slot and from the w values of the window (conflict free) and
+// keep one accumulator per owned column across all windows of the CTA.
+// The coefficient c_i = <v_i, w> is formed from the registers of the step head (column i of V is being written by this kernel).
+// Reduction: warp shuffle tree, fixed order inside the CTA, grid_reduce_fixed_order across CTAs (bit-reproducible).
+// Output: red[0..i] = V[:, :i+1]^T w.  Algorithmic bytes: those of the SpMV block + 24 B/row (step head) + 8 * nrows * i (V).
+// ---------------------------------------------------------------------------------------------
+constexpr int kFusedThreads = 512;
+constexpr int kFusedWarps = kFusedThreads / 32;
+constexpr int kFusedColsPerWarp = kPanelMaxCols / kFusedWarps;  // 4
+constexpr int kFusedTaskRows = 256;                             // rows per bulk copy (2 KB)
+constexpr int kFusedSlots = 3;                                  // ring depth per warp
+constexpr int kFusedQuarters = kSellWindow / kFusedTaskRows;    // 4 tasks per column and window
+constexpr size_t kFusedRingBytes = (size_t) kFusedWarps * kFusedSlots * kFusedTaskRows * sizeof(double);  // 96 KB
+
+template <bool SYM, bool ACCUM>
+__global__ void __launch_bounds__(kFusedThreads, 2)
+    sell_step_dot_kernel(const int* __restrict__ slice_ptr, const int* __restrict__ scol, const double* __restrict__ sval, const unsigned short* __restrict__ perm,
+                         const double* __restrict__ x_full, const double* __restrict__ f_loc, double* V, int64_t ldv, double* w, int64_t nrows, int64_t nwin,
+                         FacCtl* ctl, double* H, int m, int i, int restarted, double* red_out, double* partials, unsigned int* ticket)
+{
+    constexpr int THREADS = kFusedThreads, WARPS = kFusedWarps;
+    extern __shared__ __align__(128) unsigned char fused_smem_raw[];
+    double* ring = reinterpret_cast<double*>(fused_smem_raw);  // [WARPS][kFusedSlots][kFusedTaskRows]
+    __shared__ __align__(16) double s_y[kSellWindow];
+    __shared__ __align__(8) uint64_t s_bar[WARPS * kFusedSlots];
+    __shared__ double s_col[kPanelMaxCols];
+    __shared__ double s_w[WARPS];
+    __shared__ double s_alpha;
+    const uint64_t pol_stream = l2_policy_evict_first();
+    const uint64_t pol_keep = l2_policy_evict_last();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double beta = ctl->beta;
+    const double hsub = restarted ? 0.0 : beta;
+    double* vi = V + (int64_t) i * ldv;
+    const double* vp = V + (int64_t) (i - 1) * ldv;
+
+    // the ring starts zeroed (rows past the end of a column are never copied and must not read as NaN), barriers armed for one arrival
+    for (int t = threadIdx.x; t < (int) (kFusedRingBytes / sizeof(double)); t += THREADS)
+        ring[t] = 0.0;
+    if (threadIdx.x < WARPS * kFusedSlots)
+        mbar_init(&s_bar[threadIdx.x], 1);
+    if (threadIdx.x == 0)
+        mbar_init_fence();
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    const int ncols_mine = (i > warp) ? (i - warp + WARPS - 1) / WARPS : 0;  // columns warp, warp + 16, ... below i
+    const int ntask = ncols_mine * kFusedQuarters;
+    double* my_ring = ring + (size_t) warp * kFusedSlots * kFusedTaskRows;
+    uint64_t* my_bar = s_bar + warp * kFusedSlots;
+    uint32_t issued = 0, consumed = 0;  // monotone over the whole kernel: slot = count % kFusedSlots, parity = (count / kFusedSlots) & 1
+
+    double acc[kFusedColsPerWarp];
+#pragma unroll
+    for (int q = 0; q < kFusedColsPerWarp; q++)
+        acc[q] = 0.0;
+    double part = 0.0;
+
+    for (int64_t win = blockIdx.x; win < nwin; win += gridDim.x)
+    {
+        const int64_t wrow0 = win * kSellWindow;
+        // task u of this window: column warp + 16 (u / 4), rows [wrow0 + 256 (u % 4), +256) clipped to the allocated ldv rows
+        auto issue_task = [&](int u) {
+            const int64_t r0 = wrow0 + (int64_t) (u % kFusedQuarters) * kFusedTaskRows;
+            const int64_t avail = ldv - r0;
+            const uint32_t bytes = (uint32_t) (avail >= kFusedTaskRows ? kFusedTaskRows : (avail > 0 ? avail : 0)) * (uint32_t) sizeof(double);
+            const int slot = (int) (issued % kFusedSlots);
+            if (lane == 0)
+            {
+                mbar_expect_tx(&my_bar[slot], bytes);
+                if (bytes > 0)
+                    tma_load_1d_hint(my_ring + (size_t) slot * kFusedTaskRows, V + (int64_t) (warp + WARPS * (u / kFusedQuarters)) * ldv + r0, bytes, &my_bar[slot],
+                                     pol_stream);
+            }
+            issued++;
+        };
+        // the first tasks of the window travel while the CTA gathers (they only read columns < i, which this kernel never writes)
+        int next = 0;
+        for (; next < ntask && next < kFusedSlots; next++)
+            issue_task(next);
+
+        // ---- phase A: row sums of the window (gather bound) ----
+        sell_window_dot<THREADS>(slice_ptr, scol, sval, perm, x_full, win, s_y, pol_stream, pol_keep);
+        __syncthreads();
+        // ---- phase B: step head on natural-order rows; the finished w values replace the row sums in shared memory ----
+        for (int r = threadIdx.x; r < kSellWindow; r += THREADS)
+        {
+            const int64_t row = wrow0 + r;
+            double wr = 0.0;
+            if (row < nrows)
+            {
+                double sum = s_y[r];
+                if (ACCUM)
+                    sum += w[row];
+                const double v = f_loc[row] / beta;  // v_i = f / ||f||      (Lanczos.h:106)
+                vi[row] = v;
+                wr = sum / beta;                     // w = A v_i, with the scaling applied after the product
+                if (SYM)
+                    wr -= hsub * vp[row];            // w -= H(i,i-1) v_{i-1}  (Lanczos.h:139)
+                part = fma(v, wr, part);             // <v_i, w>               (Lanczos.h:142, Arnoldi.h:251 entry i)
+                w[row] = wr;
+            }
+            s_y[r] = wr;
+        }
+        __syncthreads();
+        // ---- phase C: c_k += V[window rows, k]^T w for the owned columns k < i (HBM stream through the TMA ring) ----
+        for (int u = 0; u < ntask; u++)
+        {
+            const int slot = (int) (consumed % kFusedSlots);
+            mbar_wait(&my_bar[slot], (consumed / kFusedSlots) & 1u);
+            consumed++;
+            const double2* vs = reinterpret_cast<const double2*>(my_ring + (size_t) slot * kFusedTaskRows) + lane;
+            const double2* ws = reinterpret_cast<const double2*>(s_y + (u % kFusedQuarters) * kFusedTaskRows) + lane;
+            double sacc = 0.0;
+#pragma unroll
+            for (int q = 0; q < kFusedTaskRows / 64; q++)
+            {
+                const double2 a = vs[q * 32], ww = ws[q * 32];
+                sacc = fma(a.x, ww.x, sacc);
+                sacc = fma(a.y, ww.y, sacc);
+            }
+            const int cl = u / kFusedQuarters;
+#pragma unroll
+            for (int q = 0; q < kFusedColsPerWarp; q++)
+                if (q == cl)
+                    acc[q] += sacc;
+            __syncwarp();  // every lane has read the slot before it is refilled
+            if (next < ntask)
+            {
+                issue_task(next);
+                next++;
+            }
+        }
+        __syncthreads();  // s_y is overwritten by the next window
+    }
+
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        // step bookkeeping (Lanczos.h:127-128, Arnoldi.h:239)
+        ctl->i = i;
+        ctl->count = 0;
+        ctl->hsub = hsub;
+        ctl->need_corr = 0;
+        ctl->f_zeroed = 0;
+        ctl->dgks_skip = 0;
+        H[i + (int64_t) (i - 1) * m] = hsub;
+        if (SYM)
+            H[(i - 1) + (int64_t) i * m] = hsub;
+    }
+
+    // ---- CTA-level combine in a fixed order ----
+#pragma unroll
+    for (int q = 0; q < kFusedColsPerWarp; q++)
+    {
+        const double sum = warp_sum(acc[q]);
+        if (lane == 0)
+            s_col[warp + WARPS * q] = sum;
+    }
+    part = warp_sum(part);
+    if (lane == 0)
+        s_w[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        double a = 0.0;
+#pragma unroll
+        for (int q = 0; q < WARPS; q++)
+            a += s_w[q];
+        s_alpha = a;
+    }
+    __syncthreads();
+    double cta = 0.0;
+    if ((int) threadIdx.x < i)
+        cta = s_col[threadIdx.x];
+    else if ((int) threadIdx.x == i)
+        cta = s_alpha;
+    grid_reduce_fixed_order<THREADS>(cta, i + 1, partials, ticket, red_out);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Complex Hermitian operand (SparseHermMatProd::perform_op, MatOp/SparseHermMatProd.h:83-88): the full CSR carries
 // interleaved complex values; x and y are interleaved complex vectors.  Sub-warp of L lanes per row as in the real kernel;
 // one 16-byte gather per entry (a complex operand entry is half a sector, so the gather is twice as sector-efficient as the
@@ -491,6 +681,31 @@ void launch_sell_step_t(const SellBlock& S, int grid, int64_t nrows, const doubl
 #undef SB200_SELL_STEP
 }
 
+void launch_sell_step_dot(const SellBlock& S, int grid, int64_t nrows, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
+                          double* H, int m, int i, int restarted, bool symmetric, bool accum, double* red_out, const RedScratch& rs, cudaStream_t stream)
+{
+    static const bool attr_set = [] {
+        SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFusedRingBytes));
+        SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFusedRingBytes));
+        SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFusedRingBytes));
+        SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFusedRingBytes));
+        return true;
+    }();
+    (void) attr_set;
+#define SB200_SELL_STEP_DOT(SYM, ACC)                                                                                                                          \
+    sell_step_dot_kernel<SYM, ACC><<<grid, kFusedThreads, kFusedRingBytes, stream>>>(S.slice_ptr.get(), S.col.get(), S.val.get(), S.perm.get(), x_full, f_loc, V, ldv, w, nrows, \
+                                                                       S.nwin, ctl, H, m, i, restarted, red_out, rs.partials, rs.ticket)
+    if (symmetric && accum)
+        SB200_SELL_STEP_DOT(true, true);
+    else if (symmetric)
+        SB200_SELL_STEP_DOT(true, false);
+    else if (accum)
+        SB200_SELL_STEP_DOT(false, true);
+    else
+        SB200_SELL_STEP_DOT(false, false);
+#undef SB200_SELL_STEP_DOT
+}
+
 template <int L>
 void launch_step_t(const BlockView& b, int grid, int64_t nrows, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl, double* H,
                    int m, int i, int restarted, bool symmetric, bool accum, const RedScratch& rs, cudaStream_t stream)
@@ -553,6 +768,10 @@ SpmvPlan make_spmv_plan(const DeviceCsr& A)
         const bool persistent = (force && force[0] == '1') || S0.nwin > (int64_t) reduction_max_grid(sms);
         p.sell_grid = (int) std::max<int64_t>(1, persistent ? std::min<int64_t>(S0.nwin, resident) : S0.nwin);
         p.sell_grid_plain = persistent && force ? p.sell_grid : (int) std::max<int64_t>(1, std::min<int64_t>(S0.nwin, 1 << 30));  // no reduction: one CTA per window
+        // fused step head + panel pass (sell_step_dot_kernel): persistent, two resident CTAs of 512 threads per SM (per-lane accumulators
+        // live across the windows of a CTA).  SB200_FUSE_DOT=0 keeps the separate panel pass (A/B knob).
+        const char* fd = std::getenv("SB200_FUSE_DOT");
+        p.sell_grid_fused = (fd && fd[0] == '0') ? 0 : (int) std::max<int64_t>(1, std::min<int64_t>(S0.nwin, (int64_t) sms * 2));
     }
     return p;
 }
@@ -599,8 +818,8 @@ void launch_spmv_z(const DeviceCsrZ& A, const double* x_ri, double* y_ri, cudaSt
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_spmv_step_block(const DeviceCsr& A, const SpmvPlan& plan, int c, const double* x_block, const double* f_loc, double* V, int64_t ldv, double* w,
-                            FacCtl* ctl, double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream)
+bool launch_spmv_step_block(const DeviceCsr& A, const SpmvPlan& plan, int c, const double* x_block, const double* f_loc, double* V, int64_t ldv, double* w,
+                            FacCtl* ctl, double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream, double* dot_out)
 {
     SB200_REQUIRE(plan.grid <= rs.max_grid, SB200_LOGIC, "spmv: reduction scratch too small");
     const int nb = nblocks_of(A);
@@ -609,10 +828,17 @@ void launch_spmv_step_block(const DeviceCsr& A, const SpmvPlan& plan, int c, con
         // all but the last column block accumulate the raw product into w
         launch_plain_block(plan, view_of(A, c), A.nrows, x_block, w, c > 0, stream);
         SB200_CUDA_CHECK(cudaGetLastError());
-        return;
+        return false;
     }
     const BlockView b = view_of(A, nb - 1);
     const bool accum = nb > 1;
+    if (b.sell && plan.sell_threads && dot_out && plan.sell_grid_fused > 0 && i >= 1 && i < kPanelMaxCols)
+    {
+        SB200_REQUIRE(plan.sell_grid_fused <= rs.max_grid, SB200_LOGIC, "spmv: reduction scratch too small");
+        launch_sell_step_dot(*b.sell, plan.sell_grid_fused, A.nrows, x_block, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, dot_out, rs, stream);
+        SB200_CUDA_CHECK(cudaGetLastError());
+        return true;
+    }
     if (b.sell && plan.sell_threads)
     {
         SB200_REQUIRE(plan.sell_grid <= rs.max_grid, SB200_LOGIC, "spmv: reduction scratch too small");
@@ -623,7 +849,7 @@ void launch_spmv_step_block(const DeviceCsr& A, const SpmvPlan& plan, int c, con
             default: launch_sell_step_t<512>(*b.sell, plan.sell_grid, A.nrows, x_block, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
         }
         SB200_CUDA_CHECK(cudaGetLastError());
-        return;
+        return false;
     }
     switch (plan.lanes)
     {
@@ -634,14 +860,17 @@ void launch_spmv_step_block(const DeviceCsr& A, const SpmvPlan& plan, int c, con
         default: launch_step_t<32>(b, plan.grid, A.nrows, x_block, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, rs, stream); break;
     }
     SB200_CUDA_CHECK(cudaGetLastError());
+    return false;
 }
 
-void launch_spmv_step(const DeviceCsr& A, const SpmvPlan& plan, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
-                      double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream)
+bool launch_spmv_step(const DeviceCsr& A, const SpmvPlan& plan, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
+                      double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream, double* dot_out)
 {
     const int nb = nblocks_of(A);
+    bool fused = false;
     for (int c = 0; c < nb; c++)
-        launch_spmv_step_block(A, plan, c, A.x_of_block(x_full, c), f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, rs, stream);
+        fused = launch_spmv_step_block(A, plan, c, A.x_of_block(x_full, c), f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, rs, stream, dot_out);
+    return fused;
 }
 
 }  // namespace sb200

@@ -249,8 +249,8 @@ def _sharded_solve(emu, n, P, rp, ci, v, k, m, kind="sym", fmt_env=None):
     return out
 
 
-@pytest.mark.parametrize("P,fmt", [(2, "csr"), (3, "csr"), (2, "sell"), (3, "sell")])
-def test_emu_row_sharded_sym_solver(emu, P, fmt):
+@pytest.mark.parametrize("P,fmt,peer", [(2, "csr", 1), (3, "csr", 1), (2, "sell", 1), (3, "sell", 1), (2, "sell", 0), (3, "csr", 0)])
+def test_emu_row_sharded_sym_solver(emu, P, fmt, peer):
     # 1-D row partition, all-gather of the SpMV operand in chunks, all-reduce of the dot products; every rank must run the
     # same iteration (identical operation counts), reproduce the single-rank eigenvalues, and hold its rows of the eigenvectors
     from spectra_b200_emu import synth
@@ -258,7 +258,10 @@ def test_emu_row_sharded_sym_solver(emu, P, fmt):
     n, k, m = 901, 5, 16
     rp, ci, v = synth.csr(n, 12, 3, True)
     A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    # peer = 1: peer-memory mode (residual rows written into every rank's operand buffer by the correction pass, one-shot mailbox
+    # all-reduce, peer.cu); peer = 0: the NCCL-style collectives (all-gather + all-reduce), the fallback when peers cannot be mapped
     fmt_env = dict(SB200_SPMV_FORMAT="sell", SB200_SELL_MAX_FILL=100) if fmt == "sell" else dict(SB200_SPMV_FORMAT="csr")
+    fmt_env["SB200_PEER"] = str(peer)
     res = _sharded_solve(emu, n, P, rp, ci, v, k, m, "sym", fmt_env)
     ref = O.sym_eigs(O.Csr.adopt(n, rp, ci, v), k, m, O.LargestAlge, want_vectors=False)
     for r, o in enumerate(res):
@@ -279,6 +282,8 @@ def test_emu_row_sharded_arnoldi_factorization(emu):
     rp, ci, v = synth.csr(n, 12, 4, False)
     A = sp.csr_matrix((v, ci, rp), shape=(n, n))
     res = _sharded_solve(emu, n, 2, rp, ci, v, k, m, "gen")
+    res_nccl = _sharded_solve(emu, n, 2, rp, ci, v, k, m, "gen", dict(SB200_PEER="0"))
+    assert np.array_equal(res[0]["H"], res_nccl[0]["H"])  # peer-memory mode and the collective path sum in the same (rank) order
     assert np.array_equal(res[0]["H"], res[1]["H"]) and res[0]["beta"] == res[1]["beta"] and res[0]["nops"] == res[1]["nops"]
     V = np.vstack([o["V"] for o in res])
     f = np.concatenate([o["f"] for o in res])

@@ -358,6 +358,7 @@ inline void __syncthreads() { ::emu::syncthreads(); }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { ::emu::warp_collective(mask, 0); }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }  // emulated ranks are OS threads: a real fence
 
 template <typename T>
 inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)

@@ -120,6 +120,33 @@ static void allreduce(sb200_comm* c, double* buf, size_t count, bool is_max)
     memcpy(buf, tmp.data(), sizeof(double) * count);
     w.barrier();
 }
+// peer windows: the "peers" are threads of this process, so a window is a plain allocation whose address every rank learns through the
+// world; the peer kernels (peer.cu) then run unchanged, their system-scope flags being atomics of this process
+bool peer_window_create(sb200_comm* c, size_t bytes, PeerWindow& w, cudaStream_t)
+{
+    if (const char* e = std::getenv("SB200_EMU_NO_PEER"))
+        if (e[0] == '1')
+            return false;  // test knob: behave like a node without peer access (NCCL path)
+    EmuWorld& wd = world_of(c);
+    void* local = nullptr;
+    SB200_CUDA_CHECK(cudaMalloc(&local, bytes));
+    memset(local, 0, bytes);
+    wd.send[(size_t) c->rank] = static_cast<const double*>(local);
+    wd.barrier();
+    w.local = local;
+    w.bytes = bytes;
+    w.nranks = c->nranks;
+    for (int r = 0; r < c->nranks; r++)
+        w.peer[r] = const_cast<double*>(wd.send[(size_t) r]);
+    wd.barrier();
+    return true;
+}
+void peer_window_destroy(sb200_comm*, PeerWindow& w)
+{
+    if (w.local)
+        cudaFree(w.local);
+    w = PeerWindow();
+}
 void nccl_allreduce_sum(sb200_comm* c, double* buf, size_t count, cudaStream_t) { allreduce(c, buf, count, false); }
 void nccl_allreduce_max(sb200_comm* c, double* buf, size_t count, cudaStream_t) { allreduce(c, buf, count, true); }
 void nccl_allgather(sb200_comm* c, const double* send, double* recv, size_t count_per_rank, cudaStream_t)

@@ -26,3 +26,13 @@ for n in (125_000, 1_250_000, 5_000_000, 10_000_000, 40_000_000):
     print(json.dumps(dict(slice_doubles=n, slice_mb=round(8 * n / 2**20, 1), gathers=G, ms=round(ms, 4), gsectors_per_s=round(G / ms / 1e6, 1),
                           l2_sector_gbs=round(32 * G / ms / 1e6, 1), spmv_gather_only_ms=round(spmv_ms, 4),
                           spmv_frac_ceiling=round(2.6e9 / (spmv_ms * 1e-3) / 1e9 / PEAK, 3), checksum=r["checksum"])), flush=True)
+
+# the same gathers fed by the (index, value) stream of a sliced SpMV (12 B per gather, coalesced), uniform and band columns: the floor of
+# ANY SpMV kernel on this access pattern -- two 40 MB slices of 1e8 entries make one n = 1e7, 20 nnz/row operator application
+for band in (False, True):
+    for n in (1_250_000, 5_000_000):
+        r = sb.bench_stream_gather(n, G, band, 5)
+        ms = r["ms"]
+        print(json.dumps(dict(kind="stream+gather", columns="band" if band else "uniform", slice_doubles=n, entries=G, ms=round(ms, 4),
+                              stream_gbs=round(12 * G / ms / 1e6, 1), spmv_floor_ms=round(2 * ms, 4),
+                              spmv_frac_ceiling=round(2.6e9 / (2 * ms * 1e-3) / 1e9 / PEAK, 3), checksum=r["checksum"])), flush=True)

@@ -39,7 +39,9 @@ for prof in ((0,) if os.environ.get("QB_NOPROF") else (0, 1)):
     if prof:
         pb = 8 * n * (st["panel_cols"] + 2 * st["panel_launches"])
         out.update(ms_spmv=round(st["ms_spmv"], 1), ms_panel=round(st["ms_panel"], 1), ms_compress=round(st["ms_compress"], 1), ms_small=round(st["ms_small"], 1),
-                   panel_gbs=round(pb / st["ms_panel"] / 1e6), spmv_gbs=round((bytes_spmv + 24 * n) * st["spmv_launches"] / st["ms_spmv"] / 1e6),
+                   panel_gbs=round(pb / st["ms_panel"] / 1e6),
+                   spmv_gbs=round(((bytes_spmv + 16 * n) * st["spmv_launches"] + 8 * n * st["fused_dot_cols"]) / st["ms_spmv"] / 1e6),
+                   fused=st["fused_dot_launches"], fused_cols=st["fused_dot_cols"], panel_launches=st["panel_launches"], host_syncs=st["host_syncs"],
                    avg_panel_ms=round(st["ms_panel"] / st["panel_launches"], 4), avg_spmv_ms=round(st["ms_spmv"] / st["spmv_launches"], 4),
                    avg_small_ms=round(st["ms_small"] / max(st["restarts"] + 1, 1), 3), avg_compress_ms=round(st["ms_compress"] / max(st["compress_launches"], 1), 3))
     print(json.dumps(out), flush=True)
