@@ -162,6 +162,10 @@ int sb200_op_destroy(sb200_op* op);
  * CSR (one lane per row; the default whenever its padding is below SB200_SELL_MAX_FILL, SB200_SPMV_FORMAT=csr forces the CSR-vector kernels); *col_blocks = column blocks the operand is
  * split into; *stored_entries = matrix entries held on the device including padding. */
 int sb200_op_layout_info(const sb200_op* op, int* format, int* col_blocks, int64_t* stored_entries);
+/* Row-sharded operators (new surface): *peer = 1 when the ranks exchange the SpMV operand and the dot products through NVLink-mapped
+ * peer memory (CUDA IPC windows: residual rows written by the correction pass, one-shot mailbox all-reduce), 0 when they use the NCCL
+ * collectives (single rank, SB200_PEER=0, or peers that cannot be mapped). */
+int sb200_op_peer_mode(const sb200_op* op, int* peer);
 /* Roofline microbenchmark (tools/gather_roof.py; not on the product path): average time of `gathers` independent, uniformly random
  * 8-byte read-only loads from a device vector of n doubles -- the operand access of a CSR SpMV with random column ids, without the
  * matrix stream.  *checksum = mean of the loaded values (1.0). */

@@ -306,6 +306,12 @@ class _SparseOp:
         _check(lib().sb200_op_layout_info(self.h, C.byref(fmt), C.byref(nb), C.byref(stored)))
         return dict(format="sell" if fmt.value == 1 else "csr", col_blocks=nb.value, stored_entries=stored.value)
 
+    def peer_mode(self) -> bool:
+        """True when a row-sharded operator exchanges operand and dot products through NVLink-mapped peer memory (False: NCCL collectives)."""
+        v = C.c_int()
+        _check(lib().sb200_op_peer_mode(self.h, C.byref(v)))
+        return bool(v.value)
+
     def close(self):
         if getattr(self, "h", None):
             lib().sb200_op_destroy(self.h)

@@ -297,6 +297,14 @@ int sb200_op_layout_info(const sb200_op* op, int* format, int* col_blocks, int64
         *stored_entries = stored;
     ABI_CATCH
 }
+int sb200_op_peer_mode(const sb200_op* op, int* peer)
+{
+    ABI_TRY
+    ABI_NONNULL(op);
+    ABI_NONNULL(peer);
+    *peer = op->peer_mode() ? 1 : 0;
+    ABI_CATCH
+}
 int sb200_bench_gather(int64_t n, int64_t gathers, int repeat, float* elapsed_ms, double* checksum)
 {
     ABI_TRY

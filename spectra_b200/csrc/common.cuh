@@ -277,6 +277,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) {}
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t*) { memcpy(dst_smem, src_gmem, bytes); }
 __device__ __forceinline__ void tma_load_1d_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t*, uint64_t) { memcpy(dst_smem, src_gmem, bytes); }
 __device__ __forceinline__ void fence_proxy_async_smem() {}
+// cp.async (LDGSTS): performed synchronously; `valid` false zero-fills
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src_gmem, bool valid, uint64_t)
+{
+    if (valid)
+        memcpy(dst_smem, src_gmem, 16);
+    else
+        memset(dst_smem, 0, 16);
+}
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
 #else
 // L2 cache policies (createpolicy): streamed-once data is marked evict_first so that the gathered
 // operand vector / small reused vectors keep their L2 residency (evict_last).
@@ -414,6 +425,18 @@ __device__ __forceinline__ void tma_load_1d_hint(void* dst_smem, const void* src
                  : "memory");
 }
 __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// 16-byte asynchronous copy global -> shared (LDGSTS, L1 bypass, L2 policy); !valid: nothing is read and the destination is zero-filled
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src_gmem, bool valid, uint64_t policy)
+{
+    const uint32_t sz = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(sz), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 // orders generic-proxy accesses of shared memory before later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif  // SB200_EMU

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -88,6 +89,17 @@ struct FacBase
     PeerX px{};
     bool peer = false;
     bool x_published = false;
+    // sweep mode: the steps of one factorize_from() are enqueued back to back without reading the status in between; kernels carry the
+    // device flag FacCtl::abort that hands control back when a step needs the host (see lanczos_decide_kernel)
+    bool in_sweep = false;
+    const int* abort_flag() { return in_sweep ? &ctl.get()->abort : nullptr; }
+    bool sweep_capable() const { return !op->indirect() && !is_cplx() && (op->nranks() == 1 || peer) && !sweep_disabled(); }
+    static bool sweep_disabled()
+    {
+        static const bool off = [] { const char* e = std::getenv("SB200_SWEEP"); return e && e[0] == '0'; }();
+        return off;
+    }
+    void clear_abort() { SB200_CUDA_CHECK(cudaMemsetAsync(&ctl.get()->abort, 0, sizeof(int), stream())); }
 
     Profiler prof;
     sb200_stats stats;
@@ -174,7 +186,7 @@ struct FacBase
         {
             ScopedKernelTimer t(&prof, stream(), KC_COMM, peer ? 1 : 0);
             if (peer)
-                launch_peer_allreduce(pctl, buf, (int) count, 0, stream());
+                launch_peer_allreduce(pctl, buf, (int) count, 0, stream(), abort_flag());
             else
                 nccl_allreduce_sum(op->comm, buf, count, stream());
         }
@@ -352,7 +364,7 @@ struct FacBase
         const bool push = peer && mode == PANEL_CORR && fo == f.get();
         {
             ScopedKernelTimer t(&prof, stream(), KC_PANEL);
-            launch_panel_pass(mode, V.get(), ld, nloc, j, x, fo, coef, ctl.get()->red, rs, stream(), pred, is_cplx(), push ? &px : nullptr);
+            launch_panel_pass(mode, V.get(), ld, nloc, j, x, fo, coef, ctl.get()->red, rs, stream(), pred, is_cplx(), push ? &px : nullptr, abort_flag());
         }
         allreduce_sum(ctl.get()->red, kRedNrm + 1);
         if (push && pred == nullptr)

@@ -24,7 +24,9 @@ struct FacCtl
     int need_corr;                // another correction pass is required      (Lanczos.h:156)
     int f_zeroed;                 // beta < eps*sqrt(n): f forced to zero     (Lanczos.h:163-168)
     int dgks_skip;                // Arnoldi: beta > 0.717 ||h||, no re-orth  (Arnoldi.h:257)
-    int pad[3];
+    int abort;                    // sweep mode: a step needs the host (extra correction, zeroed residual, tiny beta) -- every later
+                                  // kernel of the enqueued sweep returns at once; `i` names the step that raised it
+    int pad[2];
     // ---- reduction outputs / coefficients -------------------------------------------------------
     double red_a[8];              // SpMV-epilogue reduction: [0] = <v_i, w>  (Lanczos.h:142)
     double c[kRedStride];         // coefficients applied by the next correction pass  (Vf, Lanczos.h:152)
@@ -169,6 +171,7 @@ int spmv_num_blocks(const DeviceCsr& A);
 bool launch_spmv_step_block(const DeviceCsr& A, const SpmvPlan& plan, int c, const double* x_block, const double* f_loc, double* V, int64_t ldv, double* w,
                             FacCtl* ctl, double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream,
                             double* dot_out = nullptr);
+// (every kernel of a step returns immediately when ctl->abort is set: sweeps enqueued without host round trips, see FacCtl::abort)
 bool launch_spmv_step(const DeviceCsr& A, const SpmvPlan& plan, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
                       double* H, int m, int i, int restarted, bool symmetric, const RedScratch& rs, cudaStream_t stream, double* dot_out = nullptr);
 
@@ -187,7 +190,8 @@ inline size_t peer_ctl_bytes(int nranks) { return sizeof(double) * 2 * (size_t) 
 // in-place all-reduce (op 0 = sum in rank order, 1 = max) of count <= kRedStride doubles in buf: every rank writes its values into every
 // peer's mailbox, releases a flag per peer, waits for the flags of all peers and combines the mailboxes in rank order (bitwise identical
 // results on every rank).  One launch, no host involvement; doubles as a barrier for peer writes issued by earlier kernels of the stream.
-void launch_peer_allreduce(const PeerCtl& pc, double* buf, int count, int op, cudaStream_t stream);
+// abort (optional): device flag; the kernel is a no-op when it is set (sweep mode; identical on every rank).
+void launch_peer_allreduce(const PeerCtl& pc, double* buf, int count, int op, cudaStream_t stream, const int* abort = nullptr);
 // Destination of this rank's residual rows in the chunk-major operand buffer of every rank (DeviceCsr::chunk_len): local row r goes to
 // x[(r / len) * stride + rank * len + r % len] on all ranks.
 struct PeerX
@@ -215,12 +219,15 @@ enum PanelMode
 // layout [0, j) = Re, [kRedNrm] = ||f||^2, [kRedNrm + 1, kRedNrm + 1 + j) = Im and j <= 63.
 // push (optional, CORR mode, real path): also write the new residual rows into every rank's SpMV operand buffer (peer memory).
 void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out,
-                       const RedScratch& rs, cudaStream_t stream, const int* pred = nullptr, bool cplx = false, const PeerX* push = nullptr);
+                       const RedScratch& rs, cudaStream_t stream, const int* pred = nullptr, bool cplx = false, const PeerX* push = nullptr,
+                       const int* abort = nullptr);
 
 // Decide kernels: consume ctl->red after a panel pass (and after the all-reduce when sharded).
 //  stage 0: after c = V^T w (fills H(i,i), H(i-1,i), the coefficients of the first pass f = w - V c); stage 1: after that pass;
 //  stage 2: after a further correction pass (also applies the H update of Lanczos.h:172-175 with the coefficients just used).
-void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated = 0, bool cplx = false);
+//  sweep != 0 (stage 1 only): the step was enqueued without a host round trip; raise ctl->abort when the host has to take over.
+void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated = 0, bool cplx = false,
+                           int sweep = 0);
 // Arnoldi flavours (Arnoldi.h:242-290): stage 0 = after h = V^T w (copies h into H(:,i) and c),
 // stage 1 = after f = w - V h (DGKS test), stage 2 = after a correction pass.
 // Hi != nullptr: complex Arnoldi (Hermitian-path layout of ctl->red / ctl->c); H receives the real and Hi the imaginary parts of H(:, i)

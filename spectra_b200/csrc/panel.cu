@@ -36,10 +36,12 @@ constexpr int kColsPerGroup = 16;
 template <int NG, int MODE, bool CPLX>
 __global__ void __launch_bounds__(kPanelBlock, 2)
     panel_kernel(const double* __restrict__ V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* __restrict__ coef,
-                 double* red_out, double* partials, unsigned int* ticket, const int* pred, const PeerX push)
+                 double* red_out, double* partials, unsigned int* ticket, const int* pred, const PeerX push, const int* abort)
 {
-    // speculatively enqueued pass: skip when the device-side flag says no correction is needed
+    // speculatively enqueued pass: skip when the device-side flag says no correction is needed; sweep mode: skip after an abort
     if (pred != nullptr && *pred == 0)
+        return;
+    if (abort != nullptr && *abort != 0)
         return;
     constexpr int CPG = CPLX ? 8 : kColsPerGroup;  // columns per group
     constexpr int NCOEF = CPLX ? 2 * kPanelMaxCols : kPanelMaxCols;
@@ -218,14 +220,14 @@ __global__ void __launch_bounds__(kPanelBlock, 2)
 
 template <int MODE>
 void launch_panel_mode(const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out, int grid,
-                       const RedScratch& rs, const int* pred, cudaStream_t stream, const PeerX& push)
+                       const RedScratch& rs, const int* pred, cudaStream_t stream, const PeerX& push, const int* abort)
 {
     if (j <= 16)
-        panel_kernel<1, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, push);
+        panel_kernel<1, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, push, abort);
     else if (j <= 32)
-        panel_kernel<2, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, push);
+        panel_kernel<2, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, push, abort);
     else
-        panel_kernel<4, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, push);
+        panel_kernel<4, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, push, abort);
 }
 
 // complex panel: 8 columns per group
@@ -235,13 +237,13 @@ void launch_panel_mode_z(const double* V, int64_t ldv, int64_t nrows, int j, con
 {
     const PeerX none{};
     if (j <= 8)
-        panel_kernel<1, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none);
+        panel_kernel<1, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none, nullptr);
     else if (j <= 16)
-        panel_kernel<2, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none);
+        panel_kernel<2, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none, nullptr);
     else if (j <= 32)
-        panel_kernel<4, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none);
+        panel_kernel<4, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none, nullptr);
     else
-        panel_kernel<8, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none);
+        panel_kernel<8, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -271,10 +273,12 @@ __device__ __forceinline__ double panel_max_abs(const double* red, int j, int la
 //            reference applies on all but a fraction of a percent of the steps -- done in one pass over V instead of two.
 //   stage 1, after that pass (red = V^T f, ||f||^2): count = 1, beta = ||f||, the test of Lanczos.h:156 on the new f.
 //   stage 2, after a further correction pass  f -= V c  (Lanczos.h:171-179): h += c with the coefficients just applied, count += 1, test.
-__global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, int predicated)
+__global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, int predicated, int sweep)
 {
     if (predicated && ctl->need_corr == 0)
         return;  // the speculative correction pass was skipped
+    if (ctl->abort != 0)
+        return;  // sweep mode: an earlier step handed control back to the host
     const int lane = threadIdx.x;
     const int i = ctl->i, j = i + 1;
     if (stage == 0)
@@ -322,6 +326,10 @@ __global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta
         ctl->count = count;
         ctl->need_corr = need;
         ctl->f_zeroed = zeroed;
+        // sweep mode: the next step may only follow on the device when this one is complete and the host-side tests at the head of the
+        // next step (beta < near_0, beta < sqrt(eps): Lanczos.h:99-113) cannot fire
+        if (sweep && (need || zeroed || !(beta >= 1.4901161193847656e-08)))
+            ctl->abort = 1;
     }
 }
 
@@ -599,7 +607,7 @@ __global__ void __launch_bounds__(kGemmBlock)
 }  // namespace
 
 void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out,
-                       const RedScratch& rs, cudaStream_t stream, const int* pred, bool cplx, const PeerX* push_or_null)
+                       const RedScratch& rs, cudaStream_t stream, const int* pred, bool cplx, const PeerX* push_or_null, const int* abort)
 {
     const PeerX none{};
     const PeerX& push = (push_or_null && mode == PANEL_CORR && !cplx) ? *push_or_null : none;
@@ -630,20 +638,20 @@ void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, in
     SB200_REQUIRE(grid <= rs.max_grid, SB200_LOGIC, "panel: reduction scratch too small");
     switch (mode)
     {
-        case PANEL_DOT: launch_panel_mode<PANEL_DOT>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream, none); break;
-        case PANEL_FORM: launch_panel_mode<PANEL_FORM>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream, none); break;
-        case PANEL_CORR: launch_panel_mode<PANEL_CORR>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream, push); break;
+        case PANEL_DOT: launch_panel_mode<PANEL_DOT>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream, none, abort); break;
+        case PANEL_FORM: launch_panel_mode<PANEL_FORM>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream, none, abort); break;
+        case PANEL_CORR: launch_panel_mode<PANEL_CORR>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream, push, abort); break;
         default: throw Error(SB200_LOGIC, "bad panel mode");
     }
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated, bool cplx)
+void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated, bool cplx, int sweep)
 {
     if (cplx)
         lanczos_decide_z_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage, predicated);
     else
-        lanczos_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage, predicated);
+        lanczos_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage, predicated, sweep);
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -20,8 +20,10 @@ namespace sb200 {
 
 namespace {
 
-__global__ void __launch_bounds__(128) peer_allreduce_kernel(PeerCtl pc, double* buf, int count, int op)
+__global__ void __launch_bounds__(128) peer_allreduce_kernel(PeerCtl pc, double* buf, int count, int op, const int* abort)
 {
+    if (abort != nullptr && *abort != 0)
+        return;  // sweep mode after an abort: every rank skips the same rounds (the flag derives from reduced, identical values)
     const int t = threadIdx.x;
     const int P = pc.nranks, me = pc.rank;
     __shared__ unsigned long long s_seq;
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(256) peer_push_kernel(PeerX px, const double* 
 
 }  // namespace
 
-void launch_peer_allreduce(const PeerCtl& pc, double* buf, int count, int op, cudaStream_t stream)
+void launch_peer_allreduce(const PeerCtl& pc, double* buf, int count, int op, cudaStream_t stream, const int* abort)
 {
     SB200_REQUIRE(count >= 1 && count <= kRedStride && pc.nranks >= 1 && pc.nranks <= kPeerMax, SB200_LOGIC, "peer all-reduce: bad arguments");
 #ifdef SB200_EMU
@@ -86,6 +88,8 @@ void launch_peer_allreduce(const PeerCtl& pc, double* buf, int count, int op, cu
     // spins on a peer's flag can never be answered.  The same mailbox protocol is therefore run by the rank's host thread, outside
     // the launch lock -- it exercises the protocol (parity, flags, rank-order sum) and the drivers' use of it, not the kernel text.
     (void) stream;
+    if (abort != nullptr && *abort != 0)
+        return;
     const int P = pc.nranks, me = pc.rank;
     const unsigned long long seq = *pc.seq + 1ull;
     const int par = (int) (seq & 1ull);
@@ -111,7 +115,7 @@ void launch_peer_allreduce(const PeerCtl& pc, double* buf, int count, int op, cu
     }
     *pc.seq = seq;
 #else
-    peer_allreduce_kernel<<<1, 128, 0, stream>>>(pc, buf, count, op);
+    peer_allreduce_kernel<<<1, 128, 0, stream>>>(pc, buf, count, op, abort);
     SB200_CUDA_CHECK(cudaGetLastError());
 #endif
 }

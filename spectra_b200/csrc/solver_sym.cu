@@ -61,6 +61,26 @@ struct sb200_sym_solver : public FacBase
         init_factorization(init_resid);
     }
 
+    // tail of one Lanczos step on the host: further corrections f -= V Vf while the device asks for them (Lanczos.h:156-182; rare),
+    // the zeroed residual of :163-168, and the host copy of beta
+    void finish_step(const FacCtl* st, int j, double beta_thresh)
+    {
+        while (st->need_corr)
+        {
+            panel(PANEL_CORR, j, f.get(), f.get(), ctl.get()->c);
+            launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 2, stream(), 0, is_cplx());
+            prof.launches++;
+            st = read_status();
+        }
+        stats.reorth_passes += st->count;
+        if (st->f_zeroed)
+        {
+            f.zero(stream());
+            x_published = false;
+        }
+        h_beta = st->beta;
+    }
+
     // ---- Lanczos::factorize_from (Lanczos.h:62-187) ----
     void factorize_from(int64_t from_k, int64_t to_m)
     {
@@ -74,7 +94,57 @@ struct sb200_sym_solver : public FacBase
         launch_trim_h(H.get(), m, (int) from_k, stream());
         prof.launches++;
 
-        for (int i = (int) from_k; i <= (int) to_m - 1; i++)
+        int i = (int) from_k;
+        // Sweep mode (common path): all remaining steps are enqueued without a host round trip; the status is read once at the end.  A
+        // step that needs the host -- a second correction pass, a zeroed residual, beta below sqrt(eps) (the restart tests at the head
+        // of the next step) -- raises FacCtl::abort on the device, the kernels enqueued behind it return at once, and the loop below
+        // finishes that step and the rest of the factorisation one step at a time.
+        if (sweep_capable() && i <= (int) to_m - 1 && h_beta >= eps_sqrt)
+        {
+            struct Snap
+            {
+                int64_t nmatop;
+                sb200_stats stats;
+                int64_t launches;
+            };
+            std::vector<Snap> snap;
+            in_sweep = true;
+            for (int s = i; s <= (int) to_m - 1; s++)
+            {
+                snap.push_back({nmatop, stats, prof.launches});
+                stats.lanczos_steps++;
+                step_dot(s, false, true);
+                launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 0, false);
+                panel(PANEL_CORR, s + 1, w.get(), f.get(), ctl.get()->c);
+                launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream(), 0, false, 1);
+                prof.launches += 2;
+                stats.reorth_passes += 1;
+            }
+            in_sweep = false;
+            const FacCtl* st = read_status();
+            if (!st->abort)
+            {
+                h_beta = st->beta;
+                k = to_m;
+                return;
+            }
+            // step st->i ran up to its first correction pass and raised the flag; nothing after it executed
+            const int ia = st->i;
+            const Snap& sn = snap[(size_t) (ia + 1 - i)];  // counters as they stood before step ia + 1 was enqueued
+            if (ia + 1 <= (int) to_m - 1)
+            {
+                nmatop = sn.nmatop;
+                const int64_t syncs = stats.host_syncs;
+                stats = sn.stats;
+                stats.host_syncs = syncs;
+                prof.launches = sn.launches;
+            }
+            stats.reorth_passes -= 1;  // re-counted from the device counter below
+            clear_abort();
+            finish_step(st, ia + 1, beta_thresh);
+            i = ia + 1;
+        }
+        for (; i <= (int) to_m - 1; i++)
         {
             stats.lanczos_steps++;
             bool restart = (h_beta < kNear0);
@@ -99,22 +169,7 @@ struct sb200_sym_solver : public FacBase
             panel(PANEL_CORR, j, w.get(), f.get(), ctl.get()->c);
             launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream(), 0, is_cplx());
             prof.launches += 2;
-            const FacCtl* st = read_status();
-            while (st->need_corr)
-            {
-                // further corrections f -= V Vf (Lanczos.h:156-182): rare, host sequenced
-                panel(PANEL_CORR, j, f.get(), f.get(), ctl.get()->c);
-                launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 2, stream(), 0, is_cplx());
-                prof.launches++;
-                st = read_status();
-            }
-            stats.reorth_passes += st->count;
-            if (st->f_zeroed)
-            {
-                f.zero(stream());
-                x_published = false;
-            }
-            h_beta = st->beta;
+            finish_step(read_status(), j, beta_thresh);
         }
         k = to_m;
     }

@@ -98,8 +98,10 @@ __device__ __forceinline__ double warp_rows_dot(const int* __restrict__ rowptr, 
 // y = (ACCUM ? y : 0) + A_block x
 template <int L, bool ACCUM>
 __global__ void __launch_bounds__(kSpmvBlock, 8) spmv_plain_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
-                                                                const double* __restrict__ x, double* y, int64_t nrows)
+                                                                const double* __restrict__ x, double* y, int64_t nrows, const int* abort)
 {
+    if (abort != nullptr && *abort != 0)
+        return;
     const uint64_t pol_stream = l2_policy_evict_first();
     const uint64_t pol_keep = l2_policy_evict_last();
     const int wlane = threadIdx.x & 31;
@@ -136,6 +138,8 @@ __global__ void __launch_bounds__(kSpmvBlock, SB200_STEP_MINBLOCKS)
     const int wlane = threadIdx.x & 31;
     const int64_t warp = (int64_t) blockIdx.x * (kSpmvBlock / 32) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t) gridDim.x * (kSpmvBlock / 32);
+    if (ctl->abort != 0)
+        return;  // sweep mode: an earlier step handed control back to the host
     const double beta = ctl->beta;
     const double hsub = restarted ? 0.0 : beta;
     double* __restrict__ vi = V + (int64_t) i * ldv;
@@ -258,9 +262,11 @@ __device__ __forceinline__ void sell_window_dot(const int* __restrict__ slice_pt
 template <int THREADS, bool ACCUM>
 __global__ void __launch_bounds__(THREADS, sell_min_blocks(THREADS))
     sell_plain_kernel(const int* __restrict__ slice_ptr, const int* __restrict__ scol, const double* __restrict__ sval, const unsigned short* __restrict__ perm,
-                      const double* __restrict__ x, double* y, int64_t nrows, int64_t nwin)
+                      const double* __restrict__ x, double* y, int64_t nrows, int64_t nwin, const int* abort)
 {
     __shared__ double s_y[kSellWindow];
+    if (abort != nullptr && *abort != 0)
+        return;
     const uint64_t pol_stream = l2_policy_evict_first();
     const uint64_t pol_keep = l2_policy_evict_last();
     for (int64_t win = blockIdx.x; win < nwin; win += gridDim.x)
@@ -292,6 +298,8 @@ __global__ void __launch_bounds__(THREADS, sell_min_blocks(THREADS))
     __shared__ double s_y[kSellWindow];
     const uint64_t pol_stream = l2_policy_evict_first();
     const uint64_t pol_keep = l2_policy_evict_last();
+    if (ctl->abort != 0)
+        return;  // sweep mode: an earlier step handed control back to the host
     const double beta = ctl->beta;
     const double hsub = restarted ? 0.0 : beta;
     double* __restrict__ vi = V + (int64_t) i * ldv;
@@ -377,12 +385,24 @@ __global__ void __launch_bounds__(THREADS, sell_min_blocks(THREADS))
 constexpr int kFusedThreads = 512;
 constexpr int kFusedWarps = kFusedThreads / 32;
 constexpr int kFusedColsPerWarp = kPanelMaxCols / kFusedWarps;  // 4
-constexpr int kFusedTaskRows = 256;                             // rows per bulk copy (2 KB)
+constexpr int kFusedTaskRows = 256;                             // rows per staged task (2 KB)
 constexpr int kFusedSlots = 3;                                  // ring depth per warp
 constexpr int kFusedQuarters = kSellWindow / kFusedTaskRows;    // 4 tasks per column and window
 constexpr size_t kFusedRingBytes = (size_t) kFusedWarps * kFusedSlots * kFusedTaskRows * sizeof(double);  // 96 KB
+// How phase C brings the V tile in (A/B knob SB200_FUSED_IMPL; the default is the measured best):
+//   FUSED_REG   plain 128-bit loads into registers, two batches of four per task -- no staging, but the bytes in flight are bounded by
+//               the 64 registers a thread may use at two 512-thread CTAs per SM;
+//   FUSED_TMA   one 1-D bulk copy (cp.async.bulk + mbarrier complete_tx) per 2 KB task, issued by one lane into the warp's ring;
+//   FUSED_CPA   16-byte cp.async (LDGSTS) copies, four per lane and task, into the same ring; a lane consumes exactly what it copied,
+//               so the ring is a per-lane FIFO that needs no barrier, only cp.async.wait_group.
+enum FusedImpl
+{
+    FUSED_REG = 0,
+    FUSED_TMA = 1,
+    FUSED_CPA = 2
+};
 
-template <bool SYM, bool ACCUM>
+template <bool SYM, bool ACCUM, int IMPL>
 __global__ void __launch_bounds__(kFusedThreads, 2)
     sell_step_dot_kernel(const int* __restrict__ slice_ptr, const int* __restrict__ scol, const double* __restrict__ sval, const unsigned short* __restrict__ perm,
                          const double* __restrict__ x_full, const double* __restrict__ f_loc, double* V, int64_t ldv, double* w, int64_t nrows, int64_t nwin,
@@ -390,7 +410,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
 {
     constexpr int THREADS = kFusedThreads, WARPS = kFusedWarps;
     extern __shared__ __align__(128) unsigned char fused_smem_raw[];
-    double* ring = reinterpret_cast<double*>(fused_smem_raw);  // [WARPS][kFusedSlots][kFusedTaskRows]
+    double* ring = reinterpret_cast<double*>(fused_smem_raw);  // [WARPS][kFusedSlots][kFusedTaskRows]   (FUSED_TMA / FUSED_CPA)
     __shared__ __align__(16) double s_y[kSellWindow];
     __shared__ __align__(8) uint64_t s_bar[WARPS * kFusedSlots];
     __shared__ double s_col[kPanelMaxCols];
@@ -399,20 +419,25 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
     const uint64_t pol_stream = l2_policy_evict_first();
     const uint64_t pol_keep = l2_policy_evict_last();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (ctl->abort != 0)
+        return;  // sweep mode: an earlier step handed control back to the host
     const double beta = ctl->beta;
     const double hsub = restarted ? 0.0 : beta;
     double* vi = V + (int64_t) i * ldv;
     const double* vp = V + (int64_t) (i - 1) * ldv;
 
-    // the ring starts zeroed (rows past the end of a column are never copied and must not read as NaN), barriers armed for one arrival
-    for (int t = threadIdx.x; t < (int) (kFusedRingBytes / sizeof(double)); t += THREADS)
-        ring[t] = 0.0;
-    if (threadIdx.x < WARPS * kFusedSlots)
-        mbar_init(&s_bar[threadIdx.x], 1);
-    if (threadIdx.x == 0)
-        mbar_init_fence();
-    fence_proxy_async_smem();
-    __syncthreads();
+    if (IMPL == FUSED_TMA)
+    {
+        // the ring starts zeroed (rows past the end of a column are never copied and must not read as NaN), barriers armed for one arrival
+        for (int t = threadIdx.x; t < (int) (kFusedRingBytes / sizeof(double)); t += THREADS)
+            ring[t] = 0.0;
+        if (threadIdx.x < WARPS * kFusedSlots)
+            mbar_init(&s_bar[threadIdx.x], 1);
+        if (threadIdx.x == 0)
+            mbar_init_fence();
+        fence_proxy_async_smem();
+        __syncthreads();
+    }
 
     const int ncols_mine = (i > warp) ? (i - warp + WARPS - 1) / WARPS : 0;  // columns warp, warp + 16, ... below i
     const int ntask = ncols_mine * kFusedQuarters;
@@ -432,22 +457,40 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
         // task u of this window: column warp + 16 (u / 4), rows [wrow0 + 256 (u % 4), +256) clipped to the allocated ldv rows
         auto issue_task = [&](int u) {
             const int64_t r0 = wrow0 + (int64_t) (u % kFusedQuarters) * kFusedTaskRows;
-            const int64_t avail = ldv - r0;
-            const uint32_t bytes = (uint32_t) (avail >= kFusedTaskRows ? kFusedTaskRows : (avail > 0 ? avail : 0)) * (uint32_t) sizeof(double);
+            const double* colp = V + (int64_t) (warp + WARPS * (u / kFusedQuarters)) * ldv;
             const int slot = (int) (issued % kFusedSlots);
-            if (lane == 0)
+            if (IMPL == FUSED_TMA)
             {
-                mbar_expect_tx(&my_bar[slot], bytes);
-                if (bytes > 0)
-                    tma_load_1d_hint(my_ring + (size_t) slot * kFusedTaskRows, V + (int64_t) (warp + WARPS * (u / kFusedQuarters)) * ldv + r0, bytes, &my_bar[slot],
-                                     pol_stream);
+                const int64_t avail = ldv - r0;
+                const uint32_t bytes = (uint32_t) (avail >= kFusedTaskRows ? kFusedTaskRows : (avail > 0 ? avail : 0)) * (uint32_t) sizeof(double);
+                if (lane == 0)
+                {
+                    mbar_expect_tx(&my_bar[slot], bytes);
+                    if (bytes > 0)
+                        tma_load_1d_hint(my_ring + (size_t) slot * kFusedTaskRows, colp + r0, bytes, &my_bar[slot], pol_stream);
+                }
+            }
+            else
+            {
+                double* dst = my_ring + (size_t) slot * kFusedTaskRows + lane * 2;
+#pragma unroll
+                for (int q = 0; q < kFusedTaskRows / 64; q++)
+                {
+                    const int64_t r = r0 + q * 64 + lane * 2;
+                    const bool ok = r < ldv;
+                    cp_async_16(dst + q * 64, colp + (ok ? r : 0), ok, pol_stream);
+                }
+                cp_async_commit();
             }
             issued++;
         };
-        // the first tasks of the window travel while the CTA gathers (they only read columns < i, which this kernel never writes)
         int next = 0;
-        for (; next < ntask && next < kFusedSlots; next++)
-            issue_task(next);
+        if (IMPL != FUSED_REG)
+        {
+            // the first tasks of the window travel while the CTA gathers (they only read columns < i, which this kernel never writes)
+            for (; next < ntask && next < kFusedSlots; next++)
+                issue_task(next);
+        }
 
         // ---- phase A: row sums of the window (gather bound) ----
         sell_window_dot<THREADS>(slice_ptr, scol, sval, perm, x_full, win, s_y, pol_stream, pol_keep);
@@ -473,33 +516,65 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
             s_y[r] = wr;
         }
         __syncthreads();
-        // ---- phase C: c_k += V[window rows, k]^T w for the owned columns k < i (HBM stream through the TMA ring) ----
+        // ---- phase C: c_k += V[window rows, k]^T w for the owned columns k < i (HBM stream) ----
         for (int u = 0; u < ntask; u++)
         {
-            const int slot = (int) (consumed % kFusedSlots);
-            mbar_wait(&my_bar[slot], (consumed / kFusedSlots) & 1u);
-            consumed++;
-            const double2* vs = reinterpret_cast<const double2*>(my_ring + (size_t) slot * kFusedTaskRows) + lane;
             const double2* ws = reinterpret_cast<const double2*>(s_y + (u % kFusedQuarters) * kFusedTaskRows) + lane;
             double sacc = 0.0;
-#pragma unroll
-            for (int q = 0; q < kFusedTaskRows / 64; q++)
+            if (IMPL == FUSED_REG)
             {
-                const double2 a = vs[q * 32], ww = ws[q * 32];
-                sacc = fma(a.x, ww.x, sacc);
-                sacc = fma(a.y, ww.y, sacc);
+                const int64_t r0 = wrow0 + (int64_t) (u % kFusedQuarters) * kFusedTaskRows + lane * 2;
+                const double* colp = V + (int64_t) (warp + WARPS * (u / kFusedQuarters)) * ldv + r0;
+                double2 a[kFusedTaskRows / 64];
+#pragma unroll
+                for (int q = 0; q < kFusedTaskRows / 64; q++)
+                    a[q] = (r0 + q * 64 < ldv) ? ld_stream_f64x2(colp + q * 64, pol_stream) : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int q = 0; q < kFusedTaskRows / 64; q++)
+                {
+                    const double2 ww = ws[q * 32];
+                    sacc = fma(a[q].x, ww.x, sacc);
+                    sacc = fma(a[q].y, ww.y, sacc);
+                }
+            }
+            else
+            {
+                const int slot = (int) (consumed % kFusedSlots);
+                if (IMPL == FUSED_TMA)
+                    mbar_wait(&my_bar[slot], (consumed / kFusedSlots) & 1u);
+                else
+                {
+                    // this lane's copies of task u have landed once at most (tasks still in flight behind it) groups are pending
+                    const int behind = next - u - 1;
+                    if (behind >= 2)
+                        cp_async_wait<2>();
+                    else if (behind == 1)
+                        cp_async_wait<1>();
+                    else
+                        cp_async_wait<0>();
+                }
+                consumed++;
+                const double2* vs = reinterpret_cast<const double2*>(my_ring + (size_t) slot * kFusedTaskRows) + lane;
+#pragma unroll
+                for (int q = 0; q < kFusedTaskRows / 64; q++)
+                {
+                    const double2 a = vs[q * 32], ww = ws[q * 32];
+                    sacc = fma(a.x, ww.x, sacc);
+                    sacc = fma(a.y, ww.y, sacc);
+                }
+                if (IMPL == FUSED_TMA)
+                    __syncwarp();  // every lane has read the slot before one lane refills it
+                if (next < ntask)
+                {
+                    issue_task(next);
+                    next++;
+                }
             }
             const int cl = u / kFusedQuarters;
 #pragma unroll
             for (int q = 0; q < kFusedColsPerWarp; q++)
                 if (q == cl)
                     acc[q] += sacc;
-            __syncwarp();  // every lane has read the slot before it is refilled
-            if (next < ntask)
-            {
-                issue_task(next);
-                next++;
-            }
         }
         __syncthreads();  // s_y is overwritten by the next window
     }
@@ -623,43 +698,44 @@ int lanes_for(double avg)
 }
 
 template <int L>
-void launch_plain_t(const BlockView& b, int grid, int64_t nrows, const double* x, double* y, bool accum, cudaStream_t stream)
+void launch_plain_t(const BlockView& b, int grid, int64_t nrows, const double* x, double* y, bool accum, cudaStream_t stream, const int* abort)
 {
     if (accum)
-        spmv_plain_kernel<L, true><<<grid, kSpmvBlock, 0, stream>>>(b.rowptr, b.col, b.val, x, y, nrows);
+        spmv_plain_kernel<L, true><<<grid, kSpmvBlock, 0, stream>>>(b.rowptr, b.col, b.val, x, y, nrows, abort);
     else
-        spmv_plain_kernel<L, false><<<grid, kSpmvBlock, 0, stream>>>(b.rowptr, b.col, b.val, x, y, nrows);
+        spmv_plain_kernel<L, false><<<grid, kSpmvBlock, 0, stream>>>(b.rowptr, b.col, b.val, x, y, nrows, abort);
 }
 
 template <int THREADS>
-void launch_sell_plain_t(const SellBlock& S, int grid, int64_t nrows, const double* x, double* y, bool accum, cudaStream_t stream)
+void launch_sell_plain_t(const SellBlock& S, int grid, int64_t nrows, const double* x, double* y, bool accum, cudaStream_t stream, const int* abort)
 {
     if (accum)
-        sell_plain_kernel<THREADS, true><<<grid, THREADS, 0, stream>>>(S.slice_ptr.get(), S.col.get(), S.val.get(), S.perm.get(), x, y, nrows, S.nwin);
+        sell_plain_kernel<THREADS, true><<<grid, THREADS, 0, stream>>>(S.slice_ptr.get(), S.col.get(), S.val.get(), S.perm.get(), x, y, nrows, S.nwin, abort);
     else
-        sell_plain_kernel<THREADS, false><<<grid, THREADS, 0, stream>>>(S.slice_ptr.get(), S.col.get(), S.val.get(), S.perm.get(), x, y, nrows, S.nwin);
+        sell_plain_kernel<THREADS, false><<<grid, THREADS, 0, stream>>>(S.slice_ptr.get(), S.col.get(), S.val.get(), S.perm.get(), x, y, nrows, S.nwin, abort);
 }
 
-void launch_plain_block(const SpmvPlan& plan, const BlockView& b, int64_t nrows, const double* x, double* y, bool accum, cudaStream_t stream)
+void launch_plain_block(const SpmvPlan& plan, const BlockView& b, int64_t nrows, const double* x, double* y, bool accum, cudaStream_t stream,
+                        const int* abort = nullptr)
 {
     if (b.sell && plan.sell_threads)
     {
         switch (plan.sell_threads)
         {
-            case 256: launch_sell_plain_t<256>(*b.sell, plan.sell_grid_plain, nrows, x, y, accum, stream); break;
-            case 1024: launch_sell_plain_t<1024>(*b.sell, plan.sell_grid_plain, nrows, x, y, accum, stream); break;
-            default: launch_sell_plain_t<512>(*b.sell, plan.sell_grid_plain, nrows, x, y, accum, stream); break;
+            case 256: launch_sell_plain_t<256>(*b.sell, plan.sell_grid_plain, nrows, x, y, accum, stream, abort); break;
+            case 1024: launch_sell_plain_t<1024>(*b.sell, plan.sell_grid_plain, nrows, x, y, accum, stream, abort); break;
+            default: launch_sell_plain_t<512>(*b.sell, plan.sell_grid_plain, nrows, x, y, accum, stream, abort); break;
         }
         return;
     }
     const int grid = plan.grid;
     switch (plan.lanes)
     {
-        case 2: launch_plain_t<2>(b, grid, nrows, x, y, accum, stream); break;
-        case 4: launch_plain_t<4>(b, grid, nrows, x, y, accum, stream); break;
-        case 8: launch_plain_t<8>(b, grid, nrows, x, y, accum, stream); break;
-        case 16: launch_plain_t<16>(b, grid, nrows, x, y, accum, stream); break;
-        default: launch_plain_t<32>(b, grid, nrows, x, y, accum, stream); break;
+        case 2: launch_plain_t<2>(b, grid, nrows, x, y, accum, stream, abort); break;
+        case 4: launch_plain_t<4>(b, grid, nrows, x, y, accum, stream, abort); break;
+        case 8: launch_plain_t<8>(b, grid, nrows, x, y, accum, stream, abort); break;
+        case 16: launch_plain_t<16>(b, grid, nrows, x, y, accum, stream, abort); break;
+        default: launch_plain_t<32>(b, grid, nrows, x, y, accum, stream, abort); break;
     }
 }
 
@@ -681,20 +757,25 @@ void launch_sell_step_t(const SellBlock& S, int grid, int64_t nrows, const doubl
 #undef SB200_SELL_STEP
 }
 
-void launch_sell_step_dot(const SellBlock& S, int grid, int64_t nrows, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
-                          double* H, int m, int i, int restarted, bool symmetric, bool accum, double* red_out, const RedScratch& rs, cudaStream_t stream)
+template <int IMPL>
+void launch_sell_step_dot_t(const SellBlock& S, int grid, int64_t nrows, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
+                            double* H, int m, int i, int restarted, bool symmetric, bool accum, double* red_out, const RedScratch& rs, cudaStream_t stream)
 {
+    constexpr size_t smem = (IMPL == FUSED_REG) ? 0 : kFusedRingBytes;
     static const bool attr_set = [] {
-        SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFusedRingBytes));
-        SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFusedRingBytes));
-        SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFusedRingBytes));
-        SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFusedRingBytes));
+        if (smem > 0)
+        {
+            SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<true, true, IMPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<true, false, IMPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<false, true, IMPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<false, false, IMPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        }
         return true;
     }();
     (void) attr_set;
 #define SB200_SELL_STEP_DOT(SYM, ACC)                                                                                                                          \
-    sell_step_dot_kernel<SYM, ACC><<<grid, kFusedThreads, kFusedRingBytes, stream>>>(S.slice_ptr.get(), S.col.get(), S.val.get(), S.perm.get(), x_full, f_loc, V, ldv, w, nrows, \
-                                                                       S.nwin, ctl, H, m, i, restarted, red_out, rs.partials, rs.ticket)
+    sell_step_dot_kernel<SYM, ACC, IMPL><<<grid, kFusedThreads, smem, stream>>>(S.slice_ptr.get(), S.col.get(), S.val.get(), S.perm.get(), x_full, f_loc, V, ldv, w, \
+                                                                                nrows, S.nwin, ctl, H, m, i, restarted, red_out, rs.partials, rs.ticket)
     if (symmetric && accum)
         SB200_SELL_STEP_DOT(true, true);
     else if (symmetric)
@@ -704,6 +785,27 @@ void launch_sell_step_dot(const SellBlock& S, int grid, int64_t nrows, const dou
     else
         SB200_SELL_STEP_DOT(false, false);
 #undef SB200_SELL_STEP_DOT
+}
+
+void launch_sell_step_dot(const SellBlock& S, int grid, int64_t nrows, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
+                          double* H, int m, int i, int restarted, bool symmetric, bool accum, double* red_out, const RedScratch& rs, cudaStream_t stream)
+{
+    static const int impl = [] {
+        const char* e = std::getenv("SB200_FUSED_IMPL");
+        if (e && std::strcmp(e, "reg") == 0)
+            return (int) FUSED_REG;
+        if (e && std::strcmp(e, "tma") == 0)
+            return (int) FUSED_TMA;
+        if (e && std::strcmp(e, "cpasync") == 0)
+            return (int) FUSED_CPA;
+        return (int) FUSED_CPA;
+    }();
+    switch (impl)
+    {
+        case FUSED_REG: launch_sell_step_dot_t<FUSED_REG>(S, grid, nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, red_out, rs, stream); break;
+        case FUSED_TMA: launch_sell_step_dot_t<FUSED_TMA>(S, grid, nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, red_out, rs, stream); break;
+        default: launch_sell_step_dot_t<FUSED_CPA>(S, grid, nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, red_out, rs, stream); break;
+    }
 }
 
 template <int L>
@@ -826,7 +928,7 @@ bool launch_spmv_step_block(const DeviceCsr& A, const SpmvPlan& plan, int c, con
     if (c + 1 < nb)
     {
         // all but the last column block accumulate the raw product into w
-        launch_plain_block(plan, view_of(A, c), A.nrows, x_block, w, c > 0, stream);
+        launch_plain_block(plan, view_of(A, c), A.nrows, x_block, w, c > 0, stream, &ctl->abort);
         SB200_CUDA_CHECK(cudaGetLastError());
         return false;
     }

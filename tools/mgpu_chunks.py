@@ -25,10 +25,12 @@ def main():
     comm = dist.make_comm()
     row0, nrows = dist.slab_range(n, rank, world)
     rp, ci, v = synth.csr(n, 20, 0, True, row0=row0, nrows=nrows)
-    for chunks in [int(c) for c in os.environ.get("CHUNK_LIST", "1,2,4,8").split(",")]:
+    settings = [(int(c), int(p)) for p in os.environ.get("PEER_LIST", "1").split(",") for c in os.environ.get("CHUNK_LIST", "1,2,4,8").split(",")]
+    for chunks, peer in settings:
         os.environ["SB200_AG_CHUNKS"] = str(chunks)
+        os.environ["SB200_PEER"] = str(peer)
         op = sb.SparseGenMatProd.from_csr_slab(n, row0, rp, ci, v, comm=comm)
-        out = {}
+        out = {"peer_mode": op.peer_mode()}
         for prof in (0, 1):
             sb.set_profiling(prof)
             eigs = sb.SymEigsSolver(op, 20, 60)
@@ -41,7 +43,7 @@ def main():
                 out.update(chunks=chunks, world=world, n=n, nops=eigs.num_operations(), ms_total=round(ms, 2), iters_per_s=round(eigs.num_operations() / ms * 1e3, 1))
             else:
                 out.update(prof_ms_spmv=round(st["ms_spmv"], 1), prof_ms_panel=round(st["ms_panel"], 1), prof_ms_comm=round(st["ms_comm"], 1),
-                           prof_ms_small=round(st["ms_small"], 1), prof_ms_total=round(st["ms_total"], 1))
+                           prof_ms_small=round(st["ms_small"], 1), prof_ms_total=round(st["ms_total"], 1), host_syncs=st["host_syncs"])
             del eigs
         sb.set_profiling(0)
         if rank == 0:
