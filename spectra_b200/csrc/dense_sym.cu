@@ -99,9 +99,13 @@ __device__ __forceinline__ void givens_rotation_fast(double x, double y, double&
     s = -y * inv;  // s = -y / r
 }
 
-// One implicit Wilkinson-shift QR step on rows start..end of the (scaled) tridiagonal (thread 0).
+// One implicit Wilkinson-shift QR step on rows start..end of the (scaled) tridiagonal (one thread; m = order of the matrix).
 // Appends the rotations to (lc, ls) and returns their number.   TridiagEigen.h:44-108
-__device__ int tridiagonal_qr_step(double* diag, double* subdiag, int start, int end, double* lc, double* ls)
+// This loop is the serial critical path of the restart (about 4000 rotations for m = 60, one lane): the matrix entries the recurrence
+// needs are carried in registers, the next column is prefetched one iteration ahead with clamped (branch-free) indices, and only the
+// entries that are final after iteration k (diag[k], subdiag[k-1]) and the rotation log are stored inside the loop -- the three
+// running entries are written once when the sweep ends.  Same operations in the same order as the straightforward form.
+__device__ int tridiagonal_qr_step(double* diag, double* subdiag, int start, int end, int m, double* lc, double* ls)
 {
     const double td = (diag[end - 1] - diag[end]) * 0.5;
     const double e = subdiag[end - 1];
@@ -119,17 +123,18 @@ __device__ int tridiagonal_qr_step(double* diag, double* subdiag, int start, int
     }
     double x = diag[start] - mu;
     double z = subdiag[start];
-    // Register-carried copies of every entry the recurrence reads, with the next column prefetched one iteration
-    // ahead, so that no shared-memory load sits on the dependent chain (stores are fire-and-forget).
     double dk = diag[start], ek = subdiag[start];
     double dk1 = diag[start + 1];
     double ek1 = (start + 1 < end) ? subdiag[start + 1] : 0.0;
     double ekm1 = 0.0;
-    int nrot = 0;
-    for (int k = start; k < end && z != 0.0; ++k)
+    double* pc = lc;
+    double* ps = ls;
+    int k = start;
+    for (; k < end && z != 0.0; ++k)
     {
-        const double dk2 = (k + 2 <= end) ? diag[k + 2] : 0.0;
-        const double ek2 = (k + 2 < end) ? subdiag[k + 2] : 0.0;
+        // entries of column k + 2 (unused when the sweep stops before it needs them: the indices are clamped, not predicated)
+        const double dk2 = diag[min(k + 2, m - 1)];
+        const double ek2 = (k + 2 < end) ? subdiag[min(k + 2, m - 2)] : 0.0;
         double c, s;
         make_givens_scaled(x, z, c, s);
         const double sdk = s * dk + c * ek;
@@ -137,7 +142,6 @@ __device__ int tridiagonal_qr_step(double* diag, double* subdiag, int start, int
         diag[k] = c * (c * dk - s * ek) - s * (c * ek - s * dk1);
         const double ndk1 = s * sdk + c * dkp1;
         const double nek = c * sdk - s * dkp1;
-        subdiag[k] = nek;
         if (k > start)
             subdiag[k - 1] = c * ekm1 - s * z;
         x = nek;
@@ -145,16 +149,22 @@ __device__ int tridiagonal_qr_step(double* diag, double* subdiag, int start, int
         {
             z = -s * ek1;
             ek = c * ek1;
-            subdiag[k + 1] = ek;
         }
         ekm1 = nek;
         dk = ndk1;
-        diag[k + 1] = ndk1;
         dk1 = dk2;
         ek1 = ek2;
-        lc[nrot] = c;
-        ls[nrot] = s;
-        nrot++;
+        *pc++ = c;
+        *ps++ = s;
+    }
+    const int nrot = k - start;
+    if (nrot > 0)
+    {
+        // running entries after the last rotation (k - 1): T(k, k-1) = nek, T(k, k) = ndk1, T(k+1, k) = c * ek1 when it exists
+        subdiag[k - 1] = ekm1;
+        diag[k] = dk;
+        if (k < end)
+            subdiag[k] = ek;
     }
     return nrot;
 }
@@ -216,13 +226,15 @@ __device__ int tridiag_eigen_block(const double* hd, const double* he, int m, Tr
     }
     __syncthreads();
 
-    // loop state lives in registers of thread 0; the other threads follow s_state
+    // Warp 0 runs the iteration: the deflation tests and the searches for the active block are spread over its lanes (votes), lane 0
+    // generates the rotations; the loop state (start, end, iter, log fill) is kept identically in every lane.  The other warps follow s_state.
     int end = m - 1, start = 0, iter = 0;
     const double considerAsZero = kMin;
     const double precision_inv = 1.0 / kEps;
+    const int lane = tid & 31;
     while (true)
     {
-        if (tid == 0)
+        if (tid < 32)
         {
             int nlog = 0, nsw = 0, more = 0;
             while (end > 0)
@@ -232,7 +244,8 @@ __device__ int tridiag_eigen_block(const double* hd, const double* he, int m, Tr
                     more = 1;  // log full: replay, then continue
                     break;
                 }
-                for (int i = start; i < end; i++)
+                // deflation tests on the active block (TridiagEigen.h:165-178), one entry per lane
+                for (int i = start + lane; i < end; i += 32)
                 {
                     const double ei = sh.e[i];
                     if (fabs(ei) <= considerAsZero)
@@ -244,31 +257,69 @@ __device__ int tridiag_eigen_block(const double* hd, const double* he, int m, Tr
                             sh.e[i] = 0.0;
                     }
                 }
-                while (end > 0 && sh.e[end - 1] == 0.0)
-                    end--;
+                __syncwarp();
+                // while (end > 0 && e[end-1] == 0) end--;   -> end = 1 + (largest j < end with e[j] != 0), or 0
+                {
+                    int ne = 0;
+                    for (int base = ((end - 1) >> 5) << 5; base >= 0; base -= 32)
+                    {
+                        const int j = base + lane;
+                        const unsigned nz = __ballot_sync(0xffffffffu, j < end && sh.e[j] != 0.0);
+                        if (nz)
+                        {
+                            ne = base + 32 - __clz((int) nz);
+                            break;
+                        }
+                    }
+                    end = ne;
+                }
                 if (end <= 0)
                     break;
                 iter++;
                 if (iter > 30 * m)
                 {
-                    s_state[3] = 1;
+                    if (lane == 0)
+                        s_state[3] = 1;
                     break;
                 }
-                start = end - 1;
-                while (start > 0 && sh.e[start - 1] != 0.0)
-                    start--;
-                const int nrot = tridiagonal_qr_step(sh.d, sh.e, start, end, sh.lc + nlog, sh.ls + nlog);
+                // start = end - 1; while (start > 0 && e[start-1] != 0) start--;   -> start = 1 + (largest j <= end-2 with e[j] == 0), or 0
+                {
+                    int ns = 0;
+                    for (int base = ((end - 1) >> 5) << 5; base >= 0; base -= 32)
+                    {
+                        const int j = base + lane;
+                        const unsigned zr = __ballot_sync(0xffffffffu, j <= end - 2 && sh.e[j] == 0.0);
+                        if (zr)
+                        {
+                            ns = base + 32 - __clz((int) zr);
+                            break;
+                        }
+                    }
+                    start = ns;
+                }
+                int nrot = 0;
+                if (lane == 0)
+                {
+                    nrot = tridiagonal_qr_step(sh.d, sh.e, start, end, m, sh.lc + nlog, sh.ls + nlog);
+                    if (nrot > 0)
+                    {
+                        sh.hdr[3 * nsw] = start;
+                        sh.hdr[3 * nsw + 1] = nrot;
+                        sh.hdr[3 * nsw + 2] = nlog;
+                    }
+                }
+                nrot = __shfl_sync(0xffffffffu, nrot, 0);  // also orders lane 0's shared-memory writes before the next tests
                 if (nrot > 0)
                 {
-                    sh.hdr[3 * nsw] = start;
-                    sh.hdr[3 * nsw + 1] = nrot;
-                    sh.hdr[3 * nsw + 2] = nlog;
                     nsw++;
                     nlog += nrot;
                 }
             }
-            s_state[0] = more;
-            s_state[1] = nsw;
+            if (lane == 0)
+            {
+                s_state[0] = more;
+                s_state[1] = nsw;
+            }
         }
         __syncthreads();
         replay_sweeps(sh.Z, m, sh.lc, sh.ls, sh.hdr, s_state[1]);

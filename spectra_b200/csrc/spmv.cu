@@ -207,7 +207,7 @@ constexpr int sell_min_blocks(int threads) { return 1536 / threads; }  // 48 res
 // Row sums of window `win` into s_y (natural row order inside the window).  The slices of a window are sorted by length (longest
 // first); warp w takes them in serpentine order -- w, 2 WARPS - 1 - w, 2 WARPS + w, ... -- so that every warp of the CTA gets about
 // the same number of steps before the barrier (w, w + WARPS, ... would give warp 0 the longest slice of every group).
-template <int THREADS>
+template <int THREADS, int UN = 4>
 __device__ __forceinline__ void sell_window_dot(const int* __restrict__ slice_ptr, const int* __restrict__ scol, const double* __restrict__ sval,
                                                 const unsigned short* __restrict__ perm, const double* __restrict__ x, int64_t win, double* s_y,
                                                 uint64_t pol_stream, uint64_t pol_keep)
@@ -227,25 +227,23 @@ __device__ __forceinline__ void sell_window_dot(const int* __restrict__ slice_pt
         const double* vp = sval + base + lane;
         double acc = 0.0;
         int t = 0;
-        // four steps (= four independent gathers per lane) in flight; padding carries col -1 / val 0
-        for (; t + 4 <= steps; t += 4)
+        // UN steps (= UN independent gathers per lane) in flight; padding carries col -1 / val 0
+        for (; t + UN <= steps; t += UN)
         {
-            const int c0 = ld_stream_s32(cp + (t + 0) * 32, pol_stream);
-            const int c1 = ld_stream_s32(cp + (t + 1) * 32, pol_stream);
-            const int c2 = ld_stream_s32(cp + (t + 2) * 32, pol_stream);
-            const int c3 = ld_stream_s32(cp + (t + 3) * 32, pol_stream);
-            const double v0 = ld_stream_f64(vp + (t + 0) * 32, pol_stream);
-            const double v1 = ld_stream_f64(vp + (t + 1) * 32, pol_stream);
-            const double v2 = ld_stream_f64(vp + (t + 2) * 32, pol_stream);
-            const double v3 = ld_stream_f64(vp + (t + 3) * 32, pol_stream);
-            const double x0 = (c0 >= 0) ? ld_keep_f64(x + c0, pol_keep) : 0.0;
-            const double x1 = (c1 >= 0) ? ld_keep_f64(x + c1, pol_keep) : 0.0;
-            const double x2 = (c2 >= 0) ? ld_keep_f64(x + c2, pol_keep) : 0.0;
-            const double x3 = (c3 >= 0) ? ld_keep_f64(x + c3, pol_keep) : 0.0;
-            acc = fma(v0, x0, acc);
-            acc = fma(v1, x1, acc);
-            acc = fma(v2, x2, acc);
-            acc = fma(v3, x3, acc);
+            int c[UN];
+            double v[UN], xv[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++)
+                c[u] = ld_stream_s32(cp + (t + u) * 32, pol_stream);
+#pragma unroll
+            for (int u = 0; u < UN; u++)
+                v[u] = ld_stream_f64(vp + (t + u) * 32, pol_stream);
+#pragma unroll
+            for (int u = 0; u < UN; u++)
+                xv[u] = (c[u] >= 0) ? ld_keep_f64(x + c[u], pol_keep) : 0.0;
+#pragma unroll
+            for (int u = 0; u < UN; u++)
+                acc = fma(v[u], xv[u], acc);
         }
         for (; t < steps; t++)
         {
@@ -382,37 +380,24 @@ __global__ void __launch_bounds__(THREADS, sell_min_blocks(THREADS))
 // Reduction: warp shuffle tree, fixed order inside the CTA, grid_reduce_fixed_order across CTAs (bit-reproducible).
 // Output: red[0..i] = V[:, :i+1]^T w.  Algorithmic bytes: those of the SpMV block + 24 B/row (step head) + 8 * nrows * i (V).
 // ---------------------------------------------------------------------------------------------
-constexpr int kFusedThreads = 512;
-constexpr int kFusedWarps = kFusedThreads / 32;
-constexpr int kFusedColsPerWarp = kPanelMaxCols / kFusedWarps;  // 4
-constexpr int kFusedTaskRows = 256;                             // rows per staged task (2 KB)
-constexpr int kFusedSlots = 3;                                  // ring depth per warp
-constexpr int kFusedQuarters = kSellWindow / kFusedTaskRows;    // 4 tasks per column and window
-constexpr size_t kFusedRingBytes = (size_t) kFusedWarps * kFusedSlots * kFusedTaskRows * sizeof(double);  // 96 KB
-// How phase C brings the V tile in (A/B knob SB200_FUSED_IMPL; the default is the measured best):
-//   FUSED_REG   plain 128-bit loads into registers, two batches of four per task -- no staging, but the bytes in flight are bounded by
-//               the 64 registers a thread may use at two 512-thread CTAs per SM;
-//   FUSED_TMA   one 1-D bulk copy (cp.async.bulk + mbarrier complete_tx) per 2 KB task, issued by one lane into the warp's ring;
-//   FUSED_CPA   16-byte cp.async (LDGSTS) copies, four per lane and task, into the same ring; a lane consumes exactly what it copied,
-//               so the ring is a per-lane FIFO that needs no barrier, only cp.async.wait_group.
-enum FusedImpl
-{
-    FUSED_REG = 0,
-    FUSED_TMA = 1,
-    FUSED_CPA = 2
-};
-
-template <bool SYM, bool ACCUM, int IMPL>
-__global__ void __launch_bounds__(kFusedThreads, 2)
+// Configurations of the fused kernel (A/B knob SB200_FUSED_CFG = "<threads>x<NB>[u<UN>]"; two CTAs are resident per SM in every one):
+//   THREADS  CTA size: 512 threads at <= 64 registers, or 256 threads at <= 128 registers;
+//   NB       16-byte loads of V in flight per lane in phase C (the bytes in flight per SM are 2 CTAs x THREADS x NB x 16 B: 64 KB at
+//            512x4, 128 KB at 256x16 -- what a pure register pipeline can afford; rings in shared memory fed by cp.async.bulk (TMA) or
+//            cp.async were measured and are SLOWER: 96 KB of ring per CTA leave the L1 ~10 KB, which throttles the gather phase
+//            (357 vs 477 SpMV-iters/s at n = 1e7, profiles/r2d_quick_*_n1e7.log));
+//   UN       row-sum steps (gathers per lane) in flight in phase A.
+template <bool SYM, bool ACCUM, int THREADS, int NB, int UN>
+__global__ void __launch_bounds__(THREADS, 2)
     sell_step_dot_kernel(const int* __restrict__ slice_ptr, const int* __restrict__ scol, const double* __restrict__ sval, const unsigned short* __restrict__ perm,
                          const double* __restrict__ x_full, const double* __restrict__ f_loc, double* V, int64_t ldv, double* w, int64_t nrows, int64_t nwin,
                          FacCtl* ctl, double* H, int m, int i, int restarted, double* red_out, double* partials, unsigned int* ticket)
 {
-    constexpr int THREADS = kFusedThreads, WARPS = kFusedWarps;
-    extern __shared__ __align__(128) unsigned char fused_smem_raw[];
-    double* ring = reinterpret_cast<double*>(fused_smem_raw);  // [WARPS][kFusedSlots][kFusedTaskRows]   (FUSED_TMA / FUSED_CPA)
+    constexpr int WARPS = THREADS / 32;
+    constexpr int CPW = kPanelMaxCols / WARPS;      // owned columns per warp (4 or 8)
+    constexpr int LPC = kSellWindow / 64;           // 16-byte loads per lane and column of a window (16)
+    static_assert(LPC % NB == 0, "NB must divide 16");
     __shared__ __align__(16) double s_y[kSellWindow];
-    __shared__ __align__(8) uint64_t s_bar[WARPS * kFusedSlots];
     __shared__ double s_col[kPanelMaxCols];
     __shared__ double s_w[WARPS];
     __shared__ double s_alpha;
@@ -425,75 +410,19 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
     const double hsub = restarted ? 0.0 : beta;
     double* vi = V + (int64_t) i * ldv;
     const double* vp = V + (int64_t) (i - 1) * ldv;
+    const int ncols_mine = (i > warp) ? (i - warp + WARPS - 1) / WARPS : 0;  // columns warp, warp + WARPS, ... below i
 
-    if (IMPL == FUSED_TMA)
-    {
-        // the ring starts zeroed (rows past the end of a column are never copied and must not read as NaN), barriers armed for one arrival
-        for (int t = threadIdx.x; t < (int) (kFusedRingBytes / sizeof(double)); t += THREADS)
-            ring[t] = 0.0;
-        if (threadIdx.x < WARPS * kFusedSlots)
-            mbar_init(&s_bar[threadIdx.x], 1);
-        if (threadIdx.x == 0)
-            mbar_init_fence();
-        fence_proxy_async_smem();
-        __syncthreads();
-    }
-
-    const int ncols_mine = (i > warp) ? (i - warp + WARPS - 1) / WARPS : 0;  // columns warp, warp + 16, ... below i
-    const int ntask = ncols_mine * kFusedQuarters;
-    double* my_ring = ring + (size_t) warp * kFusedSlots * kFusedTaskRows;
-    uint64_t* my_bar = s_bar + warp * kFusedSlots;
-    uint32_t issued = 0, consumed = 0;  // monotone over the whole kernel: slot = count % kFusedSlots, parity = (count / kFusedSlots) & 1
-
-    double acc[kFusedColsPerWarp];
+    double acc[CPW];
 #pragma unroll
-    for (int q = 0; q < kFusedColsPerWarp; q++)
+    for (int q = 0; q < CPW; q++)
         acc[q] = 0.0;
     double part = 0.0;
 
     for (int64_t win = blockIdx.x; win < nwin; win += gridDim.x)
     {
         const int64_t wrow0 = win * kSellWindow;
-        // task u of this window: column warp + 16 (u / 4), rows [wrow0 + 256 (u % 4), +256) clipped to the allocated ldv rows
-        auto issue_task = [&](int u) {
-            const int64_t r0 = wrow0 + (int64_t) (u % kFusedQuarters) * kFusedTaskRows;
-            const double* colp = V + (int64_t) (warp + WARPS * (u / kFusedQuarters)) * ldv;
-            const int slot = (int) (issued % kFusedSlots);
-            if (IMPL == FUSED_TMA)
-            {
-                const int64_t avail = ldv - r0;
-                const uint32_t bytes = (uint32_t) (avail >= kFusedTaskRows ? kFusedTaskRows : (avail > 0 ? avail : 0)) * (uint32_t) sizeof(double);
-                if (lane == 0)
-                {
-                    mbar_expect_tx(&my_bar[slot], bytes);
-                    if (bytes > 0)
-                        tma_load_1d_hint(my_ring + (size_t) slot * kFusedTaskRows, colp + r0, bytes, &my_bar[slot], pol_stream);
-                }
-            }
-            else
-            {
-                double* dst = my_ring + (size_t) slot * kFusedTaskRows + lane * 2;
-#pragma unroll
-                for (int q = 0; q < kFusedTaskRows / 64; q++)
-                {
-                    const int64_t r = r0 + q * 64 + lane * 2;
-                    const bool ok = r < ldv;
-                    cp_async_16(dst + q * 64, colp + (ok ? r : 0), ok, pol_stream);
-                }
-                cp_async_commit();
-            }
-            issued++;
-        };
-        int next = 0;
-        if (IMPL != FUSED_REG)
-        {
-            // the first tasks of the window travel while the CTA gathers (they only read columns < i, which this kernel never writes)
-            for (; next < ntask && next < kFusedSlots; next++)
-                issue_task(next);
-        }
-
         // ---- phase A: row sums of the window (gather bound) ----
-        sell_window_dot<THREADS>(slice_ptr, scol, sval, perm, x_full, win, s_y, pol_stream, pol_keep);
+        sell_window_dot<THREADS, UN>(slice_ptr, scol, sval, perm, x_full, win, s_y, pol_stream, pol_keep);
         __syncthreads();
         // ---- phase B: step head on natural-order rows; the finished w values replace the row sums in shared memory ----
         for (int r = threadIdx.x; r < kSellWindow; r += THREADS)
@@ -517,64 +446,32 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
         }
         __syncthreads();
         // ---- phase C: c_k += V[window rows, k]^T w for the owned columns k < i (HBM stream) ----
-        for (int u = 0; u < ntask; u++)
+        const double2* wsm = reinterpret_cast<const double2*>(s_y) + lane;
+        const int64_t rlane = wrow0 + lane * 2;
+#pragma unroll
+        for (int cl = 0; cl < CPW; cl++)
         {
-            const double2* ws = reinterpret_cast<const double2*>(s_y + (u % kFusedQuarters) * kFusedTaskRows) + lane;
-            double sacc = 0.0;
-            if (IMPL == FUSED_REG)
+            if (cl < ncols_mine)
             {
-                const int64_t r0 = wrow0 + (int64_t) (u % kFusedQuarters) * kFusedTaskRows + lane * 2;
-                const double* colp = V + (int64_t) (warp + WARPS * (u / kFusedQuarters)) * ldv + r0;
-                double2 a[kFusedTaskRows / 64];
+                const double* colp = V + (int64_t) (warp + WARPS * cl) * ldv + rlane;
+                double sacc = 0.0;
 #pragma unroll
-                for (int q = 0; q < kFusedTaskRows / 64; q++)
-                    a[q] = (r0 + q * 64 < ldv) ? ld_stream_f64x2(colp + q * 64, pol_stream) : make_double2(0.0, 0.0);
-#pragma unroll
-                for (int q = 0; q < kFusedTaskRows / 64; q++)
+                for (int b = 0; b < LPC; b += NB)
                 {
-                    const double2 ww = ws[q * 32];
-                    sacc = fma(a[q].x, ww.x, sacc);
-                    sacc = fma(a[q].y, ww.y, sacc);
+                    double2 a[NB];
+#pragma unroll
+                    for (int u = 0; u < NB; u++)
+                        a[u] = (rlane + (b + u) * 64 < ldv) ? ld_stream_f64x2(colp + (b + u) * 64, pol_stream) : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int u = 0; u < NB; u++)
+                    {
+                        const double2 ww = wsm[(b + u) * 32];
+                        sacc = fma(a[u].x, ww.x, sacc);
+                        sacc = fma(a[u].y, ww.y, sacc);
+                    }
                 }
+                acc[cl] += sacc;
             }
-            else
-            {
-                const int slot = (int) (consumed % kFusedSlots);
-                if (IMPL == FUSED_TMA)
-                    mbar_wait(&my_bar[slot], (consumed / kFusedSlots) & 1u);
-                else
-                {
-                    // this lane's copies of task u have landed once at most (tasks still in flight behind it) groups are pending
-                    const int behind = next - u - 1;
-                    if (behind >= 2)
-                        cp_async_wait<2>();
-                    else if (behind == 1)
-                        cp_async_wait<1>();
-                    else
-                        cp_async_wait<0>();
-                }
-                consumed++;
-                const double2* vs = reinterpret_cast<const double2*>(my_ring + (size_t) slot * kFusedTaskRows) + lane;
-#pragma unroll
-                for (int q = 0; q < kFusedTaskRows / 64; q++)
-                {
-                    const double2 a = vs[q * 32], ww = ws[q * 32];
-                    sacc = fma(a.x, ww.x, sacc);
-                    sacc = fma(a.y, ww.y, sacc);
-                }
-                if (IMPL == FUSED_TMA)
-                    __syncwarp();  // every lane has read the slot before one lane refills it
-                if (next < ntask)
-                {
-                    issue_task(next);
-                    next++;
-                }
-            }
-            const int cl = u / kFusedQuarters;
-#pragma unroll
-            for (int q = 0; q < kFusedColsPerWarp; q++)
-                if (q == cl)
-                    acc[q] += sacc;
         }
         __syncthreads();  // s_y is overwritten by the next window
     }
@@ -595,7 +492,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
 
     // ---- CTA-level combine in a fixed order ----
 #pragma unroll
-    for (int q = 0; q < kFusedColsPerWarp; q++)
+    for (int q = 0; q < CPW; q++)
     {
         const double sum = warp_sum(acc[q]);
         if (lane == 0)
@@ -757,25 +654,13 @@ void launch_sell_step_t(const SellBlock& S, int grid, int64_t nrows, const doubl
 #undef SB200_SELL_STEP
 }
 
-template <int IMPL>
+template <int THREADS, int NB, int UN>
 void launch_sell_step_dot_t(const SellBlock& S, int grid, int64_t nrows, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
                             double* H, int m, int i, int restarted, bool symmetric, bool accum, double* red_out, const RedScratch& rs, cudaStream_t stream)
 {
-    constexpr size_t smem = (IMPL == FUSED_REG) ? 0 : kFusedRingBytes;
-    static const bool attr_set = [] {
-        if (smem > 0)
-        {
-            SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<true, true, IMPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<true, false, IMPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<false, true, IMPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            SB200_CUDA_CHECK(cudaFuncSetAttribute(sell_step_dot_kernel<false, false, IMPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        }
-        return true;
-    }();
-    (void) attr_set;
 #define SB200_SELL_STEP_DOT(SYM, ACC)                                                                                                                          \
-    sell_step_dot_kernel<SYM, ACC, IMPL><<<grid, kFusedThreads, smem, stream>>>(S.slice_ptr.get(), S.col.get(), S.val.get(), S.perm.get(), x_full, f_loc, V, ldv, w, \
-                                                                                nrows, S.nwin, ctl, H, m, i, restarted, red_out, rs.partials, rs.ticket)
+    sell_step_dot_kernel<SYM, ACC, THREADS, NB, UN><<<grid, THREADS, 0, stream>>>(S.slice_ptr.get(), S.col.get(), S.val.get(), S.perm.get(), x_full, f_loc, V, ldv, w, \
+                                                                                  nrows, S.nwin, ctl, H, m, i, restarted, red_out, rs.partials, rs.ticket)
     if (symmetric && accum)
         SB200_SELL_STEP_DOT(true, true);
     else if (symmetric)
@@ -787,25 +672,39 @@ void launch_sell_step_dot_t(const SellBlock& S, int grid, int64_t nrows, const d
 #undef SB200_SELL_STEP_DOT
 }
 
+// 0: 512 threads x 4 loads (default), 1: 512x8, 2: 256x8, 3: 256x16, 4: 256x16 with 8 gathers in flight
+int fused_config()
+{
+    static const int cfg = [] {
+        const char* e = std::getenv("SB200_FUSED_CFG");
+        if (!e)
+            return 0;
+        if (std::strcmp(e, "512x8") == 0)
+            return 1;
+        if (std::strcmp(e, "256x8") == 0)
+            return 2;
+        if (std::strcmp(e, "256x16") == 0)
+            return 3;
+        if (std::strcmp(e, "256x16u8") == 0)
+            return 4;
+        return 0;
+    }();
+    return cfg;
+}
+
 void launch_sell_step_dot(const SellBlock& S, int grid, int64_t nrows, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
                           double* H, int m, int i, int restarted, bool symmetric, bool accum, double* red_out, const RedScratch& rs, cudaStream_t stream)
 {
-    static const int impl = [] {
-        const char* e = std::getenv("SB200_FUSED_IMPL");
-        if (e && std::strcmp(e, "reg") == 0)
-            return (int) FUSED_REG;
-        if (e && std::strcmp(e, "tma") == 0)
-            return (int) FUSED_TMA;
-        if (e && std::strcmp(e, "cpasync") == 0)
-            return (int) FUSED_CPA;
-        return (int) FUSED_REG;  // measured (profiles/r2b_quick_fused_n1e7.log): 1.44 ms per operator step vs 1.64 ms unfused; TMA ring 2.09 ms
-    }();
-    switch (impl)
+#define SB200_FUSED_ARGS S, grid, nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, red_out, rs, stream
+    switch (fused_config())
     {
-        case FUSED_REG: launch_sell_step_dot_t<FUSED_REG>(S, grid, nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, red_out, rs, stream); break;
-        case FUSED_TMA: launch_sell_step_dot_t<FUSED_TMA>(S, grid, nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, red_out, rs, stream); break;
-        default: launch_sell_step_dot_t<FUSED_CPA>(S, grid, nrows, x_full, f_loc, V, ldv, w, ctl, H, m, i, restarted, symmetric, accum, red_out, rs, stream); break;
+        case 1: launch_sell_step_dot_t<512, 8, 4>(SB200_FUSED_ARGS); break;
+        case 2: launch_sell_step_dot_t<256, 8, 4>(SB200_FUSED_ARGS); break;
+        case 3: launch_sell_step_dot_t<256, 16, 4>(SB200_FUSED_ARGS); break;
+        case 4: launch_sell_step_dot_t<256, 16, 8>(SB200_FUSED_ARGS); break;
+        default: launch_sell_step_dot_t<512, 4, 4>(SB200_FUSED_ARGS); break;
     }
+#undef SB200_FUSED_ARGS
 }
 
 template <int L>

@@ -367,6 +367,18 @@ inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)
     const int base = lane & ~(width - 1);
     return ::emu::shfl_from<T>(mask, v, base + (src & (width - 1)));
 }
+// warp vote: every participating lane deposits its predicate; the result is assembled from the collective's buffer
+inline unsigned __ballot_sync(unsigned mask, int pred)
+{
+    const int my = ::emu::warp_collective(mask, pred ? 1u : 0u);
+    const ::emu::Warp& w = ::emu::g.warps[(size_t) ::emu::g.cur / 32];
+    unsigned r = 0;
+    for (int l = 0; l < 32; l++)
+        if (((mask & w.live) >> l) & 1u)
+            r |= (w.buf[my & 1][l] ? 1u : 0u) << l;
+    return r;
+}
+inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned) x); }
 template <typename T>
 inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask, int width = 32)
 {
