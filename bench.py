@@ -280,6 +280,8 @@ def main():
 
     # =========================== value arm: operator resident in HBM ===========================
     op = make_op()
+    comm_mode = "single GPU" if world == 1 else ("peer memory over NVLink (IPC windows, one-shot all-reduce, residual pushed by the correction pass)"
+                                                  if op.peer_mode() else "NCCL all-gather + all-reduce")
     eigs = sb.SymEigsSolver(op, args.nev, args.ncv)
     sampler = None
     step_ms, step_wall, launches = [], [], 0
@@ -452,7 +454,7 @@ def main():
             "converged": bool(info_ok), "accuracy": {"max_rel_residual": float(np.max(rel_res)), "bound": 1e-10},
             "wall_ms_per_step": wall_per_step, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kern, "cpu_baseline": cpu,
             "clocks": clocks, "algo_counters": {k: last_stats[k] for k in ("lanczos_steps", "reorth_passes", "restarts", "expand_calls", "host_syncs", "fused_dot_launches")},
-            "device": info, "nnz": nnz_total, "gen_seconds": gen_s, "configs": configs,
+            "device": info, "nnz": nnz_total, "gen_seconds": gen_s, "configs": configs, "comm_mode": comm_mode,
         }
         print(json.dumps(line), flush=True)
 

@@ -672,12 +672,16 @@ void launch_sell_step_dot_t(const SellBlock& S, int grid, int64_t nrows, const d
 #undef SB200_SELL_STEP_DOT
 }
 
-// 0: 512 threads x 4 loads (default), 1: 512x8, 2: 256x8, 3: 256x16, 4: 256x16 with 8 gathers in flight
+// 0: 512 threads x 4 loads, 1: 512x8 (default), 2: 256x8, 3: 256x16, 4: 256x16 with 8 gathers in flight.  Measured at n = 1e7 on the first 12
+// restarts (profiles/r2e_quick_*_n1e7.log): 486 / 505 / 439 / 457 / 453 SpMV-iters/s -- the 256-thread CTAs lose more in the gather phase than
+// their deeper V pipeline wins.
 int fused_config()
 {
     static const int cfg = [] {
         const char* e = std::getenv("SB200_FUSED_CFG");
         if (!e)
+            return 1;
+        if (std::strcmp(e, "512x4") == 0)
             return 0;
         if (std::strcmp(e, "512x8") == 0)
             return 1;
