@@ -374,17 +374,18 @@ def main():
             roofs = {"error": f"{type(e).__name__}: {e}"}
     # DRAM traffic per launch from the committed `ncu --set full` capture of this same workload and device layout (profiles/traffic.json;
     # dram__bytes_read.sum + dram__bytes_write.sum, summed over the column-block kernels of one operator application)
-    traffic, traffic_src = None, None
+    traffic, traffic_src, traffic_ctx = None, None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             tj = json.load(fh)
         ent = tj.get(dominant)
         if ent and int(ent["n"]) == n and int(ent.get("n_gpus", 1)) == world and ent.get("layout") == kern["operator_step"]["layout"]["format"]:
             traffic, traffic_src = float(ent["dram_bytes_per_launch"]), ent.get("source")
+            traffic_ctx = {"captured_at_panel_width": ent.get("captured_at_panel_width"), "algorithmic_bytes_at_that_width": ent.get("algorithmic_bytes_at_that_width")}
     except (OSError, ValueError, KeyError):
         pass
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": kern[dominant]["gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": kern[dominant]["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "frac": kern[dominant]["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src, "traffic_context": traffic_ctx,
                 "algorithmic_bytes_per_launch": kern[dominant]["algorithmic_bytes_per_launch"],
                 "spmv_plain_frac": kern["spmv_plain"]["frac_of_hbm_peak"], "gather_roofs": roofs,
                 "share_of_step": {"panel_pass": ps["ms_panel"] / ps["ms_total"], "operator_step": ps["ms_spmv"] / ps["ms_total"]}}

@@ -68,6 +68,12 @@ struct FacBase
     int nev = 0, m = 0;
 
     DevBuf<double> V, f, w, t0, H, Q, S, X;
+    // w of the step being built: `w`, or -- when a sweep overlaps the tail of a correction pass with the first operator kernels of the
+    // next step (solver_sym.cu, factorize_from) -- alternately `w` and `w_alt`
+    DevBuf<double> w_alt;
+    double* wp = nullptr;
+    cudaStream_t aux_stream = nullptr;                 // carries the speculatively launched operator kernels of the next step
+    cudaEvent_t ev_part_a = nullptr, ev_k0 = nullptr;  // first part of the residual final / those kernels done
     DevBuf<double> Hi;        // complex Arnoldi only: imaginary parts of the Hessenberg matrix (H holds the real parts)
     bool complex_h = false;   // keep the imaginary parts of the projected matrix (general complex operator; Hermitian ones drop them)
     DevBuf<FacCtl> ctl;
@@ -100,6 +106,65 @@ struct FacBase
         return off;
     }
     void clear_abort() { SB200_CUDA_CHECK(cudaMemsetAsync(&ctl.get()->abort, 0, sizeof(int), stream())); }
+    // Overlapped sweeps (sliced or CSR layout with >= 2 column blocks; one GPU in the natural layout, or peer mode): the correction pass
+    // runs in two row ranges, and as soon as the rows that the first column blocks of the NEXT operator application gather from are
+    // final, those (gather-bound) kernels start on a second stream next to the (HBM-bound) second range.  SB200_OVERLAP=0 disables it.
+    int num_blocks() const { return op->A.blocks.empty() ? 1 : (int) op->A.blocks.size(); }
+    bool overlap_capable() const
+    {
+        static const bool off = [] { const char* e = std::getenv("SB200_OVERLAP"); return e && e[0] == '0'; }();
+        if (off || !sweep_capable() || num_blocks() < 2)
+            return false;
+        return peer || (op->nranks() == 1 && op->A.chunk_len == 0);
+    }
+    // local rows [0, h) are what column blocks 0 .. nb-2 gather from (this rank's share of them in the chunk-major layout)
+    int64_t overlap_split_rows() const
+    {
+        const int64_t per = op->A.chunk_len ? op->A.chunk_len : op->A.col_block_width;
+        const int64_t h = std::min<int64_t>(nloc, per * (num_blocks() - 1));
+        return h & ~int64_t(1);
+    }
+    void ensure_overlap_resources()
+    {
+        if (!aux_stream)
+        {
+            SB200_CUDA_CHECK(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+            SB200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_part_a, cudaEventDisableTiming));
+            SB200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_k0, cudaEventDisableTiming));
+        }
+        if (w_alt.n < (size_t) ld)
+        {
+            w_alt.alloc((size_t) ld);
+            w_alt.zero(stream());
+        }
+    }
+    // column blocks 0 .. nb-2 of the operator application of step i (raw products accumulated into wdst) on stream st
+    void launch_head_blocks(int i, cudaStream_t st, double* wdst)
+    {
+        const DeviceCsr& A = op->A;
+        const int nb = num_blocks();
+        ScopedKernelTimer t(&prof, st, KC_SPMV, nb - 1);
+        for (int c = 0; c + 1 < nb; c++)
+        {
+            const double* xb = A.chunk_len ? op->xc + (int64_t) c * A.chunk_stride() : f.get();
+            launch_spmv_step_block(A, op->plan, c, xb, f.get(), V.get(), ld, wdst, ctl.get(), H.get(), m, i, 0, true, rs, st, nullptr);
+        }
+    }
+    // last column block of step i on the main stream: step head + (sliced layout) c = V^T w; returns whether the panel pass was fused
+    bool launch_last_block(int i, bool symmetric, double* wbuf)
+    {
+        const DeviceCsr& A = op->A;
+        const int nb = num_blocks();
+        const double* xb = A.chunk_len ? op->xc + (int64_t) (nb - 1) * A.chunk_stride() : f.get();
+        bool fused;
+        {
+            ScopedKernelTimer t(&prof, stream(), KC_SPMV);
+            fused = launch_spmv_step_block(A, op->plan, nb - 1, xb, f.get(), V.get(), ld, wbuf, ctl.get(), H.get(), m, i, 0, symmetric, rs, stream(), ctl.get()->red);
+        }
+        stats.spmv_launches++;
+        nmatop++;
+        return count_fused(fused, i);
+    }
 
     Profiler prof;
     sb200_stats stats;
@@ -114,6 +179,12 @@ struct FacBase
             cudaEventDestroy(ev_begin);
         if (ev_end)
             cudaEventDestroy(ev_end);
+        if (ev_part_a)
+            cudaEventDestroy(ev_part_a);
+        if (ev_k0)
+            cudaEventDestroy(ev_k0);
+        if (aux_stream)
+            cudaStreamDestroy(aux_stream);
     }
 
     void alloc_common(sb200_op* op_, int64_t nev_, int64_t m_)
@@ -132,6 +203,7 @@ struct FacBase
         V.alloc((size_t) ld * m);
         f.alloc((size_t) ld);
         w.alloc((size_t) ld);
+        wp = w.get();
         t0.alloc((size_t) std::max<int64_t>(ld, n));
         H.alloc((size_t) m * m);
         if (complex_h)
@@ -262,8 +334,8 @@ struct FacBase
             ScopedKernelTimer t(&prof, stream(), KC_SPMV, 2);
             double* vi = V.get() + (int64_t) i * ld;
             launch_step_scale(f.get(), ctl.get(), vi, nloc, stream());
-            op_spmv_device(op, vi, w.get());
-            launch_step_epilogue(w.get(), V.get(), ld, nloc, ctl.get(), H.get(), m, i, restarted ? 1 : 0, symmetric, rs, stream());
+            op_spmv_device(op, vi, wp);
+            launch_step_epilogue(wp, V.get(), ld, nloc, ctl.get(), H.get(), m, i, restarted ? 1 : 0, symmetric, rs, stream());
             stats.spmv_launches++;
             nmatop++;
             return false;
@@ -280,7 +352,7 @@ struct FacBase
             // single-GPU test layout (SB200_FORCE_CHUNK_RANKS): permute instead of gathering
             ScopedKernelTimer t(&prof, stream(), KC_SPMV, 1 + (int) op->A.blocks.size());
             launch_permute_to_chunks(op->A, f.get(), op->xc, stream());
-            const bool fused = launch_spmv_step(op->A, op->plan, op->xc, f.get(), V.get(), ld, w.get(), ctl.get(), H.get(), m, i, restarted ? 1 : 0,
+            const bool fused = launch_spmv_step(op->A, op->plan, op->xc, f.get(), V.get(), ld, wp, ctl.get(), H.get(), m, i, restarted ? 1 : 0,
                                                 symmetric, rs, stream(), dot_out);
             stats.spmv_launches++;
             nmatop++;
@@ -290,7 +362,7 @@ struct FacBase
         bool fused;
         {
             ScopedKernelTimer t(&prof, stream(), KC_SPMV);
-            fused = launch_spmv_step(op->A, op->plan, xfull, f.get(), V.get(), ld, w.get(), ctl.get(), H.get(), m, i, restarted ? 1 : 0, symmetric, rs, stream(),
+            fused = launch_spmv_step(op->A, op->plan, xfull, f.get(), V.get(), ld, wp, ctl.get(), H.get(), m, i, restarted ? 1 : 0, symmetric, rs, stream(),
                                      dot_out);
         }
         stats.spmv_launches++;
@@ -313,7 +385,7 @@ struct FacBase
         if (spmv_step(i, restarted, symmetric, !is_cplx()))
             allreduce_sum(ctl.get()->red, (size_t) j);
         else
-            panel(PANEL_DOT, j, w.get(), nullptr, nullptr);
+            panel(PANEL_DOT, j, wp, nullptr, nullptr);
     }
     // Sharded operator: the operand is all-gathered in chunks on the communication stream; the SpMV of column block c (the
     // columns that chunk c delivers) starts as soon as chunk c has landed, while chunk c+1 is still on the wire.
@@ -330,7 +402,7 @@ struct FacBase
             bool fused_p = false;
             ScopedKernelTimer t(&prof, stream(), KC_SPMV, nb);
             for (int c = 0; c < nb; c++)
-                fused_p = launch_spmv_step_block(A, op->plan, c, op->xc + (int64_t) c * stride, f.get(), V.get(), ld, w.get(), ctl.get(), H.get(), m, i,
+                fused_p = launch_spmv_step_block(A, op->plan, c, op->xc + (int64_t) c * stride, f.get(), V.get(), ld, wp, ctl.get(), H.get(), m, i,
                                                  restarted ? 1 : 0, symmetric, rs, stream(), dot_out);
             x_published = false;  // w / f move on; the next correction pass republishes
             return fused_p;
@@ -352,7 +424,7 @@ struct FacBase
                 SB200_CUDA_CHECK(cudaStreamWaitEvent(stream(), op->ev_chunk[(size_t) c], 0));
             }
             ScopedKernelTimer t(&prof, stream(), KC_SPMV);
-            fused = launch_spmv_step_block(A, op->plan, c, op->xc + (int64_t) c * stride, f.get(), V.get(), ld, w.get(), ctl.get(), H.get(), m, i,
+            fused = launch_spmv_step_block(A, op->plan, c, op->xc + (int64_t) c * stride, f.get(), V.get(), ld, wp, ctl.get(), H.get(), m, i,
                                            restarted ? 1 : 0, symmetric, rs, stream(), dot_out);
         }
         return fused;
@@ -369,6 +441,20 @@ struct FacBase
         allreduce_sum(ctl.get()->red, kRedNrm + 1);
         if (push && pred == nullptr)
             x_published = true;  // the all-reduce above is the barrier for the rows just written into the peers' operand buffers
+    }
+    // One row range [r0, r1) of the correction pass f = x - V c (real path): its partial V^T f and ||f||^2 go to red_out (all-reduced);
+    // r1 == nloc covers the zero padding rows up to ld as the full pass does.
+    void panel_corr_range(int j, const double* x, const double* coef, int64_t r0, int64_t r1, double* red_out)
+    {
+        const int64_t limit = (r1 >= nloc ? ld : r1) - r0;
+        PeerX pr = px;
+        pr.row0 = r0;
+        {
+            ScopedKernelTimer t(&prof, stream(), KC_PANEL);
+            launch_panel_pass(PANEL_CORR, V.get() + r0, ld, std::max<int64_t>(r1 - r0, 0), j, x + r0, f.get() + r0, coef, red_out, rs, stream(), nullptr, false,
+                              peer ? &pr : nullptr, abort_flag(), limit);
+        }
+        allreduce_sum(red_out, kRedNrm + 1);
     }
     // A speculatively enqueued pass turned out to be skipped on the device: undo its accounting.
     void uncount_panel(int j)
@@ -482,20 +568,20 @@ struct FacBase
             launch_vec_scale(v, vnorm, 1, v, nloc, stream());  // v /= ||v||
         prof.launches++;
         const double* vfull = gather_full(v);
-        spmv_plain(vfull, w.get());  // w = A * v
-        const double h00 = reduce_scalar(VR_DOT, v, w.get());
+        spmv_plain(vfull, wp);  // w = A * v
+        const double h00 = reduce_scalar(VR_DOT, v, wp);
         launch_set_scalar(H.get(), h00, stream());
         double h00_im = 0.0;
         if (complex_h)
         {
             // H(0,0) = v^H w is genuinely complex for a general complex operator (Arnoldi.h:176-177)
-            h00_im = reduce_scalar(VR_CDOT_IM, v, w.get());
+            h00_im = reduce_scalar(VR_CDOT_IM, v, wp);
             launch_set_scalar(Hi.get(), h00_im, stream());
-            launch_vec_caxpy(w.get(), v, h00, h00_im, f.get(), nloc, stream());
+            launch_vec_caxpy(wp, v, h00, h00_im, f.get(), nloc, stream());
             prof.launches++;
         }
         else
-            launch_vec_axpy(w.get(), v, h00, f.get(), nloc, stream());  // f = w - v * H(0,0)
+            launch_vec_axpy(wp, v, h00, f.get(), nloc, stream());  // f = w - v * H(0,0)
         prof.launches += 2;
         const double fmax = reduce_scalar(is_cplx() ? VR_CMAXABS : VR_MAXABS, f.get(), nullptr);  // m_fac_f.cwiseAbs().maxCoeff()
         if (fmax < kEps * std::hypot(h00, h00_im))

@@ -31,6 +31,7 @@ struct FacCtl
     double red_a[8];              // SpMV-epilogue reduction: [0] = <v_i, w>  (Lanczos.h:142)
     double c[kRedStride];         // coefficients applied by the next correction pass  (Vf, Lanczos.h:152)
     double red[kRedStride];       // output of the last panel reduction: [0..j) = V^T f, [kRedNrm] = ||f||^2
+    double red2[kRedStride];      // the same for the first row range of a correction pass run in two parts (added by the decide kernel)
 };
 constexpr size_t kFacCtlStatusBytes = 64;
 
@@ -200,6 +201,7 @@ struct PeerX
     int np;
     int rank;
     int64_t len, stride, rows;  // rows = chunk rows (len * number of chunks): rows at or beyond it have no destination
+    int64_t row0;               // local row of the first entry the kernel sees (row-range launches of the correction pass)
 };
 // x (all ranks) <- f_loc rows of this rank (cold paths: after init / restart / expand_basis; the hot path writes from the panel pass)
 void launch_peer_push(const PeerX& px, const double* f_loc, int64_t nrows_ld, cudaStream_t stream);
@@ -220,14 +222,17 @@ enum PanelMode
 // push (optional, CORR mode, real path): also write the new residual rows into every rank's SpMV operand buffer (peer memory).
 void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out,
                        const RedScratch& rs, cudaStream_t stream, const int* pred = nullptr, bool cplx = false, const PeerX* push = nullptr,
-                       const int* abort = nullptr);
+                       const int* abort = nullptr, int64_t row_limit = -1);
+// (row_limit: rows at or beyond it -- relative to the pointers passed -- are treated as absent; default ldv, i.e. the zero padding rows of a
+//  full-length pass are read like real ones.  Row-range launches pass V / x / f_out already offset and the length of their range.)
 
 // Decide kernels: consume ctl->red after a panel pass (and after the all-reduce when sharded).
 //  stage 0: after c = V^T w (fills H(i,i), H(i-1,i), the coefficients of the first pass f = w - V c); stage 1: after that pass;
 //  stage 2: after a further correction pass (also applies the H update of Lanczos.h:172-175 with the coefficients just used).
 //  sweep != 0 (stage 1 only): the step was enqueued without a host round trip; raise ctl->abort when the host has to take over.
+//  two_part != 0 (stage 1, real path): the pass ran in two row ranges; ctl->red2 is added to ctl->red first.
 void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated = 0, bool cplx = false,
-                           int sweep = 0);
+                           int sweep = 0, int two_part = 0);
 // Arnoldi flavours (Arnoldi.h:242-290): stage 0 = after h = V^T w (copies h into H(:,i) and c),
 // stage 1 = after f = w - V h (DGKS test), stage 2 = after a correction pass.
 // Hi != nullptr: complex Arnoldi (Hermitian-path layout of ctl->red / ctl->c); H receives the real and Hi the imaginary parts of H(:, i)

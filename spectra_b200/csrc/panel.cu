@@ -36,7 +36,7 @@ constexpr int kColsPerGroup = 16;
 template <int NG, int MODE, bool CPLX>
 __global__ void __launch_bounds__(kPanelBlock, 2)
     panel_kernel(const double* __restrict__ V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* __restrict__ coef,
-                 double* red_out, double* partials, unsigned int* ticket, const int* pred, const PeerX push, const int* abort)
+                 double* red_out, double* partials, unsigned int* ticket, const int* pred, const PeerX push, const int* abort, int64_t row_limit)
 {
     // speculatively enqueued pass: skip when the device-side flag says no correction is needed; sweep mode: skip after an abort
     if (pred != nullptr && *pred == 0)
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kPanelBlock, 2)
     for (int64_t base = (int64_t) blockIdx.x * RPI; base < nrows; base += (int64_t) gridDim.x * RPI)
     {
         const int64_t r0 = base + rs * 64 + lane * 2;
-        const bool valid = r0 < ldv;  // padding rows [nrows, ldv) hold zeros
+        const bool valid = r0 < row_limit;  // full pass: ldv (padding rows [nrows, ldv) hold zeros); row-range pass: the range length
         double2 v[CPG];
 #pragma unroll
         for (int kk = 0; kk < CPG; kk++)
@@ -138,12 +138,13 @@ __global__ void __launch_bounds__(kPanelBlock, 2)
         }
         if (MODE != PANEL_DOT && g == 0 && valid)
             *reinterpret_cast<double2*>(f_out + r0) = fn;
-        if (MODE == PANEL_CORR && !CPLX && push.np > 0 && g == 0 && r0 < push.rows)
+        if (MODE == PANEL_CORR && !CPLX && push.np > 0 && g == 0 && valid && r0 + push.row0 < push.rows)
         {
             // row-sharded runs: the new residual is the next SpMV operand of EVERY rank -- store this rank's rows straight into all
             // operand buffers (peer memory over NVLink, chunk-major layout) instead of all-gathering them afterwards
-            const int64_t c = r0 / push.len;
-            const int64_t dst = c * push.stride + (int64_t) push.rank * push.len + (r0 - c * push.len);
+            const int64_t rl = r0 + push.row0;  // local row
+            const int64_t c = rl / push.len;
+            const int64_t dst = c * push.stride + (int64_t) push.rank * push.len + (rl - c * push.len);
             for (int p = 0; p < push.np; p++)
                 st_peer_f64x2(push.dst[p] + dst, fn);
         }
@@ -220,14 +221,14 @@ __global__ void __launch_bounds__(kPanelBlock, 2)
 
 template <int MODE>
 void launch_panel_mode(const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out, int grid,
-                       const RedScratch& rs, const int* pred, cudaStream_t stream, const PeerX& push, const int* abort)
+                       const RedScratch& rs, const int* pred, cudaStream_t stream, const PeerX& push, const int* abort, int64_t row_limit)
 {
     if (j <= 16)
-        panel_kernel<1, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, push, abort);
+        panel_kernel<1, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, push, abort, row_limit);
     else if (j <= 32)
-        panel_kernel<2, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, push, abort);
+        panel_kernel<2, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, push, abort, row_limit);
     else
-        panel_kernel<4, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, push, abort);
+        panel_kernel<4, MODE, false><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, push, abort, row_limit);
 }
 
 // complex panel: 8 columns per group
@@ -237,13 +238,13 @@ void launch_panel_mode_z(const double* V, int64_t ldv, int64_t nrows, int j, con
 {
     const PeerX none{};
     if (j <= 8)
-        panel_kernel<1, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none, nullptr);
+        panel_kernel<1, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none, nullptr, ldv);
     else if (j <= 16)
-        panel_kernel<2, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none, nullptr);
+        panel_kernel<2, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none, nullptr, ldv);
     else if (j <= 32)
-        panel_kernel<4, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none, nullptr);
+        panel_kernel<4, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none, nullptr, ldv);
     else
-        panel_kernel<8, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none, nullptr);
+        panel_kernel<8, MODE, true><<<grid, kPanelBlock, 0, stream>>>(V, ldv, nrows, j, x, f_out, coef, red_out, rs.partials, rs.ticket, pred, none, nullptr, ldv);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -273,7 +274,7 @@ __device__ __forceinline__ double panel_max_abs(const double* red, int j, int la
 //            reference applies on all but a fraction of a percent of the steps -- done in one pass over V instead of two.
 //   stage 1, after that pass (red = V^T f, ||f||^2): count = 1, beta = ||f||, the test of Lanczos.h:156 on the new f.
 //   stage 2, after a further correction pass  f -= V c  (Lanczos.h:171-179): h += c with the coefficients just applied, count += 1, test.
-__global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, int predicated, int sweep)
+__global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, int predicated, int sweep, int two_part)
 {
     if (predicated && ctl->need_corr == 0)
         return;  // the speculative correction pass was skipped
@@ -295,6 +296,15 @@ __global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta
             ctl->need_corr = 1;
         }
         return;
+    }
+    if (two_part)
+    {
+        // the pass ran in two row ranges (first range -> red2, second -> red): their sum, in that order, is the result of the pass
+        for (int k = lane; k < j; k += 32)
+            ctl->red[k] = ctl->red2[k] + ctl->red[k];
+        if (lane == 0)
+            ctl->red[kRedNrm] = ctl->red2[kRedNrm] + ctl->red[kRedNrm];
+        __syncwarp();
     }
     int count = ctl->count;
     if (lane == 0 && stage == 2)
@@ -607,8 +617,10 @@ __global__ void __launch_bounds__(kGemmBlock)
 }  // namespace
 
 void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, int j, const double* x, double* f_out, const double* coef, double* red_out,
-                       const RedScratch& rs, cudaStream_t stream, const int* pred, bool cplx, const PeerX* push_or_null, const int* abort)
+                       const RedScratch& rs, cudaStream_t stream, const int* pred, bool cplx, const PeerX* push_or_null, const int* abort, int64_t row_limit)
 {
+    if (row_limit < 0)
+        row_limit = ldv;
     const PeerX none{};
     const PeerX& push = (push_or_null && mode == PANEL_CORR && !cplx) ? *push_or_null : none;
     SB200_REQUIRE(j >= 1 && j <= kPanelMaxCols, SB200_INVALID_ARGUMENT, "panel width must be in [1, 64]");
@@ -638,20 +650,20 @@ void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, in
     SB200_REQUIRE(grid <= rs.max_grid, SB200_LOGIC, "panel: reduction scratch too small");
     switch (mode)
     {
-        case PANEL_DOT: launch_panel_mode<PANEL_DOT>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream, none, abort); break;
-        case PANEL_FORM: launch_panel_mode<PANEL_FORM>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream, none, abort); break;
-        case PANEL_CORR: launch_panel_mode<PANEL_CORR>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream, push, abort); break;
+        case PANEL_DOT: launch_panel_mode<PANEL_DOT>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream, none, abort, row_limit); break;
+        case PANEL_FORM: launch_panel_mode<PANEL_FORM>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream, none, abort, row_limit); break;
+        case PANEL_CORR: launch_panel_mode<PANEL_CORR>(V, ldv, nrows, j, x, f_out, coef, red_out, grid, rs, pred, stream, push, abort, row_limit); break;
         default: throw Error(SB200_LOGIC, "bad panel mode");
     }
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated, bool cplx, int sweep)
+void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated, bool cplx, int sweep, int two_part)
 {
     if (cplx)
         lanczos_decide_z_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage, predicated);
     else
-        lanczos_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage, predicated, sweep);
+        lanczos_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage, predicated, sweep, two_part);
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -82,7 +82,7 @@ struct sb200_gen_solver : public FacBase
             step_dot(i, restart, false);
             launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 0, hi);
             // f = w - V h, beta, and V^T f for the DGKS test in the same pass  (:254-262)
-            panel(PANEL_CORR, j, w.get(), f.get(), ctl.get()->c);
+            panel(PANEL_CORR, j, wp, f.get(), ctl.get()->c);
             launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream(), 0, hi);
             prof.launches += 2;
             // correction passes (:266-290); the first one is enqueued speculatively (device-side predicate)

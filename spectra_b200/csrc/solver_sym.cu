@@ -109,16 +109,63 @@ struct sb200_sym_solver : public FacBase
             };
             std::vector<Snap> snap;
             in_sweep = true;
-            for (int s = i; s <= (int) to_m - 1; s++)
+            if (overlap_capable())
             {
-                snap.push_back({nmatop, stats, prof.launches});
-                stats.lanczos_steps++;
-                step_dot(s, false, true);
-                launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 0, false);
-                panel(PANEL_CORR, s + 1, w.get(), f.get(), ctl.get()->c);
-                launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream(), 0, false, 1);
-                prof.launches += 2;
-                stats.reorth_passes += 1;
+                // two-part correction pass; the head blocks of step s + 1 run on the second stream beside the second part of step s
+                ensure_overlap_resources();
+                const int64_t h = overlap_split_rows();
+                double* wother = (wp == w.get()) ? w_alt.get() : w.get();
+                if (peer && !x_published)
+                    publish_f();
+                launch_head_blocks(i, stream(), wp);
+                bool aux_used = false;
+                for (int s = i; s <= (int) to_m - 1; s++)
+                {
+                    snap.push_back({nmatop, stats, prof.launches});
+                    stats.lanczos_steps++;
+                    const int j = s + 1;
+                    if (s > i)
+                        SB200_CUDA_CHECK(cudaStreamWaitEvent(stream(), ev_k0, 0));  // head blocks of this step (second stream) are done
+                    if (launch_last_block(s, true, wp))
+                        allreduce_sum(ctl.get()->red, (size_t) j);
+                    else
+                        panel(PANEL_DOT, j, wp, nullptr, nullptr);
+                    launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 0, false);
+                    stats.panel_launches++;
+                    stats.panel_cols += j;
+                    panel_corr_range(j, wp, ctl.get()->c, 0, h, ctl.get()->red2);
+                    if (s < (int) to_m - 1)
+                    {
+                        SB200_CUDA_CHECK(cudaEventRecord(ev_part_a, stream()));
+                        SB200_CUDA_CHECK(cudaStreamWaitEvent(aux_stream, ev_part_a, 0));
+                        launch_head_blocks(s + 1, aux_stream, wother);
+                        SB200_CUDA_CHECK(cudaEventRecord(ev_k0, aux_stream));
+                        aux_used = true;
+                    }
+                    panel_corr_range(j, wp, ctl.get()->c, h, nloc, ctl.get()->red);
+                    launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream(), 0, false, 1, 1);
+                    prof.launches += 2;
+                    stats.reorth_passes += 1;
+                    std::swap(wp, wother);
+                }
+                if (aux_used)
+                    SB200_CUDA_CHECK(cudaStreamWaitEvent(stream(), ev_k0, 0));
+                if (peer)
+                    x_published = true;  // both parts of the last correction pass wrote this rank's rows into every operand buffer
+            }
+            else
+            {
+                for (int s = i; s <= (int) to_m - 1; s++)
+                {
+                    snap.push_back({nmatop, stats, prof.launches});
+                    stats.lanczos_steps++;
+                    step_dot(s, false, true);
+                    launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 0, false);
+                    panel(PANEL_CORR, s + 1, wp, f.get(), ctl.get()->c);
+                    launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream(), 0, false, 1);
+                    prof.launches += 2;
+                    stats.reorth_passes += 1;
+                }
             }
             in_sweep = false;
             const FacCtl* st = read_status();
@@ -166,7 +213,7 @@ struct sb200_sym_solver : public FacBase
             launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 0, is_cplx());
             // K-C: f = w - V c, beta = ||f||, Vf = V^T f in one pass (Lanczos.h:145-153 and the first correction :171-179, see
             // lanczos_decide_kernel); then the test of :156 on the device
-            panel(PANEL_CORR, j, w.get(), f.get(), ctl.get()->c);
+            panel(PANEL_CORR, j, wp, f.get(), ctl.get()->c);
             launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream(), 0, is_cplx());
             prof.launches += 2;
             finish_step(read_status(), j, beta_thresh);

@@ -786,7 +786,7 @@ int choose_col_blocks(int64_t n)
 {
     double slice_mb = 40.0;
     if (const char* e = std::getenv("SB200_XSLICE_MB"))
-        slice_mb = std::max(1.0, std::atof(e));
+        slice_mb = std::max(1e-3, std::atof(e));
     const double x_mb = 8.0 * double(n) / (1024.0 * 1024.0);
     const int nb = (int) std::ceil(x_mb / slice_mb);
     return std::max(1, std::min(nb, kMaxColBlocks));

@@ -117,6 +117,32 @@ def test_emu_herm_factorization(emu):
     HC.factorization_case(emu)
 
 
+
+
+@pytest.mark.parametrize("fmt", ["sell", "csr"])
+def test_emu_overlapped_sweep_column_blocks(emu, fmt):
+    # natural single-rank layout with several column blocks: the sweep runs the correction pass in two row ranges and starts the head
+    # blocks of the next operator application on a second stream in between (solver_sym.cu, overlap_capable); same history and
+    # eigenvalues as the plain sweep, as the per-step path and as the oracle
+    A = O.gen_sparse_data(2600, 0.004)
+    ref = O.sym_eigs(O.Csr.from_scipy(A, "lower"), 6, 20, O.LargestAlge)
+    out = {}
+    for name, kw in (("overlap", {}), ("plain_sweep", dict(SB200_OVERLAP=0)), ("per_step", dict(SB200_SWEEP=0))):
+        # the knobs are read once per process and cached, so the three variants are distinguished by the layout they are created with:
+        # 0.005 MB slices -> 4 column blocks (overlap eligible); one block otherwise
+        with X.env(SB200_SPMV_FORMAT=fmt, SB200_SELL_MAX_FILL=100, SB200_XSLICE_MB=0.005 if name == "overlap" else 1000):
+            op = emu.SparseSymMatProd(A)
+        assert op.spmv_layout()["col_blocks"] == (4 if name == "overlap" else 1)
+        e = emu.SymEigsSolver(op, 6, 20)
+        e.init()
+        assert e.compute(emu.SortRule.LargestAlge) == 6
+        out[name] = (e.eigenvalues(), e.num_operations(), e.num_iterations(), e.stats()["host_syncs"])
+    for name, (ev, nops, niter, syncs) in out.items():
+        assert nops == ref.nops and niter == ref.niter, name
+        assert np.abs(ev - ref.eigenvalues).max() <= 1e-10 * np.abs(ref.eigenvalues).max(), name
+    assert np.abs(out["overlap"][0] - out["plain_sweep"][0]).max() <= 1e-12 * np.abs(ref.eigenvalues).max()
+
+
 @pytest.mark.parametrize("selection", [O.LargestMagn, O.LargestAlge, O.SmallestAlge, O.BothEnds])
 @pytest.mark.parametrize("n", [10, 100])
 def test_emu_herm_solver(emu_order, n, selection):
