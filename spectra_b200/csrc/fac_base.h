@@ -106,14 +106,18 @@ struct FacBase
         return off;
     }
     void clear_abort() { SB200_CUDA_CHECK(cudaMemsetAsync(&ctl.get()->abort, 0, sizeof(int), stream())); }
-    // Overlapped sweeps (sliced or CSR layout with >= 2 column blocks; one GPU in the natural layout, or peer mode): the correction pass
+    // Overlapped sweeps (opt-in, SB200_OVERLAP=1; >= 2 column blocks; one GPU in the natural layout, or peer mode): the correction pass
     // runs in two row ranges, and as soon as the rows that the first column blocks of the NEXT operator application gather from are
-    // final, those (gather-bound) kernels start on a second stream next to the (HBM-bound) second range.  SB200_OVERLAP=0 disables it.
+    // final, those (gather-bound) kernels start on a second stream next to the (HBM-bound) second range.  Measured SLOWER than the plain
+    // sweep (438 vs 487 SpMV-iters/s at n = 1e7, profiles/r2g_quick_*overlap_n1e7.log): the two kernels do not share SMs (registers), so
+    // each runs on a subset of the SMs, and the gather kernel's bound is per SM (L1TEX wavefronts) -- unlike the fused operator kernel,
+    // whose two phases alternate inside every SM.  Kept as a tested code path, off by default.
     int num_blocks() const { return op->A.blocks.empty() ? 1 : (int) op->A.blocks.size(); }
     bool overlap_capable() const
     {
-        static const bool off = [] { const char* e = std::getenv("SB200_OVERLAP"); return e && e[0] == '0'; }();
-        if (off || !sweep_capable() || num_blocks() < 2)
+        const char* e = std::getenv("SB200_OVERLAP");  // read per sweep: a test knob, not a hot path
+        const bool on = e && e[0] == '1';
+        if (!on || !sweep_capable() || num_blocks() < 2)
             return false;
         return peer || (op->nranks() == 1 && op->A.chunk_len == 0);
     }

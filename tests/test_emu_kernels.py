@@ -123,19 +123,20 @@ def test_emu_herm_factorization(emu):
 def test_emu_overlapped_sweep_column_blocks(emu, fmt):
     # natural single-rank layout with several column blocks: the sweep runs the correction pass in two row ranges and starts the head
     # blocks of the next operator application on a second stream in between (solver_sym.cu, overlap_capable); same history and
-    # eigenvalues as the plain sweep, as the per-step path and as the oracle
+    # eigenvalues as the plain sweep and as the oracle
     A = O.gen_sparse_data(2600, 0.004)
     ref = O.sym_eigs(O.Csr.from_scipy(A, "lower"), 6, 20, O.LargestAlge)
     out = {}
-    for name, kw in (("overlap", {}), ("plain_sweep", dict(SB200_OVERLAP=0)), ("per_step", dict(SB200_SWEEP=0))):
-        # the knobs are read once per process and cached, so the three variants are distinguished by the layout they are created with:
-        # 0.005 MB slices -> 4 column blocks (overlap eligible); one block otherwise
+    for name in ("overlap", "plain_sweep"):
+        # the variants are distinguished by the layout the operator is created with: 0.005 MB slices -> 4 column blocks (overlapped sweep);
+        # one block -> plain sweep
         with X.env(SB200_SPMV_FORMAT=fmt, SB200_SELL_MAX_FILL=100, SB200_XSLICE_MB=0.005 if name == "overlap" else 1000):
             op = emu.SparseSymMatProd(A)
         assert op.spmv_layout()["col_blocks"] == (4 if name == "overlap" else 1)
         e = emu.SymEigsSolver(op, 6, 20)
         e.init()
-        assert e.compute(emu.SortRule.LargestAlge) == 6
+        with X.env(SB200_OVERLAP=1 if name == "overlap" else 0):
+            assert e.compute(emu.SortRule.LargestAlge) == 6
         out[name] = (e.eigenvalues(), e.num_operations(), e.num_iterations(), e.stats()["host_syncs"])
     for name, (ev, nops, niter, syncs) in out.items():
         assert nops == ref.nops and niter == ref.niter, name
@@ -288,6 +289,8 @@ def test_emu_row_sharded_sym_solver(emu, P, fmt, peer):
     # all-reduce, peer.cu); peer = 0: the NCCL-style collectives (all-gather + all-reduce), the fallback when peers cannot be mapped
     fmt_env = dict(SB200_SPMV_FORMAT="sell", SB200_SELL_MAX_FILL=100) if fmt == "sell" else dict(SB200_SPMV_FORMAT="csr")
     fmt_env["SB200_PEER"] = str(peer)
+    if P == 3 and peer:
+        fmt_env["SB200_OVERLAP"] = "1"  # the opt-in two-part correction pass / early head blocks, in peer mode
     res = _sharded_solve(emu, n, P, rp, ci, v, k, m, "sym", fmt_env)
     ref = O.sym_eigs(O.Csr.adopt(n, rp, ci, v), k, m, O.LargestAlge, want_vectors=False)
     for r, o in enumerate(res):
