@@ -344,7 +344,11 @@ struct ColMap
 {
     int chunked;
     int64_t W, slab, len;
-    __device__ __forceinline__ int block(int col) const { return chunked ? (int) (((int64_t) col % slab) / len) : (int) (col / W); }
+    int64_t W0 = 0;  // natural layout, two blocks of unequal width: columns below W0 form block 0 (0: equal widths W)
+    __device__ __forceinline__ int block(int col) const
+    {
+        return chunked ? (int) (((int64_t) col % slab) / len) : (W0 > 0 ? (col >= W0 ? 1 : 0) : (int) (col / W));
+    }
     __device__ __forceinline__ int remap(int col) const
     {
         return chunked ? (int) (((int64_t) col / slab) * len + ((int64_t) col % slab) % len) : col;
@@ -456,8 +460,20 @@ void split_column_blocks(DeviceCsr& A, int nb, cudaStream_t stream)
         return;
     nb = std::min(nb, kMaxColBlocks);
     const int64_t W = (A.n + nb - 1) / nb;
-    split_by_map(A, nb, ColMap{0, W, 0, 0}, stream);
-    A.col_block_width = W;
+    // A/B knob SB200_XSPLIT0_MB (two blocks only): size of the first operand slice.  A smaller first slice moves gathers from the head kernel
+    // (gather bound, HBM idle) into the fused kernel, where they hide under the V stream -- as long as the larger slice still lives in L2.
+    int64_t W0 = 0;
+    if (nb == 2)
+        if (const char* e = std::getenv("SB200_XSPLIT0_MB"))
+        {
+            const int64_t w0 = (int64_t) (std::atof(e) * 1024.0 * 1024.0 / 8.0);
+            if (w0 >= 1024 && w0 < A.n - 1024)
+                W0 = w0 & ~int64_t(15);
+        }
+    ColMap map{0, W, 0, 0};
+    map.W0 = W0;
+    split_by_map(A, nb, map, stream);
+    A.col_block_width = W0 > 0 ? W0 : W;
 }
 
 void split_column_chunks(DeviceCsr& A, int nchunks, int64_t slab, int nranks, cudaStream_t stream)
