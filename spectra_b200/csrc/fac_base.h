@@ -310,6 +310,7 @@ struct FacBase
             allreduce_sum(slot, 1);
         SB200_CUDA_CHECK(cudaMemcpyAsync(hred.get(), slot, sizeof(double), cudaMemcpyDeviceToHost, stream()));
         SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+        stats.host_syncs++;
         return hred.get()[0];
     }
     void set_beta_host(double b)
@@ -433,7 +434,8 @@ struct FacBase
         }
         return fused;
     }
-    void panel(int mode, int j, const double* x, double* fo, const double* coef, const int* pred = nullptr)
+    // reduce = false: the caller combines the partial results over the ranks itself (decide_after: all-reduce fused into the decide kernel)
+    void panel(int mode, int j, const double* x, double* fo, const double* coef, const int* pred = nullptr, bool reduce = true)
     {
         stats.panel_launches++;
         stats.panel_cols += j;
@@ -442,7 +444,8 @@ struct FacBase
             ScopedKernelTimer t(&prof, stream(), KC_PANEL);
             launch_panel_pass(mode, V.get(), ld, nloc, j, x, fo, coef, ctl.get()->red, rs, stream(), pred, is_cplx(), push ? &px : nullptr, abort_flag());
         }
-        allreduce_sum(ctl.get()->red, kRedNrm + 1);
+        if (reduce)
+            allreduce_sum(ctl.get()->red, kRedNrm + 1);
         if (push && pred == nullptr)
             x_published = true;  // the all-reduce above is the barrier for the rows just written into the peers' operand buffers
     }
@@ -460,6 +463,22 @@ struct FacBase
         }
         allreduce_sum(red_out, kRedNrm + 1);
     }
+    // Lanczos (real path): combine ctl->red[0..count) over the ranks, then the decisions of `stage` -- one kernel in peer mode
+    // (lanczos_decide_peer_kernel), all-reduce + decide kernel otherwise.
+    void decide_after(int stage, int count, double beta_thresh, int sweep)
+    {
+        if (peer)
+        {
+            ScopedKernelTimer t(&prof, stream(), KC_COMM, 1);
+            launch_lanczos_decide_peer(pctl, count, ctl.get(), H.get(), m, beta_thresh, stage, stream(), sweep, 0);
+        }
+        else
+        {
+            allreduce_sum(ctl.get()->red, (size_t) count);
+            launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, stage, stream(), 0, false, sweep);
+            prof.launches++;
+        }
+    }
     // A speculatively enqueued pass turned out to be skipped on the device: undo its accounting.
     void uncount_panel(int j)
     {
@@ -471,6 +490,7 @@ struct FacBase
     {
         SB200_CUDA_CHECK(cudaMemcpyAsync(hred.get(), ctl.get()->red, sizeof(double) * (is_cplx() ? kRedStride : kRedNrm + 1), cudaMemcpyDeviceToHost, stream()));
         SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+        stats.host_syncs++;
         ortho_err = 0.0;
         for (int q = 0; q < j; q++)
             ortho_err = std::max(ortho_err, is_cplx() ? std::hypot(hred.get()[q], hred.get()[kRedNrm + 1 + q]) : std::fabs(hred.get()[q]));

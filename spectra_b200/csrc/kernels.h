@@ -233,6 +233,9 @@ void launch_panel_pass(int mode, const double* V, int64_t ldv, int64_t nrows, in
 //  two_part != 0 (stage 1, real path): the pass ran in two row ranges; ctl->red2 is added to ctl->red first.
 void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated = 0, bool cplx = false,
                            int sweep = 0, int two_part = 0);
+// Peer-memory runs: all-reduce of ctl->red[0..count) over the ranks and the decisions of `stage` in one launch (real Lanczos path).
+void launch_lanczos_decide_peer(const PeerCtl& pc, int count, FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int sweep = 0,
+                                int two_part = 0);
 // Arnoldi flavours (Arnoldi.h:242-290): stage 0 = after h = V^T w (copies h into H(:,i) and c),
 // stage 1 = after f = w - V h (DGKS test), stage 2 = after a correction pass.
 // Hi != nullptr: complex Arnoldi (Hermitian-path layout of ctl->red / ctl->c); H receives the real and Hi the imaginary parts of H(:, i)

@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "peer_dev.cuh"
 
 namespace sb200 {
 
@@ -138,14 +139,16 @@ __global__ void __launch_bounds__(kPanelBlock, 2)
         }
         if (MODE != PANEL_DOT && g == 0 && valid)
             *reinterpret_cast<double2*>(f_out + r0) = fn;
-        if (MODE == PANEL_CORR && !CPLX && push.np > 0 && g == 0 && valid && r0 + push.row0 < push.rows)
+        if (MODE == PANEL_CORR && !CPLX && push.np > 0 && valid && r0 + push.row0 < push.rows)
         {
             // row-sharded runs: the new residual is the next SpMV operand of EVERY rank -- store this rank's rows straight into all
-            // operand buffers (peer memory over NVLink, chunk-major layout) instead of all-gathering them afterwards
+            // operand buffers (peer memory over NVLink, chunk-major layout) instead of all-gathering them afterwards.  Every column group
+            // holds the complete f_new of its rows, so the NG groups share the destinations (group g serves ranks g, g + NG, ...) and the
+            // remote stores are spread over all warps of the CTA.
             const int64_t rl = r0 + push.row0;  // local row
             const int64_t c = rl / push.len;
             const int64_t dst = c * push.stride + (int64_t) push.rank * push.len + (rl - c * push.len);
-            for (int p = 0; p < push.np; p++)
+            for (int p = g; p < push.np; p += NG)
                 st_peer_f64x2(push.dst[p] + dst, fn);
         }
 #pragma unroll
@@ -274,13 +277,8 @@ __device__ __forceinline__ double panel_max_abs(const double* red, int j, int la
 //            reference applies on all but a fraction of a percent of the steps -- done in one pass over V instead of two.
 //   stage 1, after that pass (red = V^T f, ||f||^2): count = 1, beta = ||f||, the test of Lanczos.h:156 on the new f.
 //   stage 2, after a further correction pass  f -= V c  (Lanczos.h:171-179): h += c with the coefficients just applied, count += 1, test.
-__global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, int predicated, int sweep, int two_part)
+__device__ __forceinline__ void lanczos_decide_body(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, int sweep, int two_part, int lane)
 {
-    if (predicated && ctl->need_corr == 0)
-        return;  // the speculative correction pass was skipped
-    if (ctl->abort != 0)
-        return;  // sweep mode: an earlier step handed control back to the host
-    const int lane = threadIdx.x;
     const int i = ctl->i, j = i + 1;
     if (stage == 0)
     {
@@ -341,6 +339,27 @@ __global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta
         if (sweep && (need || zeroed || !(beta >= 1.4901161193847656e-08)))
             ctl->abort = 1;
     }
+}
+
+__global__ void lanczos_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, int predicated, int sweep, int two_part)
+{
+    if (predicated && ctl->need_corr == 0)
+        return;  // the speculative correction pass was skipped
+    if (ctl->abort != 0)
+        return;  // sweep mode: an earlier step handed control back to the host
+    lanczos_decide_body(ctl, H, m, beta_thresh, stage, sweep, two_part, threadIdx.x);
+}
+
+// Peer-memory runs: the all-reduce of the panel result (count values of ctl->red, one-shot mailbox protocol of peer.cu) and the decisions in
+// ONE launch of 128 threads -- a sharded Lanczos step then is K-A, K-A+B, this kernel, K-C, this kernel.
+__global__ void __launch_bounds__(128) lanczos_decide_peer_kernel(PeerCtl pc, int count, FacCtl* ctl, double* H, int m, double beta_thresh, int stage, int sweep,
+                                                                  int two_part)
+{
+    if (ctl->abort != 0)
+        return;  // identical on every rank: all ranks skip the same rounds
+    peer_allreduce_body(pc, ctl->red, count, 0);
+    if (threadIdx.x < 32)
+        lanczos_decide_body(ctl, H, m, beta_thresh, stage, sweep, two_part, threadIdx.x);
 }
 
 // Complex (Hermitian) flavour of lanczos_decide_kernel: ctl->red / ctl->c carry Re at [k] and Im at [kRedNrm + 1 + k]; the
@@ -665,6 +684,18 @@ void launch_lanczos_decide(FacCtl* ctl, double* H, int m, double beta_thresh, in
     else
         lanczos_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage, predicated, sweep, two_part);
     SB200_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_lanczos_decide_peer(const PeerCtl& pc, int count, FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int sweep, int two_part)
+{
+#ifdef SB200_EMU
+    // kernel-logic emulator: a kernel that spins on a peer cannot run under the serialised launches (see launch_peer_allreduce)
+    launch_peer_allreduce(pc, ctl->red, count, 0, stream, &ctl->abort);
+    launch_lanczos_decide(ctl, H, m, beta_thresh, stage, stream, 0, false, sweep, two_part);
+#else
+    lanczos_decide_peer_kernel<<<1, 128, 0, stream>>>(pc, count, ctl, H, m, beta_thresh, stage, sweep, two_part);
+    SB200_CUDA_CHECK(cudaGetLastError());
+#endif
 }
 
 void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated, double* Hi)

@@ -11,7 +11,7 @@
 //     also the barrier that makes the residual rows written by the preceding pass visible before the next SpMV reads them.
 // Mailboxes and flags are double-buffered by round parity: a rank can be at most one round ahead of a peer (it needs that peer's flag
 // of the current round to finish it), so round r + 2 never overwrites data of round r that is still being read.
-#include "kernels.h"
+#include "peer_dev.cuh"
 #ifdef SB200_EMU
 #include <sched.h>
 #endif
@@ -24,44 +24,7 @@ __global__ void __launch_bounds__(128) peer_allreduce_kernel(PeerCtl pc, double*
 {
     if (abort != nullptr && *abort != 0)
         return;  // sweep mode after an abort: every rank skips the same rounds (the flag derives from reduced, identical values)
-    const int t = threadIdx.x;
-    const int P = pc.nranks, me = pc.rank;
-    __shared__ unsigned long long s_seq;
-    if (t == 0)
-        s_seq = *pc.seq + 1ull;
-    __syncthreads();
-    const unsigned long long seq = s_seq;
-    const int par = (int) (seq & 1ull);
-    if (t < count)
-    {
-        const double v = buf[t];
-        for (int p = 0; p < P; p++)
-            st_sys_f64(pc.slots[p] + ((size_t) (par * P + me)) * kRedStride + t, v);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (t < P)
-    {
-        st_release_sys_u64(pc.flags[t] + (par * P + me), seq);                  // tell rank t that my contribution of this round has landed
-        const unsigned long long* mine = pc.flags[me] + (par * P + t);
-        while (ld_acquire_sys_u64(mine) != seq)                                 // wait for rank t's contribution
-        {
-        }
-    }
-    __syncthreads();
-    if (t < count)
-    {
-        const double* box = pc.slots[me] + (size_t) par * P * kRedStride + t;
-        double a = ld_sys_f64(box);
-        for (int q = 1; q < P; q++)
-        {
-            const double b = ld_sys_f64(box + (size_t) q * kRedStride);
-            a = (op == 1) ? fmax(a, b) : a + b;
-        }
-        buf[t] = a;
-    }
-    if (t == 0)
-        *pc.seq = seq;
+    peer_allreduce_body(pc, buf, count, op);
 }
 
 __global__ void __launch_bounds__(256) peer_push_kernel(PeerX px, const double* __restrict__ f_loc, int64_t nrows_ld)

@@ -124,6 +124,7 @@ struct sb200_gen_solver : public FacBase
         }
         SB200_CUDA_CHECK(cudaMemcpyAsync(hstat.get(), rout.get(), sizeof(GenRestartOut), cudaMemcpyDeviceToHost, stream()));
         SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+        stats.host_syncs++;
         GenRestartOut o = *reinterpret_cast<const GenRestartOut*>(hstat.get());
         if (o.info != 0)
             throw Error(SB200_RUNTIME, "UpperHessenbergSchur: Schur decomposition failed");
@@ -200,6 +201,7 @@ struct sb200_gen_solver : public FacBase
             std::vector<int> conv_keep(nev);
             SB200_CUDA_CHECK(cudaMemcpyAsync(conv_keep.data(), ritz_conv.get(), sizeof(int) * nev, cudaMemcpyDeviceToHost, stream()));
             SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+            stats.host_syncs++;
             run_restart_kernel(selection, tol, 0);
             SB200_CUDA_CHECK(cudaMemcpyAsync(ritz_conv.get(), conv_keep.data(), sizeof(int) * nev, cudaMemcpyHostToDevice, stream()));
         }
@@ -219,6 +221,7 @@ struct sb200_gen_solver : public FacBase
         SB200_CUDA_CHECK(cudaMemcpyAsync(rvec.data(), ritz_vec.get(), sizeof(double) * 2 * m * nev, cudaMemcpyDeviceToHost, stream()));
         SB200_CUDA_CHECK(cudaMemcpyAsync(h_ritz_conv.data(), ritz_conv.get(), sizeof(int) * nev, cudaMemcpyDeviceToHost, stream()));
         SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+        stats.host_syncs++;
         std::vector<cplx> val(m), vec((size_t) m * nev);
         for (int q = 0; q < m; q++)
             val[q] = cplx(rv[2 * q], rv[2 * q + 1]);
@@ -280,6 +283,7 @@ struct sb200_gen_solver : public FacBase
             }
         SB200_CUDA_CHECK(cudaMemcpyAsync(S.get(), sel.data(), sizeof(double) * 2 * m * m, cudaMemcpyHostToDevice, stream()));
         SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+        stats.host_syncs++;
         if (X.n < (size_t) ld * 2 * nev)
             X.alloc((size_t) ld * 2 * nev);
         // two GEMMs (real and imaginary coefficient blocks) so that the output width stays <= m

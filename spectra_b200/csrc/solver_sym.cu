@@ -159,11 +159,16 @@ struct sb200_sym_solver : public FacBase
                 {
                     snap.push_back({nmatop, stats, prof.launches});
                     stats.lanczos_steps++;
-                    step_dot(s, false, true);
-                    launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 0, false);
-                    panel(PANEL_CORR, s + 1, wp, f.get(), ctl.get()->c);
-                    launch_lanczos_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream(), 0, false, 1);
-                    prof.launches += 2;
+                    const int j = s + 1;
+                    int count = j;  // values to combine over the ranks after the first panel pass
+                    if (!spmv_step(s, false, true, true))
+                    {
+                        panel(PANEL_DOT, j, wp, nullptr, nullptr, nullptr, false);
+                        count = kRedNrm + 1;
+                    }
+                    decide_after(0, count, beta_thresh, 0);
+                    panel(PANEL_CORR, j, wp, f.get(), ctl.get()->c, nullptr, false);
+                    decide_after(1, kRedNrm + 1, beta_thresh, 1);
                     stats.reorth_passes += 1;
                 }
             }
@@ -230,6 +235,7 @@ struct sb200_sym_solver : public FacBase
         }
         SB200_CUDA_CHECK(cudaMemcpyAsync(hstat.get(), rout.get(), sizeof(SymRestartOut), cudaMemcpyDeviceToHost, stream()));
         SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+        stats.host_syncs++;
         SymRestartOut o = *reinterpret_cast<const SymRestartOut*>(hstat.get());
         if (o.info != 0)
             throw Error(SB200_RUNTIME, "TridiagEigen: eigen decomposition failed");
@@ -273,6 +279,7 @@ struct sb200_sym_solver : public FacBase
             std::vector<int> conv_keep(nev);
             SB200_CUDA_CHECK(cudaMemcpyAsync(conv_keep.data(), ritz_conv.get(), sizeof(int) * nev, cudaMemcpyDeviceToHost, stream()));
             SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+            stats.host_syncs++;
             run_restart_kernel(selection, tol, 0);
             SB200_CUDA_CHECK(cudaMemcpyAsync(ritz_conv.get(), conv_keep.data(), sizeof(int) * nev, cudaMemcpyHostToDevice, stream()));
         }
@@ -290,6 +297,7 @@ struct sb200_sym_solver : public FacBase
         SB200_CUDA_CHECK(cudaMemcpyAsync(h_ritz_vec.data(), ritz_vec.get(), sizeof(double) * m * nev, cudaMemcpyDeviceToHost, stream()));
         SB200_CUDA_CHECK(cudaMemcpyAsync(h_ritz_conv.data(), ritz_conv.get(), sizeof(int) * nev, cudaMemcpyDeviceToHost, stream()));
         SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+        stats.host_syncs++;
         if (shift_mode)
             for (int i = 0; i < nev; i++)
                 h_ritz_val[i] = 1.0 / h_ritz_val[i] + sigma;
@@ -345,7 +353,8 @@ struct sb200_sym_solver : public FacBase
                 j++;
             }
         SB200_CUDA_CHECK(cudaMemcpyAsync(S.get(), sel.data(), sizeof(double) * m * m, cudaMemcpyHostToDevice, stream()));
-        SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));  // `sel` is pageable stack-lifetime memory
+        SB200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+        stats.host_syncs++;  // `sel` is pageable stack-lifetime memory
         if (X.n < (size_t) ld * nev)
             X.alloc((size_t) ld * nev);
         {
