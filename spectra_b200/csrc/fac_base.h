@@ -102,8 +102,8 @@ struct FacBase
     bool sweep_capable() const { return !op->indirect() && !is_cplx() && (op->nranks() == 1 || peer) && !sweep_disabled(); }
     static bool sweep_disabled()
     {
-        static const bool off = [] { const char* e = std::getenv("SB200_SWEEP"); return e && e[0] == '0'; }();
-        return off;
+        const char* e = std::getenv("SB200_SWEEP");  // read per factorisation: an A/B and test knob
+        return e && e[0] == '0';
     }
     void clear_abort() { SB200_CUDA_CHECK(cudaMemsetAsync(&ctl.get()->abort, 0, sizeof(int), stream())); }
     // Overlapped sweeps (opt-in, SB200_OVERLAP=1; >= 2 column blocks; one GPU in the natural layout, or peer mode): the correction pass

@@ -92,7 +92,9 @@ def test_sym_shift_eigs_reference_cases(gpu, n, prob, k, m, sigma, rule):
     eigs.init()
     nconv = eigs.compute(getattr(gpu.SortRule, rule), 500)
     if rule == "SmallestMagn" and eigs.info() != gpu.CompInfo.Successful:
-        pytest.skip("allowed failure in the reference test (allow_fail = true)")
+        # test/SymEigsShift.cpp runs this rule with allow_fail = true (it only warns): the documented status and accounting must still hold
+        assert eigs.info() == gpu.CompInfo.NotConverging and eigs.num_iterations() == 501 and nconv < k
+        return
     assert eigs.info() == gpu.CompInfo.Successful and nconv == k
     evals, U = eigs.eigenvalues(), eigs.eigenvectors()
     assert np.abs(Afull @ U - U * evals).max() <= 1e-9

@@ -478,6 +478,36 @@ def test_sym_eigs_c4_size_properties(gpu):
     assert abs(eigs.num_operations() - g["nops"]) <= 0.1 * g["nops"] and abs(eigs.num_iterations() - g["niter"]) <= 0.1 * g["niter"]
 
 
+def test_sweep_modes_agree(gpu, monkeypatch):
+    # The three ways the host can sequence a factorisation -- one round trip per Lanczos step (SB200_SWEEP=0), a whole sweep enqueued behind
+    # the device-side abort flag (default), and the opt-in overlapped sweep (two-part correction pass, head blocks of the next operator
+    # application on a second stream) -- run the same kernels on the same data: identical histories, eigenvalues equal to rounding
+    # (bitwise for the first two, which also use the same reduction order).  Two column blocks, so that the overlapped variant applies.
+    from spectra_b200 import synth
+
+    n = 300_000
+    rp, ci, v = synth.csr(n, 20, 9, True)
+    monkeypatch.setenv("SB200_XSLICE_MB", "1.2")  # 2.4 MB of x -> 2 column blocks
+    op = gpu.SparseGenMatProd.from_csr_slab(n, 0, rp, ci, v)
+    assert op.spmv_layout()["col_blocks"] == 2
+    out = {}
+    for name, env in (("sweep", {}), ("per_step", {"SB200_SWEEP": "0"}), ("overlap", {"SB200_OVERLAP": "1"})):
+        for k, val in env.items():
+            monkeypatch.setenv(k, val)
+        e = gpu.SymEigsSolver(op, 10, 30)
+        e.init()
+        assert e.compute(gpu.SortRule.LargestAlge) == 10
+        out[name] = (e.eigenvalues(), e.num_operations(), e.num_iterations(), e.stats()["host_syncs"])
+        for k in env:
+            monkeypatch.delenv(k)
+    assert out["sweep"][1:3] == out["per_step"][1:3] == out["overlap"][1:3]
+    assert np.array_equal(out["sweep"][0], out["per_step"][0])
+    assert np.abs(out["overlap"][0] - out["sweep"][0]).max() <= 1e-12 * np.abs(out["sweep"][0]).max()
+    assert out["sweep"][3] < out["per_step"][3] / 4  # far fewer host synchronisations
+    ref = O.sym_eigs(O.Csr.adopt(n, rp, ci, v), 10, 30, O.LargestAlge, want_vectors=False, threads=O.max_threads())
+    assert np.abs(out["sweep"][0] - ref.eigenvalues).max() <= 1e-10 * np.abs(ref.eigenvalues).max()
+
+
 def test_column_blocked_operator_and_solver(gpu, monkeypatch):
     # Large operands are stored as column blocks so that each SpMV pass gathers from an L2-resident slice of x
     # (csr_build.cu: split_column_blocks).  Force the blocked layout at a small size and compare with the unblocked one.
