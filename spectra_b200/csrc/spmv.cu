@@ -387,8 +387,8 @@ __global__ void __launch_bounds__(THREADS, sell_min_blocks(THREADS))
 //            cp.async were measured and are SLOWER: 96 KB of ring per CTA leave the L1 ~10 KB, which throttles the gather phase
 //            (357 vs 477 SpMV-iters/s at n = 1e7, profiles/r2d_quick_*_n1e7.log));
 //   UN       row-sum steps (gathers per lane) in flight in phase A.
-template <bool SYM, bool ACCUM, int THREADS, int NB, int UN>
-__global__ void __launch_bounds__(THREADS, 2)
+template <bool SYM, bool ACCUM, int THREADS, int NB, int UN, int RES = 2>
+__global__ void __launch_bounds__(THREADS, RES)
     sell_step_dot_kernel(const int* __restrict__ slice_ptr, const int* __restrict__ scol, const double* __restrict__ sval, const unsigned short* __restrict__ perm,
                          const double* __restrict__ x_full, const double* __restrict__ f_loc, double* V, int64_t ldv, double* w, int64_t nrows, int64_t nwin,
                          FacCtl* ctl, double* H, int m, int i, int restarted, double* red_out, double* partials, unsigned int* ticket)
@@ -654,12 +654,12 @@ void launch_sell_step_t(const SellBlock& S, int grid, int64_t nrows, const doubl
 #undef SB200_SELL_STEP
 }
 
-template <int THREADS, int NB, int UN>
+template <int THREADS, int NB, int UN, int RES = 2>
 void launch_sell_step_dot_t(const SellBlock& S, int grid, int64_t nrows, const double* x_full, const double* f_loc, double* V, int64_t ldv, double* w, FacCtl* ctl,
                             double* H, int m, int i, int restarted, bool symmetric, bool accum, double* red_out, const RedScratch& rs, cudaStream_t stream)
 {
 #define SB200_SELL_STEP_DOT(SYM, ACC)                                                                                                                          \
-    sell_step_dot_kernel<SYM, ACC, THREADS, NB, UN><<<grid, THREADS, 0, stream>>>(S.slice_ptr.get(), S.col.get(), S.val.get(), S.perm.get(), x_full, f_loc, V, ldv, w, \
+    sell_step_dot_kernel<SYM, ACC, THREADS, NB, UN, RES><<<grid, THREADS, 0, stream>>>(S.slice_ptr.get(), S.col.get(), S.val.get(), S.perm.get(), x_full, f_loc, V, ldv, w, \
                                                                                   nrows, S.nwin, ctl, H, m, i, restarted, red_out, rs.partials, rs.ticket)
     if (symmetric && accum)
         SB200_SELL_STEP_DOT(true, true);
@@ -691,6 +691,8 @@ int fused_config()
             return 3;
         if (std::strcmp(e, "256x16u8") == 0)
             return 4;
+        if (std::strcmp(e, "512x4r3") == 0)
+            return 5;  // three resident CTAs per SM (<= 42 registers): finer wave granularity for small row counts
         return 0;
     }();
     return cfg;
@@ -706,6 +708,7 @@ void launch_sell_step_dot(const SellBlock& S, int grid, int64_t nrows, const dou
         case 2: launch_sell_step_dot_t<256, 8, 4>(SB200_FUSED_ARGS); break;
         case 3: launch_sell_step_dot_t<256, 16, 4>(SB200_FUSED_ARGS); break;
         case 4: launch_sell_step_dot_t<256, 16, 8>(SB200_FUSED_ARGS); break;
+        case 5: launch_sell_step_dot_t<512, 4, 4, 3>(SB200_FUSED_ARGS); break;
         default: launch_sell_step_dot_t<512, 4, 4>(SB200_FUSED_ARGS); break;
     }
 #undef SB200_FUSED_ARGS
@@ -776,7 +779,9 @@ SpmvPlan make_spmv_plan(const DeviceCsr& A)
         // fused step head + panel pass (sell_step_dot_kernel): persistent, two resident CTAs of 512 threads per SM (per-lane accumulators
         // live across the windows of a CTA).  SB200_FUSE_DOT=0 keeps the separate panel pass (A/B knob).
         const char* fd = std::getenv("SB200_FUSE_DOT");
-        p.sell_grid_fused = (fd && fd[0] == '0') ? 0 : (int) std::max<int64_t>(1, std::min<int64_t>(S0.nwin, (int64_t) sms * 2));
+        const char* fc = std::getenv("SB200_FUSED_CFG");
+        const int fused_res = (fc && std::strcmp(fc, "512x4r3") == 0) ? 3 : 2;
+        p.sell_grid_fused = (fd && fd[0] == '0') ? 0 : (int) std::max<int64_t>(1, std::min<int64_t>(S0.nwin, (int64_t) sms * fused_res));
     }
     return p;
 }
