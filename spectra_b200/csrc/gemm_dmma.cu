@@ -93,17 +93,20 @@ __global__ void __launch_bounds__(kDmmaBlock, 2)
     }
     double nrm = 0.0;
 
+    // warp 0 arms the barrier (lane 0) and launches one bulk copy per panel column (64 rows * 8 B = 512 B each), the columns spread over
+    // its lanes so that the 60 copy instructions of a tile issue in two rounds instead of one after the other
     auto issue = [&](int64_t tile, int stage) {
-        // one thread arms the barrier and launches one bulk copy per panel column (64 rows * 8 B = 512 B each)
-        mbar_expect_tx(&full_bar[stage], (uint32_t) (m * kTR * sizeof(double)));
+        if (lane == 0)
+            mbar_expect_tx(&full_bar[stage], (uint32_t) (m * kTR * sizeof(double)));
+        __syncwarp();
         const double* src = V + tile * kTR;
         double* dst = Vs + (size_t) stage * kTC * kLds;
-        for (int c = 0; c < m; c++)
+        for (int c = lane; c < m; c += 32)
             tma_load_1d(dst + c * kLds, src + (int64_t) c * ldv, kTR * sizeof(double), &full_bar[stage]);
     };
 
     int64_t tile = blockIdx.x;
-    if (tid == 0)
+    if (warp == 0)
         for (int s = 0; s < kStages; s++)
             if (tile + (int64_t) s * gridDim.x < ntiles)
                 issue(tile + (int64_t) s * gridDim.x, s);
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(kDmmaBlock, 2)
         }
         // every warp has consumed its fragments of this stage: the buffer may be refilled
         __syncthreads();
-        if (tid == 0 && tile + (int64_t) kStages * gridDim.x < ntiles)
+        if (warp == 0 && tile + (int64_t) kStages * gridDim.x < ntiles)
             issue(tile + (int64_t) kStages * gridDim.x, stage);
 
         // C fragment: row = grp, cols = 2*tig + {0,1} of each 8 x 8 tile
