@@ -74,3 +74,24 @@ def test_product_does_not_reference_oracle():
                 assert "import oracle" not in txt and "liboracle" not in txt and "oracle/" not in txt, os.path.join(dp, f)
     out = subprocess.run(["ldd", _lib_path()], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_result_buffer_never_overruns_a_caller_array():
+    # perform_op(x, y_out): a caller-supplied y_out is handed to the C ABI only when it is a writeable C-contiguous array of exactly the
+    # element type and length the library writes; anything else gets the result through a temporary (round-1 advisor finding)
+    import spectra_b200 as sb
+
+    y = np.zeros(5)
+    buf, user = sb._result_buffer(y, 5, np.float64)
+    assert buf is y and user is None
+    ro = np.zeros(5)
+    ro.setflags(write=False)
+    for bad in (np.zeros(5, dtype=np.float32), np.zeros(10)[::2], ro):
+        buf, user = sb._result_buffer(bad, 5, np.float64)
+        assert user is bad and buf is not bad and buf.dtype == np.float64 and buf.flags.c_contiguous and buf.size == 5
+    with pytest.raises(sb.InvalidArgument):
+        sb._result_buffer(np.zeros(4), 5, np.float64)
+    with pytest.raises(sb.InvalidArgument):
+        sb._result_buffer([0.0] * 5, 5, np.float64)
+    buf, user = sb._result_buffer(None, 3, np.complex128)
+    assert user is None and buf.dtype == np.complex128 and buf.size == 3

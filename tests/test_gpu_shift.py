@@ -171,3 +171,11 @@ def test_sym_shift_eigs_full_size_properties(gpu):
     ref = O.sym_shift_eigs(O.BandLu(csr, sigma), 10, 30, O.LargestMagn, want_vectors=False)
     assert np.abs(np.sort(evals) - np.sort(ref.eigenvalues)).max() <= 1e-10 * np.abs(ref.eigenvalues).max()
     assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1] == runs[1][1]
+
+
+def test_shift_solver_rejects_operators_without_set_shift(gpu):
+    # SymEigsShiftSolver.h:193 calls op.set_shift(sigma): a plain product operator does not compile in the reference; here the C ABI rejects
+    # it (it would otherwise run Lanczos on A itself and return 1/theta + sigma -- a wrong answer without an error)
+    A = O.gen_sparse_data(100, 0.1)
+    with pytest.raises(gpu.InvalidArgument):
+        gpu.SymEigsShiftSolver(gpu.SparseSymMatProd(A), 5, 20, 0.5)
