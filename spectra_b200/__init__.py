@@ -179,7 +179,9 @@ def _result_buffer(y_out, count, dtype):
         return np.empty(count, dtype=dtype), None
     if not isinstance(y_out, np.ndarray) or y_out.size != count:
         raise InvalidArgument(1, "y_out has the wrong length")
-    if y_out.dtype == np.dtype(dtype) and y_out.flags.c_contiguous and y_out.flags.writeable:
+    if not y_out.flags.writeable:
+        raise InvalidArgument(1, "y_out is read-only")
+    if y_out.dtype == np.dtype(dtype) and y_out.flags.c_contiguous:
         return y_out, None
     return np.empty(count, dtype=dtype), y_out
 

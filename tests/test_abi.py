@@ -84,14 +84,16 @@ def test_result_buffer_never_overruns_a_caller_array():
     y = np.zeros(5)
     buf, user = sb._result_buffer(y, 5, np.float64)
     assert buf is y and user is None
-    ro = np.zeros(5)
-    ro.setflags(write=False)
-    for bad in (np.zeros(5, dtype=np.float32), np.zeros(10)[::2], ro):
+    for bad in (np.zeros(5, dtype=np.float32), np.zeros(10)[::2]):
         buf, user = sb._result_buffer(bad, 5, np.float64)
         assert user is bad and buf is not bad and buf.dtype == np.float64 and buf.flags.c_contiguous and buf.size == 5
     with pytest.raises(sb.InvalidArgument):
         sb._result_buffer(np.zeros(4), 5, np.float64)
     with pytest.raises(sb.InvalidArgument):
         sb._result_buffer([0.0] * 5, 5, np.float64)
+    ro = np.zeros(5)
+    ro.setflags(write=False)
+    with pytest.raises(sb.InvalidArgument):
+        sb._result_buffer(ro, 5, np.float64)
     buf, user = sb._result_buffer(None, 3, np.complex128)
     assert user is None and buf.dtype == np.complex128 and buf.size == 3
