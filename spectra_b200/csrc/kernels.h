@@ -26,14 +26,17 @@ struct FacCtl
     int dgks_skip;                // Arnoldi: beta > 0.717 ||h||, no re-orth  (Arnoldi.h:257)
     int abort;                    // sweep mode: a step needs the host (extra correction, zeroed residual, tiny beta) -- every later
                                   // kernel of the enqueued sweep returns at once; `i` names the step that raised it
-    int pad[2];
+    int acc_count;                // Arnoldi sweeps: correction passes of the steps completed on the device since the sweep began
+    int acc_skipped;              //   speculatively enqueued passes that turned out unnecessary (returned in their prologue)
+    int acc_skipped_cols;         //   and the sum of their panel widths (host-side traffic accounting)
+    int pad[3];
     // ---- reduction outputs / coefficients -------------------------------------------------------
     double red_a[8];              // SpMV-epilogue reduction: [0] = <v_i, w>  (Lanczos.h:142)
     double c[kRedStride];         // coefficients applied by the next correction pass  (Vf, Lanczos.h:152)
     double red[kRedStride];       // output of the last panel reduction: [0..j) = V^T f, [kRedNrm] = ||f||^2
     double red2[kRedStride];      // the same for the first row range of a correction pass run in two parts (added by the decide kernel)
 };
-constexpr size_t kFacCtlStatusBytes = 64;
+constexpr size_t kFacCtlStatusBytes = 80;
 
 // Largest grid a solver's reduction scratch serves: the persistent kernels use at most sm_count * 16 CTAs; the sliced-layout step
 // kernel runs one CTA per 1024-row window up to this bound (16384 windows = 16.7 M rows per rank) and turns persistent beyond it.
@@ -239,7 +242,10 @@ void launch_lanczos_decide_peer(const PeerCtl& pc, int count, FacCtl* ctl, doubl
 // Arnoldi flavours (Arnoldi.h:242-290): stage 0 = after h = V^T w (copies h into H(:,i) and c),
 // stage 1 = after f = w - V h (DGKS test), stage 2 = after a correction pass.
 // Hi != nullptr: complex Arnoldi (Hermitian-path layout of ctl->red / ctl->c); H receives the real and Hi the imaginary parts of H(:, i)
-void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated = 0, double* Hi = nullptr);
+// sweep != 0 (real path): the step was enqueued without a host round trip -- completed steps add their counters to ctl->acc_*, a step that
+// needs the host (a third pass, a zeroed residual, beta below near_0) raises ctl->abort.
+void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated = 0, double* Hi = nullptr,
+                           int sweep = 0);
 
 // ---- restart GEMM (panel.cu) ------------------------------------------------------------------------
 // Vout[:, c] = sum_j V[:, j] * Q[j, c]  for c < kk  (Q: m x m column-major on device, ldq = m).

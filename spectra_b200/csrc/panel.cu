@@ -427,12 +427,22 @@ __global__ void lanczos_decide_z_kernel(FacCtl* ctl, double* H, int m, double be
     }
 }
 
-__global__ void arnoldi_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, int predicated)
+__global__ void arnoldi_decide_kernel(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, int predicated, int sweep)
 {
-    if (predicated && ctl->need_corr == 0)
-        return;
+    if (ctl->abort != 0)
+        return;  // sweep mode: an earlier step handed control back to the host
     const int lane = threadIdx.x;
     const int i = ctl->i, j = i + 1;
+    if (predicated && ctl->need_corr == 0)
+    {
+        // the speculative correction pass was skipped (it returned in its prologue)
+        if (sweep && lane == 0)
+        {
+            ctl->acc_skipped += 1;
+            ctl->acc_skipped_cols += j;
+        }
+        return;
+    }
     if (stage == 0)
     {
         // h = V^T w -> H(0:i, i)  (Arnoldi.h:249-251); it is also the coefficient vector of f = w - V h
@@ -487,6 +497,16 @@ __global__ void arnoldi_decide_kernel(FacCtl* ctl, double* H, int m, double beta
         ctl->need_corr = need;
         ctl->f_zeroed = zeroed;
         ctl->dgks_skip = skip;
+        if (sweep)
+        {
+            // stage 1 with need set: the speculatively enqueued pass and its stage-2 decision follow on the device.  Otherwise the step is
+            // complete, unless the host is needed: a third pass, a residual to zero, or beta below near_0 (expand_basis at the next step).
+            const bool host = (stage == 2 && need) || zeroed || !(beta >= kNear0);
+            if (host)
+                ctl->abort = 1;
+            else if (!need)
+                ctl->acc_count += count;
+        }
     }
 }
 
@@ -698,12 +718,12 @@ void launch_lanczos_decide_peer(const PeerCtl& pc, int count, FacCtl* ctl, doubl
 #endif
 }
 
-void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated, double* Hi)
+void launch_arnoldi_decide(FacCtl* ctl, double* H, int m, double beta_thresh, int stage, cudaStream_t stream, int predicated, double* Hi, int sweep)
 {
     if (Hi)
         arnoldi_decide_z_kernel<<<1, 32, 0, stream>>>(ctl, H, Hi, m, beta_thresh, stage, predicated);
     else
-        arnoldi_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage, predicated);
+        arnoldi_decide_kernel<<<1, 32, 0, stream>>>(ctl, H, m, beta_thresh, stage, predicated, sweep);
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 

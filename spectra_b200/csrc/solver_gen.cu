@@ -67,7 +67,68 @@ struct sb200_gen_solver : public FacBase
         prof.launches++;
         double* hi = complex_h ? Hi.get() : nullptr;
 
-        for (int i = (int) from_k; i <= (int) to_m - 1; i++)
+        int i = (int) from_k;
+        // Sweep mode (real operators resident on the device; see solver_sym.cu): the remaining steps are enqueued without a host round
+        // trip -- K-A(+B), decide, f = w - V h, DGKS decide, and the first correction pass with its decision predicated on the device --
+        // and the status is read once.  A step that needs a third pass, zeroes the residual or ends with beta < near_0 raises
+        // FacCtl::abort; the per-step loop below takes over from there.
+        if (sweep_capable() && !complex_h && i <= (int) to_m - 1 && h_beta >= kNear0)
+        {
+            struct Snap
+            {
+                int64_t nmatop;
+                sb200_stats stats;
+                int64_t launches;
+            };
+            std::vector<Snap> snap;
+            SB200_CUDA_CHECK(cudaMemsetAsync(&ctl.get()->acc_count, 0, 3 * sizeof(int), stream()));
+            in_sweep = true;
+            for (int s = i; s <= (int) to_m - 1; s++)
+            {
+                snap.push_back({nmatop, stats, prof.launches});
+                stats.lanczos_steps++;
+                const int j = s + 1;
+                step_dot(s, false, false);
+                launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 0, stream(), 0, nullptr, 1);
+                panel(PANEL_CORR, j, wp, f.get(), ctl.get()->c);
+                launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 1, stream(), 0, nullptr, 1);
+                panel(PANEL_CORR, j, f.get(), f.get(), ctl.get()->c, &ctl.get()->need_corr);
+                launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 2, stream(), 1, nullptr, 1);
+                prof.launches += 3;
+            }
+            in_sweep = false;
+            const FacCtl* st = read_status();
+            const int acc_count = st->acc_count, acc_skipped = st->acc_skipped, acc_cols = st->acc_skipped_cols;
+            if (!st->abort)
+            {
+                stats.reorth_passes += acc_count;
+                stats.panel_launches -= acc_skipped;
+                stats.panel_cols -= acc_cols;
+                h_beta = st->beta;
+                k = to_m;
+                return;
+            }
+            // step st->i raised the flag; nothing after its deciding kernel executed
+            const int ia = st->i;
+            if (ia + 1 <= (int) to_m - 1)
+            {
+                const Snap& sn = snap[(size_t) (ia + 1 - i)];
+                nmatop = sn.nmatop;
+                const int64_t syncs = stats.host_syncs;
+                stats = sn.stats;
+                stats.host_syncs = syncs;
+                prof.launches = sn.launches;
+            }
+            stats.reorth_passes += acc_count;
+            stats.panel_launches -= acc_skipped;
+            stats.panel_cols -= acc_cols;
+            clear_abort();
+            if (st->count == 0)
+                uncount_panel(ia + 1);  // the speculative pass of step ia did not run (the DGKS test or a zeroed residual ended the step)
+            finish_step(st, ia + 1, beta_thresh, hi);
+            i = ia + 1;
+        }
+        for (; i <= (int) to_m - 1; i++)
         {
             stats.lanczos_steps++;
             bool restart = false;
@@ -92,22 +153,29 @@ struct sb200_gen_solver : public FacBase
             const FacCtl* st = read_status();
             if (st->count == 0)
                 uncount_panel(j);
-            while (st->need_corr)
-            {
-                panel(PANEL_CORR, j, f.get(), f.get(), ctl.get()->c);  // (:281-287)
-                launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 2, stream(), 0, hi);
-                prof.launches++;
-                st = read_status();
-            }
-            stats.reorth_passes += st->count;
-            if (st->f_zeroed)
-            {
-                f.zero(stream());
-                x_published = false;
-            }
-            h_beta = st->beta;
+            finish_step(st, j, beta_thresh, hi);
         }
         k = to_m;
+    }
+
+    // tail of one Arnoldi step on the host: further corrections while the device asks for them (Arnoldi.h:266-290), the zeroed residual of
+    // :273-278, and the host copy of beta
+    void finish_step(const FacCtl* st, int j, double beta_thresh, double* hi)
+    {
+        while (st->need_corr)
+        {
+            panel(PANEL_CORR, j, f.get(), f.get(), ctl.get()->c);  // (:281-287)
+            launch_arnoldi_decide(ctl.get(), H.get(), m, beta_thresh, 2, stream(), 0, hi);
+            prof.launches++;
+            st = read_status();
+        }
+        stats.reorth_passes += st->count;
+        if (st->f_zeroed)
+        {
+            f.zero(stream());
+            x_published = false;
+        }
+        h_beta = st->beta;
     }
 
     GenRestartOut run_restart_kernel(int selection, double tol, int do_restart)
