@@ -119,6 +119,22 @@ def test_emu_herm_factorization(emu):
 
 
 
+def test_emu_arnoldi_sweep_hands_rare_paths_back(emu):
+    # Arnoldi sweep mode (solver_gen.cu): low-rank operators drive the residual to zero inside a sweep (f_zeroed -> FacCtl::abort -> host tail),
+    # a full-rank one runs whole sweeps on the device; operation and iteration counts must be the oracle's in both regimes
+    rng = np.random.default_rng(3)
+    for n, r, k, m in ((30, 5, 3, 10), (40, 3, 2, 12), (25, 25, 4, 12)):
+        M = rng.standard_normal((n, r)) @ rng.standard_normal((r, n)) if r < n else rng.standard_normal((n, n))
+        A = sp.csc_matrix(M)
+        g = emu.GenEigsSolver(emu.SparseGenMatProd(A), k, m)
+        g.init()
+        nconv = g.compute(emu.SortRule.LargestMagn, 300)
+        ref = O.gen_eigs(O.Csr.from_scipy(A), k, m, O.LargestMagn, 300)
+        assert nconv == ref.nconv and g.num_operations() == ref.nops and g.num_iterations() == ref.niter and int(g.info()) == ref.info
+        if nconv:
+            assert np.abs(np.sort_complex(g.eigenvalues()) - np.sort_complex(ref.eigenvalues)).max() <= 1e-9 * np.abs(ref.eigenvalues).max()
+
+
 @pytest.mark.parametrize("fmt", ["sell", "csr"])
 def test_emu_overlapped_sweep_column_blocks(emu, fmt):
     # natural single-rank layout with several column blocks: the sweep runs the correction pass in two row ranges and starts the head
