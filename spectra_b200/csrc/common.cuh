@@ -269,25 +269,6 @@ __device__ __forceinline__ double ld_sys_f64(const double* p)
     return v;
 }
 __device__ __forceinline__ void st_peer_f64x2(double* p, double2 v) { p[0] = v.x; p[1] = v.y; }
-// mbarrier / bulk-copy (TMA) helpers: under emulation the copy is performed synchronously at issue, so the barriers have nothing to wait for
-__device__ __forceinline__ void mbar_init(uint64_t*, uint32_t) {}
-__device__ __forceinline__ void mbar_init_fence() {}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
-__device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) {}
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t*) { memcpy(dst_smem, src_gmem, bytes); }
-__device__ __forceinline__ void tma_load_1d_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t*, uint64_t) { memcpy(dst_smem, src_gmem, bytes); }
-__device__ __forceinline__ void fence_proxy_async_smem() {}
-// cp.async (LDGSTS): performed synchronously; `valid` false zero-fills
-__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src_gmem, bool valid, uint64_t)
-{
-    if (valid)
-        memcpy(dst_smem, src_gmem, 16);
-    else
-        memset(dst_smem, 0, 16);
-}
-__device__ __forceinline__ void cp_async_commit() {}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {}
 #else
 // L2 cache policies (createpolicy): streamed-once data is marked evict_first so that the gathered
 // operand vector / small reused vectors keep their L2 residency (evict_last).
@@ -417,28 +398,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  "r"(smem_u32(bar))
                  : "memory");
 }
-// the same with an L2 cache policy (createpolicy) for read-once streams
-__device__ __forceinline__ void tma_load_1d_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-// 16-byte asynchronous copy global -> shared (LDGSTS, L1 bypass, L2 policy); !valid: nothing is read and the destination is zero-filled
-__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src_gmem, bool valid, uint64_t policy)
-{
-    const uint32_t sz = valid ? 16u : 0u;
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(sz), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
-{
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-// orders generic-proxy accesses of shared memory before later async-proxy (TMA) accesses
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif  // SB200_EMU
 
 // Grid-wide deterministic reduction of K (<= 128) per-CTA partial values.

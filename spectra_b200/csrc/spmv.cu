@@ -693,6 +693,8 @@ int fused_config()
             return 4;
         if (std::strcmp(e, "512x4r3") == 0)
             return 5;  // three resident CTAs per SM (<= 42 registers): finer wave granularity for small row counts
+        if (std::strcmp(e, "512x8u8") == 0)
+            return 6;  // eight gathers per lane in flight in phase A
         return 0;
     }();
     return cfg;
@@ -709,6 +711,7 @@ void launch_sell_step_dot(const SellBlock& S, int grid, int64_t nrows, const dou
         case 3: launch_sell_step_dot_t<256, 16, 4>(SB200_FUSED_ARGS); break;
         case 4: launch_sell_step_dot_t<256, 16, 8>(SB200_FUSED_ARGS); break;
         case 5: launch_sell_step_dot_t<512, 4, 4, 3>(SB200_FUSED_ARGS); break;
+        case 6: launch_sell_step_dot_t<512, 8, 8>(SB200_FUSED_ARGS); break;
         default: launch_sell_step_dot_t<512, 4, 4>(SB200_FUSED_ARGS); break;
     }
 #undef SB200_FUSED_ARGS
