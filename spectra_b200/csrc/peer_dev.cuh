@@ -30,9 +30,15 @@ __device__ __forceinline__ void peer_allreduce_body(const PeerCtl& pc, double* b
     {
         st_release_sys_u64(pc.flags[t] + (par * P + me), seq);                  // tell rank t that my contribution of this round has landed
         const unsigned long long* mine = pc.flags[me] + (par * P + t);
+        unsigned int spins = 0;
         while (ld_acquire_sys_u64(mine) != seq)                                 // wait for rank t's contribution
         {
+#ifndef SB200_EMU
+            if (++spins > (1u << 27))
+                __trap();  // a peer that never arrives (crashed rank, mismatched call sequence) must not hang the device for good
+#endif
         }
+        (void) spins;
     }
     __syncthreads();
     if (t < count)
