@@ -17,7 +17,10 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+_STRICT_PATH = os.path.join(_HERE, "_build", "liboracle_strict.so")
 _lib = None
+_libs = {}
+_build_name = "default"
 
 # SortRule (Util/SelectionRule.h:33-58)
 LargestMagn, LargestReal, LargestImag, LargestAlge, SmallestMagn, SmallestReal, SmallestImag, SmallestAlge, BothEnds = range(9)
@@ -27,8 +30,8 @@ Successful, NotComputed, NotConverging, NumericalIssue = range(4)
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (g++ -O2, OpenMP)."""
-    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "dense.hpp", "solver.hpp", "Makefile")]
-    stale = (not os.path.exists(_LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "dense.hpp", "solver.hpp", "band.hpp", "Makefile")]
+    stale = any((not os.path.exists(p)) or any(os.path.getmtime(s) > os.path.getmtime(p) for s in srcs) for p in (_LIB_PATH, _STRICT_PATH))
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "--no-print-directory"], check=True, capture_output=True)
     return _LIB_PATH
@@ -48,12 +51,24 @@ class _Result(C.Structure):
     ]
 
 
+def select_build(name: str) -> str:
+    """Choose which build of the restatement the functions below call: "default" (FMA contraction, AVX2: the fast one) or
+    "strict" (-ffp-contract=off: every operation rounded once as written, bit-comparable with oracle/_ref).  Returns the previous choice."""
+    global _lib, _build_name
+    if name not in ("default", "strict"):
+        raise ValueError(name)
+    prev, _build_name = _build_name, name
+    _lib = _libs.get(name)
+    return prev
+
+
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
+        path = _LIB_PATH if _build_name == "default" else _STRICT_PATH
+        if not os.path.exists(path):
             build()
-        _lib = C.CDLL(_LIB_PATH)
+        _lib = _libs[_build_name] = C.CDLL(path)
         _lib.oracle_last_error.restype = C.c_char_p
         _lib.oracle_csr_nnz.restype = C.c_int64
         _lib.oracle_gen_sparse_data.restype = C.c_int64

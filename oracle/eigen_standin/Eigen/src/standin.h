@@ -1,0 +1,1302 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product path.
+//
+// A stand-in for the subset of the Eigen 3.4 API that yixuan/spectra's Lanczos / Arnoldi path uses,
+// so that the reference's OWN headers (/root/reference/include/Spectra, compiled where they lie,
+// never copied) build into oracle/_ref/libspectra_ref.so without Eigen, which this image does not
+// have (the reference fetches Eigen 3.4 through CPM at configure time, CMakeLists.txt:25-38).
+//
+// What this is: eager (no expression templates) column-major dense matrices, strided views for
+// Map / Ref / Block, the Jacobi / Householder primitives restated from Eigen 3.4.0's published
+// definitions (Jacobi.h makeGivens, Householder.h makeHouseholder, MathFunctions.h hypot), and a
+// compressed sparse matrix with the two products the reference calls.  Everything the reference
+// decides -- every branch, shift, deflation test, restart rule, iteration count -- is the
+// reference's own compiled code; only the BLAS-level loops (dot, axpy, gemv, small gemm) and their
+// summation order are this file's.  Eigen itself does not specify that order either (it depends
+// on the SIMD width of the build), so the reference's results are defined up to it.
+//
+// Not a general Eigen replacement: unsupported calls fail to compile.
+#pragma once
+
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <complex>
+#include <cstddef>
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+namespace Eigen {
+
+using Index = std::ptrdiff_t;
+enum : int { Dynamic = -1 };
+enum : int { ColMajor = 0, RowMajor = 1 };
+enum : int { Lower = 1, Upper = 2 };
+enum ComputationInfo { Success = 0, NumericalIssue = 1, NoConvergence = 2, InvalidInput = 3 };
+
+// ------------------------------------------------------------------------------------------------
+// NumTraits / numext
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct NumTraits
+{
+    using Real = T;
+    enum { IsComplex = 0 };
+    static constexpr T epsilon() { return std::numeric_limits<T>::epsilon(); }
+    static constexpr T lowest() { return std::numeric_limits<T>::lowest(); }
+    static constexpr T highest() { return (std::numeric_limits<T>::max)(); }
+};
+template <typename T>
+struct NumTraits<std::complex<T>>
+{
+    using Real = T;
+    enum { IsComplex = 1 };
+    static constexpr T epsilon() { return std::numeric_limits<T>::epsilon(); }
+};
+
+namespace numext {
+template <typename T>
+using numeric_limits = std::numeric_limits<T>;
+
+template <typename T>
+inline T real(const T& x) { return x; }
+template <typename T>
+inline T real(const std::complex<T>& x) { return x.real(); }
+template <typename T>
+inline T imag(const T&) { return T(0); }
+template <typename T>
+inline T imag(const std::complex<T>& x) { return x.imag(); }
+template <typename T>
+inline T conj(const T& x) { return x; }
+template <typename T>
+inline std::complex<T> conj(const std::complex<T>& x) { return std::conj(x); }
+template <typename T>
+inline T abs2(const T& x) { return x * x; }
+template <typename T>
+inline T abs2(const std::complex<T>& x) { return x.real() * x.real() + x.imag() * x.imag(); }
+template <typename T>
+inline T norm1(const T& x) { return std::abs(x); }
+template <typename T>
+inline T norm1(const std::complex<T>& x) { return std::abs(x.real()) + std::abs(x.imag()); }
+template <typename T>
+inline T maxi(const T& a, const T& b) { return a < b ? b : a; }
+template <typename T>
+inline T mini(const T& a, const T& b) { return b < a ? b : a; }
+template <typename T>
+inline T& real_ref(std::complex<T>& x) { return reinterpret_cast<T*>(&x)[0]; }
+template <typename T>
+inline T& real_ref(T& x) { return x; }
+
+// Eigen 3.4.0 MathFunctions.h, positive_real_hypot
+template <typename T>
+inline T hypot(const T& xx, const T& yy)
+{
+    T x = std::abs(xx), y = std::abs(yy);
+    if (std::isinf(x) || std::isinf(y))
+        return std::numeric_limits<T>::infinity();
+    if (std::isnan(x) || std::isnan(y))
+        return std::numeric_limits<T>::quiet_NaN();
+    T p = (std::max)(x, y);
+    if (p == T(0))
+        return T(0);
+    T qp = (std::min)(y, x) / p;
+    return p * std::sqrt(T(1) + qp * qp);
+}
+}  // namespace numext
+
+namespace internal {
+template <typename T>
+struct is_scalar : std::is_arithmetic<T>
+{};
+template <typename T>
+struct is_scalar<std::complex<T>> : std::true_type
+{};
+
+template <typename A, typename B>
+using prod_t = decltype(std::declval<A>() * std::declval<B>());
+
+// "Packets" for UpperHessenbergSchur.h's hand-vectorised Householder update (:204-270): two lanes,
+// element-wise arithmetic, so the results equal the scalar loop's.
+template <typename T>
+struct Packet2
+{
+    T v[2];
+};
+template <typename T>
+struct packet_traits
+{
+    using type = Packet2<T>;
+    enum { size = 2 };
+};
+template <typename P, typename T>
+inline P ploadu(const T* p) { return P{{p[0], p[1]}}; }
+template <typename T>
+inline void pstoreu(T* p, const Packet2<T>& a) { p[0] = a.v[0]; p[1] = a.v[1]; }
+template <typename P, typename T>
+inline P pset1(const T& a) { return P{{a, a}}; }
+template <typename T>
+inline Packet2<T> padd(const Packet2<T>& a, const Packet2<T>& b) { return {{a.v[0] + b.v[0], a.v[1] + b.v[1]}}; }
+template <typename T>
+inline Packet2<T> psub(const Packet2<T>& a, const Packet2<T>& b) { return {{a.v[0] - b.v[0], a.v[1] - b.v[1]}}; }
+template <typename T>
+inline Packet2<T> pmul(const Packet2<T>& a, const Packet2<T>& b) { return {{a.v[0] * b.v[0], a.v[1] * b.v[1]}}; }
+}  // namespace internal
+
+// ------------------------------------------------------------------------------------------------
+// Forward declarations
+// ------------------------------------------------------------------------------------------------
+template <typename Derived>
+class MatrixBase;
+template <typename S, int R, int C, int Opt = ColMajor>
+class Matrix;
+template <typename S, int R = Dynamic, int C = Dynamic>
+class View;
+template <typename S, int R, int C>
+class Array;
+template <typename S>
+class ArrayRef;
+template <typename S>
+class JacobiRotation;
+template <typename S>
+class AdjointView;
+
+namespace internal {
+template <typename T>
+struct traits;
+template <typename S, int R, int C, int Opt>
+struct traits<Matrix<S, R, C, Opt>>
+{
+    using Scalar = S;
+    enum { Rows = R, Cols = C };
+};
+template <typename S, int R, int C>
+struct traits<View<S, R, C>>
+{
+    using Scalar = S;
+    enum { Rows = R, Cols = C };
+};
+}  // namespace internal
+
+template <typename S>
+class JacobiRotation
+{
+    S m_c, m_s;
+
+public:
+    JacobiRotation() : m_c(1), m_s(0) {}
+    JacobiRotation(const S& c, const S& s) : m_c(c), m_s(s) {}
+    S& c() { return m_c; }
+    S c() const { return m_c; }
+    S& s() { return m_s; }
+    S s() const { return m_s; }
+    JacobiRotation adjoint() const { return JacobiRotation(numext::conj(m_c), -m_s); }
+    JacobiRotation transpose() const { return JacobiRotation(m_c, -numext::conj(m_s)); }
+
+    // Eigen 3.4.0 Jacobi.h, makeGivens(p, q, r, false_type): real scalars
+    void makeGivens(const S& p, const S& q, S* r = nullptr)
+    {
+        using std::abs;
+        using std::sqrt;
+        if (q == S(0))
+        {
+            m_c = p < S(0) ? S(-1) : S(1);
+            m_s = S(0);
+            if (r)
+                *r = abs(p);
+        }
+        else if (p == S(0))
+        {
+            m_c = S(0);
+            m_s = q < S(0) ? S(1) : S(-1);
+            if (r)
+                *r = abs(q);
+        }
+        else if (abs(p) > abs(q))
+        {
+            S t = q / p;
+            S u = sqrt(S(1) + numext::abs2(t));
+            if (p < S(0))
+                u = -u;
+            m_c = S(1) / u;
+            m_s = -t * m_c;
+            if (r)
+                *r = p * u;
+        }
+        else
+        {
+            S t = p / q;
+            S u = sqrt(S(1) + numext::abs2(t));
+            if (q < S(0))
+                u = -u;
+            m_s = -S(1) / u;
+            m_c = -t * m_s;
+            if (r)
+                *r = q * u;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// MatrixBase: every dense object.  Derived provides rows(), cols(), ptr(), rstride(), cstride().
+// ------------------------------------------------------------------------------------------------
+template <typename Derived>
+class MatrixBase
+{
+public:
+    using Scalar = typename internal::traits<Derived>::Scalar;
+    using RealScalar = typename NumTraits<Scalar>::Real;
+    enum { RowsAtCompileTime = internal::traits<Derived>::Rows, ColsAtCompileTime = internal::traits<Derived>::Cols };
+    using PlainObject = Matrix<Scalar, Dynamic, Dynamic, ColMajor>;
+    using DynView = View<Scalar, Dynamic, Dynamic>;
+    using ColView = View<Scalar, Dynamic, 1>;
+    using RowView = View<Scalar, 1, Dynamic>;
+
+    Derived& derived() { return *static_cast<Derived*>(this); }
+    const Derived& derived() const { return *static_cast<const Derived*>(this); }
+
+    Index rows() const { return derived().rows_(); }
+    Index cols() const { return derived().cols_(); }
+    Index size() const { return rows() * cols(); }
+    Scalar* ptr_() const { return derived().ptr_impl(); }
+    Index rs() const { return derived().rs_impl(); }
+    Index cs() const { return derived().cs_impl(); }
+
+    Scalar& coeffRef(Index i, Index j) { return ptr_()[i * rs() + j * cs()]; }
+    const Scalar& coeffRef(Index i, Index j) const { return ptr_()[i * rs() + j * cs()]; }
+    const Scalar& coeff(Index i, Index j) const { return ptr_()[i * rs() + j * cs()]; }
+    Scalar& operator()(Index i, Index j) { return coeffRef(i, j); }
+    const Scalar& operator()(Index i, Index j) const { return coeff(i, j); }
+
+    // linear (vector) access
+    Index lstride() const { return cols() == 1 ? rs() : cs(); }
+    Scalar& coeffRef(Index i) { return ptr_()[i * lstride()]; }
+    const Scalar& coeff(Index i) const { return ptr_()[i * lstride()]; }
+    Scalar& operator()(Index i) { return coeffRef(i); }
+    const Scalar& operator()(Index i) const { return coeff(i); }
+    Scalar& operator[](Index i) { return coeffRef(i); }
+    const Scalar& operator[](Index i) const { return coeff(i); }
+
+    Scalar* data() { return ptr_(); }
+    const Scalar* data() const { return ptr_(); }
+
+    Derived& noalias() { return derived(); }
+
+    // ---- views ----
+    DynView block(Index i, Index j, Index r, Index c) const { return DynView(ptr_() + i * rs() + j * cs(), r, c, rs(), cs()); }
+    template <int R, int C>
+    View<Scalar, R, C> block(Index i, Index j) const
+    {
+        return View<Scalar, R, C>(ptr_() + i * rs() + j * cs(), R, C, rs(), cs());
+    }
+    ColView col(Index j) const { return ColView(ptr_() + j * cs(), rows(), 1, rs(), cs()); }
+    RowView row(Index i) const { return RowView(ptr_() + i * rs(), 1, cols(), rs(), cs()); }
+    DynView leftCols(Index n) const { return block(0, 0, rows(), n); }
+    DynView rightCols(Index n) const { return block(0, cols() - n, rows(), n); }
+    DynView topRows(Index n) const { return block(0, 0, n, cols()); }
+    DynView bottomRows(Index n) const { return block(rows() - n, 0, n, cols()); }
+    ColView diagonal(Index k = 0) const
+    {
+        const Index i0 = k < 0 ? -k : 0, j0 = k > 0 ? k : 0;
+        const Index len = (std::max)(Index(0), (std::min)(rows() - i0, cols() - j0));
+        return ColView(ptr_() + i0 * rs() + j0 * cs(), len, 1, rs() + cs(), 0);
+    }
+    // segment / head / tail keep the orientation of the vector they are taken from
+    View<Scalar, RowsAtCompileTime == 1 ? 1 : Dynamic, RowsAtCompileTime == 1 ? Dynamic : 1> segment(Index i, Index n) const
+    {
+        using V = View<Scalar, RowsAtCompileTime == 1 ? 1 : Dynamic, RowsAtCompileTime == 1 ? Dynamic : 1>;
+        if (cols() == 1 && RowsAtCompileTime != 1)
+            return V(ptr_() + i * rs(), n, 1, rs(), cs());
+        return V(ptr_() + i * cs(), 1, n, rs(), cs());
+    }
+    auto head(Index n) const { return segment(0, n); }
+    auto tail(Index n) const { return segment(size() - n, n); }
+
+    AdjointView<Scalar> adjoint() const { return AdjointView<Scalar>(DynView(ptr_(), rows(), cols(), rs(), cs())); }
+    AdjointView<Scalar> transpose() const
+    {
+        static_assert(!NumTraits<Scalar>::IsComplex, "transpose() of complex objects is not provided by the stand-in");
+        return adjoint();
+    }
+
+    // real(): the object itself for real scalars, a real copy for complex ones
+    template <typename T = Scalar>
+    typename std::enable_if<!NumTraits<T>::IsComplex, const Derived&>::type real() const { return derived(); }
+    template <typename T = Scalar>
+    typename std::enable_if<NumTraits<T>::IsComplex, Matrix<RealScalar, Dynamic, Dynamic>>::type real() const
+    {
+        Matrix<RealScalar, Dynamic, Dynamic> res(rows(), cols());
+        for (Index j = 0; j < cols(); j++)
+            for (Index i = 0; i < rows(); i++)
+                res(i, j) = coeff(i, j).real();
+        return res;
+    }
+
+    // ---- fills ----
+    Derived& setZero() { return setConstant(Scalar(0)); }
+    Derived& setConstant(const Scalar& v)
+    {
+        const Index r = rows(), c = cols();
+        for (Index j = 0; j < c; j++)
+            for (Index i = 0; i < r; i++)
+                coeffRef(i, j) = v;
+        return derived();
+    }
+    Derived& setIdentity()
+    {
+        setZero();
+        const Index k = (std::min)(rows(), cols());
+        for (Index i = 0; i < k; i++)
+            coeffRef(i, i) = Scalar(1);
+        return derived();
+    }
+
+    // ---- element-wise assignment helpers (shape: equal, or both vectors of equal length) ----
+    template <typename Other, typename F>
+    void zip_(const MatrixBase<Other>& o, F f)
+    {
+        const Index r = rows(), c = cols();
+        if (o.rows() == r && o.cols() == c)
+        {
+            if (c == 1 && rs() == 1 && o.rs() == 1)
+            {
+                Scalar* d = ptr_();
+                const auto* s = o.ptr_();
+                for (Index i = 0; i < r; i++)
+                    f(d[i], s[i]);
+                return;
+            }
+            for (Index j = 0; j < c; j++)
+                for (Index i = 0; i < r; i++)
+                    f(coeffRef(i, j), o.coeff(i, j));
+        }
+        else if ((r == 1 || c == 1) && (o.rows() == 1 || o.cols() == 1) && size() == o.size())
+        {
+            const Index n = size();
+            for (Index i = 0; i < n; i++)
+                f(coeffRef(i), o.coeff(i));
+        }
+        else
+            throw std::logic_error("Eigen stand-in: shape mismatch in element-wise operation");
+    }
+    template <typename Other>
+    Derived& operator+=(const MatrixBase<Other>& o)
+    {
+        zip_(o, [](Scalar& a, const typename Other::Scalar& b) { a += b; });
+        return derived();
+    }
+    template <typename Other>
+    Derived& operator-=(const MatrixBase<Other>& o)
+    {
+        zip_(o, [](Scalar& a, const typename Other::Scalar& b) { a -= b; });
+        return derived();
+    }
+    template <typename T, typename = typename std::enable_if<internal::is_scalar<T>::value>::type>
+    Derived& operator*=(const T& s)
+    {
+        const Index r = rows(), c = cols();
+        for (Index j = 0; j < c; j++)
+            for (Index i = 0; i < r; i++)
+                coeffRef(i, j) *= s;
+        return derived();
+    }
+    template <typename T, typename = typename std::enable_if<internal::is_scalar<T>::value>::type>
+    Derived& operator/=(const T& s)
+    {
+        const Index r = rows(), c = cols();
+        for (Index j = 0; j < c; j++)
+            for (Index i = 0; i < r; i++)
+                coeffRef(i, j) /= s;
+        return derived();
+    }
+
+    template <typename Other>
+    void swap(MatrixBase<Other>& o)
+    {
+        zip_(o, [](Scalar& a, const Scalar& b) { std::swap(a, const_cast<Scalar&>(b)); });
+    }
+    template <typename Other>
+    void swap(MatrixBase<Other>&& o) { swap(o); }
+
+    // ---- reductions ----
+    template <typename Other>
+    Scalar dot(const MatrixBase<Other>& o) const
+    {
+        const Index n = size();
+        if (o.size() != n)
+            throw std::logic_error("Eigen stand-in: dot() of different lengths");
+        const Index sa = lstride(), sb = o.lstride();
+        const Scalar* a = ptr_();
+        const auto* b = o.ptr_();
+        // one accumulator, ascending index: the order of the restatement's single-thread dot (oracle/solver.hpp Blas::dot),
+        // so that a strict (-ffp-contract=off) build of the restatement can be compared with the reference bit for bit
+        Scalar res(0);
+        for (Index i = 0; i < n; i++)
+            res += numext::conj(a[i * sa]) * b[i * sb];
+        return res;
+    }
+    RealScalar squaredNorm() const
+    {
+        const Index r = rows(), c = cols();
+        RealScalar total(0);
+        for (Index j = 0; j < c; j++)
+        {
+            const Scalar* a = ptr_() + j * cs();
+            const Index s = rs();
+            for (Index i = 0; i < r; i++)
+                total += numext::abs2(a[i * s]);
+        }
+        return total;
+    }
+    RealScalar norm() const { return std::sqrt(squaredNorm()); }
+    void normalize()
+    {
+        const RealScalar z = squaredNorm();
+        if (z > RealScalar(0))
+            *this /= std::sqrt(z);
+    }
+    Matrix<RealScalar, Dynamic, Dynamic> cwiseAbs() const
+    {
+        Matrix<RealScalar, Dynamic, Dynamic> res(rows(), cols());
+        for (Index j = 0; j < cols(); j++)
+            for (Index i = 0; i < rows(); i++)
+                res(i, j) = std::abs(coeff(i, j));
+        return res;
+    }
+    Scalar sum() const
+    {
+        Scalar acc(0);
+        for (Index j = 0; j < cols(); j++)
+            for (Index i = 0; i < rows(); i++)
+                acc += coeff(i, j);
+        return acc;
+    }
+    Scalar maxCoeff() const
+    {
+        if (size() == 0)
+            throw std::logic_error("Eigen stand-in: maxCoeff() of an empty object");
+        Scalar m = coeff(0, 0);
+        for (Index j = 0; j < cols(); j++)
+            for (Index i = 0; i < rows(); i++)
+                if (coeff(i, j) > m)
+                    m = coeff(i, j);
+        return m;
+    }
+    // vector form with index (UpperHessenbergEigen.h:370)
+    Scalar minCoeff(Index* idx) const
+    {
+        Scalar m = coeff(0);
+        *idx = 0;
+        for (Index i = 1; i < size(); i++)
+            if (coeff(i) < m)
+            {
+                m = coeff(i);
+                *idx = i;
+            }
+        return m;
+    }
+    Scalar value() const { return coeff(0, 0); }
+
+    template <typename T>
+    Matrix<T, Dynamic, Dynamic> cast() const
+    {
+        Matrix<T, Dynamic, Dynamic> res(rows(), cols());
+        for (Index j = 0; j < cols(); j++)
+            for (Index i = 0; i < rows(); i++)
+                res(i, j) = T(coeff(i, j));
+        return res;
+    }
+
+    ArrayRef<Scalar> array() const { return ArrayRef<Scalar>(ptr_(), size(), lstride()); }
+
+    // ---- plane rotations (Eigen 3.4.0 Jacobi.h: apply_rotation_in_the_plane(x, y, j) is
+    // x_i <- c x_i + conj(s) y_i ; y_i <- -s x_i + conj(c) y_i; applyOnTheLeft passes rows p, q and j,
+    // applyOnTheRight passes columns p, q and j.transpose()) ----
+    template <typename T>
+    void applyOnTheRight(Index p, Index q, const JacobiRotation<T>& j)
+    {
+        const JacobiRotation<T> jt = j.transpose();
+        const Index r = rows();
+        for (Index i = 0; i < r; i++)
+        {
+            const Scalar xi = coeff(i, p), yi = coeff(i, q);
+            coeffRef(i, p) = jt.c() * xi + numext::conj(jt.s()) * yi;
+            coeffRef(i, q) = -jt.s() * xi + numext::conj(jt.c()) * yi;
+        }
+    }
+    template <typename T>
+    void applyOnTheLeft(Index p, Index q, const JacobiRotation<T>& j)
+    {
+        const Index c = cols();
+        for (Index k = 0; k < c; k++)
+        {
+            const Scalar xi = coeff(p, k), yi = coeff(q, k);
+            coeffRef(p, k) = j.c() * xi + numext::conj(j.s()) * yi;
+            coeffRef(q, k) = -j.s() * xi + numext::conj(j.c()) * yi;
+        }
+    }
+
+    // Eigen 3.4.0 Householder.h, makeHouseholder(essential, tau, beta)
+    template <typename Ess>
+    void makeHouseholder(Ess& essential, Scalar& tau, RealScalar& beta) const
+    {
+        using std::sqrt;
+        const Index n = size();
+        RealScalar tailSqNorm(0);
+        for (Index i = 1; i < n; i++)
+            tailSqNorm += numext::abs2(coeff(i));
+        const Scalar c0 = coeff(0);
+        const RealScalar tol = (std::numeric_limits<RealScalar>::min)();
+        if (tailSqNorm <= tol && numext::abs2(numext::imag(c0)) <= tol)
+        {
+            tau = Scalar(0);
+            beta = numext::real(c0);
+            essential.setZero();
+        }
+        else
+        {
+            beta = sqrt(numext::abs2(c0) + tailSqNorm);
+            if (numext::real(c0) >= RealScalar(0))
+                beta = -beta;
+            for (Index i = 1; i < n; i++)
+                essential.coeffRef(i - 1) = coeff(i) / (c0 - beta);
+            tau = numext::conj((beta - c0) / beta);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// View: (pointer, rows, cols, row stride, column stride).  Map, Ref and every block are views.
+// Constness is not tracked (a view of a const object can be written through; the reference does not).
+// ------------------------------------------------------------------------------------------------
+template <typename S, int R, int C>
+class View : public MatrixBase<View<S, R, C>>
+{
+protected:
+    S* m_p;
+    Index m_r, m_c, m_rs, m_cs;
+
+public:
+    using Base = MatrixBase<View<S, R, C>>;
+    using Scalar = S;
+    enum { IsRowMajor = 0 };
+    View() : m_p(nullptr), m_r(0), m_c(0), m_rs(1), m_cs(0) {}
+    View(const S* p, Index r, Index c, Index rs, Index cs) : m_p(const_cast<S*>(p)), m_r(r), m_c(c), m_rs(rs), m_cs(cs) {}
+    View(const View&) = default;
+    template <int R2, int C2>
+    View(const View<S, R2, C2>& o) : m_p(o.ptr_impl()), m_r(o.rows_()), m_c(o.cols_()), m_rs(o.rs_impl()), m_cs(o.cs_impl())
+    {}
+    template <int R2, int C2, int Opt>
+    View(const Matrix<S, R2, C2, Opt>& o) : m_p(o.ptr_impl()), m_r(o.rows_()), m_c(o.cols_()), m_rs(o.rs_impl()), m_cs(o.cs_impl())
+    {}
+
+    Index rows_() const { return m_r; }
+    Index cols_() const { return m_c; }
+    S* ptr_impl() const { return m_p; }
+    Index rs_impl() const { return m_rs; }
+    Index cs_impl() const { return m_cs; }
+
+    // assignment copies elements (never rebinds)
+    View& operator=(const View& o)
+    {
+        this->zip_(o, [](S& a, const S& b) { a = b; });
+        return *this;
+    }
+    template <typename Other>
+    View& operator=(const MatrixBase<Other>& o)
+    {
+        this->zip_(o, [](S& a, const typename Other::Scalar& b) { a = b; });
+        return *this;
+    }
+};
+
+template <typename S>
+class AdjointView
+{
+public:
+    View<S, Dynamic, Dynamic> m;  // the object whose adjoint this is
+    explicit AdjointView(const View<S, Dynamic, Dynamic>& v) : m(v) {}
+};
+
+// ------------------------------------------------------------------------------------------------
+// Matrix: owning, column-major (the RowMajor option exists only as a compile-time flag for the
+// reference's static_asserts; RowMajor dense matrices are not instantiated on this path).
+// ------------------------------------------------------------------------------------------------
+template <typename S, int R, int C, int Opt>
+class Matrix : public MatrixBase<Matrix<S, R, C, Opt>>
+{
+    std::vector<S> m_a;
+    Index m_r, m_c;
+
+    void alloc_(Index r, Index c)
+    {
+        m_r = r;
+        m_c = c;
+        m_a.assign(static_cast<size_t>(r * c), S());
+    }
+
+public:
+    using Base = MatrixBase<Matrix<S, R, C, Opt>>;
+    using Scalar = S;
+    using PlainObject = Matrix;
+    enum { IsRowMajor = (Opt == RowMajor) ? 1 : 0 };
+
+    Matrix() { alloc_(R == Dynamic ? 0 : R, C == Dynamic ? 0 : C); }
+    explicit Matrix(Index n)
+    {
+        static_assert(R == 1 || C == 1 || R == Dynamic || C == Dynamic, "");
+        if (C == 1)
+            alloc_(n, 1);
+        else if (R == 1)
+            alloc_(1, n);
+        else
+            alloc_(n, n);  // not used by the reference
+    }
+    Matrix(Index r, Index c) { alloc_(r, c); }
+    Matrix(const Matrix&) = default;
+    Matrix(Matrix&&) = default;
+    template <typename Other>
+    Matrix(const MatrixBase<Other>& o) : m_r(0), m_c(0)
+    {
+        assign_(o);
+    }
+
+    Index rows_() const { return m_r; }
+    Index cols_() const { return m_c; }
+    S* ptr_impl() const { return const_cast<S*>(m_a.data()); }
+    Index rs_impl() const { return 1; }
+    Index cs_impl() const { return m_r; }
+
+    void resize(Index n)
+    {
+        if (C == 1)
+            resize(n, 1);
+        else
+            resize(1, n);
+    }
+    void resize(Index r, Index c)
+    {
+        if (r != m_r || c != m_c)
+            alloc_(r, c);
+    }
+
+    template <typename Other>
+    void assign_(const MatrixBase<Other>& o)
+    {
+        Index r = o.rows(), c = o.cols();
+        // a compile-time vector takes a vector of the other orientation as a sequence
+        if (C == 1 && c != 1 && r == 1)
+            std::swap(r, c);
+        if (R == 1 && r != 1 && c == 1)
+            std::swap(r, c);
+        if (r != m_r || c != m_c)
+        {
+            m_r = r;
+            m_c = c;
+            m_a.resize(static_cast<size_t>(r * c));
+        }
+        this->zip_(o, [](S& a, const typename Other::Scalar& b) { a = S(b); });
+    }
+    Matrix& operator=(const Matrix& o)
+    {
+        m_a = o.m_a;
+        m_r = o.m_r;
+        m_c = o.m_c;
+        return *this;
+    }
+    Matrix& operator=(Matrix&& o) = default;
+    template <typename Other>
+    Matrix& operator=(const MatrixBase<Other>& o)
+    {
+        assign_(o);
+        return *this;
+    }
+
+    // Matrix <-> Matrix swap exchanges storage (Arnoldi.h:337, UpperHessenbergSchur.h swap_T/swap_U)
+    void swap(Matrix& o)
+    {
+        m_a.swap(o.m_a);
+        std::swap(m_r, o.m_r);
+        std::swap(m_c, o.m_c);
+    }
+    using Base::swap;
+
+    static Matrix Zero(Index r, Index c)
+    {
+        Matrix m(r, c);
+        return m;
+    }
+    static Matrix Zero(Index n)
+    {
+        Matrix m(n);
+        return m;
+    }
+    static Matrix Zero()
+    {
+        Matrix m;
+        m.setZero();
+        return m;
+    }
+    static Matrix Identity(Index r, Index c)
+    {
+        Matrix m(r, c);
+        m.setIdentity();
+        return m;
+    }
+    static Matrix Constant(Index r, Index c, const S& v)
+    {
+        Matrix m(r, c);
+        m.setConstant(v);
+        return m;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Map<PlainT>, Ref<PlainT>: views with Eigen's constructor forms
+// ------------------------------------------------------------------------------------------------
+namespace internal {
+template <typename PlainT>
+struct plain_info
+{
+    using P = typename std::remove_const<PlainT>::type;
+    using Scalar = typename P::Scalar;
+    enum { Rows = P::RowsAtCompileTime, Cols = P::ColsAtCompileTime };
+};
+}  // namespace internal
+
+template <typename PlainT, typename Enable = void>
+class Map : public View<typename internal::plain_info<PlainT>::Scalar, internal::plain_info<PlainT>::Rows, internal::plain_info<PlainT>::Cols>
+{
+    using Info = internal::plain_info<PlainT>;
+    using S = typename Info::Scalar;
+    using V = View<S, Info::Rows, Info::Cols>;
+
+public:
+    using Scalar = S;
+    using PlainObject = typename Info::P;
+    Map(const S* p, Index n) : V(p, Info::Rows == 1 ? 1 : n, Info::Rows == 1 ? n : 1, 1, Info::Rows == 1 ? 1 : n) {}
+    Map(const S* p, Index r, Index c) : V(p, r, c, 1, r) {}
+    Map(const Map&) = default;
+    Map& operator=(const Map& o)
+    {
+        V::operator=(static_cast<const V&>(o));
+        return *this;
+    }
+    template <typename Other>
+    Map& operator=(const MatrixBase<Other>& o)
+    {
+        V::operator=(o);
+        return *this;
+    }
+};
+
+template <typename PlainT, typename Enable = void>
+class Ref : public View<typename internal::plain_info<PlainT>::Scalar, internal::plain_info<PlainT>::Rows, internal::plain_info<PlainT>::Cols>
+{
+    using Info = internal::plain_info<PlainT>;
+    using S = typename Info::Scalar;
+    using V = View<S, Info::Rows, Info::Cols>;
+
+public:
+    using Scalar = S;
+    using PlainObject = typename Info::P;
+    template <typename Other, typename = typename std::enable_if<std::is_same<typename Other::Scalar, S>::value>::type>
+    Ref(const MatrixBase<Other>& o) : V(o.ptr_(), o.rows(), o.cols(), o.rs(), o.cs())
+    {}
+    Ref(const Ref&) = default;
+    Ref& operator=(const Ref& o)
+    {
+        V::operator=(static_cast<const V&>(o));
+        return *this;
+    }
+    template <typename Other>
+    Ref& operator=(const MatrixBase<Other>& o)
+    {
+        V::operator=(o);
+        return *this;
+    }
+};
+
+namespace internal {
+template <typename PlainT, typename E>
+struct traits<Map<PlainT, E>> : traits<View<typename plain_info<PlainT>::Scalar, plain_info<PlainT>::Rows, plain_info<PlainT>::Cols>>
+{};
+template <typename PlainT, typename E>
+struct traits<Ref<PlainT, E>> : traits<View<typename plain_info<PlainT>::Scalar, plain_info<PlainT>::Rows, plain_info<PlainT>::Cols>>
+{};
+}  // namespace internal
+
+// ------------------------------------------------------------------------------------------------
+// Eager arithmetic
+// ------------------------------------------------------------------------------------------------
+template <typename A, typename B>
+Matrix<internal::prod_t<typename A::Scalar, typename B::Scalar>, Dynamic, Dynamic> operator+(const MatrixBase<A>& a, const MatrixBase<B>& b)
+{
+    Matrix<internal::prod_t<typename A::Scalar, typename B::Scalar>, Dynamic, Dynamic> res(a);
+    res += b;
+    return res;
+}
+template <typename A, typename B>
+Matrix<internal::prod_t<typename A::Scalar, typename B::Scalar>, Dynamic, Dynamic> operator-(const MatrixBase<A>& a, const MatrixBase<B>& b)
+{
+    Matrix<internal::prod_t<typename A::Scalar, typename B::Scalar>, Dynamic, Dynamic> res(a);
+    res -= b;
+    return res;
+}
+template <typename A>
+Matrix<typename A::Scalar, Dynamic, Dynamic> operator-(const MatrixBase<A>& a)
+{
+    Matrix<typename A::Scalar, Dynamic, Dynamic> res(a);
+    res *= typename A::Scalar(-1);
+    return res;
+}
+template <typename A, typename T, typename = typename std::enable_if<internal::is_scalar<T>::value>::type>
+Matrix<internal::prod_t<typename A::Scalar, T>, Dynamic, Dynamic> operator*(const MatrixBase<A>& a, const T& s)
+{
+    Matrix<internal::prod_t<typename A::Scalar, T>, Dynamic, Dynamic> res(a);
+    res *= s;
+    return res;
+}
+template <typename A, typename T, typename = typename std::enable_if<internal::is_scalar<T>::value>::type>
+Matrix<internal::prod_t<typename A::Scalar, T>, Dynamic, Dynamic> operator*(const T& s, const MatrixBase<A>& a)
+{
+    Matrix<internal::prod_t<typename A::Scalar, T>, Dynamic, Dynamic> res(a);
+    res *= s;
+    return res;
+}
+template <typename A, typename T, typename = typename std::enable_if<internal::is_scalar<T>::value>::type>
+Matrix<internal::prod_t<typename A::Scalar, T>, Dynamic, Dynamic> operator/(const MatrixBase<A>& a, const T& s)
+{
+    Matrix<internal::prod_t<typename A::Scalar, T>, Dynamic, Dynamic> res(a);
+    res /= s;
+    return res;
+}
+
+// C = A B, column-oriented (each column of C is a sum of scaled columns of A, ascending k)
+template <typename A, typename B>
+Matrix<internal::prod_t<typename A::Scalar, typename B::Scalar>, Dynamic, Dynamic> operator*(const MatrixBase<A>& a, const MatrixBase<B>& b)
+{
+    using RS = internal::prod_t<typename A::Scalar, typename B::Scalar>;
+    if (a.cols() != b.rows())
+        throw std::logic_error("Eigen stand-in: inner dimensions differ in a matrix product");
+    const Index m = a.rows(), kk = a.cols(), n = b.cols();
+    Matrix<RS, Dynamic, Dynamic> res(m, n);
+    for (Index j = 0; j < n; j++)
+    {
+        RS* c = res.data() + j * m;
+        for (Index k = 0; k < kk; k++)
+        {
+            const auto bk = b.coeff(k, j);
+            const typename A::Scalar* ak = a.ptr_() + k * a.cs();
+            const Index s = a.rs();
+            if (s == 1)
+                for (Index i = 0; i < m; i++)
+                    c[i] += ak[i] * bk;
+            else
+                for (Index i = 0; i < m; i++)
+                    c[i] += ak[i * s] * bk;
+        }
+    }
+    return res;
+}
+
+// C = A^H B: one conjugated dot product per entry
+template <typename SA, typename B>
+Matrix<internal::prod_t<SA, typename B::Scalar>, Dynamic, Dynamic> operator*(const AdjointView<SA>& at, const MatrixBase<B>& b)
+{
+    using RS = internal::prod_t<SA, typename B::Scalar>;
+    const auto& a = at.m;
+    if (a.rows() != b.rows())
+        throw std::logic_error("Eigen stand-in: inner dimensions differ in an adjoint product");
+    Matrix<RS, Dynamic, Dynamic> res(a.cols(), b.cols());
+    for (Index j = 0; j < b.cols(); j++)
+        for (Index i = 0; i < a.cols(); i++)
+            res(i, j) = a.col(i).dot(b.col(j));
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Arrays (coefficient-wise world): only what HermEigsBase / GenEigsBase / UpperHessenbergQR touch
+// ------------------------------------------------------------------------------------------------
+template <typename S, int R = Dynamic, int C = 1>
+class Array
+{
+    std::vector<S> m_a;
+
+public:
+    using Scalar = S;
+    using RealScalar = typename NumTraits<S>::Real;
+    Array() {}
+    explicit Array(Index n) : m_a(static_cast<size_t>(n), S()) {}
+    Array(const ArrayRef<S>& r);
+    Index size() const { return static_cast<Index>(m_a.size()); }
+    void resize(Index n) { m_a.assign(static_cast<size_t>(n), S()); }
+    void setZero() { std::fill(m_a.begin(), m_a.end(), S()); }
+    // std::vector<bool> has no data(); bool arrays are stored as unsigned char underneath
+    S* data() { return m_a.data(); }
+    const S* data() const { return m_a.data(); }
+    S& coeffRef(Index i) { return m_a[static_cast<size_t>(i)]; }
+    const S& coeff(Index i) const { return m_a[static_cast<size_t>(i)]; }
+    S& operator[](Index i) { return m_a[static_cast<size_t>(i)]; }
+    const S& operator[](Index i) const { return m_a[static_cast<size_t>(i)]; }
+    S& operator()(Index i) { return m_a[static_cast<size_t>(i)]; }
+    const S& operator()(Index i) const { return m_a[static_cast<size_t>(i)]; }
+    void swap(Array& o) { m_a.swap(o.m_a); }
+
+    Array<RealScalar, R, C> abs() const
+    {
+        Array<RealScalar, R, C> res(size());
+        for (Index i = 0; i < size(); i++)
+            res[i] = std::abs(m_a[i]);
+        return res;
+    }
+    Array max(const S& v) const
+    {
+        Array res(size());
+        for (Index i = 0; i < size(); i++)
+            res[i] = (std::max)(m_a[i], v);
+        return res;
+    }
+    Array operator*(const S& v) const
+    {
+        Array res(size());
+        for (Index i = 0; i < size(); i++)
+            res[i] = m_a[i] * v;
+        return res;
+    }
+    friend Array operator*(const S& v, const Array& a) { return a * v; }
+    Array operator-(const S& v) const
+    {
+        Array res(size());
+        for (Index i = 0; i < size(); i++)
+            res[i] = m_a[i] - v;
+        return res;
+    }
+    Index count() const
+    {
+        Index n = 0;
+        for (Index i = 0; i < size(); i++)
+            n += m_a[i] ? 1 : 0;
+        return n;
+    }
+    template <typename T>
+    Array<T, R, C> cast() const
+    {
+        Array<T, R, C> res(size());
+        for (Index i = 0; i < size(); i++)
+            res[i] = T(m_a[i]);
+        return res;
+    }
+    S sum() const
+    {
+        S acc(0);
+        for (Index i = 0; i < size(); i++)
+            acc += m_a[i];
+        return acc;
+    }
+};
+
+// bool arrays: element type unsigned char underneath so that operator[] returns a real reference
+template <int R, int C>
+class Array<bool, R, C>
+{
+    std::vector<unsigned char> m_a;
+
+public:
+    using Scalar = bool;
+    Array() {}
+    explicit Array(Index n) : m_a(static_cast<size_t>(n), 0) {}
+    Index size() const { return static_cast<Index>(m_a.size()); }
+    void resize(Index n) { m_a.assign(static_cast<size_t>(n), 0); }
+    void setZero() { std::fill(m_a.begin(), m_a.end(), 0); }
+    struct BoolRef
+    {
+        unsigned char& b;
+        BoolRef& operator=(bool v)
+        {
+            b = v ? 1 : 0;
+            return *this;
+        }
+        BoolRef& operator=(const BoolRef& o)
+        {
+            b = o.b;
+            return *this;
+        }
+        operator bool() const { return b != 0; }
+    };
+    BoolRef operator[](Index i) { return BoolRef{m_a[static_cast<size_t>(i)]}; }
+    bool operator[](Index i) const { return m_a[static_cast<size_t>(i)] != 0; }
+    void swap(Array& o) { m_a.swap(o.m_a); }
+    Index count() const
+    {
+        Index n = 0;
+        for (unsigned char b : m_a)
+            n += b ? 1 : 0;
+        return n;
+    }
+    template <typename T>
+    Array<T, R, C> cast() const
+    {
+        Array<T, R, C> res(size());
+        for (Index i = 0; i < size(); i++)
+            res[i] = T(m_a[static_cast<size_t>(i)] ? 1 : 0);
+        return res;
+    }
+};
+
+template <typename S, int R, int C>
+Array<bool, R, C> operator<(const Array<S, R, C>& a, const Array<S, R, C>& b)
+{
+    if (a.size() != b.size())
+        throw std::logic_error("Eigen stand-in: array size mismatch");
+    Array<bool, R, C> res(a.size());
+    for (Index i = 0; i < a.size(); i++)
+        res[i] = a[i] < b[i];
+    return res;
+}
+
+// a strided window onto a matrix / vector, seen coefficient-wise
+template <typename S>
+class ArrayRef
+{
+    S* m_p;
+    Index m_n, m_s;
+
+public:
+    using RealScalar = typename NumTraits<S>::Real;
+    ArrayRef(S* p, Index n, Index s) : m_p(p), m_n(n), m_s(s) {}
+    Index size() const { return m_n; }
+    const S& operator[](Index i) const { return m_p[i * m_s]; }
+    ArrayRef& operator-=(const S& v)
+    {
+        for (Index i = 0; i < m_n; i++)
+            m_p[i * m_s] -= v;
+        return *this;
+    }
+    ArrayRef& operator+=(const S& v)
+    {
+        for (Index i = 0; i < m_n; i++)
+            m_p[i * m_s] += v;
+        return *this;
+    }
+    ArrayRef& operator=(const Array<S, Dynamic, 1>& a)
+    {
+        if (a.size() != m_n)
+            throw std::logic_error("Eigen stand-in: array size mismatch");
+        for (Index i = 0; i < m_n; i++)
+            m_p[i * m_s] = a[i];
+        return *this;
+    }
+    Array<S, Dynamic, 1> operator-(const S& v) const
+    {
+        Array<S, Dynamic, 1> res(m_n);
+        for (Index i = 0; i < m_n; i++)
+            res[i] = m_p[i * m_s] - v;
+        return res;
+    }
+    Array<RealScalar, Dynamic, 1> abs() const
+    {
+        Array<RealScalar, Dynamic, 1> res(m_n);
+        for (Index i = 0; i < m_n; i++)
+            res[i] = std::abs(m_p[i * m_s]);
+        return res;
+    }
+};
+template <typename S, int R, int C>
+Array<S, R, C>::Array(const ArrayRef<S>& r) : m_a(static_cast<size_t>(r.size()))
+{
+    for (Index i = 0; i < r.size(); i++)
+        m_a[static_cast<size_t>(i)] = r[i];
+}
+
+// Declared only: the complex specialisation of UpperHessenbergEigen (UpperHessenbergEigen.h:328-454)
+// names it as a member type; that specialisation is not instantiated by oracle/_ref.
+template <typename MatrixType>
+class ComplexSchur;
+
+// ------------------------------------------------------------------------------------------------
+// SparseCore subset: compressed storage + the two products of MatOp/Sparse{Sym,Gen}MatProd.h
+// ------------------------------------------------------------------------------------------------
+template <typename Derived>
+class SparseMatrixBase
+{
+public:
+    const Derived& derived() const { return *static_cast<const Derived*>(this); }
+};
+
+template <typename S, int Flags = ColMajor, typename StorageIndex = int>
+class SparseMatrix;
+
+// the compressed arrays of a matrix somebody else owns
+template <typename S, int Flags, typename StorageIndex>
+struct SparseData
+{
+    Index rows = 0, cols = 0, nnz = 0;
+    const StorageIndex* outer = nullptr;
+    const StorageIndex* inner = nullptr;
+    const S* values = nullptr;
+};
+
+template <typename S, int Flags, typename StorageIndex, int Uplo>
+class SparseSelfAdjointView
+{
+public:
+    SparseData<S, Flags, StorageIndex> d;
+};
+
+template <typename S, int Flags, typename StorageIndex>
+class SparseCompressedBase
+{
+protected:
+    SparseData<S, Flags, StorageIndex> m_d;
+
+public:
+    using Scalar = S;
+    enum { IsRowMajor = (Flags & RowMajor) ? 1 : 0 };
+    Index rows() const { return m_d.rows; }
+    Index cols() const { return m_d.cols; }
+    Index nonZeros() const { return m_d.nnz; }
+    Index outerSize() const { return IsRowMajor ? m_d.rows : m_d.cols; }
+    const SparseData<S, Flags, StorageIndex>& raw() const { return m_d; }
+    // SparseMatrix::coeff: search inside the outer vector (inner indices ascending or not)
+    S coeff(Index i, Index j) const
+    {
+        const Index o = IsRowMajor ? i : j, in = IsRowMajor ? j : i;
+        S acc(0);
+        for (Index k = m_d.outer[o]; k < m_d.outer[o + 1]; k++)
+            if (m_d.inner[k] == in)
+                acc += m_d.values[k];
+        return acc;
+    }
+    template <int Uplo>
+    SparseSelfAdjointView<S, Flags, StorageIndex, Uplo> selfadjointView() const
+    {
+        SparseSelfAdjointView<S, Flags, StorageIndex, Uplo> v;
+        v.d = m_d;
+        return v;
+    }
+};
+
+template <typename S, int Flags, typename StorageIndex>
+class SparseMatrix : public SparseCompressedBase<S, Flags, StorageIndex>, public SparseMatrixBase<SparseMatrix<S, Flags, StorageIndex>>
+{
+public:
+    using PlainObject = SparseMatrix;
+    using Scalar = S;
+    enum { IsRowMajor = (Flags & RowMajor) ? 1 : 0 };
+};
+
+// Map<const SparseMatrix>(rows, cols, nnz, outerIndexPtr, innerIndexPtr, valuePtr): Eigen's constructor
+template <typename S, int Flags, typename StorageIndex>
+class Map<const SparseMatrix<S, Flags, StorageIndex>, void>
+    : public SparseCompressedBase<S, Flags, StorageIndex>, public SparseMatrixBase<Map<const SparseMatrix<S, Flags, StorageIndex>, void>>
+{
+public:
+    using PlainObject = SparseMatrix<S, Flags, StorageIndex>;
+    using Scalar = S;
+    Map(Index rows, Index cols, Index nnz, const StorageIndex* outer, const StorageIndex* inner, const S* values)
+    {
+        this->m_d.rows = rows;
+        this->m_d.cols = cols;
+        this->m_d.nnz = nnz;
+        this->m_d.outer = outer;
+        this->m_d.inner = inner;
+        this->m_d.values = values;
+    }
+};
+
+template <typename S, int Flags, typename StorageIndex>
+class Ref<const SparseMatrix<S, Flags, StorageIndex>, void> : public SparseCompressedBase<S, Flags, StorageIndex>
+{
+public:
+    using Scalar = S;
+    template <typename Derived>
+    Ref(const SparseMatrixBase<Derived>& m)
+    {
+        this->m_d = m.derived().raw();
+    }
+};
+
+// y = A x, A general compressed (SparseGenMatProd.h:86): row-major = one dot product per row,
+// column-major = scaled columns accumulated in column order (Eigen's sparse_time_dense_product)
+template <typename S, int Flags, typename StorageIndex, typename B>
+Matrix<S, Dynamic, Dynamic> operator*(const SparseCompressedBase<S, Flags, StorageIndex>& A, const MatrixBase<B>& x)
+{
+    const auto& d = A.raw();
+    Matrix<S, Dynamic, Dynamic> y(d.rows, x.cols());
+    for (Index c = 0; c < x.cols(); c++)
+    {
+        if (Flags & RowMajor)
+        {
+            for (Index i = 0; i < d.rows; i++)
+            {
+                S acc(0);
+                for (Index k = d.outer[i]; k < d.outer[i + 1]; k++)
+                    acc += d.values[k] * x.coeff(d.inner[k], c);
+                y(i, c) = acc;
+            }
+        }
+        else
+        {
+            for (Index j = 0; j < d.cols; j++)
+            {
+                const S xj = x.coeff(j, c);
+                for (Index k = d.outer[j]; k < d.outer[j + 1]; k++)
+                    y(d.inner[k], c) += d.values[k] * xj;
+            }
+        }
+    }
+    return y;
+}
+
+// y = selfadjointView<Uplo>(A) x (SparseSymMatProd.h:87): only the Uplo triangle of A is read; each
+// stored off-diagonal entry contributes to two rows (Eigen's sparse_selfadjoint_time_dense_product)
+template <typename S, int Flags, typename StorageIndex, int Uplo, typename B>
+Matrix<S, Dynamic, Dynamic> operator*(const SparseSelfAdjointView<S, Flags, StorageIndex, Uplo>& A, const MatrixBase<B>& x)
+{
+    const auto& d = A.d;
+    const bool row_major = (Flags & RowMajor) != 0;
+    const Index nouter = row_major ? d.rows : d.cols;
+    Matrix<S, Dynamic, Dynamic> y(d.rows, x.cols());
+    for (Index c = 0; c < x.cols(); c++)
+    {
+        for (Index o = 0; o < nouter; o++)
+        {
+            const S xo = x.coeff(o, c);
+            S acc(0);
+            for (Index k = d.outer[o]; k < d.outer[o + 1]; k++)
+            {
+                const Index in = d.inner[k];
+                // (row, col) of the stored entry
+                const Index r = row_major ? o : in, cc = row_major ? in : o;
+                const bool in_triangle = (Uplo == Lower) ? (r >= cc) : (r <= cc);
+                if (!in_triangle)
+                    continue;
+                const S v = d.values[k];
+                if (in == o)
+                    y(o, c) += numext::real(v) * xo;
+                else
+                {
+                    // entry A(r, cc) = v and its mirror A(cc, r) = conj(v); seen from outer index o:
+                    // the entry's own row/column gets v * x(other), the mirrored one conj(v) * x(o)
+                    if (row_major)
+                    {
+                        acc += v * x.coeff(in, c);                // row o, column in
+                        y(in, c) += numext::conj(v) * xo;        // row in, column o
+                    }
+                    else
+                    {
+                        y(in, c) += v * xo;                       // row in, column o
+                        acc += numext::conj(v) * x.coeff(in, c);  // row o, column in
+                    }
+                }
+            }
+            y(o, c) += acc;
+        }
+    }
+    return y;
+}
+
+}  // namespace Eigen

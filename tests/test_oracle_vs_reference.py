@@ -1,0 +1,389 @@
+"""Pins the CPU restatement (oracle/*.hpp) on outputs of THE REFERENCE ITSELF: oracle/_ref/libspectra_ref.so is the
+reference's own headers (/root/reference/include/Spectra, compiled where they lie by `make -C oracle ref`) behind
+oracle/ref_capi.cpp, with oracle/eigen_standin in place of Eigen 3.4 (absent from this image).  The reference's
+control flow, constants and decisions are its own compiled code; only dot / axpy / gemv loops come from the
+stand-in.  Tier by tier, on identical inputs: small dense kernels, sort rules, random stream, operators,
+factorisations, complete solves (eigenvalues, eigenvectors, nconv, iteration and operation counts).
+
+Both sides are built with -ffp-contract=off here (the restatement's "strict" build, oracle/Makefile), so wherever the
+two perform the same operations in the same order the results must be EQUAL BIT FOR BIT -- and they are: every dense
+kernel, both factorisations and complete solves.  Tolerances appear only where the summation order legitimately
+differs (the symmetric operator: the reference scatters one stored triangle, the restatement sums full rows).
+CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle as O
+from oracle import ref as R
+from helpers import EXAMPLE2, cycle_laplacian, readme_banded, sym_full
+
+pytestmark = pytest.mark.skipif(not R.available(), reason="oracle/_ref is not built and /root/reference is not present")
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _strict_restatement():
+    prev = O.select_build("strict")
+    yield
+    O.select_build(prev)
+
+
+def _eq(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def _both(A_csc_lower_source, mode="lower"):
+    """The same stored matrix for the reference (as Eigen would hold it) and for the oracle."""
+    A = sp.csc_matrix(A_csc_lower_source)
+    return R.Compressed.from_scipy(A), O.Csr.from_scipy(A, mode)
+
+
+def test_reference_library_is_the_reference():
+    assert R.version().startswith("spectra 1.2.0")
+
+
+def test_simple_random_stream_identical():
+    for seed in (0, 1, 7, 2 * 5 + 123):
+        assert np.array_equal(R.simple_random(seed, 1000), O.simple_random(seed, 1000))
+
+
+def test_givens_identical_including_taylor_branch():
+    # Givens.h:166-205 + StableScaling :28-86
+    rng = np.random.default_rng(0)
+    xs = rng.standard_normal(4000)
+    ys = rng.standard_normal(4000)
+    ys[::10] = 0.0
+    xs[5::10] = 0.0
+    ys[3::7] *= 1e-9       # ratio below the 0.1 * eps^(1/4) cut-off: Taylor branch
+    xs[4::11] *= 1e-7      # ... with the roles of x and y exchanged
+    xs[1::13] *= 1e150
+    ys[2::17] *= 1e-150
+    for x, y in zip(xs, ys):
+        rr, rc, rs = R.givens(x, y)
+        orr, oc, os_ = O.givens(x, y)
+        assert (rr, rc, rs) == (orr, oc, os_)
+        assert rr >= 0 and abs(rc * x - rs * y - rr) <= 1e-12 * max(1.0, abs(rr))  # test/Givens.cpp:82-95
+
+
+@pytest.mark.parametrize("m", [2, 3, 10, 31, 60, 100])
+def test_dense_kernels_bit_identical_to_reference(m):
+    rng = np.random.default_rng(m)
+    H = np.triu(rng.standard_normal((m, m)), -1)
+    d, e = rng.standard_normal(m), rng.standard_normal(m - 1)
+    Tm = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    # TridiagQR / UpperHessenbergQR: R, Q'HQ, Q (UpperHessenbergQR.h:90-140, :577-693); exact-eigenvalue shift included
+    for kind, Mx in (("tridiag", Tm), ("hess", H)):
+        for shift in (0.0, 0.3, float(np.linalg.eigvalsh(Tm)[0]) if kind == "tridiag" else -1.7):
+            for a, b in zip(R.shifted_qr(Mx, shift, kind), O.shifted_qr(Mx, shift, kind)):
+                assert _eq(a, b)
+    # DoubleShiftQR (DoubleShiftQR.h:60-380)
+    for s, t in ((0.4, 1.3), (-2.0, 5.0), (0.0, 0.0)):
+        for a, b in zip(R.double_shift_qr(H, s, t), O.double_shift_qr(H, s, t)):
+            assert _eq(a, b)
+    # TridiagEigen (TridiagEigen.h:47-210): eigenvalues in the reference's order, eigenvectors with its signs
+    for a, b in zip(R.tridiag_eigen(Tm), O.tridiag_eigen(Tm)):
+        assert _eq(a, b)
+    # UpperHessenbergSchur / UpperHessenbergEigen (UpperHessenbergSchur.h:37-420, UpperHessenbergEigen.h:45-320)
+    for a, b in zip(R.hess_schur(H), O.hess_schur(H)):
+        assert _eq(a, b)
+    (rev, rV), (oev, oV) = R.hess_eigen(H), O.hess_eigen(H)
+    assert _eq(rev, oev) and _eq(rV, oV)
+    assert np.abs(H @ rV - rV * rev).max() <= 1e-12 * m  # test/Eigen.cpp:47-56
+
+
+def test_restart_chain_bit_identical_to_reference():
+    # the sequence HermEigsBase::restart runs (:105-147): one TridiagQR per unwanted Ritz value, largest shift first,
+    # H <- Q'HQ each time, Q accumulated by apply_YQ
+    m, k = 30, 12
+    rng = np.random.default_rng(5)
+    d, e = rng.standard_normal(m), np.abs(rng.standard_normal(m - 1))
+    Hr = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    Ho = Hr.copy()
+    shifts = sorted(np.linalg.eigvalsh(Hr)[: m - k], key=lambda v: -abs(v))
+    Qr, Qo = np.eye(m), np.eye(m)
+    for sft in shifts:
+        _, Hr, q = R.shifted_qr(Hr, sft, "tridiag")
+        Qr = Qr @ q
+        _, Ho, q = O.shifted_qr(Ho, sft, "tridiag")
+        Qo = Qo @ q
+    assert _eq(Hr, Ho) and _eq(Qr, Qo)
+
+
+def test_dense_kernels_degenerate_inputs_match_reference():
+    # deflated tridiagonals, zero matrix, repeated eigenvalues: the branches the restart hits on converged pairs
+    m = 12
+    for Tm in (np.zeros((m, m)), np.eye(m) * 3.0, np.diag(np.arange(1.0, m + 1)),
+               np.diag(np.ones(m)) + np.diag(np.r_[np.ones(5), 0, np.ones(5)] * 1e-300, 1) + np.diag(np.r_[np.ones(5), 0, np.ones(5)] * 1e-300, -1)):
+        (rv, rz), (ov, oz) = R.tridiag_eigen(Tm), O.tridiag_eigen(Tm)
+        assert np.array_equal(rv, ov) and np.array_equal(rz, oz)
+        for a, b in zip(R.shifted_qr(Tm, 1.0, "tridiag"), O.shifted_qr(Tm, 1.0, "tridiag")):
+            assert np.abs(a - b).max() <= 1e-15
+
+
+def test_sort_rules_identical():
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal(50)
+    v[10] = v[20]  # ties
+    for rule in (O.LargestMagn, O.LargestAlge, O.SmallestMagn, O.SmallestAlge, O.BothEnds):
+        assert list(R.argsort(rule, v)) == list(O.argsort(rule, v))
+    z = rng.standard_normal(40) + 1j * rng.standard_normal(40)
+    z[1::2] = np.conj(z[0::2])
+    lib = O.lib()
+    for rule in (O.LargestMagn, O.LargestReal, O.LargestImag, O.SmallestMagn, O.SmallestReal, O.SmallestImag):
+        ind = np.empty(z.size, dtype=np.int64)
+        zz = np.ascontiguousarray(z)
+        assert lib.oracle_argsort_complex(int(rule), zz.ctypes.data_as(O.C.c_void_p), O.C.c_int64(z.size), ind.ctypes.data_as(O.C.c_void_p)) == 0
+        assert list(R.argsort(rule, z)) == list(ind)
+    with pytest.raises(O.OracleError):
+        R.argsort(O.LargestReal, v)  # SelectionRule.h: unsupported rule for real values
+
+
+@pytest.mark.parametrize("order", ["col", "row"])
+@pytest.mark.parametrize("uplo", ["lower", "upper"])
+def test_sym_operator_matches_reference(order, uplo):
+    # SparseSymMatProd<double, Uplo, Flags>::perform_op reads ONE triangle of whatever is stored (:83-88)
+    n = 300
+    A = sp.random(n, n, 0.05, random_state=5, format="csc") + sp.diags(np.arange(n, dtype=float))
+    A = A.tocsr() if order == "row" else A.tocsc()
+    x = np.random.default_rng(1).standard_normal(n)
+    y_ref = R.spmv(R.Compressed.from_scipy(A), x, sym=True, uplo=uplo)
+    op = O.Csr(n, A.indptr, A.indices, A.data, order=order, mode=uplo)
+    assert np.abs(y_ref - op.spmv(x)).max() <= 1e-13 * np.abs(y_ref).max()
+    T = sp.tril(A) if uplo == "lower" else sp.triu(A)
+    dense = (T + T.T - sp.diags(A.diagonal())).toarray()
+    assert np.abs(y_ref - dense @ x).max() <= 1e-13 * np.abs(y_ref).max()
+
+
+@pytest.mark.parametrize("order", ["col", "row"])
+def test_gen_operator_matches_reference(order):
+    n = 300
+    A = sp.random(n, n, 0.05, random_state=6, format="csc")
+    A = A.tocsr() if order == "row" else A.tocsc()
+    x = np.random.default_rng(2).standard_normal(n)
+    y_ref = R.spmv(R.Compressed.from_scipy(A), x)
+    op = O.Csr(n, A.indptr, A.indices, A.data, order=order, mode="gen")
+    assert np.abs(y_ref - op.spmv(x)).max() <= 1e-13 * np.abs(y_ref).max()
+    assert R.coeff(R.Compressed.from_scipy(A), 3, 7) == A[3, 7]
+
+
+@pytest.mark.parametrize("kind", ["lanczos", "arnoldi"])
+@pytest.mark.parametrize("n,m,mid", [(10, 6, 3), (500, 30, 11)])
+def test_factorization_matches_reference(kind, n, m, mid):
+    # test/Arnoldi.cpp flow: init, factorize_from(1, mid), factorize_from(mid, m)
+    rng = np.random.default_rng(n)
+    M = sp.random(n, n, min(1.0, 20.0 / n), random_state=n, format="csc") + sp.diags(rng.standard_normal(n))
+    if kind == "lanczos":
+        M = sym_full(M).tocsc()
+    v0 = rng.standard_normal(n)
+    rc, oc = _both(M, "lower" if kind == "lanczos" else "gen")
+    V, H, f, beta, nops = R.factorize(rc, m, v0=v0, mid=mid, kind=kind)
+    fz = O.factorize(oc, m, v0=v0, mid=mid, kind=kind)
+    assert nops == fz["nops"]
+    assert np.abs(H - fz["H"]).max() <= 1e-11 * max(1.0, np.abs(H).max())
+    assert np.abs(V - fz["V"]).max() <= 1e-9 and np.abs(f - fz["f"]).max() <= 1e-9 * max(1.0, beta)
+    assert abs(beta - fz["beta"]) <= 1e-10 * max(1.0, beta)
+    Md = M.toarray()
+    E = Md @ V - V @ H
+    E[:, -1] -= f
+    assert np.abs(E).max() <= 1e-12 * max(1.0, np.abs(Md).max()) and np.abs(V.T @ V - np.eye(m)).max() <= 1e-12
+    if kind == "arnoldi":
+        # stored row-major with ascending columns, the reference's product sums each row exactly as the restatement does:
+        # the whole factorisation is then bit-identical
+        Mr = sp.csr_matrix(M)
+        Mr.sort_indices()
+        V2, H2, f2, beta2, nops2 = R.factorize(R.Compressed.from_scipy(Mr), m, v0=v0, mid=mid, kind=kind)
+        assert nops2 == fz["nops"] and _eq(V2, fz["V"]) and _eq(H2, fz["H"]) and _eq(f2, fz["f"]) and beta2 == fz["beta"]
+
+
+def _assert_same_solve(r, o, tol=1e-12, vec_tol=1e-8):
+    """Different operator summation orders: same outcome, histories equal up to a few restarts on long runs."""
+    assert (r.info, r.nconv) == (o.info, o.nconv)
+    assert abs(r.niter - o.niter) <= max(0, o.niter // 30) and abs(r.nops - o.nops) <= max(0, o.nops // 30)
+    scale = max(1.0, float(np.abs(r.eigenvalues).max())) if r.nconv else 1.0
+    assert np.abs(r.eigenvalues - o.eigenvalues).max() <= tol * scale if r.nconv else True
+    if r.eigenvectors is not None and o.eigenvectors is not None and r.nconv:
+        # same sign convention: both follow the same rotations from the same start vector
+        assert np.abs(r.eigenvectors - o.eigenvectors).max() <= vec_tol
+
+
+def _assert_bit_identical_solve(r, o):
+    assert (r.info, r.nconv, r.niter, r.nops) == (o.info, o.nconv, o.niter, o.nops)
+    assert _eq(r.eigenvalues, o.eigenvalues)
+    if r.nconv:
+        assert _eq(r.eigenvectors, o.eigenvectors)
+
+
+def test_readme_diag_kat_reference():
+    # SymEigsSolver.h:99-126 with a user-defined OpType: the same operator bits on both sides
+    n = 10
+    r = R.sym_eigs_userop(n, lambda x: x * np.arange(1, n + 1), 3, 6, selection=O.LargestAlge)
+    o = O.sym_eigs_userop(n, lambda x: x * np.arange(1, n + 1), 3, 6, selection=O.LargestAlge)
+    assert np.allclose(r.eigenvalues, [10, 9, 8], atol=1e-10)
+    _assert_bit_identical_solve(r, o)
+
+
+@pytest.mark.parametrize("k,m", [(3, 6), (5, 12), (6, 12)])
+def test_example1_cycle_laplacian_reference(k, m):
+    # test/Example1.cpp:98-129 (issue #144): every eigenvalue but two is double.  In exact arithmetic Lanczos from one start
+    # vector sees each distinct eigenvalue once; the second copies enter through rounding errors of the operator, so the
+    # outcome depends on the operator's summation order.  With ONE operator on both sides (the dense y = M x the reference's
+    # test uses) the reference and the restatement agree bit for bit and find the copies the reference's test asks for.
+    M = cycle_laplacian(20)
+    true = np.linalg.eigvalsh(M)
+    fn = lambda x: M @ x  # noqa: E731
+    r = R.sym_eigs_userop(20, fn, k, m, O.LargestMagn, 1000, 1e-15, O.SmallestAlge)
+    o = O.sym_eigs_userop(20, fn, k, m, O.LargestMagn, 1000, 1e-15, O.SmallestAlge)
+    assert r.info == O.Successful
+    _assert_bit_identical_solve(r, o)
+    assert np.abs(M @ r.eigenvectors - r.eigenvectors * r.eigenvalues).max() <= 1e-9
+    assert np.abs(true[-k:] - r.eigenvalues).max() <= 1e-9
+    # through the sparse operators (one stored triangle scattered vs full rows summed) both must still return converged
+    # eigenpairs of M; which copies of a double eigenvalue they hold is not determined
+    rc, oc = _both(sp.csc_matrix(M))
+    for res in (R.sym_eigs(rc, k, m, O.LargestMagn, 1000, 1e-15, O.SmallestAlge), O.sym_eigs(oc, k, m, O.LargestMagn, 1000, 1e-15, O.SmallestAlge)):
+        assert res.info == O.Successful and res.nconv == k
+        assert np.abs(M @ res.eigenvectors - res.eigenvectors * res.eigenvalues).max() <= 1e-9
+        assert all(np.abs(true - ev).min() <= 1e-9 for ev in res.eigenvalues)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_example2_near_rank_one_reference(idx):
+    M = EXAMPLE2[idx]
+    rc, oc = _both(sp.csc_matrix(M))
+    r, o = R.sym_eigs(rc, 1, 3, O.LargestMagn), O.sym_eigs(oc, 1, 3, O.LargestMagn)
+    assert r.info == O.Successful
+    _assert_same_solve(r, o, tol=1e-11)
+
+
+def test_example4_zero_matrix_and_null_init_reference():
+    n = 100
+    rng = np.random.default_rng(123)
+    v0 = rng.uniform(-1, 1, n)
+    Z = sp.csc_matrix((n, n))
+    r = R.sym_eigs(R.Compressed.from_scipy(Z), 3, 6, O.LargestAlge, init_resid=v0)
+    o = O.sym_eigs(O.Csr.from_scipy(Z, "lower"), 3, 6, O.LargestAlge, init_resid=v0)
+    assert r.info == O.Successful and np.abs(r.eigenvalues).max() <= 1e-8
+    assert (r.info, r.nconv, r.niter, r.nops) == (o.info, o.nconv, o.niter, o.nops)
+    U = rng.uniform(-1, 1, (n, n))
+    w, Q = np.linalg.eigh(U + U.T)
+    w[-1] = 0.0
+    A = (Q * w) @ Q.T
+    A = (A + A.T) / 2
+    rc, oc = _both(sp.csc_matrix(A))
+    r = R.sym_eigs(rc, 3, 6, O.LargestAlge, init_resid=Q[:, -1].copy())
+    o = O.sym_eigs(oc, 3, 6, O.LargestAlge, init_resid=Q[:, -1].copy())
+    assert r.info == O.Successful
+    assert (r.info, r.nconv) == (o.info, o.nconv) and abs(r.nops - o.nops) <= 12
+    assert np.abs(r.eigenvalues - o.eigenvalues).max() <= 1e-9
+
+
+SYM_CASES = [(10, 0.5, 3, 6), (100, 0.1, 10, 20), (1000, 0.01, 20, 50)]
+
+
+@pytest.mark.parametrize("n,prob,k,m", SYM_CASES)
+@pytest.mark.parametrize("rule", [O.LargestMagn, O.LargestAlge, O.SmallestMagn, O.SmallestAlge, O.BothEnds])
+def test_sym_eigs_reference_cases_same_history(n, prob, k, m, rule):
+    # test/SymEigs.cpp:133-167 fixtures (gen_sparse_data): reference vs restatement, complete solve
+    if n == 1000 and rule == O.SmallestMagn:
+        pytest.skip("interior eigenvalues of the n=1000 case need ~23k matvecs; covered at n<=100")
+    A = O.gen_sparse_data(n, prob)
+    rc, oc = _both(A)
+    r, o = R.sym_eigs(rc, k, m, rule), O.sym_eigs(oc, k, m, rule)
+    assert r.info == O.Successful and r.nconv == k
+    Af = sym_full(A)
+    assert np.abs(Af @ r.eigenvectors - r.eigenvectors * r.eigenvalues).max() <= 1e-9  # the reference's own threshold
+    _assert_same_solve(r, o)
+    # with ONE operator on both sides (a user-defined OpType computing y = A x) the complete solve -- every Lanczos step,
+    # every restart, eigenvalues AND eigenvectors -- is bit-identical between the reference and the restatement
+    fn = lambda x: Af @ x  # noqa: E731
+    r2, o2 = R.sym_eigs_userop(n, fn, k, m, selection=rule), O.sym_eigs_userop(n, fn, k, m, selection=rule)
+    assert r2.info == O.Successful
+    _assert_bit_identical_solve(r2, o2)
+
+
+GEN_CASES = [(10, 0.5, 3, 6), (100, 0.1, 10, 30), (1000, 0.01, 20, 50)]
+
+
+@pytest.mark.parametrize("n,prob,k,m", GEN_CASES)
+@pytest.mark.parametrize("rule", [O.LargestMagn, O.LargestReal, O.LargestImag, O.SmallestMagn, O.SmallestReal, O.SmallestImag])
+def test_gen_eigs_reference_cases_same_history(n, prob, k, m, rule):
+    # test/GenEigs.cpp:38-107,143-174: maxit = 300; SmallestMagn / SmallestImag are allowed to fail there --
+    # reference and restatement must then fail the same way
+    A = sp.csr_matrix(O.gen_sparse_data(n, prob))
+    A.sort_indices()
+    # stored row-major with ascending columns the reference's product (SparseGenMatProd.h:86) sums each row exactly as the
+    # restatement's does, so the complete Arnoldi solve is bit-identical -- failures included
+    r = R.gen_eigs(R.Compressed.from_scipy(A), k, m, rule, 300)
+    o = O.gen_eigs(O.Csr(n, A.indptr, A.indices, A.data, order="row", mode="gen"), k, m, rule, 300)
+    _assert_bit_identical_solve(r, o)
+    if r.info == O.Successful:
+        assert np.abs(A @ r.eigenvectors - r.eigenvectors * r.eigenvalues).max() <= 1e-9
+    else:
+        assert rule in (O.SmallestMagn, O.SmallestImag)  # the rules test/GenEigs.cpp:143-174 allows to fail
+    # column-major storage: same matrix, the reference scatters columns -- a different summation order, same answer
+    rc = R.gen_eigs(R.Compressed.from_scipy(A.tocsc()), k, m, rule, 300)
+    assert (rc.info, rc.nconv) == (r.info, r.nconv)
+    if rule in (O.LargestMagn, O.LargestReal, O.SmallestReal) and rc.nconv:
+        assert np.abs(np.sort_complex(rc.eigenvalues) - np.sort_complex(r.eigenvalues)).max() <= 1e-10 * max(1.0, np.abs(r.eigenvalues).max())
+
+
+def test_readme_banded_nonsymmetric_reference():
+    M = sp.csr_matrix(readme_banded(10))
+    M.sort_indices()
+    r = R.gen_eigs(R.Compressed.from_scipy(M), 3, 6, O.LargestMagn)
+    o = O.gen_eigs(O.Csr(10, M.indptr, M.indices, M.data, order="row", mode="gen"), 3, 6, O.LargestMagn)
+    assert r.info == O.Successful
+    _assert_bit_identical_solve(r, o)
+
+
+def test_argument_checks_reference():
+    A = R.Compressed.from_scipy(sp.identity(10, format="csc"))
+    for nev, ncv in [(0, 5), (10, 12), (3, 3), (3, 11)]:
+        with pytest.raises(O.OracleError) as e:
+            R.sym_eigs(A, nev, ncv)
+        assert e.value.code == 1  # std::invalid_argument (HermEigsBase.h:267-271)
+    with pytest.raises(O.OracleError) as e:
+        R.sym_eigs(A, 3, 6, init_resid=np.zeros(10))
+    assert e.value.code == 1  # Arnoldi.h:147-148
+    for nev, ncv in [(0, 5), (9, 10), (3, 4), (3, 11)]:
+        with pytest.raises(O.OracleError) as e:
+            R.gen_eigs(A, nev, ncv)
+        assert e.value.code == 1  # GenEigsBase.h:390-394
+
+
+def test_mid_size_synthetic_same_history():
+    # the BASELINE matrix family (G_sym: 20 nnz/row, uniform columns) at n = 5e4
+    from spectra_b200 import synth  # the host-side synthetic-matrix generator only (plain C, no device code)
+
+    n = 50_000
+    A = synth.scipy_csr(n, 20, seed=7, sym=True).tocsc()
+    rc, oc = _both(A)
+    r = R.sym_eigs(rc, 10, 30, O.LargestAlge, want_vectors=False)
+    o = O.sym_eigs(oc, 10, 30, O.LargestAlge, want_vectors=False)
+    assert r.info == O.Successful
+    assert (r.nconv, r.niter, r.nops) == (o.nconv, o.niter, o.nops)
+    assert np.abs(r.eigenvalues - o.eigenvalues).max() <= 1e-11 * np.abs(r.eigenvalues).max()
+
+
+@pytest.mark.parametrize("cfg", ["C2", "C3"])
+def test_full_size_reference_results_agree_with_oracle(cfg):
+    # committed outputs of complete BASELINE solves: the reference (tests/golden/reference_*.json, written by
+    # make_reference_golden.py) next to the restatement (baseline_*.json, make_baseline_golden.py)
+    ref_path = os.path.join(GOLDEN, f"reference_{cfg}.json")
+    if not os.path.exists(ref_path):
+        pytest.skip(f"{ref_path} not generated")
+    ref = json.load(open(ref_path))
+    orc = json.load(open(os.path.join(GOLDEN, f"baseline_{cfg}.json")))
+    assert ref["nconv"] == orc["nconv"] and ref["info"] == orc["info"]
+    if cfg == "C2":
+        rv, ov = np.array(ref["eigenvalues"]), np.array(orc["eigenvalues"])
+        assert np.abs(rv - ov).max() <= 1e-10 * np.abs(rv).max()
+        # the histories differ only through summation order (1 thread here, 8 OpenMP threads there)
+        assert abs(ref["nops"] - orc["nops"]) <= 0.05 * orc["nops"]
+    else:
+        assert ref["nops"] == orc["nops"] and ref["niter"] == orc["niter"]
