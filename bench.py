@@ -143,6 +143,23 @@ def golden_full_solves():
     return out
 
 
+def reference_own_code_sample(n, rp, ci, v, sample_ops):
+    """The same bounded sample through THE REFERENCE'S OWN CODE: oracle/_ref/libspectra_ref.so is yixuan/spectra's headers compiled in the
+    development container (`make -C oracle ref`; Eigen replaced by oracle/eigen_standin -- scalar loops, no SIMD, so real Eigen would be
+    somewhat faster on the panel products).  Single-threaded, as the reference ships.  None when the library did not travel."""
+    try:
+        from oracle import ref as R
+
+        if not os.path.exists(R._LIB_PATH) or n * 21 >= 2 ** 31:
+            return None
+        A = R.Compressed(n, np.asarray(rp, dtype=np.int32), ci, v, order="col")  # full symmetric CSR == the same matrix column-major; Lower is read
+        nops, sec = R.lanczos_sample(A, sample_ops - 1)
+        return {"value": nops / sec, "unit": "SpMV-iters/s", "cores": 1, "kind": "reference", "library": R.version(),
+                "sample": f"Lanczos::init + first {nops - 2} steps of Lanczos::factorize_from over SparseSymMatProd<double> (the head of the n={n} solve), {sec:.1f} s"}
+    except Exception as e:  # noqa: BLE001 -- an optional extra arm must not break the line
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def run_reference(args, n):
     """The reference algorithm (CPU restatement in oracle/) on bounded samples of the workload: once single-threaded -- what the
     reference, a single-threaded header library, does as shipped -- and once with the fastest OpenMP team of this host.  `value` is the
@@ -180,6 +197,7 @@ def run_reference(args, n):
     ops, sec = sample(threads, args.steps, args.warmup)
     ops1, sec1 = sample(1, 1, 0)
     value = ops / sec
+    ref_own = reference_own_code_sample(n, rp, ci, v, args.cpu_sample_ops)
     what = (f"init + first {ops - 2} Lanczos steps (op_limit={args.cpu_sample_ops}) of the n={n} solve, {threads} OpenMP threads "
             f"(fastest team of {cands} on the SpMV; {avail} hardware threads available, OMP_NUM_THREADS ignored)")
     line = {
@@ -188,6 +206,8 @@ def run_reference(args, n):
         "config": workload_config(args, n),
         "cpu_baseline": {"value": value, "unit": "SpMV-iters/s", "cores": threads, "kind": "port", "sample": what,
                          "single_thread_value": ops1 / sec1, "single_thread_note": "the reference as shipped is single-threaded; same sample, 1 thread",
+                         "reference_own_code": ref_own,
+                         "value_is": "the fastest CPU arm measured here (the OpenMP port): the conservative denominator for GPU/CPU ratios",
                          "spmv_seconds_by_team": {str(k): round(val, 4) for k, val in calib.items()},
                          "full_solves_cached": golden_full_solves()},
         "e2e": {"value": value, "unit": "SpMV-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -434,6 +454,7 @@ def main():
         cpu = {"value": r.nops / r.seconds, "unit": "SpMV-iters/s", "cores": 1, "kind": "port",
                "sample": f"init + first {r.nops - 2} Lanczos steps (op_limit={args.cpu_sample_ops}) of the same n={n} solve, {r.seconds:.1f} s; early steps have "
                          f"narrow panels, so this over-states the CPU's steady-state rate", "host_cores_available": host_threads(),
+               "reference_own_code": reference_own_code_sample(n, rp, ci, v, args.cpu_sample_ops),
                "full_solves_cached": golden_full_solves()}
 
     # ---- the other BASELINE configurations on one GPU (C2, C3, C5): one solve each after a warm-up solve, device time; parity of

@@ -198,8 +198,18 @@ def factorize(A: Compressed, m: int, v0=None, mid=None, kind="lanczos"):
     nops = C.c_int64()
     v0a = _f64(v0) if v0 is not None else None
     _check(lib().ref_factorize(0 if kind == "lanczos" else 1, A.order, C.byref(A.c), C.c_int64(m), _p(v0a), C.c_int64(mid), _p(V), _p(H), _p(f),
-                               C.byref(beta), C.byref(nops)))
+                               C.byref(beta), C.byref(nops), None))
     return V, H, f, beta.value, nops.value
+
+
+def lanczos_sample(A: Compressed, m: int):
+    """init() + the first m - 1 steps of Lanczos::factorize_from on SparseSymMatProd<double> from the default SimpleRandom(0) residual -- the
+    head of a SymEigsSolver solve -- timed inside the library.  Returns (operator applications, seconds)."""
+    beta = C.c_double()
+    nops = C.c_int64()
+    sec = C.c_double()
+    _check(lib().ref_factorize(0, A.order, C.byref(A.c), C.c_int64(m), None, C.c_int64(m), None, None, None, C.byref(beta), C.byref(nops), C.byref(sec)))
+    return nops.value, sec.value
 
 
 def sym_eigs(A: Compressed, nev, ncv, selection=0, maxit=1000, tol=1e-10, sorting=3, init_resid=None, uplo="lower", want_vectors=True) -> EigsResult:
