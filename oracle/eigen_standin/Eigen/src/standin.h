@@ -7,7 +7,7 @@
 //
 // What this is: eager (no expression templates) column-major dense matrices, strided views for
 // Map / Ref / Block, the Jacobi / Householder primitives restated from Eigen 3.4.0's published
-// definitions (Jacobi.h makeGivens, Householder.h makeHouseholder, MathFunctions.h hypot), and a
+// definitions (Jacobi.h makeGivens, Householder.h makeHouseholder, MathFunctions.h hypot, ComplexSchur.h), and a
 // compressed sparse matrix with the two products the reference calls.  Everything the reference
 // decides -- every branch, shift, deflation test, restart rule, iteration count -- is the
 // reference's own compiled code; only the BLAS-level loops (dot, axpy, gemv, small gemm) and their
@@ -195,8 +195,68 @@ public:
     JacobiRotation adjoint() const { return JacobiRotation(numext::conj(m_c), -m_s); }
     JacobiRotation transpose() const { return JacobiRotation(m_c, -numext::conj(m_s)); }
 
+    void makeGivens(const S& p, const S& q, S* r = nullptr) { make_givens_(p, q, r, std::integral_constant<bool, NumTraits<S>::IsComplex != 0>()); }
+
+private:
+    // Eigen 3.4.0 Jacobi.h, makeGivens(p, q, r, true_type): complex scalars (used by ComplexSchur)
+    void make_givens_(const S& p, const S& q, S* r, std::true_type)
+    {
+        using std::abs;
+        using std::sqrt;
+        using RealScalar = typename NumTraits<S>::Real;
+        if (q == S(0))
+        {
+            m_c = numext::real(p) < 0 ? S(-1) : S(1);
+            m_s = 0;
+            if (r)
+                *r = m_c * p;
+        }
+        else if (p == S(0))
+        {
+            m_c = 0;
+            m_s = -q / abs(q);
+            if (r)
+                *r = abs(q);
+        }
+        else
+        {
+            RealScalar p1 = numext::norm1(p);
+            RealScalar q1 = numext::norm1(q);
+            if (p1 >= q1)
+            {
+                S ps = p / p1;
+                RealScalar p2 = numext::abs2(ps);
+                S qs = q / p1;
+                RealScalar q2 = numext::abs2(qs);
+                RealScalar u = sqrt(RealScalar(1) + q2 / p2);
+                if (numext::real(p) < RealScalar(0))
+                    u = -u;
+                m_c = S(1) / u;
+                m_s = -qs * numext::conj(ps) * (m_c / p2);
+                if (r)
+                    *r = p * u;
+            }
+            else
+            {
+                S ps = p / q1;
+                RealScalar p2 = numext::abs2(ps);
+                S qs = q / q1;
+                RealScalar q2 = numext::abs2(qs);
+                RealScalar u = q1 * sqrt(p2 + q2);
+                if (numext::real(p) < RealScalar(0))
+                    u = -u;
+                p1 = abs(p);
+                ps = p / p1;
+                m_c = p1 / u;
+                m_s = -numext::conj(ps) * (q / u);
+                if (r)
+                    *r = ps * u;
+            }
+        }
+    }
+
     // Eigen 3.4.0 Jacobi.h, makeGivens(p, q, r, false_type): real scalars
-    void makeGivens(const S& p, const S& q, S* r = nullptr)
+    void make_givens_(const S& p, const S& q, S* r, std::false_type)
     {
         using std::abs;
         using std::sqrt;
@@ -1111,10 +1171,120 @@ Array<S, R, C>::Array(const ArrayRef<S>& r) : m_a(static_cast<size_t>(r.size()))
         m_a[static_cast<size_t>(i)] = r[i];
 }
 
-// Declared only: the complex specialisation of UpperHessenbergEigen (UpperHessenbergEigen.h:328-454)
-// names it as a member type; that specialisation is not instantiated by oracle/_ref.
+// Eigen::ComplexSchur, the part UpperHessenbergEigen<std::complex<T>> uses (UpperHessenbergEigen.h:328-454):
+// computeFromHessenberg -> reduceToTriangularForm.  Restated from Eigen 3.4.0's published ComplexSchur.h:
+// deflation test |T(i+1,i)|_1 <= eps (|T(i,i)|_1 + |T(i+1,i+1)|_1), Wilkinson-type shift from the trailing 2x2
+// block, EISPACK comqr exceptional shifts at iterations 10 and 20, at most 30 iterations per row.
 template <typename MatrixType>
-class ComplexSchur;
+class ComplexSchur
+{
+public:
+    using ComplexScalar = typename MatrixType::Scalar;
+    using RealScalar = typename NumTraits<ComplexScalar>::Real;
+    using ComplexMatrixType = Matrix<ComplexScalar, Dynamic, Dynamic>;
+
+    ComplexSchur() : m_info(Success) {}
+
+    template <typename HessMatrixType, typename OrthMatrixType>
+    ComplexSchur& computeFromHessenberg(const HessMatrixType& matrixH, const OrthMatrixType& matrixQ, bool computeU = true)
+    {
+        m_matT = matrixH;
+        if (computeU)
+            m_matU = matrixQ;
+        reduceToTriangularForm(computeU);
+        return *this;
+    }
+    const ComplexMatrixType& matrixT() const { return m_matT; }
+    const ComplexMatrixType& matrixU() const { return m_matU; }
+    ComputationInfo info() const { return m_info; }
+
+private:
+    ComplexMatrixType m_matT, m_matU;
+    ComputationInfo m_info;
+
+    bool subdiagonalEntryIsNeglegible(Index i)
+    {
+        RealScalar d = numext::norm1(m_matT.coeff(i, i)) + numext::norm1(m_matT.coeff(i + 1, i + 1));
+        RealScalar sd = numext::norm1(m_matT.coeff(i + 1, i));
+        if (std::abs(sd) <= std::abs(d) * NumTraits<RealScalar>::epsilon())  // internal::isMuchSmallerThan
+        {
+            m_matT.coeffRef(i + 1, i) = ComplexScalar(0);
+            return true;
+        }
+        return false;
+    }
+
+    ComplexScalar computeShift(Index iu, Index iter)
+    {
+        using std::abs;
+        if (iter == 10 || iter == 20)
+            return abs(numext::real(m_matT.coeff(iu, iu - 1))) + abs(numext::real(m_matT.coeff(iu - 1, iu - 2)));
+        Matrix<ComplexScalar, 2, 2> t = m_matT.template block<2, 2>(iu - 1, iu - 1);
+        RealScalar normt = t.cwiseAbs().sum();
+        t /= normt;
+        ComplexScalar b = t.coeff(0, 1) * t.coeff(1, 0);
+        ComplexScalar c = t.coeff(0, 0) - t.coeff(1, 1);
+        ComplexScalar disc = std::sqrt(c * c + RealScalar(4) * b);
+        ComplexScalar det = t.coeff(0, 0) * t.coeff(1, 1) - b;
+        ComplexScalar trace = t.coeff(0, 0) + t.coeff(1, 1);
+        ComplexScalar eival1 = (trace + disc) / RealScalar(2);
+        ComplexScalar eival2 = (trace - disc) / RealScalar(2);
+        RealScalar eival1_norm = numext::norm1(eival1);
+        RealScalar eival2_norm = numext::norm1(eival2);
+        if (eival1_norm > eival2_norm)
+            eival2 = det / eival1;
+        else if (eival2_norm != RealScalar(0))
+            eival1 = det / eival2;
+        if (numext::norm1(eival1 - t.coeff(1, 1)) < numext::norm1(eival2 - t.coeff(1, 1)))
+            return normt * eival1;
+        return normt * eival2;
+    }
+
+    void reduceToTriangularForm(bool computeU)
+    {
+        const Index maxIterations = 30 * m_matT.rows();
+        Index iu = m_matT.cols() - 1;
+        Index il;
+        Index iter = 0;
+        Index totalIter = 0;
+        while (true)
+        {
+            while (iu > 0)
+            {
+                if (!subdiagonalEntryIsNeglegible(iu - 1))
+                    break;
+                iter = 0;
+                --iu;
+            }
+            if (iu == 0)
+                break;
+            iter++;
+            totalIter++;
+            if (totalIter > maxIterations)
+                break;
+            il = iu - 1;
+            while (il > 0 && !subdiagonalEntryIsNeglegible(il - 1))
+                --il;
+            ComplexScalar shift = computeShift(iu, iter);
+            JacobiRotation<ComplexScalar> rot;
+            rot.makeGivens(m_matT.coeff(il, il) - shift, m_matT.coeff(il + 1, il));
+            m_matT.rightCols(m_matT.cols() - il).applyOnTheLeft(il, il + 1, rot.adjoint());
+            m_matT.topRows((std::min)(il + 2, iu) + 1).applyOnTheRight(il, il + 1, rot);
+            if (computeU)
+                m_matU.applyOnTheRight(il, il + 1, rot);
+            for (Index i = il + 1; i < iu; i++)
+            {
+                rot.makeGivens(m_matT.coeffRef(i, i - 1), m_matT.coeffRef(i + 1, i - 1), &m_matT.coeffRef(i, i - 1));
+                m_matT.coeffRef(i + 1, i - 1) = ComplexScalar(0);
+                m_matT.rightCols(m_matT.cols() - i).applyOnTheLeft(i, i + 1, rot.adjoint());  // column i - 1 already holds (r, 0)
+                m_matT.topRows((std::min)(i + 2, iu) + 1).applyOnTheRight(i, i + 1, rot);
+                if (computeU)
+                    m_matU.applyOnTheRight(i, i + 1, rot);
+            }
+        }
+        m_info = (totalIter <= maxIterations) ? Success : NoConvergence;
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // SparseCore subset: compressed storage + the two products of MatOp/Sparse{Sym,Gen}MatProd.h

@@ -262,3 +262,150 @@ def gen_eigs(A: Compressed, nev, ncv, selection=0, maxit=1000, tol=1e-10, sortin
     vec = evecs.view(np.complex128)[: n * nconv].reshape((n, nconv), order="F").copy() if want_vectors and nconv else None
     return EigsResult(nconv=nconv, niter=int(res.niter), nops=int(res.nops), info=int(res.info), eigenvalues=ev, eigenvectors=vec,
                       reorth_passes=-1, expand_calls=-1, restarts=-1, steps=-1, seconds=float(res.seconds))
+
+
+# ---------------------------------------------------------------- complex Hermitian path (HermEigsSolver + SparseHermMatProd)
+class CompressedZ:
+    """Column-major compressed complex matrix (Eigen::SparseMatrix<std::complex<double>>), values interleaved (re, im)."""
+
+    def __init__(self, A):
+        import scipy.sparse as sp
+
+        A = sp.csc_matrix(A)
+        self.n = int(A.shape[0])
+        self.outer = np.ascontiguousarray(A.indptr, dtype=np.int32)
+        self.inner = np.ascontiguousarray(A.indices, dtype=np.int32)
+        self.val = np.ascontiguousarray(A.data, dtype=np.complex128)
+        self.c = _Compressed(self.n, self.val.size, self.outer.ctypes.data, self.inner.ctypes.data, self.val.ctypes.data)
+
+
+def simple_random_complex(seed: int, n: int) -> np.ndarray:
+    out = np.empty(n, dtype=np.complex128)
+    lib().ref_simple_random_complex(C.c_uint64(seed), C.c_int64(n), _p(out))
+    return out
+
+
+def herm_spmv(A: CompressedZ, x, uplo="lower"):
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    y = np.empty(A.n, dtype=np.complex128)
+    _check(lib().ref_herm_spmv(0 if uplo == "lower" else 1, C.byref(A.c), _p(x), _p(y)))
+    return y
+
+
+def _herm_result(res, evals, evecs, n):
+    nconv = int(res.nconv)
+    vec = evecs[: n * nconv].reshape((n, nconv), order="F").copy() if nconv else None
+    return EigsResult(nconv=nconv, niter=int(res.niter), nops=int(res.nops), info=int(res.info), eigenvalues=evals[:nconv].copy(), eigenvectors=vec,
+                      reorth_passes=-1, expand_calls=-1, restarts=-1, steps=-1, seconds=float(res.seconds))
+
+
+def herm_eigs(A: CompressedZ, nev, ncv, selection=0, maxit=1000, tol=1e-10, sorting=3, init_resid=None, uplo="lower") -> EigsResult:
+    """HermEigsSolver<SparseHermMatProd<std::complex<double>, Uplo>>."""
+    res = _RefResult()
+    evals = np.zeros(nev)
+    evecs = np.zeros(A.n * nev, dtype=np.complex128)
+    r0 = np.ascontiguousarray(init_resid, dtype=np.complex128) if init_resid is not None else None
+    _check(lib().ref_herm_eigs(0 if uplo == "lower" else 1, C.byref(A.c), C.c_int64(nev), C.c_int64(ncv), int(selection), C.c_int64(maxit), C.c_double(tol),
+                               int(sorting), _p(r0), _p(evals), _p(evecs), C.byref(res)))
+    return _herm_result(res, evals, evecs, A.n)
+
+
+def herm_eigs_userop(n, fn, nev, ncv, selection=0, maxit=1000, tol=1e-10, sorting=3, init_resid=None) -> EigsResult:
+    """HermEigsSolver over a user-defined complex OpType: fn maps a complex vector to a complex vector."""
+    CB = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+
+    def tramp(xp, yp, _):
+        x = np.ctypeslib.as_array(xp, shape=(2 * n,)).view(np.complex128)
+        y = np.ctypeslib.as_array(yp, shape=(2 * n,)).view(np.complex128)
+        y[:] = fn(x)
+
+    cb = CB(tramp)
+    res = _RefResult()
+    evals = np.zeros(nev)
+    evecs = np.zeros(n * nev, dtype=np.complex128)
+    r0 = np.ascontiguousarray(init_resid, dtype=np.complex128) if init_resid is not None else None
+    _check(lib().ref_herm_eigs_userop(C.c_int64(n), cb, None, C.c_int64(nev), C.c_int64(ncv), int(selection), C.c_int64(maxit), C.c_double(tol), int(sorting),
+                                      _p(r0), _p(evals), _p(evecs), C.byref(res)))
+    return _herm_result(res, evals, evecs, n)
+
+
+# ---------------------------------------------------------------- complex general path (GenEigsSolver with a complex Scalar)
+class CompressedZG(CompressedZ):
+    """Complex compressed matrix, column-major (default) or row-major as given."""
+
+    def __init__(self, A):
+        import scipy.sparse as sp
+
+        if sp.isspmatrix_csr(A):
+            self.order = 1
+            self.n = int(A.shape[0])
+            self.outer = np.ascontiguousarray(A.indptr, dtype=np.int32)
+            self.inner = np.ascontiguousarray(A.indices, dtype=np.int32)
+            self.val = np.ascontiguousarray(A.data, dtype=np.complex128)
+            self.c = _Compressed(self.n, self.val.size, self.outer.ctypes.data, self.inner.ctypes.data, self.val.ctypes.data)
+        else:
+            super().__init__(A)
+            self.order = 0
+
+
+def _genz_result(res, evals, evecs, n):
+    nconv = int(res.nconv)
+    ev = evals.view(np.complex128)[:nconv].copy()
+    vec = evecs[: n * nconv].reshape((n, nconv), order="F").copy() if nconv else None
+    return EigsResult(nconv=nconv, niter=int(res.niter), nops=int(res.nops), info=int(res.info), eigenvalues=ev, eigenvectors=vec,
+                      reorth_passes=-1, expand_calls=-1, restarts=-1, steps=-1, seconds=float(res.seconds))
+
+
+def gen_eigs_complex(A: CompressedZG, nev, ncv, selection=0, maxit=1000, tol=1e-10, sorting=0, init_resid=None) -> EigsResult:
+    res = _RefResult()
+    evals = np.zeros(2 * nev)
+    evecs = np.zeros(A.n * nev, dtype=np.complex128)
+    r0 = np.ascontiguousarray(init_resid, dtype=np.complex128) if init_resid is not None else None
+    _check(lib().ref_gen_eigs_complex(A.order, C.byref(A.c), C.c_int64(nev), C.c_int64(ncv), int(selection), C.c_int64(maxit), C.c_double(tol), int(sorting),
+                                      _p(r0), _p(evals), _p(evecs), C.byref(res)))
+    return _genz_result(res, evals, evecs, A.n)
+
+
+def gen_eigs_complex_userop(n, fn, nev, ncv, selection=0, maxit=1000, tol=1e-10, sorting=0, init_resid=None) -> EigsResult:
+    CB = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+
+    def tramp(xp, yp, _):
+        x = np.ctypeslib.as_array(xp, shape=(2 * n,)).view(np.complex128)
+        y = np.ctypeslib.as_array(yp, shape=(2 * n,)).view(np.complex128)
+        y[:] = fn(x)
+
+    cb = CB(tramp)
+    res = _RefResult()
+    evals = np.zeros(2 * nev)
+    evecs = np.zeros(n * nev, dtype=np.complex128)
+    r0 = np.ascontiguousarray(init_resid, dtype=np.complex128) if init_resid is not None else None
+    _check(lib().ref_gen_eigs_complex_userop(C.c_int64(n), cb, None, C.c_int64(nev), C.c_int64(ncv), int(selection), C.c_int64(maxit), C.c_double(tol),
+                                             int(sorting), _p(r0), _p(evals), _p(evecs), C.byref(res)))
+    return _genz_result(res, evals, evecs, n)
+
+
+def hess_eigen_complex(H):
+    H = np.asfortranarray(np.asarray(H, dtype=np.complex128))
+    m = H.shape[0]
+    ev = np.empty(m, dtype=np.complex128)
+    V = np.empty((m, m), dtype=np.complex128, order="F")
+    _check(lib().ref_hess_eigen_complex(C.c_int64(m), _p(H), _p(ev), _p(V)))
+    return ev, V
+
+
+def shifted_qr_complex(H, shift):
+    H = np.asfortranarray(np.asarray(H, dtype=np.complex128))
+    m = H.shape[0]
+    R_, D, Q = (np.empty((m, m), dtype=np.complex128, order="F") for _ in range(3))
+    z = complex(shift)
+    _check(lib().ref_shifted_qr_complex(C.c_int64(m), _p(H), C.c_double(z.real), C.c_double(z.imag), _p(R_), _p(D), _p(Q)))
+    return R_, D, Q
+
+
+def givens_complex(x, y):
+    x, y = complex(x), complex(y)
+    r = (C.c_double * 2)()
+    s = (C.c_double * 2)()
+    c = C.c_double()
+    lib().ref_givens_complex(C.c_double(x.real), C.c_double(x.imag), C.c_double(y.real), C.c_double(y.imag), r, C.byref(c), s)
+    return complex(r[0], r[1]), c.value, complex(s[0], s[1])

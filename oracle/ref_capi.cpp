@@ -13,6 +13,8 @@
 // put the restatement (oracle/*.hpp) next to the reference on identical inputs.
 #include <Spectra/SymEigsSolver.h>
 #include <Spectra/GenEigsSolver.h>
+#include <Spectra/HermEigsSolver.h>
+#include <Spectra/MatOp/SparseHermMatProd.h>
 #include <Spectra/MatOp/SparseSymMatProd.h>
 #include <Spectra/MatOp/SparseGenMatProd.h>
 #include <Spectra/LinAlg/DoubleShiftQR.h>
@@ -502,6 +504,218 @@ int ref_gen_eigs(int order, const Compressed* A, int64_t nev, int64_t ncv, int s
         run(eigs);
     }
     REF_CATCH
+}
+
+}  // extern "C"
+
+// ---- complex Hermitian path ------------------------------------------------------
+// HermEigsSolver<SparseHermMatProd<std::complex<double>, Uplo, ColMajor>> (HermEigsSolver.h:121-122,
+// MatOp/SparseHermMatProd.h:21-89).  val / init_resid / evecs are interleaved (re, im); eigenvalues are real.
+namespace {
+using CVector = Eigen::Matrix<Complex, Eigen::Dynamic, 1>;
+using CMatrix = Eigen::Matrix<Complex, Eigen::Dynamic, Eigen::Dynamic>;
+
+struct CallbackOpZ
+{
+    using Scalar = Complex;
+    Index n;
+    void (*fn)(const double*, double*, void*);
+    void* user;
+    Index rows() const { return n; }
+    Index cols() const { return n; }
+    void perform_op(const Complex* x, Complex* y) const { fn(reinterpret_cast<const double*>(x), reinterpret_cast<double*>(y), user); }
+};
+
+template <typename Eigs>
+void run_herm(Eigs& eigs, int selection, int64_t maxit, double tol, int sorting, const double* init_resid, double* evals, double* evecs, RefResult* res)
+{
+    const double t0 = now_s();
+    if (init_resid)
+        eigs.init(reinterpret_cast<const Complex*>(init_resid));
+    else
+        eigs.init();
+    const Index nconv = eigs.compute(Spectra::SortRule(selection), maxit, tol, Spectra::SortRule(sorting));
+    res->seconds = now_s() - t0;
+    res->nconv = nconv;
+    res->niter = eigs.num_iterations();
+    res->nops = eigs.num_operations();
+    res->info = int32_t(eigs.info());
+    Vector ev = eigs.eigenvalues();
+    if (evals)
+        std::memcpy(evals, ev.data(), sizeof(double) * size_t(ev.size()));
+    if (evecs)
+        cmat_to(eigs.eigenvectors(), evecs);
+}
+}  // namespace
+
+extern "C" {
+
+int ref_herm_eigs(int uplo, const Compressed* A, int64_t nev, int64_t ncv, int selection, int64_t maxit, double tol, int sorting, const double* init_resid,
+                  double* evals, double* evecs, RefResult* res)
+{
+    REF_TRY
+    Eigen::Map<const Eigen::SparseMatrix<Complex, Eigen::ColMajor, int>> mat(A->n, A->n, A->nnz, A->outer, A->inner, reinterpret_cast<const Complex*>(A->val));
+    if (uplo == 0)
+    {
+        using Op = Spectra::SparseHermMatProd<Complex, Eigen::Lower>;
+        Op op(mat);
+        Spectra::HermEigsSolver<Op> eigs(op, nev, ncv);
+        run_herm(eigs, selection, maxit, tol, sorting, init_resid, evals, evecs, res);
+    }
+    else
+    {
+        using Op = Spectra::SparseHermMatProd<Complex, Eigen::Upper>;
+        Op op(mat);
+        Spectra::HermEigsSolver<Op> eigs(op, nev, ncv);
+        run_herm(eigs, selection, maxit, tol, sorting, init_resid, evals, evecs, res);
+    }
+    REF_CATCH
+}
+
+int ref_herm_eigs_userop(int64_t n, void (*fn)(const double*, double*, void*), void* user, int64_t nev, int64_t ncv, int selection, int64_t maxit, double tol,
+                         int sorting, const double* init_resid, double* evals, double* evecs, RefResult* res)
+{
+    REF_TRY
+    CallbackOpZ op{Index(n), fn, user};
+    Spectra::HermEigsSolver<CallbackOpZ> eigs(op, nev, ncv);
+    run_herm(eigs, selection, maxit, tol, sorting, init_resid, evals, evecs, res);
+    REF_CATCH
+}
+
+// y = selfadjointView<Uplo>(A) x through SparseHermMatProd::perform_op
+int ref_herm_spmv(int uplo, const Compressed* A, const double* x, double* y)
+{
+    REF_TRY
+    Eigen::Map<const Eigen::SparseMatrix<Complex, Eigen::ColMajor, int>> mat(A->n, A->n, A->nnz, A->outer, A->inner, reinterpret_cast<const Complex*>(A->val));
+    if (uplo == 0)
+    {
+        Spectra::SparseHermMatProd<Complex, Eigen::Lower> op(mat);
+        op.perform_op(reinterpret_cast<const Complex*>(x), reinterpret_cast<Complex*>(y));
+    }
+    else
+    {
+        Spectra::SparseHermMatProd<Complex, Eigen::Upper> op(mat);
+        op.perform_op(reinterpret_cast<const Complex*>(x), reinterpret_cast<Complex*>(y));
+    }
+    REF_CATCH
+}
+
+void ref_simple_random_complex(uint64_t seed, int64_t n, double* out_ri)
+{
+    Spectra::SimpleRandom<Complex> rng(seed);
+    CVector v = rng.random_vec(n);
+    std::memcpy(out_ri, v.data(), sizeof(Complex) * size_t(n));
+}
+
+}  // extern "C"
+
+// ---- complex general path --------------------------------------------------------
+// GenEigsSolver<SparseGenMatProd<std::complex<double>, Flags>> (GenEigsBase.h:111-140 complex restart, UpperHessenbergQR<complex>,
+// Givens<complex>, UpperHessenbergEigen<complex> over the stand-in's ComplexSchur).  Everything interleaved (re, im).
+namespace {
+template <typename Eigs>
+void run_gen_z(Eigs& eigs, int selection, int64_t maxit, double tol, int sorting, const double* init_resid, double* evals, double* evecs, RefResult* res)
+{
+    const double t0 = now_s();
+    if (init_resid)
+        eigs.init(reinterpret_cast<const Complex*>(init_resid));
+    else
+        eigs.init();
+    const Index nconv = eigs.compute(Spectra::SortRule(selection), maxit, tol, Spectra::SortRule(sorting));
+    res->seconds = now_s() - t0;
+    res->nconv = nconv;
+    res->niter = eigs.num_iterations();
+    res->nops = eigs.num_operations();
+    res->info = int32_t(eigs.info());
+    auto ev = eigs.eigenvalues();
+    for (Index i = 0; i < ev.size(); i++)
+    {
+        evals[2 * i] = ev[i].real();
+        evals[2 * i + 1] = ev[i].imag();
+    }
+    if (evecs)
+        cmat_to(eigs.eigenvectors(), evecs);
+}
+}  // namespace
+
+extern "C" {
+
+int ref_gen_eigs_complex(int order, const Compressed* A, int64_t nev, int64_t ncv, int selection, int64_t maxit, double tol, int sorting,
+                         const double* init_resid, double* evals, double* evecs, RefResult* res)
+{
+    REF_TRY
+    if (order == 0)
+    {
+        Eigen::Map<const Eigen::SparseMatrix<Complex, Eigen::ColMajor, int>> mat(A->n, A->n, A->nnz, A->outer, A->inner, reinterpret_cast<const Complex*>(A->val));
+        using Op = Spectra::SparseGenMatProd<Complex, Eigen::ColMajor>;
+        Op op(mat);
+        Spectra::GenEigsSolver<Op> eigs(op, nev, ncv);
+        run_gen_z(eigs, selection, maxit, tol, sorting, init_resid, evals, evecs, res);
+    }
+    else
+    {
+        Eigen::Map<const Eigen::SparseMatrix<Complex, Eigen::RowMajor, int>> mat(A->n, A->n, A->nnz, A->outer, A->inner, reinterpret_cast<const Complex*>(A->val));
+        using Op = Spectra::SparseGenMatProd<Complex, Eigen::RowMajor>;
+        Op op(mat);
+        Spectra::GenEigsSolver<Op> eigs(op, nev, ncv);
+        run_gen_z(eigs, selection, maxit, tol, sorting, init_resid, evals, evecs, res);
+    }
+    REF_CATCH
+}
+
+int ref_gen_eigs_complex_userop(int64_t n, void (*fn)(const double*, double*, void*), void* user, int64_t nev, int64_t ncv, int selection, int64_t maxit,
+                                double tol, int sorting, const double* init_resid, double* evals, double* evecs, RefResult* res)
+{
+    REF_TRY
+    CallbackOpZ op{Index(n), fn, user};
+    Spectra::GenEigsSolver<CallbackOpZ> eigs(op, nev, ncv);
+    run_gen_z(eigs, selection, maxit, tol, sorting, init_resid, evals, evecs, res);
+    REF_CATCH
+}
+
+// UpperHessenbergEigen<std::complex<double>> (UpperHessenbergEigen.h:328-454): H, evals, evecs interleaved, column-major
+int ref_hess_eigen_complex(int64_t m, const double* H_ri, double* evals, double* evecs)
+{
+    REF_TRY
+    Eigen::Map<const CMatrix> h(reinterpret_cast<const Complex*>(H_ri), m, m);
+    Spectra::UpperHessenbergEigen<Complex> dec(h);
+    const auto& ev = dec.eigenvalues();
+    for (int64_t i = 0; i < m; i++)
+    {
+        evals[2 * i] = ev[i].real();
+        evals[2 * i + 1] = ev[i].imag();
+    }
+    cmat_to(dec.eigenvectors(), evecs);
+    REF_CATCH
+}
+
+// UpperHessenbergQR<std::complex<double>> with a complex shift (:136-255, :383-417): R, Q^H H Q, Q = I G_1 G_2 ...
+int ref_shifted_qr_complex(int64_t m, const double* H_ri, double shift_re, double shift_im, double* R, double* QtHQ, double* Q)
+{
+    REF_TRY
+    Eigen::Map<const CMatrix> h(reinterpret_cast<const Complex*>(H_ri), m, m);
+    CMatrix q = CMatrix::Identity(m, m), d;
+    Spectra::UpperHessenbergQR<Complex> dec(m);
+    dec.compute(h, Complex(shift_re, shift_im));
+    cmat_to(dec.matrix_R(), R);
+    dec.matrix_QtHQ(d);
+    dec.apply_YQ(q);
+    cmat_to(d, QtHQ);
+    cmat_to(q, Q);
+    REF_CATCH
+}
+
+// Givens<std::complex<double>>::compute_rotation (Givens.h:218-335)
+void ref_givens_complex(double xr, double xi, double yr, double yi, double* r_ri, double* c, double* s_ri)
+{
+    Complex r, s;
+    double cc;
+    Spectra::Givens<Complex>::compute_rotation(Complex(xr, xi), Complex(yr, yi), r, cc, s);
+    r_ri[0] = r.real();
+    r_ri[1] = r.imag();
+    *c = cc;
+    s_ri[0] = s.real();
+    s_ri[1] = s.imag();
 }
 
 }  // extern "C"

@@ -387,3 +387,101 @@ def test_full_size_reference_results_agree_with_oracle(cfg):
         assert abs(ref["nops"] - orc["nops"]) <= 0.05 * orc["nops"]
     else:
         assert ref["nops"] == orc["nops"] and ref["niter"] == orc["niter"]
+
+
+# ---------------------------------------------------------------- complex Hermitian path: oracle/herm.py vs the reference
+@pytest.mark.parametrize("n", [10, 100, 1000])
+def test_herm_eigs_reference_cases(n):
+    # test/HermEigs.cpp:140-174 fixtures: HermEigsSolver<SparseHermMatProd<std::complex<double>>> (the reference's own code) next to the numpy
+    # restatement oracle/herm.py.  numpy's dot products sum pairwise, so this tier is tolerance-level: equal nconv and operation counts on the
+    # short runs, eigenvalues to 1e-12
+    from oracle import herm as OH
+
+    prob, k, m = {10: (0.5, 3, 6), 100: (0.1, 10, 20), 1000: (0.01, 20, 50)}[n]
+    A = OH.gen_sparse_data_herm(n, prob)
+    Af = OH.herm_full(A)
+    rz = R.CompressedZ(A)
+    x = R.simple_random_complex(3, n)
+    assert _eq(x, OH.simple_random_complex(3, n))  # SimpleRandom<complex>: re, im consecutive draws
+    y = R.herm_spmv(rz, x)
+    assert np.abs(y - Af @ x).max() <= 1e-13 * np.abs(y).max()  # one triangle mirrored conjugated, real diagonal
+    for sel in (O.LargestMagn, O.LargestAlge, O.SmallestMagn, O.SmallestAlge, O.BothEnds):
+        if n == 1000 and sel == O.SmallestMagn:
+            continue
+        r = R.herm_eigs(rz, k, m, sel)
+        o = OH.herm_eigs(Af.dot, n, k, m, sel)
+        assert r.info == O.Successful and (r.info, r.nconv) == (o.info, o.nconv)
+        assert abs(r.niter - o.niter) <= max(1, o.niter // 20) and abs(r.nops - o.nops) <= max(m, o.nops // 20)
+        assert np.abs(r.eigenvalues - o.eigenvalues).max() <= 1e-11 * max(1.0, np.abs(r.eigenvalues).max())
+        U = r.eigenvectors
+        assert np.abs(Af @ U - U * r.eigenvalues).max() <= 1e-9  # test/HermEigs.cpp:66-70
+        assert np.abs(U.conj().T @ U - np.eye(k)).max() <= 1e-9
+        # the same solve through a user-defined complex OpType
+        r2 = R.herm_eigs_userop(n, Af.dot, k, m, sel)
+        assert (r2.info, r2.nconv) == (r.info, r.nconv)
+        assert np.abs(r2.eigenvalues - r.eigenvalues).max() <= 1e-11 * max(1.0, np.abs(r.eigenvalues).max())
+
+
+# ---------------------------------------------------------------- complex general path: oracle/herm.py vs the reference
+def test_complex_givens_and_hessenberg_qr_match_reference():
+    # Givens<complex>::compute_rotation (Givens.h:218-335) and UpperHessenbergQR<complex> (:136-255, :383-417): the numpy restatement
+    # performs the same scalar operations, so the agreement is at the level of a few ulp
+    from oracle import herm as OH
+
+    rng = np.random.default_rng(0)
+    for _ in range(3000):
+        x = complex(*rng.standard_normal(2)) * 10 ** rng.uniform(-8, 8)
+        y = complex(*rng.standard_normal(2)) * 10 ** rng.uniform(-8, 8)
+        if rng.random() < 0.1:
+            x = 0j
+        if rng.random() < 0.1:
+            y = 0j
+        (rr, rc, rs), (orr, oc, os_) = R.givens_complex(x, y), OH.givens_complex(x, y)
+        sc = max(abs(x), abs(y), 1e-300)
+        assert abs(rr - orr) <= 8e-16 * sc and abs(rc - oc) <= 8e-16 and abs(rs - os_) <= 8e-16
+    for m in (2, 6, 30, 63):
+        H = np.triu(rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m)), -1)
+        mu = complex(*rng.standard_normal(2))
+        Rm, D, Q = R.shifted_qr_complex(H, mu)
+        RQ, cs, sn = OH.hess_qr_complex(H, mu)
+        Qo = np.eye(m, dtype=complex)
+        OH.apply_yq_complex(Qo, cs, sn)
+        assert np.abs(D - RQ).max() <= 1e-13 * m and np.abs(Q - Qo).max() <= 1e-13 * m
+        assert np.abs(Q @ Rm - (H - mu * np.eye(m))).max() <= 1e-13 * m  # test/QR.cpp:177-189
+
+
+@pytest.mark.parametrize("m", [2, 5, 30, 63])
+def test_complex_hessenberg_eigen_reference(m):
+    # UpperHessenbergEigen<complex> (the reference's back-substitution, normalisation and modulus sort, :347-404) over the stand-in's
+    # ComplexSchur: a valid eigen-decomposition with LAPACK's spectrum, ascending modulus
+    rng = np.random.default_rng(m)
+    H = np.triu(rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m)), -1)
+    ev, V = R.hess_eigen_complex(H)
+    assert np.abs(H @ V - V * ev).max() <= 1e-12 * m
+    assert np.abs(np.linalg.norm(V, axis=0) - 1.0).max() <= 1e-14
+    assert np.all(np.diff(np.abs(ev)) >= -1e-13)
+    w = np.linalg.eigvals(H)
+    assert max(np.abs(w - e).min() for e in ev) <= 1e-12 * m
+
+
+@pytest.mark.parametrize("n", [10, 100, 1000])
+def test_complex_gen_eigs_reference_cases(n):
+    # test/ComplexEigs.cpp:112-192 fixtures (maxit = 300): GenEigsSolver<SparseGenMatProd<std::complex<double>>> -- the reference's own
+    # code -- next to oracle/herm.py::gen_eigs_complex, whose Ritz pairs come from LAPACK: same outcome, eigenvalues to 1e-10
+    from oracle import herm as OH
+
+    prob, k, m = {10: (0.5, 3, 6), 100: (0.1, 10, 30), 1000: (0.01, 20, 50)}[n]
+    A = OH.gen_sparse_data_complex(n, prob).tocsr()
+    rz = R.CompressedZG(A)
+    for sel in (O.LargestMagn, O.LargestReal, O.LargestImag, O.SmallestReal):
+        if n == 1000 and sel != O.LargestReal:
+            continue
+        r = R.gen_eigs_complex(rz, k, m, sel, 300)
+        o = OH.gen_eigs_complex(A.dot, n, k, m, sel, 300)
+        assert r.info == O.Successful and (r.info, r.nconv) == (o.info, o.nconv)
+        assert abs(r.niter - o.niter) <= max(2, o.niter // 10)
+        assert np.abs(A @ r.eigenvectors - r.eigenvectors * r.eigenvalues).max() <= 1e-9  # test/ComplexEigs.cpp:60-64
+        key = lambda z: (round(z.real, 8), round(z.imag, 8))  # noqa: E731
+        assert np.abs(np.array(sorted(r.eigenvalues, key=key)) - np.array(sorted(o.eigenvalues, key=key))).max() <= 1e-10 * max(1.0, np.abs(r.eigenvalues).max())
+        r2 = R.gen_eigs_complex_userop(n, A.dot, k, m, sel, 300)
+        assert (r2.info, r2.nconv) == (r.info, r.nconv)
