@@ -25,13 +25,19 @@ public:
 #ifdef SPECTRA_B200_HAS_EIGEN
     explicit SparseGenMatProd(const Eigen::SparseMatrix<Scalar, Flags, StorageIndex>& mat)
     {
-        if (!mat.isCompressed())
-            throw std::invalid_argument("SparseGenMatProd: matrix must be in compressed mode (call makeCompressed())");
         if (mat.rows() != mat.cols())
             throw std::invalid_argument("SparseGenMatProd: matrix must be square");
-        create_any(mat.rows(), mat.outerIndexPtr(), mat.innerIndexPtr(), mat.valuePtr(), Flags == Eigen::RowMajor,
-               SB200_GENERAL);
+        if (mat.isCompressed())
+            create_any(mat.rows(), mat.outerIndexPtr(), mat.innerIndexPtr(), mat.valuePtr(), Flags == Eigen::RowMajor, SB200_GENERAL);
+        else
+        {
+            m_packed.pack(mat);  // uncompressed mode, as in the reference's README example (README.md:150-160)
+            create_any(mat.rows(), m_packed.outer.data(), m_packed.inner.data(), m_packed.values.data(), Flags == Eigen::RowMajor, SB200_GENERAL);
+        }
     }
+
+private:
+    b200::PackedCopy<StorageIndex, Scalar> m_packed;
 #endif
 };
 
@@ -68,11 +74,16 @@ public:
 #ifdef SPECTRA_B200_HAS_EIGEN
     explicit SparseGenMatProd(const Eigen::SparseMatrix<Scalar, Flags, StorageIndex>& mat)
     {
-        if (!mat.isCompressed())
-            throw std::invalid_argument("SparseGenMatProd: matrix must be in compressed mode (call makeCompressed())");
         if (mat.rows() != mat.cols())
             throw std::invalid_argument("SparseGenMatProd: matrix must be square");
-        create(mat.rows(), mat.outerIndexPtr(), mat.innerIndexPtr(), mat.valuePtr());
+        if (mat.isCompressed())
+            create(mat.rows(), mat.outerIndexPtr(), mat.innerIndexPtr(), mat.valuePtr());
+        else
+        {
+            b200::PackedCopy<StorageIndex, Scalar> packed;  // the arrays are uploaded at construction and not referenced afterwards
+            packed.pack(mat);
+            create(mat.rows(), packed.outer.data(), packed.inner.data(), packed.values.data());
+        }
     }
 #endif
     SparseGenMatProd(const SparseGenMatProd&) = delete;

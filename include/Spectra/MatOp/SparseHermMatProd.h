@@ -46,12 +46,19 @@ public:
     // Raw compressed arrays with Eigen's layout: outer[n + 1], inner[nnz], values[nnz] (uploaded once).
     SparseHermMatProd(Index n, const StorageIndex* outer, const StorageIndex* inner, const Scalar* values) { create(n, outer, inner, values); }
 #ifdef SPECTRA_B200_HAS_EIGEN
-    // Same constructor as the reference (SparseHermMatProd.h:46-54); the matrix must be compressed.
+    // Same constructor as the reference (SparseHermMatProd.h:46-54).
     explicit SparseHermMatProd(const Eigen::SparseMatrix<Scalar, Flags, StorageIndex>& mat)
     {
-        if (!mat.isCompressed())
-            throw std::invalid_argument("SparseHermMatProd: matrix must be in compressed mode (call makeCompressed())");
-        create(mat.rows(), mat.outerIndexPtr(), mat.innerIndexPtr(), mat.valuePtr());
+        if (mat.rows() != mat.cols())
+            throw std::invalid_argument("SparseHermMatProd: matrix must be square");
+        if (mat.isCompressed())
+            create(mat.rows(), mat.outerIndexPtr(), mat.innerIndexPtr(), mat.valuePtr());
+        else
+        {
+            b200::PackedCopy<StorageIndex, Scalar> packed;  // uncompressed mode: packed once; the arrays are uploaded at construction
+            packed.pack(mat);
+            create(mat.rows(), packed.outer.data(), packed.inner.data(), packed.values.data());
+        }
     }
 #endif
     SparseHermMatProd(const SparseHermMatProd&) = delete;

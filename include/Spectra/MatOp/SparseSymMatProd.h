@@ -40,14 +40,24 @@ public:
                Uplo == SPECTRA_B200_LOWER ? SB200_SYM_LOWER : SB200_SYM_UPPER);
     }
 #ifdef SPECTRA_B200_HAS_EIGEN
-    // Same constructor as the reference (SparseSymMatProd.h:57-65); the matrix must be compressed and outlive the operator.
+    // Same constructor as the reference (SparseSymMatProd.h:57-65); the matrix must outlive the operator.
     explicit SparseSymMatProd(const Eigen::SparseMatrix<Scalar, Flags, StorageIndex>& mat)
     {
-        if (!mat.isCompressed())
-            throw std::invalid_argument("SparseSymMatProd: matrix must be in compressed mode (call makeCompressed())");
-        create_any(mat.rows(), mat.outerIndexPtr(), mat.innerIndexPtr(), mat.valuePtr(), Flags == Eigen::RowMajor,
-               Uplo == Eigen::Lower ? SB200_SYM_LOWER : SB200_SYM_UPPER);
+        if (mat.rows() != mat.cols())
+            throw std::invalid_argument("SparseSymMatProd: matrix must be square");
+        if (mat.isCompressed())
+            create_any(mat.rows(), mat.outerIndexPtr(), mat.innerIndexPtr(), mat.valuePtr(), Flags == Eigen::RowMajor,
+                       Uplo == Eigen::Lower ? SB200_SYM_LOWER : SB200_SYM_UPPER);
+        else
+        {
+            m_packed.pack(mat);  // uncompressed mode (reserve + insert): accepted by the reference's Eigen::Ref, packed here
+            create_any(mat.rows(), m_packed.outer.data(), m_packed.inner.data(), m_packed.values.data(), Flags == Eigen::RowMajor,
+                       Uplo == Eigen::Lower ? SB200_SYM_LOWER : SB200_SYM_UPPER);
+        }
     }
+
+private:
+    b200::PackedCopy<StorageIndex, Scalar> m_packed;
 #endif
 };
 

@@ -28,11 +28,21 @@ public:
     {
         if (mat.rows() != mat.cols())
             throw std::invalid_argument("SparseSymShiftSolve: matrix must be square");
-        if (!mat.isCompressed())
-            throw std::invalid_argument("SparseSymShiftSolve: matrix must be in compressed mode (call makeCompressed())");
-        create_any(mat.rows(), mat.outerIndexPtr(), mat.innerIndexPtr(), mat.valuePtr(), Flags == Eigen::RowMajor,
-               Uplo == Eigen::Lower ? SB200_SYM_LOWER : SB200_SYM_UPPER, true);
+        if (mat.isCompressed())
+            create_any(mat.rows(), mat.outerIndexPtr(), mat.innerIndexPtr(), mat.valuePtr(), Flags == Eigen::RowMajor,
+                       Uplo == Eigen::Lower ? SB200_SYM_LOWER : SB200_SYM_UPPER, true);
+        else
+        {
+            m_packed.pack(mat);
+            create_any(mat.rows(), m_packed.outer.data(), m_packed.inner.data(), m_packed.values.data(), Flags == Eigen::RowMajor,
+                       Uplo == Eigen::Lower ? SB200_SYM_LOWER : SB200_SYM_UPPER, true);
+        }
     }
+
+private:
+    b200::PackedCopy<StorageIndex, Scalar> m_packed;
+
+public:
 #endif
 
     // set_shift(sigma) (SparseSymShiftSolve.h:85-95); throws std::invalid_argument when the factorisation fails

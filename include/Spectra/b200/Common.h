@@ -140,6 +140,39 @@ inline const double* widen(const float* p, Index n, std::vector<double>& buf)
     return buf.data();
 }
 
+#ifdef SPECTRA_B200_HAS_EIGEN
+// An Eigen::SparseMatrix in UNCOMPRESSED mode (after reserve() / insert(), e.g. the reference's README example, README.md:146-178): the
+// reference binds its matrix through Eigen::Ref<const SparseMatrix>, which accepts either mode, so the wrappers must too.  The inner
+// vectors (outer[k] .. outer[k] + innerNonZeros[k]) are packed once into compressed arrays owned by the wrapper.
+template <typename StorageIndex, typename Scalar>
+struct PackedCopy
+{
+    std::vector<StorageIndex> outer, inner;
+    std::vector<Scalar> values;
+    template <typename SpMat>
+    void pack(const SpMat& mat)
+    {
+        const Index no = mat.outerSize();
+        const StorageIndex* o = mat.outerIndexPtr();
+        const StorageIndex* c = mat.innerNonZeroPtr();
+        const StorageIndex* in = mat.innerIndexPtr();
+        const Scalar* v = mat.valuePtr();
+        outer.assign(static_cast<size_t>(no + 1), StorageIndex(0));
+        inner.clear();
+        values.clear();
+        for (Index k = 0; k < no; k++)
+        {
+            for (StorageIndex p = o[k]; p < o[k] + c[k]; p++)
+            {
+                inner.push_back(in[p]);
+                values.push_back(v[p]);
+            }
+            outer[static_cast<size_t>(k + 1)] = static_cast<StorageIndex>(inner.size());
+        }
+    }
+};
+#endif
+
 // Marks operator wrappers that own a device-resident sb200_op (exposed through handle()); any other OpType is treated as a
 // user-defined host operator and wrapped in a callback adapter.
 struct DeviceOpTag

@@ -811,6 +811,30 @@ public:
         m.setConstant(v);
         return m;
     }
+    static Matrix Constant(Index n, const S& v)
+    {
+        Matrix m(n);
+        m.setConstant(v);
+        return m;
+    }
+    // keeps the leading block
+    void conservativeResize(Index r, Index c)
+    {
+        if (r == m_r && c == m_c)
+            return;
+        Matrix t(r, c);
+        for (Index j = 0; j < (std::min)(c, m_c); j++)
+            for (Index i = 0; i < (std::min)(r, m_r); i++)
+                t(i, j) = (*this)(i, j);
+        swap(t);
+    }
+    void conservativeResize(Index n)
+    {
+        if (C == 1)
+            conservativeResize(n, 1);
+        else
+            conservativeResize(1, n);
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1349,14 +1373,273 @@ public:
     }
 };
 
+template <typename S, typename StorageIndex = int>
+class Triplet
+{
+    StorageIndex m_r, m_c;
+    S m_v;
+
+public:
+    Triplet() : m_r(0), m_c(0), m_v(0) {}
+    Triplet(const StorageIndex& i, const StorageIndex& j, const S& v = S(0)) : m_r(i), m_c(j), m_v(v) {}
+    const StorageIndex& row() const { return m_r; }
+    const StorageIndex& col() const { return m_c; }
+    const S& value() const { return m_v; }
+};
+
+// Owning sparse matrix in Eigen's storage scheme: compressed (outer[k] .. outer[k + 1]) or, after reserve() / insert(), uncompressed
+// (outer[k] .. outer[k] + innerNonZeros[k], free room behind each inner vector).  Inner vectors are kept sorted, as Eigen's insert() does.
 template <typename S, int Flags, typename StorageIndex>
-class SparseMatrix : public SparseCompressedBase<S, Flags, StorageIndex>, public SparseMatrixBase<SparseMatrix<S, Flags, StorageIndex>>
+class SparseMatrix : public SparseMatrixBase<SparseMatrix<S, Flags, StorageIndex>>
 {
 public:
     using PlainObject = SparseMatrix;
     using Scalar = S;
     enum { IsRowMajor = (Flags & RowMajor) ? 1 : 0 };
+
+private:
+    Index m_rows = 0, m_cols = 0;
+    std::vector<StorageIndex> m_outer;     // outerSize + 1
+    std::vector<StorageIndex> m_innernnz;  // outerSize; empty <=> compressed
+    std::vector<StorageIndex> m_inner;
+    std::vector<S> m_values;
+    mutable SparseData<S, Flags, StorageIndex> m_view;
+    mutable std::vector<StorageIndex> m_couter, m_cinner;  // compressed copy handed to Ref<> while *this is uncompressed
+    mutable std::vector<S> m_cvalues;
+
+    Index outer_of(Index i, Index j) const { return IsRowMajor ? i : j; }
+    Index inner_of(Index i, Index j) const { return IsRowMajor ? j : i; }
+    Index count(Index o) const { return m_innernnz.empty() ? Index(m_outer[o + 1] - m_outer[o]) : Index(m_innernnz[o]); }
+
+    void uncompress(Index extra_per_outer)
+    {
+        const Index no = outerSize();
+        std::vector<StorageIndex> outer(no + 1), nnz(no);
+        Index pos = 0;
+        for (Index o = 0; o < no; o++)
+        {
+            outer[o] = StorageIndex(pos);
+            nnz[o] = StorageIndex(count(o));
+            pos += count(o) + extra_per_outer;
+        }
+        outer[no] = StorageIndex(pos);
+        std::vector<StorageIndex> inner(pos);
+        std::vector<S> values(pos);
+        for (Index o = 0; o < no; o++)
+            for (Index k = 0; k < count(o); k++)
+            {
+                inner[outer[o] + k] = m_inner[m_outer[o] + k];
+                values[outer[o] + k] = m_values[m_outer[o] + k];
+            }
+        m_outer.swap(outer);
+        m_innernnz.swap(nnz);
+        m_inner.swap(inner);
+        m_values.swap(values);
+    }
+
+public:
+    SparseMatrix() { m_outer.assign(1, 0); }
+    SparseMatrix(Index rows, Index cols) { resize(rows, cols); }
+
+    void resize(Index rows, Index cols)
+    {
+        m_rows = rows;
+        m_cols = cols;
+        m_outer.assign(size_t(outerSize() + 1), 0);
+        m_innernnz.clear();
+        m_inner.clear();
+        m_values.clear();
+    }
+    Index rows() const { return m_rows; }
+    Index cols() const { return m_cols; }
+    Index outerSize() const { return IsRowMajor ? m_rows : m_cols; }
+    Index innerSize() const { return IsRowMajor ? m_cols : m_rows; }
+    bool isCompressed() const { return m_innernnz.empty(); }
+    Index nonZeros() const
+    {
+        Index n = 0;
+        for (Index o = 0; o < outerSize(); o++)
+            n += count(o);
+        return n;
+    }
+    const StorageIndex* outerIndexPtr() const { return m_outer.data(); }
+    const StorageIndex* innerIndexPtr() const { return m_inner.data(); }
+    const StorageIndex* innerNonZeroPtr() const { return m_innernnz.empty() ? nullptr : m_innernnz.data(); }
+    const S* valuePtr() const { return m_values.data(); }
+
+    // reserve(sizes): room for sizes[k] more entries in inner vector k; switches to uncompressed mode
+    template <typename SizesType>
+    void reserve(const SizesType& sizes)
+    {
+        const Index no = outerSize();
+        std::vector<StorageIndex> outer(no + 1), nnz(no);
+        Index pos = 0;
+        for (Index o = 0; o < no; o++)
+        {
+            outer[o] = StorageIndex(pos);
+            nnz[o] = StorageIndex(count(o));
+            pos += count(o) + Index(sizes[o]);
+        }
+        outer[no] = StorageIndex(pos);
+        std::vector<StorageIndex> inner(pos);
+        std::vector<S> values(pos);
+        for (Index o = 0; o < no; o++)
+            for (Index k = 0; k < count(o); k++)
+            {
+                inner[outer[o] + k] = m_inner[m_outer[o] + k];
+                values[outer[o] + k] = m_values[m_outer[o] + k];
+            }
+        m_outer.swap(outer);
+        m_innernnz.swap(nnz);
+        m_inner.swap(inner);
+        m_values.swap(values);
+    }
+    void reserve(Index) {}  // reserve(nnz): a capacity hint in Eigen; nothing to do here
+
+    // insert(i, j): the entry must not exist yet; returns a reference to its (zero) value
+    S& insert(Index i, Index j)
+    {
+        const Index o = outer_of(i, j), in = inner_of(i, j);
+        if (isCompressed())
+            uncompress(2);
+        if (m_outer[o] + m_innernnz[o] >= m_outer[o + 1])
+        {
+            // inner vector full: give every inner vector more room
+            std::vector<Index> more(size_t(outerSize()), Index(2));
+            more[size_t(o)] = (std::max)(Index(2), Index(m_innernnz[o]));
+            reserve(more);
+        }
+        Index k = m_outer[o] + m_innernnz[o];
+        while (k > m_outer[o] && m_inner[k - 1] > in)
+        {
+            m_inner[k] = m_inner[k - 1];
+            m_values[k] = m_values[k - 1];
+            k--;
+        }
+        if (k > m_outer[o] && m_inner[k - 1] == in)
+            throw std::logic_error("Eigen stand-in: insert() of an existing entry");
+        m_inner[k] = StorageIndex(in);
+        m_values[k] = S(0);
+        m_innernnz[o]++;
+        return m_values[k];
+    }
+    S& coeffRef(Index i, Index j)
+    {
+        const Index o = outer_of(i, j), in = inner_of(i, j);
+        for (Index k = m_outer[o]; k < m_outer[o] + count(o); k++)
+            if (m_inner[k] == in)
+                return m_values[k];
+        return insert(i, j);
+    }
+    S coeff(Index i, Index j) const
+    {
+        const Index o = outer_of(i, j), in = inner_of(i, j);
+        for (Index k = m_outer[o]; k < m_outer[o] + count(o); k++)
+            if (m_inner[k] == in)
+                return m_values[k];
+        return S(0);
+    }
+
+    void makeCompressed()
+    {
+        if (isCompressed())
+            return;
+        const Index no = outerSize();
+        Index pos = 0;
+        for (Index o = 0; o < no; o++)
+        {
+            const Index start = m_outer[o], cnt = m_innernnz[o];
+            for (Index k = 0; k < cnt; k++)
+            {
+                m_inner[pos + k] = m_inner[start + k];
+                m_values[pos + k] = m_values[start + k];
+            }
+            m_outer[o] = StorageIndex(pos);
+            pos += cnt;
+        }
+        m_outer[no] = StorageIndex(pos);
+        m_inner.resize(pos);
+        m_values.resize(pos);
+        m_innernnz.clear();
+    }
+
+    // setFromTriplets(begin, end): duplicates are summed, result compressed
+    template <typename It>
+    void setFromTriplets(It begin, It end)
+    {
+        const Index no = outerSize();
+        std::vector<std::vector<std::pair<StorageIndex, S>>> cols(no);
+        for (It it = begin; it != end; ++it)
+            cols[size_t(outer_of(it->row(), it->col()))].emplace_back(StorageIndex(inner_of(it->row(), it->col())), it->value());
+        m_outer.assign(size_t(no + 1), 0);
+        m_inner.clear();
+        m_values.clear();
+        m_innernnz.clear();
+        for (Index o = 0; o < no; o++)
+        {
+            auto& c = cols[size_t(o)];
+            std::stable_sort(c.begin(), c.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+            for (size_t k = 0; k < c.size(); k++)
+            {
+                if (k > 0 && c[k].first == c[k - 1].first)
+                    m_values.back() += c[k].second;
+                else
+                {
+                    m_inner.push_back(c[k].first);
+                    m_values.push_back(c[k].second);
+                }
+            }
+            m_outer[size_t(o + 1)] = StorageIndex(m_inner.size());
+        }
+    }
+
+    // what Ref<const SparseMatrix> binds to: the arrays themselves when compressed, a packed copy otherwise
+    const SparseData<S, Flags, StorageIndex>& raw() const
+    {
+        m_view.rows = m_rows;
+        m_view.cols = m_cols;
+        if (isCompressed())
+        {
+            m_view.nnz = Index(m_inner.size());
+            m_view.outer = m_outer.data();
+            m_view.inner = m_inner.data();
+            m_view.values = m_values.data();
+            return m_view;
+        }
+        const Index no = outerSize();
+        m_couter.assign(size_t(no + 1), 0);
+        m_cinner.clear();
+        m_cvalues.clear();
+        for (Index o = 0; o < no; o++)
+        {
+            for (Index k = 0; k < m_innernnz[o]; k++)
+            {
+                m_cinner.push_back(m_inner[m_outer[o] + k]);
+                m_cvalues.push_back(m_values[m_outer[o] + k]);
+            }
+            m_couter[size_t(o + 1)] = StorageIndex(m_cinner.size());
+        }
+        m_view.nnz = Index(m_cinner.size());
+        m_view.outer = m_couter.data();
+        m_view.inner = m_cinner.data();
+        m_view.values = m_cvalues.data();
+        return m_view;
+    }
+    template <int Uplo>
+    SparseSelfAdjointView<S, Flags, StorageIndex, Uplo> selfadjointView() const
+    {
+        SparseSelfAdjointView<S, Flags, StorageIndex, Uplo> v;
+        v.d = raw();
+        return v;
+    }
 };
+
+template <typename S, int Flags, typename StorageIndex, typename B>
+Matrix<S, Dynamic, Dynamic> operator*(const SparseMatrix<S, Flags, StorageIndex>& A, const MatrixBase<B>& x)
+{
+    Ref<const SparseMatrix<S, Flags, StorageIndex>> r(A);
+    return static_cast<const SparseCompressedBase<S, Flags, StorageIndex>&>(r) * x;
+}
 
 // Map<const SparseMatrix>(rows, cols, nnz, outerIndexPtr, innerIndexPtr, valuePtr): Eigen's constructor
 template <typename S, int Flags, typename StorageIndex>
@@ -1468,5 +1751,14 @@ Matrix<S, Dynamic, Dynamic> operator*(const SparseSelfAdjointView<S, Flags, Stor
     }
     return y;
 }
+
+using MatrixXd = Matrix<double, Dynamic, Dynamic>;
+using VectorXd = Matrix<double, Dynamic, 1>;
+using MatrixXf = Matrix<float, Dynamic, Dynamic>;
+using VectorXf = Matrix<float, Dynamic, 1>;
+using MatrixXcd = Matrix<std::complex<double>, Dynamic, Dynamic>;
+using VectorXcd = Matrix<std::complex<double>, Dynamic, 1>;
+using VectorXi = Matrix<int, Dynamic, 1>;
+using ArrayXd = Array<double, Dynamic, 1>;
 
 }  // namespace Eigen
