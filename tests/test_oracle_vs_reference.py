@@ -383,8 +383,9 @@ def test_full_size_reference_results_agree_with_oracle(cfg):
     if cfg == "C2":
         rv, ov = np.array(ref["eigenvalues"]), np.array(orc["eigenvalues"])
         assert np.abs(rv - ov).max() <= 1e-10 * np.abs(rv).max()
-        # the histories differ only through summation order (1 thread here, 8 OpenMP threads there)
-        assert abs(ref["nops"] - orc["nops"]) <= 0.05 * orc["nops"]
+        # summation orders differ (the reference: 1 thread, one triangle scattered; the restatement: 8 OpenMP threads, full rows), the
+        # history does not: 3016 operations, 95 restarts on both sides -- and on the GPU (tests/test_gpu_sym.py)
+        assert (ref["nops"], ref["niter"]) == (orc["nops"], orc["niter"])
     else:
         assert ref["nops"] == orc["nops"] and ref["niter"] == orc["niter"]
 
