@@ -140,6 +140,16 @@ def golden_full_solves():
                          "spmv_iters_per_sec": g["nops"] / g["seconds"], "host": "development container, 8 vCPU (not the GPU box)"}
         except (OSError, KeyError, ValueError):
             pass
+    # ... and of the reference's own code (oracle/_ref: yixuan/spectra's headers over the Eigen stand-in, one thread, make_reference_golden.py)
+    for name in ("C2",):
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", f"reference_{name}.json")) as fh:
+                g = json.load(fh)
+            out[name + "_reference_own_code"] = {"nops": g["nops"], "niter": g["niter"], "nconv": g["nconv"], "seconds": g["solve_seconds"], "threads": 1,
+                                                 "spmv_iters_per_sec": g["nops"] / g["solve_seconds"], "library": g["library"],
+                                                 "host": "development container (not the GPU box)"}
+        except (OSError, KeyError, ValueError):
+            pass
     return out
 
 
