@@ -60,3 +60,25 @@ def sym_full(A_lower_source):
     L = sp.tril(sp.csr_matrix(A_lower_source), 0)
     D = sp.diags(L.diagonal())
     return (L + L.T - D).tocsr()
+
+
+def stencil_matrix(dims, full=True, seed=1, diag_shift=0.3):
+    """A symmetric mesh-like matrix in natural (lexicographic) ordering: random weights on the edges of a grid graph whose nodes are
+    coupled to all neighbours within Chebyshev distance 1 (`full`: 9-point in 2-D, 27-point in 3-D) or to the axis neighbours only
+    (5- / 7-point), random diagonal.  Half-bandwidth: the stride of the slowest index (+ lower strides + 1 when `full`).  CSC."""
+    import itertools
+
+    n = int(np.prod(dims))
+    idx = np.arange(n).reshape(dims)
+    rng = np.random.default_rng(seed)
+    rows, cols = [], []
+    offs = [o for o in itertools.product(*[(-1, 0, 1)] * len(dims)) if any(o) and (full or sum(abs(x) for x in o) == 1)]
+    for o in offs:
+        src = tuple(slice(max(0, -d), dims[a] - max(0, d)) for a, d in enumerate(o))
+        dst = tuple(slice(max(0, d), dims[a] - max(0, -d)) for a, d in enumerate(o))
+        rows.append(idx[src].ravel())
+        cols.append(idx[dst].ravel())
+    r, c = np.concatenate(rows), np.concatenate(cols)
+    A = sp.csr_matrix((rng.uniform(-1, 1, r.size), (r, c)), shape=(n, n))
+    A = (A + A.T) / 2 + sp.diags(rng.uniform(-1, 1, n) + diag_shift)
+    return A.tocsc()

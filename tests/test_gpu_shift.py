@@ -8,7 +8,10 @@ import scipy.sparse as sp
 from scipy.sparse.linalg import eigsh, splu
 
 import oracle as O
-from helpers import sym_full
+import contextlib
+import os
+
+from helpers import stencil_matrix, sym_full
 
 pytestmark = pytest.mark.gpu
 
@@ -66,9 +69,11 @@ def test_shift_solve_errors(gpu):
     opd.set_shift(7.5)
     y = opd.perform_op(np.ones(n))
     assert np.abs(y - 1.0 / (np.arange(1.0, n + 1) - 7.5)).max() <= 1e-13 * np.abs(y).max()
-    # large and not banded: rejected at construction
+    # large and without band structure: the block factors (3 n b doubles, b ~ n) cannot fit -- rejected at construction
     rng = np.random.default_rng(0)
-    R = sp.random(5000, 5000, density=0.002, random_state=rng, format="csc")
+    nbig = 400_000
+    r, c = rng.integers(0, nbig, 2 * nbig), rng.integers(0, nbig, 2 * nbig)
+    R = sp.csr_matrix((rng.standard_normal(r.size), (r, c)), shape=(nbig, nbig)) + sp.identity(nbig)
     with pytest.raises(gpu.InvalidArgument):
         gpu.SparseSymShiftSolve(sp.tril(R + R.T).tocsc())
     # a non-shift operator cannot take set_shift
@@ -78,6 +83,129 @@ def test_shift_solve_errors(gpu):
 
 
 RULES = ["LargestMagn", "LargestAlge", "SmallestMagn", "SmallestAlge", "BothEnds"]
+_ON_EMULATOR = os.environ.get("SB200_TEST_BACKEND") == "emu"
+
+
+@contextlib.contextmanager
+def _route(name):
+    old = os.environ.get("SB200_SHIFT_ROUTE")
+    if name:
+        os.environ["SB200_SHIFT_ROUTE"] = name
+    try:
+        yield
+    finally:
+        if old is None:
+            os.environ.pop("SB200_SHIFT_ROUTE", None)
+        else:
+            os.environ["SB200_SHIFT_ROUTE"] = old
+
+
+# ---- wide bands / mesh-like patterns (round 2): block-tridiagonal elimination with grid-wide block kernels (band_solve.cu, factor_thomas) ----
+@pytest.mark.parametrize("dims,full,route", [((12, 9), True, "thomas"), ((7, 6, 5), True, "thomas"), ((40, 35), False, "thomas"), ((33, 3), False, "thomas"),
+                                             ((90, 80), True, None), ((30, 30, 30), True, None), ((400, 500), False, None)])
+def test_shift_solve_operator_mesh(gpu, dims, full, route):
+    # 5- / 9-point (2-D) and 27-point (3-D) stencil matrices in natural ordering: half-bandwidth = stride of the slowest index, far above 32.
+    # perform_op = (A - sigma I)^{-1} x against SuperLU; small cases force the route (their default would be the dense inverse)
+    n = int(np.prod(dims))
+    if _ON_EMULATOR and n > 2000:
+        pytest.skip("device-sized case")
+    A = stencil_matrix(dims, full, seed=n)
+    sigma = 0.37
+    with _route(route):
+        op = gpu.SparseSymShiftSolve(sp.tril(A).tocsc())
+    lay = op.layout()
+    stride = int(np.prod(dims[1:]))
+    assert lay["half_bandwidth"] >= stride and lay["levels"] == -1 and lay["block"] == max(4, lay["half_bandwidth"])
+    assert lay["block_rows"] == -(-n // lay["block"])
+    op.set_shift(sigma)
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n)
+    y = op.perform_op(x)
+    M = (A - sigma * sp.identity(n)).tocsc()
+    assert np.linalg.norm(M @ y - x) <= 1e-12 * np.linalg.norm(x) * max(1.0, np.abs(y).max())
+    if n <= 30_000:
+        y_ref = splu(M).solve(x)
+        assert np.abs(y - y_ref).max() <= 1e-9 * np.abs(y_ref).max()
+    # the unrefined solve is usable on its own; a second shift re-factorises
+    op.set_refine(0)
+    y0 = op.perform_op(x)
+    assert np.linalg.norm(M @ y0 - x) <= 1e-7 * np.linalg.norm(x) * max(1.0, np.abs(y0).max())
+    op.set_refine(1)
+    op.set_shift(-1.25)
+    y2 = op.perform_op(x)
+    M2 = (A + 1.25 * sp.identity(n)).tocsc()
+    assert np.linalg.norm(M2 @ y2 - x) <= 1e-12 * np.linalg.norm(x) * max(1.0, np.abs(y2).max())
+
+
+def test_shift_solve_mesh_singular_shift_and_column_blocks(gpu):
+    # a singular shift is reported like the reference's "factorization failed with the given shift" (SparseSymShiftSolve.h:93-94)
+    n = 40 * 36
+    D = sp.diags(np.arange(1.0, n + 1)).tocsc() + stencil_matrix((40, 36), False, seed=3) * 0.0
+    with _route("thomas"):
+        opd = gpu.SparseSymShiftSolve(stencil_matrix((40, 36), False, seed=3))
+        opd.set_shift(0.25)
+    A = stencil_matrix((40, 36), False, seed=3).tolil()
+    A[5, :] = 0.0
+    A[:, 5] = 0.0
+    A[5, 5] = 2.0  # decoupled node: (A - 2 I) is exactly singular
+    A = A.tocsc()
+    with _route("thomas"):
+        ops = gpu.SparseSymShiftSolve(sp.tril(A).tocsc())
+    with pytest.raises(gpu.InvalidArgument):
+        ops.set_shift(2.0)
+    ops.set_shift(2.5)
+    x = np.random.default_rng(1).standard_normal(n)
+    y = ops.perform_op(x)
+    M = (A - 2.5 * sp.identity(n)).tocsc()
+    assert np.linalg.norm(M @ y - x) <= 1e-12 * np.linalg.norm(x) * max(1.0, np.abs(y).max())
+    del D
+
+
+@pytest.mark.parametrize("dims,full,route,k,m", [((9, 8, 7), True, "thomas", 4, 14), ((20, 20, 20), True, None, 6, 20)])
+def test_sym_shift_eigs_mesh_vs_arpack(gpu, dims, full, route, k, m):
+    # SymEigsShiftSolver over the wide-band operator: the k eigenvalues nearest sigma of a 27-point stencil matrix, against ARPACK's shift-invert
+    n = int(np.prod(dims))
+    if _ON_EMULATOR and n > 2000:
+        pytest.skip("device-sized case")
+    A = stencil_matrix(dims, full, seed=7)
+    sigma = 0.11
+    with _route(route):
+        op = gpu.SparseSymShiftSolve(sp.tril(A).tocsc())
+    assert op.layout()["levels"] == -1
+    eigs = gpu.SymEigsShiftSolver(op, k, m, sigma)
+    eigs.init()
+    nconv = eigs.compute(gpu.SortRule.LargestMagn)
+    assert eigs.info() == gpu.CompInfo.Successful and nconv == k
+    evals, X = eigs.eigenvalues(), eigs.eigenvectors()
+    assert (np.linalg.norm(A @ X - X * evals, axis=0) / np.maximum(np.abs(evals), 1e-3)).max() <= 1e-9
+    w = eigsh(A, k=k, sigma=sigma, which="LM", ncv=m, tol=1e-12, return_eigenvectors=False)
+    assert np.abs(np.sort(evals) - np.sort(w)).max() <= 1e-10 * max(1.0, np.abs(w).max())
+    assert np.all(np.diff(evals) <= 0)
+
+
+def test_sym_shift_eigs_mesh_full_size_properties(gpu):
+    # BASELINE config 5's size with a mesh pattern: 27-point stencil on 58^3 = 195112 points (27 nnz/row, half-bandwidth 3423, 58 block rows,
+    # 16.3 GB of block factors), k = 10, sigma = 0.5.  Size-independent properties: residuals, orthonormality, run-to-run reproducibility.
+    if _ON_EMULATOR:
+        pytest.skip("device-sized case")
+    dims = (58, 58, 58)
+    n = int(np.prod(dims))
+    A = stencil_matrix(dims, True, seed=5)
+    op = gpu.SparseSymShiftSolve(sp.tril(A).tocsc())
+    lay = op.layout()
+    assert lay["half_bandwidth"] == 58 * 58 + 58 + 1 and lay["levels"] == -1
+    runs = []
+    for _ in range(2):
+        eigs = gpu.SymEigsShiftSolver(op, 10, 30, 0.5)
+        eigs.init()
+        nconv = eigs.compute(gpu.SortRule.LargestMagn)
+        assert eigs.info() == gpu.CompInfo.Successful and nconv == 10
+        runs.append((eigs.eigenvalues(), eigs.num_operations()))
+    evals, X = eigs.eigenvalues(), eigs.eigenvectors()
+    assert (np.linalg.norm(A @ X - X * evals, axis=0) / np.abs(evals)).max() <= 1e-10
+    assert np.abs(X.T @ X - np.eye(10)).max() <= 1e-10
+    assert np.all(np.abs(evals - 0.5) <= 0.05) and np.all(np.diff(evals) <= 0)
+    assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1] == runs[1][1]
 
 
 @pytest.mark.parametrize("rule", RULES)

@@ -574,6 +574,13 @@ inline cudaError_t cudaMemset(void* p, int v, size_t n)
     return cudaSuccess;
 }
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t = nullptr) { return cudaMemset(p, v, n); }
+// a fixed, generous figure: the emulator has no device memory of its own (host allocations)
+inline cudaError_t cudaMemGetInfo(size_t* free_b, size_t* total_b)
+{
+    *free_b = (size_t) 8 << 30;
+    *total_b = (size_t) 16 << 30;
+    return cudaSuccess;
+}
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned int)
 {
     *s = new CUstream_st{0};
