@@ -549,7 +549,10 @@ __global__ void __launch_bounds__(256) dense_gemv_kernel(const double* __restric
 
 // Gauss-Jordan step kernels of the wide-band route: the dense route's five launches per pivot folded into three (the pivot kernel also
 // saves M(k,k); the swap kernel takes colk[p] from that saved value and leaves column k of M alone; the update writes it as e_k)
-__global__ void __launch_bounds__(1024) gj3_pivot_kernel(const double* __restrict__ M, int64_t n, int k, int* piv_row, double* piv_val, int* flag)
+// orig[r] = original index of the row now at position r; active[j] = 1 once original row j has served as a pivot row -- column j of the
+// Inv half of the tableau is then dense, before that it is a unit vector whose row k entry is zero (nothing to update)
+__global__ void __launch_bounds__(1024) gj3_pivot_kernel(const double* __restrict__ M, int64_t n, int k, int* piv_row, double* piv_val, int* flag, int* orig,
+                                                         int* active)
 {
     __shared__ double s_best[32];
     __shared__ int s_arg[32];
@@ -594,6 +597,10 @@ __global__ void __launch_bounds__(1024) gj3_pivot_kernel(const double* __restric
         piv_val[1] = M[k + (int64_t) k * n];  // M(k,k) before the row swap
         if (!(best > 0.0))
             *flag = 1;
+        const int o = orig[arg];
+        orig[arg] = orig[k];
+        orig[k] = o;
+        active[o] = 1;
     }
 }
 
@@ -620,7 +627,7 @@ __global__ void gj3_swap_scale_kernel(double* M, double* Inv, int64_t n, int k, 
     }
 }
 // rank-1 update of the (M | Inv) tableau; column k of M is written directly (it becomes e_k), so nothing reads it after the pivot step
-__global__ void gj3_eliminate_kernel(double* M, double* Inv, int64_t n, int k, const double* __restrict__ colk)
+__global__ void gj3_eliminate_kernel(double* M, double* Inv, int64_t n, int k, const double* __restrict__ colk, const int* __restrict__ active)
 {
     const int64_t total = 2 * n * n;
     for (int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x)
@@ -629,6 +636,10 @@ __global__ void gj3_eliminate_kernel(double* M, double* Inv, int64_t n, int k, c
         double* X = in_m ? M : Inv;
         const int64_t ee = in_m ? e : e - n * n;
         const int64_t r = ee % n, c = ee / n;
+        // structurally finished parts of the tableau are neither read nor written: columns < k of M are unit vectors with M(k, c) = 0,
+        // and so are the columns of Inv whose original row has not been a pivot row yet -- about half of the tableau at any pivot
+        if (in_m ? c < k : active[c] == 0)
+            continue;
         if (in_m && c == k)
         {
             X[ee] = (r == k) ? 1.0 : 0.0;
@@ -660,10 +671,12 @@ __global__ void thomas_diag_scatter_kernel(const int* __restrict__ rowptr, const
 }
 
 // diagonal of block row bi: -= sigma on real rows, identity on the padding rows of the last block; Inv := I
-__global__ void thomas_diag_shift_kernel(double* S, double* Inv, int64_t n, int B, int64_t bi, double sigma)
+__global__ void thomas_diag_shift_kernel(double* S, double* Inv, int64_t n, int B, int64_t bi, double sigma, int* orig, int* active)
 {
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < B; r += gridDim.x * blockDim.x)
     {
+        orig[r] = r;
+        active[r] = 0;
         const int64_t row = bi * B + r;
         if (row < n)
             S[r + (int64_t) r * B] -= sigma;
@@ -743,6 +756,62 @@ __global__ void __launch_bounds__(256) block_gemv_kernel(const double* __restric
     }
 }
 
+// The same product with the columns split over gridDim.y CTAs per 32-row group (enough loads in flight to stream a large block at HBM
+// speed): every CTA writes the partial sums of its column range to `part`, the CTA that takes the last ticket of its row group adds them
+// in split order (fixed => bit-reproducible) and applies alpha / beta.  tickets[] must be zero on entry and is left zero.
+__global__ void __launch_bounds__(256) block_gemv_split_kernel(const double* __restrict__ M, const double* __restrict__ x, double* __restrict__ y, int64_t B, double alpha,
+                                                               double beta, double* part, unsigned int* tickets)
+{
+    __shared__ double s_part[8][32];
+    __shared__ unsigned int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nsplit = gridDim.y, split = blockIdx.y;
+    const int64_t r = (int64_t) blockIdx.x * 32 + lane;
+    const int64_t per = (B + nsplit - 1) / nsplit;
+    const int64_t c0 = (int64_t) split * per, c1 = c0 + per < B ? c0 + per : B;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (r < B)
+    {
+        int64_t c = c0 + warp;
+        for (; c + 24 < c1; c += 32)
+        {
+            const double m0 = M[r + c * B], m1 = M[r + (c + 8) * B], m2 = M[r + (c + 16) * B], m3 = M[r + (c + 24) * B];
+            a0 = fma(m0, x[c], a0);
+            a1 = fma(m1, x[c + 8], a1);
+            a2 = fma(m2, x[c + 16], a2);
+            a3 = fma(m3, x[c + 24], a3);
+        }
+        for (; c < c1; c += 8)
+            a0 = fma(M[r + c * B], x[c], a0);
+    }
+    s_part[warp][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (warp == 0 && r < B)
+    {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++)
+            t += s_part[w][lane];
+        part[(int64_t) split * B + r] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        s_last = atomicAdd(&tickets[blockIdx.x], 1u) == (unsigned int) (nsplit - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last == 0u)
+        return;
+    __threadfence();
+    if (warp == 0 && r < B)
+    {
+        double t = 0.0;
+        for (int q = 0; q < nsplit; q++)
+            t += part[(int64_t) q * B + r];
+        y[r] = (beta == 0.0 ? 0.0 : beta * y[r]) + alpha * t;
+    }
+    if (threadIdx.x == 0)
+        tickets[blockIdx.x] = 0u;
+}
+
 int grid_for(int64_t n, int block = 256)
 {
     const int sms = device_info().sm_count;
@@ -769,7 +838,20 @@ struct BandSolve
     DevBuf<int> ipiv;
     // wide bands: block-tridiagonal elimination (B = half-bandwidth > 32); factors ML / Sinv / GU, N blocks of B x B each
     bool thomas = false;
-    DevBuf<double> tML, tSinv, tGU, tS, tvec;
+    DevBuf<double> tML, tSinv, tGU, tS, tX, tpart;
+    DevBuf<unsigned int> ttick;
+    DevBuf<int> torig;  // [0, B): original row index per position, [B, 2B): active flags of the Inv columns (gj3_* kernels)
+    int tsplit = 1;
+#ifndef SB200_EMU
+    // the solve is a fixed sequence of 3 N launches on fixed buffers: captured once per factorisation, replayed per solve (SB200_SHIFT_GRAPH=0 turns it off)
+    cudaGraphExec_t tgraph[2] = {nullptr, nullptr};
+    ~BandSolve()
+    {
+        for (cudaGraphExec_t g : tgraph)
+            if (g)
+                cudaGraphExecDestroy(g);
+    }
+#endif
 };
 
 void band_destroy(BandSolve* b) { delete b; }
@@ -807,7 +889,7 @@ BandSolve* band_create(sb200_op* op)
         b->N = (A.n + b->B - 1) / b->B;
         b->levels = -1;  // marks the sequential block elimination in band_info()
         const size_t bb = (size_t) b->B * b->B;
-        const size_t need = sizeof(double) * (3 * (size_t) b->N * bb + 2 * bb + 4 * (size_t) b->N * b->B);
+        const size_t need = sizeof(double) * (3 * (size_t) b->N * bb + 2 * bb + 5 * (size_t) b->N * b->B + 17 * (size_t) b->B);
         size_t free_b = 0, total_b = 0;
         SB200_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
         SB200_REQUIRE(need <= free_b - free_b / 8, SB200_INVALID_ARGUMENT,
@@ -817,7 +899,21 @@ BandSolve* band_create(sb200_op* op)
         b->tSinv.alloc((size_t) b->N * bb);
         b->tGU.alloc((size_t) b->N * bb);
         b->tS.alloc(bb);
-        b->tvec.alloc((size_t) b->B);
+        {
+            // column splits of the solve's block products: about four CTAs per SM in total
+            const int64_t groups = (b->B + 31) / 32;
+            const int sms = device_info().sm_count;
+            b->tsplit = (int) std::max<int64_t>(1, std::min<int64_t>(16, (4 * (int64_t) sms + groups - 1) / groups));
+            if (b->B < 256)
+                b->tsplit = 1;
+            if (const char* e = std::getenv("SB200_SHIFT_SPLIT"))  // tests: force the split kernel on small blocks
+                b->tsplit = std::max(1, std::min(16, std::atoi(e)));
+            b->tpart.alloc((size_t) b->tsplit * b->B);
+            b->ttick.alloc((size_t) groups);
+            SB200_CUDA_CHECK(cudaMemsetAsync(b->ttick.get(), 0, sizeof(unsigned int) * (size_t) groups, op->stream));
+        }
+        b->tX.alloc((size_t) b->N * b->B);
+        b->torig.alloc(2 * (size_t) b->B);
         b->colk.alloc((size_t) b->B);
         b->scal.alloc(2);
         b->ipiv.alloc(1);
@@ -915,22 +1011,68 @@ static void bcr_solve_inplace(BandSolve* b, double* f, cudaStream_t st)
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 
-// one block-elimination solve in place on the padded vector f (N*B entries)
-static void thomas_solve_inplace(BandSolve* b, double* f, cudaStream_t st)
+// y = beta y + alpha M x for one B x B block of the factors
+static void thomas_gemv(BandSolve* b, const double* M, const double* x, double* y, double alpha, double beta, cudaStream_t st)
+{
+    const int64_t B = b->B;
+    const unsigned g = (unsigned) ((B + 31) / 32);
+    if (b->tsplit > 1)
+        block_gemv_split_kernel<<<dim3(g, (unsigned) b->tsplit), 256, 0, st>>>(M, x, y, B, alpha, beta, b->tpart.get(), b->ttick.get());
+    else
+        block_gemv_kernel<<<g, 256, 0, st>>>(M, x, y, B, alpha, beta);
+}
+
+// one block-elimination solve in place on the padded vector f (N*B entries): 3 N - 2 block products
+static void thomas_enqueue(BandSolve* b, double* f, cudaStream_t st)
 {
     const int64_t B = b->B, N = b->N;
     const size_t bb = (size_t) B * B;
-    const unsigned g = (unsigned) ((B + 31) / 32);
+    double* X = b->tX.get();
     for (int64_t i = 1; i < N; i++)  // g_i = f_i - ML_i g_{i-1}
-        block_gemv_kernel<<<g, 256, 0, st>>>(b->tML.get() + (size_t) i * bb, f + (i - 1) * B, f + i * B, B, -1.0, 1.0);
+        thomas_gemv(b, b->tML.get() + (size_t) i * bb, f + (i - 1) * B, f + i * B, -1.0, 1.0, st);
     for (int64_t i = N - 1; i >= 0; i--)  // x_i = Sinv_i g_i - GU_i x_{i+1}
     {
-        block_gemv_kernel<<<g, 256, 0, st>>>(b->tSinv.get() + (size_t) i * bb, f + i * B, b->tvec.get(), B, 1.0, 0.0);
+        thomas_gemv(b, b->tSinv.get() + (size_t) i * bb, f + i * B, X + i * B, 1.0, 0.0, st);
         if (i + 1 < N)
-            block_gemv_kernel<<<g, 256, 0, st>>>(b->tGU.get() + (size_t) i * bb, f + (i + 1) * B, b->tvec.get(), B, -1.0, 1.0);
-        SB200_CUDA_CHECK(cudaMemcpyAsync(f + i * B, b->tvec.get(), sizeof(double) * (size_t) B, cudaMemcpyDeviceToDevice, st));
+            thomas_gemv(b, b->tGU.get() + (size_t) i * bb, X + (i + 1) * B, X + i * B, -1.0, 1.0, st);
     }
-    b->launches += 4 * N - 2;
+    SB200_CUDA_CHECK(cudaMemcpyAsync(f, X, sizeof(double) * (size_t) (N * B), cudaMemcpyDeviceToDevice, st));
+}
+
+static void thomas_solve_inplace(BandSolve* b, double* f, cudaStream_t st)
+{
+#ifndef SB200_EMU
+    static const bool use_graph = [] { const char* e = std::getenv("SB200_SHIFT_GRAPH"); return !(e && e[0] == '0'); }();
+    const int which = f == b->xb.get() ? 0 : (f == b->rb.get() ? 1 : -1);
+    if (use_graph && which >= 0)
+    {
+        if (!b->tgraph[which])
+        {
+            cudaGraph_t graph = nullptr;
+            SB200_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            try
+            {
+                thomas_enqueue(b, f, st);
+            }
+            catch (...)
+            {
+                cudaStreamEndCapture(st, &graph);
+                if (graph)
+                    cudaGraphDestroy(graph);
+                throw;
+            }
+            SB200_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+            const cudaError_t e = cudaGraphInstantiate(&b->tgraph[which], graph, 0);
+            cudaGraphDestroy(graph);
+            SB200_CUDA_CHECK(e);
+        }
+        SB200_CUDA_CHECK(cudaGraphLaunch(b->tgraph[which], st));
+        b->launches += 1;
+        return;
+    }
+#endif
+    thomas_enqueue(b, f, st);
+    b->launches += 3 * b->N - 1;
     SB200_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -1060,7 +1202,7 @@ static void factor_thomas(sb200_op* op, BandSolve* b, double sigma)
         double* ML = b->tML.get() + (size_t) i * bb;
         SB200_CUDA_CHECK(cudaMemsetAsync(S, 0, sizeof(double) * bb, st));
         for_blocks([&](const int* rp, const int* ci, const double* v) { thomas_diag_scatter_kernel<<<gr, 256, 0, st>>>(rp, ci, v, n, B, i, S); });
-        thomas_diag_shift_kernel<<<gr, 256, 0, st>>>(S, Sinv, n, B, i, sigma);
+        thomas_diag_shift_kernel<<<gr, 256, 0, st>>>(S, Sinv, n, B, i, sigma, b->torig.get(), b->torig.get() + B);
         if (i > 0)
         {
             const double* Sprev = b->tSinv.get() + (size_t) (i - 1) * bb;
@@ -1070,9 +1212,9 @@ static void factor_thomas(sb200_op* op, BandSolve* b, double sigma)
         // Sinv_i = S^{-1}: the Gauss-Jordan kernels of the dense route on the (S | I) tableau
         for (int k = 0; k < B; k++)
         {
-            gj3_pivot_kernel<<<1, 1024, 0, st>>>(S, B, k, b->ipiv.get(), b->scal.get(), b->flag.get());
+            gj3_pivot_kernel<<<1, 1024, 0, st>>>(S, B, k, b->ipiv.get(), b->scal.get(), b->flag.get(), b->torig.get(), b->torig.get() + B);
             gj3_swap_scale_kernel<<<grid_for(2 * (int64_t) B), 256, 0, st>>>(S, Sinv, B, k, b->ipiv.get(), b->scal.get(), b->colk.get());
-            gj3_eliminate_kernel<<<ge, 256, 0, st>>>(S, Sinv, B, k, b->colk.get());
+            gj3_eliminate_kernel<<<ge, 256, 0, st>>>(S, Sinv, B, k, b->colk.get(), b->torig.get() + B);
         }
         if (i + 1 < N)
         {

@@ -340,3 +340,16 @@ def test_emu_row_sharded_arnoldi_factorization(emu):
     assert np.abs(V.T @ V - np.eye(m)).max() <= 1e-12
     ref = O.factorize(O.Csr.adopt(n, rp, ci, v), m, kind="arnoldi")
     assert np.abs(H - ref["H"]).max() <= 1e-9 * scale
+
+
+# ---------------------------------------------------------------- wide-band shift-solve route (round 2; GPU twins: tests/test_gpu_shift.py)
+def test_emu_shift_solve_mesh_route(emu):
+    # block-tridiagonal elimination with grid-wide block kernels on 9-point (2-D) and 27-point (3-D) stencil matrices, the split block
+    # products, a singular shift, and a complete SymEigsShiftSolver solve against ARPACK
+    import test_gpu_shift as S
+
+    S.test_shift_solve_operator_mesh(emu, (12, 9), True, "thomas")
+    S.test_shift_solve_operator_mesh(emu, (7, 6, 5), True, "thomas")
+    S.test_shift_solve_mesh_split_products(emu, (7, 6, 5), 16)
+    S.test_shift_solve_mesh_singular_shift_and_column_blocks(emu)
+    S.test_sym_shift_eigs_mesh_vs_arpack(emu, (9, 8, 7), True, "thomas", 4, 14)

@@ -137,6 +137,31 @@ def test_shift_solve_operator_mesh(gpu, dims, full, route):
     assert np.linalg.norm(M2 @ y2 - x) <= 1e-12 * np.linalg.norm(x) * max(1.0, np.abs(y2).max())
 
 
+@pytest.mark.parametrize("dims,split", [((12, 9), 3), ((7, 6, 5), 16), ((40, 35), 2)])
+def test_shift_solve_mesh_split_products(gpu, dims, split):
+    # the block products of the solve with their columns split over several CTAs and combined in ticket order (block_gemv_split_kernel;
+    # chosen automatically for blocks of 256 rows and more, forced here on small ones): same answer, bit-reproducible
+    n = int(np.prod(dims))
+    A = stencil_matrix(dims, True, seed=n)
+    old = os.environ.get("SB200_SHIFT_SPLIT")
+    os.environ["SB200_SHIFT_SPLIT"] = str(split)
+    try:
+        with _route("thomas"):
+            op = gpu.SparseSymShiftSolve(sp.tril(A).tocsc())
+    finally:
+        if old is None:
+            os.environ.pop("SB200_SHIFT_SPLIT", None)
+        else:
+            os.environ["SB200_SHIFT_SPLIT"] = old
+    op.set_shift(0.2)
+    x = np.random.default_rng(n).standard_normal(n)
+    y = op.perform_op(x)
+    M = (A - 0.2 * sp.identity(n)).tocsc()
+    y_ref = splu(M).solve(x)
+    assert np.abs(y - y_ref).max() <= 1e-9 * np.abs(y_ref).max()
+    assert np.array_equal(y, op.perform_op(x))
+
+
 def test_shift_solve_mesh_singular_shift_and_column_blocks(gpu):
     # a singular shift is reported like the reference's "factorization failed with the given shift" (SparseSymShiftSolve.h:93-94)
     n = 40 * 36
