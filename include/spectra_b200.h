@@ -138,10 +138,15 @@ int sb200_op_create_shift_solve(int64_t n, const void* outer, int outer_is_64, c
 /* set_shift(sigma) (SparseSymShiftSolve.h:85-95): factorises A - sigma I on the device.  SB200_INVALID_ARGUMENT
  * ("factorization failed with the given shift", :93-94) when a pivot block is singular or the verification solve fails. */
 int sb200_op_set_shift(sb200_op* op, double sigma);
-/* layout chosen for the factorisation: half-bandwidth found, block size B, number of block rows, reduction levels */
+/* layout chosen for the factorisation: half-bandwidth found, block size B, number of block rows, reduction levels (block cyclic
+ * reduction, half-bandwidth <= 32) or -1 (sequential block elimination with grid-wide block kernels: wider bands, mesh-like patterns) */
 int sb200_op_shift_solve_info(const sb200_op* op, int* half_bandwidth, int* block, int64_t* block_rows, int* levels);
-/* iterative-refinement steps per solve (0 or 1, default 1) */
+/* iterative-refinement steps per solve: 0 or 1 fixes it; a negative value (the default) lets set_shift() decide -- the refinement sweep is
+ * dropped when the plain solve of its verification right-hand side already has a relative residual <= 5e-14 */
 int sb200_op_shift_solve_refine(sb200_op* op, int steps);
+/* outcome of the last set_shift(): refinement steps in use, relative residual of the verification solve as the solves now run, and of
+ * the unrefined solve (-1 when it was not measured) */
+int sb200_op_shift_solve_status(const sb200_op* op, int* refine_steps, double* verify_residual, double* unrefined_residual);
 int sb200_op_rows(const sb200_op* op, int64_t* rows);      /* rows()  SparseSymMatProd.h:70 */
 int sb200_op_cols(const sb200_op* op, int64_t* cols);      /* cols()  SparseSymMatProd.h:74 */
 int sb200_op_local_rows(const sb200_op* op, int64_t* row0, int64_t* nrows);

@@ -513,7 +513,8 @@ class SparseHermMatProd:
 
 class SparseSymShiftSolve(_SparseOp):
     """MatOp/SparseSymShiftSolve.h — perform_op computes y = (A - sigma I)^{-1} x after set_shift(sigma).  Device
-    implementation: block cyclic reduction, banded matrices (half-bandwidth <= 32) only."""
+    implementation: block cyclic reduction for half-bandwidth <= 32, sequential block elimination with grid-wide block kernels for wider
+    bands / mesh-like patterns (as long as the 3 n b doubles of block factors fit in device memory), explicit inverse for n <= 2048."""
     _mode = 1
     _shift_solve = True
 
@@ -524,7 +525,14 @@ class SparseSymShiftSolve(_SparseOp):
         _check(lib().sb200_op_set_shift(self.h, C.c_double(sigma)))
 
     def set_refine(self, steps: int):
+        """0 / 1: fixed number of refinement steps per solve; negative: set_shift() decides (the default)."""
         _check(lib().sb200_op_shift_solve_refine(self.h, int(steps)))
+
+    def status(self) -> dict:
+        """Outcome of the last set_shift(): refinement steps in use and the relative residuals of its verification solve."""
+        steps, rel, rel0 = C.c_int(), C.c_double(), C.c_double()
+        _check(lib().sb200_op_shift_solve_status(self.h, C.byref(steps), C.byref(rel), C.byref(rel0)))
+        return dict(refine_steps=steps.value, verify_residual=rel.value, unrefined_residual=rel0.value)
 
     def layout(self) -> dict:
         bw, blk, lev, rows = C.c_int(), C.c_int(), C.c_int(), C.c_int64()

@@ -246,6 +246,13 @@ int sb200_op_shift_solve_refine(sb200_op* op, int steps)
     band_set_refine(op, steps);
     ABI_CATCH
 }
+int sb200_op_shift_solve_status(const sb200_op* op, int* refine_steps, double* verify_residual, double* unrefined_residual)
+{
+    ABI_TRY
+    ABI_NONNULL(op);
+    band_status(op, refine_steps, verify_residual, unrefined_residual);
+    ABI_CATCH
+}
 int sb200_op_rows(const sb200_op* op, int64_t* rows)
 {
     ABI_TRY

@@ -826,7 +826,9 @@ struct BandSolve
     int B = 0, levels = 0, first_top = 0, bw = 0;
     bool factored = false;
     double sigma = 0.0;
-    int refine = 1;
+    int refine = 1;        // refinement steps the solve performs (0 / 1)
+    int refine_mode = -1;  // -1: decided by set_shift (the unrefined verification residual), 0 / 1: fixed by band_set_refine()
+    double verify_rel = 0.0, verify_rel_unrefined = -1.0;
     DevBuf<double> D, Lo, Up, Dinv, GL, GU, ML, MU;
     DevBuf<double> xb, rb, t;
     DevBuf<int> flag;
@@ -1285,7 +1287,9 @@ void band_set_shift(sb200_op* op, double sigma)
     SB200_REQUIRE(h != 2, SB200_LOGIC, "band scatter met an entry outside the block tridiagonal");
     SB200_REQUIRE(h == 0, SB200_INVALID_ARGUMENT, "SparseSymShiftSolve: factorization failed with the given shift");
     b->factored = true;
-    // verification solve: relative residual of one deterministic right-hand side
+    // verification solve: relative residual of one deterministic right-hand side.  It also decides whether the solves need their
+    // refinement step: when the plain solve already reaches working precision (pivoted large blocks, diagonally dominant bands) the second
+    // sweep is dropped; block cyclic reduction on an indefinite shifted band (residual ~1e-11) keeps it.
     {
         std::vector<double> hx((size_t) A.n), hy((size_t) A.n), ht((size_t) A.n);
         uint64_t sstate = 0x9E3779B97F4A7C15ULL;
@@ -1296,21 +1300,41 @@ void band_set_shift(sb200_op* op, double sigma)
         }
         const size_t npad_v = std::max<size_t>((size_t) b->N * B, (size_t) A.n);
         DevBuf<double> dx((size_t) A.n), dy(npad_v), dt(npad_v);
-        dy.zero(st);
         SB200_CUDA_CHECK(cudaMemcpyAsync(dx.get(), hx.data(), sizeof(double) * A.n, cudaMemcpyHostToDevice, st));
-        band_solve_device(op, dx.get(), dy.get());
-        launch_spmv(op->A, op->plan, dy.get(), dt.get(), st);
-        SB200_CUDA_CHECK(cudaMemcpyAsync(hy.data(), dy.get(), sizeof(double) * A.n, cudaMemcpyDeviceToHost, st));
-        SB200_CUDA_CHECK(cudaMemcpyAsync(ht.data(), dt.get(), sizeof(double) * A.n, cudaMemcpyDeviceToHost, st));
-        SB200_CUDA_CHECK(cudaStreamSynchronize(st));
-        double rn = 0.0, xn = 0.0;
-        for (int64_t i = 0; i < A.n; i++)
+        auto residual = [&]() {
+            dy.zero(st);
+            band_solve_device(op, dx.get(), dy.get());
+            launch_spmv(op->A, op->plan, dy.get(), dt.get(), st);
+            SB200_CUDA_CHECK(cudaMemcpyAsync(hy.data(), dy.get(), sizeof(double) * A.n, cudaMemcpyDeviceToHost, st));
+            SB200_CUDA_CHECK(cudaMemcpyAsync(ht.data(), dt.get(), sizeof(double) * A.n, cudaMemcpyDeviceToHost, st));
+            SB200_CUDA_CHECK(cudaStreamSynchronize(st));
+            double rn = 0.0, xn = 0.0;
+            for (int64_t i = 0; i < A.n; i++)
+            {
+                const double r = hx[(size_t) i] - (ht[(size_t) i] - sigma * hy[(size_t) i]);
+                rn += r * r;
+                xn += hx[(size_t) i] * hx[(size_t) i];
+            }
+            return std::sqrt(rn / xn);
+        };
+        double rel;
+        b->verify_rel_unrefined = -1.0;
+        if (b->refine_mode < 0)
         {
-            const double r = hx[(size_t) i] - (ht[(size_t) i] - sigma * hy[(size_t) i]);
-            rn += r * r;
-            xn += hx[(size_t) i] * hx[(size_t) i];
+            b->refine = 0;
+            rel = b->verify_rel_unrefined = residual();
+            if (!(rel <= 5e-14))
+            {
+                b->refine = 1;
+                rel = residual();
+            }
         }
-        const double rel = std::sqrt(rn / xn);
+        else
+        {
+            b->refine = b->refine_mode;
+            rel = residual();
+        }
+        b->verify_rel = rel;
         if (!(rel <= 1e-8))
         {
             b->factored = false;
@@ -1335,10 +1359,26 @@ void band_info(const sb200_op* op, int* half_bandwidth, int* block, int64_t* blo
         *levels = b->levels;
 }
 
+void band_status(const sb200_op* op, int* refine_steps, double* verify_residual, double* unrefined_residual)
+{
+    const BandSolve* b = op->band;
+    SB200_REQUIRE(b != nullptr, SB200_INVALID_ARGUMENT, "operator is not a shift-solve operator");
+    SB200_REQUIRE(b->factored, SB200_LOGIC, "SparseSymShiftSolve: set_shift() has not been called");
+    if (refine_steps)
+        *refine_steps = b->refine;
+    if (verify_residual)
+        *verify_residual = b->verify_rel;
+    if (unrefined_residual)
+        *unrefined_residual = b->verify_rel_unrefined;
+}
+
 void band_set_refine(sb200_op* op, int steps)
 {
     SB200_REQUIRE(op->band != nullptr, SB200_INVALID_ARGUMENT, "operator is not a shift-solve operator");
-    op->band->refine = steps > 0 ? 1 : 0;
+    // steps < 0: back to the automatic choice made by the next set_shift(); 0 / >= 1: fixed from now on (also for the current factorisation)
+    op->band->refine_mode = steps < 0 ? -1 : (steps > 0 ? 1 : 0);
+    if (steps >= 0)
+        op->band->refine = op->band->refine_mode;
 }
 
 }  // namespace sb200

@@ -47,6 +47,7 @@ void band_set_shift(sb200_op* op, double sigma);
 void band_solve_device(sb200_op* op, const double* x_dev, double* y_dev);
 void band_info(const sb200_op* op, int* half_bandwidth, int* block, int64_t* block_rows, int* levels);
 void band_set_refine(sb200_op* op, int steps);
+void band_status(const sb200_op* op, int* refine_steps, double* verify_residual, double* unrefined_residual);
 
 }  // namespace sb200
 
