@@ -651,6 +651,311 @@ __global__ void gj3_eliminate_kernel(double* M, double* Inv, int64_t n, int k, c
     }
 }
 
+// ---- blocked Gauss-Jordan inverse of a large diagonal block (wide-band route, B >= 128): pivots are taken in panels of kGjP columns.
+// Per panel: (1) partial-pivoting LU of a copy of the panel columns by ONE CTA fixes the kGjP pivot rows; (2) the row swaps are applied to
+// the (M | Inv) tableau; (3) the kGjP x kGjP pivot block A_KK is inverted in shared memory; (4) the pivot rows become A_KK^{-1} T(K, :);
+// (5) every other row gets T(r, :) -= A_RK(r, :) T(K, :) -- a rank-kGjP update done in 64 x 64 tiles through shared memory, so the tableau is
+// streamed once per PANEL instead of once per pivot (1/32 of the traffic of the rank-1 form, ~6 launches per 32 pivots instead of 96).
+constexpr int kGjP = 32;
+
+__global__ void __launch_bounds__(1024) gjb_panel_kernel(const double* __restrict__ M, int64_t B, int k0, int pw, double* work, int* piv, int* flag)
+{
+    __shared__ double s_best[32];
+    __shared__ int s_arg[32];
+    __shared__ int s_p;
+    __shared__ double s_row[kGjP];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int64_t e = tid; e < (B - k0) * pw; e += nt)
+    {
+        const int64_t r = k0 + e % (B - k0);
+        const int j = (int) (e / (B - k0));
+        work[r + (int64_t) j * B] = M[r + (int64_t) (k0 + j) * B];
+    }
+    __syncthreads();
+    for (int k = 0; k < pw; k++)
+    {
+        double best = -1.0;
+        int arg = k0 + k;
+        for (int64_t r = k0 + k + tid; r < B; r += nt)
+        {
+            const double a = fabs(work[r + (int64_t) k * B]);
+            if (a > best)
+            {
+                best = a;
+                arg = (int) r;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ob > best || (ob == best && oa < arg))
+            {
+                best = ob;
+                arg = oa;
+            }
+        }
+        if ((tid & 31) == 0)
+        {
+            s_best[tid >> 5] = best;
+            s_arg[tid >> 5] = arg;
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            for (int w = 1; w < (nt >> 5); w++)
+                if (s_best[w] > best || (s_best[w] == best && s_arg[w] < arg))
+                {
+                    best = s_best[w];
+                    arg = s_arg[w];
+                }
+            s_p = arg;
+            piv[k] = arg;
+            if (!(best > 0.0))
+                *flag = 1;
+        }
+        __syncthreads();
+        const int p = s_p;
+        if (tid < pw)
+        {
+            const double a = work[(k0 + k) + (int64_t) tid * B], b = work[p + (int64_t) tid * B];
+            work[p + (int64_t) tid * B] = a;
+            work[(k0 + k) + (int64_t) tid * B] = b;
+            s_row[tid] = b;  // pivot row k of the panel after the swap
+        }
+        __syncthreads();
+        const double pv = s_row[k];
+        const double inv_pv = pv != 0.0 ? 1.0 / pv : 0.0;
+        for (int64_t r = k0 + k + 1 + tid; r < B; r += nt)
+        {
+            const double l = work[r + (int64_t) k * B] * inv_pv;
+            if (l != 0.0)
+                for (int c = k + 1; c < pw; c++)
+                    work[r + (int64_t) c * B] = fma(-l, s_row[c], work[r + (int64_t) c * B]);
+        }
+        __syncthreads();
+    }
+}
+
+// the panel's row swaps on every tableau column (in pivot order); block 0 / thread 0 keeps the row bookkeeping of the Inv half
+__global__ void gjb_swap_kernel(double* M, double* Inv, int64_t B, int k0, int pw, const int* __restrict__ piv, int* orig, int* active)
+{
+    for (int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; c < 2 * B; c += (int64_t) gridDim.x * blockDim.x)
+    {
+        double* X = c < B ? M + c * B : Inv + (c - B) * B;
+        for (int k = 0; k < pw; k++)
+        {
+            const int p = piv[k];
+            if (p != k0 + k)
+            {
+                const double a = X[k0 + k];
+                X[k0 + k] = X[p];
+                X[p] = a;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int k = 0; k < pw; k++)
+        {
+            const int p = piv[k];
+            const int o = orig[p];
+            orig[p] = orig[k0 + k];
+            orig[k0 + k] = o;
+            active[o] = 1;
+        }
+}
+
+// A_KK^{-1} (pw x pw, column-major with leading dimension kGjP) by Gauss-Jordan with partial pivoting in shared memory: one warp
+__global__ void __launch_bounds__(32) gjb_kk_kernel(const double* __restrict__ M, int64_t B, int k0, int pw, double* Akk_inv, int* flag)
+{
+    __shared__ double a[kGjP][kGjP + 1], v[kGjP][kGjP + 1];
+    const int lane = threadIdx.x;
+    for (int i = 0; i < pw; i++)
+    {
+        a[i][lane] = lane < pw ? M[(k0 + i) + (int64_t) (k0 + lane) * B] : 0.0;
+        v[i][lane] = (i == lane) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    for (int k = 0; k < pw; k++)
+    {
+        double best = (lane >= k && lane < pw) ? fabs(a[lane][k]) : -1.0;
+        int arg = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ob > best || (ob == best && oa < arg))
+            {
+                best = ob;
+                arg = oa;
+            }
+        }
+        if (!(best > 0.0))
+        {
+            if (lane == 0)
+                *flag = 1;
+            break;
+        }
+        // lane = column index: swap rows k and arg, scale row k
+        {
+            const double ak = a[k][lane], ap = a[arg][lane], vk = v[k][lane], vp = v[arg][lane];
+            __syncwarp();
+            a[arg][lane] = ak;
+            v[arg][lane] = vk;
+            const double pvt = __shfl_sync(0xffffffffu, ap, k);  // a(arg, k) before the swap = the pivot
+            a[k][lane] = ap / pvt;
+            v[k][lane] = vp / pvt;
+        }
+        __syncwarp();
+        for (int r = 0; r < pw; r++)
+        {
+            if (r == k)
+                continue;
+            const double f = a[r][k];
+            __syncwarp();
+            if (f != 0.0)
+            {
+                a[r][lane] = fma(-f, a[k][lane], a[r][lane]);
+                v[r][lane] = fma(-f, v[k][lane], v[r][lane]);
+            }
+            __syncwarp();
+        }
+    }
+    for (int i = 0; i < kGjP; i++)  // the whole kGjP x kGjP array is defined: zero outside the pw x pw block
+        Akk_inv[i + lane * kGjP] = (i < pw && lane < pw) ? v[i][lane] : 0.0;
+}
+
+// tableau column c takes part in the panel's update: M columns right of the panel, Inv columns whose original row has been a pivot row
+__device__ __forceinline__ bool gjb_col_live(int64_t c, int64_t B, int k0, int pw, const int* __restrict__ active)
+{
+    return c < B ? c >= k0 + pw : (c < 2 * B && active[c - B] != 0);
+}
+
+// ARK <- the panel columns of M (all rows; only rows outside the pivot rows are used); pivot rows: T(K, c) <- A_KK^{-1} T(K, c), also kept
+// in TK (kGjP x 2B); panel columns of the pivot rows become the identity
+__global__ void __launch_bounds__(256) gjb_rows_kernel(double* M, double* Inv, int64_t B, int k0, int pw, const double* __restrict__ Akk_inv, double* ARK, double* TK,
+                                                       const int* __restrict__ active)
+{
+    __shared__ double s_inv[kGjP * kGjP];
+    for (int e = threadIdx.x; e < kGjP * kGjP; e += blockDim.x)
+        s_inv[e] = Akk_inv[e];
+    __syncthreads();
+    for (int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < B * pw; e += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int64_t r = e % B;
+        if (r >= k0 && r < k0 + pw)
+            continue;  // pivot rows are rewritten below by other threads; their ARK entries are never read
+        ARK[e] = M[r + (int64_t) (k0 + e / B) * B];
+    }
+    for (int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; c < 2 * B; c += (int64_t) gridDim.x * blockDim.x)
+    {
+        double* X = c < B ? M + c * B : Inv + (c - B) * B;
+        if (c >= k0 && c < k0 + pw)
+        {
+            for (int i = 0; i < pw; i++)
+                X[k0 + i] = (c - k0 == i) ? 1.0 : 0.0;
+            continue;
+        }
+        if (!gjb_col_live(c, B, k0, pw, active))
+            continue;
+        double t[kGjP];
+#pragma unroll
+        for (int j = 0; j < kGjP; j++)
+            t[j] = j < pw ? X[k0 + j] : 0.0;
+        for (int i = 0; i < pw; i++)
+        {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < kGjP; j++)
+                acc = fma(s_inv[i + j * kGjP], t[j], acc);
+            X[k0 + i] = acc;
+            TK[i + c * kGjP] = acc;
+        }
+    }
+}
+
+// T(r, c) -= sum_j ARK(r, j) TK(j, c) for rows outside the pivot rows and live columns: 64 x 64 tiles, 256 threads, 4 x 4 outputs per thread
+__global__ void __launch_bounds__(256) gjb_update_kernel(double* M, double* Inv, int64_t B, int k0, int pw, const double* __restrict__ ARK, const double* __restrict__ TK,
+                                                         const int* __restrict__ active)
+{
+    __shared__ double As[kGjP][64 + 1];   // As[j][i] = ARK(r0 + i, j)
+    __shared__ double Ts[kGjP][64 + 1];   // Ts[j][cc] = TK(j, c0 + cc), zero for columns that are not live
+    __shared__ int s_any;
+    const int64_t r0 = (int64_t) blockIdx.x * 64, c0 = (int64_t) blockIdx.y * 64;
+    const int tid = threadIdx.x;
+    if (tid == 0)
+        s_any = 0;
+    __syncthreads();
+    if (tid < 64 && gjb_col_live(c0 + tid, B, k0, pw, active))
+        s_any = 1;
+    __syncthreads();
+    if (!s_any)
+        return;
+    for (int e = tid; e < kGjP * 64; e += 256)
+    {
+        const int i = e % 64, j = e / 64;
+        const int64_t r = r0 + i;
+        As[j][i] = (j < pw && r < B && (r < k0 || r >= k0 + pw)) ? ARK[r + (int64_t) j * B] : 0.0;
+    }
+    for (int e = tid; e < kGjP * 64; e += 256)
+    {
+        const int j = e % kGjP, cc = e / kGjP;
+        const int64_t c = c0 + cc;
+        Ts[j][cc] = (j < pw && gjb_col_live(c, B, k0, pw, active)) ? TK[j + c * kGjP] : 0.0;
+    }
+    __syncthreads();
+    const int tx = tid & 15, ty = tid >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            acc[a][b] = 0.0;
+    for (int j = 0; j < kGjP; j++)
+    {
+        double av[4], tv[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+            av[a] = As[j][tx + 16 * a];
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            tv[b] = Ts[j][ty + 16 * b];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                acc[a][b] = fma(av[a], tv[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+    {
+        const int64_t c = c0 + ty + 16 * b;
+        if (!gjb_col_live(c, B, k0, pw, active))
+            continue;
+        double* X = c < B ? M + c * B : Inv + (c - B) * B;
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+        {
+            const int64_t r = r0 + tx + 16 * a;
+            if (r < B && (r < k0 || r >= k0 + pw) && acc[a][b] != 0.0)
+                X[r] -= acc[a][b];
+        }
+    }
+}
+
+// panel columns of the rows outside the pivot rows are eliminated exactly
+__global__ void gjb_clear_panel_kernel(double* M, int64_t B, int k0, int pw)
+{
+    for (int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < B * pw; e += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int64_t r = e % B;
+        if (r < k0 || r >= k0 + pw)
+            M[r + (int64_t) (k0 + e / B) * B] = 0.0;
+    }
+}
+
 // ---- wide bands: block-tridiagonal elimination with grid-wide block kernels (see the header) ----
 // S (B x B, column-major) += entries of block row `bi` of the CSR whose column lies in block `bi`
 __global__ void thomas_diag_scatter_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, int64_t n, int B, int64_t bi,
@@ -842,7 +1147,9 @@ struct BandSolve
     bool thomas = false;
     DevBuf<double> tML, tSinv, tGU, tS, tX, tpart;
     DevBuf<unsigned int> ttick;
-    DevBuf<int> torig;  // [0, B): original row index per position, [B, 2B): active flags of the Inv columns (gj3_* kernels)
+    DevBuf<int> torig;  // [0, B): original row index per position, [B, 2B): active flags of the Inv columns (gj3_* / gjb_* kernels)
+    DevBuf<double> twork, tark, ttk, tkk;  // blocked Gauss-Jordan: panel copy, A_RK, T(K, :), A_KK^{-1}
+    DevBuf<int> tpiv;
     int tsplit = 1;
 #ifndef SB200_EMU
     // the solve is a fixed sequence of 3 N launches on fixed buffers: captured once per factorisation, replayed per solve (SB200_SHIFT_GRAPH=0 turns it off)
@@ -1197,6 +1504,22 @@ static void factor_thomas(sb200_op* op, BandSolve* b, double sigma)
     b->tML.zero(st);
     b->tSinv.zero(st);
     b->tGU.zero(st);
+    const bool blocked = [&] {
+        const char* e = std::getenv("SB200_SHIFT_GJ");
+        if (e && std::string(e) == "rank1")
+            return false;
+        if (e && std::string(e) == "blocked")
+            return true;
+        return B >= 128;
+    }();
+    if (blocked && b->twork.n == 0)
+    {
+        b->twork.alloc((size_t) B * kGjP);
+        b->tark.alloc((size_t) B * kGjP);
+        b->ttk.alloc((size_t) kGjP * 2 * (size_t) B);
+        b->tkk.alloc((size_t) kGjP * kGjP);
+        b->tpiv.alloc(kGjP);
+    }
     for (int64_t i = 0; i < N; i++)
     {
         double* S = b->tS.get();
@@ -1211,7 +1534,22 @@ static void factor_thomas(sb200_op* op, BandSolve* b, double sigma)
             for_blocks([&](const int* rp, const int* ci, const double* v) { thomas_sparse_dense_kernel<<<gb, 256, 0, st>>>(rp, ci, v, n, B, i, i - 1, Sprev, ML, 1.0); });
             for_blocks([&](const int* rp, const int* ci, const double* v) { thomas_dense_sparse_t_kernel<<<gb, 256, 0, st>>>(rp, ci, v, n, B, i, i - 1, ML, S, -1.0); });
         }
-        // Sinv_i = S^{-1}: the Gauss-Jordan kernels of the dense route on the (S | I) tableau
+        // Sinv_i = S^{-1} by Gauss-Jordan on the (S | I) tableau: blocked (panels of kGjP pivots) for large blocks, rank-1 updates otherwise
+        if (blocked)
+        {
+            const dim3 gt((unsigned) ((B + 63) / 64), (unsigned) ((2 * (int64_t) B + 63) / 64));
+            for (int k0 = 0; k0 < B; k0 += kGjP)
+            {
+                const int pw = std::min(kGjP, B - k0);
+                gjb_panel_kernel<<<1, 1024, 0, st>>>(S, B, k0, pw, b->twork.get(), b->tpiv.get(), b->flag.get());
+                gjb_swap_kernel<<<grid_for(2 * (int64_t) B), 256, 0, st>>>(S, Sinv, B, k0, pw, b->tpiv.get(), b->torig.get(), b->torig.get() + B);
+                gjb_kk_kernel<<<1, 32, 0, st>>>(S, B, k0, pw, b->tkk.get(), b->flag.get());
+                gjb_rows_kernel<<<grid_for(2 * (int64_t) B), 256, 0, st>>>(S, Sinv, B, k0, pw, b->tkk.get(), b->tark.get(), b->ttk.get(), b->torig.get() + B);
+                gjb_update_kernel<<<gt, 256, 0, st>>>(S, Sinv, B, k0, pw, b->tark.get(), b->ttk.get(), b->torig.get() + B);
+                gjb_clear_panel_kernel<<<grid_for((int64_t) B * pw), 256, 0, st>>>(S, B, k0, pw);
+            }
+        }
+        else
         for (int k = 0; k < B; k++)
         {
             gj3_pivot_kernel<<<1, 1024, 0, st>>>(S, B, k, b->ipiv.get(), b->scal.get(), b->flag.get(), b->torig.get(), b->torig.get() + B);

@@ -352,4 +352,6 @@ def test_emu_shift_solve_mesh_route(emu):
     S.test_shift_solve_operator_mesh(emu, (7, 6, 5), True, "thomas")
     S.test_shift_solve_mesh_split_products(emu, (7, 6, 5), 16)
     S.test_shift_solve_mesh_singular_shift_and_column_blocks(emu)
+    S.test_shift_solve_mesh_inverse_variants(emu, (5, 8, 9), True, "blocked")
+    S.test_shift_solve_mesh_inverse_variants(emu, (3, 2), True, "blocked")
     S.test_sym_shift_eigs_mesh_vs_arpack(emu, (9, 8, 7), True, "thomas", 4, 14)

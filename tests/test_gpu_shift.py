@@ -162,6 +162,34 @@ def test_shift_solve_mesh_split_products(gpu, dims, split):
     assert np.array_equal(y, op.perform_op(x))
 
 
+@pytest.mark.parametrize("variant", ["blocked", "rank1"])
+@pytest.mark.parametrize("dims,full", [((8, 80), True), ((5, 8, 9), True), ((3, 2), True), ((12, 9), True)])
+def test_shift_solve_mesh_inverse_variants(gpu, dims, full, variant):
+    # the diagonal blocks are inverted by Gauss-Jordan with partial pivoting: in panels of 32 pivots with a tiled rank-32 update (default for
+    # blocks of 128 rows and more) or by rank-1 updates; both on every size here (several panels, a ragged last panel, a single short panel)
+    n = int(np.prod(dims))
+    A = stencil_matrix(dims, full, seed=3)
+    old = os.environ.get("SB200_SHIFT_GJ")
+    os.environ["SB200_SHIFT_GJ"] = variant
+    try:
+        with _route("thomas"):
+            op = gpu.SparseSymShiftSolve(sp.tril(A).tocsc())
+        op.set_shift(0.37)
+    finally:
+        if old is None:
+            os.environ.pop("SB200_SHIFT_GJ", None)
+        else:
+            os.environ["SB200_SHIFT_GJ"] = old
+    st = op.status()
+    assert st["verify_residual"] <= 5e-14 and st["refine_steps"] in (0, 1)
+    x = np.random.default_rng(2).standard_normal(n)
+    y = op.perform_op(x)
+    M = (A - 0.37 * sp.identity(n)).tocsc()
+    y_ref = splu(M).solve(x)
+    assert np.abs(y - y_ref).max() <= 1e-9 * np.abs(y_ref).max()
+    assert np.linalg.norm(M @ y - x) <= 1e-12 * np.linalg.norm(x) * max(1.0, np.abs(y).max())
+
+
 def test_shift_solve_mesh_singular_shift_and_column_blocks(gpu):
     # a singular shift is reported like the reference's "factorization failed with the given shift" (SparseSymShiftSolve.h:93-94)
     n = 40 * 36
