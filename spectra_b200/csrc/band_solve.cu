@@ -1194,13 +1194,27 @@ BandSolve* band_create(sb200_op* op)
     if (want_thomas)
     {
         b->thomas = true;
-        b->B = std::max(b->bw, 4);
-        b->N = (A.n + b->B - 1) / b->B;
         b->levels = -1;  // marks the sequential block elimination in band_info()
-        const size_t bb = (size_t) b->B * b->B;
-        const size_t need = sizeof(double) * (3 * (size_t) b->N * bb + 2 * bb + 5 * (size_t) b->N * b->B + 17 * (size_t) b->B);
         size_t free_b = 0, total_b = 0;
         SB200_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        auto bytes_for = [&](int64_t Bq) {
+            const size_t Nq = (size_t) ((A.n + Bq - 1) / Bq), bbq = (size_t) Bq * Bq;
+            return sizeof(double) * (3 * Nq * bbq + 2 * bbq + 5 * Nq * (size_t) Bq + 17 * (size_t) Bq);
+        };
+        // Block size: any B >= half-bandwidth keeps the block-tridiagonal form.  A solve is 3 N sequential block products, so narrow bands with
+        // many block rows would be launch bound; merging m = floor(Bmin / b) band-widths per block (B ~ 1000) trades a larger factor stream
+        // (3 n B doubles) and inverse (n B^2 flops) for m times fewer steps.  SB200_SHIFT_BMIN overrides the target (0: B = b).
+        const int64_t b0 = std::max(b->bw, 4);
+        int64_t bmin = 1024;
+        if (const char* e = std::getenv("SB200_SHIFT_BMIN"))
+            bmin = std::max(0, std::atoi(e));
+        int64_t m = std::max<int64_t>(1, bmin / b0);
+        while (m > 1 && (b0 * m > A.n || bytes_for(b0 * m) > free_b / 2))
+            m--;
+        b->B = (int) (b0 * m);
+        b->N = (A.n + b->B - 1) / b->B;
+        const size_t bb = (size_t) b->B * b->B;
+        const size_t need = bytes_for(b->B);
         SB200_REQUIRE(need <= free_b - free_b / 8, SB200_INVALID_ARGUMENT,
                       "SparseSymShiftSolve: half-bandwidth " + std::to_string(b->bw) + " at n = " + std::to_string(A.n) + " needs " + std::to_string(need >> 20) +
                           " MiB of block factors, more than the free device memory; the device shift-solve handles banded / mesh-like patterns only");

@@ -354,4 +354,5 @@ def test_emu_shift_solve_mesh_route(emu):
     S.test_shift_solve_mesh_singular_shift_and_column_blocks(emu)
     S.test_shift_solve_mesh_inverse_variants(emu, (5, 8, 9), True, "blocked")
     S.test_shift_solve_mesh_inverse_variants(emu, (3, 2), True, "blocked")
+    S.test_shift_solve_mesh_merged_blocks(emu, (40, 9), True, 30)
     S.test_sym_shift_eigs_mesh_vs_arpack(emu, (9, 8, 7), True, "thomas", 4, 14)

@@ -87,17 +87,25 @@ _ON_EMULATOR = os.environ.get("SB200_TEST_BACKEND") == "emu"
 
 
 @contextlib.contextmanager
-def _route(name):
-    old = os.environ.get("SB200_SHIFT_ROUTE")
+def _route(name, bmin=None):
+    """Force a factorisation route (small cases would take the dense inverse by default); a forced route also pins the block size to the
+    half-bandwidth (SB200_SHIFT_BMIN=0) unless `bmin` says otherwise -- the default merges band-widths into blocks of ~1000 rows."""
+    new = {}
     if name:
-        os.environ["SB200_SHIFT_ROUTE"] = name
+        new["SB200_SHIFT_ROUTE"] = name
+        new["SB200_SHIFT_BMIN"] = "0" if bmin is None else str(bmin)
+    elif bmin is not None:
+        new["SB200_SHIFT_BMIN"] = str(bmin)
+    old = {k: os.environ.get(k) for k in new}
+    os.environ.update(new)
     try:
         yield
     finally:
-        if old is None:
-            os.environ.pop("SB200_SHIFT_ROUTE", None)
-        else:
-            os.environ["SB200_SHIFT_ROUTE"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 # ---- wide bands / mesh-like patterns (round 2): block-tridiagonal elimination with grid-wide block kernels (band_solve.cu, factor_thomas) ----
@@ -115,7 +123,9 @@ def test_shift_solve_operator_mesh(gpu, dims, full, route):
         op = gpu.SparseSymShiftSolve(sp.tril(A).tocsc())
     lay = op.layout()
     stride = int(np.prod(dims[1:]))
-    assert lay["half_bandwidth"] >= stride and lay["levels"] == -1 and lay["block"] == max(4, lay["half_bandwidth"])
+    b0 = max(4, lay["half_bandwidth"])
+    assert lay["half_bandwidth"] >= stride and lay["levels"] == -1 and lay["block"] % b0 == 0 and lay["block"] <= max(b0, 1024)
+    assert lay["block"] == b0 if route else lay["block"] == b0 * max(1, 1024 // b0)  # forced routes pin B = b; the default merges band-widths
     assert lay["block_rows"] == -(-n // lay["block"])
     op.set_shift(sigma)
     rng = np.random.default_rng(n)
@@ -160,6 +170,25 @@ def test_shift_solve_mesh_split_products(gpu, dims, split):
     y_ref = splu(M).solve(x)
     assert np.abs(y - y_ref).max() <= 1e-9 * np.abs(y_ref).max()
     assert np.array_equal(y, op.perform_op(x))
+
+
+@pytest.mark.parametrize("dims,full,bmin", [((40, 9), True, 30), ((30, 35), False, 80), ((6, 5, 4), True, 100), ((33, 3), False, 10)])
+def test_shift_solve_mesh_merged_blocks(gpu, dims, full, bmin):
+    # several band-widths merged into one block (B = floor(bmin / b) b): fewer, larger steps per solve; same answer
+    n = int(np.prod(dims))
+    A = stencil_matrix(dims, full, seed=11)
+    with _route("thomas", bmin=bmin):
+        op = gpu.SparseSymShiftSolve(sp.tril(A).tocsc())
+    lay = op.layout()
+    b0 = max(4, lay["half_bandwidth"])
+    assert lay["block"] == b0 * max(1, bmin // b0) and lay["block"] > b0 and lay["block_rows"] == -(-n // lay["block"])
+    op.set_shift(-0.4)
+    x = np.random.default_rng(3).standard_normal(n)
+    y = op.perform_op(x)
+    M = (A + 0.4 * sp.identity(n)).tocsc()
+    y_ref = splu(M).solve(x)
+    assert np.abs(y - y_ref).max() <= 1e-9 * np.abs(y_ref).max()
+    assert np.linalg.norm(M @ y - x) <= 1e-12 * np.linalg.norm(x) * max(1.0, np.abs(y).max())
 
 
 @pytest.mark.parametrize("variant", ["blocked", "rank1"])
