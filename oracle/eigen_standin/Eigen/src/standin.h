@@ -835,6 +835,14 @@ public:
         else
             conservativeResize(1, n);
     }
+    // vector of n equally spaced values from low to high
+    Matrix& setLinSpaced(Index n, const S& low, const S& high)
+    {
+        resize(n);
+        for (Index i = 0; i < n; i++)
+            (*this)[i] = n > 1 ? S(low + (high - low) * i / (n - 1)) : high;
+        return *this;
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1058,6 +1066,13 @@ public:
             res[i] = m_a[i] - v;
         return res;
     }
+    Array operator+(const S& v) const
+    {
+        Array res(size());
+        for (Index i = 0; i < size(); i++)
+            res[i] = m_a[i] + v;
+        return res;
+    }
     Index count() const
     {
         Index n = 0;
@@ -1188,6 +1203,16 @@ public:
         return res;
     }
 };
+// scalar / array, coefficient-wise (SymEigsShiftSolver.h:167: lambda = 1 / nu + sigma)
+template <typename S>
+Array<S, Dynamic, 1> operator/(const S& v, const ArrayRef<S>& a)
+{
+    Array<S, Dynamic, 1> res(a.size());
+    for (Index i = 0; i < a.size(); i++)
+        res[i] = v / a[i];
+    return res;
+}
+
 template <typename S, int R, int C>
 Array<S, R, C>::Array(const ArrayRef<S>& r) : m_a(static_cast<size_t>(r.size()))
 {
@@ -1318,6 +1343,8 @@ class SparseMatrixBase
 {
 public:
     const Derived& derived() const { return *static_cast<const Derived*>(this); }
+    Index rows() const { return derived().sm_rows(); }
+    Index cols() const { return derived().sm_cols(); }
 };
 
 template <typename S, int Flags = ColMajor, typename StorageIndex = int>
@@ -1351,6 +1378,8 @@ public:
     enum { IsRowMajor = (Flags & RowMajor) ? 1 : 0 };
     Index rows() const { return m_d.rows; }
     Index cols() const { return m_d.cols; }
+    Index sm_rows() const { return m_d.rows; }
+    Index sm_cols() const { return m_d.cols; }
     Index nonZeros() const { return m_d.nnz; }
     Index outerSize() const { return IsRowMajor ? m_d.rows : m_d.cols; }
     const SparseData<S, Flags, StorageIndex>& raw() const { return m_d; }
@@ -1440,6 +1469,57 @@ private:
 public:
     SparseMatrix() { m_outer.assign(1, 0); }
     SparseMatrix(Index rows, Index cols) { resize(rows, cols); }
+    // the full (Hermitian) matrix a selfadjointView<Uplo> stands for: the stored triangle plus its conjugated mirror, real diagonal
+    template <int Uplo>
+    SparseMatrix(const SparseSelfAdjointView<S, Flags, StorageIndex, Uplo>& v)
+    {
+        const auto& d = v.d;
+        resize(d.rows, d.cols);
+        std::vector<Triplet<S, StorageIndex>> t;
+        const Index no = IsRowMajor ? d.rows : d.cols;
+        for (Index o = 0; o < no; o++)
+            for (Index k = d.outer[o]; k < d.outer[o + 1]; k++)
+            {
+                const Index in = d.inner[k];
+                const Index r = IsRowMajor ? o : in, c = IsRowMajor ? in : o;
+                if ((Uplo == Lower) ? r < c : r > c)
+                    continue;
+                if (r == c)
+                    t.emplace_back(StorageIndex(r), StorageIndex(c), S(numext::real(d.values[k])));
+                else
+                {
+                    t.emplace_back(StorageIndex(r), StorageIndex(c), d.values[k]);
+                    t.emplace_back(StorageIndex(c), StorageIndex(r), numext::conj(d.values[k]));
+                }
+            }
+        setFromTriplets(t.begin(), t.end());
+    }
+    void setIdentity()
+    {
+        std::vector<Triplet<S, StorageIndex>> t;
+        for (Index i = 0; i < (std::min)(m_rows, m_cols); i++)
+            t.emplace_back(StorageIndex(i), StorageIndex(i), S(1));
+        setFromTriplets(t.begin(), t.end());
+    }
+    // eager sparse arithmetic: alpha * A + beta * B as a new compressed matrix (entries that cancel stay stored, as in Eigen)
+    static SparseMatrix combine(const S& alpha, const SparseMatrix& A, const S& beta, const SparseMatrix& Bm)
+    {
+        SparseMatrix R(A.rows(), A.cols());
+        std::vector<Triplet<S, StorageIndex>> t;
+        auto push = [&](const SparseMatrix& X, const S& f) {
+            const auto& d = X.raw();
+            for (Index o = 0; o < X.outerSize(); o++)
+                for (Index k = d.outer[o]; k < d.outer[o + 1]; k++)
+                    t.emplace_back(StorageIndex(IsRowMajor ? o : d.inner[k]), StorageIndex(IsRowMajor ? d.inner[k] : o), f * d.values[k]);
+        };
+        push(A, alpha);
+        push(Bm, beta);
+        R.setFromTriplets(t.begin(), t.end());
+        return R;
+    }
+    friend SparseMatrix operator*(const S& f, const SparseMatrix& A) { return combine(f, A, S(0), SparseMatrix(A.rows(), A.cols())); }
+    friend SparseMatrix operator-(const SparseMatrix& A, const SparseMatrix& Bm) { return combine(S(1), A, S(-1), Bm); }
+    friend SparseMatrix operator+(const SparseMatrix& A, const SparseMatrix& Bm) { return combine(S(1), A, S(1), Bm); }
 
     void resize(Index rows, Index cols)
     {
@@ -1452,6 +1532,8 @@ public:
     }
     Index rows() const { return m_rows; }
     Index cols() const { return m_cols; }
+    Index sm_rows() const { return m_rows; }
+    Index sm_cols() const { return m_cols; }
     Index outerSize() const { return IsRowMajor ? m_rows : m_cols; }
     Index innerSize() const { return IsRowMajor ? m_cols : m_rows; }
     bool isCompressed() const { return m_innernnz.empty(); }
@@ -1649,6 +1731,8 @@ class Map<const SparseMatrix<S, Flags, StorageIndex>, void>
 public:
     using PlainObject = SparseMatrix<S, Flags, StorageIndex>;
     using Scalar = S;
+    using SparseCompressedBase<S, Flags, StorageIndex>::rows;
+    using SparseCompressedBase<S, Flags, StorageIndex>::cols;
     Map(Index rows, Index cols, Index nnz, const StorageIndex* outer, const StorageIndex* inner, const S* values)
     {
         this->m_d.rows = rows;
@@ -1751,6 +1835,107 @@ Matrix<S, Dynamic, Dynamic> operator*(const SparseSelfAdjointView<S, Flags, Stor
     }
     return y;
 }
+
+// Eigen::SparseLU as MatOp/SparseSymShiftSolve.h uses it (:51, :91-94, :108): compute() / info() / solve().  Stand-in: LU with partial
+// pivoting on LAPACK band storage (the DGBTF2 / DGBTRS algorithm), with the band limits read off the pattern -- a direct P A = L U solve
+// like SuperLU's; the factors differ from Eigen's supernodal ones, the solve result does not (to rounding).  A zero pivot gives
+// info() == NumericalIssue, which the reference turns into "factorization failed with the given shift".
+template <typename MatrixType>
+class SparseLU
+{
+    using S = typename MatrixType::Scalar;
+    Index m_n = 0, m_kl = 0, m_ku = 0, m_ld = 0;
+    std::vector<S> m_ab;
+    std::vector<Index> m_ipiv;
+    ComputationInfo m_info = InvalidInput;
+    S& ab(Index i, Index j) { return m_ab[size_t((m_kl + m_ku + i - j) + j * m_ld)]; }  // A(i, j), max(0, j - ku - kl) <= i <= min(n - 1, j + kl)
+    const S& ab(Index i, Index j) const { return m_ab[size_t((m_kl + m_ku + i - j) + j * m_ld)]; }
+
+public:
+    SparseLU() {}
+    void isSymmetric(bool) {}
+    ComputationInfo info() const { return m_info; }
+    void compute(const MatrixType& A)
+    {
+        const auto& d = A.raw();
+        const bool row_major = MatrixType::IsRowMajor != 0;
+        m_n = A.rows();
+        m_kl = m_ku = 0;
+        for (Index o = 0; o < A.outerSize(); o++)
+            for (Index k = d.outer[o]; k < d.outer[o + 1]; k++)
+            {
+                const Index r = row_major ? o : d.inner[k], c = row_major ? d.inner[k] : o;
+                m_kl = (std::max)(m_kl, r - c);
+                m_ku = (std::max)(m_ku, c - r);
+            }
+        m_ld = 2 * m_kl + m_ku + 1;
+        m_ab.assign(size_t(m_ld * m_n), S(0));
+        for (Index o = 0; o < A.outerSize(); o++)
+            for (Index k = d.outer[o]; k < d.outer[o + 1]; k++)
+            {
+                const Index r = row_major ? o : d.inner[k], c = row_major ? d.inner[k] : o;
+                ab(r, c) += d.values[k];
+            }
+        m_ipiv.assign(size_t(m_n), 0);
+        m_info = Success;
+        for (Index j = 0; j < m_n; j++)
+        {
+            const Index last = (std::min)(m_n - 1, j + m_kl);
+            Index p = j;
+            for (Index i = j + 1; i <= last; i++)
+                if (std::abs(ab(i, j)) > std::abs(ab(p, j)))
+                    p = i;
+            m_ipiv[size_t(j)] = p;
+            if (ab(p, j) == S(0))
+            {
+                m_info = NumericalIssue;
+                return;
+            }
+            const Index cmax = (std::min)(m_n - 1, j + m_ku + m_kl);
+            if (p != j)
+                for (Index c = j; c <= cmax; c++)
+                    std::swap(ab(j, c), ab(p, c));
+            const S inv = S(1) / ab(j, j);
+            for (Index i = j + 1; i <= last; i++)
+            {
+                const S l = ab(i, j) * inv;
+                ab(i, j) = l;
+                if (l != S(0))
+                    for (Index c = j + 1; c <= cmax; c++)
+                        ab(i, c) -= l * ab(j, c);
+            }
+        }
+    }
+    template <typename Rhs>
+    Matrix<S, Dynamic, Dynamic> solve(const MatrixBase<Rhs>& b) const
+    {
+        if (m_info != Success)
+            throw std::logic_error("Eigen stand-in: SparseLU::solve() without a successful compute()");
+        Matrix<S, Dynamic, Dynamic> x(b);
+        for (Index col = 0; col < x.cols(); col++)
+        {
+            for (Index j = 0; j < m_n; j++)
+            {
+                const Index p = m_ipiv[size_t(j)];
+                if (p != j)
+                    std::swap(x(j, col), x(p, col));
+                const S xj = x(j, col);
+                if (xj != S(0))
+                    for (Index i = j + 1; i <= (std::min)(m_n - 1, j + m_kl); i++)
+                        x(i, col) -= ab(i, j) * xj;
+            }
+            for (Index j = m_n - 1; j >= 0; j--)
+            {
+                x(j, col) /= ab(j, j);
+                const S xj = x(j, col);
+                if (xj != S(0))
+                    for (Index i = (std::max)(Index(0), j - m_ku - m_kl); i < j; i++)
+                        x(i, col) -= ab(i, j) * xj;
+            }
+        }
+        return x;
+    }
+};
 
 using MatrixXd = Matrix<double, Dynamic, Dynamic>;
 using VectorXd = Matrix<double, Dynamic, 1>;

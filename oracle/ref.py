@@ -409,3 +409,29 @@ def givens_complex(x, y):
     c = C.c_double()
     lib().ref_givens_complex(C.c_double(x.real), C.c_double(x.imag), C.c_double(y.real), C.c_double(y.imag), r, C.byref(c), s)
     return complex(r[0], r[1]), c.value, complex(s[0], s[1])
+
+
+# ---------------------------------------------------------------- shift-and-invert (SymEigsShiftSolver + SparseSymShiftSolve)
+def shift_solve(A: Compressed, sigma, x, uplo="lower"):
+    """SparseSymShiftSolve<double, Uplo>(A).set_shift(sigma); perform_op(x) = (A - sigma I)^{-1} x  (A column-major)."""
+    assert A.order == 0
+    x = _f64(x)
+    y = np.empty(A.n)
+    _check(lib().ref_shift_solve(0 if uplo == "lower" else 1, C.byref(A.c), C.c_double(sigma), _p(x), _p(y)))
+    return y
+
+
+def sym_shift_eigs(A: Compressed, sigma, nev, ncv, selection=0, maxit=1000, tol=1e-10, sorting=3, init_resid=None, uplo="lower", want_vectors=True) -> EigsResult:
+    """SymEigsShiftSolver<SparseSymShiftSolve<double, Uplo>>(op, nev, ncv, sigma)."""
+    assert A.order == 0
+    n = A.n
+    res = _RefResult()
+    evals = np.zeros(nev)
+    evecs = np.zeros(n * nev) if want_vectors else None
+    r0 = _f64(init_resid) if init_resid is not None else None
+    _check(lib().ref_sym_shift_eigs(0 if uplo == "lower" else 1, C.byref(A.c), C.c_double(sigma), C.c_int64(nev), C.c_int64(ncv), int(selection), C.c_int64(maxit),
+                                    C.c_double(tol), int(sorting), _p(r0), _p(evals), _p(evecs), C.byref(res)))
+    nconv = int(res.nconv)
+    vec = evecs.reshape((n, -1), order="F")[:, :nconv].copy() if want_vectors and nconv else None
+    return EigsResult(nconv=nconv, niter=int(res.niter), nops=int(res.nops), info=int(res.info), eigenvalues=evals[:nconv].copy(), eigenvectors=vec,
+                      reorth_passes=-1, expand_calls=-1, restarts=-1, steps=-1, seconds=float(res.seconds))

@@ -14,6 +14,8 @@
 #include <Spectra/SymEigsSolver.h>
 #include <Spectra/GenEigsSolver.h>
 #include <Spectra/HermEigsSolver.h>
+#include <Spectra/SymEigsShiftSolver.h>
+#include <Spectra/MatOp/SparseSymShiftSolve.h>
 #include <Spectra/MatOp/SparseHermMatProd.h>
 #include <Spectra/MatOp/SparseSymMatProd.h>
 #include <Spectra/MatOp/SparseGenMatProd.h>
@@ -716,6 +718,71 @@ void ref_givens_complex(double xr, double xi, double yr, double yi, double* r_ri
     *c = cc;
     s_ri[0] = s.real();
     s_ri[1] = s.imag();
+}
+
+}  // extern "C"
+
+// ---- shift-and-invert (BASELINE config 5) ------------------------------------------
+// SymEigsShiftSolver<SparseSymShiftSolve<double, Uplo, ColMajor>> (SymEigsShiftSolver.h:148-196, MatOp/SparseSymShiftSolve.h:30-110).  The
+// reference's set_shift() builds A - sigma I from the stored triangle and hands it to Eigen::SparseLU -- here the stand-in's band LU with
+// partial pivoting -- and sort_ritzpair() maps nu back to lambda = 1 / nu + sigma.
+extern "C" {
+
+int ref_shift_solve(int uplo, const Compressed* A, double sigma, const double* x, double* y)
+{
+    REF_TRY
+    SpMap<Eigen::ColMajor> mat(A->n, A->n, A->nnz, A->outer, A->inner, A->val);
+    if (uplo == 0)
+    {
+        Spectra::SparseSymShiftSolve<double, Eigen::Lower> op(mat);
+        op.set_shift(sigma);
+        op.perform_op(x, y);
+    }
+    else
+    {
+        Spectra::SparseSymShiftSolve<double, Eigen::Upper> op(mat);
+        op.set_shift(sigma);
+        op.perform_op(x, y);
+    }
+    REF_CATCH
+}
+
+int ref_sym_shift_eigs(int uplo, const Compressed* A, double sigma, int64_t nev, int64_t ncv, int selection, int64_t maxit, double tol, int sorting,
+                       const double* init_resid, double* evals, double* evecs, RefResult* res)
+{
+    REF_TRY
+    SpMap<Eigen::ColMajor> mat(A->n, A->n, A->nnz, A->outer, A->inner, A->val);
+    auto run = [&](auto& op) {
+        using Op = typename std::remove_reference<decltype(op)>::type;
+        Spectra::SymEigsShiftSolver<Op> eigs(op, nev, ncv, sigma);
+        const double t0 = now_s();
+        if (init_resid)
+            eigs.init(init_resid);
+        else
+            eigs.init();
+        const Index nconv = eigs.compute(Spectra::SortRule(selection), maxit, tol, Spectra::SortRule(sorting));
+        res->seconds = now_s() - t0;
+        res->nconv = nconv;
+        res->niter = eigs.num_iterations();
+        res->nops = eigs.num_operations();
+        res->info = int32_t(eigs.info());
+        Vector ev = eigs.eigenvalues();
+        if (evals)
+            std::memcpy(evals, ev.data(), sizeof(double) * size_t(ev.size()));
+        if (evecs)
+            mat_to(eigs.eigenvectors(), evecs);
+    };
+    if (uplo == 0)
+    {
+        Spectra::SparseSymShiftSolve<double, Eigen::Lower> op(mat);
+        run(op);
+    }
+    else
+    {
+        Spectra::SparseSymShiftSolve<double, Eigen::Upper> op(mat);
+        run(op);
+    }
+    REF_CATCH
 }
 
 }  // extern "C"

@@ -11,7 +11,7 @@ import scipy.sparse as sp
 
 import oracle as O
 from oracle import ref as R
-from helpers import readme_banded, sym_full
+from helpers import readme_banded, stencil_matrix, sym_full
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(R._LIB_PATH), reason="oracle/_ref/libspectra_ref.so is not in the snapshot")]
 
@@ -124,6 +124,32 @@ def test_complex_gen_eigs_vs_reference(gpu, n):
         ref = R.gen_eigs_complex(R.CompressedZG(A.tocsr()), k, m, int(gpu.SortRule[rule]), 300)
         assert ref.info == O.Successful and g.info() == gpu.CompInfo.Successful and nconv == ref.nconv == k
         assert np.abs(np.sort_complex(g.eigenvalues()) - np.sort_complex(ref.eigenvalues)).max() <= 1e-10 * np.abs(ref.eigenvalues).max()
+
+
+@pytest.mark.parametrize("case", ["banded", "mesh", "fixture"])
+def test_sym_shift_eigs_vs_reference(gpu, case):
+    # SymEigsShiftSolver<SparseSymShiftSolve<double>> (BASELINE config 5's solver): the device against the reference's own driver
+    # (set_shift, lambda = 1 / nu + sigma, sorting) over the stand-in's band LU -- banded (block cyclic reduction on the device), a 27-point
+    # stencil, and the reference's random sparse fixture (test/SymEigsShift.cpp:148-186)
+    if case == "banded":
+        from spectra_b200 import synth
+
+        n, sigma, k, m = 20_000, 0.5, 10, 30
+        rp, ci, v = synth.band_csr(n, 15, 0, 0.0)
+        A = sp.csr_matrix((v, ci, rp), shape=(n, n)).tocsc()
+    elif case == "mesh":
+        A, sigma, k, m = stencil_matrix((9, 8, 7), True, seed=7), 0.11, 4, 14
+    else:
+        A, sigma, k, m = sym_full(O.gen_sparse_data(100, 0.1)).tocsc(), 10.0, 10, 20
+    op = gpu.SparseSymShiftSolve(sp.tril(A).tocsc())
+    eigs = gpu.SymEigsShiftSolver(op, k, m, sigma)
+    eigs.init()
+    nconv = eigs.compute(gpu.SortRule.LargestMagn)
+    ref = R.sym_shift_eigs(R.Compressed.from_scipy(sp.csc_matrix(A)), sigma, k, m, O.LargestMagn, want_vectors=False)
+    assert ref.info == O.Successful and eigs.info() == gpu.CompInfo.Successful and nconv == ref.nconv == k
+    evals = eigs.eigenvalues()
+    assert np.abs(np.sort(evals) - np.sort(ref.eigenvalues)).max() <= 1e-10 * max(1.0, np.abs(ref.eigenvalues).max())
+    assert abs(eigs.num_operations() - ref.nops) <= max(30, ref.nops // 5)
 
 
 def test_c2_full_size_vs_reference_golden(gpu):
