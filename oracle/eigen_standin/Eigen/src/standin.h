@@ -23,7 +23,9 @@
 #include <complex>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <limits>
+#include <ostream>
 #include <stdexcept>
 #include <type_traits>
 #include <utility>
@@ -34,7 +36,7 @@ namespace Eigen {
 using Index = std::ptrdiff_t;
 enum : int { Dynamic = -1 };
 enum : int { ColMajor = 0, RowMajor = 1 };
-enum : int { Lower = 1, Upper = 2 };
+enum : int { Lower = 1, Upper = 2, StrictlyLower = 9, StrictlyUpper = 10, UnitLower = 5, UnitUpper = 6 };
 enum ComputationInfo { Success = 0, NumericalIssue = 1, NoConvergence = 2, InvalidInput = 3 };
 
 // ------------------------------------------------------------------------------------------------
@@ -118,6 +120,23 @@ struct is_scalar<std::complex<T>> : std::true_type
 template <typename A, typename B>
 using prod_t = decltype(std::declval<A>() * std::declval<B>());
 
+// Random(): uniform in [-1, 1] from std::rand(), as Eigen's default does (the reference's tests seed it with std::srand(123))
+template <typename T>
+struct random_scalar
+{
+    static T run() { return T(2.0 * double(std::rand()) / double(RAND_MAX) - 1.0); }
+};
+template <typename T>
+struct random_scalar<std::complex<T>>
+{
+    static std::complex<T> run()
+    {
+        const T re = random_scalar<T>::run();
+        const T im = random_scalar<T>::run();
+        return std::complex<T>(re, im);
+    }
+};
+
 // "Packets" for UpperHessenbergSchur.h's hand-vectorised Householder update (:204-270): two lanes,
 // element-wise arithmetic, so the results equal the scalar loop's.
 template <typename T>
@@ -162,6 +181,10 @@ template <typename S>
 class JacobiRotation;
 template <typename S>
 class AdjointView;
+template <typename S, int Uplo>
+class DenseSelfAdjointView;
+template <typename S>
+class DiagonalWrapper;
 
 namespace internal {
 template <typename T>
@@ -375,10 +398,104 @@ public:
     auto tail(Index n) const { return segment(size() - n, n); }
 
     AdjointView<Scalar> adjoint() const { return AdjointView<Scalar>(DynView(ptr_(), rows(), cols(), rs(), cs())); }
-    AdjointView<Scalar> transpose() const
+    Matrix<Scalar, Dynamic, Dynamic> transpose() const  // evaluated on the spot (used by the reference's tests, not by its solvers)
     {
-        static_assert(!NumTraits<Scalar>::IsComplex, "transpose() of complex objects is not provided by the stand-in");
-        return adjoint();
+        Matrix<Scalar, Dynamic, Dynamic> res(cols(), rows());
+        for (Index j = 0; j < cols(); j++)
+            for (Index i = 0; i < rows(); i++)
+                res(j, i) = coeff(i, j);
+        return res;
+    }
+
+    // ---- what the reference's own unit tests (test/*.cpp) use on top of the solver headers ----
+    template <int Uplo>
+    DenseSelfAdjointView<Scalar, Uplo> selfadjointView() const
+    {
+        return DenseSelfAdjointView<Scalar, Uplo>(DynView(ptr_(), rows(), cols(), rs(), cs()));
+    }
+    // triangularView<Mode>(): converts to a plain matrix (zeros outside the triangle); setZero() clears the triangle in place
+    template <int Mode>
+    struct TriView
+    {
+        DynView v;
+        static bool inside(Index i, Index j)
+        {
+            return Mode == Upper ? i <= j : (Mode == Lower ? i >= j : (Mode == StrictlyLower ? i > j : (Mode == StrictlyUpper ? i < j : false)));
+        }
+        operator Matrix<Scalar, Dynamic, Dynamic>() const
+        {
+            Matrix<Scalar, Dynamic, Dynamic> res(v.rows(), v.cols());
+            for (Index j = 0; j < v.cols(); j++)
+                for (Index i = 0; i < v.rows(); i++)
+                    if (inside(i, j))
+                        res(i, j) = v.coeff(i, j);
+            return res;
+        }
+        void setZero()
+        {
+            for (Index j = 0; j < v.cols(); j++)
+                for (Index i = 0; i < v.rows(); i++)
+                    if (inside(i, j))
+                        v.coeffRef(i, j) = Scalar(0);
+        }
+    };
+    template <int Mode>
+    TriView<Mode> triangularView() const { return TriView<Mode>{DynView(ptr_(), rows(), cols(), rs(), cs())}; }
+    DiagonalWrapper<Scalar> asDiagonal() const { return DiagonalWrapper<Scalar>(ColView(ptr_(), size(), 1, lstride(), 0)); }
+    DynView topLeftCorner(Index r, Index c) const { return block(0, 0, r, c); }
+    DynView bottomRightCorner(Index r, Index c) const { return block(rows() - r, cols() - c, r, c); }
+    template <int N>
+    DynView rightCols() const { return block(0, cols() - N, rows(), N); }
+    template <int N>
+    DynView leftCols() const { return block(0, 0, rows(), N); }
+    Matrix<Scalar, Dynamic, Dynamic> eval() const { return Matrix<Scalar, Dynamic, Dynamic>(derived()); }
+    Matrix<Scalar, Dynamic, Dynamic> inverse() const;  // Gauss-Jordan with partial pivoting (tests only)
+    template <typename Other>
+    bool isApprox(const MatrixBase<Other>& o, const RealScalar& prec = RealScalar(sizeof(RealScalar) == 4 ? 1e-5 : 1e-12)) const  // NumTraits::dummy_precision()
+    {
+        // Eigen: ||a - b||^2 <= prec^2 min(||a||^2, ||b||^2)
+        if (o.rows() != rows() || o.cols() != cols())
+            return false;
+        RealScalar d(0);
+        for (Index j = 0; j < cols(); j++)
+            for (Index i = 0; i < rows(); i++)
+                d += numext::abs2(coeff(i, j) - o.coeff(i, j));
+        return d <= prec * prec * (std::min)(squaredNorm(), o.squaredNorm());
+    }
+    Scalar maxCoeff(Index* idx) const
+    {
+        Scalar m = coeff(0);
+        *idx = 0;
+        for (Index i = 1; i < size(); i++)
+            if (coeff(i) > m)
+            {
+                m = coeff(i);
+                *idx = i;
+            }
+        return m;
+    }
+    Scalar minCoeff() const
+    {
+        Scalar m = coeff(0, 0);
+        for (Index j = 0; j < cols(); j++)
+            for (Index i = 0; i < rows(); i++)
+                if (coeff(i, j) < m)
+                    m = coeff(i, j);
+        return m;
+    }
+    Scalar trace() const
+    {
+        Scalar t(0);
+        for (Index i = 0; i < (std::min)(rows(), cols()); i++)
+            t += coeff(i, i);
+        return t;
+    }
+    Derived& setRandom()
+    {
+        for (Index j = 0; j < cols(); j++)
+            for (Index i = 0; i < rows(); i++)
+                coeffRef(i, j) = internal::random_scalar<Scalar>::run();
+        return derived();
     }
 
     // real(): the object itself for real scalars, a real copy for complex ones
@@ -569,7 +686,17 @@ public:
         return res;
     }
 
-    ArrayRef<Scalar> array() const { return ArrayRef<Scalar>(ptr_(), size(), lstride()); }
+    // coefficient-wise view: vectors by their stride, contiguous matrices flattened in storage order
+    ArrayRef<Scalar> array() const
+    {
+        if (cols() > 1 && rows() > 1)
+        {
+            if (!(rs() == 1 && cs() == rows()))
+                throw std::logic_error("Eigen stand-in: array() of a non-contiguous matrix block");
+            return ArrayRef<Scalar>(ptr_(), size(), 1);
+        }
+        return ArrayRef<Scalar>(ptr_(), size(), lstride());
+    }
 
     // ---- plane rotations (Eigen 3.4.0 Jacobi.h: apply_rotation_in_the_plane(x, y, j) is
     // x_i <- c x_i + conj(s) y_i ; y_i <- -s x_i + conj(c) y_i; applyOnTheLeft passes rows p, q and j,
@@ -676,8 +803,36 @@ template <typename S>
 class AdjointView
 {
 public:
+    using Scalar = S;
     View<S, Dynamic, Dynamic> m;  // the object whose adjoint this is
     explicit AdjointView(const View<S, Dynamic, Dynamic>& v) : m(v) {}
+    Index rows() const { return m.cols(); }
+    Index cols() const { return m.rows(); }
+    Matrix<S, Dynamic, Dynamic> eval() const;
+};
+
+template <typename S, int Uplo>
+class DenseSelfAdjointView
+{
+public:
+    View<S, Dynamic, Dynamic> m;
+    explicit DenseSelfAdjointView(const View<S, Dynamic, Dynamic>& v) : m(v) {}
+    // entry (i, j) of the Hermitian matrix the stored triangle stands for
+    S at(Index i, Index j) const
+    {
+        if (i == j)
+            return S(numext::real(m.coeff(i, i)));
+        const bool stored = (Uplo == Lower) ? i > j : i < j;
+        return stored ? m.coeff(i, j) : numext::conj(m.coeff(j, i));
+    }
+};
+
+template <typename S>
+class DiagonalWrapper
+{
+public:
+    View<S, Dynamic, 1> d;
+    explicit DiagonalWrapper(const View<S, Dynamic, 1>& v) : d(v) {}
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -774,6 +929,23 @@ public:
         return *this;
     }
 
+    // M << a, b, c, ...;  row by row
+    struct CommaInit
+    {
+        Matrix& m;
+        Index k;
+        CommaInit& operator,(const S& v)
+        {
+            m(k / m.cols(), k % m.cols()) = v;
+            k++;
+            return *this;
+        }
+    };
+    CommaInit operator<<(const S& v)
+    {
+        (*this)(0, 0) = v;
+        return CommaInit{*this, 1};
+    }
     // Matrix <-> Matrix swap exchanges storage (Arnoldi.h:337, UpperHessenbergSchur.h swap_T/swap_U)
     void swap(Matrix& o)
     {
@@ -816,6 +988,29 @@ public:
         Matrix m(n);
         m.setConstant(v);
         return m;
+    }
+    static Matrix Random(Index r, Index c)
+    {
+        Matrix m(r, c);
+        m.setRandom();
+        return m;
+    }
+    static Matrix Random(Index n)
+    {
+        Matrix m(n);
+        m.setRandom();
+        return m;
+    }
+    static Matrix Identity(Index n)
+    {
+        Matrix m(n, n);
+        m.setIdentity();
+        return m;
+    }
+    template <typename SA>
+    Matrix(const AdjointView<SA>& a) : m_r(0), m_c(0)
+    {
+        assign_(a.eval());
     }
     // keeps the leading block
     void conservativeResize(Index r, Index c)
@@ -1009,6 +1204,108 @@ Matrix<internal::prod_t<SA, typename B::Scalar>, Dynamic, Dynamic> operator*(con
     return res;
 }
 
+template <typename S>
+Matrix<S, Dynamic, Dynamic> AdjointView<S>::eval() const
+{
+    Matrix<S, Dynamic, Dynamic> res(m.cols(), m.rows());
+    for (Index j = 0; j < m.rows(); j++)
+        for (Index i = 0; i < m.cols(); i++)
+            res(i, j) = numext::conj(m.coeff(j, i));
+    return res;
+}
+// an adjoint / transpose anywhere else in an expression is evaluated first (the reference's unit tests: Q.adjoint() * H * Q, mat + mat.transpose(), ...)
+template <typename A, typename SB>
+auto operator*(const MatrixBase<A>& a, const AdjointView<SB>& b) -> decltype(a * b.eval()) { return a * b.eval(); }
+template <typename SA, typename SB>
+auto operator*(const AdjointView<SA>& a, const AdjointView<SB>& b) -> decltype(a * b.eval()) { return a * b.eval(); }
+template <typename A, typename SB>
+auto operator+(const MatrixBase<A>& a, const AdjointView<SB>& b) -> decltype(a + b.eval()) { return a + b.eval(); }
+template <typename A, typename SB>
+auto operator-(const MatrixBase<A>& a, const AdjointView<SB>& b) -> decltype(a - b.eval()) { return a - b.eval(); }
+template <typename SA, typename B>
+auto operator+(const AdjointView<SA>& a, const MatrixBase<B>& b) -> decltype(a.eval() + b) { return a.eval() + b; }
+template <typename SA, typename B>
+auto operator-(const AdjointView<SA>& a, const MatrixBase<B>& b) -> decltype(a.eval() - b) { return a.eval() - b; }
+
+// selfadjointView<Uplo>(A) * B and A * diag(d) for dense objects
+template <typename S, int Uplo, typename B>
+Matrix<internal::prod_t<S, typename B::Scalar>, Dynamic, Dynamic> operator*(const DenseSelfAdjointView<S, Uplo>& a, const MatrixBase<B>& b)
+{
+    using RS = internal::prod_t<S, typename B::Scalar>;
+    const Index n = a.m.rows();
+    Matrix<RS, Dynamic, Dynamic> res(n, b.cols());
+    for (Index j = 0; j < b.cols(); j++)
+        for (Index k = 0; k < n; k++)
+        {
+            const auto bk = b.coeff(k, j);
+            for (Index i = 0; i < n; i++)
+                res(i, j) += a.at(i, k) * bk;
+        }
+    return res;
+}
+template <typename A, typename S>
+Matrix<internal::prod_t<typename A::Scalar, S>, Dynamic, Dynamic> operator*(const MatrixBase<A>& a, const DiagonalWrapper<S>& d)
+{
+    Matrix<internal::prod_t<typename A::Scalar, S>, Dynamic, Dynamic> res(a.rows(), a.cols());
+    for (Index j = 0; j < a.cols(); j++)
+        for (Index i = 0; i < a.rows(); i++)
+            res(i, j) = a.coeff(i, j) * d.d.coeff(j);
+    return res;
+}
+
+template <typename Derived>
+std::ostream& operator<<(std::ostream& os, const MatrixBase<Derived>& m)
+{
+    for (Index i = 0; i < m.rows(); i++)
+    {
+        for (Index j = 0; j < m.cols(); j++)
+            os << (j ? " " : "") << m.coeff(i, j);
+        if (i + 1 < m.rows())
+            os << "\n";
+    }
+    return os;
+}
+template <typename S>
+std::ostream& operator<<(std::ostream& os, const AdjointView<S>& a) { return os << a.eval(); }
+
+template <typename Derived>
+Matrix<typename MatrixBase<Derived>::Scalar, Dynamic, Dynamic> MatrixBase<Derived>::inverse() const
+{
+    const Index n = rows();
+    Matrix<Scalar, Dynamic, Dynamic> a(derived()), inv = Matrix<Scalar, Dynamic, Dynamic>::Identity(n, n);
+    for (Index k = 0; k < n; k++)
+    {
+        Index p = k;
+        for (Index i = k + 1; i < n; i++)
+            if (std::abs(a(i, k)) > std::abs(a(p, k)))
+                p = i;
+        for (Index j = 0; j < n; j++)
+        {
+            std::swap(a(k, j), a(p, j));
+            std::swap(inv(k, j), inv(p, j));
+        }
+        const Scalar piv = a(k, k);
+        for (Index j = 0; j < n; j++)
+        {
+            a(k, j) /= piv;
+            inv(k, j) /= piv;
+        }
+        for (Index i = 0; i < n; i++)
+        {
+            if (i == k)
+                continue;
+            const Scalar f = a(i, k);
+            if (f != Scalar(0))
+                for (Index j = 0; j < n; j++)
+                {
+                    a(i, j) -= f * a(k, j);
+                    inv(i, j) -= f * inv(k, j);
+                }
+        }
+    }
+    return inv;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Arrays (coefficient-wise world): only what HermEigsBase / GenEigsBase / UpperHessenbergQR touch
 // ------------------------------------------------------------------------------------------------
@@ -1073,6 +1370,29 @@ public:
             res[i] = m_a[i] + v;
         return res;
     }
+    Array operator/(const S& v) const
+    {
+        Array res(size());
+        for (Index i = 0; i < size(); i++)
+            res[i] = m_a[i] / v;
+        return res;
+    }
+    S maxCoeff() const
+    {
+        S m = m_a.at(0);
+        for (Index i = 1; i < size(); i++)
+            if (m_a[i] > m)
+                m = m_a[i];
+        return m;
+    }
+    Array log10() const
+    {
+        Array res(size());
+        for (Index i = 0; i < size(); i++)
+            res[i] = std::log10(m_a[i]);
+        return res;
+    }
+    S mean() const { return sum() / S(size()); }
     Index count() const
     {
         Index n = 0;
@@ -1200,6 +1520,13 @@ public:
         Array<RealScalar, Dynamic, 1> res(m_n);
         for (Index i = 0; i < m_n; i++)
             res[i] = std::abs(m_p[i * m_s]);
+        return res;
+    }
+    Array<S, Dynamic, 1> operator/(const S& v) const
+    {
+        Array<S, Dynamic, 1> res(m_n);
+        for (Index i = 0; i < m_n; i++)
+            res[i] = m_p[i * m_s] / v;
         return res;
     }
 };
@@ -1494,6 +1821,17 @@ public:
             }
         setFromTriplets(t.begin(), t.end());
     }
+    SparseMatrix transpose() const
+    {
+        SparseMatrix R(m_cols, m_rows);
+        std::vector<Triplet<S, StorageIndex>> t;
+        const auto& d = raw();
+        for (Index o = 0; o < outerSize(); o++)
+            for (Index k = d.outer[o]; k < d.outer[o + 1]; k++)
+                t.emplace_back(StorageIndex(IsRowMajor ? d.inner[k] : o), StorageIndex(IsRowMajor ? o : d.inner[k]), d.values[k]);
+        R.setFromTriplets(t.begin(), t.end());
+        return R;
+    }
     void setIdentity()
     {
         std::vector<Triplet<S, StorageIndex>> t;
@@ -1717,7 +2055,7 @@ public:
 };
 
 template <typename S, int Flags, typename StorageIndex, typename B>
-Matrix<S, Dynamic, Dynamic> operator*(const SparseMatrix<S, Flags, StorageIndex>& A, const MatrixBase<B>& x)
+Matrix<internal::prod_t<S, typename B::Scalar>, Dynamic, Dynamic> operator*(const SparseMatrix<S, Flags, StorageIndex>& A, const MatrixBase<B>& x)
 {
     Ref<const SparseMatrix<S, Flags, StorageIndex>> r(A);
     return static_cast<const SparseCompressedBase<S, Flags, StorageIndex>&>(r) * x;
@@ -1759,17 +2097,18 @@ public:
 // y = A x, A general compressed (SparseGenMatProd.h:86): row-major = one dot product per row,
 // column-major = scaled columns accumulated in column order (Eigen's sparse_time_dense_product)
 template <typename S, int Flags, typename StorageIndex, typename B>
-Matrix<S, Dynamic, Dynamic> operator*(const SparseCompressedBase<S, Flags, StorageIndex>& A, const MatrixBase<B>& x)
+Matrix<internal::prod_t<S, typename B::Scalar>, Dynamic, Dynamic> operator*(const SparseCompressedBase<S, Flags, StorageIndex>& A, const MatrixBase<B>& x)
 {
+    using RS = internal::prod_t<S, typename B::Scalar>;
     const auto& d = A.raw();
-    Matrix<S, Dynamic, Dynamic> y(d.rows, x.cols());
+    Matrix<RS, Dynamic, Dynamic> y(d.rows, x.cols());
     for (Index c = 0; c < x.cols(); c++)
     {
         if (Flags & RowMajor)
         {
             for (Index i = 0; i < d.rows; i++)
             {
-                S acc(0);
+                RS acc(0);
                 for (Index k = d.outer[i]; k < d.outer[i + 1]; k++)
                     acc += d.values[k] * x.coeff(d.inner[k], c);
                 y(i, c) = acc;
@@ -1779,7 +2118,7 @@ Matrix<S, Dynamic, Dynamic> operator*(const SparseCompressedBase<S, Flags, Stora
         {
             for (Index j = 0; j < d.cols; j++)
             {
-                const S xj = x.coeff(j, c);
+                const auto xj = x.coeff(j, c);
                 for (Index k = d.outer[j]; k < d.outer[j + 1]; k++)
                     y(d.inner[k], c) += d.values[k] * xj;
             }
@@ -1791,18 +2130,19 @@ Matrix<S, Dynamic, Dynamic> operator*(const SparseCompressedBase<S, Flags, Stora
 // y = selfadjointView<Uplo>(A) x (SparseSymMatProd.h:87): only the Uplo triangle of A is read; each
 // stored off-diagonal entry contributes to two rows (Eigen's sparse_selfadjoint_time_dense_product)
 template <typename S, int Flags, typename StorageIndex, int Uplo, typename B>
-Matrix<S, Dynamic, Dynamic> operator*(const SparseSelfAdjointView<S, Flags, StorageIndex, Uplo>& A, const MatrixBase<B>& x)
+Matrix<internal::prod_t<S, typename B::Scalar>, Dynamic, Dynamic> operator*(const SparseSelfAdjointView<S, Flags, StorageIndex, Uplo>& A, const MatrixBase<B>& x)
 {
+    using RS = internal::prod_t<S, typename B::Scalar>;
     const auto& d = A.d;
     const bool row_major = (Flags & RowMajor) != 0;
     const Index nouter = row_major ? d.rows : d.cols;
-    Matrix<S, Dynamic, Dynamic> y(d.rows, x.cols());
+    Matrix<RS, Dynamic, Dynamic> y(d.rows, x.cols());
     for (Index c = 0; c < x.cols(); c++)
     {
         for (Index o = 0; o < nouter; o++)
         {
-            const S xo = x.coeff(o, c);
-            S acc(0);
+            const auto xo = x.coeff(o, c);
+            RS acc(0);
             for (Index k = d.outer[o]; k < d.outer[o + 1]; k++)
             {
                 const Index in = d.inner[k];
@@ -1935,6 +2275,130 @@ public:
         }
         return x;
     }
+};
+
+// Eigen::SelfAdjointEigenSolver as the reference's tests use it for "true" eigenvalues (test/Example1.cpp:40-41 ...): cyclic Jacobi on the
+// lower triangle, eigenvalues ascending with matching eigenvector columns.  Real symmetric matrices only.
+template <typename MatrixType>
+class SelfAdjointEigenSolver
+{
+    using S = typename MatrixType::Scalar;
+    Matrix<S, Dynamic, 1> m_vals;
+    Matrix<S, Dynamic, Dynamic> m_vecs;
+
+public:
+    SelfAdjointEigenSolver() {}
+    template <typename Derived>
+    explicit SelfAdjointEigenSolver(const MatrixBase<Derived>& A) { compute(A); }
+    template <typename Derived>
+    SelfAdjointEigenSolver& compute(const MatrixBase<Derived>& A)
+    {
+        const Index n = A.rows();
+        Matrix<S, Dynamic, Dynamic> a(n, n), v = Matrix<S, Dynamic, Dynamic>::Identity(n, n);
+        for (Index j = 0; j < n; j++)
+            for (Index i = 0; i < n; i++)
+                a(i, j) = i >= j ? A.coeff(i, j) : A.coeff(j, i);
+        for (int sweep = 0; sweep < 100; sweep++)
+        {
+            S off(0);
+            for (Index q = 1; q < n; q++)
+                for (Index p = 0; p < q; p++)
+                    off += a(p, q) * a(p, q);
+            if (off <= S(1e-32) * a.squaredNorm() || off == S(0))
+                break;
+            for (Index p = 0; p < n - 1; p++)
+                for (Index q = p + 1; q < n; q++)
+                {
+                    if (a(p, q) == S(0))
+                        continue;
+                    const S theta = (a(q, q) - a(p, p)) / (S(2) * a(p, q));
+                    const S t = (theta >= S(0) ? S(1) : S(-1)) / (std::abs(theta) + std::sqrt(theta * theta + S(1)));
+                    const S c = S(1) / std::sqrt(t * t + S(1)), sn = t * c;
+                    for (Index k = 0; k < n; k++)
+                    {
+                        const S akp = a(k, p), akq = a(k, q);
+                        a(k, p) = c * akp - sn * akq;
+                        a(k, q) = sn * akp + c * akq;
+                    }
+                    for (Index k = 0; k < n; k++)
+                    {
+                        const S apk = a(p, k), aqk = a(q, k);
+                        a(p, k) = c * apk - sn * aqk;
+                        a(q, k) = sn * apk + c * aqk;
+                    }
+                    for (Index k = 0; k < n; k++)
+                    {
+                        const S vkp = v(k, p), vkq = v(k, q);
+                        v(k, p) = c * vkp - sn * vkq;
+                        v(k, q) = sn * vkp + c * vkq;
+                    }
+                }
+        }
+        std::vector<Index> order(static_cast<size_t>(n));
+        for (Index i = 0; i < n; i++)
+            order[size_t(i)] = i;
+        std::stable_sort(order.begin(), order.end(), [&](Index x, Index y) { return a(x, x) < a(y, y); });
+        m_vals.resize(n);
+        m_vecs.resize(n, n);
+        for (Index j = 0; j < n; j++)
+        {
+            m_vals[j] = a(order[size_t(j)], order[size_t(j)]);
+            for (Index i = 0; i < n; i++)
+                m_vecs(i, j) = v(i, order[size_t(j)]);
+        }
+        return *this;
+    }
+    const Matrix<S, Dynamic, 1>& eigenvalues() const { return m_vals; }
+    const Matrix<S, Dynamic, Dynamic>& eigenvectors() const { return m_vecs; }
+    ComputationInfo info() const { return Success; }
+};
+
+// Eigen::HouseholderQR (test/QR.cpp:145-146 takes householderQ() as the reference Q): Householder reflections, Q accumulated explicitly
+template <typename MatrixType>
+class HouseholderQR
+{
+    using S = typename MatrixType::Scalar;
+    Matrix<S, Dynamic, Dynamic> m_q, m_r;
+
+public:
+    template <typename Derived>
+    explicit HouseholderQR(const MatrixBase<Derived>& A)
+    {
+        const Index m = A.rows(), n = A.cols();
+        m_r = A;
+        m_q = Matrix<S, Dynamic, Dynamic>::Identity(m, m);
+        for (Index k = 0; k < (std::min)(m - 1, n); k++)
+        {
+            Matrix<S, Dynamic, 1> x(m - k), ess(m - k - 1);
+            for (Index i = k; i < m; i++)
+                x[i - k] = m_r(i, k);
+            S tau;
+            typename NumTraits<S>::Real beta;
+            x.makeHouseholder(ess, tau, beta);
+            if (tau == S(0))
+                continue;
+            // H = I - tau v v^H with v = (1, ess); R <- H R, Q <- Q H
+            auto vi = [&](Index i) { return i == 0 ? S(1) : ess[i - 1]; };
+            for (Index j = 0; j < n; j++)
+            {
+                S dot(0);
+                for (Index i = 0; i < m - k; i++)
+                    dot += numext::conj(vi(i)) * m_r(k + i, j);
+                for (Index i = 0; i < m - k; i++)
+                    m_r(k + i, j) -= tau * vi(i) * dot;
+            }
+            for (Index i = 0; i < m; i++)
+            {
+                S dot(0);
+                for (Index j = 0; j < m - k; j++)
+                    dot += m_q(i, k + j) * vi(j);
+                for (Index j = 0; j < m - k; j++)
+                    m_q(i, k + j) -= numext::conj(tau) * dot * numext::conj(vi(j));
+            }
+        }
+    }
+    const Matrix<S, Dynamic, Dynamic>& householderQ() const { return m_q; }
+    Matrix<S, Dynamic, Dynamic> matrixQR() const { return m_r; }
 };
 
 using MatrixXd = Matrix<double, Dynamic, Dynamic>;
