@@ -90,4 +90,31 @@ public:
 };
 
 }  // namespace Spectra
+
+// Scalar = std::complex<double> (test/ComplexEigs.cpp:74-76 uses DenseGenMatProd<std::complex<double>>): a dense general complex matrix
+// behind the complex CSR SpMV kernel of SparseGenMatProd<std::complex<double>>
+#include "DenseHermMatProd.h"
+#include "SparseGenMatProd.h"
+
+namespace Spectra {
+
+template <int Flags>
+class DenseGenMatProd<std::complex<double>, Flags> : private b200::DenseAsCompressed32<std::complex<double>>, public SparseGenMatProd<std::complex<double>, Flags, int>
+{
+    using Pattern = b200::DenseAsCompressed32<std::complex<double>>;
+    using Base = SparseGenMatProd<std::complex<double>, Flags, int>;
+
+public:
+    using Scalar = std::complex<double>;
+
+    DenseGenMatProd(Index n, const Scalar* data) : Pattern(Pattern::checked(n, n, "")), Base(n, Pattern::outer.data(), Pattern::inner.data(), data) {}
+#ifdef SPECTRA_B200_HAS_EIGEN
+    explicit DenseGenMatProd(const Eigen::Matrix<Scalar, Eigen::Dynamic, Eigen::Dynamic, Flags>& mat) :
+        Pattern(Pattern::checked(mat.rows(), mat.cols(), "DenseGenMatProd: matrix must be square")), Base(mat.rows(), Pattern::outer.data(), Pattern::inner.data(), mat.data())
+    {
+    }
+#endif
+};
+
+}  // namespace Spectra
 #endif

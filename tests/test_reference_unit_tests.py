@@ -3,9 +3,10 @@
   (A) against the reference's headers over the Eigen stand-in (oracle/eigen_standin): Givens, QR, Schur, Arnoldi, SymEigs, GenEigs,
       SparseSymMatProd, SparseGenMatProd, SymEigsShift, HermEigs, ComplexEigs, Example1, Example2, Example4 all pass -- i.e. the stand-in is a
       sufficient Eigen for this path, which is what the pinning of the restatement on oracle/_ref rests on;
-  (B) against THIS REPOSITORY'S include/ (the drop-in shim) linked with the kernel-logic emulator build of the library: the solver-level
-      files the shim's surface covers -- SymEigs, GenEigs, SparseSymMatProd (float and double), SparseGenMatProd, Example2, Example4 -- pass
-      as they stand.  (The rest instantiate classes the shim does not replace: Dense*ShiftSolve, DenseHermMatProd, internal LinAlg types.)
+  (B) against THIS REPOSITORY'S include/ (the drop-in shim) linked with the kernel-logic emulator build of the library: every solver-level
+      file -- SymEigs, GenEigs, SymEigsShift, HermEigs, ComplexEigs, SparseSymMatProd (float and double), SparseGenMatProd, Example1, Example2,
+      Example4 -- passes as it stands.  (Givens, QR, Schur and Arnoldi instantiate the reference's internal LinAlg classes, which the shim
+      replaces by device kernels behind the solver facades; their parity is the job of the dense-kernel and factorisation tiers.)
 
 The CPU suite runs every file of (A) and (B), the slow ones restricted to their small cases through Catch's test-name filter;
 tools/run_reference_unit_tests.sh runs everything in full (profiles/r2_reference_unit_tests.log: (B) SymEigs 60 assertions in 792 s and
@@ -27,7 +28,8 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(REF_TEST), reason="/root/refer
 REFERENCE_SIDE = {"Givens": None, "QR": None, "Schur": None, "Arnoldi": None, "SparseSymMatProd": None, "SparseGenMatProd": None, "Example1": None, "Example2": None,
                   "Example4": None, "SymEigsShift": "*10x10*,*100x100*", "SymEigs": "*10x10*,*100x100*", "GenEigs": "*10x10*,*100x100*",
                   "HermEigs": "*10x10*,*100x100*", "ComplexEigs": "*10x10*,*100x100*"}
-SHIM_SIDE = {"SparseSymMatProd": None, "SparseGenMatProd": None, "Example2": None, "Example4": None, "SymEigs": "*10x10*", "GenEigs": "*10x10*"}
+SHIM_SIDE = {"SparseSymMatProd": None, "SparseGenMatProd": None, "Example1": None, "Example2": None, "Example4": None, "SymEigs": "*10x10*", "GenEigs": "*general*10x10*",
+             "SymEigsShift": "*sparse*10x10*", "HermEigs": "*10x10*", "ComplexEigs": "*general*10x10*"}  # the emulator is slow: one small case each
 
 
 def _run(cmd, **kw):
