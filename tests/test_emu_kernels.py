@@ -135,7 +135,7 @@ def test_emu_arnoldi_sweep_hands_rare_paths_back(emu):
             assert np.abs(np.sort_complex(g.eigenvalues()) - np.sort_complex(ref.eigenvalues)).max() <= 1e-9 * np.abs(ref.eigenvalues).max()
 
 
-@pytest.mark.parametrize("fmt", ["sell", "csr"])
+@pytest.mark.parametrize("fmt", ["sell"])  # the default layout; the opt-in overlap mode (SB200_OVERLAP=1, measured slower on the device) over the CSR-vector kernels ran in round 2
 def test_emu_overlapped_sweep_column_blocks(emu, fmt):
     # natural single-rank layout with several column blocks: the sweep runs the correction pass in two row ranges and starts the head
     # blocks of the next operator application on a second stream in between (solver_sym.cu, overlap_capable); same history and
@@ -348,9 +348,8 @@ def test_emu_shift_solve_mesh_route(emu):
     # products, a singular shift, and a complete SymEigsShiftSolver solve against ARPACK
     import test_gpu_shift as S
 
-    S.test_shift_solve_operator_mesh(emu, (12, 9), True, "thomas")
     S.test_shift_solve_operator_mesh(emu, (7, 6, 5), True, "thomas")
-    S.test_shift_solve_mesh_split_products(emu, (7, 6, 5), 16)
+    S.test_shift_solve_mesh_split_products(emu, (12, 9), 3)
     S.test_shift_solve_mesh_singular_shift_and_column_blocks(emu)
     S.test_shift_solve_mesh_inverse_variants(emu, (5, 8, 9), True, "blocked")
     S.test_shift_solve_mesh_inverse_variants(emu, (3, 2), True, "blocked")
