@@ -36,7 +36,7 @@ struct GenBinding<OpType, true> : OpBindingZ<OpType>
 }  // namespace b200
 
 // Scalar = double / float: real nonsymmetric problems (complex Ritz pairs).  Scalar = std::complex<double>: GenEigsBase with a complex
-// Scalar (GenEigsBase.h:111-140, test/ComplexEigs.cpp); experimental in round 1, see DESIGN.md.
+// Scalar (GenEigsBase.h:111-140, test/ComplexEigs.cpp); device-verified in round 2, see DESIGN.md §4b.
 template <typename OpType = DenseGenMatProd<double>>  // the reference's default (GenEigsSolver.h:157)
 class GenEigsSolver
 {

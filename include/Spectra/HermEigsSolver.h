@@ -1,6 +1,6 @@
 // B200 shim of Spectra/HermEigsSolver.h:121-122 (+ the public surface of HermEigsBase.h:257-478 with a complex Scalar):
 // implicitly restarted Lanczos for complex Hermitian operators on the GPU.  Eigenvalues are real, eigenvectors complex.
-// (experimental in round 1.)
+// (device-verified in round 2.)
 #ifndef SPECTRA_B200_HERM_EIGS_SOLVER_H
 #define SPECTRA_B200_HERM_EIGS_SOLVER_H
 

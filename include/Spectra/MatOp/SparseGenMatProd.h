@@ -42,7 +42,7 @@ private:
 };
 
 // Scalar = std::complex<double> (the reference's wrapper is templated on Scalar; test/ComplexEigs.cpp:77-79 uses this instantiation):
-// a general complex sparse matrix behind the complex CSR SpMV kernel, for GenEigsSolver.  (experimental in round 1.)
+// a general complex sparse matrix behind the complex CSR SpMV kernel, for GenEigsSolver.  (device-verified in round 2.)
 template <int Flags, typename StorageIndex>
 class SparseGenMatProd<std::complex<double>, Flags, StorageIndex> : public b200::DeviceOpTag
 {

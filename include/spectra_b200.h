@@ -124,15 +124,15 @@ int sb200_op_create_callback_z(int64_t n, sb200_matvec_fn fn, void* user, sb200_
  * nnz complex values interleaved (re, im) -- the memory layout of std::complex<double> --, matrix_mode is SB200_HERM_LOWER /
  * SB200_HERM_UPPER (the Uplo template argument: only that triangle is read, mirrored conjugated, the diagonal taken as real) or
  * SB200_GENERAL.  Every vector the operator or its solver exchanges is interleaved complex too: perform_op / apply_matrix take
- * and return 2 n doubles per column.  Single GPU.  (experimental in round 1: verified on the kernel-logic
- * emulator, not yet on a device.) */
+ * and return 2 n doubles per column.  Single GPU.  (device-verified in round 2: tests/test_gpu_layouts_complex.py.) */
 int sb200_op_create_sparse_herm(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values_ri, int storage_order, int matrix_mode,
                                 sb200_op** out);
 /* Shift-solve operator: replaces MatOp/SparseSymShiftSolve.h:30-110.  Same matrix arguments as sb200_op_create_sparse
  * (matrix_mode SB200_SYM_LOWER / SB200_SYM_UPPER = the Uplo template argument).  perform_op then computes
- * y = (A - sigma I)^{-1} x.  Device implementation: block cyclic reduction on the block-tridiagonal form, which needs a
- * banded matrix (half-bandwidth <= 32, BASELINE config 5's class); wider patterns return SB200_INVALID_ARGUMENT.
- * Single-GPU. */
+ * y = (A - sigma I)^{-1} x.  Device implementation, chosen from the half-bandwidth b of the pattern: block cyclic reduction on the
+ * block-tridiagonal form for b <= 32 (BASELINE config 5's class); sequential block elimination with grid-wide block kernels for wider
+ * bands and mesh-like patterns (2-D / 3-D stencils in natural ordering), as long as the 3 n B doubles of block factors fit in device
+ * memory; an explicit inverse for n <= 2048.  A large pattern without band structure returns SB200_INVALID_ARGUMENT.  Single-GPU. */
 int sb200_op_create_shift_solve(int64_t n, const void* outer, int outer_is_64, const int32_t* inner, const double* values, int storage_order, int matrix_mode,
                                 sb200_op** out);
 /* set_shift(sigma) (SparseSymShiftSolve.h:85-95): factorises A - sigma I on the device.  SB200_INVALID_ARGUMENT
