@@ -190,6 +190,7 @@ def coeff(A: Compressed, i, j, sym=False):
 def factorize(A: Compressed, m: int, v0=None, mid=None, kind="lanczos"):
     """Lanczos (SparseSymMatProd<Lower, ColMajor>: A must be 'col' ordered) or Arnoldi factorisation."""
     n = A.n
+    assert kind != "lanczos" or A.order == 0, "the Lanczos hook binds SparseSymMatProd<double, Lower, ColMajor>"
     mid = m if mid is None else mid
     V = np.empty((n, m), order="F")
     H = np.empty((m, m), order="F")

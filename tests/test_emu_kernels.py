@@ -350,7 +350,10 @@ def test_emu_shift_solve_mesh_route(emu):
 
     S.test_shift_solve_operator_mesh(emu, (7, 6, 5), True, "thomas")
     S.test_shift_solve_mesh_split_products(emu, (12, 9), 3)
-    S.test_shift_solve_mesh_singular_shift_and_column_blocks(emu)
+    S.test_shift_solve_mesh_singular_shift(emu)
+    # an operator stored in several column blocks (large n on a device; forced here): every CSR kernel of the route runs once per block
+    with X.env(SB200_XSLICE_MB="0.002"):
+        S.test_shift_solve_operator_mesh(emu, (40, 35), False, "thomas")
     S.test_shift_solve_mesh_inverse_variants(emu, (5, 8, 9), True, "blocked")
     S.test_shift_solve_mesh_inverse_variants(emu, (3, 2), True, "blocked")
     S.test_shift_solve_mesh_merged_blocks(emu, (40, 9), True, 30)

@@ -219,13 +219,9 @@ def test_shift_solve_mesh_inverse_variants(gpu, dims, full, variant):
     assert np.linalg.norm(M @ y - x) <= 1e-12 * np.linalg.norm(x) * max(1.0, np.abs(y).max())
 
 
-def test_shift_solve_mesh_singular_shift_and_column_blocks(gpu):
+def test_shift_solve_mesh_singular_shift(gpu):
     # a singular shift is reported like the reference's "factorization failed with the given shift" (SparseSymShiftSolve.h:93-94)
     n = 40 * 36
-    D = sp.diags(np.arange(1.0, n + 1)).tocsc() + stencil_matrix((40, 36), False, seed=3) * 0.0
-    with _route("thomas"):
-        opd = gpu.SparseSymShiftSolve(stencil_matrix((40, 36), False, seed=3))
-        opd.set_shift(0.25)
     A = stencil_matrix((40, 36), False, seed=3).tolil()
     A[5, :] = 0.0
     A[:, 5] = 0.0
@@ -240,7 +236,6 @@ def test_shift_solve_mesh_singular_shift_and_column_blocks(gpu):
     y = ops.perform_op(x)
     M = (A - 2.5 * sp.identity(n)).tocsc()
     assert np.linalg.norm(M @ y - x) <= 1e-12 * np.linalg.norm(x) * max(1.0, np.abs(y).max())
-    del D
 
 
 @pytest.mark.parametrize("dims,full,route,k,m", [((9, 8, 7), True, "thomas", 4, 14), ((20, 20, 20), True, None, 6, 20)])
