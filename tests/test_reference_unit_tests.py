@@ -40,8 +40,22 @@ def _run(cmd, **kw):
     return r
 
 
+def _newest(paths):
+    t = 0.0
+    for p in paths:
+        if os.path.isdir(p):
+            for d, _, files in os.walk(p):
+                for f in files:
+                    t = max(t, os.path.getmtime(os.path.join(d, f)))
+        elif os.path.exists(p):
+            t = max(t, os.path.getmtime(p))
+    return t
+
+
 def _compile(job):
-    exe, cmd = job
+    exe, cmd, deps = job
+    if os.path.exists(exe) and os.path.getmtime(exe) >= _newest(deps):
+        return exe, 0, ""  # built by an earlier run from the same sources
     r = subprocess.run(cmd, capture_output=True, text=True)
     return exe, r.returncode, r.stderr[-3000:]
 
@@ -67,12 +81,13 @@ def built():
     for name in REFERENCE_SIDE:
         exe = os.path.join(BUILD, f"ref_{name}")
         jobs.append((exe, ["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", STANDIN, "-I", REF_INC, "-I", REF_TEST, os.path.join(REF_TEST, name + ".cpp"),
-                           main_obj, "-o", exe]))
+                           main_obj, "-o", exe], [STANDIN, os.path.join(REF_TEST, name + ".cpp"), main_obj, __file__]))
     if have_emu:
         for name in SHIM_SIDE:
             exe = os.path.join(BUILD, f"shim_{name}")
             jobs.append((exe, ["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", STANDIN, "-I", os.path.join(ROOT, "include"), "-I", REF_TEST,
-                               os.path.join(REF_TEST, name + ".cpp"), main_obj, "-L", libdir, "-lspectra_b200_emu", f"-Wl,-rpath,{libdir}", "-o", exe]))
+                               os.path.join(REF_TEST, name + ".cpp"), main_obj, "-L", libdir, "-lspectra_b200_emu", f"-Wl,-rpath,{libdir}", "-o", exe],
+                         [STANDIN, os.path.join(ROOT, "include"), os.path.join(REF_TEST, name + ".cpp"), main_obj, __file__]))
     with ThreadPoolExecutor(max_workers=max(1, os.cpu_count() or 1)) as pool:
         results = {exe: (rc, err) for exe, rc, err in pool.map(_compile, jobs)}
     return results
