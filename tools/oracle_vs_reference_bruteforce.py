@@ -1,6 +1,6 @@
 """Brute-force twin of tests/test_oracle_vs_reference_fuzz.py: random dense kernels and complete solves through the reference's own code (oracle/_ref) and the
 restatement (strict build) for a given number of seconds; every result is compared with np.array_equal.  Development container only.
-usage: python tools/oracle_vs_reference_bruteforce.py [seconds]   (round 2: 240 s -> 27 378 cases, 0 mismatches)"""
+usage: python tools/oracle_vs_reference_bruteforce.py [seconds]   (round 2: 240 s -> 27 378 cases, 1200 s -> 122 420 cases, 0 mismatches)"""
 import sys, time
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, scipy.sparse as sp
